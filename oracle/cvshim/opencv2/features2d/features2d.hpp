@@ -1,0 +1,3 @@
+// ORACLE shim forwarding header (test infrastructure only) — see cvshim.hpp
+#pragma once
+#include "../../cvshim.hpp"
