@@ -168,3 +168,30 @@ def port_distribute(xys: np.ndarray, width: int, height: int, N: int) -> np.ndar
     out = np.zeros((len(xys) + 8, 3), np.int32)
     n = lib.orbport_distribute(_p(xys, _i32p), len(xys), width, height, N, _p(out, _i32p), len(out))
     return out[:n]
+
+
+def port_stereo(kL, dL, kR, dR, pyrL, pyrR, scale, inv_scale, bf, fx):
+    """Frame::ComputeStereoMatches restatement. pyrL/pyrR: lists of tight uint8 level images.
+    Returns (uRight, depth, sad) with -1 for 'no match'."""
+    lib = C.CDLL(PORT_SO)
+    nlev = len(pyrL)
+    pyrL = [np.ascontiguousarray(p, np.uint8) for p in pyrL]
+    pyrR = [np.ascontiguousarray(p, np.uint8) for p in pyrR]
+    lw = np.array([p.shape[1] for p in pyrL], np.int32)
+    lh = np.array([p.shape[0] for p in pyrL], np.int32)
+    PL = (C.c_void_p * nlev)(*[p.ctypes.data for p in pyrL])
+    PR = (C.c_void_p * nlev)(*[p.ctypes.data for p in pyrR])
+    kL = np.ascontiguousarray(kL); kR = np.ascontiguousarray(kR)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    n = len(kL)
+    ur = np.zeros(max(n, 1), np.float32); dp = np.zeros(max(n, 1), np.float32); sad = np.zeros(max(n, 1), np.int32)
+    scale = np.ascontiguousarray(scale, np.float32); inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+    b = np.float32(bf) / np.float32(fx)
+    lib.orbport_stereo.restype = C.c_int
+    lib.orbport_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.orbport_stereo(kL.ctypes.data, dL.ctypes.data, n, kR.ctypes.data, dR.ctypes.data, len(kR), PL, PR,
+                       lw.ctypes.data, lh.ctypes.data, nlev, scale.ctypes.data, inv_scale.ctypes.data,
+                       float(bf), float(b), ur.ctypes.data, dp.ctypes.data, sad.ctypes.data)
+    return ur[:n], dp[:n], sad[:n]

@@ -1,0 +1,650 @@
+// Host side of libborb: C ABI (include/borb.h), geometry/tables, workspace, launch orchestration.
+// No CPU compute path exists here: every entry point that produces results launches CUDA kernels.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "borb_internal.h"
+
+namespace borb {
+
+static thread_local std::string tl_error;
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    tl_error = buf;
+}
+
+namespace {
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }     // cvRound: round-half-even
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// Scale tables and per-level quotas exactly as the reference constructor derives them
+// (src/ORBextractor.cc:410-470): float chain with a double scaleFactor member, cvRound quotas, umax.
+void init_tables(borb_extractor* e) {
+    const int L = e->cfg.n_levels;
+    const double sf = (double)e->cfg.scale_factor;
+    e->scale.assign(L, 1.f); e->sigma2.assign(L, 1.f); e->inv_scale.assign(L, 1.f); e->inv_sigma2.assign(L, 1.f);
+    for (int i = 1; i < L; i++) {
+        e->scale[i] = (float)((double)e->scale[i - 1] * sf);
+        e->sigma2[i] = e->scale[i] * e->scale[i];
+    }
+    for (int i = 0; i < L; i++) { e->inv_scale[i] = 1.0f / e->scale[i]; e->inv_sigma2[i] = 1.0f / e->sigma2[i]; }
+    e->per_level.assign(L, 0);
+    const float factor = (float)(1.0 / sf);
+    float want = (float)e->cfg.n_features * (1.f - factor) / (1.f - (float)std::pow((double)factor, (double)L));
+    int sum = 0;
+    for (int l = 0; l < L - 1; l++) {
+        e->per_level[l] = cv_round_f(want);
+        sum += e->per_level[l];
+        want *= factor;
+    }
+    e->per_level[L - 1] = e->cfg.n_features - sum > 0 ? e->cfg.n_features - sum : 0;
+    // circular patch row extents
+    const int vmax = (int)std::floor(HALF_PATCH * std::sqrt(2.f) / 2 + 1);
+    const int vmin = (int)std::ceil(HALF_PATCH * std::sqrt(2.f) / 2);
+    for (int v = 0; v < 16; v++) e->umax[v] = 0;
+    for (int v = 0; v <= vmax; ++v) e->umax[v] = (int)lrint(std::sqrt((double)HALF_PATCH * HALF_PATCH - (double)v * v));
+    for (int v = HALF_PATCH, v0 = 0; v >= vmin; --v) {
+        while (e->umax[v0] == e->umax[v0 + 1]) ++v0;
+        e->umax[v] = v0;
+        ++v0;
+    }
+}
+
+// cv::resize INTER_LINEAR 8U coefficient tables (OpenCV imgproc/resize.cpp): (offset, c0, c1) int16 triplets
+void resize_table(int src, int dst, bool clamp_edges, std::vector<int16_t>& out) {
+    const double inv = (double)dst / src, scale = 1. / inv;
+    for (int d = 0; d < dst; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)std::floor(f);
+        f -= s;
+        if (clamp_edges) {
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= src - 1) { f = 0; s = src - 1; }
+        }
+        out.push_back((int16_t)s);
+        out.push_back((int16_t)cv_round_f((1.f - f) * 2048.f));
+        out.push_back((int16_t)cv_round_f(f * 2048.f));
+    }
+}
+
+borb_status build_geometry(borb_extractor* e, int w, int h, std::vector<int16_t>& tabs) {
+    Geometry& g = e->geom;
+    std::memset(&g, 0, sizeof(g));
+    const int L = e->cfg.n_levels;
+    g.nlevels = L; g.w = w; g.h = h;
+    g.ini_th = e->cfg.ini_th_fast < 0 ? 0 : (e->cfg.ini_th_fast > 255 ? 255 : e->cfg.ini_th_fast);
+    g.min_th = e->cfg.min_th_fast < 0 ? 0 : (e->cfg.min_th_fast > 255 ? 255 : e->cfg.min_th_fast);
+    for (int i = 0; i < 16; i++) g.umax[i] = e->umax[i];
+    unsigned pyr_off = 0, cand_off = 0;
+    int blk = 0, sel_off = 0, btile = 0;
+    tabs.clear();
+    for (int l = 0; l < L; l++) {
+        LevelGeom& v = g.lv[l];
+        v.w = cv_round_f((float)w * e->inv_scale[l]);
+        v.h = cv_round_f((float)h * e->inv_scale[l]);
+        const float width = (float)(v.w - 2 * MIN_BORDER), height = (float)(v.h - 2 * MIN_BORDER);
+        v.nCols = (int)(width / 30.f);
+        v.nRows = (int)(height / 30.f);
+        if (v.nCols < 1 || v.nRows < 1) {
+            set_error("level %d is %dx%d: too small for the 30-px FAST cell grid (reference divides by zero)", l, v.w, v.h);
+            return BORB_ERR_UNSUPPORTED;
+        }
+        v.wCell = (int)std::ceil(width / v.nCols);
+        v.hCell = (int)std::ceil(height / v.nRows);
+        v.pitch = align_up(v.w, 128);
+        v.pyr_off = pyr_off;
+        pyr_off += (unsigned)v.pitch * v.h;
+        v.cellsPerBlk = FAST_TILE_W / v.wCell > 0 ? FAST_TILE_W / v.wCell : 1;
+        v.blkCols = (v.nCols + v.cellsPerBlk - 1) / v.cellsPerBlk;
+        v.blkBase = blk;
+        blk += v.blkCols * v.nRows;
+        v.cand_off = cand_off;
+        v.cand_cap = v.nCols * v.nRows * ((v.wCell + 1) / 2) * ((v.hCell + 1) / 2);   // strict 3x3 NMS: <=1 per 2x2
+        cand_off += (unsigned)align_up(v.cand_cap, 32);
+        v.quota = e->per_level[l];
+        v.nIni = (int)std::round(width / height);
+        if (v.nIni < 1) { set_error("level %d aspect ratio gives zero quadtree roots (reference divides by zero)", l); return BORB_ERR_UNSUPPORTED; }
+        v.hX = width / v.nIni;
+        v.node_cap = (v.quota > 4 * v.nIni ? v.quota : 4 * v.nIni) + 3;
+        v.node_cap = align_up(v.node_cap + 1, 4);
+        v.sel_off = sel_off;
+        sel_off += v.node_cap;
+        v.scale = e->scale[l];
+        v.inv_scale = e->inv_scale[l];
+        v.patch_size = (float)(int)(PATCH * e->scale[l]);
+        g.blur_base[l] = btile;
+        btile += ((v.w + 63) / 64) * ((v.h + 31) / 32);
+        if (l > 0) {
+            v.xtab_off = (unsigned)(tabs.size() / 3);
+            resize_table(g.lv[l - 1].w, v.w, true, tabs);
+            v.ytab_off = (unsigned)(tabs.size() / 3);
+            resize_table(g.lv[l - 1].h, v.h, false, tabs);
+        }
+        if (quadtree_smem_bytes(v.node_cap) > 200 * 1024) {
+            set_error("per-level quota %d exceeds the quadtree kernel's shared-memory envelope", v.quota);
+            return BORB_ERR_UNSUPPORTED;
+        }
+    }
+    g.blur_base[L] = btile;
+    g.blur_tiles = btile;
+    g.fast_blocks = blk;
+    g.pyr_image_stride = (unsigned)align_up((int)pyr_off, g.lv[0].pitch);   // whole level-0 rows: lets batches move as one 3-D copy
+    g.cand_image_stride = cand_off;
+    g.sel_image_stride = sel_off;
+    if (sel_off >= 65536) { set_error("keypoint capacity %d exceeds 65535", sel_off); return BORB_ERR_UNSUPPORTED; }
+    return BORB_OK;
+}
+
+void free_workspace(Workspace& ws) {
+    cudaFree(ws.pyr); cudaFree(ws.blur); cudaFree(ws.cand); cudaFree(ws.cand_cnt); cudaFree(ws.pnode); cudaFree(ws.sel);
+    cudaFree(ws.sel_cnt); cudaFree(ws.kps); cudaFree(ws.desc); cudaFree(ws.nkp); cudaFree(ws.u_right); cudaFree(ws.depth);
+    cudaFree(ws.sad); cudaFree(ws.tabs); cudaFree(ws.pair_idx);
+    ws = Workspace();
+}
+
+borb_status ensure(borb_extractor* e, int w, int h, int n_images) {
+    if (w < 1 || h < 1 || w > BORB_MAX_DIM || h > BORB_MAX_DIM) { set_error("image size %dx%d outside [1,%d]", w, h, BORB_MAX_DIM); return BORB_ERR_UNSUPPORTED; }
+    BORB_CUDA(cudaSetDevice(e->device));
+    const bool same_shape = e->have_geom && e->geom.w == w && e->geom.h == h;
+    if (same_shape && e->ws.max_images >= n_images) return BORB_OK;
+    BORB_CUDA(cudaStreamSynchronize(e->stream));
+    std::vector<int16_t> tabs;
+    e->have_geom = false;
+    e->last_n_images = 0;
+    borb_status st = build_geometry(e, w, h, tabs);
+    if (st != BORB_OK) return st;
+    size_t n = (size_t)(n_images > 2 ? n_images : 2);
+    if (same_shape && (size_t)e->ws.max_images > n) n = (size_t)e->ws.max_images;
+    free_workspace(e->ws);
+    if (e->h_counts) { cudaFreeHost(e->h_counts); e->h_counts = nullptr; }
+    e->pair_cache.clear();
+    const Geometry& g = e->geom;
+    Workspace& ws = e->ws;
+    BORB_CUDA(cudaMalloc(&ws.pyr, n * g.pyr_image_stride));
+    BORB_CUDA(cudaMalloc(&ws.blur, n * g.pyr_image_stride));
+    BORB_CUDA(cudaMalloc(&ws.cand, n * g.cand_image_stride * sizeof(uint32_t)));
+    BORB_CUDA(cudaMalloc(&ws.pnode, n * g.cand_image_stride * sizeof(int)));
+    BORB_CUDA(cudaMalloc(&ws.cand_cnt, n * g.nlevels * sizeof(int)));
+    BORB_CUDA(cudaMalloc(&ws.sel, n * g.sel_image_stride * sizeof(uint32_t)));
+    BORB_CUDA(cudaMalloc(&ws.sel_cnt, n * g.nlevels * sizeof(int)));
+    BORB_CUDA(cudaMalloc(&ws.kps, n * g.sel_image_stride * sizeof(borb_keypoint)));
+    BORB_CUDA(cudaMalloc(&ws.desc, n * g.sel_image_stride * 32));
+    BORB_CUDA(cudaMalloc(&ws.nkp, n * sizeof(int)));
+    BORB_CUDA(cudaMalloc(&ws.u_right, n * g.sel_image_stride * sizeof(float)));
+    BORB_CUDA(cudaMalloc(&ws.depth, n * g.sel_image_stride * sizeof(float)));
+    BORB_CUDA(cudaMalloc(&ws.sad, n * g.sel_image_stride * sizeof(int)));
+    BORB_CUDA(cudaMalloc(&ws.pair_idx, n * 2 * sizeof(int)));
+    BORB_CUDA(cudaMalloc(&ws.tabs, (tabs.size() + 4) * sizeof(int16_t)));
+    BORB_CUDA(cudaMemcpy(ws.tabs, tabs.data(), tabs.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    BORB_CUDA(cudaMemset(ws.nkp, 0, n * sizeof(int)));
+    BORB_CUDA(cudaMallocHost(&e->h_counts, n * 2 * sizeof(int)));
+    ws.max_images = (int)n;
+    e->have_geom = true;
+    return BORB_OK;
+}
+
+void mark(borb_extractor* e, int i) { if (e->timing) cudaEventRecord(e->ev[i], e->stream); }
+
+// Queues pyramid .. descriptors for n images whose level 0 is already in ws.pyr.
+borb_status enqueue_extract(borb_extractor* e, int n) {
+    const Geometry& g = e->geom;
+    Workspace& ws = e->ws;
+    cudaStream_t s = e->stream;
+    BORB_CUDA(cudaMemsetAsync(ws.cand_cnt, 0, (size_t)n * g.nlevels * sizeof(int), s));
+    mark(e, 1);
+    e->launches += launch_pyramid(g, ws, n, s);
+    mark(e, 2);
+    e->launches += launch_fast(g, ws, n, s);
+    mark(e, 3);
+    e->launches += launch_quadtree(g, ws, n, s);
+    mark(e, 4);
+    e->launches += launch_blur(g, ws, n, s);
+    mark(e, 5);
+    e->launches += launch_describe(g, ws, n, s);
+    mark(e, 6);
+    BORB_CUDA(cudaGetLastError());
+    e->last_n_images = n;
+    return BORB_OK;
+}
+
+borb_status upload_host(borb_extractor* e, const uint8_t* const* gray, int first, int count, int step, int w, int h, int stride) {
+    const Geometry& g = e->geom;
+    for (int i = 0; i < count; i++) {
+        if (!gray[i]) { set_error("image %d is NULL", i); return BORB_ERR_INVALID_ARG; }
+        uint8_t* dst = e->ws.pyr + (size_t)(first + i * step) * g.pyr_image_stride + g.lv[0].pyr_off;
+        BORB_CUDA(cudaMemcpy2DAsync(dst, g.lv[0].pitch, gray[i], stride, w, h, cudaMemcpyHostToDevice, e->stream));
+    }
+    return BORB_OK;
+}
+
+borb_status upload_device(borb_extractor* e, const uint8_t* d_gray, int n, int w, int h, size_t pitch, size_t image_stride) {
+    const Geometry& g = e->geom;
+    cudaMemcpy3DParms p = {};
+    p.srcPtr = make_cudaPitchedPtr((void*)d_gray, pitch, w, image_stride / pitch);
+    p.dstPtr = make_cudaPitchedPtr(e->ws.pyr + g.lv[0].pyr_off, g.lv[0].pitch, w, g.pyr_image_stride / g.lv[0].pitch);
+    if (image_stride % pitch == 0 && g.pyr_image_stride % g.lv[0].pitch == 0) {
+        p.extent = make_cudaExtent(w, h, n);
+        p.kind = cudaMemcpyDeviceToDevice;
+        BORB_CUDA(cudaMemcpy3DAsync(&p, e->stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            BORB_CUDA(cudaMemcpy2DAsync(e->ws.pyr + (size_t)i * g.pyr_image_stride + g.lv[0].pyr_off, g.lv[0].pitch,
+                                        d_gray + (size_t)i * image_stride, pitch, w, h, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    return BORB_OK;
+}
+
+// Queues the D2H copies of keypoints / descriptors / counts of images [first, first+count) step `step`.
+borb_status download_kps(borb_extractor* e, int first, int count, int step, borb_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+    const Geometry& g = e->geom;
+    const int m = cap < g.sel_image_stride ? cap : g.sel_image_stride;
+    cudaStream_t s = e->stream;
+    if (kps && m > 0)
+        BORB_CUDA(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(borb_keypoint), e->ws.kps + (size_t)first * g.sel_image_stride,
+                                    (size_t)step * g.sel_image_stride * sizeof(borb_keypoint), (size_t)m * sizeof(borb_keypoint),
+                                    count, cudaMemcpyDeviceToHost, s));
+    if (desc && m > 0)
+        BORB_CUDA(cudaMemcpy2DAsync(desc, (size_t)cap * 32, e->ws.desc + (size_t)first * g.sel_image_stride * 32,
+                                    (size_t)step * g.sel_image_stride * 32, (size_t)m * 32, count, cudaMemcpyDeviceToHost, s));
+    if (n_out)
+        BORB_CUDA(cudaMemcpy2DAsync(n_out, sizeof(int), e->ws.nkp + first, (size_t)step * sizeof(int), sizeof(int), count,
+                                    cudaMemcpyDeviceToHost, s));
+    return BORB_OK;
+}
+
+borb_status check_args(borb_extractor* e, int n, int w, int h) {
+    if (!e) { set_error("null handle"); return BORB_ERR_INVALID_ARG; }
+    if (n < 0) { set_error("negative image count"); return BORB_ERR_INVALID_ARG; }
+    (void)w; (void)h;
+    return BORB_OK;
+}
+
+borb_status enqueue_stereo(borb_extractor* eL, borb_extractor* eR, int n_pairs, const int* left_idx, const int* right_idx,
+                           float bf, float b) {
+    borb_extractor* e = eL;
+    const Geometry& g = e->geom;
+    std::vector<int> idx(2 * (size_t)n_pairs);
+    for (int p = 0; p < n_pairs; p++) {
+        idx[2 * p] = left_idx ? left_idx[p] : (eL == eR ? 2 * p : 0);
+        idx[2 * p + 1] = right_idx ? right_idx[p] : (eL == eR ? 2 * p + 1 : 0);
+        if (idx[2 * p] < 0 || idx[2 * p] >= eL->last_n_images || idx[2 * p + 1] < 0 || idx[2 * p + 1] >= eR->last_n_images) {
+            set_error("stereo pair %d refers to an image outside the last batch", p);
+            return BORB_ERR_STATE;
+        }
+    }
+    if (n_pairs > e->ws.max_images) { set_error("too many pairs"); return BORB_ERR_INVALID_ARG; }
+    if (idx != e->pair_cache) {
+        // the (rarely changing) pair table rides through a pinned staging buffer; wait for earlier work so
+        // the staging buffer is not overwritten under a pending copy
+        BORB_CUDA(cudaStreamSynchronize(e->stream));
+        std::memcpy(e->h_counts, idx.data(), idx.size() * sizeof(int));
+        BORB_CUDA(cudaMemcpyAsync(e->ws.pair_idx, e->h_counts, idx.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        e->pair_cache = idx;
+    }
+    StereoView L{eL->ws.pyr, eL->ws.kps, eL->ws.desc, eL->ws.nkp, eL->geom.pyr_image_stride, eL->geom.sel_image_stride};
+    StereoView R{eR->ws.pyr, eR->ws.kps, eR->ws.desc, eR->ws.nkp, eR->geom.pyr_image_stride, eR->geom.sel_image_stride};
+    mark(e, 6);
+    e->launches += launch_stereo(g, L, R, e->ws.pair_idx, n_pairs, bf, b, e->ws.u_right, e->ws.depth, e->ws.sad, g.sel_image_stride, e->stream);
+    mark(e, 7);
+    BORB_CUDA(cudaGetLastError());
+    return BORB_OK;
+}
+
+borb_status download_stereo(borb_extractor* e, int n_pairs, float* u_right, float* depth, int cap) {
+    const Geometry& g = e->geom;
+    const int m = cap < g.sel_image_stride ? cap : g.sel_image_stride;
+    if (u_right && m > 0)
+        BORB_CUDA(cudaMemcpy2DAsync(u_right, (size_t)cap * 4, e->ws.u_right, (size_t)g.sel_image_stride * 4, (size_t)m * 4, n_pairs, cudaMemcpyDeviceToHost, e->stream));
+    if (depth && m > 0)
+        BORB_CUDA(cudaMemcpy2DAsync(depth, (size_t)cap * 4, e->ws.depth, (size_t)g.sel_image_stride * 4, (size_t)m * 4, n_pairs, cudaMemcpyDeviceToHost, e->stream));
+    return BORB_OK;
+}
+
+borb_status finish_timing(borb_extractor* e) {
+    if (!e->timing) return BORB_OK;
+    for (int i = 0; i < 8; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
+        e->stage_ms[i] = ms;
+    }
+    return BORB_OK;
+}
+
+}  // namespace
+}  // namespace borb
+
+using namespace borb;
+
+extern "C" {
+
+const char* borb_last_error(void) { return tl_error.c_str(); }
+const char* borb_status_str(borb_status s) {
+    switch (s) {
+        case BORB_OK: return "ok";
+        case BORB_ERR_INVALID_ARG: return "invalid argument";
+        case BORB_ERR_NO_DEVICE: return "no CUDA device (libborb has no CPU path)";
+        case BORB_ERR_CUDA: return "CUDA error";
+        case BORB_ERR_UNSUPPORTED: return "unsupported shape or quota";
+        case BORB_ERR_CAPACITY: return "output capacity too small";
+        case BORB_ERR_STATE: return "invalid call order";
+    }
+    return "unknown";
+}
+int borb_version(void) { return BORB_VERSION; }
+
+borb_status borb_device_count(int* n) {
+    if (!n) return BORB_ERR_INVALID_ARG;
+    *n = 0;
+    cudaError_t err = cudaGetDeviceCount(n);
+    if (err != cudaSuccess) { *n = 0; cudaGetLastError(); set_error("cudaGetDeviceCount: %s", cudaGetErrorString(err)); return BORB_ERR_NO_DEVICE; }
+    return BORB_OK;
+}
+
+borb_status borb_host_alloc(void** p, size_t bytes) {
+    if (!p) return BORB_ERR_INVALID_ARG;
+    BORB_CUDA(cudaMallocHost(p, bytes));
+    return BORB_OK;
+}
+borb_status borb_host_free(void* p) {
+    if (p) BORB_CUDA(cudaFreeHost(p));
+    return BORB_OK;
+}
+
+borb_status borb_extractor_create(const borb_extractor_cfg* cfg, int device, borb_extractor** out) {
+    if (!cfg || !out) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (cfg->n_levels < 1 || cfg->n_levels > BORB_MAX_LEVELS || cfg->n_features < 1 || !(cfg->scale_factor > 1.0f)) {
+        set_error("bad extractor cfg (n_features=%d scale=%f levels=%d)", cfg->n_features, cfg->scale_factor, cfg->n_levels);
+        return BORB_ERR_INVALID_ARG;
+    }
+    int ndev = 0;
+    borb_status st = borb_device_count(&ndev);
+    if (st != BORB_OK) return st;
+    if (ndev < 1) { set_error("no CUDA device visible; libborb has no CPU fallback"); return BORB_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d visible)", device, ndev); return BORB_ERR_INVALID_ARG; }
+    borb_extractor* e = new borb_extractor();
+    e->cfg = *cfg;
+    e->device = device;
+    init_tables(e);
+    cudaError_t err = cudaSetDevice(device);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 9 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev[i]);
+    if (err != cudaSuccess) {
+        set_error("CUDA init failed: %s", cudaGetErrorString(err));
+        delete e;
+        return BORB_ERR_CUDA;
+    }
+    *out = e;
+    return BORB_OK;
+}
+
+borb_status borb_extractor_destroy(borb_extractor* e) {
+    if (!e) return BORB_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    free_workspace(e->ws);
+    if (e->h_counts) cudaFreeHost(e->h_counts);
+    for (int i = 0; i < 9; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return BORB_OK;
+}
+
+borb_status borb_extractor_tables(const borb_extractor* e, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                                  int32_t* features_per_level) {
+    if (!e) return BORB_ERR_INVALID_ARG;
+    for (int l = 0; l < e->cfg.n_levels; l++) {
+        if (scale) scale[l] = e->scale[l];
+        if (inv_scale) inv_scale[l] = e->inv_scale[l];
+        if (sigma2) sigma2[l] = e->sigma2[l];
+        if (inv_sigma2) inv_sigma2[l] = e->inv_sigma2[l];
+        if (features_per_level) features_per_level[l] = e->per_level[l];
+    }
+    return BORB_OK;
+}
+
+borb_status borb_extractor_capacity(const borb_extractor* e, int width, int height, int* cap) {
+    if (!e || !cap) return BORB_ERR_INVALID_ARG;
+    borb_extractor tmp;
+    tmp.cfg = e->cfg; tmp.scale = e->scale; tmp.inv_scale = e->inv_scale; tmp.per_level = e->per_level;
+    std::memcpy(tmp.umax, e->umax, sizeof(tmp.umax));
+    std::vector<int16_t> tabs;
+    if (width < 1 || height < 1 || width > BORB_MAX_DIM || height > BORB_MAX_DIM) { set_error("image size out of range"); return BORB_ERR_UNSUPPORTED; }
+    borb_status st = build_geometry(&tmp, width, height, tabs);
+    if (st != BORB_OK) return st;
+    *cap = tmp.geom.sel_image_stride;
+    return BORB_OK;
+}
+
+borb_status borb_extractor_reserve(borb_extractor* e, int width, int height, int max_images) {
+    if (!e || max_images < 1) return BORB_ERR_INVALID_ARG;
+    return ensure(e, width, height, max_images);
+}
+
+borb_status borb_sync(borb_extractor* e) {
+    if (!e) return BORB_ERR_INVALID_ARG;
+    BORB_CUDA(cudaSetDevice(e->device));
+    BORB_CUDA(cudaStreamSynchronize(e->stream));
+    return finish_timing(e);
+}
+
+borb_status borb_extract_batch_enqueue(borb_extractor* e, const uint8_t* const* gray, int n, int w, int h, int stride,
+                                       borb_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+    borb_status st = check_args(e, n, w, h);
+    if (st != BORB_OK) return st;
+    if (n == 0) return BORB_OK;
+    if (!gray || cap < 0 || stride < w) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
+    if ((st = ensure(e, w, h, n)) != BORB_OK) return st;
+    mark(e, 0);
+    if ((st = upload_host(e, gray, 0, n, 1, w, h, stride)) != BORB_OK) return st;
+    if ((st = enqueue_extract(e, n)) != BORB_OK) return st;
+    mark(e, 7);
+    st = download_kps(e, 0, n, 1, kps, desc, cap, n_out);
+    mark(e, 8);
+    return st;
+}
+
+borb_status borb_extract_batch(borb_extractor* e, const uint8_t* const* gray, int n, int w, int h, int stride,
+                               borb_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+    if (!n_out) { set_error("n_out is required"); return BORB_ERR_INVALID_ARG; }
+    borb_status st = borb_extract_batch_enqueue(e, gray, n, w, h, stride, kps, desc, cap, n_out);
+    if (st != BORB_OK) return st;
+    if (n == 0) return BORB_OK;
+    if ((st = borb_sync(e)) != BORB_OK) return st;
+    for (int i = 0; i < n; i++)
+        if (n_out[i] > cap) { set_error("image %d produced %d keypoints, capacity %d", i, n_out[i], cap); return BORB_ERR_CAPACITY; }
+    return BORB_OK;
+}
+
+borb_status borb_extract(borb_extractor* e, const uint8_t* gray, int w, int h, int stride, borb_keypoint* kps, uint8_t* desc,
+                         int cap, int* n_out) {
+    if (!n_out) { set_error("n_out is required"); return BORB_ERR_INVALID_ARG; }
+    *n_out = 0;
+    if (!gray || w == 0 || h == 0) return BORB_OK;     // empty image: silent return (ORBextractor.cc:1046-1047)
+    const uint8_t* one[1] = {gray};
+    return borb_extract_batch(e, one, 1, w, h, stride, kps, desc, cap, n_out);
+}
+
+borb_status borb_extract_batch_device(borb_extractor* e, const uint8_t* d_gray, int n, int w, int h, size_t pitch,
+                                      size_t image_stride, borb_keypoint* kps, uint8_t* desc, int cap, int* n_out) {
+    borb_status st = check_args(e, n, w, h);
+    if (st != BORB_OK) return st;
+    if (n == 0) return BORB_OK;
+    if (!d_gray || pitch < (size_t)w) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
+    if ((st = ensure(e, w, h, n)) != BORB_OK) return st;
+    mark(e, 0);
+    if ((st = upload_device(e, d_gray, n, w, h, pitch, image_stride)) != BORB_OK) return st;
+    if ((st = enqueue_extract(e, n)) != BORB_OK) return st;
+    mark(e, 7);
+    if ((st = download_kps(e, 0, n, 1, kps, desc, cap, n_out)) != BORB_OK) return st;
+    mark(e, 8);
+    return borb_sync(e);
+}
+
+borb_status borb_extractor_pyramid(borb_extractor* e, int image, int level, uint8_t* dst, int* w, int* h) {
+    if (!e || !e->have_geom || image < 0 || image >= e->last_n_images || level < 0 || level >= e->geom.nlevels) {
+        set_error("no such image/level in the last batch");
+        return BORB_ERR_STATE;
+    }
+    const LevelGeom& L = e->geom.lv[level];
+    if (w) *w = L.w;
+    if (h) *h = L.h;
+    if (!dst) return BORB_OK;
+    BORB_CUDA(cudaSetDevice(e->device));
+    BORB_CUDA(cudaMemcpy2DAsync(dst, L.w, e->ws.pyr + (size_t)image * e->geom.pyr_image_stride + L.pyr_off, L.pitch, L.w, L.h,
+                                cudaMemcpyDeviceToHost, e->stream));
+    BORB_CUDA(cudaStreamSynchronize(e->stream));
+    return BORB_OK;
+}
+
+borb_status borb_debug_blurred(borb_extractor* e, int image, int level, uint8_t* dst, int* w, int* h) {
+    if (!e || !e->have_geom || image < 0 || image >= e->last_n_images || level < 0 || level >= e->geom.nlevels) {
+        set_error("no such image/level in the last batch");
+        return BORB_ERR_STATE;
+    }
+    const LevelGeom& L = e->geom.lv[level];
+    if (w) *w = L.w;
+    if (h) *h = L.h;
+    if (!dst) return BORB_OK;
+    BORB_CUDA(cudaSetDevice(e->device));
+    BORB_CUDA(cudaMemcpy2DAsync(dst, L.w, e->ws.blur + (size_t)image * e->geom.pyr_image_stride + L.pyr_off, L.pitch, L.w, L.h,
+                                cudaMemcpyDeviceToHost, e->stream));
+    BORB_CUDA(cudaStreamSynchronize(e->stream));
+    return BORB_OK;
+}
+
+static borb_status debug_list(borb_extractor* e, int image, int level, bool selected, int32_t* xys, int cap, int* n_out) {
+    if (!e || !n_out || !e->have_geom || image < 0 || image >= e->last_n_images || level < 0 || level >= e->geom.nlevels) {
+        set_error("no such image/level in the last batch");
+        return BORB_ERR_STATE;
+    }
+    const Geometry& g = e->geom;
+    const LevelGeom& L = g.lv[level];
+    BORB_CUDA(cudaSetDevice(e->device));
+    BORB_CUDA(cudaStreamSynchronize(e->stream));
+    int n = 0;
+    BORB_CUDA(cudaMemcpy(&n, (selected ? e->ws.sel_cnt : e->ws.cand_cnt) + image * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    const int m = n < cap ? n : cap;
+    if (m <= 0 || !xys) return BORB_OK;
+    std::vector<uint32_t> raw(m);
+    const uint32_t* src = selected ? e->ws.sel + (size_t)image * g.sel_image_stride + L.sel_off
+                                   : e->ws.cand + (size_t)image * g.cand_image_stride + L.cand_off;
+    BORB_CUDA(cudaMemcpy(raw.data(), src, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++) { xys[3 * i] = xys_x(raw[i]); xys[3 * i + 1] = xys_y(raw[i]); xys[3 * i + 2] = xys_s(raw[i]); }
+    return BORB_OK;
+}
+borb_status borb_debug_candidates(borb_extractor* e, int image, int level, int32_t* xys, int cap, int* n_out) {
+    return debug_list(e, image, level, false, xys, cap, n_out);
+}
+borb_status borb_debug_selected(borb_extractor* e, int image, int level, int32_t* xys, int cap, int* n_out) {
+    return debug_list(e, image, level, true, xys, cap, n_out);
+}
+
+borb_status borb_launch_count(const borb_extractor* e, uint64_t* n) {
+    if (!e || !n) return BORB_ERR_INVALID_ARG;
+    *n = e->launches;
+    return BORB_OK;
+}
+borb_status borb_set_timing(borb_extractor* e, int enable) {
+    if (!e) return BORB_ERR_INVALID_ARG;
+    e->timing = enable != 0;
+    return BORB_OK;
+}
+borb_status borb_stage_times(borb_extractor* e, float* ms8) {
+    if (!e || !ms8) return BORB_ERR_INVALID_ARG;
+    for (int i = 0; i < 8; i++) ms8[i] = e->stage_ms[i];
+    return BORB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- stereo
+borb_status borb_stereo_match(borb_extractor* e, int n_pairs, const int* left_idx, const int* right_idx, float bf, float b,
+                              float* u_right, float* depth, int cap) {
+    if (!e || n_pairs < 0 || !(b > 0.f)) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
+    if (!e->have_geom || e->last_n_images == 0) { set_error("stereo match before any extract"); return BORB_ERR_STATE; }
+    if (n_pairs == 0) return BORB_OK;
+    BORB_CUDA(cudaSetDevice(e->device));
+    borb_status st = enqueue_stereo(e, e, n_pairs, left_idx, right_idx, bf, b);
+    if (st != BORB_OK) return st;
+    if ((st = download_stereo(e, n_pairs, u_right, depth, cap)) != BORB_OK) return st;
+    mark(e, 8);
+    return borb_sync(e);
+}
+
+borb_status borb_stereo_match2(borb_extractor* left, borb_extractor* right, float bf, float b, float* u_right, float* depth, int cap) {
+    if (!left || !right || !(b > 0.f)) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
+    if (!left->have_geom || !right->have_geom || left->last_n_images < 1 || right->last_n_images < 1) { set_error("stereo match before extract"); return BORB_ERR_STATE; }
+    if (left->device != right->device || left->geom.w != right->geom.w || left->geom.h != right->geom.h ||
+        left->geom.nlevels != right->geom.nlevels) {
+        set_error("left/right extractors differ in device or geometry");
+        return BORB_ERR_INVALID_ARG;
+    }
+    BORB_CUDA(cudaSetDevice(left->device));
+    BORB_CUDA(cudaStreamSynchronize(right->stream));   // right results must be complete before left's stream reads them
+    borb_status st = enqueue_stereo(left, right, 1, nullptr, nullptr, bf, b);
+    if (st != BORB_OK) return st;
+    if ((st = download_stereo(left, 1, u_right, depth, cap)) != BORB_OK) return st;
+    mark(left, 8);
+    return borb_sync(left);
+}
+
+borb_status borb_stereo_frames_enqueue(borb_extractor* e, const uint8_t* const* left, const uint8_t* const* right, int n_pairs,
+                                       int w, int h, int stride, float bf, float b, borb_keypoint* kps_left, uint8_t* desc_left,
+                                       int* n_left, borb_keypoint* kps_right, uint8_t* desc_right, int* n_right, float* u_right,
+                                       float* depth, int cap) {
+    borb_status st = check_args(e, n_pairs, w, h);
+    if (st != BORB_OK) return st;
+    if (n_pairs == 0) return BORB_OK;
+    if (!left || !right || stride < w || !(b > 0.f)) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
+    if ((st = ensure(e, w, h, 2 * n_pairs)) != BORB_OK) return st;
+    mark(e, 0);
+    if ((st = upload_host(e, left, 0, n_pairs, 2, w, h, stride)) != BORB_OK) return st;
+    if ((st = upload_host(e, right, 1, n_pairs, 2, w, h, stride)) != BORB_OK) return st;
+    if ((st = enqueue_extract(e, 2 * n_pairs)) != BORB_OK) return st;
+    if ((st = enqueue_stereo(e, e, n_pairs, nullptr, nullptr, bf, b)) != BORB_OK) return st;
+    if ((st = download_kps(e, 0, n_pairs, 2, kps_left, desc_left, cap, n_left)) != BORB_OK) return st;
+    if ((st = download_kps(e, 1, n_pairs, 2, kps_right, desc_right, cap, n_right)) != BORB_OK) return st;
+    if ((st = download_stereo(e, n_pairs, u_right, depth, cap)) != BORB_OK) return st;
+    mark(e, 8);
+    return BORB_OK;
+}
+
+borb_status borb_stereo_frames(borb_extractor* e, const uint8_t* const* left, const uint8_t* const* right, int n_pairs, int w,
+                               int h, int stride, float bf, float b, borb_keypoint* kps_left, uint8_t* desc_left, int* n_left,
+                               borb_keypoint* kps_right, uint8_t* desc_right, int* n_right, float* u_right, float* depth, int cap) {
+    borb_status st = borb_stereo_frames_enqueue(e, left, right, n_pairs, w, h, stride, bf, b, kps_left, desc_left, n_left,
+                                                kps_right, desc_right, n_right, u_right, depth, cap);
+    if (st != BORB_OK || n_pairs == 0) return st;
+    if ((st = borb_sync(e)) != BORB_OK) return st;
+    for (int p = 0; p < n_pairs; p++)
+        if ((n_left && n_left[p] > cap) || (n_right && n_right[p] > cap)) { set_error("pair %d exceeds capacity %d", p, cap); return BORB_ERR_CAPACITY; }
+    return BORB_OK;
+}
+
+borb_status borb_stereo_frames_device(borb_extractor* e, const uint8_t* d_gray, int n_pairs, int w, int h, size_t pitch,
+                                      size_t image_stride, float bf, float b, int* n_left, int* n_right, float* u_right,
+                                      float* depth, int cap) {
+    borb_status st = check_args(e, n_pairs, w, h);
+    if (st != BORB_OK) return st;
+    if (n_pairs == 0) return BORB_OK;
+    if (!d_gray || pitch < (size_t)w || !(b > 0.f)) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
+    if ((st = ensure(e, w, h, 2 * n_pairs)) != BORB_OK) return st;
+    mark(e, 0);
+    if ((st = upload_device(e, d_gray, 2 * n_pairs, w, h, pitch, image_stride)) != BORB_OK) return st;
+    if ((st = enqueue_extract(e, 2 * n_pairs)) != BORB_OK) return st;
+    if ((st = enqueue_stereo(e, e, n_pairs, nullptr, nullptr, bf, b)) != BORB_OK) return st;
+    if ((st = download_kps(e, 0, n_pairs, 2, nullptr, nullptr, cap, n_left)) != BORB_OK) return st;
+    if ((st = download_kps(e, 1, n_pairs, 2, nullptr, nullptr, cap, n_right)) != BORB_OK) return st;
+    if ((st = download_stereo(e, n_pairs, u_right, depth, cap)) != BORB_OK) return st;
+    mark(e, 8);
+    return borb_sync(e);
+}
+
+}  // extern "C"

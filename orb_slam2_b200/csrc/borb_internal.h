@@ -1,0 +1,135 @@
+// Internal declarations of libborb (B200 / sm_100a ORB front-end).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/borb.h"
+
+namespace borb {
+
+constexpr int EDGE = 19;          // EDGE_THRESHOLD   (ORBextractor.cc:74)
+constexpr int PATCH = 31;         // PATCH_SIZE       (:72)
+constexpr int HALF_PATCH = 15;    // HALF_PATCH_SIZE  (:73)
+constexpr int MIN_BORDER = 16;    // EDGE_THRESHOLD-3 (:773)
+constexpr int TH_HIGH = 100;      // ORBmatcher.cc:37
+constexpr int TH_LOW = 50;        // ORBmatcher.cc:38
+constexpr int FAST_TILE_W = 128;  // max detection-domain width handled by one FAST CTA
+
+// Candidate / selected-keypoint record: x | y<<12 | score<<24   (x,y <= 4095, score <= 255)
+__host__ __device__ inline uint32_t pack_xys(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
+__host__ __device__ inline int xys_x(uint32_t v) { return (int)(v & 0xFFFu); }
+__host__ __device__ inline int xys_y(uint32_t v) { return (int)((v >> 12) & 0xFFFu); }
+__host__ __device__ inline int xys_s(uint32_t v) { return (int)(v >> 24); }
+
+struct LevelGeom {
+    int w, h;               // level size, cvRound(orig * invScale) (ORBextractor.cc:1111-1112)
+    int pitch;              // bytes per row in the pyramid buffers
+    unsigned pyr_off;       // byte offset of this level inside one image's pyramid block
+    // FAST cell grid (ORBextractor.cc:781-787)
+    int nCols, nRows, wCell, hCell;
+    int cellsPerBlk;        // cells per FAST CTA along x
+    int blkCols;            // CTAs per cell row
+    int blkBase;            // first CTA of this level inside one image's FAST grid
+    unsigned cand_off;      // entry offset of this level's candidate list inside one image's block
+    int cand_cap;
+    int quota;              // mnFeaturesPerLevel[level]
+    int nIni;               // quadtree roots (ORBextractor.cc:543)
+    float hX;               // (:545)
+    int node_cap;           // max list size + slack
+    int sel_off;            // entry offset of this level's selected list inside one image's block
+    float scale;            // mvScaleFactor[level]
+    float inv_scale;        // mvInvScaleFactor[level]
+    float patch_size;       // (float)(int)(PATCH_SIZE*scale)  (:837)
+    unsigned xtab_off, ytab_off;   // resize tables (int16 triplets: ofs, c0, c1), entries
+};
+
+struct Geometry {
+    int nlevels;
+    int w, h;
+    int ini_th, min_th;
+    int fast_blocks;            // FAST CTAs per image (all levels)
+    unsigned pyr_image_stride;  // bytes
+    unsigned cand_image_stride; // entries
+    int sel_image_stride;       // entries  (== keypoint capacity per image)
+    int blur_tiles;             // blur CTAs per image (all levels)
+    int blur_base[BORB_MAX_LEVELS + 1];
+    int umax[16];
+    LevelGeom lv[BORB_MAX_LEVELS];
+};
+
+// Per-batch device buffers of one handle
+struct Workspace {
+    int max_images = 0;
+    uint8_t* pyr = nullptr;        // max_images * pyr_image_stride
+    uint8_t* blur = nullptr;       // same layout, GaussianBlur'ed levels
+    uint32_t* cand = nullptr;      // max_images * cand_image_stride
+    int* cand_cnt = nullptr;       // max_images * nlevels
+    int* pnode = nullptr;          // quadtree scratch, same shape as cand
+    uint32_t* sel = nullptr;       // max_images * sel_image_stride
+    int* sel_cnt = nullptr;        // max_images * nlevels
+    borb_keypoint* kps = nullptr;  // max_images * sel_image_stride
+    uint8_t* desc = nullptr;       // max_images * sel_image_stride * 32
+    int* nkp = nullptr;            // max_images
+    float* u_right = nullptr;      // max_images/2+1 pairs * sel_image_stride
+    float* depth = nullptr;
+    int* sad = nullptr;            // SAD distance per left keypoint (-1: none)
+    int16_t* tabs = nullptr;       // resize tables
+    int* pair_idx = nullptr;       // 2 * max_pairs (left,right image indices)
+};
+
+void set_error(const char* fmt, ...);
+#define BORB_CUDA(call)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            borb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? BORB_ERR_NO_DEVICE : BORB_ERR_CUDA; \
+        }                                                                                           \
+    } while (0)
+
+// ---- kernel launchers (each returns the number of kernel launches it issued) -----------------
+int launch_pyramid(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s);
+int launch_fast(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s);
+int launch_quadtree(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s);
+int launch_blur(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s);
+int launch_describe(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s);
+
+struct StereoView {          // device pointers of one side of a stereo pair set
+    const uint8_t* pyr;      // pyramid base (image 0)
+    const borb_keypoint* kps;
+    const uint8_t* desc;
+    const int* nkp;
+    unsigned pyr_image_stride;
+    int kp_image_stride;
+};
+int launch_stereo(const Geometry& g, const StereoView& L, const StereoView& R, const int* d_pair_idx, int n_pairs,
+                  float bf, float b, float* d_u_right, float* d_depth, int* d_sad, int out_stride, cudaStream_t s);
+size_t quadtree_smem_bytes(int node_cap);
+
+}  // namespace borb
+
+struct borb_extractor {
+    borb_extractor_cfg cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // reference ctor tables (ORBextractor.cc:410-470)
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> per_level;
+    int umax[16];
+    // geometry + workspace for the current (w,h)
+    bool have_geom = false;
+    borb::Geometry geom;
+    borb::Workspace ws;
+    int last_n_images = 0;       // images of the last batch (0: none)
+    uint64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[9] = {};
+    float stage_ms[8] = {};
+    // staging
+    int* h_counts = nullptr;     // pinned staging for the stereo pair table (2 ints per image)
+    std::vector<int> pair_cache; // pair table currently resident in ws.pair_idx
+};
