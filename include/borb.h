@@ -147,7 +147,10 @@ BORB_API borb_status borb_stereo_frames_enqueue(borb_extractor* e, const uint8_t
                                        borb_keypoint* kps_left, uint8_t* desc_left, int* n_left,
                                        borb_keypoint* kps_right, uint8_t* desc_right, int* n_right, float* u_right,
                                        float* depth, int cap);
-/* HBM-resident variant (inputs as in borb_extract_batch_device: image 2p = left, 2p+1 = right). */
+/* HBM-resident variants (inputs as in borb_extract_batch_device: image 2p = left, 2p+1 = right). */
+BORB_API borb_status borb_stereo_frames_device_enqueue(borb_extractor* e, const uint8_t* d_gray, int n_pairs, int width,
+                                              int height, size_t pitch, size_t image_stride, float bf, float b,
+                                              int* n_left, int* n_right, float* u_right, float* depth, int cap);
 BORB_API borb_status borb_stereo_frames_device(borb_extractor* e, const uint8_t* d_gray, int n_pairs, int width, int height,
                                       size_t pitch, size_t image_stride, float bf, float b, int* n_left, int* n_right,
                                       float* u_right, float* depth, int cap);
@@ -163,7 +166,12 @@ BORB_API borb_status borb_launch_count(const borb_extractor* e, uint64_t* n);
 /* Device time (ms, CUDA events on the handle's stream) of each stage of the last batch:
  * [0] upload, [1] pyramid, [2] FAST/NMS, [3] quadtree, [4] blur, [5] orient+rBRIEF, [6] stereo, [7] download. */
 BORB_API borb_status borb_stage_times(borb_extractor* e, float* ms8);
-BORB_API borb_status borb_set_timing(borb_extractor* e, int enable);
+BORB_API borb_status borb_set_timing(borb_extractor* e, int enable);   /* also resets the accumulators */
+/* Per-stage device time summed over every step completed (synced) since borb_set_timing(e,1); steps may
+ * be queued back to back without host syncs (a ring of CUDA events on the handle's stream). */
+BORB_API borb_status borb_stage_times_total(borb_extractor* e, double* ms8, uint64_t* steps);
+/* The handle's cudaStream_t, so callers can bracket work with their own CUDA events. */
+BORB_API borb_status borb_extractor_stream(borb_extractor* e, void** stream);
 
 #ifdef __cplusplus
 }

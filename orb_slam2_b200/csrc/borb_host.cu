@@ -190,7 +190,47 @@ borb_status ensure(borb_extractor* e, int w, int h, int n_images) {
     return BORB_OK;
 }
 
-void mark(borb_extractor* e, int i) { if (e->timing) cudaEventRecord(e->ev[i], e->stream); }
+void drain_timing(borb_extractor* e);
+void begin_step(borb_extractor* e) {
+    if (!e->timing) return;
+    if (e->ev.empty()) {
+        e->ev.resize((size_t)borb_extractor::EV_RING * 9);
+        for (auto& x : e->ev) cudaEventCreate(&x);
+    }
+    if (e->ev_pending >= borb_extractor::EV_RING) {   // ring full: drain (costs a sync, only in timing mode)
+        cudaStreamSynchronize(e->stream);
+        drain_timing(e);
+    }
+    e->ev_slot = (e->ev_slot + 1) % borb_extractor::EV_RING;
+    e->ev_mask[e->ev_slot] = 0;
+    e->ev_pending++;
+}
+void mark(borb_extractor* e, int i) {
+    if (!e->timing || e->ev.empty()) return;
+    cudaEventRecord(e->ev[(size_t)e->ev_slot * 9 + i], e->stream);
+    e->ev_mask[e->ev_slot] |= 1u << i;
+}
+// After a stream sync: fold the pending slots into stage_ms / stage_sum_ms.
+void drain_timing(borb_extractor* e) {
+    const int R = borb_extractor::EV_RING;
+    for (int k = e->ev_pending - 1; k >= 0; k--) {
+        const int slot = ((e->ev_slot - k) % R + R) % R;
+        const unsigned m = e->ev_mask[slot];
+        for (int i = 0; i < 8; i++) {
+            float ms = 0.f;
+            // stage i = [mark i, next recorded mark)
+            if (m & (1u << i)) {
+                int j = i + 1;
+                while (j < 9 && !(m & (1u << j))) j++;
+                if (j < 9 && cudaEventElapsedTime(&ms, e->ev[(size_t)slot * 9 + i], e->ev[(size_t)slot * 9 + j]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
+            }
+            e->stage_ms[i] = ms;
+            e->stage_sum_ms[i] += ms;
+        }
+        e->stage_steps++;
+    }
+    e->ev_pending = 0;
+}
 
 // Queues pyramid .. descriptors for n images whose level 0 is already in ws.pyr.
 borb_status enqueue_extract(borb_extractor* e, int n) {
@@ -308,12 +348,7 @@ borb_status download_stereo(borb_extractor* e, int n_pairs, float* u_right, floa
 }
 
 borb_status finish_timing(borb_extractor* e) {
-    if (!e->timing) return BORB_OK;
-    for (int i = 0; i < 8; i++) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
-        e->stage_ms[i] = ms;
-    }
+    if (e->timing && e->ev_pending > 0) drain_timing(e);
     return BORB_OK;
 }
 
@@ -375,7 +410,6 @@ borb_status borb_extractor_create(const borb_extractor_cfg* cfg, int device, bor
     init_tables(e);
     cudaError_t err = cudaSetDevice(device);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 9 && err == cudaSuccess; i++) err = cudaEventCreate(&e->ev[i]);
     if (err != cudaSuccess) {
         set_error("CUDA init failed: %s", cudaGetErrorString(err));
         delete e;
@@ -391,7 +425,7 @@ borb_status borb_extractor_destroy(borb_extractor* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     free_workspace(e->ws);
     if (e->h_counts) cudaFreeHost(e->h_counts);
-    for (int i = 0; i < 9; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (auto& x : e->ev) cudaEventDestroy(x);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return BORB_OK;
@@ -442,6 +476,7 @@ borb_status borb_extract_batch_enqueue(borb_extractor* e, const uint8_t* const* 
     if (n == 0) return BORB_OK;
     if (!gray || cap < 0 || stride < w) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
     if ((st = ensure(e, w, h, n)) != BORB_OK) return st;
+    begin_step(e);
     mark(e, 0);
     if ((st = upload_host(e, gray, 0, n, 1, w, h, stride)) != BORB_OK) return st;
     if ((st = enqueue_extract(e, n)) != BORB_OK) return st;
@@ -479,6 +514,7 @@ borb_status borb_extract_batch_device(borb_extractor* e, const uint8_t* d_gray, 
     if (n == 0) return BORB_OK;
     if (!d_gray || pitch < (size_t)w) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
     if ((st = ensure(e, w, h, n)) != BORB_OK) return st;
+    begin_step(e);
     mark(e, 0);
     if ((st = upload_device(e, d_gray, n, w, h, pitch, image_stride)) != BORB_OK) return st;
     if ((st = enqueue_extract(e, n)) != BORB_OK) return st;
@@ -556,6 +592,20 @@ borb_status borb_launch_count(const borb_extractor* e, uint64_t* n) {
 borb_status borb_set_timing(borb_extractor* e, int enable) {
     if (!e) return BORB_ERR_INVALID_ARG;
     e->timing = enable != 0;
+    for (int i = 0; i < 8; i++) { e->stage_sum_ms[i] = 0; e->stage_ms[i] = 0; }
+    e->stage_steps = 0;
+    e->ev_pending = 0;
+    return BORB_OK;
+}
+borb_status borb_stage_times_total(borb_extractor* e, double* ms8, uint64_t* steps) {
+    if (!e || !ms8 || !steps) return BORB_ERR_INVALID_ARG;
+    for (int i = 0; i < 8; i++) ms8[i] = e->stage_sum_ms[i];
+    *steps = e->stage_steps;
+    return BORB_OK;
+}
+borb_status borb_extractor_stream(borb_extractor* e, void** stream) {
+    if (!e || !stream) return BORB_ERR_INVALID_ARG;
+    *stream = (void*)e->stream;
     return BORB_OK;
 }
 borb_status borb_stage_times(borb_extractor* e, float* ms8) {
@@ -571,6 +621,7 @@ borb_status borb_stereo_match(borb_extractor* e, int n_pairs, const int* left_id
     if (!e->have_geom || e->last_n_images == 0) { set_error("stereo match before any extract"); return BORB_ERR_STATE; }
     if (n_pairs == 0) return BORB_OK;
     BORB_CUDA(cudaSetDevice(e->device));
+    begin_step(e);
     borb_status st = enqueue_stereo(e, e, n_pairs, left_idx, right_idx, bf, b);
     if (st != BORB_OK) return st;
     if ((st = download_stereo(e, n_pairs, u_right, depth, cap)) != BORB_OK) return st;
@@ -588,6 +639,7 @@ borb_status borb_stereo_match2(borb_extractor* left, borb_extractor* right, floa
     }
     BORB_CUDA(cudaSetDevice(left->device));
     BORB_CUDA(cudaStreamSynchronize(right->stream));   // right results must be complete before left's stream reads them
+    begin_step(left);
     borb_status st = enqueue_stereo(left, right, 1, nullptr, nullptr, bf, b);
     if (st != BORB_OK) return st;
     if ((st = download_stereo(left, 1, u_right, depth, cap)) != BORB_OK) return st;
@@ -604,6 +656,7 @@ borb_status borb_stereo_frames_enqueue(borb_extractor* e, const uint8_t* const* 
     if (n_pairs == 0) return BORB_OK;
     if (!left || !right || stride < w || !(b > 0.f)) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
     if ((st = ensure(e, w, h, 2 * n_pairs)) != BORB_OK) return st;
+    begin_step(e);
     mark(e, 0);
     if ((st = upload_host(e, left, 0, n_pairs, 2, w, h, stride)) != BORB_OK) return st;
     if ((st = upload_host(e, right, 1, n_pairs, 2, w, h, stride)) != BORB_OK) return st;
@@ -628,14 +681,15 @@ borb_status borb_stereo_frames(borb_extractor* e, const uint8_t* const* left, co
     return BORB_OK;
 }
 
-borb_status borb_stereo_frames_device(borb_extractor* e, const uint8_t* d_gray, int n_pairs, int w, int h, size_t pitch,
-                                      size_t image_stride, float bf, float b, int* n_left, int* n_right, float* u_right,
-                                      float* depth, int cap) {
+borb_status borb_stereo_frames_device_enqueue(borb_extractor* e, const uint8_t* d_gray, int n_pairs, int w, int h, size_t pitch,
+                                              size_t image_stride, float bf, float b, int* n_left, int* n_right, float* u_right,
+                                              float* depth, int cap) {
     borb_status st = check_args(e, n_pairs, w, h);
     if (st != BORB_OK) return st;
     if (n_pairs == 0) return BORB_OK;
     if (!d_gray || pitch < (size_t)w || !(b > 0.f)) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
     if ((st = ensure(e, w, h, 2 * n_pairs)) != BORB_OK) return st;
+    begin_step(e);
     mark(e, 0);
     if ((st = upload_device(e, d_gray, 2 * n_pairs, w, h, pitch, image_stride)) != BORB_OK) return st;
     if ((st = enqueue_extract(e, 2 * n_pairs)) != BORB_OK) return st;
@@ -644,6 +698,15 @@ borb_status borb_stereo_frames_device(borb_extractor* e, const uint8_t* d_gray, 
     if ((st = download_kps(e, 1, n_pairs, 2, nullptr, nullptr, cap, n_right)) != BORB_OK) return st;
     if ((st = download_stereo(e, n_pairs, u_right, depth, cap)) != BORB_OK) return st;
     mark(e, 8);
+    return BORB_OK;
+}
+
+borb_status borb_stereo_frames_device(borb_extractor* e, const uint8_t* d_gray, int n_pairs, int w, int h, size_t pitch,
+                                      size_t image_stride, float bf, float b, int* n_left, int* n_right, float* u_right,
+                                      float* depth, int cap) {
+    borb_status st = borb_stereo_frames_device_enqueue(e, d_gray, n_pairs, w, h, pitch, image_stride, bf, b, n_left, n_right,
+                                                       u_right, depth, cap);
+    if (st != BORB_OK || n_pairs == 0) return st;
     return borb_sync(e);
 }
 

@@ -126,9 +126,16 @@ struct borb_extractor {
     borb::Workspace ws;
     int last_n_images = 0;       // images of the last batch (0: none)
     uint64_t launches = 0;
+    // stage timing: a ring of event sets so that many queued steps can be timed without host syncs
+    static constexpr int EV_RING = 128;
     bool timing = false;
-    cudaEvent_t ev[9] = {};
-    float stage_ms[8] = {};
+    std::vector<cudaEvent_t> ev;          // EV_RING * 9, created lazily
+    unsigned ev_mask[EV_RING] = {};       // which of the 9 marks were recorded in that slot
+    int ev_slot = 0;                      // slot of the step being enqueued
+    int ev_pending = 0;                   // steps enqueued since the last borb_sync
+    float stage_ms[8] = {};               // last step
+    double stage_sum_ms[8] = {};          // accumulated since borb_set_timing(1)
+    uint64_t stage_steps = 0;
     // staging
     int* h_counts = nullptr;     // pinned staging for the stereo pair table (2 ints per image)
     std::vector<int> pair_cache; // pair table currently resident in ws.pair_idx
