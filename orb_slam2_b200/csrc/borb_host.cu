@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "borb_internal.h"
@@ -146,6 +147,7 @@ void free_workspace(Workspace& ws) {
     cudaFree(ws.pyr); cudaFree(ws.blur); cudaFree(ws.cand); cudaFree(ws.cand_cnt); cudaFree(ws.pnode); cudaFree(ws.sel);
     cudaFree(ws.sel_cnt); cudaFree(ws.kps); cudaFree(ws.desc); cudaFree(ws.nkp); cudaFree(ws.u_right); cudaFree(ws.depth);
     cudaFree(ws.sad); cudaFree(ws.tabs); cudaFree(ws.pair_idx);
+    free(ws.fast_tmaps);
     ws = Workspace();
 }
 
@@ -186,6 +188,8 @@ borb_status ensure(borb_extractor* e, int w, int h, int n_images) {
     BORB_CUDA(cudaMemset(ws.nkp, 0, n * sizeof(int)));
     BORB_CUDA(cudaMallocHost(&e->h_counts, n * 2 * sizeof(int)));
     ws.max_images = (int)n;
+    ws.fast_tmaps = malloc(fast_tmaps_bytes());
+    if ((st = build_fast_tmaps(g, ws, ws.fast_tmaps)) != BORB_OK) return st;
     e->have_geom = true;
     return BORB_OK;
 }

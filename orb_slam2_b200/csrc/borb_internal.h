@@ -17,7 +17,7 @@ constexpr int HALF_PATCH = 15;    // HALF_PATCH_SIZE  (:73)
 constexpr int MIN_BORDER = 16;    // EDGE_THRESHOLD-3 (:773)
 constexpr int TH_HIGH = 100;      // ORBmatcher.cc:37
 constexpr int TH_LOW = 50;        // ORBmatcher.cc:38
-constexpr int FAST_TILE_W = 128;  // max detection-domain width handled by one FAST CTA
+constexpr int FAST_TILE_W = 124;  // max detection-domain width of one FAST CTA (<= 32 aligned words incl. misalignment)
 
 // Candidate / selected-keypoint record: x | y<<12 | score<<24   (x,y <= 4095, score <= 255)
 __host__ __device__ inline uint32_t pack_xys(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
@@ -79,6 +79,7 @@ struct Workspace {
     int* sad = nullptr;            // SAD distance per left keypoint (-1: none)
     int16_t* tabs = nullptr;       // resize tables
     int* pair_idx = nullptr;       // 2 * max_pairs (left,right image indices)
+    void* fast_tmaps = nullptr;    // HOST: per-level CUtensorMap set for fast_kernel (passed by value at launch)
 };
 
 void set_error(const char* fmt, ...);
@@ -109,6 +110,8 @@ struct StereoView {          // device pointers of one side of a stereo pair set
 int launch_stereo(const Geometry& g, const StereoView& L, const StereoView& R, const int* d_pair_idx, int n_pairs,
                   float bf, float b, float* d_u_right, float* d_depth, int* d_sad, int out_stride, cudaStream_t s);
 size_t quadtree_smem_bytes(int node_cap);
+borb_status build_fast_tmaps(const Geometry& g, const Workspace& ws, void* out_tmaps);
+size_t fast_tmaps_bytes();
 
 }  // namespace borb
 

@@ -11,22 +11,44 @@
 //             detection domain (neighbours outside count as 0);
 //   a cell emits keep(p) with S>=iniTh if any exists, else keep(p) with S>=minTh.
 // One CTA owns `cellsPerBlk` whole cells of one cell row, so NMS and the threshold decision are CTA-local.
+//
+// Pipeline inside a CTA (v2):
+//   0. one elected thread issues a 3-D TMA tile load (cp.async.bulk.tensor, box 160 x (hCell+6) bytes at
+//      ((x0-4)&~15, y0-3, image): the inner start coordinate must be 16-byte aligned) into shared memory
+//      and everybody waits on its mbarrier;
+//   1. packed quick-reject: a thread owns the 4 pixels of one ALIGNED 32-bit word of the tile and
+//      slides down its rows; per ring position one VABSDIFF4 gives |I_q - I_p| for the 4 pixels and three
+//      logic ops turn it into a per-byte ">t" flag; a FAST-9 arc contains at least one pixel of each of
+//      the 8 antipodal ring pairs, so AND_j (f_j | f_{j+8}) == 0 rejects the pixel.  Even positions first;
+//      odd positions only if something survives.  Survivors are appended to a shared-memory queue;
+//   2. exact arc test + score for queued pixels only;  3. cell-local NMS for scored pixels only;
+//   4. per-cell threshold decision and warp-aggregated append to the global candidate list.
 // Output: unordered candidate list per (image, level) of packed (x,y,score); consumers break ties with
 // the reference's emission order key (cell row, cell col, y, x), never with list position.
 //
-// Bound (target): HBM read of the level pixels, once — sum_l w_l*h_l bytes per image.
+// Bound (target): HBM read of the level pixels, once — sum_l w_l*h_l bytes per image.  Measured: issue
+// bound (see profiles/); the packed reject is what keeps the instruction count per pixel low.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "borb_internal.h"
 
 namespace borb {
 
 namespace {
 
-constexpr int TILE_PITCH = FAST_TILE_W + 8;   // smem image-tile pitch (domain + 3 halo each side, padded)
-constexpr int TILE_ROWS = 64 + 6;             // hCell < 61
+constexpr int TP = 160;                 // TMA box width == smem tile pitch (bytes).  TMA needs a 16-byte aligned start
+                                        // column, so the box starts at xs = (x0-4) & ~15 and domain px xx sits at column xx+off
+constexpr int TROWS = 66;               // hCell <= 60, + 3 halo rows above and below
+constexpr int SW = 128;                 // score-map pitch
+constexpr int QCAP = 60 * 128;          // queue capacity >= every pixel of the largest tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // S(p) if p is a FAST-9 corner at threshold t, else 0.  c points at p inside the smem tile.
 __device__ __forceinline__ int fast_score(const uint8_t* c, int t) {
-    constexpr int P = TILE_PITCH;
+    constexpr int P = TP;
     const int v = c[0];
     int r[16];
     r[0] = c[3 * P];       r[1] = c[3 * P + 1];   r[2] = c[2 * P + 2];   r[3] = c[P + 3];
@@ -40,8 +62,7 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int t) {
         B |= (r[k] > hi ? 1u : 0u) << k;
         D |= (r[k] < lo ? 1u : 0u) << k;
     }
-    // 9 contiguous set bits in the circular 16-bit mask
-    auto arc9 = [](unsigned m) -> bool {
+    auto arc9 = [](unsigned m) -> bool {      // 9 contiguous set bits in the circular 16-bit mask
         unsigned x = m | (m << 16);
         unsigned a = x & (x >> 1);
         a &= a >> 2;
@@ -51,8 +72,8 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int t) {
     };
     const bool cb = arc9(B), cd = arc9(D);
     if (!cb && !cd) return 0;
-    // score: max over arcs of min over the arc of the signed difference, for the polarity that fired
-    // (both cannot fire: 9+9 > 16).  Sliding 9-window minimum on the circular sequence by doubling.
+    // score: max over arcs of the min signed difference, for the polarity that fired (both cannot:
+    // 9+9 > 16).  Sliding 9-window minimum on the circular sequence by doubling.
     int d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) d[k] = cd ? (v - r[k]) : (r[k] - v);
@@ -69,13 +90,33 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int t) {
     return best - 1;
 }
 
+// 4-byte window starting DX bytes after the start of W1 (W0|W1|W2 are three consecutive aligned words)
+template <int DX>
+__device__ __forceinline__ uint32_t win(uint32_t W0, uint32_t W1, uint32_t W2) {
+    if (DX == 0) return W1;
+    if (DX > 0) return __byte_perm(W1, W2, DX | ((DX + 1) << 4) | ((DX + 2) << 8) | ((DX + 3) << 12));
+    constexpr int K = 4 + DX;
+    return __byte_perm(W0, W1, K | ((K + 1) << 4) | ((K + 2) << 8) | ((K + 3) << 12));
+}
+
+// bit 7 of every byte of the result is set iff that byte of |q - v| exceeds t  (T1 = (t+1)*0x01010101, t <= 127)
+__device__ __forceinline__ uint32_t gt_flag(uint32_t q, uint32_t v, uint32_t T1) {
+    const uint32_t a = __vabsdiffu4(q, v);
+    return ((a | 0x80808080u) - T1) | a;
+}
+
 }  // namespace
 
-__global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ pyr,
+struct TMaps { CUtensorMap m[BORB_MAX_LEVELS]; };
+
+__global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ TMaps tm,
                                                    uint32_t* __restrict__ cand, int* __restrict__ cand_cnt) {
-    __shared__ __align__(16) uint8_t tile[TILE_ROWS * TILE_PITCH];
-    __shared__ uint8_t score[64 * FAST_TILE_W];
-    __shared__ int cellHasIni[FAST_TILE_W / 30 + 1];
+    __shared__ __align__(128) uint8_t tile[TROWS * TP];
+    __shared__ __align__(16) uint8_t score[60 * SW];
+    __shared__ uint16_t queue[QCAP];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ int qn;
+    __shared__ int cellHasIni[128 / 30 + 1];
 
     const int img = blockIdx.y;
     int l = 0;
@@ -89,81 +130,225 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     const int y0 = EDGE + cellRow * L.hCell, y1 = min(y0 + L.hCell, L.h - EDGE);
     if (x0 >= x1 || y0 >= y1) return;
     const int tw = x1 - x0, th = y1 - y0;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    const uint8_t* src = pyr + (size_t)img * g.pyr_image_stride + L.pyr_off;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, wrp = tid >> 5;
 
-    if (tid < FAST_TILE_W / 30 + 1) cellHasIni[tid] = 0;
-    // stage the tile (domain + 3-px ring halo).  [19,W-19) x [19,H-19) keeps every read >= 16 px inside.
+    // ---- 0. TMA: tile rows y0-3 .. y0+hCell+2, columns xs .. xs+159 of image `img`, level l
+    const int xs = (x0 - 4) & ~15;          // 16-byte aligned box start (TMA requirement)
+    const int off = x0 - xs;                // tile column of domain pixel xx = 0   (4..19)
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)TP * (uint32_t)(L.hCell + 6);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tm.m[l])), "r"(xs), "r"(y0 - 3), "r"(img), "r"(smem_u32(&bar))
+            : "memory");
+    }
+    // overlap with the copy: clear the score map and the bookkeeping
+    for (int i = tid; i < (th * SW) / 16; i += 256) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 128 / 30 + 1) cellHasIni[tid] = 0;
+    if (tid == 0) qn = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FAST_TMA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra FAST_TMA_DONE;\n"
+        "bra FAST_TMA_WAIT;\n"
+        "FAST_TMA_DONE:\n"
+        "}\n" ::"r"(smem_u32(&bar))
+        : "memory");
+    __syncthreads();
+
+    const int tlow = min(g.ini_th, g.min_th);
+
+    // ---- 1. packed quick reject -> queue of survivors
     {
-        const int lw = tw + 6, lh = th + 6;
-        for (int yy = threadIdx.y; yy < lh; yy += 8) {
-            const uint8_t* row = src + (size_t)(y0 - 3 + yy) * L.pitch + (x0 - 3);
-            for (int xx = threadIdx.x; xx < lw; xx += 32) tile[yy * TILE_PITCH + xx] = row[xx];
+        const int RG = (th + 7) >> 3;                 // rows per warp (8 warps)
+        const int yBeg = wrp * RG, yEnd = min(th, yBeg + RG);
+        // lane owns aligned tile word wbase+lane; its byte b is domain pixel xx = xxb + b
+        const int wbase = off >> 2;
+        const int xxb = 4 * lane - (off & 3);
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (xxb + b >= 0 && xxb + b < tw) vmask |= 0x80u << (8 * b);
+        const uint32_t T1 = (uint32_t)(tlow + 1) * 0x01010101u;
+        const bool packed_ok = tlow <= 127;
+        const uint32_t* T32 = reinterpret_cast<const uint32_t*>(tile);
+        // rolling window of 7 tile rows x 3 words; slot (j % 7) holds tile row (yy + j), j = 0..6 <=> dy = j-3
+        uint32_t a0[7], a1[7], a2[7];
+        if (yBeg < yEnd) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const uint32_t* rp = T32 + (yBeg + j) * (TP / 4) + wbase + lane - 1;
+                a0[j] = rp[0]; a1[j] = rp[1]; a2[j] = rp[2];
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int yy = yBeg + it;
+            if (yy < yEnd) {          // warp-uniform
+                {
+                    const uint32_t* rp = T32 + (yy + 6) * (TP / 4) + wbase + lane - 1;
+                    a0[(it + 6) % 7] = rp[0]; a1[(it + 6) % 7] = rp[1]; a2[(it + 6) % 7] = rp[2];
+                }
+#define ROW(dy) a0[(it + (dy) + 3) % 7], a1[(it + (dy) + 3) % 7], a2[(it + (dy) + 3) % 7]
+                uint32_t m;
+                if (packed_ok) {
+                    const uint32_t v = a1[(it + 3) % 7];
+                    // even ring positions: pairs (0,8) (2,10) (4,12) (6,14)
+                    uint32_t acc = gt_flag(win<0>(ROW(3)), v, T1) | gt_flag(win<0>(ROW(-3)), v, T1);
+                    acc &= gt_flag(win<2>(ROW(2)), v, T1) | gt_flag(win<-2>(ROW(-2)), v, T1);
+                    acc &= gt_flag(win<3>(ROW(0)), v, T1) | gt_flag(win<-3>(ROW(0)), v, T1);
+                    acc &= gt_flag(win<2>(ROW(-2)), v, T1) | gt_flag(win<-2>(ROW(2)), v, T1);
+                    m = acc & vmask;
+                    if (m) {
+                        // odd ring positions: pairs (1,9) (3,11) (5,13) (7,15)
+                        acc &= gt_flag(win<1>(ROW(3)), v, T1) | gt_flag(win<-1>(ROW(-3)), v, T1);
+                        acc &= gt_flag(win<3>(ROW(1)), v, T1) | gt_flag(win<-3>(ROW(-1)), v, T1);
+                        acc &= gt_flag(win<3>(ROW(-1)), v, T1) | gt_flag(win<-3>(ROW(1)), v, T1);
+                        acc &= gt_flag(win<1>(ROW(-3)), v, T1) | gt_flag(win<-1>(ROW(3)), v, T1);
+                        m = acc & vmask;
+                    }
+                } else {
+                    m = vmask;          // thresholds above 127: no packed reject, every pixel is scored exactly
+                }
+#undef ROW
+                const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
+                if (any) {
+                    const int c = __popc(m);
+                    int incl = c;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                        if (lane >= off) incl += t;
+                    }
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(&qn, incl);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - c;
+                    uint32_t mm = m;
+                    while (mm) {
+                        const int b = (__ffs(mm) - 1) >> 3;
+                        mm &= mm - 1;
+                        queue[base++] = (uint16_t)((yy << 7) | (xxb + b));
+                    }
+                }
+            }
         }
     }
     __syncthreads();
-    const int tlow = min(g.ini_th, g.min_th);
-    for (int yy = threadIdx.y; yy < th; yy += 8)
-        for (int xx = threadIdx.x; xx < tw; xx += 32)
-            score[yy * FAST_TILE_W + xx] = (uint8_t)fast_score(&tile[(yy + 3) * TILE_PITCH + xx + 3], tlow);
+    const int nq = qn;
+
+    // ---- 2. exact arc test + score for the survivors
+    for (int e = tid; e < nq; e += 256) {
+        const int q = queue[e];
+        const int xx = q & 127, yy = q >> 7;
+        const int s = fast_score(&tile[(yy + 3) * TP + xx + off], tlow);
+        if (s > 0) score[yy * SW + xx] = (uint8_t)s;
+        else queue[e] = 0xFFFF;
+    }
     __syncthreads();
-    // cell-local strict NMS; survivors overwrite the tile buffer (reused as "kept score" map)
-    uint8_t* kept = tile;
-    for (int yy = threadIdx.y; yy < th; yy += 8)
-        for (int xx = threadIdx.x; xx < tw; xx += 32) {
-            const int s = score[yy * FAST_TILE_W + xx];
-            int k = 0;
-            if (s > 0) {
-                const int c = xx / L.wCell;
-                const int cx0 = c * L.wCell, cx1 = min(cx0 + L.wCell, tw);
-                bool ismax = true;
+
+    // ---- 3. cell-local strict NMS for scored pixels; entry keeps its score in place (0xFFFF = dropped)
+    for (int e = tid; e < nq; e += 256) {
+        const int q = queue[e];
+        if (q == 0xFFFF) continue;
+        const int xx = q & 127, yy = q >> 7;
+        const int s = score[yy * SW + xx];
+        const int c = xx / L.wCell;
+        const int cx0 = c * L.wCell, cx1 = min(cx0 + L.wCell, tw);
+        bool ismax = true;
 #pragma unroll
-                for (int dy = -1; dy <= 1; dy++)
+        for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
-                    for (int dx = -1; dx <= 1; dx++) {
-                        if (dx == 0 && dy == 0) continue;
-                        const int qx = xx + dx, qy = yy + dy;
-                        if (qx < cx0 || qx >= cx1 || qy < 0 || qy >= th) continue;
-                        if (!(s > (int)score[qy * FAST_TILE_W + qx])) ismax = false;
-                    }
-                if (ismax) {
-                    k = s;
-                    if (s >= g.ini_th) cellHasIni[c] = 1;
-                }
+            for (int dx = -1; dx <= 1; dx++) {
+                if (dx == 0 && dy == 0) continue;
+                const int qx = xx + dx, qy = yy + dy;
+                if (qx < cx0 || qx >= cx1 || qy < 0 || qy >= th) continue;
+                if (!(s > (int)score[qy * SW + qx])) ismax = false;
             }
-            kept[yy * FAST_TILE_W + xx] = (uint8_t)k;
-        }
+        if (ismax) {
+            if (s >= g.ini_th) cellHasIni[c] = 1;
+        } else
+            queue[e] = 0xFFFF;
+    }
     __syncthreads();
-    // emit (warp-aggregated append)
+
+    // ---- 4. per-cell threshold + emit (warp-aggregated append)
     uint32_t* out = cand + (size_t)img * g.cand_image_stride + L.cand_off;
     int* cnt = cand_cnt + img * g.nlevels + l;
-    for (int yy = threadIdx.y; yy < th; yy += 8)
-        for (int xb = 0; xb < tw; xb += 32) {
-            const int xx = xb + threadIdx.x;
-            int s = 0;
-            if (xx < tw) {
-                s = kept[yy * FAST_TILE_W + xx];
-                if (s > 0) {
-                    const int t = cellHasIni[xx / L.wCell] ? g.ini_th : g.min_th;
-                    if (s < t) s = 0;
-                }
-            }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, s > 0);
-            if (m) {
-                int base = 0;
-                if (threadIdx.x == 0) base = atomicAdd(cnt, __popc(m));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (s > 0) {
-                    const int pos = base + __popc(m & ((1u << threadIdx.x) - 1));
-                    if (pos < L.cand_cap) out[pos] = pack_xys(x0 + xx, y0 + yy, s);
-                }
+    for (int eb = 0; eb < nq; eb += 256) {
+        const int e = eb + tid;
+        int s = 0, xx = 0, yy = 0;
+        if (e < nq) {
+            const int q = queue[e];
+            if (q != 0xFFFF) {
+                xx = q & 127; yy = q >> 7;
+                s = score[yy * SW + xx];
+                const int t = cellHasIni[xx / L.wCell] ? g.ini_th : g.min_th;
+                if (s < t) s = 0;
             }
         }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, s > 0);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cnt, __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (s > 0) {
+                const int pos = base + __popc(m & ((1u << lane) - 1));
+                if (pos < L.cand_cap) out[pos] = pack_xys(x0 + xx, y0 + yy, s);
+            }
+        }
+    }
 }
 
+// ---- host: tensor maps (one per level: 3-D {x, y, image} view of the pyramid buffer)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+borb_status build_fast_tmaps(const Geometry& g, const Workspace& ws, void* out_tmaps) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+            return BORB_ERR_CUDA;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    TMaps* tm = reinterpret_cast<TMaps*>(out_tmaps);
+    std::memset(tm, 0, sizeof(TMaps));
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)ws.max_images};
+        cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyr_image_stride};
+        cuuint32_t box[3] = {(cuuint32_t)TP, (cuuint32_t)(L.hCell + 6), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tm->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ws.pyr + L.pyr_off, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+            return BORB_ERR_CUDA;
+        }
+    }
+    return BORB_OK;
+}
+
+size_t fast_tmaps_bytes() { return sizeof(TMaps); }
+
 int launch_fast(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s) {
-    dim3 block(32, 8), grid(g.fast_blocks, n_images);
-    fast_kernel<<<grid, block, 0, s>>>(g, ws.pyr, ws.cand, ws.cand_cnt);
+    dim3 grid(g.fast_blocks, n_images);
+    fast_kernel<<<grid, 256, 0, s>>>(g, *reinterpret_cast<const TMaps*>(ws.fast_tmaps), ws.cand, ws.cand_cnt);
     return 1;
 }
 
