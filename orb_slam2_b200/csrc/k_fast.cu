@@ -46,23 +46,20 @@ constexpr int QCAP = 60 * 128;          // queue capacity >= every pixel of the 
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// S(p) if p is a FAST-9 corner at threshold t, else 0.  c points at p inside the smem tile.
-__device__ __forceinline__ int fast_score(const uint8_t* c, int t) {
+// Scalar 9-arc test (only used for thresholds > 127, outside the packed path): 0 none, 1 bright arc, 2 dark arc.
+__device__ __forceinline__ int scalar_arc(const uint8_t* c, int t) {
     constexpr int P = TP;
+    const int offs[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1,
+                          -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
     const int v = c[0];
-    int r[16];
-    r[0] = c[3 * P];       r[1] = c[3 * P + 1];   r[2] = c[2 * P + 2];   r[3] = c[P + 3];
-    r[4] = c[3];           r[5] = c[-P + 3];      r[6] = c[-2 * P + 2];  r[7] = c[-3 * P + 1];
-    r[8] = c[-3 * P];      r[9] = c[-3 * P - 1];  r[10] = c[-2 * P - 2]; r[11] = c[-P - 3];
-    r[12] = c[-3];         r[13] = c[P - 3];      r[14] = c[2 * P - 2];  r[15] = c[3 * P - 1];
-    const int hi = v + t, lo = v - t;
     unsigned B = 0, D = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        B |= (r[k] > hi ? 1u : 0u) << k;
-        D |= (r[k] < lo ? 1u : 0u) << k;
+        const int r = c[offs[k]];
+        B |= (r > v + t ? 1u : 0u) << k;
+        D |= (r < v - t ? 1u : 0u) << k;
     }
-    auto arc9 = [](unsigned m) -> bool {      // 9 contiguous set bits in the circular 16-bit mask
+    auto arc9 = [](unsigned m) -> bool {
         unsigned x = m | (m << 16);
         unsigned a = x & (x >> 1);
         a &= a >> 2;
@@ -70,23 +67,32 @@ __device__ __forceinline__ int fast_score(const uint8_t* c, int t) {
         a &= x >> 8;
         return (a & 0xFFFFu) != 0;
     };
-    const bool cb = arc9(B), cd = arc9(D);
-    if (!cb && !cd) return 0;
-    // score: max over arcs of the min signed difference, for the polarity that fired (both cannot:
-    // 9+9 > 16).  Sliding 9-window minimum on the circular sequence by doubling.
+    return arc9(B) ? 1 : (arc9(D) ? 2 : 0);
+}
+
+// S(p) for a pixel already known to be a FAST-9 corner with the given polarity (dark: ring < centre).
+// = max over the 16 nine-pixel arcs of the min signed difference, minus 1 (cornerScore<16>); the other
+// polarity cannot have a 9-arc (9+9 > 16).  Sliding 9-window minimum as min3 of min3 on the circular ring.
+__device__ __forceinline__ int corner_score(const uint8_t* c, bool dark) {
+    constexpr int P = TP;
+    const int v = c[0];
     int d[16];
+    d[0] = c[3 * P];       d[1] = c[3 * P + 1];   d[2] = c[2 * P + 2];   d[3] = c[P + 3];
+    d[4] = c[3];           d[5] = c[-P + 3];      d[6] = c[-2 * P + 2];  d[7] = c[-3 * P + 1];
+    d[8] = c[-3 * P];      d[9] = c[-3 * P - 1];  d[10] = c[-2 * P - 2]; d[11] = c[-P - 3];
+    d[12] = c[-3];         d[13] = c[P - 3];      d[14] = c[2 * P - 2];  d[15] = c[3 * P - 1];
 #pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = cd ? (v - r[k]) : (r[k] - v);
-    int m2[16], m4[16], m8[16];
+    for (int k = 0; k < 16; k++) d[k] = dark ? (v - d[k]) : (d[k] - v);
+    int m3[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) m2[k] = min(d[k], d[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) m4[k] = min(m2[k], m2[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; k++) m8[k] = min(m4[k], m4[(k + 4) & 15]);
+    for (int k = 0; k < 16; k++) m3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
     int best = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) best = max(best, min(m8[k], d[(k + 8) & 15]));
+    for (int k = 0; k < 16; k += 2) {
+        const int a = min(min(m3[k], m3[(k + 3) & 15]), m3[(k + 6) & 15]);
+        const int b = min(min(m3[k + 1], m3[(k + 4) & 15]), m3[(k + 7) & 15]);
+        best = max(max(best, a), b);
+    }
     return best - 1;
 }
 
@@ -105,6 +111,13 @@ __device__ __forceinline__ uint32_t gt_flag(uint32_t q, uint32_t v, uint32_t T1)
     return ((a | 0x80808080u) - T1) | a;
 }
 
+constexpr uint32_t M7 = 0x7f7f7f7fu;
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t nb, uint32_t c) { return (a & nb) | (a & c) | (nb & c); }
+// bit 7 of each byte: q > hi (unsigned bytes);  nhi7 = ~hi & M7 precomputed
+__device__ __forceinline__ uint32_t gtu7(uint32_t q, uint32_t hi, uint32_t nhi7) { return maj3(q, ~hi, (q & M7) + nhi7); }
+// bit 7 of each byte: lo > q;  lo7 = lo & M7 precomputed
+__device__ __forceinline__ uint32_t ltu7(uint32_t q, uint32_t lo, uint32_t lo7) { return maj3(lo, ~q, lo7 + (~q & M7)); }
+
 }  // namespace
 
 struct TMaps { CUtensorMap m[BORB_MAX_LEVELS]; };
@@ -117,6 +130,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int qn;
     __shared__ int cellHasIni[128 / 30 + 1];
+    __shared__ uint8_t cellOf[128];
 
     const int img = blockIdx.y;
     int l = 0;
@@ -152,6 +166,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     // overlap with the copy: clear the score map and the bookkeeping
     for (int i = tid; i < (th * SW) / 16; i += 256) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
     if (tid < 128 / 30 + 1) cellHasIni[tid] = 0;
+    if (tid < 128) cellOf[tid] = (uint8_t)(tid / L.wCell);
     if (tid == 0) qn = 0;
     asm volatile(
         "{\n"
@@ -166,6 +181,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     __syncthreads();
 
     const int tlow = min(g.ini_th, g.min_th);
+    const bool packed_ok = tlow <= 127;
 
     // ---- 1. packed quick reject -> queue of survivors
     {
@@ -179,7 +195,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
         for (int b = 0; b < 4; b++)
             if (xxb + b >= 0 && xxb + b < tw) vmask |= 0x80u << (8 * b);
         const uint32_t T1 = (uint32_t)(tlow + 1) * 0x01010101u;
-        const bool packed_ok = tlow <= 127;
+        const uint32_t Tt = (uint32_t)tlow * 0x01010101u;
         const uint32_t* T32 = reinterpret_cast<const uint32_t*>(tile);
         // rolling window of 7 tile rows x 3 words; slot (j % 7) holds tile row (yy + j), j = 0..6 <=> dy = j-3
         uint32_t a0[7], a1[7], a2[7];
@@ -199,25 +215,52 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
                     a0[(it + 6) % 7] = rp[0]; a1[(it + 6) % 7] = rp[1]; a2[(it + 6) % 7] = rp[2];
                 }
 #define ROW(dy) a0[(it + (dy) + 3) % 7], a1[(it + (dy) + 3) % 7], a2[(it + (dy) + 3) % 7]
-                uint32_t m;
+                uint32_t m = 0, mdark = 0;      // m: corner flags (bit 7 per pixel); mdark: which of them are dark-arc corners
                 if (packed_ok) {
                     const uint32_t v = a1[(it + 3) % 7];
-                    // even ring positions: pairs (0,8) (2,10) (4,12) (6,14)
+                    // (a) cheap reject on |diff| of the even ring positions: pairs (0,8) (2,10) (4,12) (6,14)
                     uint32_t acc = gt_flag(win<0>(ROW(3)), v, T1) | gt_flag(win<0>(ROW(-3)), v, T1);
                     acc &= gt_flag(win<2>(ROW(2)), v, T1) | gt_flag(win<-2>(ROW(-2)), v, T1);
                     acc &= gt_flag(win<3>(ROW(0)), v, T1) | gt_flag(win<-3>(ROW(0)), v, T1);
                     acc &= gt_flag(win<2>(ROW(-2)), v, T1) | gt_flag(win<-2>(ROW(2)), v, T1);
-                    m = acc & vmask;
-                    if (m) {
-                        // odd ring positions: pairs (1,9) (3,11) (5,13) (7,15)
-                        acc &= gt_flag(win<1>(ROW(3)), v, T1) | gt_flag(win<-1>(ROW(-3)), v, T1);
-                        acc &= gt_flag(win<3>(ROW(1)), v, T1) | gt_flag(win<-3>(ROW(-1)), v, T1);
-                        acc &= gt_flag(win<3>(ROW(-1)), v, T1) | gt_flag(win<-3>(ROW(1)), v, T1);
-                        acc &= gt_flag(win<1>(ROW(-3)), v, T1) | gt_flag(win<-1>(ROW(3)), v, T1);
-                        m = acc & vmask;
+                    if (acc & vmask) {
+                        // (b) exact, sign-aware: per polarity the 16 per-position flags, then 9 contiguous by
+                        // AND-doubling on the packed flag words (bit 7 of each byte = that pixel's flag)
+                        const uint32_t hi = __vaddus4(v, Tt), lo = __vsubus4(v, Tt);
+#pragma unroll
+                        for (int pol = 0; pol < 2; pol++) {
+                            uint32_t f[16];
+                            const uint32_t k7 = pol ? (lo & M7) : (~hi & M7);
+#define FLAG(q) (pol ? ltu7((q), lo, k7) : gtu7((q), hi, k7))
+                            f[0] = FLAG(win<0>(ROW(3)));   f[8] = FLAG(win<0>(ROW(-3)));
+                            f[2] = FLAG(win<2>(ROW(2)));   f[10] = FLAG(win<-2>(ROW(-2)));
+                            f[4] = FLAG(win<3>(ROW(0)));   f[12] = FLAG(win<-3>(ROW(0)));
+                            f[6] = FLAG(win<2>(ROW(-2)));  f[14] = FLAG(win<-2>(ROW(2)));
+                            uint32_t ap = (f[0] | f[8]) & (f[2] | f[10]) & (f[4] | f[12]) & (f[6] | f[14]);
+                            if (ap & vmask) {
+                                f[1] = FLAG(win<1>(ROW(3)));   f[9] = FLAG(win<-1>(ROW(-3)));
+                                f[3] = FLAG(win<3>(ROW(1)));   f[11] = FLAG(win<-3>(ROW(-1)));
+                                f[5] = FLAG(win<3>(ROW(-1)));  f[13] = FLAG(win<-3>(ROW(1)));
+                                f[7] = FLAG(win<1>(ROW(-3)));  f[15] = FLAG(win<-1>(ROW(3)));
+                                ap &= (f[1] | f[9]) & (f[3] | f[11]) & (f[5] | f[13]) & (f[7] | f[15]);
+                                if (ap & vmask) {
+                                    uint32_t p3[16];
+#pragma unroll
+                                    for (int k = 0; k < 16; k++) p3[k] = f[k] & f[(k + 1) & 15] & f[(k + 2) & 15];
+                                    uint32_t any9 = 0;
+#pragma unroll
+                                    for (int k = 0; k < 16; k++) any9 |= p3[k] & p3[(k + 3) & 15] & p3[(k + 6) & 15];
+                                    any9 &= vmask;
+                                    m |= any9;
+                                    if (pol) mdark = any9;
+                                }
+                            }
+#undef FLAG
+                        }
                     }
                 } else {
-                    m = vmask;          // thresholds above 127: no packed reject, every pixel is scored exactly
+                    m = vmask;          // thresholds above 127 (never used by the reference configs): exact scalar test
+                    mdark = 0x01010101u;  // marker: polarity unknown -> phase 2 runs the scalar arc test
                 }
 #undef ROW
                 const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
@@ -236,7 +279,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
                     while (mm) {
                         const int b = (__ffs(mm) - 1) >> 3;
                         mm &= mm - 1;
-                        queue[base++] = (uint16_t)((yy << 7) | (xxb + b));
+                        queue[base++] = (uint16_t)((((mdark >> (8 * b + 7)) & 1u) << 15) | (yy << 7) | (xxb + b));
                     }
                 }
             }
@@ -245,25 +288,32 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     __syncthreads();
     const int nq = qn;
 
-    // ---- 2. exact arc test + score for the survivors
+    // ---- 2. score of every corner (polarity known from the packed test)
     for (int e = tid; e < nq; e += 256) {
         const int q = queue[e];
-        const int xx = q & 127, yy = q >> 7;
-        const int s = fast_score(&tile[(yy + 3) * TP + xx + off], tlow);
-        if (s > 0) score[yy * SW + xx] = (uint8_t)s;
+        const int xx = q & 127, yy = (q >> 7) & 63;
+        const uint8_t* c = &tile[(yy + 3) * TP + xx + off];
+        bool dark = (q >> 15) != 0;
+        bool corner = true;
+        if (!packed_ok) {               // thresholds > 127: scalar 9-arc test decides corner-ness and polarity
+            const int pol = scalar_arc(c, tlow);
+            corner = pol != 0;
+            dark = pol == 2;
+        }
+        if (corner) score[yy * SW + xx] = (uint8_t)corner_score(c, dark);
         else queue[e] = 0xFFFF;
     }
     __syncthreads();
 
-    // ---- 3. cell-local strict NMS for scored pixels; entry keeps its score in place (0xFFFF = dropped)
+    // ---- 3. cell-local strict NMS for the corners (0xFFFF = dropped)
     for (int e = tid; e < nq; e += 256) {
         const int q = queue[e];
         if (q == 0xFFFF) continue;
-        const int xx = q & 127, yy = q >> 7;
+        const int xx = q & 127, yy = (q >> 7) & 63;
         const int s = score[yy * SW + xx];
-        const int c = xx / L.wCell;
+        const int c = cellOf[xx];
         const int cx0 = c * L.wCell, cx1 = min(cx0 + L.wCell, tw);
-        bool ismax = true;
+        bool ismax = s > 0;
 #pragma unroll
         for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
@@ -289,9 +339,9 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
         if (e < nq) {
             const int q = queue[e];
             if (q != 0xFFFF) {
-                xx = q & 127; yy = q >> 7;
+                xx = q & 127; yy = (q >> 7) & 63;
                 s = score[yy * SW + xx];
-                const int t = cellHasIni[xx / L.wCell] ? g.ini_th : g.min_th;
+                const int t = cellHasIni[cellOf[xx]] ? g.ini_th : g.min_th;
                 if (s < t) s = 0;
             }
         }
