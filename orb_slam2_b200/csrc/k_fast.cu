@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     __shared__ __align__(16) uint8_t score[60 * SW];
     __shared__ uint16_t queue[QCAP];
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ int qn;
+    __shared__ uint16_t wqueue[60 * 32];    // words (row, lane) that survive the cheap reject
+    __shared__ int qn, wqn;
     __shared__ int cellHasIni[128 / 30 + 1];
     __shared__ uint8_t cellOf[128];
 
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     for (int i = tid; i < (th * SW) / 16; i += 256) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
     if (tid < 128 / 30 + 1) cellHasIni[tid] = 0;
     if (tid < 128) cellOf[tid] = (uint8_t)(tid / L.wCell);
-    if (tid == 0) qn = 0;
+    if (tid == 0) { qn = 0; wqn = 0; }
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -183,20 +184,20 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     const int tlow = min(g.ini_th, g.min_th);
     const bool packed_ok = tlow <= 127;
 
-    // ---- 1. packed quick reject -> queue of survivors
+    // ---- 1a. packed reject on |diff| of the even ring positions; surviving WORDS (4 px) go to a word queue so
+    //          that the exact test below runs with all lanes busy
+    const uint32_t* T32 = reinterpret_cast<const uint32_t*>(tile);
+    const int wbase = off >> 2;             // lane owns aligned tile word wbase+lane; byte b is domain px xx = 4*lane-(off&3)+b
+    const uint32_t T1 = (uint32_t)(tlow + 1) * 0x01010101u;
+    const uint32_t Tt = (uint32_t)tlow * 0x01010101u;
     {
         const int RG = (th + 7) >> 3;                 // rows per warp (8 warps)
         const int yBeg = wrp * RG, yEnd = min(th, yBeg + RG);
-        // lane owns aligned tile word wbase+lane; its byte b is domain pixel xx = xxb + b
-        const int wbase = off >> 2;
         const int xxb = 4 * lane - (off & 3);
         uint32_t vmask = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++)
             if (xxb + b >= 0 && xxb + b < tw) vmask |= 0x80u << (8 * b);
-        const uint32_t T1 = (uint32_t)(tlow + 1) * 0x01010101u;
-        const uint32_t Tt = (uint32_t)tlow * 0x01010101u;
-        const uint32_t* T32 = reinterpret_cast<const uint32_t*>(tile);
         // rolling window of 7 tile rows x 3 words; slot (j % 7) holds tile row (yy + j), j = 0..6 <=> dy = j-3
         uint32_t a0[7], a1[7], a2[7];
         if (yBeg < yEnd) {
@@ -215,72 +216,108 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
                     a0[(it + 6) % 7] = rp[0]; a1[(it + 6) % 7] = rp[1]; a2[(it + 6) % 7] = rp[2];
                 }
 #define ROW(dy) a0[(it + (dy) + 3) % 7], a1[(it + (dy) + 3) % 7], a2[(it + (dy) + 3) % 7]
-                uint32_t m = 0, mdark = 0;      // m: corner flags (bit 7 per pixel); mdark: which of them are dark-arc corners
+                bool keep = vmask != 0;
                 if (packed_ok) {
                     const uint32_t v = a1[(it + 3) % 7];
-                    // (a) cheap reject on |diff| of the even ring positions: pairs (0,8) (2,10) (4,12) (6,14)
-                    uint32_t acc = gt_flag(win<0>(ROW(3)), v, T1) | gt_flag(win<0>(ROW(-3)), v, T1);
-                    acc &= gt_flag(win<2>(ROW(2)), v, T1) | gt_flag(win<-2>(ROW(-2)), v, T1);
-                    acc &= gt_flag(win<3>(ROW(0)), v, T1) | gt_flag(win<-3>(ROW(0)), v, T1);
-                    acc &= gt_flag(win<2>(ROW(-2)), v, T1) | gt_flag(win<-2>(ROW(2)), v, T1);
-                    if (acc & vmask) {
-                        // (b) exact, sign-aware: per polarity the 16 per-position flags, then 9 contiguous by
-                        // AND-doubling on the packed flag words (bit 7 of each byte = that pixel's flag)
-                        const uint32_t hi = __vaddus4(v, Tt), lo = __vsubus4(v, Tt);
-#pragma unroll
-                        for (int pol = 0; pol < 2; pol++) {
-                            uint32_t f[16];
-                            const uint32_t k7 = pol ? (lo & M7) : (~hi & M7);
-#define FLAG(q) (pol ? ltu7((q), lo, k7) : gtu7((q), hi, k7))
-                            f[0] = FLAG(win<0>(ROW(3)));   f[8] = FLAG(win<0>(ROW(-3)));
-                            f[2] = FLAG(win<2>(ROW(2)));   f[10] = FLAG(win<-2>(ROW(-2)));
-                            f[4] = FLAG(win<3>(ROW(0)));   f[12] = FLAG(win<-3>(ROW(0)));
-                            f[6] = FLAG(win<2>(ROW(-2)));  f[14] = FLAG(win<-2>(ROW(2)));
-                            uint32_t ap = (f[0] | f[8]) & (f[2] | f[10]) & (f[4] | f[12]) & (f[6] | f[14]);
-                            if (ap & vmask) {
-                                f[1] = FLAG(win<1>(ROW(3)));   f[9] = FLAG(win<-1>(ROW(-3)));
-                                f[3] = FLAG(win<3>(ROW(1)));   f[11] = FLAG(win<-3>(ROW(-1)));
-                                f[5] = FLAG(win<3>(ROW(-1)));  f[13] = FLAG(win<-3>(ROW(1)));
-                                f[7] = FLAG(win<1>(ROW(-3)));  f[15] = FLAG(win<-1>(ROW(3)));
-                                ap &= (f[1] | f[9]) & (f[3] | f[11]) & (f[5] | f[13]) & (f[7] | f[15]);
-                                if (ap & vmask) {
-                                    uint32_t p3[16];
-#pragma unroll
-                                    for (int k = 0; k < 16; k++) p3[k] = f[k] & f[(k + 1) & 15] & f[(k + 2) & 15];
-                                    uint32_t any9 = 0;
-#pragma unroll
-                                    for (int k = 0; k < 16; k++) any9 |= p3[k] & p3[(k + 3) & 15] & p3[(k + 6) & 15];
-                                    any9 &= vmask;
-                                    m |= any9;
-                                    if (pol) mdark = any9;
-                                }
-                            }
-#undef FLAG
-                        }
-                    }
-                } else {
-                    m = vmask;          // thresholds above 127 (never used by the reference configs): exact scalar test
-                    mdark = 0x01010101u;  // marker: polarity unknown -> phase 2 runs the scalar arc test
+                    uint32_t acc = gt_flag(win<0>(ROW(3)), v, T1) | gt_flag(win<0>(ROW(-3)), v, T1);      // pair (0,8)
+                    acc &= gt_flag(win<2>(ROW(2)), v, T1) | gt_flag(win<-2>(ROW(-2)), v, T1);               // (2,10)
+                    acc &= gt_flag(win<3>(ROW(0)), v, T1) | gt_flag(win<-3>(ROW(0)), v, T1);                // (4,12)
+                    acc &= gt_flag(win<2>(ROW(-2)), v, T1) | gt_flag(win<-2>(ROW(2)), v, T1);               // (6,14)
+                    keep = (acc & vmask) != 0;
                 }
 #undef ROW
-                const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
-                if (any) {
-                    const int c = __popc(m);
-                    int incl = c;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-                        if (lane >= off) incl += t;
-                    }
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                if (bal) {
                     int base = 0;
-                    if (lane == 31) base = atomicAdd(&qn, incl);
-                    base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - c;
-                    uint32_t mm = m;
-                    while (mm) {
-                        const int b = (__ffs(mm) - 1) >> 3;
-                        mm &= mm - 1;
-                        queue[base++] = (uint16_t)((((mdark >> (8 * b + 7)) & 1u) << 15) | (yy << 7) | (xxb + b));
+                    if (lane == 0) base = atomicAdd(&wqn, __popc(bal));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (keep) wqueue[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((yy << 5) | lane);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 1b. exact, sign-aware 9-arc test on the queued words: per polarity the 16 per-position flags (bit 7 of
+    //          each byte = that pixel's flag), antipodal early-outs, then "9 contiguous" as AND of three 3-runs
+    {
+        const int nw = wqn;
+        for (int eb = 0; eb < nw; eb += 256) {
+            const int e = eb + tid;
+            uint32_t m = 0, mdark = 0;
+            int yy = 0, xxb = 0;
+            if (e < nw) {
+                const int we = wqueue[e];
+                yy = we >> 5;
+                const int ln = we & 31;
+                xxb = 4 * ln - (off & 3);
+                uint32_t vmask = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (xxb + b >= 0 && xxb + b < tw) vmask |= 0x80u << (8 * b);
+                if (packed_ok) {
+                    uint32_t a0[7], a1[7], a2[7];
+#pragma unroll
+                    for (int j = 0; j < 7; j++) {
+                        const uint32_t* rp = T32 + (yy + j) * (TP / 4) + wbase + ln - 1;
+                        a0[j] = rp[0]; a1[j] = rp[1]; a2[j] = rp[2];
                     }
+#define ROW(dy) a0[(dy) + 3], a1[(dy) + 3], a2[(dy) + 3]
+                    const uint32_t v = a1[3];
+                    const uint32_t hi = __vaddus4(v, Tt), lo = __vsubus4(v, Tt);
+#pragma unroll
+                    for (int pol = 0; pol < 2; pol++) {
+                        uint32_t f[16];
+                        const uint32_t k7 = pol ? (lo & M7) : (~hi & M7);
+#define FLAG(q) (pol ? ltu7((q), lo, k7) : gtu7((q), hi, k7))
+                        f[0] = FLAG(win<0>(ROW(3)));   f[8] = FLAG(win<0>(ROW(-3)));
+                        f[2] = FLAG(win<2>(ROW(2)));   f[10] = FLAG(win<-2>(ROW(-2)));
+                        f[4] = FLAG(win<3>(ROW(0)));   f[12] = FLAG(win<-3>(ROW(0)));
+                        f[6] = FLAG(win<2>(ROW(-2)));  f[14] = FLAG(win<-2>(ROW(2)));
+                        uint32_t ap = (f[0] | f[8]) & (f[2] | f[10]) & (f[4] | f[12]) & (f[6] | f[14]);
+                        if (ap & vmask) {
+                            f[1] = FLAG(win<1>(ROW(3)));   f[9] = FLAG(win<-1>(ROW(-3)));
+                            f[3] = FLAG(win<3>(ROW(1)));   f[11] = FLAG(win<-3>(ROW(-1)));
+                            f[5] = FLAG(win<3>(ROW(-1)));  f[13] = FLAG(win<-3>(ROW(1)));
+                            f[7] = FLAG(win<1>(ROW(-3)));  f[15] = FLAG(win<-1>(ROW(3)));
+                            ap &= (f[1] | f[9]) & (f[3] | f[11]) & (f[5] | f[13]) & (f[7] | f[15]);
+                            if (ap & vmask) {
+                                uint32_t p3[16];
+#pragma unroll
+                                for (int k = 0; k < 16; k++) p3[k] = f[k] & f[(k + 1) & 15] & f[(k + 2) & 15];
+                                uint32_t any9 = 0;
+#pragma unroll
+                                for (int k = 0; k < 16; k++) any9 |= p3[k] & p3[(k + 3) & 15] & p3[(k + 6) & 15];
+                                any9 &= vmask;
+                                m |= any9;
+                                if (pol) mdark = any9;
+                            }
+                        }
+#undef FLAG
+                    }
+#undef ROW
+                } else {
+                    m = vmask;          // thresholds above 127 (never used by the reference configs): scalar test in phase 2
+                }
+            }
+            // append this word's corner pixels to the corner queue (warp-aggregated)
+            const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
+            if (any) {
+                const int c = __popc(m);
+                int incl = c;
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o2);
+                    if (lane >= o2) incl += t;
+                }
+                int base = 0;
+                if (lane == 31) base = atomicAdd(&qn, incl);
+                base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - c;
+                uint32_t mm = m;
+                while (mm) {
+                    const int b = (__ffs(mm) - 1) >> 3;
+                    mm &= mm - 1;
+                    queue[base++] = (uint16_t)((((mdark >> (8 * b + 7)) & 1u) << 15) | (yy << 7) | (xxb + b));
                 }
             }
         }

@@ -1,7 +1,7 @@
 """Deterministic synthetic camera frames (no datasets are available offline).
 
 SURVEY.md §8(d): left image = smooth low-frequency background (uniform noise in [70,150] at 1/6
-resolution, smoothly upsampled) + 300 random axis-aligned rectangles (6-40 x 6-30 px, additive
+resolution, bicubic-upsampled) + 300 random axis-aligned rectangles (6-40 x 6-30 px, additive
 contrast in [-90,90]) + Gaussian sensor noise (sigma 2); right image = the noise-free left image
 resampled with a smooth disparity field d(x,y) in [2,80] px plus independent sensor noise, so
 that Frame::ComputeStereoMatches (reference src/Frame.cc:466) finds matches for most keypoints.
@@ -34,13 +34,36 @@ def _bilinear(img: np.ndarray, xs: np.ndarray, ys: np.ndarray) -> np.ndarray:
     return a * (1 - fy) + b * fy
 
 
+def _cubic_w(t: np.ndarray, a: float = -0.75) -> np.ndarray:
+    t = np.abs(t)
+    return np.where(t <= 1, (a + 2) * t ** 3 - (a + 3) * t ** 2 + 1, np.where(t < 2, a * t ** 3 - 5 * a * t ** 2 + 8 * a * t - 4 * a, 0.0))
+
+
+def _bicubic_upsample(low: np.ndarray, h: int, w: int, factor: float = 6.0) -> np.ndarray:
+    """Separable 4-tap bicubic (a=-0.75, the OpenCV INTER_CUBIC kernel) upsampling of a coarse grid (SURVEY §8d:
+    "uniform noise in [70,150] at 1/6 resolution, bicubic-upsampled")."""
+    lh, lw = low.shape
+
+    def taps(n, ln):
+        x = np.arange(n, dtype=np.float64) / factor
+        x0 = np.floor(x).astype(np.int64)
+        idx = [np.clip(x0 + k, 0, ln - 1) for k in (-1, 0, 1, 2)]
+        wt = [_cubic_w(x - (x0 + k)).astype(np.float32) for k in (-1, 0, 1, 2)]
+        return idx, wt
+
+    iy, wy = taps(h, lh)
+    ix, wx = taps(w, lw)
+    low = low.astype(np.float32)
+    tmp = sum(low[iy[k], :] * wy[k][:, None] for k in range(4))          # h x lw
+    return sum(tmp[:, ix[k]] * wx[k][None, :] for k in range(4)).astype(np.float32)
+
+
 def clean_left(seed: int, stream_id: int, frame_idx: int, w: int, h: int, n_rect: int = 300) -> np.ndarray:
     """Noise-free left image as float32 (HxW)."""
     rng = _rng(seed, stream_id, frame_idx)
     lw, lh = w // 6 + 3, h // 6 + 3
     low = rng.uniform(70.0, 150.0, (lh, lw)).astype(np.float32)
-    ys, xs = np.meshgrid(np.arange(h, dtype=np.float32) / 6.0, np.arange(w, dtype=np.float32) / 6.0, indexing="ij")
-    img = _bilinear(low.astype(np.float32), xs, ys)
+    img = _bicubic_upsample(low, h, w)
     for _ in range(n_rect):
         rw = int(rng.integers(6, 41))
         rh = int(rng.integers(6, 31))
