@@ -121,7 +121,7 @@ borb_status build_geometry(borb_extractor* e, int w, int h, std::vector<int16_t>
         v.inv_scale = e->inv_scale[l];
         v.patch_size = (float)(int)(PATCH * e->scale[l]);
         g.blur_base[l] = btile;
-        btile += ((v.w + 63) / 64) * ((v.h + 31) / 32);
+        btile += ((v.w + 127) / 128) * ((v.h + 63) / 64);   // blur_kernel: 128 x 64 strips
         if (l > 0) {
             v.xtab_off = (unsigned)(tabs.size() / 3);
             resize_table(g.lv[l - 1].w, v.w, true, tabs);
@@ -146,7 +146,7 @@ borb_status build_geometry(borb_extractor* e, int w, int h, std::vector<int16_t>
 void free_workspace(Workspace& ws) {
     cudaFree(ws.pyr); cudaFree(ws.blur); cudaFree(ws.cand); cudaFree(ws.cand_cnt); cudaFree(ws.pnode); cudaFree(ws.sel);
     cudaFree(ws.sel_cnt); cudaFree(ws.kps); cudaFree(ws.desc); cudaFree(ws.nkp); cudaFree(ws.u_right); cudaFree(ws.depth);
-    cudaFree(ws.sad); cudaFree(ws.tabs); cudaFree(ws.pair_idx);
+    cudaFree(ws.sad); cudaFree(ws.tabs); cudaFree(ws.pair_idx); cudaFree(ws.st_bins); cudaFree(ws.st_recs); cudaFree(ws.stage);
     free(ws.fast_tmaps);
     ws = Workspace();
 }
@@ -183,6 +183,8 @@ borb_status ensure(borb_extractor* e, int w, int h, int n_images) {
     BORB_CUDA(cudaMalloc(&ws.depth, n * g.sel_image_stride * sizeof(float)));
     BORB_CUDA(cudaMalloc(&ws.sad, n * g.sel_image_stride * sizeof(int)));
     BORB_CUDA(cudaMalloc(&ws.pair_idx, n * 2 * sizeof(int)));
+    BORB_CUDA(cudaMalloc(&ws.st_bins, n * stereo_bins_bytes_per_pair()));
+    BORB_CUDA(cudaMalloc(&ws.st_recs, n * (size_t)stereo_rec_stride(g) * stereo_rec_bytes()));
     BORB_CUDA(cudaMalloc(&ws.tabs, (tabs.size() + 4) * sizeof(int16_t)));
     BORB_CUDA(cudaMemcpy(ws.tabs, tabs.data(), tabs.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
     BORB_CUDA(cudaMemset(ws.nkp, 0, n * sizeof(int)));
@@ -258,12 +260,33 @@ borb_status enqueue_extract(borb_extractor* e, int n) {
     return BORB_OK;
 }
 
-borb_status upload_host(borb_extractor* e, const uint8_t* const* gray, int first, int count, int step, int w, int h, int stride) {
+// Host images -> level 0.  slots[k] is the host pointer of batch image k (k = 0..n-1).  When the n images form
+// one contiguous block in slot order (camera frames in one pinned buffer) they travel as ONE 1-D copy into a
+// packed landing buffer and a kernel re-pitches them; otherwise one 2-D copy per image.
+borb_status upload_slots(borb_extractor* e, const uint8_t* const* slots, int n, int w, int h, int stride) {
     const Geometry& g = e->geom;
-    for (int i = 0; i < count; i++) {
-        if (!gray[i]) { set_error("image %d is NULL", i); return BORB_ERR_INVALID_ARG; }
-        uint8_t* dst = e->ws.pyr + (size_t)(first + i * step) * g.pyr_image_stride + g.lv[0].pyr_off;
-        BORB_CUDA(cudaMemcpy2DAsync(dst, g.lv[0].pitch, gray[i], stride, w, h, cudaMemcpyHostToDevice, e->stream));
+    const size_t img_bytes = (size_t)stride * h;
+    bool contiguous = n > 1;
+    for (int k = 0; k < n; k++) {
+        if (!slots[k]) { set_error("image %d is NULL", k); return BORB_ERR_INVALID_ARG; }
+        if (slots[k] != slots[0] + (size_t)k * img_bytes) contiguous = false;
+    }
+    if (contiguous) {
+        const size_t need = img_bytes * n;
+        if (e->ws.stage_bytes < need) {
+            BORB_CUDA(cudaStreamSynchronize(e->stream));
+            cudaFree(e->ws.stage);
+            e->ws.stage = nullptr; e->ws.stage_bytes = 0;
+            BORB_CUDA(cudaMalloc(&e->ws.stage, need));
+            e->ws.stage_bytes = need;
+        }
+        BORB_CUDA(cudaMemcpyAsync(e->ws.stage, slots[0], need, cudaMemcpyHostToDevice, e->stream));
+        e->launches += launch_repack(g, e->ws, e->ws.stage, stride, img_bytes, n, e->stream);
+        return BORB_OK;
+    }
+    for (int k = 0; k < n; k++) {
+        uint8_t* dst = e->ws.pyr + (size_t)k * g.pyr_image_stride + g.lv[0].pyr_off;
+        BORB_CUDA(cudaMemcpy2DAsync(dst, g.lv[0].pitch, slots[k], stride, w, h, cudaMemcpyHostToDevice, e->stream));
     }
     return BORB_OK;
 }
@@ -335,7 +358,7 @@ borb_status enqueue_stereo(borb_extractor* eL, borb_extractor* eR, int n_pairs, 
     StereoView L{eL->ws.pyr, eL->ws.kps, eL->ws.desc, eL->ws.nkp, eL->geom.pyr_image_stride, eL->geom.sel_image_stride};
     StereoView R{eR->ws.pyr, eR->ws.kps, eR->ws.desc, eR->ws.nkp, eR->geom.pyr_image_stride, eR->geom.sel_image_stride};
     mark(e, 6);
-    e->launches += launch_stereo(g, L, R, e->ws.pair_idx, n_pairs, bf, b, e->ws.u_right, e->ws.depth, e->ws.sad, g.sel_image_stride, e->stream);
+    e->launches += launch_stereo(g, L, R, e->ws.pair_idx, n_pairs, bf, b, e->ws.u_right, e->ws.depth, e->ws.sad, g.sel_image_stride, e->ws.st_bins, e->ws.st_recs, e->stream);
     mark(e, 7);
     BORB_CUDA(cudaGetLastError());
     return BORB_OK;
@@ -482,7 +505,7 @@ borb_status borb_extract_batch_enqueue(borb_extractor* e, const uint8_t* const* 
     if ((st = ensure(e, w, h, n)) != BORB_OK) return st;
     begin_step(e);
     mark(e, 0);
-    if ((st = upload_host(e, gray, 0, n, 1, w, h, stride)) != BORB_OK) return st;
+    if ((st = upload_slots(e, gray, n, w, h, stride)) != BORB_OK) return st;
     if ((st = enqueue_extract(e, n)) != BORB_OK) return st;
     mark(e, 7);
     st = download_kps(e, 0, n, 1, kps, desc, cap, n_out);
@@ -662,8 +685,11 @@ borb_status borb_stereo_frames_enqueue(borb_extractor* e, const uint8_t* const* 
     if ((st = ensure(e, w, h, 2 * n_pairs)) != BORB_OK) return st;
     begin_step(e);
     mark(e, 0);
-    if ((st = upload_host(e, left, 0, n_pairs, 2, w, h, stride)) != BORB_OK) return st;
-    if ((st = upload_host(e, right, 1, n_pairs, 2, w, h, stride)) != BORB_OK) return st;
+    {
+        std::vector<const uint8_t*> slots(2 * (size_t)n_pairs);
+        for (int p = 0; p < n_pairs; p++) { slots[2 * p] = left[p]; slots[2 * p + 1] = right[p]; }
+        if ((st = upload_slots(e, slots.data(), 2 * n_pairs, w, h, stride)) != BORB_OK) return st;
+    }
     if ((st = enqueue_extract(e, 2 * n_pairs)) != BORB_OK) return st;
     if ((st = enqueue_stereo(e, e, n_pairs, nullptr, nullptr, bf, b)) != BORB_OK) return st;
     if ((st = download_kps(e, 0, n_pairs, 2, kps_left, desc_left, cap, n_left)) != BORB_OK) return st;

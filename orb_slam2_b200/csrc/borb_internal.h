@@ -79,6 +79,10 @@ struct Workspace {
     int* sad = nullptr;            // SAD distance per left keypoint (-1: none)
     int16_t* tabs = nullptr;       // resize tables
     int* pair_idx = nullptr;       // 2 * max_pairs (left,right image indices)
+    int* st_bins = nullptr;        // stereo row-bin offsets, per pair
+    void* st_recs = nullptr;       // stereo binned right-keypoint records, per pair
+    uint8_t* stage = nullptr;      // tightly packed H2D landing buffer (grow-only)
+    size_t stage_bytes = 0;
     void* fast_tmaps = nullptr;    // HOST: per-level CUtensorMap set for fast_kernel (passed by value at launch)
 };
 
@@ -93,6 +97,8 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 // ---- kernel launchers (each returns the number of kernel launches it issued) -----------------
+int launch_repack(const Geometry& g, const Workspace& ws, const uint8_t* stage, int src_stride, size_t src_image_bytes,
+                  int n_images, cudaStream_t s);
 int launch_pyramid(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s);
 int launch_fast(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s);
 int launch_quadtree(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s);
@@ -108,7 +114,11 @@ struct StereoView {          // device pointers of one side of a stereo pair set
     int kp_image_stride;
 };
 int launch_stereo(const Geometry& g, const StereoView& L, const StereoView& R, const int* d_pair_idx, int n_pairs,
-                  float bf, float b, float* d_u_right, float* d_depth, int* d_sad, int out_stride, cudaStream_t s);
+                  float bf, float b, float* d_u_right, float* d_depth, int* d_sad, int out_stride, int* d_bins, void* d_recs,
+                  cudaStream_t s);
+int stereo_rec_stride(const Geometry& g);
+size_t stereo_bins_bytes_per_pair();
+size_t stereo_rec_bytes();
 size_t quadtree_smem_bytes(int node_cap);
 borb_status build_fast_tmaps(const Geometry& g, const Workspace& ws, void* out_tmaps);
 size_t fast_tmaps_bytes();

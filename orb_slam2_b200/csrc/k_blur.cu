@@ -4,7 +4,11 @@
 // src/ORBextractor.cc:1085-1086 with OpenCV >= 3.4 fixed-point semantics (pinned against cv2 4.13 in
 // tests/test_oracle_prims.py): separable kernel q = [18 34 48 56 48 34 18]/256; row pass exact u16,
 // column pass (sum + 2^15) >> 16; reflect-101 of the LEVEL itself at its borders.
-// One launch covers all levels of all images; a CTA produces a 64x32 tile through shared memory.
+//
+// v2: no shared memory.  A warp owns a 128-px wide strip (one aligned 32-bit word = 4 px per lane) and
+// slides down R rows: per input row one coalesced 128-byte load per warp, neighbour words by shuffle, the
+// row pass as two IDP.4A (dp4a) per pixel on PRMT-extracted byte windows, a 7-row register window for the
+// column pass, one aligned 32-bit store per 4 output pixels.  One launch covers all levels of all images.
 //
 // Bound: HBM/L2 streaming (read + write of sum_l w_l*h_l bytes per image).
 #include "borb_internal.h"
@@ -12,19 +16,19 @@
 namespace borb {
 
 namespace {
-constexpr int BT_W = 64, BT_H = 32;
+constexpr int BT_W = 128;     // strip width (32 lanes x 4 px)
+constexpr int BT_R = 8;       // output rows per warp
+constexpr int BT_H = 64;      // rows per CTA (8 warps)
+
 __device__ __forceinline__ int reflect101(int p, int len) {
-    // |p| excursions are <= 3 here; levels are >= 7 px wide/tall
     if (p < 0) p = -p;
     if (p >= len) p = 2 * len - 2 - p;
-    return min(max(p, 0), len - 1);   // clamp only matters for tile lanes beyond the image (results discarded)
+    return min(max(p, 0), len - 1);
 }
 }  // namespace
 
 __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ pyr,
                                                    uint8_t* __restrict__ blur) {
-    __shared__ uint8_t in[(BT_H + 6) * (BT_W + 8)];
-    __shared__ uint16_t rowp[(BT_H + 6) * BT_W];
     const int img = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && (int)blockIdx.x >= g.blur_base[l + 1]) l++;
@@ -32,30 +36,67 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geome
     const int local = blockIdx.x - g.blur_base[l];
     const int tilesX = (L.w + BT_W - 1) / BT_W;
     const int ty = local / tilesX, tx = local - ty * tilesX;
-    const int x0 = tx * BT_W, y0 = ty * BT_H;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int x = tx * BT_W + 4 * lane;            // first of this lane's 4 pixels
+    const int yb = ty * BT_H + wrp * BT_R;          // first output row of this warp
+    if (yb >= L.h) return;
     const uint8_t* src = pyr + (size_t)img * g.pyr_image_stride + L.pyr_off;
     uint8_t* dst = blur + (size_t)img * g.pyr_image_stride + L.pyr_off;
-    constexpr int IW = BT_W + 6, IP = BT_W + 8, IH = BT_H + 6;
-    for (int i = tid; i < IW * IH; i += 256) {
-        const int yy = i / IW, xx = i - yy * IW;
-        const int sx = reflect101(x0 + xx - 3, L.w), sy = reflect101(y0 + yy - 3, L.h);
-        in[yy * IP + xx] = src[(size_t)sy * L.pitch + sx];
-    }
-    __syncthreads();
-    for (int i = tid; i < IH * BT_W; i += 256) {
-        const int yy = i / BT_W, xx = i - yy * BT_W;
-        const uint8_t* p = &in[yy * IP + xx];
-        rowp[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    for (int i = tid; i < BT_H * BT_W; i += 256) {
-        const int yy = i / BT_W, xx = i - yy * BT_W;
-        const int gx = x0 + xx, gy = y0 + yy;
-        if (gx < L.w && gy < L.h) {
-            const uint16_t* p = &rowp[yy * BT_W + xx];
-            const uint32_t s = 18u * (p[0] + p[6 * BT_W]) + 34u * (p[BT_W] + p[5 * BT_W]) + 48u * (p[2 * BT_W] + p[4 * BT_W]) + 56u * p[3 * BT_W];
-            dst[(size_t)gy * L.pitch + gx] = (uint8_t)min((s + 32768u) >> 16, 255u);
+    const int W = L.w, H = L.h, pitch = L.pitch;
+    const bool left_edge = (x == 0);
+    // lanes whose 12-byte window [x-4, x+8) reaches past the last pixel need reflected bytes
+    const bool right_fix = (x + 8 > W);
+    const unsigned WLO = 18u | (34u << 8) | (48u << 16) | (56u << 24);
+    const unsigned WHI = 48u | (34u << 8) | (18u << 16);
+
+    // issue every row's load up front (independent, coalesced 128 B per warp) so that their latencies overlap
+    uint32_t own[BT_R + 6];
+#pragma unroll
+    for (int step = 0; step < BT_R + 6; step++)
+        own[step] = *reinterpret_cast<const uint32_t*>(src + (size_t)reflect101(yb + step - 3, H) * pitch + x);
+
+    int win[7][4];    // row-pass results of the last 7 input rows (slot = input step % 7)
+#pragma unroll
+    for (int step = 0; step < BT_R + 6; step++) {
+        const int yin = yb + step - 3;                    // input row feeding output rows yin-3 .. yin+3
+        const int sy = reflect101(yin, H);
+        const uint8_t* row = src + (size_t)sy * pitch;
+        // the pitch is a multiple of 128 and x < pitch: the lane's own word is always inside the row buffer
+        uint32_t W1 = own[step];
+        uint32_t W0 = __shfl_up_sync(0xFFFFFFFFu, W1, 1);
+        uint32_t W2 = __shfl_down_sync(0xFFFFFFFFu, W1, 1);
+        if (lane == 0 && !left_edge) W0 = *reinterpret_cast<const uint32_t*>(row + x - 4);
+        if (lane == 31 && x + 4 < pitch) W2 = *reinterpret_cast<const uint32_t*>(row + x + 4);
+        if (left_edge) W0 = __byte_perm(W1, W2, 0x1234);  // bytes -4..-1 = pixels 4,3,2,1 (reflect-101)
+        if (right_fix) {
+            // rebuild the window byte by byte with reflected indices (only the 1-3 lanes at the right image edge)
+            uint32_t w[3] = {0, 0, 0};
+#pragma unroll
+            for (int b = 0; b < 12; b++) {
+                const int sx = reflect101(x - 4 + b, W);
+                w[b >> 2] |= (uint32_t)row[sx] << (8 * (b & 3));
+            }
+            W0 = w[0]; W1 = w[1]; W2 = w[2];
+        }
+        int* r = win[step % 7];
+        r[0] = __dp4a(__byte_perm(W0, W1, 0x4321), WLO, __dp4a(__byte_perm(W1, W2, 0x4321), WHI, 0u));
+        r[1] = __dp4a(__byte_perm(W0, W1, 0x5432), WLO, __dp4a(__byte_perm(W1, W2, 0x5432), WHI, 0u));
+        r[2] = __dp4a(__byte_perm(W0, W1, 0x6543), WLO, __dp4a(__byte_perm(W1, W2, 0x6543), WHI, 0u));
+        r[3] = __dp4a(W1, WLO, __dp4a(W2, WHI, 0u));
+        if (step >= 6) {
+            const int yout = yb + step - 6;
+            if (yout < H && x < W) {
+                uint32_t out = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    // slots: output row yout uses input steps step-6 .. step
+                    const int s = 18 * (win[(step - 6) % 7][i] + win[step % 7][i]) + 34 * (win[(step - 5) % 7][i] + win[(step - 1) % 7][i]) +
+                                  48 * (win[(step - 4) % 7][i] + win[(step - 2) % 7][i]) + 56 * win[(step - 3) % 7][i];
+                    out |= (uint32_t)min((unsigned)(s + 32768) >> 16, 255u) << (8 * i);
+                }
+                // rows are pitch-aligned and x % 4 == 0: one aligned store; bytes past W inside the pitch are scratch
+                *reinterpret_cast<uint32_t*>(dst + (size_t)yout * pitch + x) = out;
+            }
         }
     }
 }

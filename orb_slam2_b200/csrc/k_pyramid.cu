@@ -42,6 +42,28 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(const uint8_t* __restri
     *reinterpret_cast<uint32_t*>(D + dx0) = out;
 }
 
+// Level 0 from a tightly packed landing buffer (one big H2D copy) into the pitched pyramid layout.
+// slot i of the landing buffer holds image `first + i*step` of the batch (stereo: left/right interleave).
+__global__ void __launch_bounds__(256) repack_kernel(const uint8_t* __restrict__ stage, int src_stride, size_t src_image_bytes,
+                                                     uint8_t* __restrict__ pyr, LevelGeom l0, unsigned image_stride) {
+    const int img = blockIdx.z, y = blockIdx.y;
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x0 >= l0.w) return;
+    const uint8_t* S = stage + (size_t)img * src_image_bytes + (size_t)y * src_stride + x0;
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (x0 + i < l0.w) v |= (uint32_t)S[i] << (8 * i);
+    *reinterpret_cast<uint32_t*>(pyr + (size_t)img * image_stride + l0.pyr_off + (size_t)y * l0.pitch + x0) = v;
+}
+
+int launch_repack(const Geometry& g, const Workspace& ws, const uint8_t* stage, int src_stride, size_t src_image_bytes,
+                  int n_images, cudaStream_t s) {
+    dim3 grid((g.lv[0].w + 1023) / 1024, g.lv[0].h, n_images);
+    repack_kernel<<<grid, 256, 0, s>>>(stage, src_stride, src_image_bytes, ws.pyr, g.lv[0], g.pyr_image_stride);
+    return 1;
+}
+
 int launch_pyramid(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s) {
     int launches = 0;
     for (int l = 1; l < g.nlevels; l++) {

@@ -1,6 +1,10 @@
 // Stereo association: warp-per-left-keypoint Hamming search + 11x11 SAD sub-pixel refinement, then a
 // per-pair median cull.  Replaces Frame::ComputeStereoMatches (reference src/Frame.cc:466-640).
 //
+// Kernel 0 (one CTA per pair): bins the right keypoints by image row — every right keypoint is registered in
+//   each 8-row bin its band [floor(y-r), ceil(y+r)] touches (count, scan, fill with shared-memory atomics), as a
+//   compact 16-byte record {iR, minr|maxr, octave, x}.  A left keypoint then only scans the bin of its own row
+//   (~100 records instead of all ~2000 right keypoints).  Order inside a bin is irrelevant (see below).
 // Kernel 1 (one warp per left keypoint):
 //   candidates = right keypoints whose row band [floor(y-r), ceil(y+r)], r = 2*mvScaleFactors[octave]
 //   (:483-493) contains (int)vL (:511), with |octaveR-octaveL| <= 1 (:533) and uR in [uL-maxD, uL]
@@ -28,10 +32,85 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 
 }  // namespace
 
+constexpr int SBIN_SHIFT = 3;      // 8 image rows per bin
+constexpr int SBIN_MAX = 512;      // bins per pair (images up to 4096 rows)
+struct __align__(16) RightRec { int iR; int band; int octave; float x; };   // band = minr | maxr << 16
+
+// grid: (pairs); writes bin_start[pair][nbins+1] and recs[pair][...]
+__global__ void __launch_bounds__(256) stereo_bin_kernel(const __grid_constant__ Geometry g, StereoView Rv,
+                                                         const int* __restrict__ pair_idx, int* __restrict__ bin_start,
+                                                         RightRec* __restrict__ recs, int rec_stride) {
+    __shared__ int cnt[SBIN_MAX + 1];
+    __shared__ int wsum[40];
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    const int imR = pair_idx[2 * pair + 1];
+    const int nR = Rv.nkp[imR];
+    const int nb = min((g.h >> SBIN_SHIFT) + 1, SBIN_MAX);
+    const borb_keypoint* kR = Rv.kps + (size_t)imR * Rv.kp_image_stride;
+    for (int i = tid; i <= nb; i += 256) cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < nR; i += 256) {
+        const borb_keypoint kr = kR[i];
+        const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
+        const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
+        const int b0 = max(minr, 0) >> SBIN_SHIFT, b1 = min(min(maxr, g.h - 1) >> SBIN_SHIFT, nb - 1);
+        for (int b = b0; b <= b1; b++) atomicAdd(&cnt[b], 1);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..nb) (nb <= 512: two elements per thread)
+    {
+        const int lane = tid & 31, w = tid >> 5;
+        const int i0 = 2 * tid, i1 = 2 * tid + 1;
+        const int c0 = i0 < nb ? cnt[i0] : 0, c1 = i1 < nb ? cnt[i1] : 0;
+        int incl = c0 + c1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int v = lane < 8 ? wsum[lane] : 0, inc2 = v;
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, inc2, off);
+                if (lane >= off) inc2 += t;
+            }
+            if (lane < 8) wsum[8 + lane] = inc2 - v;
+            if (lane == 7) wsum[16] = inc2;
+        }
+        __syncthreads();
+        const int base = wsum[8 + w] + incl - (c0 + c1);
+        if (i0 < nb) cnt[i0] = base;
+        if (i1 < nb) cnt[i1] = base + c0;
+        if (tid == 0) cnt[nb] = wsum[16];
+        __syncthreads();
+    }
+    int* bs = bin_start + (size_t)pair * (SBIN_MAX + 1);
+    for (int i = tid; i <= nb; i += 256) bs[i] = cnt[i];
+    __syncthreads();
+    RightRec* out = recs + (size_t)pair * rec_stride;
+    for (int i = tid; i < nR; i += 256) {
+        const borb_keypoint kr = kR[i];
+        const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
+        const int maxr = (int)ceilf(__fadd_rn(kr.y, r)), minr = (int)floorf(__fsub_rn(kr.y, r));
+        const int b0 = max(minr, 0) >> SBIN_SHIFT, b1 = min(min(maxr, g.h - 1) >> SBIN_SHIFT, nb - 1);
+        RightRec rec;
+        rec.iR = i; rec.band = (minr & 0xFFFF) | (maxr << 16); rec.octave = kr.octave; rec.x = kr.x;
+        for (int b = b0; b <= b1; b++) {
+            const int pos = atomicAdd(&cnt[b], 1);
+            if (pos < rec_stride) out[pos] = rec;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) stereo_match_kernel(const __grid_constant__ Geometry g, StereoView Lv, StereoView Rv,
                                                            const int* __restrict__ pair_idx, float bf, float b,
                                                            float* __restrict__ u_right, float* __restrict__ depth,
-                                                           int* __restrict__ sad, int out_stride) {
+                                                           int* __restrict__ sad, int out_stride,
+                                                           const int* __restrict__ bin_start, const RightRec* __restrict__ recs,
+                                                           int rec_stride) {
     const int pair = blockIdx.y;
     const int imL = pair_idx[2 * pair], imR = pair_idx[2 * pair + 1];
     const int lane = threadIdx.x & 31;
@@ -56,17 +135,20 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(const __grid_constant
     const uint4 a0 = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32)[0];
     const uint4 a1 = reinterpret_cast<const uint4*>(dL + (size_t)iL * 32)[1];
     unsigned best = ((unsigned)TH_HIGH << 16);      // strict '<' against TH_HIGH: keys >= TH_HIGH<<16 never win
-    if (!(maxU < 0)) {
-        for (int iR = lane; iR < nR; iR += 32) {
-            const borb_keypoint kr = kR[iR];
-            const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
-            const int maxr = (int)ceilf(__fadd_rn(kr.y, r));
-            const int minr = (int)floorf(__fsub_rn(kr.y, r));
+    if (!(maxU < 0) && row >= 0 && row < g.h) {
+        const int nb = min((g.h >> SBIN_SHIFT) + 1, SBIN_MAX);
+        const int bin = min(row >> SBIN_SHIFT, nb - 1);
+        const int* bs = bin_start + (size_t)pair * (SBIN_MAX + 1);
+        const int e0 = bs[bin], e1 = min(bs[bin + 1], rec_stride);
+        const RightRec* rr = recs + (size_t)pair * rec_stride;
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const RightRec rc = rr[e];
+            const int minr = (int)(short)(rc.band & 0xFFFF), maxr = rc.band >> 16;
             if (row < minr || row > maxr) continue;
-            if (kr.octave < levelL - 1 || kr.octave > levelL + 1) continue;
-            if (kr.x >= minU && kr.x <= maxU) {
-                const int dist = hamming256(a0, a1, reinterpret_cast<const uint4*>(dR + (size_t)iR * 32));
-                const unsigned key = ((unsigned)dist << 16) | (unsigned)iR;
+            if (rc.octave < levelL - 1 || rc.octave > levelL + 1) continue;
+            if (rc.x >= minU && rc.x <= maxU) {
+                const int dist = hamming256(a0, a1, reinterpret_cast<const uint4*>(dR + (size_t)rc.iR * 32));
+                const unsigned key = ((unsigned)dist << 16) | (unsigned)rc.iR;
                 best = min(best, key);
             }
         }
@@ -204,12 +286,24 @@ __global__ void __launch_bounds__(256) stereo_median_kernel(StereoView Lv, const
     }
 }
 
+// Worst-case records per pair: a band spans 2*ceil(2*scale_max)+2 rows, i.e. at most (that >> 3) + 2 bins.
+int stereo_rec_stride(const Geometry& g) {
+    const int band = 2 * (int)ceilf(2.0f * g.lv[g.nlevels - 1].scale) + 3;
+    return g.sel_image_stride * ((band >> SBIN_SHIFT) + 2);
+}
+size_t stereo_bins_bytes_per_pair() { return (size_t)(SBIN_MAX + 1) * sizeof(int); }
+size_t stereo_rec_bytes() { return sizeof(RightRec); }
+
 int launch_stereo(const Geometry& g, const StereoView& L, const StereoView& R, const int* d_pair_idx, int n_pairs,
-                  float bf, float b, float* d_u_right, float* d_depth, int* d_sad, int out_stride, cudaStream_t s) {
+                  float bf, float b, float* d_u_right, float* d_depth, int* d_sad, int out_stride, int* d_bins, void* d_recs,
+                  cudaStream_t s) {
+    const int rec_stride = stereo_rec_stride(g);
+    stereo_bin_kernel<<<n_pairs, 256, 0, s>>>(g, R, d_pair_idx, d_bins, reinterpret_cast<RightRec*>(d_recs), rec_stride);
     dim3 grid((g.sel_image_stride + 7) / 8, n_pairs);
-    stereo_match_kernel<<<grid, 256, 0, s>>>(g, L, R, d_pair_idx, bf, b, d_u_right, d_depth, d_sad, out_stride);
+    stereo_match_kernel<<<grid, 256, 0, s>>>(g, L, R, d_pair_idx, bf, b, d_u_right, d_depth, d_sad, out_stride, d_bins,
+                                             reinterpret_cast<const RightRec*>(d_recs), rec_stride);
     stereo_median_kernel<<<n_pairs, 256, 0, s>>>(L, d_pair_idx, d_u_right, d_depth, d_sad, out_stride);
-    return 2;
+    return 3;
 }
 
 }  // namespace borb
