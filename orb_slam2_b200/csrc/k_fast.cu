@@ -12,22 +12,25 @@
 //   a cell emits keep(p) with S>=iniTh if any exists, else keep(p) with S>=minTh.
 // One CTA owns `cellsPerBlk` whole cells of one cell row, so NMS and the threshold decision are CTA-local.
 //
-// Pipeline inside a CTA (v2):
+// Pipeline inside a CTA (v3):
 //   0. one elected thread issues a 3-D TMA tile load (cp.async.bulk.tensor, box 160 x (hCell+6) bytes at
 //      ((x0-4)&~15, y0-3, image): the inner start coordinate must be 16-byte aligned) into shared memory
 //      and everybody waits on its mbarrier;
-//   1. packed quick-reject: a thread owns the 4 pixels of one ALIGNED 32-bit word of the tile and
-//      slides down its rows; per ring position one VABSDIFF4 gives |I_q - I_p| for the 4 pixels and three
-//      logic ops turn it into a per-byte ">t" flag; a FAST-9 arc contains at least one pixel of each of
-//      the 8 antipodal ring pairs, so AND_j (f_j | f_{j+8}) == 0 rejects the pixel.  Even positions first;
-//      odd positions only if something survives.  Survivors are appended to a shared-memory queue;
-//   2. exact arc test + score for queued pixels only;  3. cell-local NMS for scored pixels only;
-//   4. per-cell threshold decision and warp-aggregated append to the global candidate list.
+//   1. a thread owns the 4 pixels of one ALIGNED 32-bit word of the tile and slides down its rows with a
+//      7-row register window.  Cheap reject: per even ring position one VABSDIFF4 gives |I_q - I_p| for the
+//      4 pixels and three logic ops a per-byte ">t" flag; a FAST-9 arc contains a pixel of each antipodal
+//      ring pair, so AND_j (f_j | f_{j+8}) == 0 rejects.  Surviving words are scored EXACTLY: ring
+//      differences as s16x2 lanes (two pixels per register), S = max(max_k min_{j<9} d_{k+j},
+//      -min_k max_{j<9} d_{k+j}) - 1 with VIMNMX3.S16x2 (min3/max3) networks — the corner test IS the score
+//      (corner at t <=> S >= t).  Dense warps score in place; sparse warps push their words to a
+//      shared-memory queue that is scored afterwards with all lanes busy;
+//   2. cell-local strict NMS over the queued corners;  3. per-cell threshold decision and warp-aggregated
+//      append to the global candidate list.
 // Output: unordered candidate list per (image, level) of packed (x,y,score); consumers break ties with
 // the reference's emission order key (cell row, cell col, y, x), never with list position.
 //
-// Bound (target): HBM read of the level pixels, once — sum_l w_l*h_l bytes per image.  Measured: issue
-// bound (see profiles/); the packed reject is what keeps the instruction count per pixel low.
+// Bound (target): HBM read of the level pixels, once — sum_l w_l*h_l bytes per image.  Measured on B200: the
+// integer ALU pipe (LOP3/PRMT/VABSDIFF4/VIMNMX3 all issue at 64 lanes/clk/SM, tools/ubench*.cu) — see DESIGN.md.
 #include <cuda.h>
 
 #include <cstring>
@@ -41,60 +44,9 @@ namespace {
 constexpr int TP = 160;                 // TMA box width == smem tile pitch (bytes).  TMA needs a 16-byte aligned start
                                         // column, so the box starts at xs = (x0-4) & ~15 and domain px xx sits at column xx+off
 constexpr int TROWS = 66;               // hCell <= 60, + 3 halo rows above and below
-constexpr int SW = 128;                 // score-map pitch
 constexpr int QCAP = 60 * 128;          // queue capacity >= every pixel of the largest tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// Scalar 9-arc test (only used for thresholds > 127, outside the packed path): 0 none, 1 bright arc, 2 dark arc.
-__device__ __forceinline__ int scalar_arc(const uint8_t* c, int t) {
-    constexpr int P = TP;
-    const int offs[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1,
-                          -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
-    const int v = c[0];
-    unsigned B = 0, D = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int r = c[offs[k]];
-        B |= (r > v + t ? 1u : 0u) << k;
-        D |= (r < v - t ? 1u : 0u) << k;
-    }
-    auto arc9 = [](unsigned m) -> bool {
-        unsigned x = m | (m << 16);
-        unsigned a = x & (x >> 1);
-        a &= a >> 2;
-        a &= a >> 4;
-        a &= x >> 8;
-        return (a & 0xFFFFu) != 0;
-    };
-    return arc9(B) ? 1 : (arc9(D) ? 2 : 0);
-}
-
-// S(p) for a pixel already known to be a FAST-9 corner with the given polarity (dark: ring < centre).
-// = max over the 16 nine-pixel arcs of the min signed difference, minus 1 (cornerScore<16>); the other
-// polarity cannot have a 9-arc (9+9 > 16).  Sliding 9-window minimum as min3 of min3 on the circular ring.
-__device__ __forceinline__ int corner_score(const uint8_t* c, bool dark) {
-    constexpr int P = TP;
-    const int v = c[0];
-    int d[16];
-    d[0] = c[3 * P];       d[1] = c[3 * P + 1];   d[2] = c[2 * P + 2];   d[3] = c[P + 3];
-    d[4] = c[3];           d[5] = c[-P + 3];      d[6] = c[-2 * P + 2];  d[7] = c[-3 * P + 1];
-    d[8] = c[-3 * P];      d[9] = c[-3 * P - 1];  d[10] = c[-2 * P - 2]; d[11] = c[-P - 3];
-    d[12] = c[-3];         d[13] = c[P - 3];      d[14] = c[2 * P - 2];  d[15] = c[3 * P - 1];
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = dark ? (v - d[k]) : (d[k] - v);
-    int m3[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) m3[k] = min(min(d[k], d[(k + 1) & 15]), d[(k + 2) & 15]);
-    int best = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k += 2) {
-        const int a = min(min(m3[k], m3[(k + 3) & 15]), m3[(k + 6) & 15]);
-        const int b = min(min(m3[k + 1], m3[(k + 4) & 15]), m3[(k + 7) & 15]);
-        best = max(max(best, a), b);
-    }
-    return best - 1;
-}
 
 // 4-byte window starting DX bytes after the start of W1 (W0|W1|W2 are three consecutive aligned words)
 template <int DX>
@@ -111,12 +63,56 @@ __device__ __forceinline__ uint32_t gt_flag(uint32_t q, uint32_t v, uint32_t T1)
     return ((a | 0x80808080u) - T1) | a;
 }
 
-constexpr uint32_t M7 = 0x7f7f7f7fu;
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t nb, uint32_t c) { return (a & nb) | (a & c) | (nb & c); }
-// bit 7 of each byte: q > hi (unsigned bytes);  nhi7 = ~hi & M7 precomputed
-__device__ __forceinline__ uint32_t gtu7(uint32_t q, uint32_t hi, uint32_t nhi7) { return maj3(q, ~hi, (q & M7) + nhi7); }
-// bit 7 of each byte: lo > q;  lo7 = lo & M7 precomputed
-__device__ __forceinline__ uint32_t ltu7(uint32_t q, uint32_t lo, uint32_t lo7) { return maj3(lo, ~q, lo7 + (~q & M7)); }
+// Exact FAST scores of the 4 pixels of one aligned word.  R0/R1/R2[j]: the three aligned words (px -4..-1, 0..3,
+// 4..7 relative to the word) of tile rows dy = j-3.  Returns 4 bytes: S(p) clamped to [0,254]; S(p) >= t <=> p
+// is a FAST-9 corner at threshold t (cornerScore<16> of OpenCV for every pixel, both polarities at once).
+__device__ __forceinline__ uint32_t score_word(const uint32_t (&R0)[7], const uint32_t (&R1)[7], const uint32_t (&R2)[7]) {
+#define ROWJ(dy) R0[(dy) + 3], R1[(dy) + 3], R2[(dy) + 3]
+    uint32_t wn[16];
+    wn[0] = win<0>(ROWJ(3));    wn[1] = win<1>(ROWJ(3));    wn[2] = win<2>(ROWJ(2));     wn[3] = win<3>(ROWJ(1));
+    wn[4] = win<3>(ROWJ(0));    wn[5] = win<3>(ROWJ(-1));   wn[6] = win<2>(ROWJ(-2));    wn[7] = win<1>(ROWJ(-3));
+    wn[8] = win<0>(ROWJ(-3));   wn[9] = win<-1>(ROWJ(-3));  wn[10] = win<-2>(ROWJ(-2));  wn[11] = win<-3>(ROWJ(-1));
+    wn[12] = win<-3>(ROWJ(0));  wn[13] = win<-3>(ROWJ(1));  wn[14] = win<-2>(ROWJ(2));   wn[15] = win<-1>(ROWJ(3));
+#undef ROWJ
+    const uint32_t v = R1[3];
+    uint32_t res[2];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        // half 0: pixels 0 and 2 (even bytes) as two s16 lanes; half 1: pixels 1 and 3 (odd bytes)
+        const uint32_t v2 = half ? __byte_perm(v, 0u, 0x4341) : (v & 0x00FF00FFu);
+        const uint32_t nv2 = __vneg2(v2);
+        uint32_t d[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t q2 = half ? __byte_perm(wn[k], 0u, 0x4341) : (wn[k] & 0x00FF00FFu);
+            d[k] = __vadd2(q2, nv2);                       // I_q - I_p per lane, in [-255, 255]
+        }
+        uint32_t lo3[16], hi3[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            lo3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+            hi3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        }
+        uint32_t lo9[16], hi9[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            lo9[k] = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);   // min over the arc k..k+8
+            hi9[k] = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);   // max over the arc k..k+8
+        }
+        uint32_t bb[5], dd[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            bb[k] = __vimax3_s16x2(lo9[3 * k], lo9[3 * k + 1], lo9[3 * k + 2]);
+            dd[k] = __vimin3_s16x2(hi9[3 * k], hi9[3 * k + 1], hi9[3 * k + 2]);
+        }
+        const uint32_t bright = __vimax3_s16x2(__vimax3_s16x2(bb[0], bb[1], bb[2]), __vimax3_s16x2(bb[3], bb[4], lo9[15]), bb[0]);
+        const uint32_t darkm = __vimin3_s16x2(__vimin3_s16x2(dd[0], dd[1], dd[2]), __vimin3_s16x2(dd[3], dd[4], hi9[15]), dd[0]);
+        // S = max(bright, -darkm) - 1, clamped at 0
+        res[half] = __viaddmax_s16x2_relu(__vmaxs2(bright, __vneg2(darkm)), 0xFFFFFFFFu, 0u);
+    }
+    // lanes hold 0..254: bytes  px0 = res0.lo, px1 = res1.lo, px2 = res0.hi, px3 = res1.hi
+    return res[1] * 256u + res[0];
+}
 
 }  // namespace
 
@@ -125,10 +121,10 @@ struct TMaps { CUtensorMap m[BORB_MAX_LEVELS]; };
 __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ TMaps tm,
                                                    uint32_t* __restrict__ cand, int* __restrict__ cand_cnt) {
     __shared__ __align__(128) uint8_t tile[TROWS * TP];
-    __shared__ __align__(16) uint8_t score[60 * SW];
-    __shared__ uint16_t queue[QCAP];
+    __shared__ __align__(16) uint8_t score[60 * TP];     // S(p) in TILE coordinates (same columns as `tile`)
+    __shared__ uint16_t queue[QCAP];                      // corners: row << 8 | tile column
+    __shared__ uint16_t wqueue[60 * 32];                  // words (row << 5 | lane) deferred to the dense scoring pass
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ uint16_t wqueue[60 * 32];    // words (row, lane) that survive the cheap reject
     __shared__ int qn, wqn;
     __shared__ int cellHasIni[128 / 30 + 1];
     __shared__ uint8_t cellOf[128];
@@ -164,8 +160,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
             ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tm.m[l])), "r"(xs), "r"(y0 - 3), "r"(img), "r"(smem_u32(&bar))
             : "memory");
     }
-    // overlap with the copy: clear the score map and the bookkeeping
-    for (int i = tid; i < (th * SW) / 16; i += 256) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+    // overlap with the copy: bookkeeping
     if (tid < 128 / 30 + 1) cellHasIni[tid] = 0;
     if (tid < 128) cellOf[tid] = (uint8_t)(tid / L.wCell);
     if (tid == 0) { qn = 0; wqn = 0; }
@@ -182,28 +177,68 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     __syncthreads();
 
     const int tlow = min(g.ini_th, g.min_th);
-    const bool packed_ok = tlow <= 127;
-
-    // ---- 1a. packed reject on |diff| of the even ring positions; surviving WORDS (4 px) go to a word queue so
-    //          that the exact test below runs with all lanes busy
     const uint32_t* T32 = reinterpret_cast<const uint32_t*>(tile);
-    const int wbase = off >> 2;             // lane owns aligned tile word wbase+lane; byte b is domain px xx = 4*lane-(off&3)+b
-    const uint32_t T1 = (uint32_t)(tlow + 1) * 0x01010101u;
-    const uint32_t Tt = (uint32_t)tlow * 0x01010101u;
+    uint32_t* S32 = reinterpret_cast<uint32_t*>(score);
+    const int wbase = off >> 2;             // lane owns aligned tile word wbase+lane (tile columns 4*(wbase+lane) .. +3)
+    const uint32_t T1 = (uint32_t)(min(tlow, 127) + 1) * 0x01010101u;
+    const uint32_t TC = (uint32_t)min(max(tlow, 1), 128) * 0x01010101u;   // corner flag: S >= max(tlow,1)
+    const bool reject_ok = tlow <= 127;
+
+    // Writes one scored word to the score map and appends its corner pixels (S >= tlow, inside the domain) to the
+    // corner queue.  Must be called by all 32 lanes (write = false for lanes without work).
+    auto commit = [&](uint32_t sw, int yy, int wc, bool write) {
+        const int col = 4 * wc;
+        uint32_t vm = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (col + b - off >= 0 && col + b - off < tw) vm |= 0x80u << (8 * b);
+        if (write) S32[yy * (TP / 4) + wc] = sw;
+        // bit 7 per byte: S >= TC byte (TC <= 128)
+        uint32_t m = (((sw | 0x80808080u) - TC) | sw) & vm;
+        if (tlow > 128) {       // never used by the reference configs: exact per-byte compare
+            m = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if ((int)((sw >> (8 * b)) & 0xFF) >= tlow) m |= 0x80u << (8 * b);
+            m &= vm;
+        }
+        if (!write) m = 0;
+        const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
+        if (any) {
+            const int c = __popc(m);
+            int incl = c;
+#pragma unroll
+            for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o2);
+                if (lane >= o2) incl += t;
+            }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&qn, incl);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - c;
+            uint32_t mm = m;
+            while (mm) {
+                const int b = (__ffs(mm) - 1) >> 3;
+                mm &= mm - 1;
+                queue[base++] = (uint16_t)((yy << 8) | (col + b));
+            }
+        }
+    };
+
+    // ---- 1a. slide down the rows: cheap reject, then score in place (dense warps) or defer (sparse warps)
     {
         const int RG = (th + 7) >> 3;                 // rows per warp (8 warps)
         const int yBeg = wrp * RG, yEnd = min(th, yBeg + RG);
-        const int xxb = 4 * lane - (off & 3);
+        const int wc = wbase + lane;
         uint32_t vmask = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++)
-            if (xxb + b >= 0 && xxb + b < tw) vmask |= 0x80u << (8 * b);
+            if (4 * wc + b - off >= 0 && 4 * wc + b - off < tw) vmask |= 0x80u << (8 * b);
         // rolling window of 7 tile rows x 3 words; slot (j % 7) holds tile row (yy + j), j = 0..6 <=> dy = j-3
         uint32_t a0[7], a1[7], a2[7];
         if (yBeg < yEnd) {
 #pragma unroll
             for (int j = 0; j < 6; j++) {
-                const uint32_t* rp = T32 + (yBeg + j) * (TP / 4) + wbase + lane - 1;
+                const uint32_t* rp = T32 + (yBeg + j) * (TP / 4) + wc - 1;
                 a0[j] = rp[0]; a1[j] = rp[1]; a2[j] = rp[2];
             }
         }
@@ -212,12 +247,12 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
             const int yy = yBeg + it;
             if (yy < yEnd) {          // warp-uniform
                 {
-                    const uint32_t* rp = T32 + (yy + 6) * (TP / 4) + wbase + lane - 1;
+                    const uint32_t* rp = T32 + (yy + 6) * (TP / 4) + wc - 1;
                     a0[(it + 6) % 7] = rp[0]; a1[(it + 6) % 7] = rp[1]; a2[(it + 6) % 7] = rp[2];
                 }
 #define ROW(dy) a0[(it + (dy) + 3) % 7], a1[(it + (dy) + 3) % 7], a2[(it + (dy) + 3) % 7]
                 bool keep = vmask != 0;
-                if (packed_ok) {
+                if (reject_ok && keep) {
                     const uint32_t v = a1[(it + 3) % 7];
                     uint32_t acc = gt_flag(win<0>(ROW(3)), v, T1) | gt_flag(win<0>(ROW(-3)), v, T1);      // pair (0,8)
                     acc &= gt_flag(win<2>(ROW(2)), v, T1) | gt_flag(win<-2>(ROW(-2)), v, T1);               // (2,10)
@@ -227,130 +262,66 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
                 }
 #undef ROW
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&wqn, __popc(bal));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (keep) wqueue[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((yy << 5) | lane);
+                if (__popc(bal) >= 16) {
+                    // dense: score here, from the registers
+                    uint32_t sw = 0;
+                    if (keep) {
+                        uint32_t R0[7], R1[7], R2[7];
+#pragma unroll
+                        for (int j = 0; j < 7; j++) { R0[j] = a0[(it + j) % 7]; R1[j] = a1[(it + j) % 7]; R2[j] = a2[(it + j) % 7]; }
+                        sw = score_word(R0, R1, R2);
+                    }
+                    commit(sw, yy, wc, vmask != 0);
+                } else {
+                    // sparse: rejected words are final (score 0), survivors wait for the dense pass
+                    if (!keep && vmask != 0) S32[yy * (TP / 4) + wc] = 0;
+                    if (bal) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&wqn, __popc(bal));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if (keep) wqueue[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((yy << 5) | lane);
+                    }
                 }
             }
         }
     }
     __syncthreads();
 
-    // ---- 1b. exact, sign-aware 9-arc test on the queued words: per polarity the 16 per-position flags (bit 7 of
-    //          each byte = that pixel's flag), antipodal early-outs, then "9 contiguous" as AND of three 3-runs
+    // ---- 1b. dense scoring pass over the deferred words
     {
         const int nw = wqn;
         for (int eb = 0; eb < nw; eb += 256) {
             const int e = eb + tid;
-            uint32_t m = 0, mdark = 0;
-            int yy = 0, xxb = 0;
-            if (e < nw) {
+            uint32_t sw = 0;
+            int yy = 0, wc = wbase;
+            const bool have = e < nw;
+            if (have) {
                 const int we = wqueue[e];
                 yy = we >> 5;
-                const int ln = we & 31;
-                xxb = 4 * ln - (off & 3);
-                uint32_t vmask = 0;
+                wc = wbase + (we & 31);
+                uint32_t R0[7], R1[7], R2[7];
 #pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if (xxb + b >= 0 && xxb + b < tw) vmask |= 0x80u << (8 * b);
-                if (packed_ok) {
-                    uint32_t a0[7], a1[7], a2[7];
-#pragma unroll
-                    for (int j = 0; j < 7; j++) {
-                        const uint32_t* rp = T32 + (yy + j) * (TP / 4) + wbase + ln - 1;
-                        a0[j] = rp[0]; a1[j] = rp[1]; a2[j] = rp[2];
-                    }
-#define ROW(dy) a0[(dy) + 3], a1[(dy) + 3], a2[(dy) + 3]
-                    const uint32_t v = a1[3];
-                    const uint32_t hi = __vaddus4(v, Tt), lo = __vsubus4(v, Tt);
-#pragma unroll
-                    for (int pol = 0; pol < 2; pol++) {
-                        uint32_t f[16];
-                        const uint32_t k7 = pol ? (lo & M7) : (~hi & M7);
-#define FLAG(q) (pol ? ltu7((q), lo, k7) : gtu7((q), hi, k7))
-                        f[0] = FLAG(win<0>(ROW(3)));   f[8] = FLAG(win<0>(ROW(-3)));
-                        f[2] = FLAG(win<2>(ROW(2)));   f[10] = FLAG(win<-2>(ROW(-2)));
-                        f[4] = FLAG(win<3>(ROW(0)));   f[12] = FLAG(win<-3>(ROW(0)));
-                        f[6] = FLAG(win<2>(ROW(-2)));  f[14] = FLAG(win<-2>(ROW(2)));
-                        uint32_t ap = (f[0] | f[8]) & (f[2] | f[10]) & (f[4] | f[12]) & (f[6] | f[14]);
-                        if (ap & vmask) {
-                            f[1] = FLAG(win<1>(ROW(3)));   f[9] = FLAG(win<-1>(ROW(-3)));
-                            f[3] = FLAG(win<3>(ROW(1)));   f[11] = FLAG(win<-3>(ROW(-1)));
-                            f[5] = FLAG(win<3>(ROW(-1)));  f[13] = FLAG(win<-3>(ROW(1)));
-                            f[7] = FLAG(win<1>(ROW(-3)));  f[15] = FLAG(win<-1>(ROW(3)));
-                            ap &= (f[1] | f[9]) & (f[3] | f[11]) & (f[5] | f[13]) & (f[7] | f[15]);
-                            if (ap & vmask) {
-                                uint32_t p3[16];
-#pragma unroll
-                                for (int k = 0; k < 16; k++) p3[k] = f[k] & f[(k + 1) & 15] & f[(k + 2) & 15];
-                                uint32_t any9 = 0;
-#pragma unroll
-                                for (int k = 0; k < 16; k++) any9 |= p3[k] & p3[(k + 3) & 15] & p3[(k + 6) & 15];
-                                any9 &= vmask;
-                                m |= any9;
-                                if (pol) mdark = any9;
-                            }
-                        }
-#undef FLAG
-                    }
-#undef ROW
-                } else {
-                    m = vmask;          // thresholds above 127 (never used by the reference configs): scalar test in phase 2
+                for (int j = 0; j < 7; j++) {
+                    const uint32_t* rp = T32 + (yy + j) * (TP / 4) + wc - 1;
+                    R0[j] = rp[0]; R1[j] = rp[1]; R2[j] = rp[2];
                 }
+                sw = score_word(R0, R1, R2);
             }
-            // append this word's corner pixels to the corner queue (warp-aggregated)
-            const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
-            if (any) {
-                const int c = __popc(m);
-                int incl = c;
-#pragma unroll
-                for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o2);
-                    if (lane >= o2) incl += t;
-                }
-                int base = 0;
-                if (lane == 31) base = atomicAdd(&qn, incl);
-                base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - c;
-                uint32_t mm = m;
-                while (mm) {
-                    const int b = (__ffs(mm) - 1) >> 3;
-                    mm &= mm - 1;
-                    queue[base++] = (uint16_t)((((mdark >> (8 * b + 7)) & 1u) << 15) | (yy << 7) | (xxb + b));
-                }
-            }
+            commit(sw, yy, wc, have);
         }
     }
     __syncthreads();
     const int nq = qn;
 
-    // ---- 2. score of every corner (polarity known from the packed test)
+    // ---- 2. cell-local strict NMS for the corners (0xFFFF = dropped)
     for (int e = tid; e < nq; e += 256) {
         const int q = queue[e];
-        const int xx = q & 127, yy = (q >> 7) & 63;
-        const uint8_t* c = &tile[(yy + 3) * TP + xx + off];
-        bool dark = (q >> 15) != 0;
-        bool corner = true;
-        if (!packed_ok) {               // thresholds > 127: scalar 9-arc test decides corner-ness and polarity
-            const int pol = scalar_arc(c, tlow);
-            corner = pol != 0;
-            dark = pol == 2;
-        }
-        if (corner) score[yy * SW + xx] = (uint8_t)corner_score(c, dark);
-        else queue[e] = 0xFFFF;
-    }
-    __syncthreads();
-
-    // ---- 3. cell-local strict NMS for the corners (0xFFFF = dropped)
-    for (int e = tid; e < nq; e += 256) {
-        const int q = queue[e];
-        if (q == 0xFFFF) continue;
-        const int xx = q & 127, yy = (q >> 7) & 63;
-        const int s = score[yy * SW + xx];
+        const int col = q & 255, yy = q >> 8;
+        const int xx = col - off;
+        const int s = score[yy * TP + col];
         const int c = cellOf[xx];
         const int cx0 = c * L.wCell, cx1 = min(cx0 + L.wCell, tw);
-        bool ismax = s > 0;
+        bool ismax = true;
 #pragma unroll
         for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
@@ -358,7 +329,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
                 if (dx == 0 && dy == 0) continue;
                 const int qx = xx + dx, qy = yy + dy;
                 if (qx < cx0 || qx >= cx1 || qy < 0 || qy >= th) continue;
-                if (!(s > (int)score[qy * SW + qx])) ismax = false;
+                if (!(s > (int)score[qy * TP + col + dx])) ismax = false;
             }
         if (ismax) {
             if (s >= g.ini_th) cellHasIni[c] = 1;
@@ -367,7 +338,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     }
     __syncthreads();
 
-    // ---- 4. per-cell threshold + emit (warp-aggregated append)
+    // ---- 3. per-cell threshold + emit (warp-aggregated append)
     uint32_t* out = cand + (size_t)img * g.cand_image_stride + L.cand_off;
     int* cnt = cand_cnt + img * g.nlevels + l;
     for (int eb = 0; eb < nq; eb += 256) {
@@ -376,8 +347,9 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
         if (e < nq) {
             const int q = queue[e];
             if (q != 0xFFFF) {
-                xx = q & 127; yy = (q >> 7) & 63;
-                s = score[yy * SW + xx];
+                const int col = q & 255;
+                yy = q >> 8; xx = col - off;
+                s = score[yy * TP + col];
                 const int t = cellHasIni[cellOf[xx]] ? g.ini_th : g.min_th;
                 if (s < t) s = 0;
             }
