@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     __shared__ uint16_t queue[QCAP];                      // corners: row << 8 | tile column
     __shared__ uint16_t wqueue[60 * 32];                  // words (row << 5 | lane) deferred to the dense scoring pass
     __shared__ __align__(8) unsigned long long bar;
-    __shared__ int qn, wqn;
+    __shared__ uint32_t scoredRow[60];                    // per tile row: lanes whose word has an exact score in `score`
+    __shared__ int qn, wqn, needB;
     __shared__ int cellHasIni[128 / 30 + 1];
     __shared__ uint8_t cellOf[128];
 
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
     // overlap with the copy: bookkeeping
     if (tid < 128 / 30 + 1) cellHasIni[tid] = 0;
     if (tid < 128) cellOf[tid] = (uint8_t)(tid / L.wCell);
-    if (tid == 0) { qn = 0; wqn = 0; }
+    if (tid == 0) { qn = 0; wqn = 0; needB = 0; }
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -176,7 +177,9 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
         : "memory");
     __syncthreads();
 
-    const int tlow = min(g.ini_th, g.min_th);
+    // Pass A works at iniThFAST only: a cell falls back to minThFAST only if it has NO kept corner at iniThFAST
+    // (ORBextractor.cc:809-816), and a pixel with S < ini can neither be kept at ini nor suppress one that is.
+    const int tlow = g.ini_th;
     const uint32_t* T32 = reinterpret_cast<const uint32_t*>(tile);
     uint32_t* S32 = reinterpret_cast<uint32_t*>(score);
     const int wbase = off >> 2;             // lane owns aligned tile word wbase+lane (tile columns 4*(wbase+lane) .. +3)
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
 
     // Writes one scored word to the score map and appends its corner pixels (S >= tlow, inside the domain) to the
     // corner queue.  Must be called by all 32 lanes (write = false for lanes without work).
-    auto commit = [&](uint32_t sw, int yy, int wc, bool write) {
+    auto commit = [&](uint32_t sw, int yy, int wc, bool write, int tlow, uint32_t TC, uint32_t needMask) {
         const int col = 4 * wc;
         uint32_t vm = 0;
 #pragma unroll
@@ -194,13 +197,13 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
             if (col + b - off >= 0 && col + b - off < tw) vm |= 0x80u << (8 * b);
         if (write) S32[yy * (TP / 4) + wc] = sw;
         // bit 7 per byte: S >= TC byte (TC <= 128)
-        uint32_t m = (((sw | 0x80808080u) - TC) | sw) & vm;
+        uint32_t m = (((sw | 0x80808080u) - TC) | sw) & vm & needMask;
         if (tlow > 128) {       // never used by the reference configs: exact per-byte compare
             m = 0;
 #pragma unroll
             for (int b = 0; b < 4; b++)
                 if ((int)((sw >> (8 * b)) & 0xFF) >= tlow) m |= 0x80u << (8 * b);
-            m &= vm;
+            m &= vm & needMask;
         }
         if (!write) m = 0;
         const unsigned any = __ballot_sync(0xFFFFFFFFu, m != 0);
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
                 }
 #undef ROW
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                if (lane == 0) scoredRow[yy] = bal;
                 if (__popc(bal) >= 16) {
                     // dense: score here, from the registers
                     uint32_t sw = 0;
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
                         for (int j = 0; j < 7; j++) { R0[j] = a0[(it + j) % 7]; R1[j] = a1[(it + j) % 7]; R2[j] = a2[(it + j) % 7]; }
                         sw = score_word(R0, R1, R2);
                     }
-                    commit(sw, yy, wc, vmask != 0);
+                    commit(sw, yy, wc, vmask != 0, tlow, TC, 0xFFFFFFFFu);
                 } else {
                     // sparse: rejected words are final (score 0), survivors wait for the dense pass
                     if (!keep && vmask != 0) S32[yy * (TP / 4) + wc] = 0;
@@ -307,63 +311,128 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
                 }
                 sw = score_word(R0, R1, R2);
             }
-            commit(sw, yy, wc, have);
+            commit(sw, yy, wc, have, tlow, TC, 0xFFFFFFFFu);
         }
     }
     __syncthreads();
-    const int nq = qn;
+    int nq = qn;
 
-    // ---- 2. cell-local strict NMS for the corners (0xFFFF = dropped)
-    for (int e = tid; e < nq; e += 256) {
-        const int q = queue[e];
-        const int col = q & 255, yy = q >> 8;
-        const int xx = col - off;
-        const int s = score[yy * TP + col];
-        const int c = cellOf[xx];
-        const int cx0 = c * L.wCell, cx1 = min(cx0 + L.wCell, tw);
-        bool ismax = true;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-                if (dx == 0 && dy == 0) continue;
-                const int qx = xx + dx, qy = yy + dy;
-                if (qx < cx0 || qx >= cx1 || qy < 0 || qy >= th) continue;
-                if (!(s > (int)score[qy * TP + col + dx])) ismax = false;
-            }
-        if (ismax) {
-            if (s >= g.ini_th) cellHasIni[c] = 1;
-        } else
-            queue[e] = 0xFFFF;
-    }
-    __syncthreads();
-
-    // ---- 3. per-cell threshold + emit (warp-aggregated append)
     uint32_t* out = cand + (size_t)img * g.cand_image_stride + L.cand_off;
     int* cnt = cand_cnt + img * g.nlevels + l;
-    for (int eb = 0; eb < nq; eb += 256) {
-        const int e = eb + tid;
-        int s = 0, xx = 0, yy = 0;
-        if (e < nq) {
+
+    // cell-local strict NMS over queue[0..n) (0xFFFF = dropped); optionally records which cells keep something
+    auto nms = [&](int n, bool mark) {
+        for (int e = tid; e < n; e += 256) {
             const int q = queue[e];
-            if (q != 0xFFFF) {
-                const int col = q & 255;
-                yy = q >> 8; xx = col - off;
-                s = score[yy * TP + col];
-                const int t = cellHasIni[cellOf[xx]] ? g.ini_th : g.min_th;
-                if (s < t) s = 0;
+            const int col = q & 255, yy = q >> 8;
+            const int xx = col - off;
+            const int s = score[yy * TP + col];
+            const int c = cellOf[xx];
+            const int cx0 = c * L.wCell, cx1 = min(cx0 + L.wCell, tw);
+            bool ismax = true;
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (dx == 0 && dy == 0) continue;
+                    const int qx = xx + dx, qy = yy + dy;
+                    if (qx < cx0 || qx >= cx1 || qy < 0 || qy >= th) continue;
+                    if (!(s > (int)score[qy * TP + col + dx])) ismax = false;
+                }
+            if (ismax) {
+                if (mark) cellHasIni[c] = 1;
+            } else
+                queue[e] = 0xFFFF;
+        }
+    };
+    // warp-aggregated append of the surviving queue entries to the global candidate list
+    auto emit = [&](int n) {
+        for (int eb = 0; eb < n; eb += 256) {
+            const int e = eb + tid;
+            int s = 0, xx = 0, yy = 0;
+            if (e < n) {
+                const int q = queue[e];
+                if (q != 0xFFFF) {
+                    const int col = q & 255;
+                    yy = q >> 8; xx = col - off;
+                    s = score[yy * TP + col];
+                }
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, s > 0);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cnt, __popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (s > 0) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1));
+                    if (pos < L.cand_cap) out[pos] = pack_xys(x0 + xx, y0 + yy, s);
+                }
             }
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, s > 0);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(cnt, __popc(m));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (s > 0) {
-                const int pos = base + __popc(m & ((1u << lane) - 1));
-                if (pos < L.cand_cap) out[pos] = pack_xys(x0 + xx, y0 + yy, s);
+    };
+
+    // ---- 2. pass A: NMS among the S >= iniTh corners; every survivor is emitted and marks its cell
+    nms(nq, true);
+    __syncthreads();
+    emit(nq);
+    if (tid < ncell && tid * L.wCell < tw && !cellHasIni[tid] && g.min_th < g.ini_th) needB = 1;
+    __syncthreads();
+    if (!needB) return;
+
+    // ---- 3. pass B (rare): cells without any kept iniTh corner are redone at minThFAST (ORBextractor.cc:812-816).
+    //         Words of those cells that pass A rejected (S < ini, not necessarily < min) are scored now.
+    {
+        if (tid == 0) qn = 0;
+        __syncthreads();
+        const int tmin = g.min_th;
+        const uint32_t T1b = (uint32_t)(min(tmin, 127) + 1) * 0x01010101u;
+        const uint32_t TCb = (uint32_t)min(max(tmin, 1), 128) * 0x01010101u;
+        const int nwords = th * 32;
+        for (int wb = 0; wb < nwords; wb += 256) {
+            const int widx = wb + tid;
+            const int yy = widx >> 5;           // warp-uniform: 32 consecutive threads share a row
+            const int wc = wbase + (widx & 31);
+            uint32_t needMask = 0, sw = 0;
+            bool write = false;
+            if (widx < nwords) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int xx = 4 * wc + b - off;
+                    if (xx >= 0 && xx < tw && !cellHasIni[cellOf[xx]]) needMask |= 0x80u << (8 * b);
+                }
+                if (needMask) {
+                    write = true;
+                    if ((scoredRow[yy] >> (widx & 31)) & 1u) {
+                        sw = S32[yy * (TP / 4) + wc];
+                    } else {
+                        uint32_t R0[7], R1[7], R2[7];
+#pragma unroll
+                        for (int j = 0; j < 7; j++) {
+                            const uint32_t* rp = T32 + (yy + j) * (TP / 4) + wc - 1;
+                            R0[j] = rp[0]; R1[j] = rp[1]; R2[j] = rp[2];
+                        }
+                        bool keep = true;
+                        if (tmin <= 127) {
+                            const uint32_t v = R1[3];
+#define ROWJ(dy) R0[(dy) + 3], R1[(dy) + 3], R2[(dy) + 3]
+                            uint32_t acc = gt_flag(win<0>(ROWJ(3)), v, T1b) | gt_flag(win<0>(ROWJ(-3)), v, T1b);
+                            acc &= gt_flag(win<2>(ROWJ(2)), v, T1b) | gt_flag(win<-2>(ROWJ(-2)), v, T1b);
+                            acc &= gt_flag(win<3>(ROWJ(0)), v, T1b) | gt_flag(win<-3>(ROWJ(0)), v, T1b);
+                            acc &= gt_flag(win<2>(ROWJ(-2)), v, T1b) | gt_flag(win<-2>(ROWJ(2)), v, T1b);
+#undef ROWJ
+                            keep = (acc & 0x80808080u) != 0;
+                        }
+                        sw = keep ? score_word(R0, R1, R2) : 0u;
+                    }
+                }
             }
+            commit(sw, yy, wc, write, tmin, TCb, needMask);
         }
+        __syncthreads();
+        nq = qn;
+        nms(nq, false);
+        __syncthreads();
+        emit(nq);
     }
 }
 
