@@ -22,8 +22,9 @@
 //      ring pair, so AND_j (f_j | f_{j+8}) == 0 rejects.  Surviving words are scored EXACTLY: ring
 //      differences as s16x2 lanes (two pixels per register), S = max(max_k min_{j<9} d_{k+j},
 //      -min_k max_{j<9} d_{k+j}) - 1 with VIMNMX3.S16x2 (min3/max3) networks — the corner test IS the score
-//      (corner at t <=> S >= t).  Dense warps score in place; sparse warps push their words to a
-//      shared-memory queue that is scored afterwards with all lanes busy;
+//      (corner at t <=> S >= t).  Survivors are pushed to a shared-memory word queue and scored in a second
+//      pass with all lanes busy.  This pass runs at iniThFAST only; cells that end up without a kept corner
+//      are redone at minThFAST afterwards (pass B), exactly the reference's per-cell fallback;
 //   2. cell-local strict NMS over the queued corners;  3. per-cell threshold decision and warp-aggregated
 //      append to the global candidate list.
 // Output: unordered candidate list per (image, level) of packed (x,y,score); consumers break ties with
@@ -118,7 +119,7 @@ __device__ __forceinline__ uint32_t score_word(const uint32_t (&R0)[7], const ui
 
 struct TMaps { CUtensorMap m[BORB_MAX_LEVELS]; };
 
-__global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ TMaps tm,
+__global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ TMaps tm,
                                                    uint32_t* __restrict__ cand, int* __restrict__ cand_cnt) {
     __shared__ __align__(128) uint8_t tile[TROWS * TP];
     __shared__ __align__(16) uint8_t score[60 * TP];     // S(p) in TILE coordinates (same columns as `tile`)
@@ -266,25 +267,13 @@ __global__ void __launch_bounds__(256) fast_kernel(const __grid_constant__ Geome
 #undef ROW
                 const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
                 if (lane == 0) scoredRow[yy] = bal;
-                if (__popc(bal) >= 16) {
-                    // dense: score here, from the registers
-                    uint32_t sw = 0;
-                    if (keep) {
-                        uint32_t R0[7], R1[7], R2[7];
-#pragma unroll
-                        for (int j = 0; j < 7; j++) { R0[j] = a0[(it + j) % 7]; R1[j] = a1[(it + j) % 7]; R2[j] = a2[(it + j) % 7]; }
-                        sw = score_word(R0, R1, R2);
-                    }
-                    commit(sw, yy, wc, vmask != 0, tlow, TC, 0xFFFFFFFFu);
-                } else {
-                    // sparse: rejected words are final (score 0), survivors wait for the dense pass
-                    if (!keep && vmask != 0) S32[yy * (TP / 4) + wc] = 0;
-                    if (bal) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&wqn, __popc(bal));
-                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                        if (keep) wqueue[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((yy << 5) | lane);
-                    }
+                // rejected words are final (S < iniTh: recorded as 0); survivors are scored in pass 1b with all lanes busy
+                if (!keep && vmask != 0) S32[yy * (TP / 4) + wc] = 0;
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&wqn, __popc(bal));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (keep) wqueue[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((yy << 5) | lane);
                 }
             }
         }
