@@ -8,6 +8,7 @@
  *   ORBmatcher::SearchForTriangulation    include/ORBmatcher.h:69-70,    src/ORBmatcher.cc:657
  *   ORBmatcher::DescriptorDistance        include/ORBmatcher.h:44,       src/ORBmatcher.cc:1647
  *   TemplatedVocabulary::transform (feeder) Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127
+ *   Frame::AssignFeaturesToGrid / GetFeaturesInArea  src/Frame.cc:230-245, 327-380
  * The reference has no FFI layer; these entry points are what the C++ adapters in
  * include/borb_adapters.hpp (same class signatures as the reference) forward to.
  *
@@ -154,6 +155,103 @@ BORB_API borb_status borb_stereo_frames_device_enqueue(borb_extractor* e, const 
 BORB_API borb_status borb_stereo_frames_device(borb_extractor* e, const uint8_t* d_gray, int n_pairs, int width, int height,
                                       size_t pitch, size_t image_stride, float bf, float b, int* n_left, int* n_right,
                                       float* u_right, float* depth, int cap);
+
+/* ---------------------------------------------------------------- matchers ------------------- */
+/* ORB_SLAM2::ORBmatcher is a stateless stack object created at every call site on three threads
+ * (include/ORBmatcher.h:37-102; src/Tracking.cc:599,764,869,1184,1357,1396, src/LocalMapping.cc:215,483,
+ * src/LoopClosing.cc:239,589).  A borb_matcher handle owns a CUDA stream and scratch: keep one per thread.
+ * The pointer graphs the reference walks (Frame, KeyFrame, MapPoint) are snapshotted by the adapter into the
+ * plain views below on the calling thread; results come back as indices. */
+typedef struct borb_matcher borb_matcher;
+BORB_API borb_status borb_matcher_create(int device, borb_matcher** out);
+BORB_API borb_status borb_matcher_destroy(borb_matcher* m);
+
+/* Frame snapshot for SearchByProjection (include/Frame.h): undistorted keypoints, descriptors, stereo
+ * coordinate, image bounds of the 64x48 feature grid (mnMinX.. / src/Frame.cc:97-102), scale factors. */
+typedef struct borb_frame_view {
+    int32_t n;                     /* N */
+    const borb_keypoint* keys_un;  /* mvKeysUn */
+    const uint8_t* desc;           /* mDescriptors, N x 32 */
+    const float* u_right;          /* mvuRight (NULL: monocular, no stereo check) */
+    const uint8_t* occupied;       /* 1 if mvpMapPoints[i] && Observations()>0 (src/ORBmatcher.cc:87-89); NULL: none */
+    float min_x, min_y, max_x, max_y;
+    int32_t n_levels;
+    const float* scale_factors;    /* mvScaleFactors */
+} borb_frame_view;
+
+/* Local map points that passed Frame::isInFrustum (src/Frame.cc:269-325), in vpMapPoints order. */
+typedef struct borb_mappoint_view {
+    int32_t n;
+    const float* proj_x;           /* mTrackProjX */
+    const float* proj_y;           /* mTrackProjY */
+    const float* proj_xr;          /* mTrackProjXR */
+    const int32_t* level;          /* mnTrackScaleLevel */
+    const float* view_cos;         /* mTrackViewCos */
+    const uint8_t* desc;           /* GetDescriptor(), n x 32 */
+    const uint8_t* valid;          /* mbTrackInView && !isBad() (NULL: all valid) */
+    const uint8_t* has_obs;        /* Observations()>0 (NULL: all) */
+} borb_mappoint_view;
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) — src/ORBmatcher.cc:45-129.
+ * match_feat[i] = index of the frame feature that received map point i (F.mvpMapPoints[idx]=pMP), or -1. */
+BORB_API borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* frame, const borb_mappoint_view* mps,
+                                               float th, float nnratio, int32_t* match_feat, int32_t* n_matches);
+
+/* DBoW2::FeatureVector (ordered map NodeId -> feature indices) as CSR; node_id ascending. */
+typedef struct borb_featvec_view {
+    int32_t n_nodes;
+    const uint32_t* node_id;
+    const int32_t* start;          /* n_nodes + 1 */
+    const uint32_t* feat_idx;
+} borb_featvec_view;
+
+/* KeyFrame (or Frame) snapshot for the BoW-guided searches. */
+typedef struct borb_keyframe_view {
+    int32_t n;
+    const borb_keypoint* keys_un;  /* mvKeysUn (angle, octave, pt) */
+    const uint8_t* desc;           /* mDescriptors */
+    const uint8_t* has_mp;         /* per feature: MapPoint present && !isBad() (NULL: none) */
+    const float* u_right;          /* mvuRight (NULL: all -1) */
+    borb_featvec_view fv;          /* mFeatVec */
+    int32_t n_levels;
+    const float* scale_factors;    /* mvScaleFactors */
+    const float* level_sigma2;     /* mvLevelSigma2 */
+} borb_keyframe_view;
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — src/ORBmatcher.cc:159-288, for n_kf keyframes
+ * against one frame in one launch (relocalisation / loop candidates).  match[k*frame->n + j] = index of the
+ * feature of keyframe k whose MapPoint frame feature j received, or -1; n_matches[k] = return value. */
+BORB_API borb_status borb_search_by_bow(borb_matcher* m, const borb_keyframe_view* kfs, int n_kf, const borb_keyframe_view* frame,
+                                        float nnratio, int check_orientation, int32_t* match, int32_t* n_matches);
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) — src/ORBmatcher.cc:522-655.
+ * match12[i] = index in kf2 of the MapPoint matched to feature i of kf1, or -1. */
+BORB_API borb_status borb_search_by_bow_kf(borb_matcher* m, const borb_keyframe_view* kf1, const borb_keyframe_view* kf2,
+                                           float nnratio, int check_orientation, int32_t* match12, int32_t* n_matches);
+/* ORBmatcher::SearchForTriangulation — src/ORBmatcher.cc:657-823.  F12 row-major 3x3; (ex,ey) = projection of
+ * kf1's camera centre into kf2 (:663-670, computed by the caller).  pairs: 2*cap ints (idx1, idx2), ascending idx1. */
+BORB_API borb_status borb_search_for_triangulation(borb_matcher* m, const borb_keyframe_view* kf1, const borb_keyframe_view* kf2,
+                                                   const float* F12, float ex, float ey, int only_stereo, int check_orientation,
+                                                   int32_t* pairs, int cap, int32_t* n_pairs);
+
+/* ---------------------------------------------------------------- vocabulary (BoW feeder) ---- */
+/* ORBVocabulary = DBoW2::TemplatedVocabulary<FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h).  The tree lives
+ * in HBM as one packed blob (so it can be broadcast over NCCL once and shared by every stream of a GPU). */
+typedef struct borb_voc borb_voc;
+/* Nodes in id order, node 0 = root; children keep the order in which they appear (loadFromTextFile :1378-1420). */
+BORB_API borb_status borb_voc_create(const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc, const double* weight,
+                                     int n_nodes, int k, int L, int device, borb_voc** out);
+/* "k L scoring weighting" + one "parent isLeaf d0..d31 weight" line per node (ORBvoc.txt, :1338-1424). */
+BORB_API borb_status borb_voc_load_text(const char* path, int device, borb_voc** out);
+BORB_API borb_status borb_voc_destroy(borb_voc* v);
+/* Device address and size of the packed blob (root rank: source of the NCCL broadcast). */
+BORB_API borb_status borb_voc_blob(const borb_voc* v, void** d_blob, size_t* bytes);
+/* Adopt a packed blob that already sits in this device's memory (receiver side of the broadcast). */
+BORB_API borb_status borb_voc_from_blob(void* d_blob, size_t bytes, int device, borb_voc** out);
+/* TemplatedVocabulary::transform(feature, id, weight, nid, levelsup) for n descriptors (:1218-1259): word id,
+ * word weight and the node id at level L-levelsup per feature.  Frame::ComputeBoW (src/Frame.cc:395-402) builds
+ * mBowVec / mFeatVec from these on the host side of the adapter. */
+BORB_API borb_status borb_bow_transform(borb_voc* v, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight,
+                                        int32_t* node);
 
 /* ---------------------------------------------------------------- introspection -------------- */
 /* Per-stage intermediates of the last batch, for parity tests (tests/ compare each stage with the

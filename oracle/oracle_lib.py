@@ -195,3 +195,151 @@ def port_stereo(kL, dL, kR, dR, pyrL, pyrR, scale, inv_scale, bf, fx):
                        lw.ctypes.data, lh.ctypes.data, nlev, scale.ctypes.data, inv_scale.ctypes.data,
                        float(bf), float(b), ur.ctypes.data, dp.ctypes.data, sad.ctypes.data)
     return ur[:n], dp[:n], sad[:n]
+
+
+# ---------------------------------------------------------------------------------------------- matchers (restatements)
+def _plib():
+    lib = C.CDLL(PORT_SO)
+    lib.orbport_voc_load_text.restype = C.c_void_p
+    lib.orbport_voc_random.restype = C.c_void_p
+    return lib
+
+
+def _a(x, dt):
+    return None if x is None else np.ascontiguousarray(x, dt)
+
+
+def _ptr(x):
+    return None if x is None else C.c_void_p(x.ctypes.data)
+
+
+def port_features_in_area(keys, bounds, x, y, r, min_level, max_level):
+    lib = _plib()
+    keys = _a(keys, KP_DTYPE)
+    out = np.zeros(max(len(keys), 1), np.int32)
+    lib.orbport_features_in_area.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = lib.orbport_features_in_area(_ptr(keys), len(keys), *[float(b) for b in bounds], float(x), float(y), float(r), min_level, max_level,
+                                     _ptr(out), len(out))
+    return out[:n]
+
+
+def port_search_by_projection(F, mps, th, nnratio):
+    """F: orb_slam2_b200.matcher.FrameView-like, mps: MapPointsView-like (duck typed)."""
+    lib = _plib()
+    k = _a(F.mvKeysUn, KP_DTYPE); d = _a(F.mDescriptors, np.uint8); ur = _a(F.mvuRight, np.float32); oc = _a(F.occupied, np.uint8)
+    sf = _a(F.mvScaleFactors, np.float32)
+    px = _a(mps.mTrackProjX, np.float32); py = _a(mps.mTrackProjY, np.float32); pxr = _a(mps.mTrackProjXR, np.float32)
+    lv = _a(mps.mnTrackScaleLevel, np.int32); vc = _a(mps.mTrackViewCos, np.float32); md = _a(mps.descriptors, np.uint8)
+    va = _a(mps.valid, np.uint8); ho = _a(mps.has_obs, np.uint8)
+    match = np.full(max(len(px), 1), -1, np.int32)
+    fn = lib.orbport_search_by_projection
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_float, C.c_float, C.c_void_p]
+    n = fn(_ptr(k), _ptr(d), _ptr(ur), _ptr(oc), len(k), *[float(b) for b in F.bounds], _ptr(sf), len(px), _ptr(px), _ptr(py), _ptr(pxr),
+           _ptr(lv), _ptr(vc), _ptr(md), _ptr(va), _ptr(ho), float(th), float(np.float32(nnratio)), _ptr(match))
+    return n, match[:len(px)]
+
+
+def _kf_args(kf):
+    k = _a(kf.mvKeysUn, KP_DTYPE); d = _a(kf.mDescriptors, np.uint8)
+    hm = _a(kf.has_mp, np.uint8) if kf.has_mp is not None else np.zeros(len(k), np.uint8)
+    nd = _a(kf.mFeatVec.node_id, np.uint32); st = _a(kf.mFeatVec.start, np.int32); fi = _a(kf.mFeatVec.feat_idx, np.uint32)
+    return k, d, hm, nd, st, fi
+
+
+def port_search_by_bow(kf, F, nnratio, check_ori):
+    lib = _plib()
+    k1, d1, hm1, nd1, st1, fi1 = _kf_args(kf)
+    k2, d2, _, nd2, st2, fi2 = _kf_args(F)
+    match = np.full(max(len(k2), 1), -1, np.int32)
+    fn = lib.orbport_search_by_bow_kf_f
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_void_p]
+    n = fn(_ptr(k1), _ptr(d1), _ptr(hm1), len(k1), len(nd1), _ptr(nd1), _ptr(st1), _ptr(fi1), _ptr(k2), _ptr(d2), len(k2), len(nd2),
+           _ptr(nd2), _ptr(st2), _ptr(fi2), float(np.float32(nnratio)), int(check_ori), _ptr(match))
+    return n, match[:len(k2)]
+
+
+def port_search_by_bow_kf(kf1, kf2, nnratio, check_ori):
+    lib = _plib()
+    k1, d1, hm1, nd1, st1, fi1 = _kf_args(kf1)
+    k2, d2, hm2, nd2, st2, fi2 = _kf_args(kf2)
+    match = np.full(max(len(k1), 1), -1, np.int32)
+    fn = lib.orbport_search_by_bow_kf_kf
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 3) * 2 + [C.c_float, C.c_int, C.c_void_p]
+    n = fn(_ptr(k1), _ptr(d1), _ptr(hm1), len(k1), len(nd1), _ptr(nd1), _ptr(st1), _ptr(fi1), _ptr(k2), _ptr(d2), _ptr(hm2), len(k2),
+           len(nd2), _ptr(nd2), _ptr(st2), _ptr(fi2), float(np.float32(nnratio)), int(check_ori), _ptr(match))
+    return n, match[:len(k1)]
+
+
+def port_search_for_triangulation(kf1, kf2, F12, epipole, only_stereo, check_ori):
+    lib = _plib()
+    k1, d1, hm1, nd1, st1, fi1 = _kf_args(kf1)
+    k2, d2, hm2, nd2, st2, fi2 = _kf_args(kf2)
+    ur1 = _a(kf1.mvuRight, np.float32); ur2 = _a(kf2.mvuRight, np.float32)
+    f = _a(np.asarray(F12).reshape(9), np.float32)
+    sf2 = _a(kf2.mvScaleFactors, np.float32); sg2 = _a(kf2.mvLevelSigma2, np.float32)
+    pairs = np.zeros((max(len(k1), 1), 2), np.int32)
+    fn = lib.orbport_search_for_triangulation
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 3) * 2 + [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    n = fn(_ptr(k1), _ptr(d1), _ptr(hm1), _ptr(ur1), len(k1), len(nd1), _ptr(nd1), _ptr(st1), _ptr(fi1), _ptr(k2), _ptr(d2), _ptr(hm2),
+           _ptr(ur2), len(k2), len(nd2), _ptr(nd2), _ptr(st2), _ptr(fi2), _ptr(f), float(epipole[0]), float(epipole[1]), _ptr(sf2), _ptr(sg2),
+           int(only_stereo), int(check_ori), _ptr(pairs))
+    return pairs[:n]
+
+
+class PortVocabulary:
+    """CPU restatement of the DBoW2 tree (text loader, seeded random tree of ORBvoc's shape, transform)."""
+
+    def __init__(self, handle):
+        self._lib = _plib()
+        self._h = C.c_void_p(handle)
+
+    @staticmethod
+    def random(k=10, L=6, seed=7):
+        lib = _plib()
+        lib.orbport_voc_random.argtypes = [C.c_int, C.c_int, C.c_uint]
+        return PortVocabulary(lib.orbport_voc_random(k, L, seed))
+
+    @staticmethod
+    def load_text(path):
+        lib = _plib()
+        lib.orbport_voc_load_text.argtypes = [C.c_char_p]
+        h = lib.orbport_voc_load_text(path.encode())
+        if not h:
+            raise IOError(path)
+        return PortVocabulary(h)
+
+    def export(self):
+        self._lib.orbport_voc_nodes.argtypes = [C.c_void_p]
+        n = self._lib.orbport_voc_nodes(self._h)
+        parent = np.zeros(n, np.int32); leaf = np.zeros(n, np.uint8); word = np.zeros(n, np.int32)
+        desc = np.zeros((n, 32), np.uint8); weight = np.zeros(n, np.float64)
+        k, L = C.c_int(), C.c_int()
+        self._lib.orbport_voc_export.argtypes = [C.c_void_p] * 6 + [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self._lib.orbport_voc_export(self._h, _ptr(parent), _ptr(leaf), _ptr(word), _ptr(desc), _ptr(weight), C.byref(k), C.byref(L))
+        return dict(parent=parent, is_leaf=leaf, word_id=word, desc=desc, weight=weight, k=k.value, L=L.value)
+
+    def save_text(self, path):
+        e = self.export()
+        with open(path, "w") as f:
+            f.write(f"{e['k']} {e['L']} 0 0\n")
+            for i in range(1, len(e["parent"])):
+                f.write(f"{e['parent'][i]} {int(e['is_leaf'][i])} " + " ".join(str(int(b)) for b in e["desc"][i]) + f" {repr(float(e['weight'][i]))}\n")
+
+    def transform_raw(self, desc, levelsup=4):
+        d = _a(desc, np.uint8)
+        n = len(d)
+        word = np.zeros(max(n, 1), np.int32); weight = np.zeros(max(n, 1), np.float64); node = np.zeros(max(n, 1), np.int32)
+        self._lib.orbport_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._lib.orbport_voc_transform(self._h, _ptr(d), n, levelsup, _ptr(word), _ptr(weight), _ptr(node))
+        return word[:n], weight[:n], node[:n]
+
+    def __del__(self):
+        try:
+            self._lib.orbport_voc_free.argtypes = [C.c_void_p]
+            self._lib.orbport_voc_free(self._h)
+        except Exception:
+            pass

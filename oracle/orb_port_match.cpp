@@ -1,0 +1,443 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/orb_prims.h / orb_port.h headers).
+// Line-by-line restatements, on POD arrays, of the matcher side of the hot path:
+//   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea   src/Frame.cc:230-245, 382-392, 327-380
+//   ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) src/ORBmatcher.cc:45-137
+//   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)               src/ORBmatcher.cc:159-288
+//   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)            src/ORBmatcher.cc:522-655
+//   ORBmatcher::SearchForTriangulation                            src/ORBmatcher.cc:657-823, CheckDistEpipolarLine :140-157
+//   ORBmatcher::ComputeThreeMaxima / DescriptorDistance           src/ORBmatcher.cc:1601-1663
+//   TemplatedVocabulary::transform / loadFromTextFile             Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259, 1338-1424
+// ORBmatcher.cc / Frame.cc cannot be compiled on their own (they include the whole type graph), and the
+// reference holds no tests for them: parity for these functions is pinned by these restatements only
+// ("parity unpinned" by the reference itself — SURVEY.md §8c).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "orb_port.h"
+
+namespace {
+constexpr int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;   // include/Frame.h:37-38
+
+struct Grid {
+    float minX, minY, maxX, maxY, invW, invH;
+    std::vector<std::vector<int>> cell;   // [x*ROWS + y], insertion order
+};
+
+Grid build_grid(const orbport_kp* k, int n, float minX, float minY, float maxX, float maxY) {
+    Grid g;
+    g.minX = minX; g.minY = minY; g.maxX = maxX; g.maxY = maxY;
+    g.invW = (float)GRID_COLS / (float)(maxX - minX);     // Frame.cc:101-102
+    g.invH = (float)GRID_ROWS / (float)(maxY - minY);
+    g.cell.assign(GRID_COLS * GRID_ROWS, {});
+    for (int i = 0; i < n; i++) {
+        const int px = (int)std::round((k[i].x - minX) * g.invW);   // PosInGrid :384-385
+        const int py = (int)std::round((k[i].y - minY) * g.invH);
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+        g.cell[px * GRID_ROWS + py].push_back(i);
+    }
+    return g;
+}
+
+std::vector<int> features_in_area(const Grid& g, const orbport_kp* k, float x, float y, float r, int minLevel, int maxLevel) {
+    std::vector<int> out;
+    const int nMinCellX = std::max(0, (int)std::floor((x - g.minX - r) * g.invW));
+    if (nMinCellX >= GRID_COLS) return out;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - g.minX + r) * g.invW));
+    if (nMaxCellX < 0) return out;
+    const int nMinCellY = std::max(0, (int)std::floor((y - g.minY - r) * g.invH));
+    if (nMinCellY >= GRID_ROWS) return out;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - g.minY + r) * g.invH));
+    if (nMaxCellY < 0) return out;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+            for (int idx : g.cell[ix * GRID_ROWS + iy]) {
+                const orbport_kp& kp = k[idx];
+                if (bCheckLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float distx = kp.x - x, disty = kp.y - y;
+                if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(idx);
+            }
+    return out;
+}
+
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+int rot_bin(float a1, float a2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+struct FeatVec { int nn; const uint32_t* node; const int32_t* start; const uint32_t* idx; };
+
+}  // namespace
+
+extern "C" {
+
+int orbport_features_in_area(const orbport_kp* k, int n, float minX, float minY, float maxX, float maxY, float x, float y, float r,
+                             int minLevel, int maxLevel, int32_t* out, int cap) {
+    Grid g = build_grid(k, n, minX, minY, maxX, maxY);
+    std::vector<int> v = features_in_area(g, k, x, y, r, minLevel, maxLevel);
+    for (int i = 0; i < (int)v.size() && i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+// match_feat[iMP] = frame feature index claimed by map point iMP, or -1.  occupied may be NULL.
+int orbport_search_by_projection(const orbport_kp* keys_un, const uint8_t* desc, const float* u_right, const uint8_t* occupied, int N,
+                                 float minX, float minY, float maxX, float maxY, const float* scale_factors, int n_mp,
+                                 const float* proj_x, const float* proj_y, const float* proj_xr, const int32_t* level,
+                                 const float* view_cos, const uint8_t* mp_desc, const uint8_t* mp_valid, const uint8_t* mp_has_obs,
+                                 float th, float nnratio, int32_t* match_feat) {
+    Grid g = build_grid(keys_un, N, minX, minY, maxX, maxY);
+    std::vector<char> held(N, 0);          // F.mvpMapPoints[idx] && Observations()>0
+    for (int i = 0; i < N; i++) held[i] = occupied ? (occupied[i] != 0) : 0;
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    for (int iMP = 0; iMP < n_mp; iMP++) {
+        match_feat[iMP] = -1;
+        if (mp_valid && !mp_valid[iMP]) continue;
+        const int nPredictedLevel = level[iMP];
+        float r = view_cos[iMP] > 0.998 ? 2.5 : 4.0;
+        if (bFactor) r *= th;
+        const std::vector<int> vIndices = features_in_area(g, keys_un, proj_x[iMP], proj_y[iMP], r * scale_factors[nPredictedLevel],
+                                                           nPredictedLevel - 1, nPredictedLevel);
+        if (vIndices.empty()) continue;
+        const uint8_t* MPdescriptor = mp_desc + (size_t)iMP * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (held[idx]) continue;
+            if (u_right && u_right[idx] > 0) {
+                const float er = std::fabs(proj_xr[iMP] - u_right[idx]);
+                if (er > r * scale_factors[nPredictedLevel]) continue;
+            }
+            const int dist = orbport_hamming(MPdescriptor, desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = keys_un[idx].octave; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = keys_un[idx].octave; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            match_feat[iMP] = bestIdx;
+            // F.mvpMapPoints[bestIdx]=pMP: later map points skip it only if pMP->Observations()>0 (:87-89)
+            held[bestIdx] = mp_has_obs ? (mp_has_obs[iMP] != 0) : 1;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+// SearchByBoW(KeyFrame*, Frame&): match_f[F.N] = KF feature whose MapPoint the frame feature received, or -1.
+int orbport_search_by_bow_kf_f(const orbport_kp* kf_keys, const uint8_t* kf_desc, const uint8_t* kf_has_mp, int kf_n, int kf_nn,
+                               const uint32_t* kf_node, const int32_t* kf_start, const uint32_t* kf_idx, const orbport_kp* f_keys,
+                               const uint8_t* f_desc, int f_n, int f_nn, const uint32_t* f_node, const int32_t* f_start,
+                               const uint32_t* f_idx, float nnratio, int check_ori, int32_t* match_f) {
+    (void)kf_n;
+    for (int i = 0; i < f_n; i++) match_f[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < kf_nn && b < f_nn) {
+        if (kf_node[a] == f_node[b]) {
+            for (int iKF = kf_start[a]; iKF < kf_start[a + 1]; iKF++) {
+                const unsigned realIdxKF = kf_idx[iKF];
+                if (!kf_has_mp[realIdxKF]) continue;
+                const uint8_t* dKF = kf_desc + (size_t)realIdxKF * 32;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = f_start[b]; iF < f_start[b + 1]; iF++) {
+                    const unsigned realIdxF = f_idx[iF];
+                    if (match_f[realIdxF] >= 0) continue;
+                    const int dist = orbport_hamming(dKF, f_desc + (size_t)realIdxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        match_f[bestIdxF] = (int)realIdxKF;
+                        if (check_ori) rotHist[rot_bin(kf_keys[realIdxKF].angle, f_keys[bestIdxF].angle)].push_back(bestIdxF);
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (kf_node[a] < f_node[b]) {
+            a = (int)(std::lower_bound(kf_node, kf_node + kf_nn, f_node[b]) - kf_node);
+        } else {
+            b = (int)(std::lower_bound(f_node, f_node + f_nn, kf_node[a]) - f_node);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { match_f[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// SearchByBoW(KeyFrame*, KeyFrame*): match12[kf1.N] = index in KF2 or -1.
+int orbport_search_by_bow_kf_kf(const orbport_kp* k1, const uint8_t* d1, const uint8_t* has_mp1, int n1, int nn1, const uint32_t* node1,
+                                const int32_t* start1, const uint32_t* idx1, const orbport_kp* k2, const uint8_t* d2,
+                                const uint8_t* has_mp2, int n2, int nn2, const uint32_t* node2, const int32_t* start2,
+                                const uint32_t* idx2, float nnratio, int check_ori, int32_t* match12) {
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    std::vector<char> vbMatched2(n2, 0);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (node1[a] == node2[b]) {
+            for (int i1 = start1[a]; i1 < start1[a + 1]; i1++) {
+                const unsigned i = idx1[i1];
+                if (!has_mp1[i]) continue;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = start2[b]; i2 < start2[b + 1]; i2++) {
+                    const unsigned j = idx2[i2];
+                    if (vbMatched2[j] || !has_mp2[j]) continue;
+                    const int dist = orbport_hamming(d1 + (size_t)i * 32, d2 + (size_t)j * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = j; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        match12[i] = bestIdx2;
+                        vbMatched2[bestIdx2] = 1;
+                        if (check_ori) rotHist[rot_bin(k1[i].angle, k2[bestIdx2].angle)].push_back(i);
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (node1[a] < node2[b]) {
+            a = (int)(std::lower_bound(node1, node1 + nn1, node2[b]) - node1);
+        } else {
+            b = (int)(std::lower_bound(node2, node2 + nn2, node1[a]) - node2);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { match12[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// SearchForTriangulation: pairs[2*m] (idx1, idx2) ascending idx1; returns m.  ex,ey: epipole of KF1's centre in KF2
+// (ORBmatcher.cc:663-670, computed by the caller); F12 row-major 3x3; sf2/sigma2_2: KF2's mvScaleFactors / mvLevelSigma2.
+int orbport_search_for_triangulation(const orbport_kp* k1, const uint8_t* d1, const uint8_t* has_mp1, const float* ur1, int n1, int nn1,
+                                     const uint32_t* node1, const int32_t* start1, const uint32_t* idx1, const orbport_kp* k2,
+                                     const uint8_t* d2, const uint8_t* has_mp2, const float* ur2, int n2, int nn2, const uint32_t* node2,
+                                     const int32_t* start2, const uint32_t* idx2, const float* F12, float ex, float ey,
+                                     const float* sf2, const float* sigma2_2, int only_stereo, int check_ori, int32_t* pairs) {
+    (void)n2;
+    int nmatches = 0;
+    std::vector<int> vMatches12(n1, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (node1[a] == node2[b]) {
+            for (int i1 = start1[a]; i1 < start1[a + 1]; i1++) {
+                const unsigned i = idx1[i1];
+                if (has_mp1[i]) continue;
+                const bool bStereo1 = ur1 && ur1[i] >= 0;
+                if (only_stereo && !bStereo1) continue;
+                const orbport_kp& kp1 = k1[i];
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = start2[b]; i2 < start2[b + 1]; i2++) {
+                    const unsigned j = idx2[i2];
+                    if (has_mp2[j]) continue;             // vbMatched2 is never set in the reference (:677,:725)
+                    const bool bStereo2 = ur2 && ur2[j] >= 0;
+                    if (only_stereo && !bStereo2) continue;
+                    const int dist = orbport_hamming(d1 + (size_t)i * 32, d2 + (size_t)j * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const orbport_kp& kp2 = k2[j];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x, distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * sf2[kp2.octave]) continue;
+                    }
+                    // CheckDistEpipolarLine (:140-157)
+                    const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+                    const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+                    const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+                    const float num = la * kp2.x + lb * kp2.y + lc;
+                    const float den = la * la + lb * lb;
+                    if (den == 0) continue;
+                    const float dsqr = num * num / den;
+                    if (dsqr < 3.84 * sigma2_2[kp2.octave]) { bestIdx2 = j; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    vMatches12[i] = bestIdx2;
+                    nmatches++;
+                    if (check_ori) rotHist[rot_bin(kp1.angle, k2[bestIdx2].angle)].push_back(i);
+                }
+            }
+            a++; b++;
+        } else if (node1[a] < node2[b]) {
+            a = (int)(std::lower_bound(node1, node1 + nn1, node2[b]) - node1);
+        } else {
+            b = (int)(std::lower_bound(node2, node2 + nn2, node1[a]) - node2);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { vMatches12[j] = -1; nmatches--; }
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < n1; i++) {
+        if (vMatches12[i] < 0) continue;
+        pairs[2 * m] = i; pairs[2 * m + 1] = vMatches12[i];
+        m++;
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------ vocabulary
+struct OVoc {
+    int k, L;
+    std::vector<int> parent;                 // node 0 = root
+    std::vector<std::vector<int>> children;
+    std::vector<uint8_t> desc;               // nodes x 32
+    std::vector<double> weight;
+    std::vector<int> word_id;                // -1 for inner nodes
+    std::vector<char> leaf;
+};
+
+static void voc_add(OVoc* v, int pid, bool leaf, const uint8_t* d, double w, int& nwords) {
+    const int nid = (int)v->parent.size();
+    v->parent.push_back(pid);
+    v->children.emplace_back();
+    v->children[pid].push_back(nid);
+    v->desc.insert(v->desc.end(), d, d + 32);
+    v->weight.push_back(w);
+    v->leaf.push_back(leaf);
+    v->word_id.push_back(leaf ? nwords++ : -1);
+}
+
+static OVoc* voc_new(int k, int L) {
+    OVoc* v = new OVoc();
+    v->k = k; v->L = L;
+    v->parent.push_back(0); v->children.emplace_back(); v->desc.assign(32, 0); v->weight.push_back(0); v->leaf.push_back(0); v->word_id.push_back(-1);
+    return v;
+}
+
+// Text format of Vocabulary/ORBvoc.txt (TemplatedVocabulary.h:1338-1424): "k L scoring weighting", then one line per
+// node "parent isLeaf d0..d31 weight".  (The reference's `while(!f.eof())` also turns a trailing empty line into a
+// garbage child of the root; that artefact is not reproduced.)
+void* orbport_voc_load_text(const char* path) {
+    // plain C stdio (this library may be linked with a static libstdc++, whose iostreams must not be used from a dlopen'ed .so)
+    FILE* f = std::fopen(path, "r");
+    if (!f) return nullptr;
+    std::vector<char> line(1 << 16);
+    if (!std::fgets(line.data(), (int)line.size(), f)) { std::fclose(f); return nullptr; }
+    int k = -1, L = -1, n1 = -1, n2 = -1;
+    if (std::sscanf(line.data(), "%d %d %d %d", &k, &L, &n1, &n2) != 4 || k < 0 || k > 20 || L < 1 || L > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) {
+        std::fclose(f);
+        return nullptr;
+    }
+    OVoc* v = voc_new(k, L);
+    int nwords = 0;
+    while (std::fgets(line.data(), (int)line.size(), f)) {
+        char* p = line.data();
+        char* end = nullptr;
+        const long pid = std::strtol(p, &end, 10);
+        if (end == p) continue;                       // blank line
+        p = end;
+        const long isLeaf = std::strtol(p, &end, 10); p = end;
+        uint8_t d[32];
+        for (int i = 0; i < 32; i++) { d[i] = (uint8_t)std::strtol(p, &end, 10); p = end; }
+        const double w = std::strtod(p, &end);
+        voc_add(v, (int)pid, isLeaf > 0, d, w, nwords);
+    }
+    std::fclose(f);
+    return v;
+}
+
+// Seeded random tree of ORBvoc's shape (k children per inner node, L levels, leaves at depth L).
+void* orbport_voc_random(int k, int L, unsigned seed) {
+    OVoc* v = voc_new(k, L);
+    std::mt19937 rng(seed);
+    int nwords = 0;
+    std::vector<int> frontier = {0};
+    for (int depth = 1; depth <= L; depth++) {
+        std::vector<int> next;
+        for (int p : frontier)
+            for (int c = 0; c < k; c++) {
+                uint8_t d[32];
+                for (int i = 0; i < 32; i += 4) { uint32_t r = rng(); std::memcpy(d + i, &r, 4); }
+                const double w = depth == L ? 0.5 + (rng() % 100000) / 10000.0 : 0.0;
+                next.push_back((int)v->parent.size());
+                voc_add(v, p, depth == L, d, w, nwords);
+            }
+        frontier.swap(next);
+    }
+    return v;
+}
+
+void orbport_voc_free(void* h) { delete (OVoc*)h; }
+int orbport_voc_nodes(void* h) { return (int)((OVoc*)h)->parent.size(); }
+// flat export (nodes in id order): parent, is_leaf, word_id, descriptor, weight
+void orbport_voc_export(void* h, int32_t* parent, uint8_t* is_leaf, int32_t* word_id, uint8_t* desc, double* weight, int* k, int* L) {
+    OVoc* v = (OVoc*)h;
+    const int n = (int)v->parent.size();
+    for (int i = 0; i < n; i++) { parent[i] = v->parent[i]; is_leaf[i] = v->leaf[i]; word_id[i] = v->word_id[i]; weight[i] = v->weight[i]; }
+    std::memcpy(desc, v->desc.data(), (size_t)n * 32);
+    *k = v->k; *L = v->L;
+}
+
+// transform(feature, word_id, weight, nid, levelsup) for n features (TemplatedVocabulary.h:1218-1259)
+void orbport_voc_transform(void* h, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node) {
+    OVoc* v = (OVoc*)h;
+    const int nid_level = v->L - levelsup;
+    for (int f = 0; f < n; f++) {
+        const uint8_t* feat = desc + (size_t)f * 32;
+        int nid = 0;
+        if (nid_level <= 0) nid = 0;
+        int final_id = 0, current_level = 0;
+        do {
+            ++current_level;
+            const std::vector<int>& nodes = v->children[final_id];
+            final_id = nodes[0];
+            double best_d = orbport_hamming(feat, &v->desc[(size_t)final_id * 32]);
+            for (size_t c = 1; c < nodes.size(); c++) {
+                const double d = orbport_hamming(feat, &v->desc[(size_t)nodes[c] * 32]);
+                if (d < best_d) { best_d = d; final_id = nodes[c]; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (!v->leaf[final_id]);
+        word[f] = v->word_id[final_id];
+        weight[f] = v->weight[final_id];
+        node[f] = nid;
+    }
+}
+
+}  // extern "C"

@@ -68,6 +68,18 @@ _SIGNATURES = {
                                                     C.c_float, vp, vp, vp, vp, C.c_int]),
     "borb_stage_times_total": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "borb_extractor_stream": (C.c_int, [vp, C.POINTER(vp)]),
+    "borb_matcher_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "borb_matcher_destroy": (C.c_int, [vp]),
+    "borb_search_by_projection": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, vp, i32p]),
+    "borb_search_by_bow": (C.c_int, [vp, vp, C.c_int, vp, C.c_float, C.c_int, vp, vp]),
+    "borb_search_by_bow_kf": (C.c_int, [vp, vp, vp, C.c_float, C.c_int, vp, i32p]),
+    "borb_search_for_triangulation": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int, i32p]),
+    "borb_voc_create": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "borb_voc_load_text": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+    "borb_voc_destroy": (C.c_int, [vp]),
+    "borb_voc_blob": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "borb_voc_from_blob": (C.c_int, [vp, C.c_size_t, C.c_int, C.POINTER(vp)]),
+    "borb_bow_transform": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),
     "borb_debug_candidates": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, i32p]),
     "borb_debug_selected": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, i32p]),
     "borb_debug_blurred": (C.c_int, [vp, C.c_int, C.c_int, vp, i32p, i32p]),

@@ -1,0 +1,66 @@
+// Internal declarations for the matcher / vocabulary part of libborb.  Not part of the C ABI.
+#pragma once
+#include "borb_internal.h"
+
+namespace borb {
+
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;     // FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.h:37-38)
+constexpr int GRID_CELLS = GRID_COLS * GRID_ROWS;
+constexpr int MATCH_MAX_FEATURES = 8192;          // per frame / keyframe (grid sort and claim bitsets live in smem)
+
+struct ProjArgs {                 // device pointers
+    int n;                        // frame features
+    const borb_keypoint* keys;
+    const uint8_t* desc;
+    const float* u_right;         // may be null
+    const uint8_t* occupied;      // may be null
+    float minX, minY, invW, invH;
+    const float* scale_factors;
+    const int* cell_start;
+    const int* cell_idx;
+    int n_mp;
+    const float *proj_x, *proj_y, *proj_xr, *view_cos;
+    const int32_t* level;
+    const uint8_t* mp_desc;
+    const uint8_t* mp_valid;      // may be null
+    const uint8_t* mp_has_obs;    // may be null
+    float th, nnratio;
+    uint32_t* cand;               // n_mp x n
+    int* cand_cnt;                // n_mp
+};
+
+struct KfDev {                    // device-side borb_keyframe_view
+    int n, nn;
+    const borb_keypoint* keys;
+    const uint8_t* desc;
+    const uint8_t* has_mp;        // may be null
+    const float* u_right;         // may be null
+    const uint32_t* node;
+    const int32_t* start;
+    const uint32_t* idx;
+    const float* scale_factors;
+    const float* level_sigma2;
+};
+
+struct TriArgs { float F[9]; float ex, ey; int only_stereo, check_ori; };
+
+struct VocDev {                   // views into the packed blob
+    int n_nodes, k, L;
+    const uint8_t* desc;          // n_nodes x 32
+    const double* weight;
+    const int32_t* word_id;       // -1 for inner nodes
+    const int32_t* child_start;   // n_nodes + 1
+    const int32_t* child_ids;     // n_nodes - 1
+};
+
+int launch_grid_sort(const borb_keypoint* keys, int n, float minX, float minY, float invW, float invH, int* cell_start, int* cell_idx,
+                     cudaStream_t s);
+int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s);
+int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
+                     int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s);
+int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,
+                         int32_t* n_pairs, cudaStream_t s);
+int launch_bow_transform(const VocDev& V, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node,
+                         cudaStream_t s);
+
+}  // namespace borb

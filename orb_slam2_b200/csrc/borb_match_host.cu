@@ -1,0 +1,452 @@
+// Host side of the matcher / vocabulary entry points of the C ABI (include/borb.h): snapshots arrive as plain host
+// arrays, are staged into one device arena per call, and every result is produced by the CUDA kernels in k_match.cu.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "borb_match.h"
+
+using namespace borb;
+
+struct borb_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t* arena = nullptr;       // device scratch, grow-only
+    size_t arena_bytes = 0, arena_off = 0;
+    uint8_t* h_stage = nullptr;     // pinned staging mirror of the arena's input part
+    size_t h_bytes = 0;
+    uint64_t launches = 0;
+};
+
+struct borb_voc {
+    int device = 0;
+    bool owns = true;
+    uint8_t* blob = nullptr;        // device
+    size_t bytes = 0;
+    VocDev dev;
+    cudaStream_t stream = nullptr;
+    uint8_t* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace {
+
+struct Stager {
+    // Lays host arrays out in one pinned buffer, then moves them with a single H2D copy; returns device addresses.
+    borb_matcher* m;
+    size_t off = 0;
+    std::vector<std::pair<const void*, std::pair<size_t, size_t>>> items;   // (src, (offset, bytes))
+    explicit Stager(borb_matcher* mm) : m(mm) {}
+    size_t reserve(size_t bytes) { off = (off + 255) & ~size_t(255); size_t o = off; off += bytes; return o; }
+    size_t add(const void* src, size_t bytes) {
+        const size_t o = reserve(bytes);
+        items.push_back({src, {o, bytes}});
+        return o;
+    }
+};
+
+borb_status ensure_arena(borb_matcher* m, size_t bytes) {
+    if (m->arena_bytes >= bytes) return BORB_OK;
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    cudaFree(m->arena);
+    m->arena = nullptr; m->arena_bytes = 0;
+    const size_t want = bytes + bytes / 2 + (1 << 20);
+    BORB_CUDA(cudaMalloc(&m->arena, want));
+    m->arena_bytes = want;
+    return BORB_OK;
+}
+borb_status ensure_host(borb_matcher* m, size_t bytes) {
+    if (m->h_bytes >= bytes) return BORB_OK;
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->h_stage) cudaFreeHost(m->h_stage);
+    m->h_stage = nullptr; m->h_bytes = 0;
+    const size_t want = bytes + bytes / 2 + (1 << 16);
+    BORB_CUDA(cudaMallocHost(&m->h_stage, want));
+    m->h_bytes = want;
+    return BORB_OK;
+}
+
+// copies the staged inputs; `extra` = device-only scratch bytes requested after the inputs
+borb_status commit(Stager& st, size_t total_with_scratch) {
+    borb_matcher* m = st.m;
+    borb_status s = ensure_host(m, st.off);
+    if (s != BORB_OK) return s;
+    if ((s = ensure_arena(m, total_with_scratch)) != BORB_OK) return s;
+    BORB_CUDA(cudaStreamSynchronize(m->stream));     // the staging buffer may still feed an earlier copy
+    for (auto& it : st.items)
+        if (it.first) std::memcpy(m->h_stage + it.second.first, it.first, it.second.second);
+    if (st.off) BORB_CUDA(cudaMemcpyAsync(m->arena, m->h_stage, st.off, cudaMemcpyHostToDevice, m->stream));
+    return BORB_OK;
+}
+
+struct KfOffsets { size_t keys, desc, has_mp, u_right, node, start, idx, sf, sig; bool has_mp_p, ur_p; };
+
+borb_status check_kf(const borb_keyframe_view* v, const char* what) {
+    if (!v || v->n < 0 || v->n > MATCH_MAX_FEATURES || (v->n > 0 && (!v->keys_un || !v->desc))) {
+        set_error("%s: bad keyframe view (n=%d, limit %d)", what, v ? v->n : -1, MATCH_MAX_FEATURES);
+        return BORB_ERR_INVALID_ARG;
+    }
+    if (v->fv.n_nodes < 0 || (v->fv.n_nodes > 0 && (!v->fv.node_id || !v->fv.start || !v->fv.feat_idx))) {
+        set_error("%s: bad feature vector", what);
+        return BORB_ERR_INVALID_ARG;
+    }
+    return BORB_OK;
+}
+
+KfOffsets stage_kf(Stager& st, const borb_keyframe_view* v) {
+    KfOffsets o{};
+    o.keys = st.add(v->keys_un, (size_t)v->n * sizeof(borb_keypoint));
+    o.desc = st.add(v->desc, (size_t)v->n * 32);
+    o.has_mp_p = v->has_mp != nullptr;
+    o.has_mp = o.has_mp_p ? st.add(v->has_mp, (size_t)v->n) : 0;
+    o.ur_p = v->u_right != nullptr;
+    o.u_right = o.ur_p ? st.add(v->u_right, (size_t)v->n * 4) : 0;
+    o.node = st.add(v->fv.node_id, (size_t)v->fv.n_nodes * 4);
+    o.start = st.add(v->fv.start, (size_t)(v->fv.n_nodes + 1) * 4);
+    const int total = v->fv.n_nodes > 0 ? v->fv.start[v->fv.n_nodes] : 0;
+    o.idx = st.add(v->fv.feat_idx, (size_t)total * 4);
+    o.sf = st.add(v->scale_factors, (size_t)(v->scale_factors ? v->n_levels : 0) * 4);
+    o.sig = st.add(v->level_sigma2, (size_t)(v->level_sigma2 ? v->n_levels : 0) * 4);
+    return o;
+}
+
+KfDev kf_dev(const borb_matcher* m, const borb_keyframe_view* v, const KfOffsets& o) {
+    KfDev d;
+    uint8_t* b = m->arena;
+    d.n = v->n; d.nn = v->fv.n_nodes;
+    d.keys = reinterpret_cast<const borb_keypoint*>(b + o.keys);
+    d.desc = b + o.desc;
+    d.has_mp = o.has_mp_p ? b + o.has_mp : nullptr;
+    d.u_right = o.ur_p ? reinterpret_cast<const float*>(b + o.u_right) : nullptr;
+    d.node = reinterpret_cast<const uint32_t*>(b + o.node);
+    d.start = reinterpret_cast<const int32_t*>(b + o.start);
+    d.idx = reinterpret_cast<const uint32_t*>(b + o.idx);
+    d.scale_factors = reinterpret_cast<const float*>(b + o.sf);
+    d.level_sigma2 = reinterpret_cast<const float*>(b + o.sig);
+    return d;
+}
+
+// packed vocabulary blob: header {magic, n_nodes, k, L, offsets...} followed by 256-byte aligned sections
+struct VocHeader { uint32_t magic; int32_t n_nodes, k, L; uint64_t off_desc, off_weight, off_word, off_cstart, off_cids, bytes; };
+constexpr uint32_t VOC_MAGIC = 0x42564f43u;   // "BVOC"
+
+void voc_views(borb_voc* v, const VocHeader& h) {
+    v->dev.n_nodes = h.n_nodes; v->dev.k = h.k; v->dev.L = h.L;
+    v->dev.desc = v->blob + h.off_desc;
+    v->dev.weight = reinterpret_cast<const double*>(v->blob + h.off_weight);
+    v->dev.word_id = reinterpret_cast<const int32_t*>(v->blob + h.off_word);
+    v->dev.child_start = reinterpret_cast<const int32_t*>(v->blob + h.off_cstart);
+    v->dev.child_ids = reinterpret_cast<const int32_t*>(v->blob + h.off_cids);
+}
+
+}  // namespace
+
+extern "C" {
+
+borb_status borb_matcher_create(int device, borb_matcher** out) {
+    if (!out) return BORB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    borb_status st = borb_device_count(&ndev);
+    if (st != BORB_OK) return st;
+    if (ndev < 1) { set_error("no CUDA device visible; libborb has no CPU fallback"); return BORB_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return BORB_ERR_INVALID_ARG; }
+    borb_matcher* m = new borb_matcher();
+    m->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("CUDA init failed: %s", cudaGetErrorString(e)); delete m; return BORB_ERR_CUDA; }
+    *out = m;
+    return BORB_OK;
+}
+
+borb_status borb_matcher_destroy(borb_matcher* m) {
+    if (!m) return BORB_OK;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    cudaFree(m->arena);
+    if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return BORB_OK;
+}
+
+borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F, const borb_mappoint_view* P, float th, float nnratio,
+                                      int32_t* match_feat, int32_t* n_matches) {
+    if (!m || !F || !P || !match_feat || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *n_matches = 0;
+    if (F->n < 0 || F->n > MATCH_MAX_FEATURES || P->n < 0) { set_error("frame has %d features (limit %d)", F->n, MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    if (P->n == 0) return BORB_OK;
+    if (F->n == 0) { for (int i = 0; i < P->n; i++) match_feat[i] = -1; return BORB_OK; }
+    if (!F->keys_un || !F->desc || !F->scale_factors || !P->proj_x || !P->proj_y || !P->proj_xr || !P->level || !P->view_cos || !P->desc ||
+        !(F->max_x > F->min_x) || !(F->max_y > F->min_y)) { set_error("incomplete frame / map point view"); return BORB_ERR_INVALID_ARG; }
+    for (int i = 0; i < P->n; i++)
+        if ((!P->valid || P->valid[i]) && (P->level[i] < 0 || P->level[i] >= F->n_levels)) { set_error("map point %d: predicted level out of range", i); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(m->device));
+    Stager st(m);
+    const size_t o_keys = st.add(F->keys_un, (size_t)F->n * sizeof(borb_keypoint));
+    const size_t o_desc = st.add(F->desc, (size_t)F->n * 32);
+    const size_t o_ur = F->u_right ? st.add(F->u_right, (size_t)F->n * 4) : 0;
+    const size_t o_occ = F->occupied ? st.add(F->occupied, (size_t)F->n) : 0;
+    const size_t o_sf = st.add(F->scale_factors, (size_t)F->n_levels * 4);
+    const size_t o_px = st.add(P->proj_x, (size_t)P->n * 4), o_py = st.add(P->proj_y, (size_t)P->n * 4), o_pxr = st.add(P->proj_xr, (size_t)P->n * 4);
+    const size_t o_lvl = st.add(P->level, (size_t)P->n * 4), o_vc = st.add(P->view_cos, (size_t)P->n * 4);
+    const size_t o_md = st.add(P->desc, (size_t)P->n * 32);
+    const size_t o_val = P->valid ? st.add(P->valid, (size_t)P->n) : 0;
+    const size_t o_obs = P->has_obs ? st.add(P->has_obs, (size_t)P->n) : 0;
+    // device-only scratch
+    const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
+    const size_t o_cand = st.reserve((size_t)P->n * F->n * 4), o_cc = st.reserve((size_t)P->n * 4);
+    const size_t o_match = st.reserve((size_t)P->n * 4), o_nm = st.reserve(16);
+    const size_t input_end = o_cs;
+    const size_t total = st.off;
+    st.off = input_end;
+    borb_status s = commit(st, total);
+    if (s != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    ProjArgs A;
+    A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
+    A.u_right = F->u_right ? (const float*)(b + o_ur) : nullptr;
+    A.occupied = F->occupied ? b + o_occ : nullptr;
+    A.minX = F->min_x; A.minY = F->min_y;
+    A.invW = (float)GRID_COLS / (float)(F->max_x - F->min_x);      // mfGridElementWidthInv (Frame.cc:101)
+    A.invH = (float)GRID_ROWS / (float)(F->max_y - F->min_y);
+    A.scale_factors = (const float*)(b + o_sf);
+    A.cell_start = (const int*)(b + o_cs); A.cell_idx = (const int*)(b + o_ci);
+    A.n_mp = P->n; A.proj_x = (const float*)(b + o_px); A.proj_y = (const float*)(b + o_py); A.proj_xr = (const float*)(b + o_pxr);
+    A.view_cos = (const float*)(b + o_vc); A.level = (const int32_t*)(b + o_lvl); A.mp_desc = b + o_md;
+    A.mp_valid = P->valid ? b + o_val : nullptr; A.mp_has_obs = P->has_obs ? b + o_obs : nullptr;
+    A.th = th; A.nnratio = nnratio;
+    A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
+    m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
+    m->launches += launch_projection(A, (int32_t*)(b + o_match), (int*)(b + o_nm), m->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaMemcpyAsync(match_feat, b + o_match, (size_t)P->n * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    return BORB_OK;
+}
+
+static borb_status bow_common(borb_matcher* m, const borb_keyframe_view* qs, int n_q, const borb_keyframe_view* t, int mode, float nnratio,
+                              int check_ori, int32_t* match, int32_t* n_matches) {
+    // mode 0: qs[0..n_q) keyframes vs ONE frame t, out stride t->n.   mode 1: n_q == 1, q = kf1, t = kf2, out stride q->n.
+    BORB_CUDA(cudaSetDevice(m->device));
+    Stager st(m);
+    std::vector<KfOffsets> qo(n_q);
+    for (int i = 0; i < n_q; i++) qo[i] = stage_kf(st, &qs[i]);
+    const KfOffsets to = stage_kf(st, t);
+    const size_t o_qd = st.reserve((size_t)n_q * sizeof(KfDev)), o_td = st.reserve(sizeof(KfDev));
+    const size_t input_end = st.off;
+    const int out_stride = mode == 0 ? t->n : qs[0].n;
+    const size_t o_match = st.reserve((size_t)n_q * (out_stride > 0 ? out_stride : 1) * 4);
+    const size_t o_bins = st.reserve((size_t)n_q * (out_stride > 0 ? out_stride : 1));
+    const size_t o_nm = st.reserve((size_t)n_q * 4);
+    const size_t total = st.off;
+    st.off = input_end;
+    // the KfDev tables are part of the staged input: fill them in the staging buffer after the layout is known
+    borb_status s = ensure_arena(m, total);
+    if (s != BORB_OK) return s;
+    std::vector<KfDev> qd(n_q);
+    for (int i = 0; i < n_q; i++) qd[i] = kf_dev(m, &qs[i], qo[i]);
+    const KfDev td = kf_dev(m, t, to);
+    st.items.push_back({qd.data(), {o_qd, (size_t)n_q * sizeof(KfDev)}});
+    st.items.push_back({&td, {o_td, sizeof(KfDev)}});
+    if ((s = commit(st, total)) != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    m->launches += launch_bow_match((const KfDev*)(b + o_qd), (const KfDev*)(b + o_td), n_q, mode, nnratio, check_ori, (int32_t*)(b + o_match),
+                                    out_stride, b + o_bins, (int32_t*)(b + o_nm), t->n, m->stream);
+    BORB_CUDA(cudaGetLastError());
+    if (out_stride > 0) BORB_CUDA(cudaMemcpyAsync(match, b + o_match, (size_t)n_q * out_stride * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, (size_t)n_q * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    return BORB_OK;
+}
+
+borb_status borb_search_by_bow(borb_matcher* m, const borb_keyframe_view* kfs, int n_kf, const borb_keyframe_view* frame, float nnratio,
+                               int check_orientation, int32_t* match, int32_t* n_matches) {
+    if (!m || !frame || !match || !n_matches || n_kf < 0 || (n_kf > 0 && !kfs)) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    borb_status s = check_kf(frame, "borb_search_by_bow(frame)");
+    for (int i = 0; i < n_kf && s == BORB_OK; i++) s = check_kf(&kfs[i], "borb_search_by_bow(keyframe)");
+    if (s != BORB_OK) return s;
+    if (n_kf == 0) return BORB_OK;
+    return bow_common(m, kfs, n_kf, frame, 0, nnratio, check_orientation, match, n_matches);
+}
+
+borb_status borb_search_by_bow_kf(borb_matcher* m, const borb_keyframe_view* kf1, const borb_keyframe_view* kf2, float nnratio,
+                                  int check_orientation, int32_t* match12, int32_t* n_matches) {
+    if (!m || !kf1 || !kf2 || !match12 || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    borb_status s = check_kf(kf1, "borb_search_by_bow_kf(kf1)");
+    if (s == BORB_OK) s = check_kf(kf2, "borb_search_by_bow_kf(kf2)");
+    if (s != BORB_OK) return s;
+    return bow_common(m, kf1, 1, kf2, 1, nnratio, check_orientation, match12, n_matches);
+}
+
+borb_status borb_search_for_triangulation(borb_matcher* m, const borb_keyframe_view* kf1, const borb_keyframe_view* kf2, const float* F12,
+                                          float ex, float ey, int only_stereo, int check_orientation, int32_t* pairs, int cap,
+                                          int32_t* n_pairs) {
+    if (!m || !kf1 || !kf2 || !F12 || !pairs || !n_pairs || cap < 0) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    borb_status s = check_kf(kf1, "borb_search_for_triangulation(kf1)");
+    if (s == BORB_OK) s = check_kf(kf2, "borb_search_for_triangulation(kf2)");
+    if (s != BORB_OK) return s;
+    if (!kf2->scale_factors || !kf2->level_sigma2) { set_error("kf2 needs scale_factors and level_sigma2"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(m->device));
+    Stager st(m);
+    const KfOffsets o1 = stage_kf(st, kf1), o2 = stage_kf(st, kf2);
+    const size_t input_end = st.off;
+    const int n1 = kf1->n > 0 ? kf1->n : 1;
+    const size_t o_vm = st.reserve((size_t)n1 * 4), o_bins = st.reserve((size_t)n1), o_pairs = st.reserve((size_t)n1 * 8), o_np = st.reserve(16);
+    const size_t total = st.off;
+    st.off = input_end;
+    if ((s = commit(st, total)) != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    TriArgs T;
+    for (int i = 0; i < 9; i++) T.F[i] = F12[i];
+    T.ex = ex; T.ey = ey; T.only_stereo = only_stereo; T.check_ori = check_orientation;
+    m->launches += launch_triangulation(kf_dev(m, kf1, o1), kf_dev(m, kf2, o2), T, (int32_t*)(b + o_vm), b + o_bins, (int32_t*)(b + o_pairs), n1,
+                                        (int32_t*)(b + o_np), m->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaMemcpyAsync(n_pairs, b + o_np, 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    const int np = *n_pairs < cap ? *n_pairs : cap;
+    if (np > 0) BORB_CUDA(cudaMemcpy(pairs, b + o_pairs, (size_t)np * 8, cudaMemcpyDeviceToHost));
+    if (*n_pairs > cap) { set_error("%d pairs, capacity %d", *n_pairs, cap); return BORB_ERR_CAPACITY; }
+    return BORB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ vocabulary
+borb_status borb_voc_create(const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc, const double* weight, int n_nodes, int k,
+                            int L, int device, borb_voc** out) {
+    if (!parent || !is_leaf || !desc || !weight || !out || n_nodes < 2) { set_error("bad vocabulary arrays"); return BORB_ERR_INVALID_ARG; }
+    *out = nullptr;
+    for (int i = 1; i < n_nodes; i++)
+        if (parent[i] < 0 || parent[i] >= i) { set_error("node %d: parent %d must precede it", i, parent[i]); return BORB_ERR_INVALID_ARG; }
+    int ndev = 0;
+    borb_status s = borb_device_count(&ndev);
+    if (s != BORB_OK) return s;
+    if (device < 0 || device >= ndev) { set_error("device %d out of range", device); return ndev < 1 ? BORB_ERR_NO_DEVICE : BORB_ERR_INVALID_ARG; }
+    // children in order of appearance; word ids in order of leaf appearance (loadFromTextFile :1378-1420)
+    std::vector<int32_t> cstart(n_nodes + 1, 0), cids(n_nodes > 1 ? n_nodes - 1 : 0), word(n_nodes, -1);
+    for (int i = 1; i < n_nodes; i++) cstart[parent[i] + 1]++;
+    for (int i = 0; i < n_nodes; i++) cstart[i + 1] += cstart[i];
+    std::vector<int32_t> fill(cstart.begin(), cstart.end() - 1);
+    for (int i = 1; i < n_nodes; i++) cids[fill[parent[i]]++] = i;
+    int nw = 0;
+    for (int i = 1; i < n_nodes; i++) if (is_leaf[i]) word[i] = nw++;
+    VocHeader h{};
+    h.magic = VOC_MAGIC; h.n_nodes = n_nodes; h.k = k; h.L = L;
+    size_t off = 256;
+    auto sec = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    h.off_desc = sec((size_t)n_nodes * 32); h.off_weight = sec((size_t)n_nodes * 8); h.off_word = sec((size_t)n_nodes * 4);
+    h.off_cstart = sec((size_t)(n_nodes + 1) * 4); h.off_cids = sec((size_t)(n_nodes > 1 ? n_nodes - 1 : 1) * 4);
+    h.bytes = off;
+    std::vector<uint8_t> host(off, 0);
+    std::memcpy(host.data(), &h, sizeof(h));
+    std::memcpy(host.data() + h.off_desc, desc, (size_t)n_nodes * 32);
+    std::memcpy(host.data() + h.off_weight, weight, (size_t)n_nodes * 8);
+    std::memcpy(host.data() + h.off_word, word.data(), (size_t)n_nodes * 4);
+    std::memcpy(host.data() + h.off_cstart, cstart.data(), (size_t)(n_nodes + 1) * 4);
+    if (n_nodes > 1) std::memcpy(host.data() + h.off_cids, cids.data(), (size_t)(n_nodes - 1) * 4);
+    borb_voc* v = new borb_voc();
+    v->device = device; v->bytes = off;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&v->blob, off);
+    if (e == cudaSuccess) e = cudaMemcpy(v->blob, host.data(), off, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("vocabulary upload failed: %s", cudaGetErrorString(e)); cudaFree(v->blob); delete v; return BORB_ERR_CUDA; }
+    voc_views(v, h);
+    *out = v;
+    return BORB_OK;
+}
+
+borb_status borb_voc_load_text(const char* path, int device, borb_voc** out) {
+    if (!path || !out) return BORB_ERR_INVALID_ARG;
+    FILE* f = std::fopen(path, "r");
+    if (!f) { set_error("cannot open %s", path); return BORB_ERR_INVALID_ARG; }
+    std::vector<char> line(1 << 16);
+    int k = -1, L = -1, n1 = -1, n2 = -1;
+    if (!std::fgets(line.data(), (int)line.size(), f) || std::sscanf(line.data(), "%d %d %d %d", &k, &L, &n1, &n2) != 4 || k < 0 || k > 20 ||
+        L < 1 || L > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) {
+        std::fclose(f);
+        set_error("%s is not a vocabulary text file", path);
+        return BORB_ERR_INVALID_ARG;
+    }
+    std::vector<int32_t> parent(1, 0);
+    std::vector<uint8_t> leaf(1, 0), desc(32, 0);
+    std::vector<double> weight(1, 0.0);
+    while (std::fgets(line.data(), (int)line.size(), f)) {
+        char* p = line.data();
+        char* end = nullptr;
+        const long pid = std::strtol(p, &end, 10);
+        if (end == p) continue;     // blank line (the reference's eof loop turns a trailing blank line into a garbage node)
+        p = end;
+        const long isLeaf = std::strtol(p, &end, 10); p = end;
+        uint8_t d[32];
+        for (int i = 0; i < 32; i++) { d[i] = (uint8_t)std::strtol(p, &end, 10); p = end; }
+        const double w = std::strtod(p, &end);
+        parent.push_back((int32_t)pid); leaf.push_back(isLeaf > 0); weight.push_back(w);
+        desc.insert(desc.end(), d, d + 32);
+    }
+    std::fclose(f);
+    return borb_voc_create(parent.data(), leaf.data(), desc.data(), weight.data(), (int)parent.size(), k, L, device, out);
+}
+
+borb_status borb_voc_destroy(borb_voc* v) {
+    if (!v) return BORB_OK;
+    cudaSetDevice(v->device);
+    if (v->stream) cudaStreamSynchronize(v->stream);
+    if (v->owns) cudaFree(v->blob);
+    cudaFree(v->scratch);
+    if (v->stream) cudaStreamDestroy(v->stream);
+    delete v;
+    return BORB_OK;
+}
+
+borb_status borb_voc_blob(const borb_voc* v, void** d_blob, size_t* bytes) {
+    if (!v || !d_blob || !bytes) return BORB_ERR_INVALID_ARG;
+    *d_blob = v->blob; *bytes = v->bytes;
+    return BORB_OK;
+}
+
+borb_status borb_voc_from_blob(void* d_blob, size_t bytes, int device, borb_voc** out) {
+    if (!d_blob || !out || bytes < sizeof(VocHeader)) return BORB_ERR_INVALID_ARG;
+    *out = nullptr;
+    BORB_CUDA(cudaSetDevice(device));
+    VocHeader h;
+    BORB_CUDA(cudaMemcpy(&h, d_blob, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h.magic != VOC_MAGIC || h.bytes != bytes) { set_error("not a packed vocabulary blob"); return BORB_ERR_INVALID_ARG; }
+    borb_voc* v = new borb_voc();
+    v->device = device; v->owns = false; v->blob = (uint8_t*)d_blob; v->bytes = bytes;
+    cudaError_t e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("stream: %s", cudaGetErrorString(e)); delete v; return BORB_ERR_CUDA; }
+    voc_views(v, h);
+    *out = v;
+    return BORB_OK;
+}
+
+borb_status borb_bow_transform(borb_voc* v, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node) {
+    if (!v || n < 0 || (n > 0 && (!desc || !word || !weight || !node))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (n == 0) return BORB_OK;
+    BORB_CUDA(cudaSetDevice(v->device));
+    const size_t need = (size_t)n * (32 + 4 + 8 + 4) + 1024;
+    if (v->scratch_bytes < need) {
+        BORB_CUDA(cudaStreamSynchronize(v->stream));
+        cudaFree(v->scratch); v->scratch = nullptr; v->scratch_bytes = 0;
+        BORB_CUDA(cudaMalloc(&v->scratch, need * 2));
+        v->scratch_bytes = need * 2;
+    }
+    uint8_t* d_desc = v->scratch;
+    double* d_w = (double*)(v->scratch + (((size_t)n * 32 + 255) & ~size_t(255)));
+    int32_t* d_word = (int32_t*)(d_w + n);
+    int32_t* d_node = d_word + n;
+    BORB_CUDA(cudaMemcpyAsync(d_desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
+    launch_bow_transform(v->dev, d_desc, n, levelsup, d_word, d_w, d_node, v->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaMemcpyAsync(word, d_word, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    BORB_CUDA(cudaMemcpyAsync(weight, d_w, (size_t)n * 8, cudaMemcpyDeviceToHost, v->stream));
+    BORB_CUDA(cudaMemcpyAsync(node, d_node, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    BORB_CUDA(cudaStreamSynchronize(v->stream));
+    return BORB_OK;
+}
+
+}  // extern "C"

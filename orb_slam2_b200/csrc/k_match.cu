@@ -1,0 +1,464 @@
+// Hamming-distance matchers of the ORB front-end (reference src/ORBmatcher.cc) and the BoW feeder.
+//
+//   grid_sort_kernel + proj_candidates_kernel + proj_resolve_kernel
+//       Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc:230-245, 327-392) and
+//       ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129).
+//       Candidate enumeration and the 256-bit distances are parallel (a warp per map point, candidates kept in
+//       the reference's (ix, iy, insertion) order); the order-dependent part — a feature claimed by an earlier
+//       map point is skipped by later ones (:87-89,:123) — is replayed exactly by one warp walking the map
+//       points in order over the precomputed lists.  best/second-best of the reference's scan ==
+//       lexicographic minimum / second minimum of (distance, list position).
+//   bow_match_kernel      SearchByBoW(KeyFrame*,Frame&) (:159-288) and SearchByBoW(KeyFrame*,KeyFrame*) (:522-655):
+//       one warp per (keyframe, frame) pair walks the keyframe's FeatureVector in order (the greedy "already
+//       claimed" skip is sequential, :209/:576) with the inner candidate loop spread over the 32 lanes
+//       (8 x __popc per candidate, warp-shuffle argmin); rotation-histogram cull (:267-285) at the end.
+//   triangulation_kernel  SearchForTriangulation (:657-823): no sequential dependence (vbMatched2 is never set in
+//       the reference), "dist<=bestDist, later wins" == min over (distance, -position); epipolar tests as :140-157.
+//   bow_transform_kernel  TemplatedVocabulary::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259):
+//       a warp per descriptor descends the tree, lanes = children, first-wins argmin.
+// All float tests use _rn intrinsics (no FMA contraction) so comparisons match the reference bit for bit.
+//
+// Bound: latency / POPC issue (15 thread-ops/clk/SM measured); the batch (map points, keyframes) supplies parallelism.
+#include "borb_match.h"
+
+namespace borb {
+
+namespace {
+
+constexpr int HISTO_LENGTH = 30;
+
+__device__ __forceinline__ int ham_words(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b) {
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d += __popc(a[i] ^ b[i]);
+    return d;
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2) {
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / HISTO_LENGTH));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// ORBmatcher::ComputeThreeMaxima (:1601-1642) on bin counts
+__device__ void three_maxima(const int* cnt, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+        const int s = cnt[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+__device__ __forceinline__ unsigned warp_min(unsigned v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, off));
+    return v;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ grid
+// One CTA: sorts (cell, feature index) keys in shared memory; writes cell_start[GRID_CELLS+1] and cell_idx[] in
+// (cell, insertion) order — the layout of Frame::mGrid[x][y] (cell = x*48 + y).
+__global__ void __launch_bounds__(1024) grid_sort_kernel(const borb_keypoint* __restrict__ keys, int n, float minX, float minY,
+                                                         float invW, float invH, int K, int* __restrict__ cell_start,
+                                                         int* __restrict__ cell_idx) {
+    extern __shared__ uint32_t skeys[];
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int i = tid; i < K; i += T) {
+        uint32_t key = 0xFFFFFFFFu;
+        if (i < n) {
+            const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, minX), invW));   // PosInGrid (Frame.cc:384-385)
+            const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, minY), invH));
+            if (px >= 0 && px < GRID_COLS && py >= 0 && py < GRID_ROWS) key = ((uint32_t)(px * GRID_ROWS + py) << 16) | (uint32_t)i;
+        }
+        skeys[i] = key;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= K; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < K; i += T) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool asc = (i & kk) == 0;
+                    const uint32_t a = skeys[i], b = skeys[ixj];
+                    if ((a > b) == asc) { skeys[i] = b; skeys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int r = tid; r < K; r += T) {
+        const uint32_t key = skeys[r];
+        const int cell = key == 0xFFFFFFFFu ? GRID_CELLS : (int)(key >> 16);
+        const int prev = r == 0 ? -1 : (skeys[r - 1] == 0xFFFFFFFFu ? GRID_CELLS : (int)(skeys[r - 1] >> 16));
+        if (key != 0xFFFFFFFFu) cell_idx[r] = (int)(key & 0xFFFFu);
+        for (int c = prev + 1; c <= cell && c <= GRID_CELLS; c++) cell_start[c] = r;
+        if (r == K - 1 && cell < GRID_CELLS)
+            for (int c = cell + 1; c <= GRID_CELLS; c++) cell_start[c] = K;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ projection
+// cand entry: idx | dist << 16 | octave << 25
+__global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int iMP = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (iMP >= A.n_mp) return;
+    uint32_t* out = A.cand + (size_t)iMP * A.n;
+    int count = 0;
+    if (A.mp_valid == nullptr || A.mp_valid[iMP]) {
+        const int lvl = A.level[iMP];
+        float r = A.view_cos[iMP] > 0.998 ? 2.5f : 4.0f;     // RadiusByViewingCos (:131-137)
+        if (A.th != 1.0f) r = __fmul_rn(r, A.th);
+        const float rs = __fmul_rn(r, A.scale_factors[lvl]);
+        const float x = A.proj_x[iMP], y = A.proj_y[iMP];
+        // GetFeaturesInArea(x, y, rs, lvl-1, lvl)  (Frame.cc:327-380)
+        const int c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, A.minX), rs), A.invW)));
+        const int c1x = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, A.minX), rs), A.invW)));
+        const int c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, A.minY), rs), A.invH)));
+        const int c1y = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, A.minY), rs), A.invH)));
+        if (!(c0x >= GRID_COLS || c1x < 0 || c0y >= GRID_ROWS || c1y < 0)) {
+            const int minLevel = lvl - 1, maxLevel = lvl;
+            const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+            const uint32_t* dm = reinterpret_cast<const uint32_t*>(A.mp_desc + (size_t)iMP * 32);
+            const float xr = A.proj_xr[iMP];
+            for (int ix = c0x; ix <= c1x; ix++)
+                for (int iy = c0y; iy <= c1y; iy++) {
+                    const int cell = ix * GRID_ROWS + iy;
+                    const int s0 = A.cell_start[cell], s1 = A.cell_start[cell + 1];
+                    for (int base = s0; base < s1; base += 32) {
+                        const int e = base + lane;
+                        bool ok = false;
+                        uint32_t entry = 0;
+                        if (e < s1) {
+                            const int idx = A.cell_idx[e];
+                            const borb_keypoint kp = A.keys[idx];
+                            ok = true;
+                            if (bCheckLevels) {
+                                if (kp.octave < minLevel) ok = false;
+                                if (maxLevel >= 0 && kp.octave > maxLevel) ok = false;
+                            }
+                            if (ok) {
+                                const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+                                ok = fabsf(dx) < rs && fabsf(dy) < rs;
+                            }
+                            if (ok && A.u_right != nullptr) {            // stereo consistency (:91-96)
+                                const float ur = A.u_right[idx];
+                                if (ur > 0) {
+                                    const float er = fabsf(__fsub_rn(xr, ur));
+                                    if (er > rs) ok = false;
+                                }
+                            }
+                            if (ok) {
+                                const int dist = ham_words(dm, reinterpret_cast<const uint32_t*>(A.desc + (size_t)idx * 32));
+                                entry = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)kp.octave << 25);
+                            }
+                        }
+                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+                        if (ok) out[count + __popc(bal & ((1u << lane) - 1))] = entry;
+                        count += __popc(bal);
+                    }
+                }
+        }
+    }
+    if (lane == 0) A.cand_cnt[iMP] = count;
+}
+
+// One warp replays the map points in order (the occupancy skip is order dependent).
+__global__ void __launch_bounds__(32) proj_resolve_kernel(ProjArgs A, int32_t* __restrict__ match_feat, int* __restrict__ n_matches) {
+    extern __shared__ uint32_t held[];       // bit per frame feature: holds a MapPoint with observations
+    const int lane = threadIdx.x;
+    const int words = (A.n + 31) / 32;
+    for (int w = lane; w < words; w += 32) {
+        uint32_t bits = 0;
+        if (A.occupied != nullptr)
+            for (int b = 0; b < 32; b++) {
+                const int i = w * 32 + b;
+                if (i < A.n && A.occupied[i]) bits |= 1u << b;
+            }
+        held[w] = bits;
+    }
+    __syncwarp();
+    int nm = 0;
+    for (int iMP = 0; iMP < A.n_mp; iMP++) {
+        const int cnt = A.cand_cnt[iMP];
+        const uint32_t* c = A.cand + (size_t)iMP * A.n;
+        // per lane: two smallest keys (dist << 16 | position) among its unheld candidates
+        unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        for (int p = lane; p < cnt; p += 32) {
+            const uint32_t e = c[p];
+            const int idx = e & 0xFFFF;
+            if ((held[idx >> 5] >> (idx & 31)) & 1u) continue;
+            const unsigned key = (((e >> 16) & 0x1FFu) << 16) | (unsigned)p;
+            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+        }
+        const unsigned best = warp_min(k1);
+        const unsigned second = warp_min(k1 == best ? k2 : k1);
+        int m = -1;
+        if (best != 0xFFFFFFFFu) {
+            const int bestDist = (int)(best >> 16);
+            if (bestDist <= TH_HIGH) {
+                const uint32_t eb = c[best & 0xFFFFu];
+                const int bestLevel = (int)(eb >> 25);
+                int bestDist2 = 256, bestLevel2 = -1;
+                if (second != 0xFFFFFFFFu) { bestDist2 = (int)(second >> 16); bestLevel2 = (int)(c[second & 0xFFFFu] >> 25); }
+                if (!(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2))) {
+                    m = (int)(eb & 0xFFFF);
+                    nm++;
+                    if (lane == 0 && (A.mp_has_obs == nullptr || A.mp_has_obs[iMP])) held[m >> 5] |= 1u << (m & 31);
+                }
+            }
+        }
+        if (lane == 0) match_feat[iMP] = m;
+        __syncwarp();
+    }
+    if (lane == 0) *n_matches = nm;
+}
+
+// ------------------------------------------------------------------------------------------------ BoW guided search
+// mode 0: SearchByBoW(KeyFrame*, Frame&)   — q = keyframe (needs has_mp), t = frame;   out match[t.n]  = q index
+// mode 1: SearchByBoW(KeyFrame*, KeyFrame*) — q = kf1, t = kf2 (both need has_mp);      out match[q.n]  = t index
+__global__ void __launch_bounds__(128) bow_match_kernel(const KfDev* __restrict__ qs, const KfDev* __restrict__ ts, int n_pairs, int mode,
+                                                        float nnratio, int check_ori, int32_t* __restrict__ match, int out_stride,
+                                                        uint8_t* __restrict__ bins, int32_t* __restrict__ n_matches, int max_t) {
+    extern __shared__ uint32_t sm[];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + wrp;
+    if (pair >= n_pairs) return;
+    const int words = (max_t + 31) / 32;
+    uint32_t* claimed = sm + (size_t)wrp * (words + 32);
+    int* hist = reinterpret_cast<int*>(claimed + words);
+    const KfDev q = qs[pair];
+    const KfDev t = ts[mode == 0 ? 0 : pair];
+    int32_t* out = match + (size_t)pair * out_stride;
+    uint8_t* bin = bins + (size_t)pair * out_stride;
+    const int nout = mode == 0 ? t.n : q.n;
+    for (int i = lane; i < nout; i += 32) out[i] = -1;
+    for (int w = lane; w < words; w += 32) claimed[w] = 0;
+    if (lane < 32) hist[lane] = 0;
+    __syncwarp();
+    int nm = 0;
+    for (int a = 0; a < q.nn; a++) {
+        const uint32_t node = q.node[a];
+        // lower_bound in the target's node list (merge-join of two ordered maps, :180-264)
+        int lo = 0, hi = t.nn;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (t.node[mid] < node) lo = mid + 1; else hi = mid; }
+        if (lo >= t.nn || t.node[lo] != node) continue;
+        const int ts0 = t.start[lo], ts1 = t.start[lo + 1];
+        for (int iq = q.start[a]; iq < q.start[a + 1]; iq++) {
+            const int r = (int)q.idx[iq];
+            if (q.has_mp == nullptr || !q.has_mp[r]) continue;
+            const uint32_t* dq = reinterpret_cast<const uint32_t*>(q.desc + (size_t)r * 32);
+            unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+            for (int p = ts0 + lane; p < ts1; p += 32) {
+                const int j = (int)t.idx[p];
+                if ((claimed[j >> 5] >> (j & 31)) & 1u) continue;
+                if (mode == 1 && (t.has_mp == nullptr || !t.has_mp[j])) continue;
+                const int dist = ham_words(dq, reinterpret_cast<const uint32_t*>(t.desc + (size_t)j * 32));
+                const unsigned key = ((unsigned)dist << 16) | (unsigned)(p - ts0);
+                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+            }
+            const unsigned best = warp_min(k1);
+            const unsigned second = warp_min(k1 == best ? k2 : k1);
+            if (best == 0xFFFFFFFFu) continue;
+            const int bestDist1 = (int)(best >> 16);
+            const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
+            const bool pass = mode == 0 ? (bestDist1 <= TH_LOW) : (bestDist1 < TH_LOW);
+            if (pass && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
+                const int j = (int)t.idx[ts0 + (int)(best & 0xFFFFu)];
+                if (lane == 0) {
+                    claimed[j >> 5] |= 1u << (j & 31);
+                    const int o = mode == 0 ? j : r;
+                    out[o] = mode == 0 ? r : j;
+                    if (check_ori) {
+                        const int b = rot_bin(q.keys[r].angle, t.keys[j].angle);
+                        bin[o] = (uint8_t)b;
+                        hist[b]++;
+                    }
+                }
+                nm++;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    if (check_ori) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        int removed = 0;
+        for (int i = lane; i < nout; i += 32)
+            if (out[i] >= 0) {
+                const int b = bin[i];
+                if (b != i1 && b != i2 && b != i3) { out[i] = -1; removed++; }
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, off);
+        nm -= removed;
+    }
+    if (lane == 0) n_matches[pair] = nm;
+}
+
+// ------------------------------------------------------------------------------------------------ triangulation
+__global__ void __launch_bounds__(256) triangulation_kernel(KfDev q, KfDev t, TriArgs T, int32_t* __restrict__ vmatch,
+                                                            uint8_t* __restrict__ bins, int32_t* __restrict__ pairs, int cap,
+                                                            int32_t* __restrict__ n_pairs) {
+    __shared__ int hist[32];
+    __shared__ int top[3];
+    __shared__ int wsum[9];
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    for (int i = tid; i < q.n; i += 256) vmatch[i] = -1;
+    if (tid < 32) hist[tid] = 0;
+    __syncthreads();
+    for (int a = wrp; a < q.nn; a += 8) {
+        const uint32_t node = q.node[a];
+        int lo = 0, hi = t.nn;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (t.node[mid] < node) lo = mid + 1; else hi = mid; }
+        if (lo >= t.nn || t.node[lo] != node) continue;
+        const int ts0 = t.start[lo], ts1 = t.start[lo + 1];
+        for (int iq = q.start[a]; iq < q.start[a + 1]; iq++) {
+            const int i = (int)q.idx[iq];
+            if (q.has_mp != nullptr && q.has_mp[i]) continue;              // already has a MapPoint (:699-703)
+            const bool bStereo1 = q.u_right != nullptr && q.u_right[i] >= 0;
+            if (T.only_stereo && !bStereo1) continue;
+            const borb_keypoint kp1 = q.keys[i];
+            const uint32_t* d1 = reinterpret_cast<const uint32_t*>(q.desc + (size_t)i * 32);
+            // epipolar line of kp1 in image 2 (CheckDistEpipolarLine, :142-145)
+            const float la = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.F[0]), __fmul_rn(kp1.y, T.F[3])), T.F[6]);
+            const float lb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.F[1]), __fmul_rn(kp1.y, T.F[4])), T.F[7]);
+            const float lc = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, T.F[2]), __fmul_rn(kp1.y, T.F[5])), T.F[8]);
+            const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+            unsigned bestKey = 0xFFFFFFFFu;
+            for (int p = ts0 + lane; p < ts1; p += 32) {
+                const int j = (int)t.idx[p];
+                if (t.has_mp != nullptr && t.has_mp[j]) continue;
+                const bool bStereo2 = t.u_right != nullptr && t.u_right[j] >= 0;
+                if (T.only_stereo && !bStereo2) continue;
+                const int dist = ham_words(d1, reinterpret_cast<const uint32_t*>(t.desc + (size_t)j * 32));
+                if (dist > TH_LOW) continue;
+                const borb_keypoint kp2 = t.keys[j];
+                if (!bStereo1 && !bStereo2) {
+                    const float distex = __fsub_rn(T.ex, kp2.x), distey = __fsub_rn(T.ey, kp2.y);
+                    if (__fadd_rn(__fmul_rn(distex, distex), __fmul_rn(distey, distey)) < __fmul_rn(100.0f, t.scale_factors[kp2.octave])) continue;
+                }
+                const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, kp2.x), __fmul_rn(lb, kp2.y)), lc);
+                if (den == 0) continue;
+                const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                if (!((double)dsqr < 3.84 * (double)t.level_sigma2[kp2.octave])) continue;
+                // "dist <= bestDist, later wins" (:738-755)  ==  min over (dist, -position)
+                bestKey = min(bestKey, ((unsigned)dist << 16) | (unsigned)(0xFFFF - (p - ts0)));
+            }
+            bestKey = warp_min(bestKey);
+            if (bestKey != 0xFFFFFFFFu && lane == 0) {
+                const int j = (int)t.idx[ts0 + (0xFFFF - (int)(bestKey & 0xFFFFu))];
+                vmatch[i] = j;
+                if (T.check_ori) {
+                    const int b = rot_bin(kp1.angle, t.keys[j].angle);
+                    bins[i] = (uint8_t)b;
+                    atomicAdd(&hist[b], 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (T.check_ori) {
+        if (tid == 0) { int a, b, c; three_maxima(hist, a, b, c); top[0] = a; top[1] = b; top[2] = c; }
+        __syncthreads();
+        for (int i = tid; i < q.n; i += 256)
+            if (vmatch[i] >= 0) { const int b = bins[i]; if (b != top[0] && b != top[1] && b != top[2]) vmatch[i] = -1; }
+        __syncthreads();
+    }
+    // ordered compaction into (idx1, idx2) pairs, ascending idx1 (:812-820)
+    int running = 0;
+    for (int base = 0; base < q.n; base += 256) {
+        const int i = base + tid;
+        const int v = i < q.n ? vmatch[i] : -1;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, v >= 0);
+        if (lane == 0) wsum[wrp] = __popc(bal);
+        __syncthreads();
+        int off = running;
+        for (int w = 0; w < wrp; w++) off += wsum[w];
+        int tot = 0;
+        for (int w = 0; w < 8; w++) tot += wsum[w];
+        if (v >= 0) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1));
+            if (pos < cap) { pairs[2 * pos] = i; pairs[2 * pos + 1] = v; }
+        }
+        running += tot;
+        __syncthreads();
+    }
+    if (tid == 0) *n_pairs = running;
+}
+
+// ------------------------------------------------------------------------------------------------ vocabulary
+__global__ void __launch_bounds__(256) bow_transform_kernel(VocDev V, const uint8_t* __restrict__ desc, int n, int levelsup,
+                                                            int32_t* __restrict__ word, double* __restrict__ weight,
+                                                            int32_t* __restrict__ node) {
+    const int lane = threadIdx.x & 31;
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= n) return;
+    const uint32_t* feat = reinterpret_cast<const uint32_t*>(desc + (size_t)f * 32);
+    const int nid_level = V.L - levelsup;
+    int nid = 0, final_id = 0, level = 0;
+    while (true) {
+        const int c0 = V.child_start[final_id], c1 = V.child_start[final_id + 1];
+        if (c1 == c0) break;                                  // leaf (isLeaf() == children.empty())
+        ++level;
+        unsigned best = 0xFFFFFFFFu;
+        for (int c = c0 + lane; c < c1; c += 32) {
+            const int id = V.child_ids[c];
+            const int d = ham_words(feat, reinterpret_cast<const uint32_t*>(V.desc + (size_t)id * 32));
+            best = min(best, ((unsigned)d << 16) | (unsigned)(c - c0));     // strict '<': first child wins ties (:1244)
+        }
+        best = warp_min(best);
+        final_id = V.child_ids[c0 + (int)(best & 0xFFFFu)];
+        if (level == nid_level) nid = final_id;
+    }
+    if (lane == 0) {
+        word[f] = V.word_id[final_id];
+        weight[f] = V.weight[final_id];
+        node[f] = nid;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+int launch_grid_sort(const borb_keypoint* keys, int n, float minX, float minY, float invW, float invH, int* cell_start, int* cell_idx,
+                     cudaStream_t s) {
+    int K = 32;
+    while (K < n) K <<= 1;
+    cudaFuncSetAttribute(grid_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K * 4);
+    grid_sort_kernel<<<1, 1024, K * 4, s>>>(keys, n, minX, minY, invW, invH, K, cell_start, cell_idx);
+    return 1;
+}
+int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s) {
+    if (A.n_mp > 0) proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
+    const int words = (A.n + 31) / 32;
+    proj_resolve_kernel<<<1, 32, words * 4, s>>>(A, match_feat, n_matches);
+    return 2;
+}
+int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
+                     int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s) {
+    const int words = (max_t + 31) / 32;
+    const size_t smem = (size_t)4 * (words + 32) * 4;
+    cudaFuncSetAttribute(bow_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bow_match_kernel<<<(n_pairs + 3) / 4, 128, smem, s>>>(qs, ts, n_pairs, mode, nnratio, check_ori, match, out_stride, bins, n_matches, max_t);
+    return 1;
+}
+int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,
+                         int32_t* n_pairs, cudaStream_t s) {
+    triangulation_kernel<<<1, 256, 0, s>>>(q, t, T, vmatch, bins, pairs, cap, n_pairs);
+    return 1;
+}
+int launch_bow_transform(const VocDev& V, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node,
+                         cudaStream_t s) {
+    if (n > 0) bow_transform_kernel<<<(n + 7) / 8, 256, 0, s>>>(V, desc, n, levelsup, word, weight, node);
+    return 1;
+}
+
+}  // namespace borb

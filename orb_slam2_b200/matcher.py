@@ -1,0 +1,274 @@
+"""Host-side mirror of ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:37-102) and ORBVocabulary over libborb.
+
+The reference methods walk pointer graphs (Frame, KeyFrame, MapPoint); here their inputs are plain snapshots
+(`FrameView`, `MapPointsView`, `KeyFrameView`) — exactly what the C++ adapter builds on the calling thread before it
+calls the C ABI — and results are indices instead of MapPoint pointers.  Same method names, argument meaning and
+thresholds as the reference; all compute happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, check
+
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30        # src/ORBmatcher.cc:37-39
+
+
+class _FrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("occupied", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("n_levels", C.c_int32),
+                ("scale_factors", C.c_void_p)]
+
+
+class _MapPointViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("proj_x", C.c_void_p), ("proj_y", C.c_void_p), ("proj_xr", C.c_void_p), ("level", C.c_void_p),
+                ("view_cos", C.c_void_p), ("desc", C.c_void_p), ("valid", C.c_void_p), ("has_obs", C.c_void_p)]
+
+
+class _FeatVecC(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("start", C.c_void_p), ("feat_idx", C.c_void_p)]
+
+
+class _KeyFrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("desc", C.c_void_p), ("has_mp", C.c_void_p), ("u_right", C.c_void_p),
+                ("fv", _FeatVecC), ("n_levels", C.c_int32), ("scale_factors", C.c_void_p), ("level_sigma2", C.c_void_p)]
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+@dataclass
+class FeatureVector:
+    """DBoW2::FeatureVector as CSR: node ids ascending, feature indices ascending inside a node."""
+    node_id: np.ndarray          # uint32 [n_nodes]
+    start: np.ndarray            # int32  [n_nodes+1]
+    feat_idx: np.ndarray         # uint32
+
+    @staticmethod
+    def from_nodes(node_of_feature: np.ndarray, keep: Optional[np.ndarray] = None) -> "FeatureVector":
+        """fv.addFeature(nid, i_feature) for i_feature = 0..N-1 (TemplatedVocabulary.h:1160-1163)."""
+        idx = np.arange(len(node_of_feature), dtype=np.uint32)
+        nodes = np.asarray(node_of_feature, np.int64)
+        if keep is not None:
+            idx, nodes = idx[keep], nodes[keep]
+        order = np.lexsort((idx, nodes))
+        nodes, idx = nodes[order], idx[order]
+        uniq, first = np.unique(nodes, return_index=True)
+        start = np.append(first, len(nodes)).astype(np.int32)
+        return FeatureVector(uniq.astype(np.uint32), start, np.ascontiguousarray(idx, np.uint32))
+
+    def as_dict(self) -> Dict[int, List[int]]:
+        return {int(n): self.feat_idx[self.start[i]:self.start[i + 1]].tolist() for i, n in enumerate(self.node_id)}
+
+
+@dataclass
+class FrameView:
+    """What SearchByProjection reads of a Frame (include/Frame.h)."""
+    mvKeysUn: np.ndarray
+    mDescriptors: np.ndarray
+    mvScaleFactors: np.ndarray
+    bounds: Tuple[float, float, float, float]            # mnMinX, mnMinY, mnMaxX, mnMaxY
+    mvuRight: Optional[np.ndarray] = None
+    occupied: Optional[np.ndarray] = None                 # mvpMapPoints[i] && Observations()>0
+
+
+@dataclass
+class MapPointsView:
+    """Local map points after Frame::isInFrustum (src/Frame.cc:269-325), in vpMapPoints order."""
+    mTrackProjX: np.ndarray
+    mTrackProjY: np.ndarray
+    mTrackProjXR: np.ndarray
+    mnTrackScaleLevel: np.ndarray
+    mTrackViewCos: np.ndarray
+    descriptors: np.ndarray
+    valid: Optional[np.ndarray] = None                    # mbTrackInView && !isBad()
+    has_obs: Optional[np.ndarray] = None                  # Observations()>0
+
+
+@dataclass
+class KeyFrameView:
+    """What the BoW-guided searches read of a KeyFrame / Frame."""
+    mvKeysUn: np.ndarray
+    mDescriptors: np.ndarray
+    mFeatVec: FeatureVector
+    has_mp: Optional[np.ndarray] = None                   # MapPoint present && !isBad(), per feature
+    mvuRight: Optional[np.ndarray] = None
+    mvScaleFactors: Optional[np.ndarray] = None
+    mvLevelSigma2: Optional[np.ndarray] = None
+    _keep: list = field(default_factory=list, repr=False)
+
+    def _c(self) -> _KeyFrameViewC:
+        k = np.ascontiguousarray(self.mvKeysUn, KP_DTYPE)
+        d = np.ascontiguousarray(self.mDescriptors, np.uint8)
+        hm = np.ascontiguousarray(self.has_mp, np.uint8) if self.has_mp is not None else None
+        ur = np.ascontiguousarray(self.mvuRight, np.float32) if self.mvuRight is not None else None
+        nd = np.ascontiguousarray(self.mFeatVec.node_id, np.uint32)
+        st = np.ascontiguousarray(self.mFeatVec.start, np.int32)
+        fi = np.ascontiguousarray(self.mFeatVec.feat_idx, np.uint32)
+        sf = np.ascontiguousarray(self.mvScaleFactors, np.float32) if self.mvScaleFactors is not None else None
+        sg = np.ascontiguousarray(self.mvLevelSigma2, np.float32) if self.mvLevelSigma2 is not None else None
+        self._keep = [k, d, hm, ur, nd, st, fi, sf, sg]
+        nl = len(sf) if sf is not None else (len(sg) if sg is not None else 0)
+        return _KeyFrameViewC(len(k), _p(k), _p(d), _p(hm), _p(ur), _FeatVecC(len(nd), _p(nd), _p(st), _p(fi)), nl, _p(sf), _p(sg))
+
+
+class ORBmatcher:
+    """ORBmatcher(nnratio=0.6, checkOri=True) — include/ORBmatcher.h:41."""
+
+    TH_LOW, TH_HIGH, HISTO_LENGTH = TH_LOW, TH_HIGH, HISTO_LENGTH
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, device: int = 0):
+        self._lib = _lib.load()
+        self.mfNNratio = float(np.float32(nnratio))
+        self.mbCheckOrientation = bool(checkOri)
+        h = C.c_void_p()
+        check(self._lib.borb_matcher_create(device, C.byref(h)), "borb_matcher_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.borb_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def DescriptorDistance(a: np.ndarray, b: np.ndarray) -> int:
+        """256-bit Hamming distance (src/ORBmatcher.cc:1647-1663) — host convenience for tests."""
+        return int(np.unpackbits(np.bitwise_xor(np.asarray(a, np.uint8), np.asarray(b, np.uint8))).sum())
+
+    def SearchByProjection(self, F: FrameView, mps: MapPointsView, th: float = 3.0) -> Tuple[int, np.ndarray]:
+        """src/ORBmatcher.cc:45-129.  Returns (nmatches, match_feat[n_mp]): frame feature that received map point i, or -1."""
+        k = np.ascontiguousarray(F.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(F.mDescriptors, np.uint8)
+        ur = np.ascontiguousarray(F.mvuRight, np.float32) if F.mvuRight is not None else None
+        oc = np.ascontiguousarray(F.occupied, np.uint8) if F.occupied is not None else None
+        sf = np.ascontiguousarray(F.mvScaleFactors, np.float32)
+        fv = _FrameViewC(len(k), _p(k), _p(d), _p(ur), _p(oc), *[float(x) for x in F.bounds], len(sf), _p(sf))
+        px = np.ascontiguousarray(mps.mTrackProjX, np.float32); py = np.ascontiguousarray(mps.mTrackProjY, np.float32)
+        pxr = np.ascontiguousarray(mps.mTrackProjXR, np.float32); lv = np.ascontiguousarray(mps.mnTrackScaleLevel, np.int32)
+        vc = np.ascontiguousarray(mps.mTrackViewCos, np.float32); md = np.ascontiguousarray(mps.descriptors, np.uint8)
+        va = np.ascontiguousarray(mps.valid, np.uint8) if mps.valid is not None else None
+        ho = np.ascontiguousarray(mps.has_obs, np.uint8) if mps.has_obs is not None else None
+        mv = _MapPointViewC(len(px), _p(px), _p(py), _p(pxr), _p(lv), _p(vc), _p(md), _p(va), _p(ho))
+        match = np.full(max(len(px), 1), -1, np.int32)
+        n = C.c_int32(0)
+        check(self._lib.borb_search_by_projection(self._h, C.byref(fv), C.byref(mv), float(th), self.mfNNratio, _p(match), C.byref(n)),
+              "borb_search_by_projection")
+        return n.value, match[:len(px)]
+
+    def SearchByBoW(self, pKF, F: KeyFrameView):
+        """SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) — src/ORBmatcher.cc:159-288.  pKF may be one KeyFrameView or a
+        sequence (batched candidates).  Returns (nmatches, match[F.N]) or lists of them: match[j] = keyframe feature whose
+        MapPoint frame feature j received, or -1."""
+        single = isinstance(pKF, KeyFrameView)
+        kfs = [pKF] if single else list(pKF)
+        arr = (_KeyFrameViewC * len(kfs))(*[kf._c() for kf in kfs])
+        fc = F._c()
+        nF = len(F.mvKeysUn)
+        match = np.full((len(kfs), max(nF, 1)), -1, np.int32)
+        nm = np.zeros(len(kfs), np.int32)
+        check(self._lib.borb_search_by_bow(self._h, arr, len(kfs), C.byref(fc), self.mfNNratio, int(self.mbCheckOrientation), _p(match), _p(nm)),
+              "borb_search_by_bow")
+        match = match[:, :nF]
+        return (int(nm[0]), match[0]) if single else (nm, match)
+
+    def SearchByBoW_KF(self, pKF1: KeyFrameView, pKF2: KeyFrameView) -> Tuple[int, np.ndarray]:
+        """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) — src/ORBmatcher.cc:522-655.  match12[i] = index in KF2 or -1."""
+        c1, c2 = pKF1._c(), pKF2._c()
+        n1 = len(pKF1.mvKeysUn)
+        match = np.full(max(n1, 1), -1, np.int32)
+        nm = C.c_int32(0)
+        check(self._lib.borb_search_by_bow_kf(self._h, C.byref(c1), C.byref(c2), self.mfNNratio, int(self.mbCheckOrientation), _p(match), C.byref(nm)),
+              "borb_search_by_bow_kf")
+        return nm.value, match[:n1]
+
+    def SearchForTriangulation(self, pKF1: KeyFrameView, pKF2: KeyFrameView, F12: np.ndarray, epipole: Tuple[float, float],
+                               bOnlyStereo: bool = False) -> np.ndarray:
+        """src/ORBmatcher.cc:657-823.  Returns vMatchedPairs as an (m,2) int array (idx1, idx2), ascending idx1."""
+        c1, c2 = pKF1._c(), pKF2._c()
+        f = np.ascontiguousarray(F12, np.float32).reshape(9)
+        cap = max(len(pKF1.mvKeysUn), 1)
+        pairs = np.zeros((cap, 2), np.int32)
+        n = C.c_int32(0)
+        check(self._lib.borb_search_for_triangulation(self._h, C.byref(c1), C.byref(c2), _p(f), float(epipole[0]), float(epipole[1]),
+                                                      int(bOnlyStereo), int(self.mbCheckOrientation), _p(pairs), cap, C.byref(n)),
+              "borb_search_for_triangulation")
+        return pairs[:n.value]
+
+
+class ORBVocabulary:
+    """ORBVocabulary = DBoW2::TemplatedVocabulary<FORB> (include/ORBVocabulary.h), device resident."""
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+
+    @staticmethod
+    def from_arrays(parent, is_leaf, desc, weight, k: int, L: int, device: int = 0) -> "ORBVocabulary":
+        lib = _lib.load()
+        parent = np.ascontiguousarray(parent, np.int32); is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8); weight = np.ascontiguousarray(weight, np.float64)
+        h = C.c_void_p()
+        check(lib.borb_voc_create(_p(parent), _p(is_leaf), _p(desc), _p(weight), len(parent), k, L, device, C.byref(h)), "borb_voc_create")
+        return ORBVocabulary(h, lib)
+
+    @staticmethod
+    def loadFromTextFile(path: str, device: int = 0) -> "ORBVocabulary":
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.borb_voc_load_text(path.encode(), device, C.byref(h)), "borb_voc_load_text")
+        return ORBVocabulary(h, lib)
+
+    @staticmethod
+    def from_blob(d_ptr: int, nbytes: int, device: int = 0) -> "ORBVocabulary":
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.borb_voc_from_blob(C.c_void_p(d_ptr), nbytes, device, C.byref(h)), "borb_voc_from_blob")
+        return ORBVocabulary(h, lib)
+
+    def blob(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_size_t()
+        check(self._lib.borb_voc_blob(self._h, C.byref(p), C.byref(n)), "borb_voc_blob")
+        return p.value, n.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.borb_voc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform_raw(self, descriptors: np.ndarray, levelsup: int = 4):
+        """Per feature: word id, word weight, node id at level L-levelsup (TemplatedVocabulary.h:1218-1259)."""
+        d = np.ascontiguousarray(descriptors, np.uint8)
+        n = len(d)
+        word = np.zeros(max(n, 1), np.int32); weight = np.zeros(max(n, 1), np.float64); node = np.zeros(max(n, 1), np.int32)
+        check(self._lib.borb_bow_transform(self._h, _p(d), n, levelsup, _p(word), _p(weight), _p(node)), "borb_bow_transform")
+        return word[:n], weight[:n], node[:n]
+
+    def transform(self, descriptors: np.ndarray, levelsup: int = 4):
+        """transform(features, BowVector, FeatureVector, levelsup) (:1127-1194) for TF-IDF / L1 (ORBvoc.txt "10 6 0 0"):
+        the tree descent runs on the GPU; the ordered-map bookkeeping is done here in feature order, as the reference does."""
+        word, weight, node = self.transform_raw(descriptors, levelsup)
+        bow: Dict[int, float] = {}
+        keep = weight > 0                               # "not stopped"
+        for i in np.nonzero(keep)[0]:
+            w = int(word[i])
+            bow[w] = bow.get(w, 0.0) + float(weight[i])     # BowVector::addWeight, accumulated in feature order
+        norm = sum(abs(v) for _, v in sorted(bow.items()))   # L1, summed in map (word id) order
+        if norm > 0.0:
+            bow = {k: v / norm for k, v in bow.items()}
+        return dict(sorted(bow.items())), FeatureVector.from_nodes(node, keep)

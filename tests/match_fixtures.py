@@ -1,0 +1,56 @@
+"""Synthetic inputs for the matcher tests: two views of one scene (a synthetic stereo pair), a seeded vocabulary tree,
+and the snapshots (FrameView / MapPointsView / KeyFrameView) the matchers consume.  Test tooling."""
+import numpy as np
+
+from orb_slam2_b200 import synth
+from orb_slam2_b200.matcher import FeatureVector, FrameView, KeyFrameView, MapPointsView
+
+BF, FX = 386.1448, 718.856
+
+
+def two_views(oracle, seed, shape=(640, 480), nf=1000):
+    w, h = shape
+    L, R, disp = synth.stereo_pair(seed, 0, 0, w, h)
+    EL, ER = oracle.PortExtractor(nf), oracle.PortExtractor(nf)
+    kl, dl = EL(L)
+    kr, dr = ER(R)
+    ur, dp, _ = oracle.port_stereo(kl, dl, kr, dr, [EL.level(i) for i in range(8)], [ER.level(i) for i in range(8)],
+                                   EL.scale, EL.inv_scale, BF, FX)
+    return dict(w=w, h=h, kl=kl, dl=dl, kr=kr, dr=dr, ur=ur, disp=disp, scale=EL.scale.copy(), sigma2=EL.sigma2.copy())
+
+
+def projection_case(v, seed, n_mp=300, occupied_frac=0.1):
+    rng = np.random.default_rng(seed)
+    w, h = v["w"], v["h"]
+    F = FrameView(mvKeysUn=v["kl"], mDescriptors=v["dl"], mvScaleFactors=v["scale"], bounds=(0.0, 0.0, float(w), float(h)),
+                  mvuRight=v["ur"], occupied=(rng.random(len(v["kl"])) < occupied_frac).astype(np.uint8))
+    sel = rng.choice(len(v["kr"]), size=min(n_mp, len(v["kr"])), replace=False)
+    kr = v["kr"][sel]
+    d = v["disp"][np.clip(kr["y"].astype(int), 0, h - 1), np.clip(kr["x"].astype(int), 0, w - 1)]
+    px = (kr["x"] + d + rng.normal(0, 1.5, len(sel))).astype(np.float32)
+    py = (kr["y"] + rng.normal(0, 1.5, len(sel))).astype(np.float32)
+    lvl = np.clip(kr["octave"] + rng.integers(-1, 2, len(sel)), 0, 7).astype(np.int32)
+    mps = MapPointsView(mTrackProjX=px, mTrackProjY=py, mTrackProjXR=(px - d.astype(np.float32) + rng.normal(0, 2, len(sel)).astype(np.float32)),
+                        mnTrackScaleLevel=lvl, mTrackViewCos=rng.uniform(0.99, 1.0, len(sel)).astype(np.float32),
+                        descriptors=v["dr"][sel], valid=(rng.random(len(sel)) < 0.95).astype(np.uint8),
+                        has_obs=(rng.random(len(sel)) < 0.9).astype(np.uint8))
+    return F, mps
+
+
+def keyframe_views(v, voc, seed, levelsup=2, mp_frac=0.7):
+    """KF1 = left view, KF2 = right view, FeatureVectors from the (oracle) vocabulary."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k, d, ur in ((v["kl"], v["dl"], v["ur"]), (v["kr"], v["dr"], None)):
+        _, weight, node = voc.transform_raw(d, levelsup)
+        fv = FeatureVector.from_nodes(node, weight > 0)
+        u = ur if ur is not None else np.where(rng.random(len(k)) < 0.5, k["x"] - 20.0, -1.0).astype(np.float32)
+        out.append(KeyFrameView(mvKeysUn=k, mDescriptors=d, mFeatVec=fv, has_mp=(rng.random(len(k)) < mp_frac).astype(np.uint8),
+                                mvuRight=u.astype(np.float32), mvScaleFactors=v["scale"], mvLevelSigma2=v["sigma2"]))
+    return out
+
+
+def rectified_F12(seed):
+    rng = np.random.default_rng(seed)
+    F = np.array([[0, 0, 0], [0, 0, 1], [0, -1, 0]], np.float32)
+    return (F + rng.normal(0, 2e-6, (3, 3))).astype(np.float32)

@@ -1,0 +1,119 @@
+"""GPU parity for the ORBmatcher paths and the BoW feeder through the C ABI, against the restatements in
+oracle/orb_port_match.cpp: bit-exact indices and counts (all integer / order-dependent work)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import match_fixtures as mf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    from orb_slam2_b200 import matcher
+    return matcher
+
+
+@pytest.fixture(scope="module")
+def views(oracle):
+    return {s: mf.two_views(oracle, s) for s in (7, 8)}
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("th,ratio", [(1.0, 0.8), (3.0, 0.8), (5.0, 0.9)])
+def test_search_by_projection(M, oracle, views, seed, th, ratio):
+    F, mps = mf.projection_case(views[seed], seed + 10, n_mp=400)
+    n_o, m_o = oracle.port_search_by_projection(F, mps, th, ratio)
+    n_g, m_g = M.ORBmatcher(ratio, True).SearchByProjection(F, mps, th)
+    assert n_o > 30
+    assert n_g == n_o and np.array_equal(m_g, m_o), int((m_g != m_o).sum())
+
+
+def test_search_by_projection_edge_cases(M, oracle, views):
+    v = views[7]
+    F, mps = mf.projection_case(v, 99, n_mp=50)
+    mt = M.ORBmatcher(0.8, True)
+    # monocular frame (no stereo check), no occupancy, all map points valid and observed
+    F2 = M.FrameView(F.mvKeysUn, F.mDescriptors, F.mvScaleFactors, F.bounds)
+    mp2 = M.MapPointsView(mps.mTrackProjX, mps.mTrackProjY, mps.mTrackProjXR, mps.mnTrackScaleLevel, mps.mTrackViewCos, mps.descriptors)
+    assert_same = lambda a, b: (a[0] == b[0] and np.array_equal(a[1], b[1]))
+    assert assert_same(mt.SearchByProjection(F2, mp2, 3.0), oracle.port_search_by_projection(F2, mp2, 3.0, 0.8))
+    # every map point projects to the same place: the order-dependent claiming decides
+    mp3 = M.MapPointsView(np.full(50, 320.0, np.float32), np.full(50, 240.0, np.float32), np.full(50, 300.0, np.float32),
+                          np.zeros(50, np.int32), np.full(50, 0.9, np.float32), mps.descriptors)
+    assert assert_same(mt.SearchByProjection(F2, mp3, 15.0), oracle.port_search_by_projection(F2, mp3, 15.0, 0.8))
+    # projections outside the image / nothing in range
+    mp4 = M.MapPointsView(np.full(50, -500.0, np.float32), np.full(50, 9000.0, np.float32), np.zeros(50, np.float32),
+                          np.full(50, 7, np.int32), np.ones(50, np.float32), mps.descriptors)
+    n, m = mt.SearchByProjection(F2, mp4, 3.0)
+    assert n == 0 and np.all(m == -1)
+    # zero map points
+    mp5 = M.MapPointsView(*[np.zeros(0, np.float32)] * 3, np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros((0, 32), np.uint8))
+    n, m = mt.SearchByProjection(F2, mp5, 3.0)
+    assert n == 0 and len(m) == 0
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("ratio,ori", [(0.7, True), (0.9, True), (0.75, False)])
+def test_search_by_bow_both_variants(M, oracle, views, seed, ratio, ori):
+    voc = oracle.PortVocabulary.random(10, 4, 5)
+    kf1, kf2 = mf.keyframe_views(views[seed], voc, seed)
+    mt = M.ORBmatcher(ratio, ori)
+    n_o, m_o = oracle.port_search_by_bow(kf1, kf2, ratio, ori)
+    n_g, m_g = mt.SearchByBoW(kf1, kf2)
+    assert n_o > 20 and n_g == n_o and np.array_equal(m_g, m_o)
+    n_o, m_o = oracle.port_search_by_bow_kf(kf1, kf2, ratio, ori)
+    n_g, m_g = mt.SearchByBoW_KF(kf1, kf2)
+    assert n_g == n_o and np.array_equal(m_g, m_o)
+
+
+def test_search_by_bow_batched_keyframes(M, oracle, views):
+    """Config-5 shape in miniature: one query frame against several keyframes in one launch."""
+    voc = oracle.PortVocabulary.random(10, 4, 5)
+    a1, a2 = mf.keyframe_views(views[7], voc, 1)
+    b1, b2 = mf.keyframe_views(views[8], voc, 2)
+    kfs = [a1, b1, b2, a1]
+    nm, match = M.ORBmatcher(0.75, True).SearchByBoW(kfs, a2)
+    for i, kf in enumerate(kfs):
+        n_o, m_o = oracle.port_search_by_bow(kf, a2, 0.75, True)
+        assert nm[i] == n_o and np.array_equal(match[i], m_o), i
+    assert np.array_equal(match[0], match[3])
+
+
+@pytest.mark.parametrize("only_stereo", [False, True])
+@pytest.mark.parametrize("ori", [True, False])
+def test_search_for_triangulation(M, oracle, views, only_stereo, ori):
+    voc = oracle.PortVocabulary.random(10, 4, 5)
+    for seed in (7, 8):
+        kf1, kf2 = mf.keyframe_views(views[seed], voc, seed + 3, mp_frac=0.3)
+        F12 = mf.rectified_F12(seed)
+        ep = (-1000.0, 200.0) if seed == 7 else (300.0, 240.0)      # the second epipole sits inside the image: exercises :743-749
+        want = oracle.port_search_for_triangulation(kf1, kf2, F12, ep, only_stereo, ori)
+        got = M.ORBmatcher(0.6, ori).SearchForTriangulation(kf1, kf2, F12, ep, only_stereo)
+        assert len(want) > 5 and np.array_equal(got, want)
+
+
+def test_vocabulary_transform_and_blob_round_trip(M, oracle, views, tmp_path):
+    pv = oracle.PortVocabulary.random(10, 5, 21)             # 111,111 nodes
+    e = pv.export()
+    voc = M.ORBVocabulary.from_arrays(e["parent"], e["is_leaf"], e["desc"], e["weight"], e["k"], e["L"])
+    d = np.concatenate([views[7]["dl"], views[8]["dr"]])
+    for levelsup in (4, 3, 0, 7):
+        wg, tg, ng = voc.transform_raw(d, levelsup)
+        wo, to, no = pv.transform_raw(d, levelsup)
+        assert np.array_equal(wg, wo) and np.array_equal(tg, to) and np.array_equal(ng, no), levelsup
+    # text loader (ORBvoc.txt format) gives the same tree
+    path = os.path.join(tmp_path, "voc.txt")
+    small = oracle.PortVocabulary.random(10, 3, 4)
+    small.save_text(path)
+    v2 = M.ORBVocabulary.loadFromTextFile(path)
+    assert all(np.array_equal(a, b) for a, b in zip(v2.transform_raw(d[:500], 2), small.transform_raw(d[:500], 2)))
+    # packed blob adoption (what the NCCL broadcast receiver does)
+    ptr, nbytes = voc.blob()
+    v3 = M.ORBVocabulary.from_blob(ptr, nbytes)
+    assert all(np.array_equal(a, b) for a, b in zip(v3.transform_raw(d[:300], 4), pv.transform_raw(d[:300], 4)))
+    bow, fv = voc.transform(views[7]["dl"], 4)
+    assert abs(sum(bow.values()) - 1.0) < 1e-9 and list(bow) == sorted(bow)
+    assert np.all(np.diff(fv.node_id.astype(np.int64)) > 0) and fv.start[-1] == len(views[7]["dl"])

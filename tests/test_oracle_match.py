@@ -1,0 +1,103 @@
+"""CPU: sanity of the matcher / vocabulary restatements (oracle/orb_port_match.cpp) against brute-force numpy
+re-derivations and invariants.  (The reference has no tests for these functions; see the file header there.)"""
+import os
+
+import numpy as np
+import pytest
+
+from tests import match_fixtures as mf
+
+
+@pytest.fixture(scope="module")
+def views(oracle):
+    return mf.two_views(oracle, 7)
+
+
+def test_features_in_area_equals_bruteforce_in_grid_order(oracle, views):
+    k = views["kl"]
+    bounds = (0.0, 0.0, 640.0, 480.0)
+    rng = np.random.default_rng(0)
+    invw, invh = np.float32(64) / np.float32(640), np.float32(48) / np.float32(480)
+    for _ in range(50):
+        x, y, r = rng.uniform(-20, 660), rng.uniform(-20, 500), rng.uniform(3, 60)
+        lo = int(rng.integers(-1, 7)); hi = lo + int(rng.integers(0, 2))
+        got = oracle.port_features_in_area(k, bounds, x, y, r, lo, hi)
+        m = (np.abs(k["x"] - np.float32(x)) < np.float32(r)) & (np.abs(k["y"] - np.float32(y)) < np.float32(r))
+        if lo > 0 or hi >= 0:
+            m &= k["octave"] >= lo
+            if hi >= 0:
+                m &= k["octave"] <= hi
+        want = np.nonzero(m)[0]
+        assert sorted(got.tolist()) == want.tolist()
+        # order: (cell x, cell y, insertion)
+        cx = np.floor(k["x"][got] * invw + np.float32(0.5)).astype(int); cy = np.floor(k["y"][got] * invh + np.float32(0.5)).astype(int)   # C round(): half away from zero
+        key = list(zip(cx.tolist(), cy.tolist(), got.tolist()))
+        assert key == sorted(key)
+
+
+def test_search_by_projection_invariants(oracle, views):
+    F, mps = mf.projection_case(views, 3)
+    n, match = oracle.port_search_by_projection(F, mps, 3.0, 0.8)
+    assert n == int((match >= 0).sum()) and n > 50
+    m = match[match >= 0]
+    assert np.all(F.occupied[m] == 0)                                   # never lands on an occupied feature
+    # a feature is claimed twice only when the first claimant had no observations
+    for f in set(m.tolist()):
+        owners = np.nonzero(match == f)[0]
+        assert np.all(mps.has_obs[owners[:-1]] == 0)
+    for i in np.nonzero(match >= 0)[0][:100]:
+        d = oracle.port_lib().orbport_hamming(mps.descriptors[i].ctypes.data_as(oracle._u8p), F.mDescriptors[match[i]].ctypes.data_as(oracle._u8p))
+        assert d <= 100
+    assert np.all(match[mps.valid == 0] == -1)
+
+
+def test_bow_searches_invariants(oracle, views):
+    voc = oracle.PortVocabulary.random(10, 4, 5)
+    kf1, kf2 = mf.keyframe_views(views, voc, 9)
+    n, match = oracle.port_search_by_bow(kf1, kf2, 0.7, True)
+    assert n == int((match >= 0).sum()) and n > 20
+    assert np.all(kf1.has_mp[match[match >= 0]] == 1)
+    assert len(set(match[match >= 0].tolist())) <= n
+    n2, m12 = oracle.port_search_by_bow_kf(kf1, kf2, 0.75, True)
+    assert n2 == int((m12 >= 0).sum())
+    j = m12[m12 >= 0]
+    assert len(set(j.tolist())) == len(j) and np.all(kf2.has_mp[j] == 1) and np.all(kf1.has_mp[np.nonzero(m12 >= 0)[0]] == 1)
+    n_no, _ = oracle.port_search_by_bow(kf1, kf2, 0.7, False)
+    assert n_no >= n                                                     # the rotation cull only removes matches
+    pairs = oracle.port_search_for_triangulation(kf1, kf2, mf.rectified_F12(1), (-1000.0, 200.0), False, True)
+    assert len(pairs) > 10 and np.all(np.diff(pairs[:, 0]) > 0)
+    assert np.all(kf1.has_mp[pairs[:, 0]] == 0) and np.all(kf2.has_mp[pairs[:, 1]] == 0)
+    so = oracle.port_search_for_triangulation(kf1, kf2, mf.rectified_F12(1), (-1000.0, 200.0), True, True)
+    assert np.all(kf1.mvuRight[so[:, 0]] >= 0) and np.all(kf2.mvuRight[so[:, 1]] >= 0)
+
+
+def test_vocabulary_text_round_trip_and_descent(oracle, tmp_path, views):
+    voc = oracle.PortVocabulary.random(10, 3, 11)
+    path = os.path.join(tmp_path, "voc.txt")
+    voc.save_text(path)
+    voc2 = oracle.PortVocabulary.load_text(path)
+    e1, e2 = voc.export(), voc2.export()
+    for key in ("parent", "is_leaf", "word_id", "desc", "weight"):
+        assert np.array_equal(e1[key], e2[key]), key
+    assert e1["k"] == 10 and e1["L"] == 3 and len(e1["parent"]) == 1 + 10 + 100 + 1000
+    d = views["dl"]
+    w1, wt1, n1 = voc.transform_raw(d, 2)
+    w2, wt2, n2 = voc2.transform_raw(d, 2)
+    assert np.array_equal(w1, w2) and np.array_equal(wt1, wt2) and np.array_equal(n1, n2)
+    # brute-force descent in numpy
+    desc = e1["desc"]; parent = e1["parent"]
+    children = {}
+    for i in range(1, len(parent)):
+        children.setdefault(int(parent[i]), []).append(i)
+    bits = np.unpackbits(desc, axis=1)
+    for f in range(0, len(d), 37):
+        fb = np.unpackbits(d[f])
+        node, lvl, at1 = 0, 0, 0
+        while node in children:
+            ch = children[node]
+            dist = [(int((bits[c] != fb).sum())) for c in ch]
+            node = ch[int(np.argmin(dist))]          # argmin: first minimum
+            lvl += 1
+            if lvl == 1:
+                at1 = node
+        assert e1["word_id"][node] == w1[f] and at1 == n1[f]
