@@ -171,14 +171,6 @@ class Clocks:
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
-def synthetic_vocabulary_bytes(seed: int = 7) -> np.ndarray:
-    """Packed stand-in for ORBvoc (k=10, L=6: 1,111,110 non-root nodes x (32 B descriptor + f32 weight +
-    i32 parent) = ~44 MB) — the object config 4 broadcasts over NCCL."""
-    n = sum(10 ** d for d in range(1, 7))
-    rng = np.random.default_rng(seed)
-    return rng.integers(0, 256, n * 40, dtype=np.uint8)
-
-
 def run_b200(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
@@ -195,15 +187,28 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     B, K, Wm = args.pairs, args.steps, args.warmup
     NBUF = 4
 
-    # ---- NCCL plumbing that the path really has: vocabulary broadcast (start-up), counter gather (end)
-    voc_ms = None
+    # ---- NCCL plumbing that the path really has: the packed vocabulary (k=10, L=6 tree of ORBvoc's shape,
+    # ~48 MB) is built on rank 0 only, broadcast ONCE over NCCL into every GPU's HBM and adopted there; counters are
+    # all-gathered at the end.  No collective touches the per-frame data path.
+    from orb_slam2_b200 import sharding
+    from orb_slam2_b200.matcher import ORBVocabulary
+    voc_ms, voc_bytes, voc = None, None, None
     if world > 1:
-        voc = torch.from_numpy(synthetic_vocabulary_bytes()).to(dev) if rank == 0 else torch.empty(sum(10 ** d for d in range(1, 7)) * 40, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            voc = ORBVocabulary.from_arrays(*sharding.random_vocabulary_arrays(10, 6, 7), 10, 6, device=local_rank)
+            ptr, nbytes = voc.blob()
+            src_blob = torch.as_tensor(sharding.DeviceBlobView(ptr, nbytes), device=dev)
+        else:
+            src_blob = None
         torch.cuda.synchronize()
+        dist.barrier()
         t0 = time.perf_counter()
-        dist.broadcast(voc, src=0)
+        blob = sharding.broadcast_blob(src_blob, src=0, device=dev)
         torch.cuda.synchronize()
         voc_ms = (time.perf_counter() - t0) * 1e3
+        voc_bytes = int(blob.numel())
+        if rank != 0:
+            voc = ORBVocabulary.from_blob(blob.data_ptr(), voc_bytes, device=local_rank)
 
     # ---- synthetic inputs: B distinct pairs of this rank's camera stream; NBUF rotating batches (row-rolled
     # copies keep the stereo geometry) so consecutive steps never re-read the same pixels from L2
@@ -318,13 +323,13 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     h2d = 2 * B * W_IMG * H_IMG
     d2h = B * (2 * cap * (28 + 32) + 2 * 4 + 2 * cap * 4)
 
-    # ---- per-stream counters gathered over NCCL
-    counters = torch.tensor([B * K, int(n_left.sum()), int(n_right.sum())], dtype=torch.int64, device=dev)
+    # ---- per-stream counters gathered over NCCL; the vocabulary checksum proves every rank walks the same tree
     gathered = None
     if world > 1:
-        lst = [torch.zeros_like(counters) for _ in range(world)]
-        dist.all_gather(lst, counters)
-        gathered = [c.tolist() for c in lst]
+        kps0 = outs[0]["dl"][0, :NFEAT].numpy()
+        words, _, _ = voc.transform_raw(kps0, 4)
+        gathered = sharding.gather_counters([B * K, int(n_left.sum()), int(n_right.sum()), int((outs[0]["ur"] >= 0).sum()),
+                                             int(words.astype(np.int64).sum() % (1 << 31))], device=dev).tolist()
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -365,7 +370,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "stage_ms_per_step": stage_ms,
                 "cpu_baseline": cpu}
         if voc_ms is not None:
-            line["nccl"] = {"vocabulary_broadcast_ms": voc_ms, "vocabulary_bytes": int(sum(10 ** d for d in range(1, 7)) * 40),
+            line["nccl"] = {"vocabulary_broadcast_ms": voc_ms, "vocabulary_bytes": voc_bytes,
+                            "counter_fields": list(sharding.COUNTER_FIELDS[:4]) + ["vocabulary_word_checksum"],
                             "counters_all_gather": gathered}
         print(json.dumps(line), flush=True)
     if world > 1:
