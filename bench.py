@@ -6,7 +6,8 @@ KITTI-shaped 1242x375 pairs at 2000 keypoints (BASELINE.json configs[1]); see DE
   N>1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of B synthetic stereo pairs per GPU.
-  value     frames/s, whole job, inputs already resident in HBM (borb_stereo_frames_device_enqueue)
+  value     frames/s, whole job, inputs already resident in HBM (borb_stereo_frames_device_enqueue, two handles =
+            two batches in flight on two CUDA streams)
   e2e       same metric through the C-ABI call with HOST (pinned) buffers: H2D of the images and D2H of
             keypoints/descriptors/uRight/depth inside the timed region (borb_stereo_frames_enqueue,
             two handles double-buffered)
@@ -182,6 +183,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     B, K, Wm = args.pairs, args.steps, args.warmup
@@ -223,49 +225,67 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     d_in = torch.from_numpy(host).to(dev)
     pitch, img_stride = W_IMG, W_IMG * H_IMG
 
-    ext = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank)
+    # Two handles (= two camera-stream batches in flight, each with its own CUDA stream) keep the GPU busy across the
+    # dependent kernels of one batch; both timed regions use the same two handles.
+    exts = [ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank) for _ in range(2)]
+    ext = exts[0]
     cap = ext.capacity(W_IMG, H_IMG)
-    ext.reserve(W_IMG, H_IMG, 2 * B)
+    for x in exts:
+        x.reserve(W_IMG, H_IMG, 2 * B)
     b = float(np.float32(BF) / np.float32(FX))
-    sp = C.c_void_p()
-    _lib.check(lib.borb_extractor_stream(ext._h, C.byref(sp)), "borb_extractor_stream")
-    stream = torch.cuda.ExternalStream(sp.value, device=dev)
-    n_left = torch.zeros(B, dtype=torch.int32).pin_memory()
-    n_right = torch.zeros(B, dtype=torch.int32).pin_memory()
+    streams = []
+    for x in exts:
+        sp = C.c_void_p()
+        _lib.check(lib.borb_extractor_stream(x._h, C.byref(sp)), "borb_extractor_stream")
+        streams.append(torch.cuda.ExternalStream(sp.value, device=dev))
+    n_lr = [(torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(2)]
+    n_left, n_right = n_lr[0]
 
     def step_resident(k):
+        x, (nl, nr) = exts[k % 2], n_lr[k % 2]
         buf = d_in[k % NBUF]
-        _lib.check(lib.borb_stereo_frames_device_enqueue(ext._h, buf.data_ptr(), B, W_IMG, H_IMG, pitch, img_stride, BF, b,
-                                                         n_left.data_ptr(), n_right.data_ptr(), None, None, cap), "stereo_frames_device_enqueue")
+        _lib.check(lib.borb_stereo_frames_device_enqueue(x._h, buf.data_ptr(), B, W_IMG, H_IMG, pitch, img_stride, BF, b,
+                                                         nl.data_ptr(), nr.data_ptr(), None, None, cap), "stereo_frames_device_enqueue")
 
-    for k in range(max(Wm, 3)):
+    def drain():
+        for x in exts:
+            _lib.check(lib.borb_sync(x._h), "borb_sync")
+
+    clocks = Clocks(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    clocks.start()          # sampled across warm-up and BOTH timed regions (continuous load)
+    for k in range(max(Wm, 3) * 2):
         step_resident(k)
-    _lib.check(lib.borb_sync(ext._h), "borb_sync")
+    drain()
     assert int(n_left.min()) >= NFEAT, "warm-up produced too few keypoints"
 
-    # ---- timed region 1: HBM-resident throughput, CUDA events on the library's stream
-    ext.set_timing(True)
-    launches0 = ext.launch_count()
+    # ---- timed region 1: HBM-resident throughput, CUDA events on the library's streams
+    launches0 = sum(x.launch_count() for x in exts)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = Clocks(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1s = [torch.cuda.Event(enable_timing=True) for _ in exts]
+    e0.record(streams[0])
+    streams[1].wait_event(e0)              # both streams start after the common start mark
     for k in range(K):
         step_resident(k)
-    e1.record(stream)
-    _lib.check(lib.borb_sync(ext._h), "borb_sync")
+    for ev, st_ in zip(e1s, streams):
+        ev.record(st_)
+    drain()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
-    launches = ext.launch_count() - launches0
+    ms = max(e0.elapsed_time(ev) for ev in e1s)
+    launches = sum(x.launch_count() for x in exts) - launches0
+    # per-kernel device times: a short single-handle pass right after the timed region (with two batches in flight the
+    # events of one stream would also count the other stream's kernels), CUDA events on the launching stream
+    exts[0].set_timing(True)
+    for k in range(0, 2 * min(K, 16), 2):
+        step_resident(k)
+    drain()
     tot = (C.c_double * 8)()
     nst = C.c_uint64()
-    _lib.check(lib.borb_stage_times_total(ext._h, tot, C.byref(nst)), "borb_stage_times_total")
-    ext.set_timing(False)
-    stage_ms = {n: tot[i] / max(nst.value, 1) for i, n in enumerate(("upload", "pyramid", "fast_nms", "quadtree", "blur", "orient_brief", "stereo", "download"))}
+    _lib.check(lib.borb_stage_times_total(exts[0]._h, tot, C.byref(nst)), "borb_stage_times_total")
+    exts[0].set_timing(False)
+    stage_ms = {n: float(tot[i] / max(nst.value, 1)) for i, n in enumerate(("upload", "pyramid", "fast_nms", "quadtree", "blur", "orient_brief", "stereo", "download"))}
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -273,9 +293,6 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     value = world * B * K / (ms_max * 1e-3)
 
     # ---- timed region 2: end to end through the C ABI with HOST buffers (two handles, double-buffered)
-    exts = [ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank) for _ in range(2)]
-    for x in exts:
-        x.reserve(W_IMG, H_IMG, 2 * B)
     h_in = torch.from_numpy(host).pin_memory()                      # pinned staging of the camera frames
     outs = []
     for _ in range(2):
@@ -299,11 +316,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                                   o["nl"].data_ptr(), o["kr"].data_ptr(), o["dr"].data_ptr(), o["nr"].data_ptr(),
                                                   o["ur"].data_ptr(), o["dp"].data_ptr(), cap), "stereo_frames_enqueue")
 
-    def drain():
-        for x in exts:
-            _lib.check(lib.borb_sync(x._h), "borb_sync")
-
-    for k in range(max(Wm, 3)):
+    for k in range(max(Wm, 3) * 2):
         step_e2e(k)
     drain()
     if world > 1:
@@ -319,6 +332,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / (float(t2.item()) * 1e-3)
+    clk = clocks.stop()
     assert int(outs[0]["nl"].min()) >= NFEAT
     h2d = 2 * B * W_IMG * H_IMG
     d2h = B * (2 * cap * (28 + 32) + 2 * 4 + 2 * cap * 4)
@@ -382,11 +396,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per step per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-pairs-per-thread", type=int, default=24)
+    ap.add_argument("--cpu-pairs-per-thread", type=int, default=8)
     ap.add_argument("--ref-pairs-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-COUNTER_FIELDS = ("frames", "keypoints_left", "keypoints_right", "stereo_matches", "device_us")
+COUNTER_FIELDS = ("frames", "keypoints_left_last_batch", "keypoints_right_last_batch", "stereo_matches_last_batch", "device_us")
 
 
 def streams_for_rank(n_streams: int, rank: int, world_size: int) -> List[int]:
