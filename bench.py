@@ -227,7 +227,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     # Two handles (= two camera-stream batches in flight, each with its own CUDA stream) keep the GPU busy across the
     # dependent kernels of one batch; both timed regions use the same two handles.
-    exts = [ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank) for _ in range(2)]
+    NH = args.handles
+    exts = [ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank) for _ in range(NH)]
     ext = exts[0]
     cap = ext.capacity(W_IMG, H_IMG)
     for x in exts:
@@ -238,11 +239,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         sp = C.c_void_p()
         _lib.check(lib.borb_extractor_stream(x._h, C.byref(sp)), "borb_extractor_stream")
         streams.append(torch.cuda.ExternalStream(sp.value, device=dev))
-    n_lr = [(torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(2)]
+    n_lr = [(torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(NH)]
     n_left, n_right = n_lr[0]
 
     def step_resident(k):
-        x, (nl, nr) = exts[k % 2], n_lr[k % 2]
+        x, (nl, nr) = exts[k % NH], n_lr[k % NH]
         buf = d_in[k % NBUF]
         _lib.check(lib.borb_stereo_frames_device_enqueue(x._h, buf.data_ptr(), B, W_IMG, H_IMG, pitch, img_stride, BF, b,
                                                          nl.data_ptr(), nr.data_ptr(), None, None, cap), "stereo_frames_device_enqueue")
@@ -253,7 +254,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     clocks = Clocks(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
     clocks.start()          # sampled across warm-up and BOTH timed regions (continuous load)
-    for k in range(max(Wm, 3) * 2):
+    for k in range(max(Wm, 3) * NH):
         step_resident(k)
     drain()
     assert int(n_left.min()) >= NFEAT, "warm-up produced too few keypoints"
@@ -266,7 +267,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     e0 = torch.cuda.Event(enable_timing=True)
     e1s = [torch.cuda.Event(enable_timing=True) for _ in exts]
     e0.record(streams[0])
-    streams[1].wait_event(e0)              # both streams start after the common start mark
+    for st_ in streams[1:]:
+        st_.wait_event(e0)                 # every stream starts after the common start mark
     for k in range(K):
         step_resident(k)
     for ev, st_ in zip(e1s, streams):
@@ -278,7 +280,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # per-kernel device times: a short single-handle pass right after the timed region (with two batches in flight the
     # events of one stream would also count the other stream's kernels), CUDA events on the launching stream
     exts[0].set_timing(True)
-    for k in range(0, 2 * min(K, 16), 2):
+    for k in range(0, NH * min(K, 16), NH):
         step_resident(k)
     drain()
     tot = (C.c_double * 8)()
@@ -295,7 +297,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # ---- timed region 2: end to end through the C ABI with HOST buffers (two handles, double-buffered)
     h_in = torch.from_numpy(host).pin_memory()                      # pinned staging of the camera frames
     outs = []
-    for _ in range(2):
+    for _ in range(NH):
         o = dict(kl=torch.empty((B, cap, 28), dtype=torch.uint8).pin_memory(), kr=torch.empty((B, cap, 28), dtype=torch.uint8).pin_memory(),
                  dl=torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory(), dr=torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory(),
                  nl=torch.zeros(B, dtype=torch.int32).pin_memory(), nr=torch.zeros(B, dtype=torch.int32).pin_memory(),
@@ -309,14 +311,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         ptr_tabs.append((pl, pr))
 
     def step_e2e(k):
-        x, o = exts[k % 2], outs[k % 2]
+        x, o = exts[k % NH], outs[k % NH]
         _lib.check(lib.borb_sync(x._h), "borb_sync")               # previous use of this handle / its host buffers
         pl, pr = ptr_tabs[k % NBUF]
         _lib.check(lib.borb_stereo_frames_enqueue(x._h, pl, pr, B, W_IMG, H_IMG, W_IMG, BF, b, o["kl"].data_ptr(), o["dl"].data_ptr(),
                                                   o["nl"].data_ptr(), o["kr"].data_ptr(), o["dr"].data_ptr(), o["nr"].data_ptr(),
                                                   o["ur"].data_ptr(), o["dp"].data_ptr(), cap), "stereo_frames_enqueue")
 
-    for k in range(max(Wm, 3) * 2):
+    for k in range(max(Wm, 3) * NH):
         step_e2e(k)
     drain()
     if world > 1:
@@ -374,7 +376,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
                 "config": {"workload": "configs[1]: stereo KITTI-00-shaped 1242x375, 2000 feats, extract + ComputeStereoMatches",
-                           "pairs_per_step_per_gpu": B, "parallelism": f"{world} independent camera streams, one per GPU (no data-path collective)",
+                           "pairs_per_step_per_gpu": B, "batches_in_flight": NH, "parallelism": f"{world} independent camera streams, one per GPU (no data-path collective)",
                            "cache": f"inputs larger than L2: {NBUF} rotating batches x {2 * B * W_IMG * H_IMG / 1e6:.0f} MB input + {2 * B * 2 * 1.75:.0f} MB pyramids per step vs 126 MB L2"},
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -399,6 +401,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per step per GPU")
+    ap.add_argument("--handles", type=int, default=4, help="batches in flight per GPU (one CUDA stream each)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-pairs-per-thread", type=int, default=8)
     ap.add_argument("--ref-pairs-per-thread", type=int, default=4)

@@ -58,9 +58,11 @@ void init_tables(borb_extractor* e) {
     }
 }
 
-// cv::resize INTER_LINEAR 8U coefficient tables (OpenCV imgproc/resize.cpp): (offset, c0, c1) int16 triplets
-void resize_table(int src, int dst, bool clamp_edges, std::vector<int16_t>& out) {
+// cv::resize INTER_LINEAR 8U coefficient tables (OpenCV imgproc/resize.cpp): {offset, c0, c1, 0} int16 quadruples.
+// `extra` > 0 appends entries for the reflect-101 padding columns dst .. dst+extra-1 (copies of the reflected column).
+void resize_table(int src, int dst, bool clamp_edges, int extra, std::vector<int16_t>& out) {
     const double inv = (double)dst / src, scale = 1. / inv;
+    const size_t first = out.size();
     for (int d = 0; d < dst; d++) {
         float f = (float)((d + 0.5) * scale - 0.5);
         int s = (int)std::floor(f);
@@ -72,6 +74,12 @@ void resize_table(int src, int dst, bool clamp_edges, std::vector<int16_t>& out)
         out.push_back((int16_t)s);
         out.push_back((int16_t)cv_round_f((1.f - f) * 2048.f));
         out.push_back((int16_t)cv_round_f(f * 2048.f));
+        out.push_back(0);
+    }
+    for (int k = 0; k < extra; k++) {
+        int r = 2 * dst - 2 - (dst + k);            // reflect-101 of column dst+k
+        if (r < 0) r = 0;
+        for (int j = 0; j < 4; j++) out.push_back(out[first + (size_t)r * 4 + j]);
     }
 }
 
@@ -99,7 +107,7 @@ borb_status build_geometry(borb_extractor* e, int w, int h, std::vector<int16_t>
         }
         v.wCell = (int)std::ceil(width / v.nCols);
         v.hCell = (int)std::ceil(height / v.nRows);
-        v.pitch = align_up(v.w, 128);
+        v.pitch = align_up(v.w + 8, 128);          // >= 8 bytes of reflect-101 padding after every row
         v.pyr_off = pyr_off;
         pyr_off += (unsigned)v.pitch * v.h;
         v.cellsPerBlk = FAST_TILE_W / v.wCell > 0 ? FAST_TILE_W / v.wCell : 1;
@@ -123,10 +131,10 @@ borb_status build_geometry(borb_extractor* e, int w, int h, std::vector<int16_t>
         g.blur_base[l] = btile;
         btile += ((v.w + 127) / 128) * ((v.h + 63) / 64);   // blur_kernel: 128 x 64 strips
         if (l > 0) {
-            v.xtab_off = (unsigned)(tabs.size() / 3);
-            resize_table(g.lv[l - 1].w, v.w, true, tabs);
-            v.ytab_off = (unsigned)(tabs.size() / 3);
-            resize_table(g.lv[l - 1].h, v.h, false, tabs);
+            v.xtab_off = (unsigned)(tabs.size() / 4);
+            resize_table(g.lv[l - 1].w, v.w, true, ((v.w + 8 + 3) & ~3) - v.w, tabs);
+            v.ytab_off = (unsigned)(tabs.size() / 4);
+            resize_table(g.lv[l - 1].h, v.h, false, 0, tabs);
         }
         if (quadtree_smem_bytes(v.node_cap) > 200 * 1024) {
             set_error("per-level quota %d exceeds the quadtree kernel's shared-memory envelope", v.quota);
@@ -169,8 +177,8 @@ borb_status ensure(borb_extractor* e, int w, int h, int n_images) {
     e->pair_cache.clear();
     const Geometry& g = e->geom;
     Workspace& ws = e->ws;
-    BORB_CUDA(cudaMalloc(&ws.pyr, n * g.pyr_image_stride));
-    BORB_CUDA(cudaMalloc(&ws.blur, n * g.pyr_image_stride));
+    BORB_CUDA(cudaMalloc(&ws.pyr, n * g.pyr_image_stride + 256));      // +slack: aligned word reads may run a few bytes past the last row
+    BORB_CUDA(cudaMalloc(&ws.blur, n * g.pyr_image_stride + 256));
     BORB_CUDA(cudaMalloc(&ws.cand, n * g.cand_image_stride * sizeof(uint32_t)));
     BORB_CUDA(cudaMalloc(&ws.pnode, n * g.cand_image_stride * sizeof(int)));
     BORB_CUDA(cudaMalloc(&ws.cand_cnt, n * g.nlevels * sizeof(int)));

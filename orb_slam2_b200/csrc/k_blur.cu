@@ -5,6 +5,7 @@
 // tests/test_oracle_prims.py): separable kernel q = [18 34 48 56 48 34 18]/256; row pass exact u16,
 // column pass (sum + 2^15) >> 16; reflect-101 of the LEVEL itself at its borders.
 //
+// The right image edge needs no special case: every pyramid row ends in 8 bytes of reflect-101 padding.
 // v2: no shared memory.  A warp owns a 128-px wide strip (one aligned 32-bit word = 4 px per lane) and
 // slides down R rows: per input row one coalesced 128-byte load per warp, neighbour words by shuffle, the
 // row pass as two IDP.4A (dp4a) per pixel on PRMT-extracted byte windows, a 7-row register window for the
@@ -44,8 +45,6 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geome
     uint8_t* dst = blur + (size_t)img * g.pyr_image_stride + L.pyr_off;
     const int W = L.w, H = L.h, pitch = L.pitch;
     const bool left_edge = (x == 0);
-    // lanes whose 12-byte window [x-4, x+8) reaches past the last pixel need reflected bytes
-    const bool right_fix = (x + 8 > W);
     const unsigned WLO = 18u | (34u << 8) | (48u << 16) | (56u << 24);
     const unsigned WHI = 48u | (34u << 8) | (18u << 16);
 
@@ -66,18 +65,10 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geome
         uint32_t W0 = __shfl_up_sync(0xFFFFFFFFu, W1, 1);
         uint32_t W2 = __shfl_down_sync(0xFFFFFFFFu, W1, 1);
         if (lane == 0 && !left_edge) W0 = *reinterpret_cast<const uint32_t*>(row + x - 4);
+        // rows carry >= 8 bytes of reflect-101 padding after the last pixel (k_pyramid.cu), so the word after the last
+        // pixel word is valid data for the right image edge too
         if (lane == 31 && x + 4 < pitch) W2 = *reinterpret_cast<const uint32_t*>(row + x + 4);
         if (left_edge) W0 = __byte_perm(W1, W2, 0x1234);  // bytes -4..-1 = pixels 4,3,2,1 (reflect-101)
-        if (right_fix) {
-            // rebuild the window byte by byte with reflected indices (only the 1-3 lanes at the right image edge)
-            uint32_t w[3] = {0, 0, 0};
-#pragma unroll
-            for (int b = 0; b < 12; b++) {
-                const int sx = reflect101(x - 4 + b, W);
-                w[b >> 2] |= (uint32_t)row[sx] << (8 * (b & 3));
-            }
-            W0 = w[0]; W1 = w[1]; W2 = w[2];
-        }
         int* r = win[step % 7];
         r[0] = __dp4a(__byte_perm(W0, W1, 0x4321), WLO, __dp4a(__byte_perm(W1, W2, 0x4321), WHI, 0u));
         r[1] = __dp4a(__byte_perm(W0, W1, 0x5432), WLO, __dp4a(__byte_perm(W1, W2, 0x5432), WHI, 0u));

@@ -94,9 +94,6 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
                                                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ sel,
                                                        const int* __restrict__ sel_cnt, borb_keypoint* __restrict__ kps,
                                                        uint8_t* __restrict__ desc, int* __restrict__ nkp) {
-    __shared__ int8_t pat[1024];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<int*>(pat)[i] = reinterpret_cast<const int*>(d_pattern)[i];
-    __syncthreads();
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -115,18 +112,22 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
     const size_t lvl_off = (size_t)img * g.pyr_image_stride + L.pyr_off;
     // ---- IC_Angle
     const uint8_t* c0 = pyr + lvl_off + (size_t)py * L.pitch + px;
-    int m01 = 0, m10 = 0;
+    // lane = column u of the 31x31 window; the disc is symmetric (umax[v] >= |u| <=> |v| <= umax[|u|]), so a lane's
+    // rows are |v| <= vmax.  m10 = sum_u u * (column sum), m01 = sum_v v * I(u,v): one add + one multiply-add per row.
+    int m01 = 0, colsum = 0;
     const int u = lane - HALF_PATCH;
-    if (lane < 31) {
-        for (int vv = -HALF_PATCH; vv <= HALF_PATCH; vv++) {
-            const int d = g.umax[vv < 0 ? -vv : vv];
-            if (u >= -d && u <= d) {
-                const int val = c0[vv * L.pitch + u];
-                m10 += u * val;
-                m01 += vv * val;
-            }
+    const int vmax = lane < 31 ? g.umax[u < 0 ? -u : u] : -1;
+    const uint8_t* col = c0 + u - HALF_PATCH * L.pitch;      // top of this lane's column; walks down one row per step
+#pragma unroll
+    for (int vv = -HALF_PATCH; vv <= HALF_PATCH; vv++) {
+        if ((vv < 0 ? -vv : vv) <= vmax) {
+            const int val = *col;
+            colsum += val;
+            m01 += vv * val;
         }
+        col += L.pitch;
     }
+    int m10 = u * colsum;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, off);
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const int tI = j * 32 + lane;
-        const char4 pp = reinterpret_cast<const char4*>(pat)[tI];
+        const char4 pp = __ldg(reinterpret_cast<const char4*>(d_pattern) + tI);     // 1 KB table, L1 resident
         const float x0 = (float)pp.x, y0 = (float)pp.y, x1 = (float)pp.z, y1 = (float)pp.w;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
