@@ -197,6 +197,28 @@ typedef struct borb_mappoint_view {
 BORB_API borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* frame, const borb_mappoint_view* mps,
                                                float th, float nnratio, int32_t* match_feat, int32_t* n_matches);
 
+/* LastFrame snapshot for the motion-model search: per last-frame feature i the keypoint (octave, angle of mvKeysUn), the
+ * world position and representative descriptor of its MapPoint, valid[i] = mvpMapPoints[i] && !mvbOutlier[i],
+ * has_obs[i] = mvpMapPoints[i]->Observations()>0. */
+typedef struct borb_lastframe_view {
+    int32_t n;
+    const borb_keypoint* keys_un;  /* LastFrame.mvKeysUn (octave == mvKeys[i].octave) */
+    const float* world_pos;        /* n x 3, pMP->GetWorldPos() */
+    const uint8_t* desc;           /* n x 32, pMP->GetDescriptor() */
+    const uint8_t* valid;          /* NULL: all valid */
+    const uint8_t* has_obs;        /* NULL: all */
+} borb_lastframe_view;
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470
+ * (Tracking::TrackWithMotionModel, src/Tracking.cc:885,891).  Tcw = CurrentFrame.mTcw rows 0..2 (3x4 row-major);
+ * forward/backward = the bForward/bBackward flags of :1348-1349 (a few float ops on the two poses, computed by the caller).
+ * state_cur[i2] (cur->n entries): >=0 = index of the LastFrame feature whose MapPoint now sits in
+ * CurrentFrame.mvpMapPoints[i2]; -1 = untouched; -2 = set to NULL by the rotation-consistency cull (:1456-1466). */
+BORB_API borb_status borb_search_by_projection_last(borb_matcher* m, const borb_frame_view* cur, const borb_lastframe_view* last,
+                                                    const float* Tcw, float fx, float fy, float cx, float cy, float bf, float th,
+                                                    int forward, int backward, int check_orientation, int32_t* state_cur,
+                                                    int32_t* n_matches);
+
 /* DBoW2::FeatureVector (ordered map NodeId -> feature indices) as CSR; node_id ascending. */
 typedef struct borb_featvec_view {
     int32_t n_nodes;

@@ -240,6 +240,23 @@ def port_search_by_projection(F, mps, th, nnratio):
     return n, match[:len(px)]
 
 
+def port_search_by_projection_last(Cur, Last, Tcw, K, bf, th, forward, backward, check_ori):
+    lib = _plib()
+    k = _a(Cur.mvKeysUn, KP_DTYPE); d = _a(Cur.mDescriptors, np.uint8); ur = _a(Cur.mvuRight, np.float32); oc = _a(Cur.occupied, np.uint8)
+    sf = _a(Cur.mvScaleFactors, np.float32)
+    lk = _a(Last.mvKeysUn, KP_DTYPE); wp = _a(Last.world_pos, np.float32); ld = _a(Last.descriptors, np.uint8)
+    va = _a(Last.valid, np.uint8); ho = _a(Last.has_obs, np.uint8)
+    T = _a(np.asarray(Tcw, np.float32)[:3, :4].reshape(12), np.float32)
+    state = np.full(max(len(k), 1), -1, np.int32)
+    fn = lib.orbport_search_by_projection_last
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p] * 6 + [C.c_int, C.c_void_p] + [C.c_float] * 6 + [C.c_int] * 3 + [C.c_void_p]
+    n = fn(_ptr(k), _ptr(d), _ptr(ur), _ptr(oc), len(k), *[float(b) for b in Cur.bounds], _ptr(sf), _ptr(lk), _ptr(wp), _ptr(ld), _ptr(va),
+           _ptr(ho), len(lk), _ptr(T), float(K[0]), float(K[1]), float(K[2]), float(K[3]), float(bf), float(th), int(forward), int(backward),
+           int(check_ori), _ptr(state))
+    return n, state[:len(k)]
+
+
 def _kf_args(kf):
     k = _a(kf.mvKeysUn, KP_DTYPE); d = _a(kf.mDescriptors, np.uint8)
     hm = _a(kf.has_mp, np.uint8) if kf.has_mp is not None else np.zeros(len(k), np.uint8)

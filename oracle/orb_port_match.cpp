@@ -441,3 +441,68 @@ void orbport_voc_transform(void* h, const uint8_t* desc, int n, int levelsup, in
 }
 
 }  // extern "C"
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470.
+// world_pos: x3Dw of LastFrame.mvpMapPoints[i] (n_last x 3); valid[i] = pMP && !mvbOutlier[i]; has_obs[i] = pMP->Observations()>0;
+// Tcw: CurrentFrame.mTcw rows 0..2 (3x4 row-major).  forward/backward: the bForward / bBackward flags of :1348-1349
+// (computed by the caller from the two poses).  cv::Mat products are float32 (r0*p0 + r1*p1) + r2*p2, then + t.
+// state_cur[i2]: >=0 index of the LastFrame feature whose MapPoint ended up in CurrentFrame.mvpMapPoints[i2]; -1 untouched;
+// -2 set to NULL by the rotation-consistency cull (:1456-1466).
+extern "C" int orbport_search_by_projection_last(const orbport_kp* cur_keys_un, const uint8_t* cur_desc, const float* cur_u_right,
+                                                 const uint8_t* cur_occupied, int n_cur, float minX, float minY, float maxX, float maxY,
+                                                 const float* scale_factors, const orbport_kp* last_keys, const float* world_pos,
+                                                 const uint8_t* last_desc, const uint8_t* valid, const uint8_t* has_obs, int n_last,
+                                                 const float* Tcw, float fx, float fy, float cx, float cy, float bf, float th, int forward,
+                                                 int backward, int check_ori, int32_t* state_cur) {
+    Grid g = build_grid(cur_keys_un, n_cur, minX, minY, maxX, maxY);
+    std::vector<char> held(n_cur, 0);
+    for (int i = 0; i < n_cur; i++) { held[i] = cur_occupied ? (cur_occupied[i] != 0) : 0; state_cur[i] = -1; }
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < n_last; i++) {
+        if (valid && !valid[i]) continue;
+        const float* P = world_pos + 3 * (size_t)i;
+        const float xc = ((Tcw[0] * P[0] + Tcw[1] * P[1]) + Tcw[2] * P[2]) + Tcw[3];
+        const float yc = ((Tcw[4] * P[0] + Tcw[5] * P[1]) + Tcw[6] * P[2]) + Tcw[7];
+        const float zc = ((Tcw[8] * P[0] + Tcw[9] * P[1]) + Tcw[10] * P[2]) + Tcw[11];
+        const float invzc = 1.0 / zc;
+        if (invzc < 0) continue;
+        const float u = fx * xc * invzc + cx;
+        const float v = fy * yc * invzc + cy;
+        if (u < minX || u > maxX) continue;
+        if (v < minY || v > maxY) continue;
+        const int nLastOctave = last_keys[i].octave;
+        const float radius = th * scale_factors[nLastOctave];
+        std::vector<int> vIndices2;
+        if (forward) vIndices2 = features_in_area(g, cur_keys_un, u, v, radius, nLastOctave, -1);
+        else if (backward) vIndices2 = features_in_area(g, cur_keys_un, u, v, radius, 0, nLastOctave);
+        else vIndices2 = features_in_area(g, cur_keys_un, u, v, radius, nLastOctave - 1, nLastOctave + 1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = last_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (held[i2]) continue;
+            if (cur_u_right && cur_u_right[i2] > 0) {
+                const float ur = u - bf * invzc;
+                const float er = std::fabs(ur - cur_u_right[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = orbport_hamming(dMP, cur_desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            state_cur[bestIdx2] = i;
+            held[bestIdx2] = has_obs ? (has_obs[i] != 0) : 1;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(last_keys[i].angle, cur_keys_un[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j : rotHist[i]) { state_cur[j] = -2; nmatches--; }
+    }
+    return nmatches;
+}

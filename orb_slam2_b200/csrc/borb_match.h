@@ -27,6 +27,29 @@ struct ProjArgs {                 // device pointers
     float th, nnratio;
     uint32_t* cand;               // n_mp x n
     int* cand_cnt;                // n_mp
+    // mode 1 (SearchByProjection(CurrentFrame, LastFrame)): the window is precomputed per query by project_last_kernel
+    const float* q_radius;        // null in mode 0
+    const int32_t* q_minl;
+    const int32_t* q_maxl;
+    int mode;                     // 0: local map points (ratio test), 1: last frame (best only, rotation histogram)
+    int check_ori;
+    const float* q_angle;         // mode 1: mvKeysUn[i].angle of the query
+    uint8_t* q_valid_out;         // mode 1: validity written by project_last_kernel (aliases mp_valid)
+};
+
+struct LastArgs {                 // inputs of project_last_kernel
+    int n_last;
+    const borb_keypoint* last_keys;
+    const float* world_pos;       // n_last x 3
+    const uint8_t* valid_in;      // may be null
+    float T[12];                  // Tcw rows 0..2
+    float fx, fy, cx, cy, bf, th;
+    float minX, minY, maxX, maxY;
+    const float* scale_factors;
+    int forward, backward;
+    float *proj_x, *proj_y, *proj_xr, *radius, *angle;
+    int32_t *minl, *maxl;
+    uint8_t* valid_out;
 };
 
 struct KfDev {                    // device-side borb_keyframe_view
@@ -56,6 +79,8 @@ struct VocDev {                   // views into the packed blob
 int launch_grid_sort(const borb_keypoint* keys, int n, float minX, float minY, float invW, float invH, int* cell_start, int* cell_idx,
                      cudaStream_t s);
 int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s);
+int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_cur, int32_t* hist_idx, uint8_t* hist_bin, int* n_matches,
+                           cudaStream_t s);
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
                      int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s);
 int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,

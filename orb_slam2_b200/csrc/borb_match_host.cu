@@ -219,10 +219,82 @@ borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F,
     A.mp_valid = P->valid ? b + o_val : nullptr; A.mp_has_obs = P->has_obs ? b + o_obs : nullptr;
     A.th = th; A.nnratio = nnratio;
     A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
+    A.q_radius = nullptr; A.q_minl = nullptr; A.q_maxl = nullptr; A.mode = 0; A.check_ori = 0; A.q_angle = nullptr; A.q_valid_out = nullptr;
     m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
     m->launches += launch_projection(A, (int32_t*)(b + o_match), (int*)(b + o_nm), m->stream);
     BORB_CUDA(cudaGetLastError());
     BORB_CUDA(cudaMemcpyAsync(match_feat, b + o_match, (size_t)P->n * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    return BORB_OK;
+}
+
+borb_status borb_search_by_projection_last(borb_matcher* m, const borb_frame_view* F, const borb_lastframe_view* Lf, const float* Tcw,
+                                           float fx, float fy, float cx, float cy, float bf, float th, int forward, int backward,
+                                           int check_orientation, int32_t* state_cur, int32_t* n_matches) {
+    if (!m || !F || !Lf || !Tcw || !state_cur || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *n_matches = 0;
+    if (F->n < 0 || F->n > MATCH_MAX_FEATURES || Lf->n < 0 || Lf->n > MATCH_MAX_FEATURES) { set_error("feature count outside [0,%d]", MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    for (int i = 0; i < F->n; i++) state_cur[i] = -1;
+    if (F->n == 0 || Lf->n == 0) return BORB_OK;
+    if (!F->keys_un || !F->desc || !F->scale_factors || !Lf->keys_un || !Lf->world_pos || !Lf->desc || !(F->max_x > F->min_x) || !(F->max_y > F->min_y)) {
+        set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG;
+    }
+    for (int i = 0; i < Lf->n; i++)
+        if (Lf->keys_un[i].octave < 0 || Lf->keys_un[i].octave >= F->n_levels) { set_error("last-frame keypoint %d: octave out of range", i); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(m->device));
+    Stager st(m);
+    const int nq = Lf->n;
+    const size_t o_keys = st.add(F->keys_un, (size_t)F->n * sizeof(borb_keypoint));
+    const size_t o_desc = st.add(F->desc, (size_t)F->n * 32);
+    const size_t o_ur = F->u_right ? st.add(F->u_right, (size_t)F->n * 4) : 0;
+    const size_t o_occ = F->occupied ? st.add(F->occupied, (size_t)F->n) : 0;
+    const size_t o_sf = st.add(F->scale_factors, (size_t)F->n_levels * 4);
+    const size_t o_lk = st.add(Lf->keys_un, (size_t)nq * sizeof(borb_keypoint));
+    const size_t o_wp = st.add(Lf->world_pos, (size_t)nq * 12);
+    const size_t o_md = st.add(Lf->desc, (size_t)nq * 32);
+    const size_t o_vin = Lf->valid ? st.add(Lf->valid, (size_t)nq) : 0;
+    const size_t o_obs = Lf->has_obs ? st.add(Lf->has_obs, (size_t)nq) : 0;
+    const size_t input_end = st.off;
+    const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
+    const size_t o_px = st.reserve((size_t)nq * 4), o_py = st.reserve((size_t)nq * 4), o_pxr = st.reserve((size_t)nq * 4), o_rad = st.reserve((size_t)nq * 4);
+    const size_t o_ang = st.reserve((size_t)nq * 4), o_minl = st.reserve((size_t)nq * 4), o_maxl = st.reserve((size_t)nq * 4), o_val = st.reserve((size_t)nq);
+    const size_t o_cand = st.reserve((size_t)nq * F->n * 4), o_cc = st.reserve((size_t)nq * 4);
+    const size_t o_state = st.reserve((size_t)F->n * 4), o_evi = st.reserve((size_t)nq * 4), o_evb = st.reserve((size_t)nq), o_nm = st.reserve(16);
+    const size_t total = st.off;
+    st.off = input_end;
+    borb_status s = commit(st, total);
+    if (s != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    LastArgs L;
+    L.n_last = nq; L.last_keys = (const borb_keypoint*)(b + o_lk); L.world_pos = (const float*)(b + o_wp);
+    L.valid_in = Lf->valid ? b + o_vin : nullptr;
+    for (int i = 0; i < 12; i++) L.T[i] = Tcw[i];
+    L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.bf = bf; L.th = th;
+    L.minX = F->min_x; L.minY = F->min_y; L.maxX = F->max_x; L.maxY = F->max_y;
+    L.scale_factors = (const float*)(b + o_sf);
+    L.forward = forward; L.backward = backward;
+    L.proj_x = (float*)(b + o_px); L.proj_y = (float*)(b + o_py); L.proj_xr = (float*)(b + o_pxr); L.radius = (float*)(b + o_rad);
+    L.angle = (float*)(b + o_ang); L.minl = (int32_t*)(b + o_minl); L.maxl = (int32_t*)(b + o_maxl); L.valid_out = b + o_val;
+    ProjArgs A;
+    A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
+    A.u_right = F->u_right ? (const float*)(b + o_ur) : nullptr;
+    A.occupied = F->occupied ? b + o_occ : nullptr;
+    A.minX = F->min_x; A.minY = F->min_y;
+    A.invW = (float)GRID_COLS / (float)(F->max_x - F->min_x);
+    A.invH = (float)GRID_ROWS / (float)(F->max_y - F->min_y);
+    A.scale_factors = (const float*)(b + o_sf);
+    A.cell_start = (const int*)(b + o_cs); A.cell_idx = (const int*)(b + o_ci);
+    A.n_mp = nq; A.proj_x = L.proj_x; A.proj_y = L.proj_y; A.proj_xr = L.proj_xr; A.view_cos = nullptr; A.level = nullptr;
+    A.mp_desc = b + o_md; A.mp_valid = b + o_val; A.mp_has_obs = Lf->has_obs ? b + o_obs : nullptr;
+    A.th = th; A.nnratio = 0.f;
+    A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
+    A.q_radius = L.radius; A.q_minl = L.minl; A.q_maxl = L.maxl; A.mode = 1; A.check_ori = check_orientation; A.q_angle = L.angle;
+    A.q_valid_out = b + o_val;
+    m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
+    m->launches += launch_projection_last(L, A, (int32_t*)(b + o_state), (int32_t*)(b + o_evi), b + o_evb, (int*)(b + o_nm), m->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaMemcpyAsync(state_cur, b + o_state, (size_t)F->n * 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaStreamSynchronize(m->stream));
     return BORB_OK;

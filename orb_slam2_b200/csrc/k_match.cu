@@ -114,10 +114,17 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
     uint32_t* out = A.cand + (size_t)iMP * A.n;
     int count = 0;
     if (A.mp_valid == nullptr || A.mp_valid[iMP]) {
-        const int lvl = A.level[iMP];
-        float r = A.view_cos[iMP] > 0.998 ? 2.5f : 4.0f;     // RadiusByViewingCos (:131-137)
-        if (A.th != 1.0f) r = __fmul_rn(r, A.th);
-        const float rs = __fmul_rn(r, A.scale_factors[lvl]);
+        float rs;
+        int minLevel, maxLevel;
+        if (A.mode == 0) {
+            const int lvl = A.level[iMP];
+            float r = A.view_cos[iMP] > 0.998 ? 2.5f : 4.0f;     // RadiusByViewingCos (:131-137)
+            if (A.th != 1.0f) r = __fmul_rn(r, A.th);
+            rs = __fmul_rn(r, A.scale_factors[lvl]);
+            minLevel = lvl - 1; maxLevel = lvl;
+        } else {
+            rs = A.q_radius[iMP]; minLevel = A.q_minl[iMP]; maxLevel = A.q_maxl[iMP];
+        }
         const float x = A.proj_x[iMP], y = A.proj_y[iMP];
         // GetFeaturesInArea(x, y, rs, lvl-1, lvl)  (Frame.cc:327-380)
         const int c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, A.minX), rs), A.invW)));
@@ -125,7 +132,6 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
         const int c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, A.minY), rs), A.invH)));
         const int c1y = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, A.minY), rs), A.invH)));
         if (!(c0x >= GRID_COLS || c1x < 0 || c0y >= GRID_ROWS || c1y < 0)) {
-            const int minLevel = lvl - 1, maxLevel = lvl;
             const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
             const uint32_t* dm = reinterpret_cast<const uint32_t*>(A.mp_desc + (size_t)iMP * 32);
             const float xr = A.proj_xr[iMP];
@@ -218,6 +224,104 @@ __global__ void __launch_bounds__(32) proj_resolve_kernel(ProjArgs A, int32_t* _
         }
         if (lane == 0) match_feat[iMP] = m;
         __syncwarp();
+    }
+    if (lane == 0) *n_matches = nm;
+}
+
+// SearchByProjection(CurrentFrame, LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470.  Projection of the last frame's
+// map points with the current pose (float32 (r0*p0 + r1*p1) + r2*p2, then + t: cv::Mat product order) and the search window.
+__global__ void __launch_bounds__(256) project_last_kernel(LastArgs L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n_last) return;
+    bool ok = L.valid_in == nullptr || L.valid_in[i] != 0;
+    float u = 0.f, v = 0.f, ur = 0.f, radius = 0.f;
+    int minl = 0, maxl = -1;
+    if (ok) {
+        const float* P = L.world_pos + 3 * (size_t)i;
+        const float p0 = P[0], p1 = P[1], p2 = P[2];
+        const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[0], p0), __fmul_rn(L.T[1], p1)), __fmul_rn(L.T[2], p2)), L.T[3]);
+        const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[4], p0), __fmul_rn(L.T[5], p1)), __fmul_rn(L.T[6], p2)), L.T[7]);
+        const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[8], p0), __fmul_rn(L.T[9], p1)), __fmul_rn(L.T[10], p2)), L.T[11]);
+        const float invzc = (float)(1.0 / (double)zc);                       // 1.0/x3Dc.at<float>(2) (:1365)
+        if (invzc < 0) ok = false;
+        u = __fadd_rn(__fmul_rn(__fmul_rn(L.fx, xc), invzc), L.cx);
+        v = __fadd_rn(__fmul_rn(__fmul_rn(L.fy, yc), invzc), L.cy);
+        if (u < L.minX || u > L.maxX || v < L.minY || v > L.maxY) ok = false;
+        if (!(u == u) || !(v == v)) ok = false;                               // NaN never passes the reference's range tests either
+        const int oct = L.last_keys[i].octave;
+        radius = __fmul_rn(L.th, L.scale_factors[oct]);
+        if (L.forward) { minl = oct; maxl = -1; }
+        else if (L.backward) { minl = 0; maxl = oct; }
+        else { minl = oct - 1; maxl = oct + 1; }
+        ur = __fsub_rn(u, __fmul_rn(L.bf, invzc));
+    }
+    L.proj_x[i] = u; L.proj_y[i] = v; L.proj_xr[i] = ur; L.radius[i] = radius; L.minl[i] = minl; L.maxl[i] = maxl;
+    L.angle[i] = L.last_keys[i].angle;
+    L.valid_out[i] = ok ? 1 : 0;
+}
+
+// One warp replays the last frame's map points in order: best candidate only (:1397-1424), occupancy by observations,
+// rotation histogram over the MATCH EVENTS (a feature re-claimed later appears twice, exactly as rotHist does).
+__global__ void __launch_bounds__(32) proj_resolve_last_kernel(ProjArgs A, const borb_keypoint* __restrict__ cur_keys,
+                                                               int32_t* __restrict__ state_cur, int32_t* __restrict__ ev_idx,
+                                                               uint8_t* __restrict__ ev_bin, int* __restrict__ n_matches) {
+    extern __shared__ uint32_t held[];
+    __shared__ int hist[32];
+    const int lane = threadIdx.x;
+    const int words = (A.n + 31) / 32;
+    for (int w = lane; w < words; w += 32) {
+        uint32_t bits = 0;
+        if (A.occupied != nullptr)
+            for (int b = 0; b < 32; b++) {
+                const int i = w * 32 + b;
+                if (i < A.n && A.occupied[i]) bits |= 1u << b;
+            }
+        held[w] = bits;
+    }
+    for (int i = lane; i < A.n; i += 32) state_cur[i] = -1;
+    hist[lane] = 0;
+    __syncwarp();
+    int nev = 0;
+    for (int iq = 0; iq < A.n_mp; iq++) {
+        const int cnt = A.cand_cnt[iq];
+        const uint32_t* c = A.cand + (size_t)iq * A.n;
+        unsigned k1 = 0xFFFFFFFFu;
+        for (int p = lane; p < cnt; p += 32) {
+            const uint32_t e = c[p];
+            const int idx = e & 0xFFFF;
+            if ((held[idx >> 5] >> (idx & 31)) & 1u) continue;
+            k1 = min(k1, (((e >> 16) & 0x1FFu) << 16) | (unsigned)p);
+        }
+        const unsigned best = warp_min(k1);
+        if (best != 0xFFFFFFFFu && (int)(best >> 16) <= TH_HIGH) {
+            const int m = (int)(c[best & 0xFFFFu] & 0xFFFF);
+            if (lane == 0) {
+                state_cur[m] = iq;
+                if (A.mp_has_obs == nullptr || A.mp_has_obs[iq]) held[m >> 5] |= 1u << (m & 31);
+                ev_idx[nev] = m;
+                if (A.check_ori) {
+                    const int b = rot_bin(A.q_angle[iq], cur_keys[m].angle);
+                    ev_bin[nev] = (uint8_t)b;
+                    hist[b]++;
+                }
+            }
+            nev++;
+        }
+        __syncwarp();
+    }
+    int nm = nev;
+    if (A.check_ori) {
+        int i1, i2, i3;
+        three_maxima(hist, i1, i2, i3);
+        // serial cull in histogram-bin order is order independent for the final state: every event of a culled bin nulls its feature
+        int removed = 0;
+        for (int e = lane; e < nev; e += 32) {
+            const int b = ev_bin[e];
+            if (b != i1 && b != i2 && b != i3) { state_cur[ev_idx[e]] = -2; removed++; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, off);
+        nm -= removed;
     }
     if (lane == 0) *n_matches = nm;
 }
@@ -441,6 +545,16 @@ int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cu
     const int words = (A.n + 31) / 32;
     proj_resolve_kernel<<<1, 32, words * 4, s>>>(A, match_feat, n_matches);
     return 2;
+}
+int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_cur, int32_t* ev_idx, uint8_t* ev_bin, int* n_matches,
+                           cudaStream_t s) {
+    if (L.n_last > 0) {
+        project_last_kernel<<<(L.n_last + 255) / 256, 256, 0, s>>>(L);
+        proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
+    }
+    const int words = (A.n + 31) / 32;
+    proj_resolve_last_kernel<<<1, 32, words * 4, s>>>(A, A.keys, state_cur, ev_idx, ev_bin, n_matches);
+    return 3;
 }
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
                      int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s) {

@@ -30,6 +30,11 @@ class _MapPointViewC(C.Structure):
                 ("view_cos", C.c_void_p), ("desc", C.c_void_p), ("valid", C.c_void_p), ("has_obs", C.c_void_p)]
 
 
+class _LastFrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("world_pos", C.c_void_p), ("desc", C.c_void_p), ("valid", C.c_void_p),
+                ("has_obs", C.c_void_p)]
+
+
 class _FeatVecC(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("start", C.c_void_p), ("feat_idx", C.c_void_p)]
 
@@ -89,6 +94,16 @@ class MapPointsView:
     descriptors: np.ndarray
     valid: Optional[np.ndarray] = None                    # mbTrackInView && !isBad()
     has_obs: Optional[np.ndarray] = None                  # Observations()>0
+
+
+@dataclass
+class LastFrameView:
+    """What SearchByProjection(CurrentFrame, LastFrame, ...) reads of LastFrame and of its MapPoints."""
+    mvKeysUn: np.ndarray
+    world_pos: np.ndarray                                  # (N,3) float32, pMP->GetWorldPos()
+    descriptors: np.ndarray                                # (N,32), pMP->GetDescriptor()
+    valid: Optional[np.ndarray] = None                     # mvpMapPoints[i] && !mvbOutlier[i]
+    has_obs: Optional[np.ndarray] = None                   # Observations()>0
 
 
 @dataclass
@@ -165,6 +180,28 @@ class ORBmatcher:
         check(self._lib.borb_search_by_projection(self._h, C.byref(fv), C.byref(mv), float(th), self.mfNNratio, _p(match), C.byref(n)),
               "borb_search_by_projection")
         return n.value, match[:len(px)]
+
+    def SearchByProjectionLast(self, Cur: FrameView, Last: LastFrameView, Tcw: np.ndarray, K: Tuple[float, float, float, float], bf: float,
+                               th: float, bForward: bool = False, bBackward: bool = False) -> Tuple[int, np.ndarray]:
+        """SearchByProjection(CurrentFrame, LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470.  Tcw: (3,4) or (4,4) current pose;
+        K = (fx, fy, cx, cy).  Returns (nmatches, state[cur.N]): >=0 last-frame index now matched, -1 untouched, -2 culled."""
+        k = np.ascontiguousarray(Cur.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(Cur.mDescriptors, np.uint8)
+        ur = np.ascontiguousarray(Cur.mvuRight, np.float32) if Cur.mvuRight is not None else None
+        oc = np.ascontiguousarray(Cur.occupied, np.uint8) if Cur.occupied is not None else None
+        sf = np.ascontiguousarray(Cur.mvScaleFactors, np.float32)
+        fv = _FrameViewC(len(k), _p(k), _p(d), _p(ur), _p(oc), *[float(x) for x in Cur.bounds], len(sf), _p(sf))
+        lk = np.ascontiguousarray(Last.mvKeysUn, KP_DTYPE); wp = np.ascontiguousarray(Last.world_pos, np.float32)
+        ld = np.ascontiguousarray(Last.descriptors, np.uint8)
+        va = np.ascontiguousarray(Last.valid, np.uint8) if Last.valid is not None else None
+        ho = np.ascontiguousarray(Last.has_obs, np.uint8) if Last.has_obs is not None else None
+        lv = _LastFrameViewC(len(lk), _p(lk), _p(wp), _p(ld), _p(va), _p(ho))
+        T = np.ascontiguousarray(np.asarray(Tcw, np.float32)[:3, :4]).reshape(12)
+        state = np.full(max(len(k), 1), -1, np.int32)
+        n = C.c_int32(0)
+        check(self._lib.borb_search_by_projection_last(self._h, C.byref(fv), C.byref(lv), _p(T), float(K[0]), float(K[1]), float(K[2]), float(K[3]),
+                                                       float(bf), float(th), int(bForward), int(bBackward), int(self.mbCheckOrientation),
+                                                       _p(state), C.byref(n)), "borb_search_by_projection_last")
+        return n.value, state[:len(k)]
 
     def SearchByBoW(self, pKF, F: KeyFrameView):
         """SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) — src/ORBmatcher.cc:159-288.  pKF may be one KeyFrameView or a

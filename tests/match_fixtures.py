@@ -54,3 +54,31 @@ def rectified_F12(seed):
     rng = np.random.default_rng(seed)
     F = np.array([[0, 0, 0], [0, 0, 1], [0, -1, 0]], np.float32)
     return (F + rng.normal(0, 2e-6, (3, 3))).astype(np.float32)
+
+
+def last_frame_case(v, seed, K=(525.0, 525.0, 319.5, 239.5), jitter=2.0):
+    """Current frame = left view; LastFrame = right view whose MapPoints project (through a non-trivial pose) close to
+    their true correspondences in the left view."""
+    from orb_slam2_b200.matcher import LastFrameView
+    rng = np.random.default_rng(seed)
+    w, h = v["w"], v["h"]
+    fx, fy, cx, cy = K
+    Cur = FrameView(mvKeysUn=v["kl"], mDescriptors=v["dl"], mvScaleFactors=v["scale"], bounds=(0.0, 0.0, float(w), float(h)),
+                    mvuRight=v["ur"], occupied=(rng.random(len(v["kl"])) < 0.05).astype(np.uint8))
+    kr = v["kr"]
+    d = v["disp"][np.clip(kr["y"].astype(int), 0, h - 1), np.clip(kr["x"].astype(int), 0, w - 1)]
+    uA = kr["x"] + d + rng.normal(0, jitter, len(kr))
+    vA = kr["y"] + rng.normal(0, jitter, len(kr))
+    z = rng.uniform(2.0, 40.0, len(kr))
+    Pc = np.stack([(uA - cx) * z / fx, (vA - cy) * z / fy, z], 1)
+    z[rng.random(len(kr)) < 0.03] *= -1.0                      # a few points behind the camera (invzc < 0)
+    Pc[:, 2] = z
+    ang = 0.05
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]) @ \
+        np.array([[1, 0, 0], [0, np.cos(0.02), -np.sin(0.02)], [0, np.sin(0.02), np.cos(0.02)]])
+    t = np.array([0.3, -0.1, 0.5])
+    Pw = (Pc - t) @ R                                             # R^T (Pc - t)
+    Tcw = np.zeros((3, 4), np.float32); Tcw[:, :3] = R; Tcw[:, 3] = t
+    Last = LastFrameView(mvKeysUn=kr, world_pos=Pw.astype(np.float32), descriptors=v["dr"],
+                         valid=(rng.random(len(kr)) < 0.9).astype(np.uint8), has_obs=(rng.random(len(kr)) < 0.9).astype(np.uint8))
+    return Cur, Last, Tcw, K

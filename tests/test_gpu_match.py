@@ -117,3 +117,18 @@ def test_vocabulary_transform_and_blob_round_trip(M, oracle, views, tmp_path):
     bow, fv = voc.transform(views[7]["dl"], 4)
     assert abs(sum(bow.values()) - 1.0) < 1e-9 and list(bow) == sorted(bow)
     assert np.all(np.diff(fv.node_id.astype(np.int64)) > 0) and fv.start[-1] == len(views[7]["dl"])
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("mode", [(False, False), (True, False), (False, True)])
+@pytest.mark.parametrize("th,ori", [(7.0, True), (15.0, True), (15.0, False)])
+def test_search_by_projection_from_last_frame(M, oracle, views, seed, mode, th, ori):
+    """SearchByProjection(CurrentFrame, LastFrame, th, bMono), src/ORBmatcher.cc:1328-1470 (TrackWithMotionModel)."""
+    Cur, Last, Tcw, K = mf.last_frame_case(views[seed], seed + 20)
+    fw, bw = mode
+    n_o, s_o = oracle.port_search_by_projection_last(Cur, Last, Tcw, K, 40.0, th, fw, bw, ori)
+    n_g, s_g = M.ORBmatcher(0.9, ori).SearchByProjectionLast(Cur, Last, Tcw, K, 40.0, th, fw, bw)
+    assert n_o > 20
+    assert n_g == n_o and np.array_equal(s_g, s_o), int((s_g != s_o).sum())
+    m = s_g[s_g >= 0]
+    assert np.all(Last.valid[m] == 1) and np.all(Cur.occupied[np.nonzero(s_g >= 0)[0]] == 0)
