@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -60,6 +61,7 @@ void init_tables(borb_extractor* e) {
 
 // cv::resize INTER_LINEAR 8U coefficient tables (OpenCV imgproc/resize.cpp): {offset, c0, c1, 0} int16 quadruples.
 // `extra` > 0 appends entries for the reflect-101 padding columns dst .. dst+extra-1 (copies of the reflected column).
+// The entry count is padded to an even number so that every table starts 16-byte aligned.
 void resize_table(int src, int dst, bool clamp_edges, int extra, std::vector<int16_t>& out) {
     const double inv = (double)dst / src, scale = 1. / inv;
     const size_t first = out.size();
@@ -81,6 +83,38 @@ void resize_table(int src, int dst, bool clamp_edges, int extra, std::vector<int
         if (r < 0) r = 0;
         for (int j = 0; j < 4; j++) out.push_back(out[first + (size_t)r * 4 + j]);
     }
+    if (((out.size() - first) / 4) & 1) for (int j = 0; j < 4; j++) out.push_back(0);
+}
+
+// The x table again, per group of 4 destination columns (one thread of pyr_resize_kernel): {c0, c1, base, selectors}.
+// base = first byte of the aligned 12-byte source window the group reads (same in all 4 entries); the selectors
+// are the two PRMT controls that pull source bytes (ofs, ofs+1) out of the window words (w0,w1) and then w2:
+//   t = prmt(w0, w1, s1), pair = prmt(t, w2, s2), s1 = selectors & 0xFF, s2 = selectors >> 8.
+// Returns false if some group spans more than 12 bytes (scale factors above ~2): the caller then uses the generic kernel.
+bool resize_window_table(const std::vector<int16_t>& tabs, size_t xtab_first, int n_entries, std::vector<int16_t>& out) {
+    bool ok = true;
+    for (int gq = 0; gq < n_entries; gq += 4) {
+        int lo = 1 << 30, hi = 0;
+        for (int i = 0; i < 4; i++) {
+            const int ofs = tabs[xtab_first + (size_t)(gq + i) * 4];
+            lo = std::min(lo, ofs); hi = std::max(hi, ofs);
+        }
+        const int base = lo & ~3;
+        if (hi + 1 - base > 11) ok = false;
+        for (int i = 0; i < 4; i++) {
+            const int16_t* e = &tabs[xtab_first + (size_t)(gq + i) * 4];
+            const int pos = e[0] - base;
+            int s1 = 0, s2 = 0x10;
+            if (pos <= 6) s1 = pos | ((pos + 1) << 4);
+            else if (pos == 7) { s1 = 7; s2 = 0x40; }
+            else { const int q = (pos - 8) + 4; s2 = q | ((q + 1) << 4); }
+            out.push_back(e[1]);
+            out.push_back(e[2]);
+            out.push_back((int16_t)base);
+            out.push_back((int16_t)((s1 | (s2 << 8)) & 0x7FFF));
+        }
+    }
+    return ok;
 }
 
 borb_status build_geometry(borb_extractor* e, int w, int h, std::vector<int16_t>& tabs) {
@@ -129,12 +163,17 @@ borb_status build_geometry(borb_extractor* e, int w, int h, std::vector<int16_t>
         v.inv_scale = e->inv_scale[l];
         v.patch_size = (float)(int)(PATCH * e->scale[l]);
         g.blur_base[l] = btile;
-        btile += ((v.w + 127) / 128) * ((v.h + 63) / 64);   // blur_kernel: 128 x 64 strips
+        btile += ((v.w + BLUR_TILE_W - 1) / BLUR_TILE_W) * ((v.h + BLUR_TILE_H - 1) / BLUR_TILE_H);   // blur_kernel strips
         if (l > 0) {
+            const int wpad = (v.w + 8 + 3) & ~3;     // pixels + reflect padding, whole words
             v.xtab_off = (unsigned)(tabs.size() / 4);
-            resize_table(g.lv[l - 1].w, v.w, true, ((v.w + 8 + 3) & ~3) - v.w, tabs);
+            resize_table(g.lv[l - 1].w, v.w, true, wpad - v.w, tabs);
             v.ytab_off = (unsigned)(tabs.size() / 4);
             resize_table(g.lv[l - 1].h, v.h, false, 0, tabs);
+            v.xwin_off = (unsigned)(tabs.size() / 4);
+            std::vector<int16_t> win;
+            v.x_windowed = resize_window_table(tabs, (size_t)v.xtab_off * 4, wpad, win) ? 1 : 0;
+            tabs.insert(tabs.end(), win.begin(), win.end());
         }
         if (quadtree_smem_bytes(v.node_cap) > 200 * 1024) {
             set_error("per-level quota %d exceeds the quadtree kernel's shared-memory envelope", v.quota);

@@ -17,6 +17,8 @@ constexpr int HALF_PATCH = 15;    // HALF_PATCH_SIZE  (:73)
 constexpr int MIN_BORDER = 16;    // EDGE_THRESHOLD-3 (:773)
 constexpr int TH_HIGH = 100;      // ORBmatcher.cc:37
 constexpr int TH_LOW = 50;        // ORBmatcher.cc:38
+constexpr int BLUR_TILE_W = 120;  // blur strip: 30 output words per warp + one halo word each side
+constexpr int BLUR_TILE_H = 64;   // rows per blur CTA
 constexpr int FAST_TILE_W = 124;  // max detection-domain width of one FAST CTA (<= 32 aligned words incl. misalignment)
 
 // Candidate / selected-keypoint record: x | y<<12 | score<<24   (x,y <= 4095, score <= 255)
@@ -44,7 +46,9 @@ struct LevelGeom {
     float scale;            // mvScaleFactor[level]
     float inv_scale;        // mvInvScaleFactor[level]
     float patch_size;       // (float)(int)(PATCH_SIZE*scale)  (:837)
-    unsigned xtab_off, ytab_off;   // resize tables (int16 triplets: ofs, c0, c1), entries
+    unsigned xtab_off, ytab_off;   // resize tables ({ofs, c0, c1, 0} int16 quadruples), in entries
+    unsigned xwin_off;             // windowed x table ({c0, c1, group base, PRMT selectors}), in entries; see k_pyramid.cu
+    int x_windowed;                // 1: every group of 4 destination columns reads inside one aligned 12-byte source window
 };
 
 struct Geometry {

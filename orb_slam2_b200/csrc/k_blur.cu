@@ -6,20 +6,23 @@
 // column pass (sum + 2^15) >> 16; reflect-101 of the LEVEL itself at its borders.
 //
 // The right image edge needs no special case: every pyramid row ends in 8 bytes of reflect-101 padding.
-// v2: no shared memory.  A warp owns a 128-px wide strip (one aligned 32-bit word = 4 px per lane) and
-// slides down R rows: per input row one coalesced 128-byte load per warp, neighbour words by shuffle, the
-// row pass as two IDP.4A (dp4a) per pixel on PRMT-extracted byte windows, a 7-row register window for the
-// column pass, one aligned 32-bit store per 4 output pixels.  One launch covers all levels of all images.
+// v3: no shared memory.  A warp owns a 120-px wide strip: lane k holds the aligned 32-bit word (4 px) at
+// x = strip + 4(k-1), lanes 0 and 31 are halo only (their words feed the neighbours' windows by shuffle), and the
+// warp slides down BT_R rows.  Per input row: one coalesced 128-byte load per warp, the row pass as two IDP.4A
+// (dp4a) per pixel on PRMT-extracted byte windows (exact u16).  Row-pass results of consecutive rows are kept
+// PACKED as u16 pairs (r, r+1), so the column pass is three IDP.2A (dp2a) + one IMAD per pixel:
+//   s = 18 h[y-3] + 34 h[y-2] + 48 h[y-1] + 56 h[y] + 48 h[y+1] + 34 h[y+2] + 18 h[y+3] + 2^15,  out = s >> 16
+// (s < 2^24, so the result is byte 2 of s: packed with PRMT, no clamp).  One launch covers all levels of all images.
 //
-// Bound: HBM/L2 streaming (read + write of sum_l w_l*h_l bytes per image).
+// Bound: FMA/ALU issue (about 55 integer instructions per 4 output pixels); traffic = read + write of
+// sum_l w_l*h_l bytes per image.
 #include "borb_internal.h"
 
 namespace borb {
 
 namespace {
-constexpr int BT_W = 128;     // strip width (32 lanes x 4 px)
-constexpr int BT_R = 8;       // output rows per warp
-constexpr int BT_H = 64;      // rows per CTA (8 warps)
+constexpr int BT_R = 16;                   // output rows per warp
+constexpr int BT_WARPS = BLUR_TILE_H / BT_R;
 
 __device__ __forceinline__ int reflect101(int p, int len) {
     if (p < 0) p = -p;
@@ -28,73 +31,84 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ pyr,
-                                                   uint8_t* __restrict__ blur) {
+__global__ void __launch_bounds__(32 * BT_WARPS) blur_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ pyr,
+                                                             uint8_t* __restrict__ blur) {
     const int img = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && (int)blockIdx.x >= g.blur_base[l + 1]) l++;
     const LevelGeom& L = g.lv[l];
     const int local = blockIdx.x - g.blur_base[l];
-    const int tilesX = (L.w + BT_W - 1) / BT_W;
+    const int tilesX = (L.w + BLUR_TILE_W - 1) / BLUR_TILE_W;
     const int ty = local / tilesX, tx = local - ty * tilesX;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const int x = tx * BT_W + 4 * lane;            // first of this lane's 4 pixels
-    const int yb = ty * BT_H + wrp * BT_R;          // first output row of this warp
+    const int x = tx * BLUR_TILE_W + 4 * (lane - 1);     // first of this lane's 4 pixels (lane 0 / 31: halo words)
+    const int yb = ty * BLUR_TILE_H + wrp * BT_R;          // first output row of this warp
     if (yb >= L.h) return;
     const uint8_t* src = pyr + (size_t)img * g.pyr_image_stride + L.pyr_off;
     uint8_t* dst = blur + (size_t)img * g.pyr_image_stride + L.pyr_off;
     const int W = L.w, H = L.h, pitch = L.pitch;
     const bool left_edge = (x == 0);
+    const bool loads = x >= 0 && x < pitch;               // the word is inside the row buffer (pitch % 128 == 0, >= W + 8)
+    const bool stores = lane >= 1 && lane <= 30 && x < W;
     const unsigned WLO = 18u | (34u << 8) | (48u << 16) | (56u << 24);
     const unsigned WHI = 48u | (34u << 8) | (18u << 16);
 
     // issue every row's load up front (independent, coalesced 128 B per warp) so that their latencies overlap
     uint32_t own[BT_R + 6];
+    if (yb >= 3 && yb + BT_R + 2 < H) {                   // warp-uniform: no reflection, rows are consecutive
+        const uint8_t* p = src + (size_t)(yb - 3) * pitch + x;
 #pragma unroll
-    for (int step = 0; step < BT_R + 6; step++)
-        own[step] = *reinterpret_cast<const uint32_t*>(src + (size_t)reflect101(yb + step - 3, H) * pitch + x);
+        for (int step = 0; step < BT_R + 6; step++, p += pitch) own[step] = loads ? *reinterpret_cast<const uint32_t*>(p) : 0u;
+    } else {
+#pragma unroll
+        for (int step = 0; step < BT_R + 6; step++)
+            own[step] = loads ? *reinterpret_cast<const uint32_t*>(src + (unsigned)(reflect101(yb + step - 3, H) * pitch) + x) : 0u;
+    }
 
-    int win[7][4];    // row-pass results of the last 7 input rows (slot = input step % 7)
+    uint32_t pk[6][4];     // pk[s % 6][i] = h[s][i] | h[s+1][i] << 16 for the last six input steps
+    uint32_t hprev[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int step = 0; step < BT_R + 6; step++) {
-        const int yin = yb + step - 3;                    // input row feeding output rows yin-3 .. yin+3
-        const int sy = reflect101(yin, H);
-        const uint8_t* row = src + (size_t)sy * pitch;
-        // the pitch is a multiple of 128 and x < pitch: the lane's own word is always inside the row buffer
-        uint32_t W1 = own[step];
+        const uint32_t W1 = own[step];
         uint32_t W0 = __shfl_up_sync(0xFFFFFFFFu, W1, 1);
-        uint32_t W2 = __shfl_down_sync(0xFFFFFFFFu, W1, 1);
-        if (lane == 0 && !left_edge) W0 = *reinterpret_cast<const uint32_t*>(row + x - 4);
+        const uint32_t W2 = __shfl_down_sync(0xFFFFFFFFu, W1, 1);
         // rows carry >= 8 bytes of reflect-101 padding after the last pixel (k_pyramid.cu), so the word after the last
         // pixel word is valid data for the right image edge too
-        if (lane == 31 && x + 4 < pitch) W2 = *reinterpret_cast<const uint32_t*>(row + x + 4);
         if (left_edge) W0 = __byte_perm(W1, W2, 0x1234);  // bytes -4..-1 = pixels 4,3,2,1 (reflect-101)
-        int* r = win[step % 7];
-        r[0] = __dp4a(__byte_perm(W0, W1, 0x4321), WLO, __dp4a(__byte_perm(W1, W2, 0x4321), WHI, 0u));
-        r[1] = __dp4a(__byte_perm(W0, W1, 0x5432), WLO, __dp4a(__byte_perm(W1, W2, 0x5432), WHI, 0u));
-        r[2] = __dp4a(__byte_perm(W0, W1, 0x6543), WLO, __dp4a(__byte_perm(W1, W2, 0x6543), WHI, 0u));
-        r[3] = __dp4a(W1, WLO, __dp4a(W2, WHI, 0u));
+        uint32_t h[4];
+        h[0] = __dp4a(__byte_perm(W0, W1, 0x4321), WLO, __dp4a(__byte_perm(W1, W2, 0x4321), WHI, 0u));
+        h[1] = __dp4a(__byte_perm(W0, W1, 0x5432), WLO, __dp4a(__byte_perm(W1, W2, 0x5432), WHI, 0u));
+        h[2] = __dp4a(__byte_perm(W0, W1, 0x6543), WLO, __dp4a(__byte_perm(W1, W2, 0x6543), WHI, 0u));
+        h[3] = __dp4a(W1, WLO, __dp4a(W2, WHI, 0u));
+        if (step >= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) pk[(step - 1) % 6][i] = __byte_perm(hprev[i], h[i], 0x5410);
+        }
         if (step >= 6) {
             const int yout = yb + step - 6;
-            if (yout < H && x < W) {
-                uint32_t out = 0;
+            if (yout < H && stores) {
+                uint32_t s[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    // slots: output row yout uses input steps step-6 .. step
-                    const int s = 18 * (win[(step - 6) % 7][i] + win[step % 7][i]) + 34 * (win[(step - 5) % 7][i] + win[(step - 1) % 7][i]) +
-                                  48 * (win[(step - 4) % 7][i] + win[(step - 2) % 7][i]) + 56 * win[(step - 3) % 7][i];
-                    out |= (uint32_t)min((unsigned)(s + 32768) >> 16, 255u) << (8 * i);
+                    // output row yout = input steps step-6 .. step: pairs (s-6,s-5) (s-4,s-3) (s-2,s-1) and h[step]
+                    uint32_t acc = h[i] * 18u + 32768u;
+                    acc = __dp2a_lo(pk[(step - 2) % 6][i], 48u | (34u << 8), acc);
+                    acc = __dp2a_lo(pk[(step - 4) % 6][i], 48u | (56u << 8), acc);
+                    s[i] = __dp2a_lo(pk[(step - 6) % 6][i], 18u | (34u << 8), acc);
                 }
+                const uint32_t out = __byte_perm(__byte_perm(s[0], s[1], 0x0062), __byte_perm(s[2], s[3], 0x0062), 0x5410);
                 // rows are pitch-aligned and x % 4 == 0: one aligned store; bytes past W inside the pitch are scratch
                 *reinterpret_cast<uint32_t*>(dst + (size_t)yout * pitch + x) = out;
             }
         }
+#pragma unroll
+        for (int i = 0; i < 4; i++) hprev[i] = h[i];
     }
 }
 
 int launch_blur(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s) {
     dim3 grid(g.blur_tiles, n_images);
-    blur_kernel<<<grid, 256, 0, s>>>(g, ws.pyr, ws.blur);
+    blur_kernel<<<grid, 32 * BT_WARPS, 0, s>>>(g, ws.pyr, ws.blur);
     return 1;
 }
 

@@ -19,7 +19,7 @@ namespace borb {
 
 namespace {
 
-__device__ const int8_t d_pattern[1024] = {
+__device__ const float d_pattern[1024] = {      // bit_pattern_31_ as float: (x0, y0, x1, y1) per test, 4 KB, L1 resident
 #include "orb_pattern.inc"
 };
 
@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const int tI = j * 32 + lane;
-        const char4 pp = __ldg(reinterpret_cast<const char4*>(d_pattern) + tI);     // 1 KB table, L1 resident
-        const float x0 = (float)pp.x, y0 = (float)pp.y, x1 = (float)pp.z, y1 = (float)pp.w;
+        const float4 pp = __ldg(reinterpret_cast<const float4*>(d_pattern) + tI);
+        const float x0 = pp.x, y0 = pp.y, x1 = pp.z, y1 = pp.w;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));

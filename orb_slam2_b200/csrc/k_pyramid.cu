@@ -8,96 +8,87 @@
 // as aligned words).  The padding columns are produced here as ordinary pixels through table entries that point at
 // the reflected column.
 //
-// A thread makes 4 destination pixels: one packed table entry per pixel (source column + two 11-bit weights), the two
-// source rows as three aligned 32-bit words each, byte pairs picked with PRMT and the horizontal pass as one
-// IDP.2A (dp2a) per pixel and row.
+// A thread makes 4 destination pixels x ROWS rows.  Per pixel one 8-byte table entry {c0|c1<<16, base|selectors<<16}
+// built on the host (borb_host.cu resize_window_table): the two source rows come in as three aligned 32-bit words
+// each (the group's 12-byte window), the byte pair (ofs, ofs+1) is pulled out with two table-driven PRMTs and the
+// horizontal pass is one IDP.2A (dp2a) per pixel and row; no data-dependent selects or branches.
+// Levels whose groups do not fit a 12-byte window (scale factors above ~2) take pyr_resize_generic_kernel.
 //
-// Bound: ALU/LSU issue (integer work per pixel), traffic sum_{l>=1} w_l*h_l bytes written + read per image.
+// Bound: ALU/FMA issue (integer work per pixel); traffic sum_{l>=1} w_l*h_l bytes written + read per image.
 #include "borb_internal.h"
 
 namespace borb {
 
-namespace {
-__device__ __forceinline__ uint32_t pick2(uint32_t w0, uint32_t w1, uint32_t w2, int pos) {
-    // bytes pos, pos+1 (pos in 0..9) of the 12-byte window w0|w1|w2, in the low half of the result
-    const int k = pos >> 2, sh = pos & 3;
-    const uint32_t lo = k == 0 ? w0 : (k == 1 ? w1 : w2);
-    const uint32_t hi = k == 0 ? w1 : w2;
-    return __byte_perm(lo, hi, sh | ((sh + 1) << 4));
-}
-}  // namespace
-
-// xt/yt entries: {offset, c0, c1, 0} as 4 x int16.  A thread makes 4 px x PYR_ROWS rows (the x entries are reused).
-constexpr int PYR_ROWS = 1;    // (4 rows per thread measured no faster: the launches are CTA-latency bound)
+template <int ROWS>
 __global__ void __launch_bounds__(256) pyr_resize_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ pyr_out,
                                                          const int16_t* __restrict__ tabs, LevelGeom src, LevelGeom dst,
                                                          unsigned image_stride) {
     const int img = blockIdx.z;
-    const int dyb = (blockIdx.y * 8 + threadIdx.y) * PYR_ROWS;
+    const int dyb = (blockIdx.y * 8 + threadIdx.y) * ROWS;
     const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int wpad = (dst.w + 8 + 3) & ~3;                  // pixels + reflect padding, whole words
     if (dyb >= dst.h || dx0 >= wpad) return;
     const uint8_t* S = pyr + (size_t)img * image_stride + src.pyr_off;
     uint8_t* D = pyr_out + (size_t)img * image_stride + dst.pyr_off;
-    const uint2* xt = reinterpret_cast<const uint2*>(tabs + (size_t)dst.xtab_off * 4);
+    const uint4* xt = reinterpret_cast<const uint4*>(tabs + ((size_t)dst.xwin_off + dx0) * 4);   // 16-byte aligned
     const uint2* yt = reinterpret_cast<const uint2*>(tabs + (size_t)dst.ytab_off * 4);
-    uint2 e[4];
+    const uint4 e01 = xt[0], e23 = xt[1];
+    const uint32_t wts[4] = {e01.x, e01.z, e23.x, e23.z};
+    const uint32_t ctl[4] = {e01.y, e01.w, e23.y, e23.w};
+    const int base = (int)(ctl[0] & 0xFFFF);
+    uint32_t ra[ROWS][3], rc[ROWS][3];
+    uint32_t B0[ROWS], B1[ROWS];
 #pragma unroll
-    for (int i = 0; i < 4; i++) e[i] = xt[dx0 + i];
-    const int base = (int)(e[0].x & 0xFFFF) & ~3;
-    int lo = (int)(e[0].x & 0xFFFF), hi = lo;
-#pragma unroll
-    for (int i = 1; i < 4; i++) { const int s = (int)(e[i].x & 0xFFFF); lo = min(lo, s); hi = max(hi, s); }
-    const bool windowed = lo >= base && hi - base <= 9;     // the 4 pixels read source columns inside one 12-byte aligned window
-    // issue all row loads first (independent), then the arithmetic
-    uint32_t ra[PYR_ROWS][3], rc[PYR_ROWS][3];
-    int b0[PYR_ROWS], b1[PYR_ROWS], sy0[PYR_ROWS], sy1[PYR_ROWS];
-#pragma unroll
-    for (int r = 0; r < PYR_ROWS; r++) {
+    for (int r = 0; r < ROWS; r++) {
         const int dy = min(dyb + r, dst.h - 1);
         const uint2 ye = yt[dy];
         const int sy = (int)(short)(ye.x & 0xFFFF);
-        b0[r] = (int)(ye.x >> 16); b1[r] = (int)(ye.y & 0xFFFF);
-        sy0[r] = min(max(sy, 0), src.h - 1); sy1[r] = min(max(sy + 1, 0), src.h - 1);
-        if (windowed) {
-            const uint32_t* R0 = reinterpret_cast<const uint32_t*>(S + (size_t)sy0[r] * src.pitch + base);
-            const uint32_t* R1 = reinterpret_cast<const uint32_t*>(S + (size_t)sy1[r] * src.pitch + base);
-            ra[r][0] = R0[0]; ra[r][1] = R0[1]; ra[r][2] = R0[2];
-            rc[r][0] = R1[0]; rc[r][1] = R1[1]; rc[r][2] = R1[2];
-        }
+        B0[r] = ye.x & 0xFFFF0000u;                         // b0 << 16: (b0 * v) >> 16 == umulhi(b0 << 16, v)
+        B1[r] = ye.y << 16;
+        const int sy0 = min(max(sy, 0), src.h - 1), sy1 = min(max(sy + 1, 0), src.h - 1);
+        const uint32_t* R0 = reinterpret_cast<const uint32_t*>(S + (size_t)sy0 * src.pitch + base);
+        const uint32_t* R1 = reinterpret_cast<const uint32_t*>(S + (size_t)sy1 * src.pitch + base);
+        ra[r][0] = R0[0]; ra[r][1] = R0[1]; ra[r][2] = R0[2];
+        rc[r][0] = R1[0]; rc[r][1] = R1[1]; rc[r][2] = R1[2];
     }
 #pragma unroll
-    for (int r = 0; r < PYR_ROWS; r++) {
-        const int dy = dyb + r;
-        if (dy >= dst.h) break;
-        uint32_t out = 0;
-        if (windowed) {
+    for (int r = 0; r < ROWS; r++) {
+        if (dyb + r >= dst.h) break;
+        uint32_t v[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int pos = (int)(e[i].x & 0xFFFF) - base;
-                const uint32_t wts = (e[i].x >> 16) | (e[i].y << 16);           // c0 | c1 << 16
-                const int r0 = (int)__dp2a_lo(wts, pick2(ra[r][0], ra[r][1], ra[r][2], pos), 0u);
-                const int r1 = (int)__dp2a_lo(wts, pick2(rc[r][0], rc[r][1], rc[r][2], pos), 0u);
-                const int v = (((b0[r] * (r0 >> 4)) >> 16) + ((b1[r] * (r1 >> 4)) >> 16) + 2) >> 2;
-                out |= (uint32_t)(v & 0xFF) << (8 * i);
-            }
-        } else {
-            // padding words that straddle the reflection point: source columns are not monotone; plain byte loads
-            const uint8_t* R0 = S + (size_t)sy0[r] * src.pitch;
-            const uint8_t* R1 = S + (size_t)sy1[r] * src.pitch;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int sx = (int)(e[i].x & 0xFFFF), x1 = min(sx + 1, src.w - 1);
-                const int w0 = (int)(e[i].x >> 16), w1 = (int)(e[i].y & 0xFFFF);
-                const int r0 = R0[sx] * w0 + R0[x1] * w1;
-                const int r1 = R1[sx] * w0 + R1[x1] * w1;
-                const int v = (((b0[r] * (r0 >> 4)) >> 16) + ((b1[r] * (r1 >> 4)) >> 16) + 2) >> 2;
-                out |= (uint32_t)(v & 0xFF) << (8 * i);
-            }
+        for (int i = 0; i < 4; i++) {
+            const uint32_t s1 = ctl[i] >> 16, s2 = ctl[i] >> 24;        // PRMT reads the low 16 bits only
+            const uint32_t p0 = __byte_perm(__byte_perm(ra[r][0], ra[r][1], s1), ra[r][2], s2);
+            const uint32_t p1 = __byte_perm(__byte_perm(rc[r][0], rc[r][1], s1), rc[r][2], s2);
+            const uint32_t h0 = __dp2a_lo(wts[i], p0, 0u), h1 = __dp2a_lo(wts[i], p1, 0u);
+            v[i] = (__umulhi(B0[r], h0 >> 4) + __umulhi(B1[r], h1 >> 4) + 2) >> 2;
         }
+        const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
         // rows are pitch-aligned (pitch % 128 == 0, pitch >= w + 8) and dx0 % 4 == 0: one aligned 32-bit store
-        *reinterpret_cast<uint32_t*>(D + (size_t)dy * dst.pitch + dx0) = out;
+        *reinterpret_cast<uint32_t*>(D + (size_t)(dyb + r) * dst.pitch + dx0) = out;
     }
+}
+
+// Any scale factor: one destination pixel per thread, byte loads through the plain {ofs, c0, c1} table.
+__global__ void __launch_bounds__(256) pyr_resize_generic_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ pyr_out,
+                                                                 const int16_t* __restrict__ tabs, LevelGeom src, LevelGeom dst,
+                                                                 unsigned image_stride) {
+    const int img = blockIdx.z;
+    const int dy = blockIdx.y * 8 + threadIdx.y;
+    const int dx = blockIdx.x * 32 + threadIdx.x;
+    const int wpad = (dst.w + 8 + 3) & ~3;
+    if (dy >= dst.h || dx >= wpad) return;
+    const uint8_t* S = pyr + (size_t)img * image_stride + src.pyr_off;
+    uint8_t* D = pyr_out + (size_t)img * image_stride + dst.pyr_off;
+    const short4 xe = reinterpret_cast<const short4*>(tabs)[(size_t)dst.xtab_off + dx];
+    const short4 ye = reinterpret_cast<const short4*>(tabs)[(size_t)dst.ytab_off + dy];
+    const int sy0 = min(max((int)ye.x, 0), src.h - 1), sy1 = min(max((int)ye.x + 1, 0), src.h - 1);
+    const uint8_t* R0 = S + (size_t)sy0 * src.pitch;
+    const uint8_t* R1 = S + (size_t)sy1 * src.pitch;
+    const int sx = xe.x;                                     // sx + 1 <= src.w: inside the row's reflect padding
+    const int r0 = R0[sx] * xe.y + R0[sx + 1] * xe.z;
+    const int r1 = R1[sx] * xe.y + R1[sx + 1] * xe.z;
+    D[(size_t)dy * dst.pitch + dx] = (uint8_t)((((ye.y * (r0 >> 4)) >> 16) + ((ye.z * (r1 >> 4)) >> 16) + 2) >> 2);
 }
 
 // Level 0 from a tightly packed landing buffer (one big H2D copy) into the pitched pyramid layout.
@@ -130,14 +121,22 @@ int launch_repack(const Geometry& g, const Workspace& ws, const uint8_t* stage, 
     return 1;
 }
 
+constexpr int PYR_ROWS = 2;
+
 int launch_pyramid(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s) {
     int launches = 0;
     pad_level0_kernel<<<dim3((g.lv[0].h + 255) / 256, n_images), 256, 0, s>>>(ws.pyr, g.lv[0], g.pyr_image_stride);
     launches++;
     for (int l = 1; l < g.nlevels; l++) {
         const LevelGeom& d = g.lv[l];
-        dim3 block(32, 8), grid((d.w + 8 + 127) / 128, (d.h + 8 * PYR_ROWS - 1) / (8 * PYR_ROWS), n_images);
-        pyr_resize_kernel<<<grid, block, 0, s>>>(ws.pyr, ws.pyr, ws.tabs, g.lv[l - 1], d, g.pyr_image_stride);
+        dim3 block(32, 8);
+        if (d.x_windowed) {
+            dim3 grid((d.w + 8 + 127) / 128, (d.h + 8 * PYR_ROWS - 1) / (8 * PYR_ROWS), n_images);
+            pyr_resize_kernel<PYR_ROWS><<<grid, block, 0, s>>>(ws.pyr, ws.pyr, ws.tabs, g.lv[l - 1], d, g.pyr_image_stride);
+        } else {
+            dim3 grid((d.w + 8 + 3 + 31) / 32, (d.h + 7) / 8, n_images);
+            pyr_resize_generic_kernel<<<grid, block, 0, s>>>(ws.pyr, ws.pyr, ws.tabs, g.lv[l - 1], d, g.pyr_image_stride);
+        }
         launches++;
     }
     return launches;

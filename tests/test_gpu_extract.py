@@ -113,6 +113,21 @@ def test_thresholds_and_levels_variants(X, oracle):
         assert_kps_equal(kg, dg, kp, dp)
 
 
+@pytest.mark.parametrize("sf,nl", [(2.0, 3), (2.5, 3), (3.1, 2), (1.05, 6)])
+def test_pyramid_scale_factor_extremes(X, oracle, sf, nl):
+    """Scale factors above ~2 leave the 12-byte source window of the table-driven resize kernel and take the
+    generic one; 1.05 packs the window tightly.  Every level and the final keypoints must still match."""
+    img = synth.mono_frame(52, 0, 0, 1000, 700)
+    G, P = X(600, sf, nl, 20, 7), oracle.PortExtractor(600, sf, nl, 20, 7)
+    kg, dg = G(img)
+    kp, dp = P(img)
+    for l in range(nl):
+        assert np.array_equal(G.pyramid(l), P.level(l)), f"pyramid level {l}"
+        if P.blurred(l) is not None:
+            assert np.array_equal(G.debug_blurred(l), P.blurred(l)), f"blur level {l}"
+    assert_kps_equal(kg, dg, kp, dp)
+
+
 def test_batch_equals_single_and_handles_reshape(X, oracle):
     G = X(1000)
     imgs = [synth.mono_frame(60 + i, 0, 0, 640, 480) for i in range(5)]
