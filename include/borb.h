@@ -219,6 +219,40 @@ BORB_API borb_status borb_search_by_projection_last(borb_matcher* m, const borb_
                                                     int forward, int backward, int check_orientation, int32_t* state_cur,
                                                     int32_t* n_matches);
 
+/* A list of MapPoints with their world-frame data, for the two pose-projection searches below. */
+typedef struct borb_worldpoints_view {
+    int32_t n;
+    const float* world_pos;        /* n x 3, pMP->GetWorldPos() */
+    const uint8_t* desc;           /* n x 32, pMP->GetDescriptor() */
+    const float* max_distance;     /* n, MapPoint::mfMaxDistance (GetMaxDistanceInvariance() = 1.2f * this, src/MapPoint.cc:379-383) */
+    const float* min_distance;     /* n, MapPoint::mfMinDistance (GetMinDistanceInvariance() = 0.8f * this, :373-377) */
+    const float* normal;           /* n x 3, pMP->GetNormal(); only read by borb_search_by_projection_sim3 */
+    const float* angle;            /* n, pKF->mvKeysUn[i].angle of the keyframe feature that observes the point; only read
+                                      by borb_search_by_projection_kf with check_orientation */
+    const uint8_t* valid;          /* NULL: all valid */
+} borb_worldpoints_view;
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+ * — src/ORBmatcher.cc:1472-1599 (Tracking::Relocalization, src/Tracking.cc:1396,1410).
+ * pts[i] = pKF->GetMapPointMatches()[i] with valid[i] = pMP && !pMP->isBad() && !sAlreadyFound.count(pMP);
+ * cur->occupied[i2] = CurrentFrame.mvpMapPoints[i2] != NULL.  Tcw = CurrentFrame.mTcw rows 0..2, Ow = -Rcw.t()*tcw
+ * (:1476-1478, the caller's cv::Mat lines); log_scale_factor = CurrentFrame.mfLogScaleFactor (PredictScale,
+ * src/MapPoint.cc:402-417).  state_cur as in borb_search_by_projection_last (index into pts, -1, -2). */
+BORB_API borb_status borb_search_by_projection_kf(borb_matcher* m, const borb_frame_view* cur, const borb_worldpoints_view* pts,
+                                                  const float* Tcw, const float* Ow, float fx, float fy, float cx, float cy,
+                                                  float log_scale_factor, float th, int orb_dist, int check_orientation,
+                                                  int32_t* state_cur, int32_t* n_matches);
+
+/* ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)
+ * — src/ORBmatcher.cc:290-403 (LoopClosing::ComputeSim3, src/LoopClosing.cc:391).
+ * kf: the keyframe's features; kf->occupied[idx] = vpMatched[idx] != NULL on entry.  Tcw = [Rcw | tcw] after the
+ * Sim3 scale has been divided out and Ow = -Rcw.t()*tcw (:298-303, the caller's cv::Mat lines).
+ * pts->valid[i] = !vpPoints[i]->isBad() && !spAlreadyFound.count(vpPoints[i]).
+ * state_kf[idx] = index into pts of the point now in vpMatched[idx], -1 = vpMatched[idx] untouched. */
+BORB_API borb_status borb_search_by_projection_sim3(borb_matcher* m, const borb_frame_view* kf, const borb_worldpoints_view* pts,
+                                                    const float* Tcw, const float* Ow, float fx, float fy, float cx, float cy,
+                                                    float log_scale_factor, int th, int32_t* state_kf, int32_t* n_matches);
+
 /* DBoW2::FeatureVector (ordered map NodeId -> feature indices) as CSR; node_id ascending. */
 typedef struct borb_featvec_view {
     int32_t n_nodes;

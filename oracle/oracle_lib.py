@@ -257,6 +257,62 @@ def port_search_by_projection_last(Cur, Last, Tcw, K, bf, th, forward, backward,
     return n, state[:len(k)]
 
 
+def _log_scale(F):
+    """Frame::mfLogScaleFactor = log(mfScaleFactor) (Frame.cc:71): glibc logf of the float scale factor."""
+    v = getattr(F, "mfLogScaleFactor", None)
+    if v is not None:
+        return float(v)
+    libm = C.CDLL("libm.so.6")
+    libm.logf.restype = C.c_float
+    libm.logf.argtypes = [C.c_float]
+    return float(libm.logf(float(np.float32(F.mvScaleFactors[1]))))
+
+
+def _points_args(P):
+    wp = _a(P.world_pos, np.float32); md = _a(P.descriptors, np.uint8)
+    mx = _a(P.max_distance, np.float32); mn = _a(P.min_distance, np.float32)
+    va = _a(P.valid, np.uint8) if P.valid is not None else np.ones(len(wp), np.uint8)
+    return wp, md, mx, mn, va
+
+
+def port_search_by_projection_kf(Cur, P, Tcw, Ow, K, th, orb_dist, check_ori):
+    """SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1472-1599)."""
+    lib = _plib()
+    k = _a(Cur.mvKeysUn, KP_DTYPE); d = _a(Cur.mDescriptors, np.uint8); oc = _a(Cur.occupied, np.uint8)
+    sf = _a(Cur.mvScaleFactors, np.float32)
+    wp, md, mx, mn, va = _points_args(P)
+    ang = _a(P.angle, np.float32)
+    T = _a(np.asarray(Tcw, np.float32)[:3, :4].reshape(12), np.float32); ow = _a(np.asarray(Ow, np.float32).reshape(3), np.float32)
+    state = np.full(max(len(k), 1), -1, np.int32)
+    fn = lib.orbport_search_by_projection_kf
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 3 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 6 + [C.c_int]
+                   + [C.c_void_p] * 2 + [C.c_float] * 5 + [C.c_int, C.c_int, C.c_void_p])
+    n = fn(_ptr(k), _ptr(d), _ptr(oc), len(k), *[float(b) for b in Cur.bounds], _ptr(sf), len(sf), _log_scale(Cur),
+           _ptr(ang), _ptr(wp), _ptr(md), _ptr(mx), _ptr(mn), _ptr(va), len(wp), _ptr(T), _ptr(ow), float(K[0]), float(K[1]), float(K[2]),
+           float(K[3]), float(th), int(orb_dist), int(check_ori), _ptr(state))
+    return n, state[:len(k)]
+
+
+def port_search_by_projection_sim3(KF, P, Tcw, Ow, K, th):
+    """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:290-403); Tcw = [Rcw|tcw] with the scale divided out."""
+    lib = _plib()
+    k = _a(KF.mvKeysUn, KP_DTYPE); d = _a(KF.mDescriptors, np.uint8); oc = _a(KF.occupied, np.uint8)
+    sf = _a(KF.mvScaleFactors, np.float32)
+    wp, md, mx, mn, va = _points_args(P)
+    nr = _a(P.normal, np.float32)
+    T = _a(np.asarray(Tcw, np.float32)[:3, :4].reshape(12), np.float32); ow = _a(np.asarray(Ow, np.float32).reshape(3), np.float32)
+    state = np.full(max(len(k), 1), -1, np.int32)
+    fn = lib.orbport_search_by_projection_sim3
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 3 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 6 + [C.c_int]
+                   + [C.c_void_p] * 2 + [C.c_float] * 4 + [C.c_int, C.c_void_p])
+    n = fn(_ptr(k), _ptr(d), _ptr(oc), len(k), *[float(b) for b in KF.bounds], _ptr(sf), len(sf), _log_scale(KF),
+           _ptr(wp), _ptr(md), _ptr(mx), _ptr(mn), _ptr(nr), _ptr(va), len(wp), _ptr(T), _ptr(ow), float(K[0]), float(K[1]), float(K[2]),
+           float(K[3]), int(th), _ptr(state))
+    return n, state[:len(k)]
+
+
 def _kf_args(kf):
     k = _a(kf.mvKeysUn, KP_DTYPE); d = _a(kf.mDescriptors, np.uint8)
     hm = _a(kf.has_mp, np.uint8) if kf.has_mp is not None else np.zeros(len(k), np.uint8)

@@ -506,3 +506,142 @@ extern "C" int orbport_search_by_projection_last(const orbport_kp* cur_keys_un, 
     }
     return nmatches;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// MapPoint::PredictScale (reference src/MapPoint.cc:385-417): log/ceil resolve to the float overloads
+// (TemplatedVocabulary.h:36 puts `using namespace std` in scope), i.e. glibc logf.
+static int predict_scale(float mfMaxDistance, float currentDist, float logScaleFactor, int nScaleLevels) {
+    const float ratio = mfMaxDistance / currentDist;
+    int nScale = (int)std::ceil(std::log(ratio) / logScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= nScaleLevels) nScale = nScaleLevels - 1;
+    return nScale;
+}
+// cv::norm(3x1 CV_32F) (NORM_L2): squares accumulated in double in index order, sqrt in double, result narrowed by the caller
+static float norm3(const float* v) {
+    double s = 0;
+    for (int i = 0; i < 3; i++) { const double d = v[i]; s += d * d; }
+    return (float)std::sqrt(s);
+}
+// cv::Mat::dot of two 3x1 CV_32F: products and sum in double, index order
+static double dot3(const float* a, const float* b) {
+    double s = 0;
+    for (int i = 0; i < 3; i++) s += (double)a[i] * b[i];
+    return s;
+}
+
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, th, ORBdist)
+// reference src/ORBmatcher.cc:1472-1599 (Tracking::Relocalization, src/Tracking.cc:1396,1410).
+// Query i = pKF->GetMapPointMatches()[i]; valid[i] = pMP && !pMP->isBad() && !sAlreadyFound.count(pMP);
+// cur_occupied[i2] = CurrentFrame.mvpMapPoints[i2] != NULL; Ow = -Rcw.t()*tcw computed by the caller (:1478).
+extern "C" int orbport_search_by_projection_kf(const orbport_kp* cur_keys_un, const uint8_t* cur_desc, const uint8_t* cur_occupied, int n_cur,
+                                               float minX, float minY, float maxX, float maxY, const float* scale_factors, int n_levels,
+                                               float log_scale_factor, const float* kf_angle, const float* world_pos, const uint8_t* mp_desc,
+                                               const float* max_distance, const float* min_distance, const uint8_t* valid, int n_q,
+                                               const float* Tcw, const float* Ow, float fx, float fy, float cx, float cy, float th,
+                                               int ORBdist, int check_ori, int32_t* state_cur) {
+    Grid g = build_grid(cur_keys_un, n_cur, minX, minY, maxX, maxY);
+    std::vector<char> held(n_cur, 0);
+    for (int i = 0; i < n_cur; i++) { held[i] = cur_occupied ? (cur_occupied[i] != 0) : 0; state_cur[i] = -1; }
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    for (int i = 0; i < n_q; i++) {
+        if (valid && !valid[i]) continue;
+        const float* P = world_pos + 3 * (size_t)i;
+        const float xc = ((Tcw[0] * P[0] + Tcw[1] * P[1]) + Tcw[2] * P[2]) + Tcw[3];
+        const float yc = ((Tcw[4] * P[0] + Tcw[5] * P[1]) + Tcw[6] * P[2]) + Tcw[7];
+        const float zc = ((Tcw[8] * P[0] + Tcw[9] * P[1]) + Tcw[10] * P[2]) + Tcw[11];
+        const float invzc = 1.0 / zc;
+        const float u = fx * xc * invzc + cx;
+        const float v = fy * yc * invzc + cy;
+        if (u < minX || u > maxX) continue;
+        if (v < minY || v > maxY) continue;
+        if (!(u == u) || !(v == v)) continue;                 // NaN would index the grid with an undefined int in the reference
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist3D = norm3(PO);
+        const float maxDistance = 1.2f * max_distance[i];     // MapPoint::GetMaxDistanceInvariance (MapPoint.cc:379-383)
+        const float minDistance = 0.8f * min_distance[i];     // GetMinDistanceInvariance (:373-377)
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = predict_scale(max_distance[i], dist3D, log_scale_factor, n_levels);
+        const float radius = th * scale_factors[nPredictedLevel];
+        const std::vector<int> vIndices2 = features_in_area(g, cur_keys_un, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (held[i2]) continue;
+            const int dist = orbport_hamming(dMP, cur_desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= ORBdist) {
+            state_cur[bestIdx2] = i;
+            held[bestIdx2] = 1;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(kf_angle[i], cur_keys_un[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j : rotHist[i]) { state_cur[j] = -2; nmatches--; }
+    }
+    return nmatches;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)
+// reference src/ORBmatcher.cc:290-403 (LoopClosing::ComputeSim3, src/LoopClosing.cc:391).
+// Tcw = [Rcw | tcw] AFTER the scale has been divided out (:299-302), Ow = -Rcw.t()*tcw (:303): the caller's cv::Mat
+// lines. valid[i] = !vpPoints[i]->isBad() && !spAlreadyFound.count(vpPoints[i]); kf_matched[idx] = vpMatched[idx] != NULL.
+// state_kf[idx] = index into vpPoints of the point now in vpMatched[idx], -1 = untouched.
+extern "C" int orbport_search_by_projection_sim3(const orbport_kp* kf_keys_un, const uint8_t* kf_desc, const uint8_t* kf_matched, int n_kf,
+                                                 float minX, float minY, float maxX, float maxY, const float* scale_factors, int n_levels,
+                                                 float log_scale_factor, const float* world_pos, const uint8_t* mp_desc,
+                                                 const float* max_distance, const float* min_distance, const float* normal,
+                                                 const uint8_t* valid, int n_q, const float* Tcw, const float* Ow, float fx, float fy,
+                                                 float cx, float cy, int th, int32_t* state_kf) {
+    Grid g = build_grid(kf_keys_un, n_kf, minX, minY, maxX, maxY);
+    std::vector<char> held(n_kf, 0);
+    for (int i = 0; i < n_kf; i++) { held[i] = kf_matched ? (kf_matched[i] != 0) : 0; state_kf[i] = -1; }
+    int nmatches = 0;
+    for (int iMP = 0; iMP < n_q; iMP++) {
+        if (valid && !valid[iMP]) continue;
+        const float* P = world_pos + 3 * (size_t)iMP;
+        const float p3Dc[3] = {((Tcw[0] * P[0] + Tcw[1] * P[1]) + Tcw[2] * P[2]) + Tcw[3],
+                               ((Tcw[4] * P[0] + Tcw[5] * P[1]) + Tcw[6] * P[2]) + Tcw[7],
+                               ((Tcw[8] * P[0] + Tcw[9] * P[1]) + Tcw[10] * P[2]) + Tcw[11]};
+        if (p3Dc[2] < 0.0) continue;
+        const float invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz;
+        const float y = p3Dc[1] * invz;
+        const float u = fx * x + cx;
+        const float v = fy * y + cy;
+        if (!(u >= minX && u < maxX && v >= minY && v < maxY)) continue;       // KeyFrame::IsInImage (KeyFrame.cc:610-613)
+        const float maxDistance = 1.2f * max_distance[iMP];
+        const float minDistance = 0.8f * min_distance[iMP];
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist = norm3(PO);
+        if (dist < minDistance || dist > maxDistance) continue;
+        if (dot3(PO, normal + 3 * (size_t)iMP) < 0.5 * dist) continue;          // viewing angle < 60 deg (:354-357)
+        const int nPredictedLevel = predict_scale(max_distance[iMP], dist, log_scale_factor, n_levels);
+        const float radius = th * scale_factors[nPredictedLevel];
+        const std::vector<int> vIndices = features_in_area(g, kf_keys_un, u, v, radius, -1, -1);   // KeyFrame::GetFeaturesInArea: no levels
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)iMP * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (held[idx]) continue;
+            const int kpLevel = kf_keys_un[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int dist2 = orbport_hamming(dMP, kf_desc + (size_t)idx * 32);
+            if (dist2 < bestDist) { bestDist = dist2; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) {
+            state_kf[bestIdx] = iMP;
+            held[bestIdx] = 1;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}

@@ -34,12 +34,21 @@ struct ProjArgs {                 // device pointers
     int mode;                     // 0: local map points (ratio test), 1: last frame (best only, rotation histogram)
     int check_ori;
     const float* q_angle;         // mode 1: mvKeysUn[i].angle of the query
+    int th_dist;                  // mode 1: accept bestDist <= th_dist (TH_HIGH / ORBdist / TH_LOW)
     uint8_t* q_valid_out;         // mode 1: validity written by project_last_kernel (aliases mp_valid)
 };
 
-struct LastArgs {                 // inputs of project_last_kernel
+struct LastArgs {                 // inputs of project_points_kernel
+    int variant;                  // 0: (CurrentFrame, LastFrame) :1328   1: (CurrentFrame, KeyFrame) :1472   2: (KeyFrame, Scw) :290
     int n_last;
-    const borb_keypoint* last_keys;
+    const borb_keypoint* last_keys;   // variant 0 only (octave, angle of the last-frame feature)
+    const float* q_angle_in;      // variant 1: angle of the observing keyframe feature (may be null)
+    const float* max_distance;    // variants 1, 2
+    const float* min_distance;
+    const float* normal;          // variant 2, n x 3
+    float Ow[3];
+    float log_scale;
+    int n_levels;
     const float* world_pos;       // n_last x 3
     const uint8_t* valid_in;      // may be null
     float T[12];                  // Tcw rows 0..2

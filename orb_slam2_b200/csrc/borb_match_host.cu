@@ -229,32 +229,61 @@ borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F,
     return BORB_OK;
 }
 
-borb_status borb_search_by_projection_last(borb_matcher* m, const borb_frame_view* F, const borb_lastframe_view* Lf, const float* Tcw,
-                                           float fx, float fy, float cx, float cy, float bf, float th, int forward, int backward,
-                                           int check_orientation, int32_t* state_cur, int32_t* n_matches) {
-    if (!m || !F || !Lf || !Tcw || !state_cur || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+// Shared body of the three SearchByProjection overloads that project world points with a pose:
+// variant 0 (CurrentFrame, LastFrame) :1328, 1 (CurrentFrame, KeyFrame) :1472, 2 (KeyFrame, Scw) :290.
+struct PointQuery {
+    int variant, n;
+    const borb_keypoint* keys;      // variant 0
+    const float* world_pos;
+    const uint8_t* desc;
+    const uint8_t* valid;
+    const uint8_t* has_obs;         // variant 0
+    const float* max_distance;      // variants 1, 2
+    const float* min_distance;
+    const float* normal;            // variant 2
+    const float* angle;             // variant 1
+    const float* Tcw;
+    const float* Ow;
+    float fx, fy, cx, cy, bf, th, log_scale;
+    int forward, backward, check_ori, th_dist;
+};
+
+static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* F, const PointQuery& Q, int32_t* state, int32_t* n_matches) {
     *n_matches = 0;
-    if (F->n < 0 || F->n > MATCH_MAX_FEATURES || Lf->n < 0 || Lf->n > MATCH_MAX_FEATURES) { set_error("feature count outside [0,%d]", MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
-    for (int i = 0; i < F->n; i++) state_cur[i] = -1;
-    if (F->n == 0 || Lf->n == 0) return BORB_OK;
-    if (!F->keys_un || !F->desc || !F->scale_factors || !Lf->keys_un || !Lf->world_pos || !Lf->desc || !(F->max_x > F->min_x) || !(F->max_y > F->min_y)) {
+    if (F->n < 0 || F->n > MATCH_MAX_FEATURES || Q.n < 0 || Q.n > MATCH_MAX_FEATURES) { set_error("feature count outside [0,%d]", MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    for (int i = 0; i < F->n; i++) state[i] = -1;
+    if (F->n == 0 || Q.n == 0) return BORB_OK;
+    if (!F->keys_un || !F->desc || !F->scale_factors || F->n_levels < 1 || !Q.world_pos || !Q.desc || !(F->max_x > F->min_x) || !(F->max_y > F->min_y)) {
         set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG;
     }
-    for (int i = 0; i < Lf->n; i++)
-        if (Lf->keys_un[i].octave < 0 || Lf->keys_un[i].octave >= F->n_levels) { set_error("last-frame keypoint %d: octave out of range", i); return BORB_ERR_INVALID_ARG; }
+    if (Q.variant == 0) {
+        if (!Q.keys) { set_error("incomplete last-frame view"); return BORB_ERR_INVALID_ARG; }
+        for (int i = 0; i < Q.n; i++)
+            if (Q.keys[i].octave < 0 || Q.keys[i].octave >= F->n_levels) { set_error("last-frame keypoint %d: octave out of range", i); return BORB_ERR_INVALID_ARG; }
+    } else {
+        if (!Q.max_distance || !Q.min_distance || !Q.Ow || (Q.variant == 2 && !Q.normal) || (Q.variant == 1 && Q.check_ori && !Q.angle)) {
+            set_error("incomplete world-points view"); return BORB_ERR_INVALID_ARG;
+        }
+        if (!(Q.log_scale > 0.f)) { set_error("log_scale_factor must be positive (Frame::mfLogScaleFactor)"); return BORB_ERR_INVALID_ARG; }
+    }
     BORB_CUDA(cudaSetDevice(m->device));
     Stager st(m);
-    const int nq = Lf->n;
+    const int nq = Q.n;
+    const bool stereo = Q.variant == 0 && F->u_right != nullptr;
     const size_t o_keys = st.add(F->keys_un, (size_t)F->n * sizeof(borb_keypoint));
     const size_t o_desc = st.add(F->desc, (size_t)F->n * 32);
-    const size_t o_ur = F->u_right ? st.add(F->u_right, (size_t)F->n * 4) : 0;
+    const size_t o_ur = stereo ? st.add(F->u_right, (size_t)F->n * 4) : 0;
     const size_t o_occ = F->occupied ? st.add(F->occupied, (size_t)F->n) : 0;
     const size_t o_sf = st.add(F->scale_factors, (size_t)F->n_levels * 4);
-    const size_t o_lk = st.add(Lf->keys_un, (size_t)nq * sizeof(borb_keypoint));
-    const size_t o_wp = st.add(Lf->world_pos, (size_t)nq * 12);
-    const size_t o_md = st.add(Lf->desc, (size_t)nq * 32);
-    const size_t o_vin = Lf->valid ? st.add(Lf->valid, (size_t)nq) : 0;
-    const size_t o_obs = Lf->has_obs ? st.add(Lf->has_obs, (size_t)nq) : 0;
+    const size_t o_lk = Q.keys ? st.add(Q.keys, (size_t)nq * sizeof(borb_keypoint)) : 0;
+    const size_t o_wp = st.add(Q.world_pos, (size_t)nq * 12);
+    const size_t o_md = st.add(Q.desc, (size_t)nq * 32);
+    const size_t o_vin = Q.valid ? st.add(Q.valid, (size_t)nq) : 0;
+    const size_t o_obs = Q.has_obs ? st.add(Q.has_obs, (size_t)nq) : 0;
+    const size_t o_mx = Q.max_distance ? st.add(Q.max_distance, (size_t)nq * 4) : 0;
+    const size_t o_mn = Q.min_distance ? st.add(Q.min_distance, (size_t)nq * 4) : 0;
+    const size_t o_nr = Q.normal ? st.add(Q.normal, (size_t)nq * 12) : 0;
+    const size_t o_qa = Q.angle ? st.add(Q.angle, (size_t)nq * 4) : 0;
     const size_t input_end = st.off;
     const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
     const size_t o_px = st.reserve((size_t)nq * 4), o_py = st.reserve((size_t)nq * 4), o_pxr = st.reserve((size_t)nq * 4), o_rad = st.reserve((size_t)nq * 4);
@@ -267,18 +296,25 @@ borb_status borb_search_by_projection_last(borb_matcher* m, const borb_frame_vie
     if (s != BORB_OK) return s;
     uint8_t* b = m->arena;
     LastArgs L;
-    L.n_last = nq; L.last_keys = (const borb_keypoint*)(b + o_lk); L.world_pos = (const float*)(b + o_wp);
-    L.valid_in = Lf->valid ? b + o_vin : nullptr;
-    for (int i = 0; i < 12; i++) L.T[i] = Tcw[i];
-    L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.bf = bf; L.th = th;
+    L.variant = Q.variant;
+    L.n_last = nq; L.last_keys = Q.keys ? (const borb_keypoint*)(b + o_lk) : nullptr; L.world_pos = (const float*)(b + o_wp);
+    L.q_angle_in = Q.angle ? (const float*)(b + o_qa) : nullptr;
+    L.max_distance = Q.max_distance ? (const float*)(b + o_mx) : nullptr;
+    L.min_distance = Q.min_distance ? (const float*)(b + o_mn) : nullptr;
+    L.normal = Q.normal ? (const float*)(b + o_nr) : nullptr;
+    for (int i = 0; i < 3; i++) L.Ow[i] = Q.Ow ? Q.Ow[i] : 0.f;
+    L.log_scale = Q.log_scale; L.n_levels = F->n_levels;
+    L.valid_in = Q.valid ? b + o_vin : nullptr;
+    for (int i = 0; i < 12; i++) L.T[i] = Q.Tcw[i];
+    L.fx = Q.fx; L.fy = Q.fy; L.cx = Q.cx; L.cy = Q.cy; L.bf = Q.bf; L.th = Q.th;
     L.minX = F->min_x; L.minY = F->min_y; L.maxX = F->max_x; L.maxY = F->max_y;
     L.scale_factors = (const float*)(b + o_sf);
-    L.forward = forward; L.backward = backward;
+    L.forward = Q.forward; L.backward = Q.backward;
     L.proj_x = (float*)(b + o_px); L.proj_y = (float*)(b + o_py); L.proj_xr = (float*)(b + o_pxr); L.radius = (float*)(b + o_rad);
     L.angle = (float*)(b + o_ang); L.minl = (int32_t*)(b + o_minl); L.maxl = (int32_t*)(b + o_maxl); L.valid_out = b + o_val;
     ProjArgs A;
     A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
-    A.u_right = F->u_right ? (const float*)(b + o_ur) : nullptr;
+    A.u_right = stereo ? (const float*)(b + o_ur) : nullptr;
     A.occupied = F->occupied ? b + o_occ : nullptr;
     A.minX = F->min_x; A.minY = F->min_y;
     A.invW = (float)GRID_COLS / (float)(F->max_x - F->min_x);
@@ -286,18 +322,54 @@ borb_status borb_search_by_projection_last(borb_matcher* m, const borb_frame_vie
     A.scale_factors = (const float*)(b + o_sf);
     A.cell_start = (const int*)(b + o_cs); A.cell_idx = (const int*)(b + o_ci);
     A.n_mp = nq; A.proj_x = L.proj_x; A.proj_y = L.proj_y; A.proj_xr = L.proj_xr; A.view_cos = nullptr; A.level = nullptr;
-    A.mp_desc = b + o_md; A.mp_valid = b + o_val; A.mp_has_obs = Lf->has_obs ? b + o_obs : nullptr;
-    A.th = th; A.nnratio = 0.f;
+    A.mp_desc = b + o_md; A.mp_valid = b + o_val; A.mp_has_obs = Q.has_obs ? b + o_obs : nullptr;
+    A.th = Q.th; A.nnratio = 0.f;
     A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
-    A.q_radius = L.radius; A.q_minl = L.minl; A.q_maxl = L.maxl; A.mode = 1; A.check_ori = check_orientation; A.q_angle = L.angle;
+    A.q_radius = L.radius; A.q_minl = L.minl; A.q_maxl = L.maxl; A.mode = 1; A.check_ori = Q.check_ori; A.q_angle = L.angle;
+    A.th_dist = Q.th_dist;
     A.q_valid_out = b + o_val;
     m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
     m->launches += launch_projection_last(L, A, (int32_t*)(b + o_state), (int32_t*)(b + o_evi), b + o_evb, (int*)(b + o_nm), m->stream);
     BORB_CUDA(cudaGetLastError());
-    BORB_CUDA(cudaMemcpyAsync(state_cur, b + o_state, (size_t)F->n * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(state, b + o_state, (size_t)F->n * 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaStreamSynchronize(m->stream));
     return BORB_OK;
+}
+
+borb_status borb_search_by_projection_last(borb_matcher* m, const borb_frame_view* F, const borb_lastframe_view* Lf, const float* Tcw,
+                                           float fx, float fy, float cx, float cy, float bf, float th, int forward, int backward,
+                                           int check_orientation, int32_t* state_cur, int32_t* n_matches) {
+    if (!m || !F || !Lf || !Tcw || !state_cur || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    PointQuery Q{};
+    Q.variant = 0; Q.n = Lf->n; Q.keys = Lf->keys_un; Q.world_pos = Lf->world_pos; Q.desc = Lf->desc; Q.valid = Lf->valid; Q.has_obs = Lf->has_obs;
+    Q.Tcw = Tcw; Q.fx = fx; Q.fy = fy; Q.cx = cx; Q.cy = cy; Q.bf = bf; Q.th = th; Q.forward = forward; Q.backward = backward;
+    Q.check_ori = check_orientation; Q.th_dist = 100;                      // TH_HIGH (:1426)
+    return run_point_projection(m, F, Q, state_cur, n_matches);
+}
+
+borb_status borb_search_by_projection_kf(borb_matcher* m, const borb_frame_view* cur, const borb_worldpoints_view* pts, const float* Tcw,
+                                         const float* Ow, float fx, float fy, float cx, float cy, float log_scale_factor, float th,
+                                         int orb_dist, int check_orientation, int32_t* state_cur, int32_t* n_matches) {
+    if (!m || !cur || !pts || !Tcw || !Ow || !state_cur || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    PointQuery Q{};
+    Q.variant = 1; Q.n = pts->n; Q.world_pos = pts->world_pos; Q.desc = pts->desc; Q.valid = pts->valid;
+    Q.max_distance = pts->max_distance; Q.min_distance = pts->min_distance; Q.angle = pts->angle;
+    Q.Tcw = Tcw; Q.Ow = Ow; Q.fx = fx; Q.fy = fy; Q.cx = cx; Q.cy = cy; Q.th = th; Q.log_scale = log_scale_factor;
+    Q.check_ori = check_orientation; Q.th_dist = orb_dist;
+    return run_point_projection(m, cur, Q, state_cur, n_matches);
+}
+
+borb_status borb_search_by_projection_sim3(borb_matcher* m, const borb_frame_view* kf, const borb_worldpoints_view* pts, const float* Tcw,
+                                           const float* Ow, float fx, float fy, float cx, float cy, float log_scale_factor, int th,
+                                           int32_t* state_kf, int32_t* n_matches) {
+    if (!m || !kf || !pts || !Tcw || !Ow || !state_kf || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    PointQuery Q{};
+    Q.variant = 2; Q.n = pts->n; Q.world_pos = pts->world_pos; Q.desc = pts->desc; Q.valid = pts->valid;
+    Q.max_distance = pts->max_distance; Q.min_distance = pts->min_distance; Q.normal = pts->normal;
+    Q.Tcw = Tcw; Q.Ow = Ow; Q.fx = fx; Q.fy = fy; Q.cx = cx; Q.cy = cy; Q.th = (float)th; Q.log_scale = log_scale_factor;
+    Q.check_ori = 0; Q.th_dist = 50;                                       // TH_LOW (:394)
+    return run_point_projection(m, kf, Q, state_kf, n_matches);
 }
 
 static borb_status bow_common(borb_matcher* m, const borb_keyframe_view* qs, int n_q, const borb_keyframe_view* t, int mode, float nnratio,

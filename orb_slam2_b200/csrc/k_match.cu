@@ -230,33 +230,111 @@ __global__ void __launch_bounds__(32) proj_resolve_kernel(ProjArgs A, int32_t* _
 
 // SearchByProjection(CurrentFrame, LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470.  Projection of the last frame's
 // map points with the current pose (float32 (r0*p0 + r1*p1) + r2*p2, then + t: cv::Mat product order) and the search window.
-__global__ void __launch_bounds__(256) project_last_kernel(LastArgs L) {
+// glibc (>= 2.28) logf for positive normal finite x — the function MapPoint::PredictScale calls (src/MapPoint.cc:393,410;
+// `log` resolves to the float overload).  ARM optimized-routines algorithm in double; checked on the CPU against glibc for
+// every positive normal float, with and without FMA contraction: 0 mismatches.
+struct LogfTab { double invc[16], logc[16]; double ln2, a0, a1, a2; };
+__device__ const LogfTab d_logf = {
+    {0x1.661ec79f8f3bep+0, 0x1.571ed4aaf883dp+0, 0x1.49539f0f010bp+0, 0x1.3c995b0b80385p+0, 0x1.30d190c8864a5p+0, 0x1.25e227b0b8eap+0,
+     0x1.1bb4a4a1a343fp+0, 0x1.12358f08ae5bap+0, 0x1.0953f419900a7p+0, 0x1p+0, 0x1.e608cfd9a47acp-1, 0x1.ca4b31f026aap-1,
+     0x1.b2036576afce6p-1, 0x1.9c2d163a1aa2dp-1, 0x1.886e6037841edp-1, 0x1.767dcf5534862p-1},
+    {-0x1.57bf7808caadep-2, -0x1.2bef0a7c06ddbp-2, -0x1.01eae7f513a67p-2, -0x1.b31d8a68224e9p-3, -0x1.6574f0ac07758p-3,
+     -0x1.1aa2bc79c81p-3, -0x1.a4e76ce8c0e5ep-4, -0x1.1973c5a611cccp-4, -0x1.252f438e10c1ep-5, 0x0p+0, 0x1.aa5aa5df25984p-5,
+     0x1.c5e53aa362eb4p-4, 0x1.526e57720db08p-3, 0x1.bc2860d22477p-3, 0x1.1058bc8a07ee1p-2, 0x1.4043057b6ee09p-2},
+    0x1.62e42fefa39efp-1, -0x1.00ea348b88334p-2, 0x1.5575b0be00b6ap-2, -0x1.ffffef20a4123p-2};
+
+__device__ __forceinline__ float glibc_logf(float x) {
+    const uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.f;
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const int k = (int)tmp >> 23;
+    const uint32_t iz = ix - (tmp & (0x1ffu << 23));
+    const double z = (double)__uint_as_float(iz);
+    const double r = __dsub_rn(__dmul_rn(z, d_logf.invc[i]), 1.0);
+    const double y0 = __dadd_rn(d_logf.logc[i], __dmul_rn((double)k, d_logf.ln2));
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(d_logf.a1, r), d_logf.a2);
+    y = __dadd_rn(__dmul_rn(d_logf.a0, r2), y);
+    y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+    return (float)y;
+}
+
+// MapPoint::PredictScale (src/MapPoint.cc:385-417)
+__device__ __forceinline__ int predict_scale(float max_distance, float dist, float log_scale, int n_levels) {
+    const float ratio = __fdiv_rn(max_distance, dist);
+    const uint32_t ir = __float_as_uint(ratio);
+    int nScale = 0;             // ratio <= 0, subnormal, inf or NaN: the reference's (int) conversion lands below 0 -> clamped to 0
+    if (ir >= 0x00800000u && ir < 0x7f800000u) {
+        const float q = ceilf(__fdiv_rn(glibc_logf(ratio), log_scale));
+        nScale = q >= 2147483648.f || !(q == q) ? 0 : (q <= -2147483648.f ? 0 : (int)q);
+    }
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= n_levels) nScale = n_levels - 1;
+    return nScale;
+}
+
+// Projection of the query points with the 3x4 pose, for the three SearchByProjection overloads that take world points.
+__global__ void __launch_bounds__(256) project_points_kernel(LastArgs L) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L.n_last) return;
     bool ok = L.valid_in == nullptr || L.valid_in[i] != 0;
-    float u = 0.f, v = 0.f, ur = 0.f, radius = 0.f;
+    float u = 0.f, v = 0.f, ur = 0.f, radius = 0.f, ang = 0.f;
     int minl = 0, maxl = -1;
     if (ok) {
         const float* P = L.world_pos + 3 * (size_t)i;
         const float p0 = P[0], p1 = P[1], p2 = P[2];
+        // cv::Mat 3x3 * 3x1 + 3x1 in float32: (r0*p0 + r1*p1) + r2*p2, then + t  
         const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[0], p0), __fmul_rn(L.T[1], p1)), __fmul_rn(L.T[2], p2)), L.T[3]);
         const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[4], p0), __fmul_rn(L.T[5], p1)), __fmul_rn(L.T[6], p2)), L.T[7]);
         const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[8], p0), __fmul_rn(L.T[9], p1)), __fmul_rn(L.T[10], p2)), L.T[11]);
-        const float invzc = (float)(1.0 / (double)zc);                       // 1.0/x3Dc.at<float>(2) (:1365)
-        if (invzc < 0) ok = false;
-        u = __fadd_rn(__fmul_rn(__fmul_rn(L.fx, xc), invzc), L.cx);
-        v = __fadd_rn(__fmul_rn(__fmul_rn(L.fy, yc), invzc), L.cy);
-        if (u < L.minX || u > L.maxX || v < L.minY || v > L.maxY) ok = false;
-        if (!(u == u) || !(v == v)) ok = false;                               // NaN never passes the reference's range tests either
-        const int oct = L.last_keys[i].octave;
-        radius = __fmul_rn(L.th, L.scale_factors[oct]);
-        if (L.forward) { minl = oct; maxl = -1; }
-        else if (L.backward) { minl = 0; maxl = oct; }
-        else { minl = oct - 1; maxl = oct + 1; }
-        ur = __fsub_rn(u, __fmul_rn(L.bf, invzc));
+        if (L.variant == 2) {
+            if (zc < 0.0f) ok = false;                                        // depth must be positive (:329-330)
+            const float invz = __fdiv_rn(1.0f, zc);                           // 1/p3Dc.at<float>(2) (:333)
+            const float x = __fmul_rn(xc, invz), y = __fmul_rn(yc, invz);
+            u = __fadd_rn(__fmul_rn(L.fx, x), L.cx);
+            v = __fadd_rn(__fmul_rn(L.fy, y), L.cy);
+            if (!(u >= L.minX && u < L.maxX && v >= L.minY && v < L.maxY)) ok = false;     // KeyFrame::IsInImage
+        } else {
+            const float invzc = (float)(1.0 / (double)zc);                   // 1.0/x3Dc.at<float>(2) (:1365, :1503)
+            if (L.variant == 0 && invzc < 0) ok = false;                      // (:1367-1368); the keyframe overload has no such test
+            u = __fadd_rn(__fmul_rn(__fmul_rn(L.fx, xc), invzc), L.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(L.fy, yc), invzc), L.cy);
+            if (u < L.minX || u > L.maxX || v < L.minY || v > L.maxY) ok = false;
+            if (!(u == u) || !(v == v)) ok = false;                           // NaN never reaches a defined grid cell in the reference either
+            ur = __fsub_rn(u, __fmul_rn(L.bf, invzc));
+        }
+        if (L.variant == 0) {
+            const int oct = L.last_keys[i].octave;
+            radius = __fmul_rn(L.th, L.scale_factors[oct]);
+            if (L.forward) { minl = oct; maxl = -1; }
+            else if (L.backward) { minl = 0; maxl = oct; }
+            else { minl = oct - 1; maxl = oct + 1; }
+            ang = L.last_keys[i].angle;
+        } else if (ok) {
+            // PO = p3Dw - Ow (float); cv::norm accumulates the squares in double, in index order
+            const float o0 = __fsub_rn(p0, L.Ow[0]), o1 = __fsub_rn(p1, L.Ow[1]), o2 = __fsub_rn(p2, L.Ow[2]);
+            const double d0 = o0, d1 = o1, d2 = o2;
+            const float dist = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
+            const float mx = L.max_distance[i];
+            const float maxD = __fmul_rn(1.2f, mx), minD = __fmul_rn(0.8f, L.min_distance[i]);
+            if (dist < minD || dist > maxD) ok = false;
+            if (ok && L.variant == 2) {                                       // viewing angle below 60 degrees (:354-357)
+                const float* N = L.normal + 3 * (size_t)i;
+                const double dot = __dadd_rn(__dadd_rn(__dmul_rn(d0, (double)N[0]), __dmul_rn(d1, (double)N[1])), __dmul_rn(d2, (double)N[2]));
+                if (dot < __dmul_rn(0.5, (double)dist)) ok = false;
+            }
+            if (ok) {
+                const int lvl = predict_scale(mx, dist, L.log_scale, L.n_levels);
+                radius = __fmul_rn(L.th, L.scale_factors[lvl]);
+                minl = lvl - 1;
+                maxl = L.variant == 1 ? lvl + 1 : lvl;
+            }
+            ang = L.q_angle_in != nullptr ? L.q_angle_in[i] : 0.f;
+        }
     }
     L.proj_x[i] = u; L.proj_y[i] = v; L.proj_xr[i] = ur; L.radius[i] = radius; L.minl[i] = minl; L.maxl[i] = maxl;
-    L.angle[i] = L.last_keys[i].angle;
+    L.angle[i] = ang;
     L.valid_out[i] = ok ? 1 : 0;
 }
 
@@ -293,7 +371,7 @@ __global__ void __launch_bounds__(32) proj_resolve_last_kernel(ProjArgs A, const
             k1 = min(k1, (((e >> 16) & 0x1FFu) << 16) | (unsigned)p);
         }
         const unsigned best = warp_min(k1);
-        if (best != 0xFFFFFFFFu && (int)(best >> 16) <= TH_HIGH) {
+        if (best != 0xFFFFFFFFu && (int)(best >> 16) <= A.th_dist) {
             const int m = (int)(c[best & 0xFFFFu] & 0xFFFF);
             if (lane == 0) {
                 state_cur[m] = iq;
@@ -549,7 +627,7 @@ int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cu
 int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_cur, int32_t* ev_idx, uint8_t* ev_bin, int* n_matches,
                            cudaStream_t s) {
     if (L.n_last > 0) {
-        project_last_kernel<<<(L.n_last + 255) / 256, 256, 0, s>>>(L);
+        project_points_kernel<<<(L.n_last + 255) / 256, 256, 0, s>>>(L);
         proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
     }
     const int words = (A.n + 31) / 32;

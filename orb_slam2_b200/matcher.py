@@ -35,6 +35,11 @@ class _LastFrameViewC(C.Structure):
                 ("has_obs", C.c_void_p)]
 
 
+class _WorldPointsViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("world_pos", C.c_void_p), ("desc", C.c_void_p), ("max_distance", C.c_void_p),
+                ("min_distance", C.c_void_p), ("normal", C.c_void_p), ("angle", C.c_void_p), ("valid", C.c_void_p)]
+
+
 class _FeatVecC(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("start", C.c_void_p), ("feat_idx", C.c_void_p)]
 
@@ -80,7 +85,8 @@ class FrameView:
     mvScaleFactors: np.ndarray
     bounds: Tuple[float, float, float, float]            # mnMinX, mnMinY, mnMaxX, mnMaxY
     mvuRight: Optional[np.ndarray] = None
-    occupied: Optional[np.ndarray] = None                 # mvpMapPoints[i] && Observations()>0
+    occupied: Optional[np.ndarray] = None                 # mvpMapPoints[i] && Observations()>0 (or != NULL, per overload)
+    mfLogScaleFactor: Optional[float] = None              # Frame::mfLogScaleFactor; default logf(mvScaleFactors[1])
 
 
 @dataclass
@@ -94,6 +100,26 @@ class MapPointsView:
     descriptors: np.ndarray
     valid: Optional[np.ndarray] = None                    # mbTrackInView && !isBad()
     has_obs: Optional[np.ndarray] = None                  # Observations()>0
+
+
+@dataclass
+class WorldPointsView:
+    """MapPoints with world-frame data for SearchByProjection(CurrentFrame, KeyFrame, ...) and (KeyFrame, Scw, ...)."""
+    world_pos: np.ndarray                                  # (n,3) float32, GetWorldPos()
+    descriptors: np.ndarray                                # (n,32), GetDescriptor()
+    max_distance: np.ndarray                               # mfMaxDistance
+    min_distance: np.ndarray                               # mfMinDistance
+    normal: Optional[np.ndarray] = None                    # (n,3) GetNormal() — Sim3 overload
+    angle: Optional[np.ndarray] = None                     # pKF->mvKeysUn[i].angle — keyframe overload, orientation check
+    valid: Optional[np.ndarray] = None
+
+
+def _libm_logf(x: float) -> float:
+    """glibc logf — what Frame::mfLogScaleFactor = log(mfScaleFactor) evaluates to (src/Frame.cc:71)."""
+    libm = C.CDLL("libm.so.6")
+    libm.logf.restype = C.c_float
+    libm.logf.argtypes = [C.c_float]
+    return float(libm.logf(float(np.float32(x))))
 
 
 @dataclass
@@ -202,6 +228,48 @@ class ORBmatcher:
                                                        float(bf), float(th), int(bForward), int(bBackward), int(self.mbCheckOrientation),
                                                        _p(state), C.byref(n)), "borb_search_by_projection_last")
         return n.value, state[:len(k)]
+
+    def _points_call(self, F: FrameView, P: WorldPointsView):
+        k = np.ascontiguousarray(F.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(F.mDescriptors, np.uint8)
+        oc = np.ascontiguousarray(F.occupied, np.uint8) if F.occupied is not None else None
+        sf = np.ascontiguousarray(F.mvScaleFactors, np.float32)
+        fv = _FrameViewC(len(k), _p(k), _p(d), None, _p(oc), *[float(x) for x in F.bounds], len(sf), _p(sf))
+        keep = [k, d, oc, sf]
+        arrs = []
+        for a, dt in ((P.world_pos, np.float32), (P.descriptors, np.uint8), (P.max_distance, np.float32), (P.min_distance, np.float32),
+                      (P.normal, np.float32), (P.angle, np.float32), (P.valid, np.uint8)):
+            arrs.append(np.ascontiguousarray(a, dt) if a is not None else None)
+        pv = _WorldPointsViewC(len(arrs[0]), *[_p(a) for a in arrs])
+        logs = F.mfLogScaleFactor if F.mfLogScaleFactor is not None else _libm_logf(sf[1] if len(sf) > 1 else 1.2)
+        return fv, pv, float(logs), len(k), keep + arrs
+
+    def SearchByProjectionKF(self, Cur: FrameView, P: WorldPointsView, Tcw: np.ndarray, Ow: np.ndarray, K: Tuple[float, float, float, float],
+                             th: float, ORBdist: int) -> Tuple[int, np.ndarray]:
+        """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) — src/ORBmatcher.cc:1472-1599 (relocalisation).
+        P = the keyframe's MapPoints (valid = present, not bad, not already found); Cur.occupied = mvpMapPoints[i] != NULL;
+        Ow = -Rcw.t()*tcw.  Returns (nmatches, state[cur.N]): >=0 index into P, -1 untouched, -2 culled by orientation."""
+        fv, pv, logs, n, keep = self._points_call(Cur, P)
+        T = np.ascontiguousarray(np.asarray(Tcw, np.float32)[:3, :4]).reshape(12)
+        ow = np.ascontiguousarray(np.asarray(Ow, np.float32).reshape(3))
+        state = np.full(max(n, 1), -1, np.int32)
+        nm = C.c_int32(0)
+        check(self._lib.borb_search_by_projection_kf(self._h, C.byref(fv), C.byref(pv), _p(T), _p(ow), float(K[0]), float(K[1]), float(K[2]),
+                                                     float(K[3]), logs, float(th), int(ORBdist), int(self.mbCheckOrientation), _p(state),
+                                                     C.byref(nm)), "borb_search_by_projection_kf")
+        return nm.value, state[:n]
+
+    def SearchByProjectionSim3(self, pKF: FrameView, P: WorldPointsView, Tcw: np.ndarray, Ow: np.ndarray,
+                               K: Tuple[float, float, float, float], th: int) -> Tuple[int, np.ndarray]:
+        """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) — src/ORBmatcher.cc:290-403 (loop closing).  Tcw = [Rcw|tcw] with
+        the Sim3 scale divided out, Ow = -Rcw.t()*tcw; pKF.occupied = vpMatched[idx] != NULL.  Returns (nmatches, state[kf.N])."""
+        fv, pv, logs, n, keep = self._points_call(pKF, P)
+        T = np.ascontiguousarray(np.asarray(Tcw, np.float32)[:3, :4]).reshape(12)
+        ow = np.ascontiguousarray(np.asarray(Ow, np.float32).reshape(3))
+        state = np.full(max(n, 1), -1, np.int32)
+        nm = C.c_int32(0)
+        check(self._lib.borb_search_by_projection_sim3(self._h, C.byref(fv), C.byref(pv), _p(T), _p(ow), float(K[0]), float(K[1]), float(K[2]),
+                                                       float(K[3]), logs, int(th), _p(state), C.byref(nm)), "borb_search_by_projection_sim3")
+        return nm.value, state[:n]
 
     def SearchByBoW(self, pKF, F: KeyFrameView):
         """SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) — src/ORBmatcher.cc:159-288.  pKF may be one KeyFrameView or a

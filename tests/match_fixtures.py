@@ -82,3 +82,46 @@ def last_frame_case(v, seed, K=(525.0, 525.0, 319.5, 239.5), jitter=2.0):
     Last = LastFrameView(mvKeysUn=kr, world_pos=Pw.astype(np.float32), descriptors=v["dr"],
                          valid=(rng.random(len(kr)) < 0.9).astype(np.uint8), has_obs=(rng.random(len(kr)) < 0.9).astype(np.uint8))
     return Cur, Last, Tcw, K
+
+
+def world_points_case(v, seed, K=(525.0, 525.0, 319.5, 239.5), jitter=2.0):
+    """Frame (or keyframe) = left view; query MapPoints = the right view's features placed in the world so that, through a
+    non-trivial pose, they project near their true correspondences in the left view.  Distances, normals and validity
+    are spread so that every rejection branch of the two pose-projection overloads is exercised."""
+    from orb_slam2_b200.matcher import WorldPointsView
+    rng = np.random.default_rng(seed)
+    w, h = v["w"], v["h"]
+    fx, fy, cx, cy = K
+    F = FrameView(mvKeysUn=v["kl"], mDescriptors=v["dl"], mvScaleFactors=v["scale"], bounds=(0.0, 0.0, float(w), float(h)),
+                  occupied=(rng.random(len(v["kl"])) < 0.05).astype(np.uint8))
+    kr = v["kr"]
+    n = len(kr)
+    d = v["disp"][np.clip(kr["y"].astype(int), 0, h - 1), np.clip(kr["x"].astype(int), 0, w - 1)]
+    uA = kr["x"] + d + rng.normal(0, jitter, n)
+    vA = kr["y"] + rng.normal(0, jitter, n)
+    z = rng.uniform(2.0, 40.0, n)
+    Pc = np.stack([(uA - cx) * z / fx, (vA - cy) * z / fy, z], 1)
+    flip = rng.random(n) < 0.03
+    Pc[flip] *= -1.0                                              # behind the camera: projects to the same pixel with z < 0
+    ang = 0.05
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]]) @ \
+        np.array([[1, 0, 0], [0, np.cos(0.02), -np.sin(0.02)], [0, np.sin(0.02), np.cos(0.02)]])
+    t = np.array([0.3, -0.1, 0.5])
+    Pw = ((Pc - t) @ R).astype(np.float32)
+    Tcw = np.zeros((3, 4), np.float32); Tcw[:, :3] = R; Tcw[:, 3] = t
+    R32, t32 = Tcw[:, :3], Tcw[:, 3]
+    Ow = (-(R32.T @ t32)).astype(np.float32)                      # -Rcw.t()*tcw
+    dist = np.linalg.norm(Pw.astype(np.float64) - Ow, axis=1)
+    scale = np.asarray(v["scale"], np.float64)
+    maxd = dist * scale[np.clip(kr["octave"], 0, len(scale) - 1)] * rng.uniform(0.9, 1.1, n)
+    maxd[rng.random(n) < 0.05] *= 0.3                            # too far for the point's scale-invariance range
+    mind = maxd / scale[-1]
+    mind[rng.random(n) < 0.05] *= 30.0                           # too close
+    view = (Pw.astype(np.float64) - Ow) / np.maximum(dist, 1e-9)[:, None]
+    tilt = rng.uniform(0.0, np.deg2rad(80.0), n)                 # > 60 deg fails the viewing-angle test
+    axis = np.cross(view, rng.normal(size=(n, 3))); axis /= np.linalg.norm(axis, axis=1)[:, None]
+    normal = view * np.cos(tilt)[:, None] + np.cross(axis, view) * np.sin(tilt)[:, None]
+    P = WorldPointsView(world_pos=Pw, descriptors=v["dr"], max_distance=maxd.astype(np.float32), min_distance=mind.astype(np.float32),
+                        normal=normal.astype(np.float32), angle=kr["angle"].astype(np.float32),
+                        valid=(rng.random(n) < 0.9).astype(np.uint8))
+    return F, P, Tcw, Ow, K

@@ -132,3 +132,55 @@ def test_search_by_projection_from_last_frame(M, oracle, views, seed, mode, th, 
     assert n_g == n_o and np.array_equal(s_g, s_o), int((s_g != s_o).sum())
     m = s_g[s_g >= 0]
     assert np.all(Last.valid[m] == 1) and np.all(Cur.occupied[np.nonzero(s_g >= 0)[0]] == 0)
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("th,orb_dist,ori", [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False), (25.0, 50, True)])
+def test_search_by_projection_from_keyframe(M, oracle, views, seed, th, orb_dist, ori):
+    """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1472-1599 (Relocalization)."""
+    Cur, P, Tcw, Ow, K = mf.world_points_case(views[seed], seed + 30)
+    n_o, s_o = oracle.port_search_by_projection_kf(Cur, P, Tcw, Ow, K, th, orb_dist, ori)
+    n_g, s_g = M.ORBmatcher(0.9, ori).SearchByProjectionKF(Cur, P, Tcw, Ow, K, th, orb_dist)
+    assert n_o > 20
+    assert n_g == n_o and np.array_equal(s_g, s_o), int((s_g != s_o).sum())
+    hit = np.nonzero(s_g >= 0)[0]
+    assert np.all(P.valid[s_g[hit]] == 1) and np.all(Cur.occupied[hit] == 0)
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("th", [3, 10, 25])
+def test_search_by_projection_sim3(M, oracle, views, seed, th):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:290-403 (LoopClosing::ComputeSim3)."""
+    KF, P, Tcw, Ow, K = mf.world_points_case(views[seed], seed + 40)
+    n_o, s_o = oracle.port_search_by_projection_sim3(KF, P, Tcw, Ow, K, th)
+    n_g, s_g = M.ORBmatcher(0.75, True).SearchByProjectionSim3(KF, P, Tcw, Ow, K, th)
+    assert n_o > 20
+    assert n_g == n_o and np.array_equal(s_g, s_o), int((s_g != s_o).sum())
+    hit = np.nonzero(s_g >= 0)[0]
+    assert np.all(P.valid[s_g[hit]] == 1) and np.all(KF.occupied[hit] == 0)
+
+
+def test_pose_projection_overloads_edge_cases(M, oracle, views):
+    v = views[7]
+    F, P, Tcw, Ow, K = mf.world_points_case(v, 77)
+    mt = M.ORBmatcher(0.9, True)
+    same = lambda a, b: (a[0] == b[0] and np.array_equal(a[1], b[1]))
+    # no occupancy, no validity mask; identity pose puts most points outside the image
+    F2 = M.FrameView(F.mvKeysUn, F.mDescriptors, F.mvScaleFactors, F.bounds)
+    P2 = M.WorldPointsView(P.world_pos, P.descriptors, P.max_distance, P.min_distance, P.normal, P.angle)
+    assert same(mt.SearchByProjectionKF(F2, P2, Tcw, Ow, K, 10.0, 100), oracle.port_search_by_projection_kf(F2, P2, Tcw, Ow, K, 10.0, 100, True))
+    assert same(mt.SearchByProjectionSim3(F2, P2, Tcw, Ow, K, 10), oracle.port_search_by_projection_sim3(F2, P2, Tcw, Ow, K, 10))
+    I = np.eye(4, dtype=np.float32)[:3]
+    z3 = np.zeros(3, np.float32)
+    assert same(mt.SearchByProjectionKF(F2, P2, I, z3, K, 10.0, 100), oracle.port_search_by_projection_kf(F2, P2, I, z3, K, 10.0, 100, True))
+    assert same(mt.SearchByProjectionSim3(F2, P2, I, z3, K, 10), oracle.port_search_by_projection_sim3(F2, P2, I, z3, K, 10))
+    # points exactly at the camera centre (zero distance, division by zero depth) and at infinity must not crash or match
+    bad = P.world_pos.copy(); bad[:40] = Ow; bad[40:80] = 1e30
+    P3 = M.WorldPointsView(bad, P.descriptors, P.max_distance, P.min_distance, P.normal, P.angle)
+    assert same(mt.SearchByProjectionKF(F2, P3, Tcw, Ow, K, 10.0, 100), oracle.port_search_by_projection_kf(F2, P3, Tcw, Ow, K, 10.0, 100, True))
+    assert same(mt.SearchByProjectionSim3(F2, P3, Tcw, Ow, K, 10), oracle.port_search_by_projection_sim3(F2, P3, Tcw, Ow, K, 10))
+    # zero query points
+    P0 = M.WorldPointsView(np.zeros((0, 3), np.float32), np.zeros((0, 32), np.uint8), np.zeros(0, np.float32), np.zeros(0, np.float32),
+                           np.zeros((0, 3), np.float32), np.zeros(0, np.float32))
+    n, s = mt.SearchByProjectionSim3(F2, P0, Tcw, Ow, K, 10)
+    assert n == 0 and np.all(s == -1)

@@ -101,3 +101,79 @@ def test_vocabulary_text_round_trip_and_descent(oracle, tmp_path, views):
             if lvl == 1:
                 at1 = node
         assert e1["word_id"][node] == w1[f] and at1 == n1[f]
+
+
+def _hamming(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def test_projection_sim3_equals_numpy_rederivation(oracle, views):
+    """SearchByProjection(pKF, Scw, ...) (ORBmatcher.cc:290-403) re-derived in float32 numpy, without the grid: the area
+    query is a brute-force window, candidates visited in the grid's (cell x, cell y, insertion) order."""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6"); libm.logf.restype = C.c_float; libm.logf.argtypes = [C.c_float]
+    f32 = np.float32
+    KF, P, Tcw, Ow, K = mf.world_points_case(views, 41)
+    fx, fy, cx, cy = map(f32, K)
+    th = 10
+    n_o, s_o = oracle.port_search_by_projection_sim3(KF, P, Tcw, Ow, K, th)
+    k = KF.mvKeysUn
+    minX, minY, maxX, maxY = map(f32, KF.bounds)
+    invw, invh = f32(64) / (maxX - minX), f32(48) / (maxY - minY)
+    cellx = np.floor((k["x"] - minX) * invw + f32(0.5)).astype(int); celly = np.floor((k["y"] - minY) * invh + f32(0.5)).astype(int)
+    order = sorted(range(len(k)), key=lambda i: (cellx[i], celly[i], i))
+    logs = f32(libm.logf(float(f32(KF.mvScaleFactors[1]))))
+    held = KF.occupied.astype(bool).copy()
+    state = np.full(len(k), -1, np.int32)
+    nm = 0
+    T = Tcw.astype(f32)
+    for i in range(len(P.world_pos)):
+        if not P.valid[i]:
+            continue
+        p = P.world_pos[i]
+        pc = [f32(f32(f32(T[r, 0] * p[0]) + f32(T[r, 1] * p[1])) + f32(T[r, 2] * p[2])) + T[r, 3] for r in range(3)]
+        if pc[2] < 0:
+            continue
+        with np.errstate(all="ignore"):
+            invz = f32(1) / pc[2]
+            u = f32(fx * f32(pc[0] * invz)) + cx
+            v = f32(fy * f32(pc[1] * invz)) + cy
+        if not (u >= minX and u < maxX and v >= minY and v < maxY):
+            continue
+        PO = (p - Ow.astype(f32)).astype(f32)
+        dist = f32(np.sqrt(np.sum(PO.astype(np.float64) ** 2)))
+        if dist < f32(0.8) * P.min_distance[i] or dist > f32(1.2) * P.max_distance[i]:
+            continue
+        if float(np.dot(PO.astype(np.float64), P.normal[i].astype(np.float64))) < 0.5 * float(dist):
+            continue
+        ratio = P.max_distance[i] / dist
+        lvl = int(np.ceil(f32(libm.logf(float(ratio))) / logs))
+        lvl = min(max(lvl, 0), len(KF.mvScaleFactors) - 1)
+        r = f32(th) * f32(KF.mvScaleFactors[lvl])
+        best, bidx = 256, -1
+        for j in order:
+            if not (abs(k["x"][j] - u) < r and abs(k["y"][j] - v) < r) or held[j]:
+                continue
+            if k["octave"][j] < lvl - 1 or k["octave"][j] > lvl:
+                continue
+            d = _hamming(P.descriptors[i], KF.mDescriptors[j])
+            if d < best:
+                best, bidx = d, j
+        if best <= 50:
+            state[bidx] = i; held[bidx] = True; nm += 1
+    assert nm == n_o and nm > 50
+    assert np.array_equal(state, s_o)
+
+
+def test_projection_kf_invariants(oracle, views):
+    Cur, P, Tcw, Ow, K = mf.world_points_case(views, 42)
+    n, s = oracle.port_search_by_projection_kf(Cur, P, Tcw, Ow, K, 10.0, 100, True)
+    n2, s2 = oracle.port_search_by_projection_kf(Cur, P, Tcw, Ow, K, 10.0, 100, False)
+    assert n == int((s >= 0).sum()) and n > 50
+    assert n2 >= n and np.all((s2 >= 0) | (s < 0))                       # the orientation cull only removes matches
+    assert np.array_equal(s2[s >= 0], s[s >= 0])
+    hit = np.nonzero(s2 >= 0)[0]
+    assert np.all(Cur.occupied[hit] == 0) and np.all(P.valid[s2[hit]] == 1)
+    assert len(set(s2[hit].tolist())) == len(hit)                        # a query claims at most one feature
+    for j in hit[:100]:
+        assert _hamming(P.descriptors[s2[j]], Cur.mDescriptors[j]) <= 100

@@ -21,6 +21,8 @@ mt = M.ORBmatcher(0.8, True)
 print("proj", mt.SearchByProjection(F, mps, 3.0)[0])
 Cur, Last, Tcw, K = mf.last_frame_case(v, 2)
 print("last", mt.SearchByProjectionLast(Cur, Last, Tcw, K, 40.0, 7.0)[0])
+Fw, Pw, Tw, Ow, Kw = mf.world_points_case(v, 4)
+print("kf/sim3", mt.SearchByProjectionKF(Fw, Pw, Tw, Ow, Kw, 10.0, 100)[0], mt.SearchByProjectionSim3(Fw, Pw, Tw, Ow, Kw, 10)[0])
 pv = O.PortVocabulary.random(10, 3, 5)
 e = pv.export()
 voc = M.ORBVocabulary.from_arrays(e["parent"], e["is_leaf"], e["desc"], e["weight"], e["k"], e["L"])
