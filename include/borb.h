@@ -253,6 +253,41 @@ BORB_API borb_status borb_search_by_projection_sim3(borb_matcher* m, const borb_
                                                     const float* Tcw, const float* Ow, float fx, float fy, float cx, float cy,
                                                     float log_scale_factor, int th, int32_t* state_kf, int32_t* n_matches);
 
+/* The search part of ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th)
+ * — src/ORBmatcher.cc:825-970 (LocalMapping::SearchInNeighbors, src/LocalMapping.cc:483-511) — with scw_variant = 0, and of
+ * ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw, vpPoints, th, vpReplacePoint) — :972-1100 (LoopClosing::SearchAndFuse,
+ * src/LoopClosing.cc:589) — with scw_variant = 1 (Tcw = [Rcw|tcw] with the scale divided out, :983-987).
+ * best_idx[i] = feature of pKF selected for point i (bestDist <= TH_LOW), else -1; n_found = how many.  The MapPoint
+ * bookkeeping that follows in the reference (:947-966 / :1077-1090: Replace, AddObservation, AddMapPoint, vpReplacePoint)
+ * stays with the caller, applied in order; it feeds back into the search only through isBad()/IsInKeyFrame() of a
+ * point listed twice, which the caller re-tests when it applies best_idx.
+ * kf->u_right = pKF->mvuRight (scw_variant 0; NULL = monocular), inv_level_sigma2 = pKF->mvInvLevelSigma2 (scw_variant 0),
+ * pts->valid[i] = pMP && !isBad() && !IsInKeyFrame(pKF) (resp. !spAlreadyFound.count(pMP)). kf->occupied is ignored. */
+BORB_API borb_status borb_fuse(borb_matcher* m, const borb_frame_view* kf, const float* inv_level_sigma2,
+                               const borb_worldpoints_view* pts, const float* Tcw, const float* Ow, float fx, float fy, float cx,
+                               float cy, float bf, float log_scale_factor, float th, int scw_variant, int32_t* best_idx,
+                               int32_t* n_found);
+
+/* ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) — src/ORBmatcher.cc:1102-1326
+ * (LoopClosing::ComputeSim3, src/LoopClosing.cc:375-378).  pts1 / pts2 = GetMapPointMatches() of the two keyframes
+ * (one slot per feature: pts->n == kf->n) with valid[i] = pMP && !vbAlreadyMatched[i] && !isBad() (:1130-1141,:1151-1155).
+ * T1w / T2w = the keyframe poses (3x4); S12 = [s12*R12 | t12], S21 = [(1/s12)*R12^T | -sR21*t12] as the reference's
+ * cv::Mat lines produce them (:1119-1122).  (fx,fy,cx,cy) = pKF1's intrinsics, used for both directions (:1105-1108).
+ * match12[i1] = index in KF2 whose MapPoint goes to vpMatches12[i1], or -1; n_found = return value. */
+BORB_API borb_status borb_search_by_sim3(borb_matcher* m, const borb_frame_view* kf1, const borb_frame_view* kf2,
+                                         const borb_worldpoints_view* pts1, const borb_worldpoints_view* pts2, const float* T1w,
+                                         const float* T2w, const float* S12, const float* S21, float fx, float fy, float cx, float cy,
+                                         float log_scale_factor1, float log_scale_factor2, float th, int32_t* match12,
+                                         int32_t* n_found);
+
+/* ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12,
+ * int windowSize) — src/ORBmatcher.cc:405-520 (Tracking::MonocularInitialization, src/Tracking.cc:599).
+ * f1/f2: keys_un, desc (and f2's grid bounds) are read; prev_matched = vbPrevMatched as f1->n x 2 floats, updated in
+ * place (:513-517); matches12[i1] = index in F2 or -1; n_matches = return value. */
+BORB_API borb_status borb_search_for_initialization(borb_matcher* m, const borb_frame_view* f1, const borb_frame_view* f2,
+                                                    float* prev_matched, int window_size, float nnratio, int check_orientation,
+                                                    int32_t* matches12, int32_t* n_matches);
+
 /* DBoW2::FeatureVector (ordered map NodeId -> feature indices) as CSR; node_id ascending. */
 typedef struct borb_featvec_view {
     int32_t n_nodes;

@@ -313,6 +313,61 @@ def port_search_by_projection_sim3(KF, P, Tcw, Ow, K, th):
     return n, state[:len(k)]
 
 
+def port_fuse(KF, P, Tcw, Ow, K, bf, th, scw):
+    """Search part of Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:825-970) / Fuse(pKF, Scw, ...) (:972-1100)."""
+    lib = _plib()
+    k = _a(KF.mvKeysUn, KP_DTYPE); d = _a(KF.mDescriptors, np.uint8); sf = _a(KF.mvScaleFactors, np.float32)
+    ur = _a(KF.mvuRight, np.float32) if KF.mvuRight is not None else None
+    inv = _a(KF.mvInvLevelSigma2, np.float32) if KF.mvInvLevelSigma2 is not None else None
+    wp, md, mx, mn, va = _points_args(P)
+    nr = _a(P.normal, np.float32)
+    T = _a(np.asarray(Tcw, np.float32)[:3, :4].reshape(12), np.float32); ow = _a(np.asarray(Ow, np.float32).reshape(3), np.float32)
+    best = np.full(max(len(wp), 1), -1, np.int32)
+    fn = lib.orbport_fuse
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 6 + [C.c_int]
+                   + [C.c_void_p] * 2 + [C.c_float] * 6 + [C.c_int, C.c_void_p])
+    n = fn(_ptr(k), _ptr(d), _ptr(ur) if ur is not None else None, _ptr(inv) if inv is not None else None, len(k),
+           *[float(b) for b in KF.bounds], _ptr(sf), len(sf), _log_scale(KF), _ptr(wp), _ptr(md), _ptr(mx), _ptr(mn), _ptr(nr), _ptr(va),
+           len(wp), _ptr(T), _ptr(ow), float(K[0]), float(K[1]), float(K[2]), float(K[3]), float(bf), float(th), int(scw), _ptr(best))
+    return n, best[:len(wp)]
+
+
+def port_search_by_sim3(KF1, KF2, P1, P2, T1w, T2w, S12, S21, K, th):
+    """SearchBySim3 (ORBmatcher.cc:1102-1326)."""
+    lib = _plib()
+    k1 = _a(KF1.mvKeysUn, KP_DTYPE); d1 = _a(KF1.mDescriptors, np.uint8); sf1 = _a(KF1.mvScaleFactors, np.float32)
+    k2 = _a(KF2.mvKeysUn, KP_DTYPE); d2 = _a(KF2.mDescriptors, np.uint8); sf2 = _a(KF2.mvScaleFactors, np.float32)
+    b1 = _a(np.asarray(KF1.bounds, np.float32), np.float32); b2 = _a(np.asarray(KF2.bounds, np.float32), np.float32)
+    wp1, md1, mx1, mn1, va1 = _points_args(P1)
+    wp2, md2, mx2, mn2, va2 = _points_args(P2)
+    mats = [_a(np.asarray(M, np.float32)[:3, :4].reshape(12), np.float32) for M in (T1w, T2w, S12, S21)]
+    match = np.full(max(len(k1), 1), -1, np.int32)
+    fn = lib.orbport_search_by_sim3
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float] * 2 + [C.c_int] + [C.c_void_p] * 10 + [C.c_void_p] * 4
+                   + [C.c_float] * 5 + [C.c_void_p])
+    n = fn(_ptr(k1), _ptr(d1), len(k1), _ptr(b1), _ptr(sf1), _log_scale(KF1), _ptr(k2), _ptr(d2), len(k2), _ptr(b2), _ptr(sf2),
+           _log_scale(KF2), len(sf1), _ptr(wp1), _ptr(md1), _ptr(mx1), _ptr(mn1), _ptr(va1), _ptr(wp2), _ptr(md2), _ptr(mx2), _ptr(mn2),
+           _ptr(va2), *[_ptr(M) for M in mats], float(K[0]), float(K[1]), float(K[2]), float(K[3]), float(th), _ptr(match))
+    return n, match[:len(k1)]
+
+
+def port_search_for_initialization(F1, F2, prev_matched, window, nnratio, check_ori):
+    """SearchForInitialization (ORBmatcher.cc:405-520); returns (nmatches, vnMatches12, updated vbPrevMatched)."""
+    lib = _plib()
+    k1 = _a(F1.mvKeysUn, KP_DTYPE); d1 = _a(F1.mDescriptors, np.uint8)
+    k2 = _a(F2.mvKeysUn, KP_DTYPE); d2 = _a(F2.mDescriptors, np.uint8)
+    prev = np.ascontiguousarray(np.asarray(prev_matched, np.float32).reshape(-1, 2)).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    fn = lib.orbport_search_for_initialization
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = fn(_ptr(k1), _ptr(d1), len(k1), _ptr(k2), _ptr(d2), len(k2), *[float(b) for b in F2.bounds], _ptr(prev), int(window),
+           float(np.float32(nnratio)), int(check_ori), _ptr(m12))
+    return n, m12[:len(k1)], prev
+
+
 def _kf_args(kf):
     k = _a(kf.mvKeysUn, KP_DTYPE); d = _a(kf.mDescriptors, np.uint8)
     hm = _a(kf.has_mp, np.uint8) if kf.has_mp is not None else np.zeros(len(k), np.uint8)

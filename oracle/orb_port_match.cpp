@@ -645,3 +645,191 @@ extern "C" int orbport_search_by_projection_sim3(const orbport_kp* kf_keys_un, c
     }
     return nmatches;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ORBmatcher::Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th) — reference
+// src/ORBmatcher.cc:825-970 (LocalMapping::SearchInNeighbors, src/LocalMapping.cc:483-511), and
+// ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw, vpPoints, th, vpReplacePoint) — :972-1100 (LoopClosing::SearchAndFuse).
+// The search part only: best_idx[i] = keyframe feature selected for point i (bestDist <= TH_LOW), else -1.  The map
+// mutation that follows (:947-966 / :1077-1090: Replace / AddObservation / AddMapPoint) does not feed back into the
+// search of later points except through `isBad()` / `IsInKeyFrame()` of a point that occurs twice in the list; the
+// adapter applies best_idx in order and re-evaluates those two tests when it does.
+// scw_variant = 0: invz = 1/z in float, stereo/mono reprojection gates (7.8 / 5.99); 1: invz = 1.0/z, no gates.
+extern "C" int orbport_fuse(const orbport_kp* kf_keys_un, const uint8_t* kf_desc, const float* kf_u_right, const float* inv_level_sigma2,
+                            int n_kf, float minX, float minY, float maxX, float maxY, const float* scale_factors, int n_levels,
+                            float log_scale_factor, const float* world_pos, const uint8_t* mp_desc, const float* max_distance,
+                            const float* min_distance, const float* normal, const uint8_t* valid, int n_q, const float* Tcw,
+                            const float* Ow, float fx, float fy, float cx, float cy, float bf, float th, int scw_variant,
+                            int32_t* best_idx) {
+    Grid g = build_grid(kf_keys_un, n_kf, minX, minY, maxX, maxY);
+    int nFound = 0;
+    for (int i = 0; i < n_q; i++) {
+        best_idx[i] = -1;
+        if (valid && !valid[i]) continue;
+        const float* P = world_pos + 3 * (size_t)i;
+        const float p3Dc[3] = {((Tcw[0] * P[0] + Tcw[1] * P[1]) + Tcw[2] * P[2]) + Tcw[3],
+                               ((Tcw[4] * P[0] + Tcw[5] * P[1]) + Tcw[6] * P[2]) + Tcw[7],
+                               ((Tcw[8] * P[0] + Tcw[9] * P[1]) + Tcw[10] * P[2]) + Tcw[11]};
+        if (p3Dc[2] < 0.0f) continue;
+        float invz;
+        if (scw_variant) invz = 1.0 / p3Dc[2]; else invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz;
+        const float y = p3Dc[1] * invz;
+        const float u = fx * x + cx;
+        const float v = fy * y + cy;
+        if (!(u >= minX && u < maxX && v >= minY && v < maxY)) continue;
+        const float ur = u - bf * invz;
+        const float maxDistance = 1.2f * max_distance[i];
+        const float minDistance = 0.8f * min_distance[i];
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist3D = norm3(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        if (dot3(PO, normal + 3 * (size_t)i) < 0.5 * dist3D) continue;
+        const int nPredictedLevel = predict_scale(max_distance[i], dist3D, log_scale_factor, n_levels);
+        const float radius = th * scale_factors[nPredictedLevel];
+        const std::vector<int> vIndices = features_in_area(g, kf_keys_un, u, v, radius, -1, -1);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            const orbport_kp& kp = kf_keys_un[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            if (!scw_variant) {
+                if (kf_u_right && kf_u_right[idx] >= 0) {
+                    const float ex = u - kp.x, ey = v - kp.y, er = ur - kf_u_right[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float ex = u - kp.x, ey = v - kp.y;
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = orbport_hamming(dMP, kf_desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) { best_idx[i] = bestIdx; nFound++; }
+    }
+    return nFound;
+}
+
+// One direction of ORBmatcher::SearchBySim3 (:1146-1222 / :1224-1300): MapPoints of keyframe A (world_pos, through
+// A's pose Taw then the similarity [sRba | tba]) searched among keyframe B's features.  match[i] = B feature or -1.
+static void sim3_direction(const orbport_kp* kB, const uint8_t* dB, int nB, const float* boundsB, const float* sfB, int n_levels,
+                           float log_scale, const float* world_pos, const uint8_t* mp_desc, const float* max_distance,
+                           const float* min_distance, const uint8_t* valid, int nA, const float* Taw, const float* Sba, float fx,
+                           float fy, float cx, float cy, float th, int32_t* match) {
+    Grid g = build_grid(kB, nB, boundsB[0], boundsB[1], boundsB[2], boundsB[3]);
+    for (int i = 0; i < nA; i++) {
+        match[i] = -1;
+        if (valid && !valid[i]) continue;
+        const float* P = world_pos + 3 * (size_t)i;
+        const float a[3] = {((Taw[0] * P[0] + Taw[1] * P[1]) + Taw[2] * P[2]) + Taw[3],
+                            ((Taw[4] * P[0] + Taw[5] * P[1]) + Taw[6] * P[2]) + Taw[7],
+                            ((Taw[8] * P[0] + Taw[9] * P[1]) + Taw[10] * P[2]) + Taw[11]};
+        const float b[3] = {((Sba[0] * a[0] + Sba[1] * a[1]) + Sba[2] * a[2]) + Sba[3],
+                            ((Sba[4] * a[0] + Sba[5] * a[1]) + Sba[6] * a[2]) + Sba[7],
+                            ((Sba[8] * a[0] + Sba[9] * a[1]) + Sba[10] * a[2]) + Sba[11]};
+        if (b[2] < 0.0) continue;
+        const float invz = 1.0 / b[2];
+        const float x = b[0] * invz;
+        const float y = b[1] * invz;
+        const float u = fx * x + cx;
+        const float v = fy * y + cy;
+        if (!(u >= boundsB[0] && u < boundsB[2] && v >= boundsB[1] && v < boundsB[3])) continue;
+        const float maxDistance = 1.2f * max_distance[i];
+        const float minDistance = 0.8f * min_distance[i];
+        const float dist3D = norm3(b);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = predict_scale(max_distance[i], dist3D, log_scale, n_levels);
+        const float radius = th * sfB[nPredictedLevel];
+        const std::vector<int> vIndices = features_in_area(g, kB, u, v, radius, -1, -1);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = mp_desc + (size_t)i * 32;
+        int bestDist = INT32_MAX, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (kB[idx].octave < nPredictedLevel - 1 || kB[idx].octave > nPredictedLevel) continue;
+            const int dist = orbport_hamming(dMP, dB + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_HIGH) match[i] = bestIdx;
+    }
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) — reference src/ORBmatcher.cc:1102-1326
+// (LoopClosing::ComputeSim3, src/LoopClosing.cc:375-378).  T1w/T2w = keyframe poses (3x4); S12 = [s12*R12 | t12] and
+// S21 = [(1/s12)*R12^T | -sR21*t12] as the caller's cv::Mat lines produce them (:1119-1122).
+// valid1[i1] = vpMapPoints1[i1] && !vbAlreadyMatched1[i1] && !isBad() (same for 2).  Both projections use pKF1's
+// intrinsics (:1105-1108) — replicated.  match12[i1] = index in KF2 of the agreed match, else -1.
+extern "C" int orbport_search_by_sim3(const orbport_kp* k1, const uint8_t* d1, int n1, const float* bounds1, const float* sf1,
+                                      float log_scale1, const orbport_kp* k2, const uint8_t* d2, int n2, const float* bounds2,
+                                      const float* sf2, float log_scale2, int n_levels, const float* wp1, const uint8_t* md1,
+                                      const float* max1, const float* min1, const uint8_t* valid1, const float* wp2,
+                                      const uint8_t* md2, const float* max2, const float* min2, const uint8_t* valid2,
+                                      const float* T1w, const float* T2w, const float* S12, const float* S21, float fx, float fy,
+                                      float cx, float cy, float th, int32_t* match12) {
+    std::vector<int32_t> vnMatch1(n1 > 0 ? n1 : 1, -1), vnMatch2(n2 > 0 ? n2 : 1, -1);
+    sim3_direction(k2, d2, n2, bounds2, sf2, n_levels, log_scale2, wp1, md1, max1, min1, valid1, n1, T1w, S21, fx, fy, cx, cy, th, vnMatch1.data());
+    sim3_direction(k1, d1, n1, bounds1, sf1, n_levels, log_scale1, wp2, md2, max2, min2, valid2, n2, T2w, S12, fx, fy, cx, cy, th, vnMatch2.data());
+    int nFound = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        match12[i1] = -1;
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0) {
+            const int idx1 = vnMatch2[idx2];
+            if (idx1 == i1) { match12[i1] = idx2; nFound++; }
+        }
+    }
+    return nFound;
+}
+
+// ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12,
+// int windowSize) — reference src/ORBmatcher.cc:405-520 (Tracking::MonocularInitialization, src/Tracking.cc:599).
+// prev_matched: n1 x 2 floats, updated in place (:513-517).
+extern "C" int orbport_search_for_initialization(const orbport_kp* k1, const uint8_t* d1, int n1, const orbport_kp* k2, const uint8_t* d2,
+                                                 int n2, float minX, float minY, float maxX, float maxY, float* prev_matched,
+                                                 int windowSize, float nnratio, int check_ori, int32_t* vnMatches12) {
+    Grid g = build_grid(k2, n2, minX, minY, maxX, maxY);
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) vnMatches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> vMatchedDistance(n2, INT32_MAX);
+    std::vector<int> vnMatches21(n2, -1);
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = k1[i1].octave;
+        if (level1 > 0) continue;
+        const std::vector<int> vIndices2 = features_in_area(g, k2, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)windowSize, level1, level1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dd1 = d1 + (size_t)i1 * 32;
+        int bestDist = INT32_MAX, bestDist2 = INT32_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = orbport_hamming(dd1, d2 + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) rotHist[rot_bin(k1[i1].angle, k2[bestIdx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (vnMatches12[i1] >= 0) { prev_matched[2 * i1] = k2[vnMatches12[i1]].x; prev_matched[2 * i1 + 1] = k2[vnMatches12[i1]].y; }
+    return nmatches;
+}

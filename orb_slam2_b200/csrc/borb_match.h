@@ -35,6 +35,8 @@ struct ProjArgs {                 // device pointers
     int check_ori;
     const float* q_angle;         // mode 1: mvKeysUn[i].angle of the query
     int th_dist;                  // mode 1: accept bestDist <= th_dist (TH_HIGH / ORBdist / TH_LOW)
+    int chi2;                     // 1: Fuse(pKF, vpMapPoints, th) reprojection gates per candidate (:907-931)
+    const float* inv_sigma2;      // chi2: mvInvLevelSigma2
     uint8_t* q_valid_out;         // mode 1: validity written by project_last_kernel (aliases mp_valid)
 };
 
@@ -49,6 +51,11 @@ struct LastArgs {                 // inputs of project_points_kernel
     float Ow[3];
     float log_scale;
     int n_levels;
+    // variant 2 options (Fuse x2, SearchBySim3 directions share its code path)
+    int invz_double;              // invz = 1.0/z evaluated in double (:1014, :1164) instead of 1/z in float (:333, :861)
+    int use_normal;               // viewing-angle gate PO.dot(Pn) < 0.5*dist
+    int chain;                    // second transform T2 applied to the camera-frame point; distance = |point in camera 2| (:1157-1177)
+    float T2[12];
     const float* world_pos;       // n_last x 3
     const uint8_t* valid_in;      // may be null
     float T[12];                  // Tcw rows 0..2
@@ -90,6 +97,10 @@ int launch_grid_sort(const borb_keypoint* keys, int n, float minX, float minY, f
 int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s);
 int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_cur, int32_t* hist_idx, uint8_t* hist_bin, int* n_matches,
                            cudaStream_t s);
+int launch_initialization(const ProjArgs& A, const borb_keypoint* keys1, int n1, int32_t* match12, int32_t* ev_idx, uint8_t* ev_bin,
+                          float* prev, int* n_matches, cudaStream_t s);
+int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best_idx, int* n_found, cudaStream_t s);
+int launch_sim3_agree(const int32_t* match1, const int32_t* match2, int n1, int n2, int32_t* match12, int* n_found, cudaStream_t s);
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
                      int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s);
 int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,

@@ -17,6 +17,8 @@ struct borb_matcher {
     uint8_t* h_stage = nullptr;     // pinned staging mirror of the arena's input part
     size_t h_bytes = 0;
     uint64_t launches = 0;
+    int32_t* aux = nullptr;         // small device buffer that survives an arena re-layout (SearchBySim3: first direction's matches)
+    size_t aux_count = 0;
 };
 
 struct borb_voc {
@@ -166,6 +168,7 @@ borb_status borb_matcher_destroy(borb_matcher* m) {
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     cudaFree(m->arena);
+    cudaFree(m->aux);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -246,12 +249,25 @@ struct PointQuery {
     const float* Ow;
     float fx, fy, cx, cy, bf, th, log_scale;
     int forward, backward, check_ori, th_dist;
+    // variant 2 family (order-independent overloads share the projection code)
+    int invz_double, use_normal, chain;
+    const float* T2;                // chain: [sR | t] applied after Tcw
+    int argmin;                     // 1: per-query first-minimum (no claim replay); `state` then has Q.n entries
+    int chi2;                       // Fuse(pKF, ...) reprojection gates
+    const float* inv_sigma2;        // chi2: mvInvLevelSigma2 (n_levels)
+    int to_aux;                     // 1: leave the result in m->aux + aux_off (device) instead of downloading it
+    size_t aux_off;
 };
 
 static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* F, const PointQuery& Q, int32_t* state, int32_t* n_matches) {
     *n_matches = 0;
     if (F->n < 0 || F->n > MATCH_MAX_FEATURES || Q.n < 0 || Q.n > MATCH_MAX_FEATURES) { set_error("feature count outside [0,%d]", MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
-    for (int i = 0; i < F->n; i++) state[i] = -1;
+    const int n_out = Q.argmin ? Q.n : F->n;
+    if (state) for (int i = 0; i < n_out; i++) state[i] = -1;
+    if (Q.to_aux) {                 // caller sized m->aux; "no match" everywhere until the kernels say otherwise
+        BORB_CUDA(cudaSetDevice(m->device));
+        if (Q.n > 0) BORB_CUDA(cudaMemsetAsync(m->aux + Q.aux_off, 0xFF, (size_t)Q.n * 4, m->stream));
+    }
     if (F->n == 0 || Q.n == 0) return BORB_OK;
     if (!F->keys_un || !F->desc || !F->scale_factors || F->n_levels < 1 || !Q.world_pos || !Q.desc || !(F->max_x > F->min_x) || !(F->max_y > F->min_y)) {
         set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG;
@@ -261,7 +277,8 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
         for (int i = 0; i < Q.n; i++)
             if (Q.keys[i].octave < 0 || Q.keys[i].octave >= F->n_levels) { set_error("last-frame keypoint %d: octave out of range", i); return BORB_ERR_INVALID_ARG; }
     } else {
-        if (!Q.max_distance || !Q.min_distance || !Q.Ow || (Q.variant == 2 && !Q.normal) || (Q.variant == 1 && Q.check_ori && !Q.angle)) {
+        if (!Q.max_distance || !Q.min_distance || (!Q.Ow && !Q.chain) || (Q.variant == 2 && Q.use_normal && !Q.normal) ||
+            (Q.variant == 1 && Q.check_ori && !Q.angle) || (Q.chain && !Q.T2) || (Q.chi2 && !Q.inv_sigma2)) {
             set_error("incomplete world-points view"); return BORB_ERR_INVALID_ARG;
         }
         if (!(Q.log_scale > 0.f)) { set_error("log_scale_factor must be positive (Frame::mfLogScaleFactor)"); return BORB_ERR_INVALID_ARG; }
@@ -269,7 +286,7 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     BORB_CUDA(cudaSetDevice(m->device));
     Stager st(m);
     const int nq = Q.n;
-    const bool stereo = Q.variant == 0 && F->u_right != nullptr;
+    const bool stereo = (Q.variant == 0 || Q.chi2) && F->u_right != nullptr;
     const size_t o_keys = st.add(F->keys_un, (size_t)F->n * sizeof(borb_keypoint));
     const size_t o_desc = st.add(F->desc, (size_t)F->n * 32);
     const size_t o_ur = stereo ? st.add(F->u_right, (size_t)F->n * 4) : 0;
@@ -284,12 +301,13 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     const size_t o_mn = Q.min_distance ? st.add(Q.min_distance, (size_t)nq * 4) : 0;
     const size_t o_nr = Q.normal ? st.add(Q.normal, (size_t)nq * 12) : 0;
     const size_t o_qa = Q.angle ? st.add(Q.angle, (size_t)nq * 4) : 0;
+    const size_t o_is2 = Q.chi2 ? st.add(Q.inv_sigma2, (size_t)F->n_levels * 4) : 0;
     const size_t input_end = st.off;
     const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
     const size_t o_px = st.reserve((size_t)nq * 4), o_py = st.reserve((size_t)nq * 4), o_pxr = st.reserve((size_t)nq * 4), o_rad = st.reserve((size_t)nq * 4);
     const size_t o_ang = st.reserve((size_t)nq * 4), o_minl = st.reserve((size_t)nq * 4), o_maxl = st.reserve((size_t)nq * 4), o_val = st.reserve((size_t)nq);
     const size_t o_cand = st.reserve((size_t)nq * F->n * 4), o_cc = st.reserve((size_t)nq * 4);
-    const size_t o_state = st.reserve((size_t)F->n * 4), o_evi = st.reserve((size_t)nq * 4), o_evb = st.reserve((size_t)nq), o_nm = st.reserve(16);
+    const size_t o_state = st.reserve((size_t)(F->n > nq ? F->n : nq) * 4), o_evi = st.reserve((size_t)nq * 4), o_evb = st.reserve((size_t)nq), o_nm = st.reserve(16);
     const size_t total = st.off;
     st.off = input_end;
     borb_status s = commit(st, total);
@@ -304,6 +322,8 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     L.normal = Q.normal ? (const float*)(b + o_nr) : nullptr;
     for (int i = 0; i < 3; i++) L.Ow[i] = Q.Ow ? Q.Ow[i] : 0.f;
     L.log_scale = Q.log_scale; L.n_levels = F->n_levels;
+    L.invz_double = Q.invz_double; L.use_normal = Q.use_normal; L.chain = Q.chain;
+    for (int i = 0; i < 12; i++) L.T2[i] = Q.chain ? Q.T2[i] : 0.f;
     L.valid_in = Q.valid ? b + o_vin : nullptr;
     for (int i = 0; i < 12; i++) L.T[i] = Q.Tcw[i];
     L.fx = Q.fx; L.fy = Q.fy; L.cx = Q.cx; L.cy = Q.cy; L.bf = Q.bf; L.th = Q.th;
@@ -327,11 +347,17 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
     A.q_radius = L.radius; A.q_minl = L.minl; A.q_maxl = L.maxl; A.mode = 1; A.check_ori = Q.check_ori; A.q_angle = L.angle;
     A.th_dist = Q.th_dist;
+    A.chi2 = Q.chi2; A.inv_sigma2 = Q.chi2 ? (const float*)(b + o_is2) : nullptr;
     A.q_valid_out = b + o_val;
     m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
-    m->launches += launch_projection_last(L, A, (int32_t*)(b + o_state), (int32_t*)(b + o_evi), b + o_evb, (int*)(b + o_nm), m->stream);
+    if (Q.argmin) m->launches += launch_projection_argmin(L, A, (int32_t*)(b + o_state), (int*)(b + o_nm), m->stream);
+    else m->launches += launch_projection_last(L, A, (int32_t*)(b + o_state), (int32_t*)(b + o_evi), b + o_evb, (int*)(b + o_nm), m->stream);
     BORB_CUDA(cudaGetLastError());
-    BORB_CUDA(cudaMemcpyAsync(state, b + o_state, (size_t)F->n * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (Q.to_aux) {
+        BORB_CUDA(cudaMemcpyAsync(m->aux + Q.aux_off, b + o_state, (size_t)n_out * 4, cudaMemcpyDeviceToDevice, m->stream));
+    } else {
+        BORB_CUDA(cudaMemcpyAsync(state, b + o_state, (size_t)n_out * 4, cudaMemcpyDeviceToHost, m->stream));
+    }
     BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaStreamSynchronize(m->stream));
     return BORB_OK;
@@ -369,7 +395,135 @@ borb_status borb_search_by_projection_sim3(borb_matcher* m, const borb_frame_vie
     Q.max_distance = pts->max_distance; Q.min_distance = pts->min_distance; Q.normal = pts->normal;
     Q.Tcw = Tcw; Q.Ow = Ow; Q.fx = fx; Q.fy = fy; Q.cx = cx; Q.cy = cy; Q.th = (float)th; Q.log_scale = log_scale_factor;
     Q.check_ori = 0; Q.th_dist = 50;                                       // TH_LOW (:394)
+    Q.use_normal = 1;
     return run_point_projection(m, kf, Q, state_kf, n_matches);
+}
+
+borb_status borb_fuse(borb_matcher* m, const borb_frame_view* kf, const float* inv_level_sigma2, const borb_worldpoints_view* pts,
+                      const float* Tcw, const float* Ow, float fx, float fy, float cx, float cy, float bf, float log_scale_factor,
+                      float th, int scw_variant, int32_t* best_idx, int32_t* n_found) {
+    if (!m || !kf || !pts || !Tcw || !Ow || !best_idx || !n_found) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (!scw_variant && !inv_level_sigma2) { set_error("Fuse(pKF, vpMapPoints, th) needs mvInvLevelSigma2"); return BORB_ERR_INVALID_ARG; }
+    PointQuery Q{};
+    Q.variant = 2; Q.n = pts->n; Q.world_pos = pts->world_pos; Q.desc = pts->desc; Q.valid = pts->valid;
+    Q.max_distance = pts->max_distance; Q.min_distance = pts->min_distance; Q.normal = pts->normal;
+    Q.Tcw = Tcw; Q.Ow = Ow; Q.fx = fx; Q.fy = fy; Q.cx = cx; Q.cy = cy; Q.bf = bf; Q.th = th; Q.log_scale = log_scale_factor;
+    Q.th_dist = 50;                                                        // TH_LOW (:944, :1075)
+    Q.use_normal = 1; Q.argmin = 1;
+    Q.invz_double = scw_variant ? 1 : 0;                                   // 1.0/z (:1014) vs 1/z (:861)
+    Q.chi2 = scw_variant ? 0 : 1; Q.inv_sigma2 = inv_level_sigma2;
+    // occupancy plays no role in either Fuse (the MapPoint already in the slot is handled by the caller, :947-960)
+    borb_frame_view F = *kf;
+    F.occupied = nullptr;
+    return run_point_projection(m, &F, Q, best_idx, n_found);
+}
+
+borb_status borb_search_by_sim3(borb_matcher* m, const borb_frame_view* kf1, const borb_frame_view* kf2, const borb_worldpoints_view* pts1,
+                                const borb_worldpoints_view* pts2, const float* T1w, const float* T2w, const float* S12, const float* S21,
+                                float fx, float fy, float cx, float cy, float log_scale_factor1, float log_scale_factor2, float th,
+                                int32_t* match12, int32_t* n_found) {
+    if (!m || !kf1 || !kf2 || !pts1 || !pts2 || !T1w || !T2w || !S12 || !S21 || !match12 || !n_found) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *n_found = 0;
+    if (pts1->n != kf1->n || pts2->n != kf2->n) { set_error("SearchBySim3: one MapPoint slot per keyframe feature (GetMapPointMatches)"); return BORB_ERR_INVALID_ARG; }
+    for (int i = 0; i < kf1->n; i++) match12[i] = -1;
+    if (kf1->n == 0 || kf2->n == 0) return BORB_OK;
+    borb_frame_view F1 = *kf1, F2 = *kf2;
+    F1.occupied = nullptr; F2.occupied = nullptr;
+    BORB_CUDA(cudaSetDevice(m->device));
+    const size_t need = (size_t)kf1->n + (size_t)kf2->n;
+    if (m->aux_count < need) {
+        cudaFree(m->aux); m->aux = nullptr; m->aux_count = 0;
+        BORB_CUDA(cudaMalloc(&m->aux, need * 4));
+        m->aux_count = need;
+    }
+    int32_t nm = 0;
+    // KF1's points into KF2 (:1146-1222) and KF2's points into KF1 (:1224-1300); both results stay on the device
+    PointQuery Q{};
+    Q.variant = 2; Q.n = pts1->n; Q.world_pos = pts1->world_pos; Q.desc = pts1->desc; Q.valid = pts1->valid;
+    Q.max_distance = pts1->max_distance; Q.min_distance = pts1->min_distance;
+    Q.Tcw = T1w; Q.chain = 1; Q.T2 = S21; Q.fx = fx; Q.fy = fy; Q.cx = cx; Q.cy = cy; Q.th = th; Q.log_scale = log_scale_factor2;
+    Q.th_dist = 100; Q.argmin = 1; Q.invz_double = 1; Q.to_aux = 1; Q.aux_off = 0;        // TH_HIGH (:1218)
+    borb_status s = run_point_projection(m, &F2, Q, nullptr, &nm);
+    if (s != BORB_OK) return s;
+    PointQuery R{};
+    R.variant = 2; R.n = pts2->n; R.world_pos = pts2->world_pos; R.desc = pts2->desc; R.valid = pts2->valid;
+    R.max_distance = pts2->max_distance; R.min_distance = pts2->min_distance;
+    R.Tcw = T2w; R.chain = 1; R.T2 = S12; R.fx = fx; R.fy = fy; R.cx = cx; R.cy = cy; R.th = th; R.log_scale = log_scale_factor1;
+    R.th_dist = 100; R.argmin = 1; R.invz_double = 1; R.to_aux = 1; R.aux_off = (size_t)kf1->n;
+    s = run_point_projection(m, &F1, R, nullptr, &nm);
+    if (s != BORB_OK) return s;
+    // agreement test (:1302-1323) on the device
+    Stager st(m);
+    const size_t o_out = st.reserve((size_t)kf1->n * 4), o_nf = st.reserve(16);
+    const size_t total = st.off;
+    st.off = 0;
+    if ((s = commit(st, total)) != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    m->launches += launch_sim3_agree(m->aux, m->aux + kf1->n, kf1->n, kf2->n, (int32_t*)(b + o_out), (int*)(b + o_nf), m->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaMemcpyAsync(match12, b + o_out, (size_t)kf1->n * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(n_found, b + o_nf, 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    return BORB_OK;
+}
+
+borb_status borb_search_for_initialization(borb_matcher* m, const borb_frame_view* f1, const borb_frame_view* f2, float* prev_matched,
+                                           int window_size, float nnratio, int check_orientation, int32_t* matches12, int32_t* n_matches) {
+    if (!m || !f1 || !f2 || !prev_matched || !matches12 || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *n_matches = 0;
+    if (f1->n < 0 || f1->n > MATCH_MAX_FEATURES || f2->n < 0 || f2->n > MATCH_MAX_FEATURES) { set_error("feature count outside [0,%d]", MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    for (int i = 0; i < f1->n; i++) matches12[i] = -1;
+    if (f1->n == 0 || f2->n == 0) return BORB_OK;
+    if (!f1->keys_un || !f1->desc || !f2->keys_un || !f2->desc || !(f2->max_x > f2->min_x) || !(f2->max_y > f2->min_y)) {
+        set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG;
+    }
+    BORB_CUDA(cudaSetDevice(m->device));
+    const int n1 = f1->n;
+    // the query windows are data the caller already has: vbPrevMatched as centre, windowSize as radius, level 0 only (:421-427)
+    std::vector<float> px(n1), py(n1), rad(n1, (float)window_size);
+    std::vector<int32_t> zero(n1, 0);
+    std::vector<uint8_t> valid(n1);
+    for (int i = 0; i < n1; i++) { px[i] = prev_matched[2 * i]; py[i] = prev_matched[2 * i + 1]; valid[i] = f1->keys_un[i].octave > 0 ? 0 : 1; }
+    Stager st(m);
+    const size_t o_k2 = st.add(f2->keys_un, (size_t)f2->n * sizeof(borb_keypoint));
+    const size_t o_d2 = st.add(f2->desc, (size_t)f2->n * 32);
+    const size_t o_k1 = st.add(f1->keys_un, (size_t)n1 * sizeof(borb_keypoint));
+    const size_t o_d1 = st.add(f1->desc, (size_t)n1 * 32);
+    const size_t o_px = st.add(px.data(), (size_t)n1 * 4), o_py = st.add(py.data(), (size_t)n1 * 4), o_rad = st.add(rad.data(), (size_t)n1 * 4);
+    const size_t o_lv = st.add(zero.data(), (size_t)n1 * 4), o_val = st.add(valid.data(), (size_t)n1);
+    const size_t o_prev = st.add(prev_matched, (size_t)n1 * 8);
+    const size_t input_end = st.off;
+    const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
+    const size_t o_cand = st.reserve((size_t)n1 * f2->n * 4), o_cc = st.reserve((size_t)n1 * 4);
+    const size_t o_m12 = st.reserve((size_t)n1 * 4), o_evi = st.reserve((size_t)n1 * 4), o_evb = st.reserve((size_t)n1), o_nm = st.reserve(16);
+    const size_t total = st.off;
+    st.off = input_end;
+    borb_status s = commit(st, total);
+    if (s != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    ProjArgs A{};
+    A.n = f2->n; A.keys = (const borb_keypoint*)(b + o_k2); A.desc = b + o_d2;
+    A.u_right = nullptr; A.occupied = nullptr;
+    A.minX = f2->min_x; A.minY = f2->min_y;
+    A.invW = (float)GRID_COLS / (float)(f2->max_x - f2->min_x);
+    A.invH = (float)GRID_ROWS / (float)(f2->max_y - f2->min_y);
+    A.scale_factors = nullptr;
+    A.cell_start = (const int*)(b + o_cs); A.cell_idx = (const int*)(b + o_ci);
+    A.n_mp = n1; A.proj_x = (const float*)(b + o_px); A.proj_y = (const float*)(b + o_py); A.proj_xr = (const float*)(b + o_px);
+    A.mp_desc = b + o_d1; A.mp_valid = b + o_val; A.mp_has_obs = nullptr;
+    A.th = 1.f; A.nnratio = nnratio;
+    A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
+    A.q_radius = (const float*)(b + o_rad); A.q_minl = (const int32_t*)(b + o_lv); A.q_maxl = (const int32_t*)(b + o_lv);
+    A.mode = 1; A.check_ori = check_orientation; A.th_dist = 50;
+    m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
+    m->launches += launch_initialization(A, (const borb_keypoint*)(b + o_k1), n1, (int32_t*)(b + o_m12), (int32_t*)(b + o_evi), b + o_evb,
+                                         (float*)(b + o_prev), (int*)(b + o_nm), m->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaMemcpyAsync(matches12, b + o_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(prev_matched, b + o_prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    return BORB_OK;
 }
 
 static borb_status bow_common(borb_matcher* m, const borb_keyframe_view* qs, int n_q, const borb_keyframe_view* t, int mode, float nnratio,

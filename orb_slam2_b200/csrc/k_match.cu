@@ -155,11 +155,24 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
                                 const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
                                 ok = fabsf(dx) < rs && fabsf(dy) < rs;
                             }
-                            if (ok && A.u_right != nullptr) {            // stereo consistency (:91-96)
+                            if (ok && A.u_right != nullptr && !A.chi2) { // stereo consistency (:91-96)
                                 const float ur = A.u_right[idx];
                                 if (ur > 0) {
                                     const float er = fabsf(__fsub_rn(xr, ur));
                                     if (er > rs) ok = false;
+                                }
+                            }
+                            if (ok && A.chi2) {                          // Fuse reprojection gates (:907-931)
+                                const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+                                const float kr = A.u_right != nullptr ? A.u_right[idx] : -1.0f;
+                                const float inv = A.inv_sigma2[kp.octave];
+                                if (kr >= 0) {
+                                    const float er = __fsub_rn(xr, kr);
+                                    const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+                                    if ((double)__fmul_rn(e2, inv) > 7.8) ok = false;
+                                } else {
+                                    const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                                    if ((double)__fmul_rn(e2, inv) > 5.99) ok = false;
                                 }
                             }
                             if (ok) {
@@ -288,13 +301,20 @@ __global__ void __launch_bounds__(256) project_points_kernel(LastArgs L) {
         const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[0], p0), __fmul_rn(L.T[1], p1)), __fmul_rn(L.T[2], p2)), L.T[3]);
         const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[4], p0), __fmul_rn(L.T[5], p1)), __fmul_rn(L.T[6], p2)), L.T[7]);
         const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T[8], p0), __fmul_rn(L.T[9], p1)), __fmul_rn(L.T[10], p2)), L.T[11]);
+        float q0 = xc, q1 = yc, q2 = zc;                                     // the point in the camera the features belong to
+        if (L.variant == 2 && L.chain) {                                      // p3Dc2 = sR21*p3Dc1 + t21 (:1158)
+            q0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T2[0], xc), __fmul_rn(L.T2[1], yc)), __fmul_rn(L.T2[2], zc)), L.T2[3]);
+            q1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T2[4], xc), __fmul_rn(L.T2[5], yc)), __fmul_rn(L.T2[6], zc)), L.T2[7]);
+            q2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T2[8], xc), __fmul_rn(L.T2[9], yc)), __fmul_rn(L.T2[10], zc)), L.T2[11]);
+        }
         if (L.variant == 2) {
-            if (zc < 0.0f) ok = false;                                        // depth must be positive (:329-330)
-            const float invz = __fdiv_rn(1.0f, zc);                           // 1/p3Dc.at<float>(2) (:333)
-            const float x = __fmul_rn(xc, invz), y = __fmul_rn(yc, invz);
+            if (q2 < 0.0f) ok = false;                                        // depth must be positive (:329-330)
+            const float invz = L.invz_double ? (float)(1.0 / (double)q2) : __fdiv_rn(1.0f, q2);   // (:1014,:1164) / (:333,:861)
+            const float x = __fmul_rn(q0, invz), y = __fmul_rn(q1, invz);
             u = __fadd_rn(__fmul_rn(L.fx, x), L.cx);
             v = __fadd_rn(__fmul_rn(L.fy, y), L.cy);
             if (!(u >= L.minX && u < L.maxX && v >= L.minY && v < L.maxY)) ok = false;     // KeyFrame::IsInImage
+            ur = __fsub_rn(u, __fmul_rn(L.bf, invz));                         // (:873)
         } else {
             const float invzc = (float)(1.0 / (double)zc);                   // 1.0/x3Dc.at<float>(2) (:1365, :1503)
             if (L.variant == 0 && invzc < 0) ok = false;                      // (:1367-1368); the keyframe overload has no such test
@@ -313,13 +333,14 @@ __global__ void __launch_bounds__(256) project_points_kernel(LastArgs L) {
             ang = L.last_keys[i].angle;
         } else if (ok) {
             // PO = p3Dw - Ow (float); cv::norm accumulates the squares in double, in index order
-            const float o0 = __fsub_rn(p0, L.Ow[0]), o1 = __fsub_rn(p1, L.Ow[1]), o2 = __fsub_rn(p2, L.Ow[2]);
+            const bool cam = L.variant == 2 && L.chain;                       // SearchBySim3: dist3D = cv::norm(p3Dc2) (:1177)
+            const float o0 = cam ? q0 : __fsub_rn(p0, L.Ow[0]), o1 = cam ? q1 : __fsub_rn(p1, L.Ow[1]), o2 = cam ? q2 : __fsub_rn(p2, L.Ow[2]);
             const double d0 = o0, d1 = o1, d2 = o2;
             const float dist = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2)));
             const float mx = L.max_distance[i];
             const float maxD = __fmul_rn(1.2f, mx), minD = __fmul_rn(0.8f, L.min_distance[i]);
             if (dist < minD || dist > maxD) ok = false;
-            if (ok && L.variant == 2) {                                       // viewing angle below 60 degrees (:354-357)
+            if (ok && L.variant == 2 && L.use_normal) {                       // viewing angle below 60 degrees (:354-357)
                 const float* N = L.normal + 3 * (size_t)i;
                 const double dot = __dadd_rn(__dadd_rn(__dmul_rn(d0, (double)N[0]), __dmul_rn(d1, (double)N[1])), __dmul_rn(d2, (double)N[2]));
                 if (dot < __dmul_rn(0.5, (double)dist)) ok = false;
@@ -402,6 +423,110 @@ __global__ void __launch_bounds__(32) proj_resolve_last_kernel(ProjArgs A, const
         nm -= removed;
     }
     if (lane == 0) *n_matches = nm;
+}
+
+// SearchForInitialization (:405-520): one warp replays F1's level-0 features in order.  A candidate i2 is skipped
+// when an earlier feature already holds it with a distance <= ours (vMatchedDistance, :441-442); a better match
+// displaces the earlier owner (:462-466).  vMatchedDistance / vnMatches21 live in shared memory.
+__global__ void __launch_bounds__(32) init_resolve_kernel(ProjArgs A, const borb_keypoint* __restrict__ keys1, int n1,
+                                                          int32_t* __restrict__ match12, int32_t* __restrict__ ev_idx,
+                                                          uint8_t* __restrict__ ev_bin, float* __restrict__ prev, int* __restrict__ n_matches) {
+    extern __shared__ uint32_t smem_init[];
+    uint16_t* matchedDist = reinterpret_cast<uint16_t*>(smem_init);           // 0xFFFF = INT_MAX
+    uint16_t* owner = matchedDist + ((A.n + 1) & ~1);                          // 0xFFFF = -1
+    __shared__ int hist[32];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < A.n; i += 32) { matchedDist[i] = 0xFFFFu; owner[i] = 0xFFFFu; }
+    for (int i = lane; i < n1; i += 32) match12[i] = -1;
+    hist[lane] = 0;
+    __syncwarp();
+    int nm = 0, nev = 0;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int cnt = A.cand_cnt[i1];
+        if (cnt == 0) continue;
+        const uint32_t* c = A.cand + (size_t)i1 * A.n;
+        unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        for (int p = lane; p < cnt; p += 32) {
+            const uint32_t e = c[p];
+            const unsigned dist = (e >> 16) & 0x1FFu;
+            if ((unsigned)matchedDist[e & 0xFFFF] <= dist) continue;
+            const unsigned key = (dist << 16) | (unsigned)p;
+            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+        }
+        const unsigned best = warp_min(k1);
+        const unsigned second = warp_min(k1 == best ? k2 : k1);
+        if (best != 0xFFFFFFFFu) {
+            const int bestDist = (int)(best >> 16);
+            const float bd2 = second != 0xFFFFFFFFu ? (float)(int)(second >> 16) : 2147483648.f;      // (float)INT_MAX
+            if (bestDist <= TH_LOW && (float)bestDist < __fmul_rn(bd2, A.nnratio)) {
+                const int i2 = (int)(c[best & 0xFFFFu] & 0xFFFF);
+                const int prevOwner = owner[i2];
+                __syncwarp();                                    // every lane has read the owner before lane 0 replaces it
+                if (prevOwner != 0xFFFF) nm--;
+                nm++;
+                if (lane == 0) {
+                    if (prevOwner != 0xFFFF) match12[prevOwner] = -1;
+                    match12[i1] = i2;
+                    owner[i2] = (uint16_t)i1;
+                    matchedDist[i2] = (uint16_t)bestDist;
+                    if (A.check_ori) {
+                        const int b = rot_bin(keys1[i1].angle, A.keys[i2].angle);
+                        ev_idx[nev] = i1; ev_bin[nev] = (uint8_t)b;
+                        hist[b]++;
+                    }
+                }
+                nev++;
+            }
+        }
+        __syncwarp();
+    }
+    if (A.check_ori) {
+        int i1m, i2m, i3m;
+        three_maxima(hist, i1m, i2m, i3m);
+        int removed = 0;
+        for (int e = lane; e < nev; e += 32) {                   // every F1 feature appears at most once in the histogram
+            const int b = ev_bin[e];
+            if (b != i1m && b != i2m && b != i3m && match12[ev_idx[e]] >= 0) { match12[ev_idx[e]] = -1; removed++; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, off);
+        nm -= removed;
+    }
+    __syncwarp();
+    for (int i = lane; i < n1; i += 32) {                        // update vbPrevMatched (:513-517)
+        const int m = match12[i];
+        if (m >= 0) { prev[2 * i] = A.keys[m].x; prev[2 * i + 1] = A.keys[m].y; }
+    }
+    if (lane == 0) *n_matches = nm;
+}
+
+// Order-independent overloads (Fuse x2, the two directions of SearchBySim3): a warp per query point takes the
+// first minimum of its candidate list (dist < bestDist scan == lexicographic min of (distance, list position)).
+__global__ void __launch_bounds__(256) proj_argmin_kernel(ProjArgs A, int32_t* __restrict__ best_idx, int* __restrict__ n_found) {
+    const int lane = threadIdx.x & 31;
+    const int iq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (iq >= A.n_mp) return;
+    const int cnt = A.cand_cnt[iq];
+    const uint32_t* c = A.cand + (size_t)iq * A.n;
+    unsigned k1 = 0xFFFFFFFFu;
+    for (int p = lane; p < cnt; p += 32) k1 = min(k1, (((c[p] >> 16) & 0x1FFu) << 16) | (unsigned)p);
+    const unsigned best = warp_min(k1);
+    if (lane == 0) {
+        int out = -1;
+        if (best != 0xFFFFFFFFu && (int)(best >> 16) <= A.th_dist) { out = (int)(c[best & 0xFFFFu] & 0xFFFF); atomicAdd(n_found, 1); }
+        best_idx[iq] = out;
+    }
+}
+
+// SearchBySim3 agreement (:1302-1323): keep i1 -> idx2 only if the reverse search sent idx2 back to i1
+__global__ void __launch_bounds__(256) sim3_agree_kernel(const int32_t* __restrict__ match1, const int32_t* __restrict__ match2, int n1,
+                                                         int n2, int32_t* __restrict__ match12, int* __restrict__ n_found) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i1 >= n1) return;
+    const int idx2 = match1[i1];
+    int out = -1;
+    if (idx2 >= 0 && idx2 < n2 && match2[idx2] == i1) { out = idx2; atomicAdd(n_found, 1); }
+    match12[i1] = out;
 }
 
 // ------------------------------------------------------------------------------------------------ BoW guided search
@@ -633,6 +758,27 @@ int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_
     const int words = (A.n + 31) / 32;
     proj_resolve_last_kernel<<<1, 32, words * 4, s>>>(A, A.keys, state_cur, ev_idx, ev_bin, n_matches);
     return 3;
+}
+int launch_initialization(const ProjArgs& A, const borb_keypoint* keys1, int n1, int32_t* match12, int32_t* ev_idx, uint8_t* ev_bin,
+                          float* prev, int* n_matches, cudaStream_t s) {
+    proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
+    const size_t smem = (size_t)((A.n + 1) & ~1) * 2 + (size_t)A.n * 2 + 16;
+    init_resolve_kernel<<<1, 32, smem, s>>>(A, keys1, n1, match12, ev_idx, ev_bin, prev, n_matches);
+    return 2;
+}
+int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best_idx, int* n_found, cudaStream_t s) {
+    cudaMemsetAsync(n_found, 0, sizeof(int), s);
+    if (A.n_mp > 0) {
+        project_points_kernel<<<(L.n_last + 255) / 256, 256, 0, s>>>(L);
+        proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
+        proj_argmin_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A, best_idx, n_found);
+    }
+    return 3;
+}
+int launch_sim3_agree(const int32_t* match1, const int32_t* match2, int n1, int n2, int32_t* match12, int* n_found, cudaStream_t s) {
+    cudaMemsetAsync(n_found, 0, sizeof(int), s);
+    if (n1 > 0) sim3_agree_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(match1, match2, n1, n2, match12, n_found);
+    return 1;
 }
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
                      int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s) {

@@ -87,6 +87,7 @@ class FrameView:
     mvuRight: Optional[np.ndarray] = None
     occupied: Optional[np.ndarray] = None                 # mvpMapPoints[i] && Observations()>0 (or != NULL, per overload)
     mfLogScaleFactor: Optional[float] = None              # Frame::mfLogScaleFactor; default logf(mvScaleFactors[1])
+    mvInvLevelSigma2: Optional[np.ndarray] = None         # only read by Fuse(pKF, vpMapPoints, th)
 
 
 @dataclass
@@ -229,12 +230,13 @@ class ORBmatcher:
                                                        _p(state), C.byref(n)), "borb_search_by_projection_last")
         return n.value, state[:len(k)]
 
-    def _points_call(self, F: FrameView, P: WorldPointsView):
+    def _points_call(self, F: FrameView, P: WorldPointsView, with_stereo: bool = False):
         k = np.ascontiguousarray(F.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(F.mDescriptors, np.uint8)
         oc = np.ascontiguousarray(F.occupied, np.uint8) if F.occupied is not None else None
         sf = np.ascontiguousarray(F.mvScaleFactors, np.float32)
-        fv = _FrameViewC(len(k), _p(k), _p(d), None, _p(oc), *[float(x) for x in F.bounds], len(sf), _p(sf))
-        keep = [k, d, oc, sf]
+        ur = np.ascontiguousarray(F.mvuRight, np.float32) if (with_stereo and F.mvuRight is not None) else None
+        fv = _FrameViewC(len(k), _p(k), _p(d), _p(ur), _p(oc), *[float(x) for x in F.bounds], len(sf), _p(sf))
+        keep = [k, d, oc, sf, ur]
         arrs = []
         for a, dt in ((P.world_pos, np.float32), (P.descriptors, np.uint8), (P.max_distance, np.float32), (P.min_distance, np.float32),
                       (P.normal, np.float32), (P.angle, np.float32), (P.valid, np.uint8)):
@@ -270,6 +272,55 @@ class ORBmatcher:
         check(self._lib.borb_search_by_projection_sim3(self._h, C.byref(fv), C.byref(pv), _p(T), _p(ow), float(K[0]), float(K[1]), float(K[2]),
                                                        float(K[3]), logs, int(th), _p(state), C.byref(nm)), "borb_search_by_projection_sim3")
         return nm.value, state[:n]
+
+    def SearchForInitialization(self, F1: FrameView, F2: FrameView, vbPrevMatched: np.ndarray, windowSize: int = 10):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — src/ORBmatcher.cc:405-520.
+        Returns (nmatches, vnMatches12[F1.N], updated vbPrevMatched (N,2))."""
+        views, keep = [], []
+        for F in (F1, F2):
+            k = np.ascontiguousarray(F.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(F.mDescriptors, np.uint8)
+            sf = np.ascontiguousarray(F.mvScaleFactors, np.float32)
+            views.append(_FrameViewC(len(k), _p(k), _p(d), None, None, *[float(x) for x in F.bounds], len(sf), _p(sf)))
+            keep += [k, d, sf]
+        n1 = views[0].n
+        prev = np.ascontiguousarray(np.asarray(vbPrevMatched, np.float32).reshape(-1, 2)).copy()
+        if len(prev) == 0:
+            prev = np.zeros((1, 2), np.float32)
+        m12 = np.full(max(n1, 1), -1, np.int32)
+        nm = C.c_int32(0)
+        check(self._lib.borb_search_for_initialization(self._h, C.byref(views[0]), C.byref(views[1]), _p(prev), int(windowSize), self.mfNNratio,
+                                                       int(self.mbCheckOrientation), _p(m12), C.byref(nm)), "borb_search_for_initialization")
+        return nm.value, m12[:n1], prev[:n1]
+
+    def Fuse(self, pKF: FrameView, P: WorldPointsView, Tcw: np.ndarray, Ow: np.ndarray, K: Tuple[float, float, float, float], bf: float,
+             th: float = 3.0, Scw: bool = False) -> Tuple[int, np.ndarray]:
+        """Search part of Fuse(pKF, vpMapPoints, th) — src/ORBmatcher.cc:825-970 — or, with Scw=True, of
+        Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) — :972-1100.  Returns (n_found, best_idx[len(P)]); the MapPoint
+        bookkeeping (Replace / AddObservation / vpReplacePoint) is the caller's, applied in order."""
+        fv, pv, logs, n, keep = self._points_call(pKF, P, with_stereo=not Scw)
+        inv = np.ascontiguousarray(pKF.mvInvLevelSigma2, np.float32) if pKF.mvInvLevelSigma2 is not None else None
+        T = np.ascontiguousarray(np.asarray(Tcw, np.float32)[:3, :4]).reshape(12)
+        ow = np.ascontiguousarray(np.asarray(Ow, np.float32).reshape(3))
+        nq = len(P.world_pos)
+        best = np.full(max(nq, 1), -1, np.int32)
+        nf = C.c_int32(0)
+        check(self._lib.borb_fuse(self._h, C.byref(fv), _p(inv), C.byref(pv), _p(T), _p(ow), float(K[0]), float(K[1]), float(K[2]), float(K[3]),
+                                  float(bf), logs, float(th), int(Scw), _p(best), C.byref(nf)), "borb_fuse")
+        return nf.value, best[:nq]
+
+    def SearchBySim3(self, pKF1: FrameView, pKF2: FrameView, P1: WorldPointsView, P2: WorldPointsView, T1w: np.ndarray, T2w: np.ndarray,
+                     S12: np.ndarray, S21: np.ndarray, K: Tuple[float, float, float, float], th: float) -> Tuple[int, np.ndarray]:
+        """SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) — src/ORBmatcher.cc:1102-1326.  S12 = [s12*R12 | t12],
+        S21 = [(1/s12)*R12^T | -sR21*t12] (3x4).  Returns (nFound, match12[kf1.N]): index in KF2 or -1."""
+        fv1, pv1, logs1, n1, keep1 = self._points_call(pKF1, P1)
+        fv2, pv2, logs2, n2, keep2 = self._points_call(pKF2, P2)
+        mats = [np.ascontiguousarray(np.asarray(Mx, np.float32)[:3, :4]).reshape(12) for Mx in (T1w, T2w, S12, S21)]
+        match = np.full(max(n1, 1), -1, np.int32)
+        nf = C.c_int32(0)
+        check(self._lib.borb_search_by_sim3(self._h, C.byref(fv1), C.byref(fv2), C.byref(pv1), C.byref(pv2), _p(mats[0]), _p(mats[1]),
+                                            _p(mats[2]), _p(mats[3]), float(K[0]), float(K[1]), float(K[2]), float(K[3]), logs1, logs2,
+                                            float(th), _p(match), C.byref(nf)), "borb_search_by_sim3")
+        return nf.value, match[:n1]
 
     def SearchByBoW(self, pKF, F: KeyFrameView):
         """SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) — src/ORBmatcher.cc:159-288.  pKF may be one KeyFrameView or a

@@ -184,3 +184,65 @@ def test_pose_projection_overloads_edge_cases(M, oracle, views):
                            np.zeros((0, 3), np.float32), np.zeros(0, np.float32))
     n, s = mt.SearchByProjectionSim3(F2, P0, Tcw, Ow, K, 10)
     assert n == 0 and np.all(s == -1)
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("th,scw", [(3.0, False), (6.0, False), (3.0, True), (4.0, True)])
+def test_fuse_search_part(M, oracle, views, seed, th, scw):
+    """Fuse(pKF, vpMapPoints, th) :825-970 and Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) :972-1100 — the search part."""
+    KF, P, Tcw, Ow, K, bf = mf.fuse_case(views[seed], seed + 50)
+    n_o, b_o = oracle.port_fuse(KF, P, Tcw, Ow, K, bf, th, scw)
+    n_g, b_g = M.ORBmatcher(0.6, True).Fuse(KF, P, Tcw, Ow, K, bf, th, Scw=scw)
+    assert n_o > 20 and n_o == int((b_o >= 0).sum())
+    assert n_g == n_o and np.array_equal(b_g, b_o), int((b_g != b_o).sum())
+    assert np.all(b_g[P.valid == 0] == -1)
+
+
+def test_fuse_gates_matter(M, oracle, views):
+    """The stereo / mono reprojection gates (7.8 / 5.99) must bite: with them off (Scw variant) more points are fused."""
+    KF, P, Tcw, Ow, K, bf = mf.fuse_case(views[7], 61, jitter=2.0)
+    n0, b0 = M.ORBmatcher().Fuse(KF, P, Tcw, Ow, K, bf, 6.0, Scw=False)
+    n1, b1 = M.ORBmatcher().Fuse(KF, P, Tcw, Ow, K, bf, 6.0, Scw=True)
+    assert (n0, n1) == (oracle.port_fuse(KF, P, Tcw, Ow, K, bf, 6.0, False)[0], oracle.port_fuse(KF, P, Tcw, Ow, K, bf, 6.0, True)[0])
+    assert n1 > n0 > 10
+    mono = M.FrameView(KF.mvKeysUn, KF.mDescriptors, KF.mvScaleFactors, KF.bounds, mvInvLevelSigma2=KF.mvInvLevelSigma2)
+    n2, b2 = M.ORBmatcher().Fuse(mono, P, Tcw, Ow, K, bf, 6.0)
+    n2o, b2o = oracle.port_fuse(mono, P, Tcw, Ow, K, bf, 6.0, False)
+    assert n2 == n2o and np.array_equal(b2, b2o)
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("th", [7.5, 3.0, 15.0])
+def test_search_by_sim3(M, oracle, views, seed, th):
+    """SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th), src/ORBmatcher.cc:1102-1326."""
+    KF1, KF2, P1, P2, T1w, T2w, S12, S21, K = mf.sim3_case(views[seed], seed + 60)
+    n_o, m_o = oracle.port_search_by_sim3(KF1, KF2, P1, P2, T1w, T2w, S12, S21, K, th)
+    n_g, m_g = M.ORBmatcher(0.75, True).SearchBySim3(KF1, KF2, P1, P2, T1w, T2w, S12, S21, K, th)
+    assert n_o > 20 and n_o == int((m_o >= 0).sum())
+    assert n_g == n_o and np.array_equal(m_g, m_o), int((m_g != m_o).sum())
+    hit = np.nonzero(m_g >= 0)[0]
+    assert np.all(P1.valid[hit] == 1) and np.all(P2.valid[m_g[hit]] == 1)
+    assert len(set(m_g[hit].tolist())) == len(hit)                       # mutual agreement makes the matching one-to-one
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("window,ratio,ori", [(100, 0.9, True), (30, 0.9, True), (100, 0.7, False), (10, 0.9, True)])
+def test_search_for_initialization(M, oracle, views, seed, window, ratio, ori):
+    """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), src/ORBmatcher.cc:405-520."""
+    v = views[seed]
+    b = (0.0, 0.0, float(v["w"]), float(v["h"]))
+    F1 = M.FrameView(v["kl"], v["dl"], v["scale"], b)
+    F2 = M.FrameView(v["kr"], v["dr"], v["scale"], b)
+    prev = np.stack([v["kl"]["x"], v["kl"]["y"]], 1).astype(np.float32)      # mvbPrevMatched = initial keypoint positions
+    n_o, m_o, p_o = oracle.port_search_for_initialization(F1, F2, prev, window, ratio, ori)
+    n_g, m_g, p_g = M.ORBmatcher(ratio, ori).SearchForInitialization(F1, F2, prev, window)
+    assert n_o == int((m_o >= 0).sum()) and (n_o > 20 or window < 30)
+    assert n_g == n_o and np.array_equal(m_g, m_o), int((m_g != m_o).sum())
+    assert np.array_equal(p_g, p_o)
+    hit = np.nonzero(m_g >= 0)[0]
+    assert np.all(v["kl"]["octave"][hit] == 0) and np.all(v["kr"]["octave"][m_g[hit]] == 0)
+    assert len(set(m_g[hit].tolist())) == len(hit)                           # displacement keeps the matching one-to-one
+    # second round with the updated window centres (what the tracker does on the next frame)
+    n_o2, m_o2, p_o2 = oracle.port_search_for_initialization(F1, F2, p_o, max(window // 2, 5), ratio, ori)
+    n_g2, m_g2, p_g2 = M.ORBmatcher(ratio, ori).SearchForInitialization(F1, F2, p_g, max(window // 2, 5))
+    assert n_g2 == n_o2 and np.array_equal(m_g2, m_o2) and np.array_equal(p_g2, p_o2)

@@ -177,3 +177,33 @@ def test_projection_kf_invariants(oracle, views):
     assert len(set(s2[hit].tolist())) == len(hit)                        # a query claims at most one feature
     for j in hit[:100]:
         assert _hamming(P.descriptors[s2[j]], Cur.mDescriptors[j]) <= 100
+
+
+def test_fuse_sim3_initialization_invariants(oracle, views):
+    """Invariants of the restatements of Fuse (search part), SearchBySim3 and SearchForInitialization."""
+    KF, P, Tcw, Ow, K, bf = mf.fuse_case(views, 43)
+    n, best = oracle.port_fuse(KF, P, Tcw, Ow, K, bf, 3.0, False)
+    n_s, best_s = oracle.port_fuse(KF, P, Tcw, Ow, K, bf, 3.0, True)
+    assert n == int((best >= 0).sum()) and n > 50 and n_s >= n              # the Scw overload has no reprojection gates
+    assert np.all(best[P.valid == 0] == -1)
+    for i in np.nonzero(best >= 0)[0][:100]:
+        assert _hamming(P.descriptors[i], KF.mDescriptors[best[i]]) <= 50
+    a = mf.sim3_case(views, 44)
+    n, m12 = oracle.port_search_by_sim3(*a, 7.5)
+    hit = np.nonzero(m12 >= 0)[0]
+    assert n == len(hit) > 50 and len(set(m12[hit].tolist())) == len(hit)
+    # swapping the roles of the two keyframes must return the inverse matching (the agreement test is symmetric)
+    KF1, KF2, P1, P2, T1w, T2w, S12, S21, Kc = a
+    n2, m21 = oracle.port_search_by_sim3(KF2, KF1, P2, P1, T2w, T1w, S21, S12, Kc, 7.5)
+    assert n2 == n and all(m21[m12[i]] == i for i in hit)
+    b = (0.0, 0.0, float(views["w"]), float(views["h"]))
+    from orb_slam2_b200.matcher import FrameView
+    F1, F2 = FrameView(views["kl"], views["dl"], views["scale"], b), FrameView(views["kr"], views["dr"], views["scale"], b)
+    prev = np.stack([views["kl"]["x"], views["kl"]["y"]], 1).astype(np.float32)
+    n, m, p = oracle.port_search_for_initialization(F1, F2, prev, 100, 0.9, True)
+    hit = np.nonzero(m >= 0)[0]
+    assert n == len(hit) > 20 and len(set(m[hit].tolist())) == len(hit)
+    assert np.all(views["kl"]["octave"][hit] == 0)
+    assert np.array_equal(p[hit], np.stack([views["kr"]["x"][m[hit]], views["kr"]["y"][m[hit]]], 1))
+    untouched = np.setdiff1d(np.arange(len(prev)), hit)
+    assert np.array_equal(p[untouched], prev[untouched])

@@ -23,6 +23,12 @@ Cur, Last, Tcw, K = mf.last_frame_case(v, 2)
 print("last", mt.SearchByProjectionLast(Cur, Last, Tcw, K, 40.0, 7.0)[0])
 Fw, Pw, Tw, Ow, Kw = mf.world_points_case(v, 4)
 print("kf/sim3", mt.SearchByProjectionKF(Fw, Pw, Tw, Ow, Kw, 10.0, 100)[0], mt.SearchByProjectionSim3(Fw, Pw, Tw, Ow, Kw, 10)[0])
+KFf, Pf, Tf, Owf, Kf, bff = mf.fuse_case(v, 5)
+print("fuse", mt.Fuse(KFf, Pf, Tf, Owf, Kf, bff, 3.0)[0], mt.Fuse(KFf, Pf, Tf, Owf, Kf, bff, 3.0, Scw=True)[0])
+print("sim3", mt.SearchBySim3(*mf.sim3_case(v, 6), 7.5)[0])
+bb = (0.0, 0.0, float(v["w"]), float(v["h"]))
+print("init", mt.SearchForInitialization(M.FrameView(v["kl"], v["dl"], v["scale"], bb), M.FrameView(v["kr"], v["dr"], v["scale"], bb),
+                                         np.stack([v["kl"]["x"], v["kl"]["y"]], 1), 100)[0])
 pv = O.PortVocabulary.random(10, 3, 5)
 e = pv.export()
 voc = M.ORBVocabulary.from_arrays(e["parent"], e["is_leaf"], e["desc"], e["weight"], e["k"], e["L"])
