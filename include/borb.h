@@ -288,6 +288,13 @@ BORB_API borb_status borb_search_for_initialization(borb_matcher* m, const borb_
                                                     float* prev_matched, int window_size, float nnratio, int check_orientation,
                                                     int32_t* matches12, int32_t* n_matches);
 
+/* MapPoint::ComputeDistinctiveDescriptors — src/MapPoint.cc:242-307, for n_points MapPoints in one launch.
+ * desc: the observing keyframes' descriptors (pKF->mDescriptors.row(idx) of every non-bad observation, in
+ * mObservations order), MapPoint p owning rows offsets[p] .. offsets[p+1]-1.  best_idx[p] = row (relative to
+ * offsets[p]) of the descriptor with the least median distance to the others, -1 if the point has none. */
+BORB_API borb_status borb_distinctive_descriptors(borb_matcher* m, const uint8_t* desc, const int32_t* offsets, int n_points,
+                                                  int32_t* best_idx);
+
 /* DBoW2::FeatureVector (ordered map NodeId -> feature indices) as CSR; node_id ascending. */
 typedef struct borb_featvec_view {
     int32_t n_nodes;
@@ -323,6 +330,35 @@ BORB_API borb_status borb_search_by_bow_kf(borb_matcher* m, const borb_keyframe_
 BORB_API borb_status borb_search_for_triangulation(borb_matcher* m, const borb_keyframe_view* kf1, const borb_keyframe_view* kf2,
                                                    const float* F12, float ex, float ey, int only_stereo, int check_orientation,
                                                    int32_t* pairs, int cap, int32_t* n_pairs);
+
+/* ---- device-resident keyframe database -------------------------------------------------------------------------
+ * KeyFrameDatabase (include/KeyFrameDatabase.h, src/KeyFrameDatabase.cc) re-designed for the GPU: instead of an inverted
+ * file walked per query word, every keyframe's BowVector (and the keyframe-side inputs of SearchByBoW: keypoints,
+ * descriptors, FeatureVector, MapPoint mask) stays in HBM, and one launch computes for ALL keyframes what the walk and
+ * the scoring loop produce: the number of words shared with the query (mnRelocWords / mnLoopWords, :91-108,:211-224) and
+ * DBoW2's L1 score (:127,:240; Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-71), bit-identical (terms added in word
+ * order).  The covisibility accumulation that follows (:134-190,:251-307) walks the keyframe graph and stays with the
+ * caller; first_word gives it the reference's list order (keyframes are met in order of their first shared word,
+ * then of insertion into that word's list). */
+typedef struct borb_kfdb borb_kfdb;
+BORB_API borb_status borb_kfdb_create(int device, borb_kfdb** out);
+BORB_API borb_status borb_kfdb_destroy(borb_kfdb* db);
+BORB_API borb_status borb_kfdb_clear(borb_kfdb* db);                                   /* KeyFrameDatabase::clear :68-73 */
+/* KeyFrameDatabase::add (:41-47).  bow_word ascending (std::map order), bow_value = BowVector weights (double).
+ * *slot_out identifies the keyframe from now on (slots are never reused). */
+BORB_API borb_status borb_kfdb_add(borb_kfdb* db, const borb_keyframe_view* kf, const uint32_t* bow_word, const double* bow_value,
+                                   int n_bow, int32_t* slot_out);
+BORB_API borb_status borb_kfdb_erase(borb_kfdb* db, int32_t slot);                     /* KeyFrameDatabase::erase :49-66 */
+BORB_API borb_status borb_kfdb_set_has_mp(borb_kfdb* db, int32_t slot, const uint8_t* has_mp);   /* MapPoints culled / added since add() */
+BORB_API borb_status borb_kfdb_size(const borb_kfdb* db, int32_t* n_slots, uint64_t* device_bytes);
+/* One query BowVector against every keyframe.  Outputs have one entry per slot (erased slots: 0 common words):
+ * common_words[s], score[s] = (float)L1 score, first_word[s] = smallest shared word id (0xFFFFFFFF if none). */
+BORB_API borb_status borb_kfdb_query(borb_matcher* m, borb_kfdb* db, const uint32_t* bow_word, const double* bow_value, int n_bow,
+                                     int32_t* common_words, float* score, uint32_t* first_word, int cap, int32_t* n_slots);
+/* borb_search_by_bow with the keyframes taken from the database (only the frame is uploaded). */
+BORB_API borb_status borb_search_by_bow_db(borb_matcher* m, borb_kfdb* db, const int32_t* slots, int n_kf,
+                                           const borb_keyframe_view* frame, float nnratio, int check_orientation, int32_t* match,
+                                           int32_t* n_matches);
 
 /* ---------------------------------------------------------------- vocabulary (BoW feeder) ---- */
 /* ORBVocabulary = DBoW2::TemplatedVocabulary<FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h).  The tree lives

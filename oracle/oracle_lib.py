@@ -368,6 +368,47 @@ def port_search_for_initialization(F1, F2, prev_matched, window, nnratio, check_
     return n, m12[:len(k1)], prev
 
 
+def port_distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) for one MapPoint's observation descriptors."""
+    lib = _plib()
+    d = _a(np.asarray(desc, np.uint8).reshape(-1, 32), np.uint8)
+    fn = lib.orbport_distinctive_descriptor
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int]
+    return int(fn(_ptr(d) if len(d) else None, len(d)))
+
+
+def port_bow_score(bow1, bow2):
+    """(L1 score, common words, first common word) of two BowVectors given as {word: value} dicts (ScoringObject.cpp:23-71)."""
+    lib = _plib()
+    w1 = _a(np.fromiter(bow1.keys(), np.uint32, len(bow1)), np.uint32); v1 = _a(np.fromiter(bow1.values(), np.float64, len(bow1)), np.float64)
+    w2 = _a(np.fromiter(bow2.keys(), np.uint32, len(bow2)), np.uint32); v2 = _a(np.fromiter(bow2.values(), np.float64, len(bow2)), np.float64)
+    fn = lib.orbport_bow_score_l1
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    common = C.c_int32(0); first = C.c_uint32(0)
+    s = fn(_ptr(w1) if len(w1) else None, _ptr(v1) if len(v1) else None, len(w1), _ptr(w2) if len(w2) else None,
+           _ptr(v2) if len(v2) else None, len(w2), C.addressof(common), C.addressof(first))
+    return float(s), common.value, first.value
+
+
+def port_detect_reloc_candidates(kf_bows, n_words, q_bow, neigh):
+    """KeyFrameDatabase::DetectRelocalizationCandidates (KeyFrameDatabase.cc:199-310) over keyframes added in list order."""
+    lib = _plib()
+    start = np.zeros(len(kf_bows) + 1, np.int32)
+    start[1:] = np.cumsum([len(b) for b in kf_bows])
+    kw = _a(np.concatenate([np.fromiter(b.keys(), np.uint32, len(b)) for b in kf_bows] + [np.zeros(0, np.uint32)]), np.uint32)
+    kv = _a(np.concatenate([np.fromiter(b.values(), np.float64, len(b)) for b in kf_bows] + [np.zeros(0, np.float64)]), np.float64)
+    qw = _a(np.fromiter(q_bow.keys(), np.uint32, len(q_bow)), np.uint32); qv = _a(np.fromiter(q_bow.values(), np.float64, len(q_bow)), np.float64)
+    ng = _a(np.asarray(neigh, np.int32).reshape(len(kf_bows), 10), np.int32)
+    out = np.zeros(max(len(kf_bows), 1), np.int32)
+    fn = lib.orbport_detect_reloc_candidates
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    n = fn(len(kf_bows), _ptr(start), _ptr(kw), _ptr(kv), int(n_words), _ptr(qw), _ptr(qv), len(qw), _ptr(ng), _ptr(out))
+    return out[:n].copy()
+
+
 def _kf_args(kf):
     k = _a(kf.mvKeysUn, KP_DTYPE); d = _a(kf.mDescriptors, np.uint8)
     hm = _a(kf.has_mp, np.uint8) if kf.has_mp is not None else np.zeros(len(k), np.uint8)

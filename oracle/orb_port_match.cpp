@@ -833,3 +833,113 @@ extern "C" int orbport_search_for_initialization(const orbport_kp* k1, const uin
         if (vnMatches12[i1] >= 0) { prev_matched[2 * i1] = k2[vnMatches12[i1]].x; prev_matched[2 * i1 + 1] = k2[vnMatches12[i1]].y; }
     return nmatches;
 }
+
+// MapPoint::ComputeDistinctiveDescriptors — reference src/MapPoint.cc:242-307: among the N descriptors observing a
+// MapPoint, the one with the least median Hamming distance to the rest (median = sorted row[(int)(0.5*(N-1))], the
+// row including the zero self-distance; first minimum wins).  Returns the index, -1 for N == 0.
+extern "C" int orbport_distinctive_descriptor(const uint8_t* desc, int N) {
+    if (N <= 0) return -1;
+    std::vector<std::vector<float>> Distances(N, std::vector<float>(N, 0.f));
+    for (int i = 0; i < N; i++) {
+        Distances[i][i] = 0;
+        for (int j = i + 1; j < N; j++) {
+            const int distij = orbport_hamming(desc + (size_t)i * 32, desc + (size_t)j * 32);
+            Distances[i][j] = (float)distij;
+            Distances[j][i] = (float)distij;
+        }
+    }
+    int BestMedian = INT32_MAX, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        std::vector<int> vDists(Distances[i].begin(), Distances[i].end());
+        std::sort(vDists.begin(), vDists.end());
+        const int median = vDists[(size_t)(0.5 * (N - 1))];
+        if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    return BestIdx;
+}
+
+// DBoW2::L1Scoring::score — reference Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-71 — on two BowVectors given as
+// ascending (word, value) arrays, and the common-word count KeyFrameDatabase::DetectRelocalizationCandidates /
+// DetectLoopCandidates accumulate through the inverted file (src/KeyFrameDatabase.cc:211-224, :91-108).
+extern "C" double orbport_bow_score_l1(const uint32_t* w1, const double* v1, int n1, const uint32_t* w2, const double* v2, int n2,
+                                       int32_t* common_words, uint32_t* first_common_word) {
+    double score = 0;
+    int i = 0, j = 0, common = 0;
+    uint32_t first = 0xFFFFFFFFu;
+    while (i < n1 && j < n2) {
+        if (w1[i] == w2[j]) {
+            const double vi = v1[i], wi = v2[j];
+            score += std::fabs(vi - wi) - std::fabs(vi) - std::fabs(wi);
+            if (!common) first = w1[i];
+            common++; ++i; ++j;
+        } else if (w1[i] < w2[j]) {
+            i = (int)(std::lower_bound(w1 + i, w1 + n1, w2[j]) - w1);
+        } else {
+            j = (int)(std::lower_bound(w2 + j, w2 + n2, w1[i]) - w2);
+        }
+    }
+    if (common_words) *common_words = common;
+    if (first_common_word) *first_common_word = first;
+    return -score / 2.0;
+}
+
+// KeyFrameDatabase::add (src/KeyFrameDatabase.cc:41-47) + DetectRelocalizationCandidates (:199-310), restated with a real
+// inverted file.  Keyframes 0..n_kf-1 are added in index order; kf_start/kf_word/kf_value = their BowVectors (CSR,
+// ascending words); neigh = GetBestCovisibilityKeyFrames(10) per keyframe as n_kf x 10 indices (-1 padded).
+// Returns the number of candidates written to out (keyframe indices, in the reference's output order).
+extern "C" int orbport_detect_reloc_candidates(int n_kf, const int32_t* kf_start, const uint32_t* kf_word, const double* kf_value,
+                                               int n_words, const uint32_t* q_word, const double* q_value, int nq,
+                                               const int32_t* neigh, int32_t* out) {
+    std::vector<std::vector<int>> mvInvertedFile(n_words);
+    for (int k = 0; k < n_kf; k++)
+        for (int e = kf_start[k]; e < kf_start[k + 1]; e++) mvInvertedFile[kf_word[e]].push_back(k);
+    std::vector<int> mnRelocWords(n_kf, 0);
+    std::vector<char> queried(n_kf, 0);          // pKFi->mnRelocQuery == F->mnId
+    std::vector<float> mRelocScore(n_kf, 0.f);
+    std::vector<int> lKFsSharingWords;
+    for (int i = 0; i < nq; i++) {
+        if (q_word[i] >= (uint32_t)n_words) continue;
+        for (int pKFi : mvInvertedFile[q_word[i]]) {
+            if (!queried[pKFi]) { mnRelocWords[pKFi] = 0; queried[pKFi] = 1; lKFsSharingWords.push_back(pKFi); }
+            mnRelocWords[pKFi]++;
+        }
+    }
+    if (lKFsSharingWords.empty()) return 0;
+    int maxCommonWords = 0;
+    for (int k : lKFsSharingWords) if (mnRelocWords[k] > maxCommonWords) maxCommonWords = mnRelocWords[k];
+    const int minCommonWords = maxCommonWords * 0.8f;
+    std::vector<std::pair<float, int>> lScoreAndMatch;
+    for (int k : lKFsSharingWords) {
+        if (mnRelocWords[k] > minCommonWords) {
+            const int s0 = kf_start[k], n2 = kf_start[k + 1] - s0;
+            const float si = (float)orbport_bow_score_l1(q_word, q_value, nq, kf_word + s0, kf_value + s0, n2, nullptr, nullptr);
+            mRelocScore[k] = si;
+            lScoreAndMatch.push_back({si, k});
+        }
+    }
+    if (lScoreAndMatch.empty()) return 0;
+    std::vector<std::pair<float, int>> lAccScoreAndMatch;
+    float bestAccScore = 0;
+    for (auto& it : lScoreAndMatch) {
+        const int pKFi = it.second;
+        float bestScore = it.first;
+        float accScore = bestScore;
+        int pBestKF = pKFi;
+        for (int j = 0; j < 10; j++) {
+            const int pKF2 = neigh[(size_t)pKFi * 10 + j];
+            if (pKF2 < 0) break;
+            if (!queried[pKF2]) continue;
+            accScore += mRelocScore[pKF2];
+            if (mRelocScore[pKF2] > bestScore) { pBestKF = pKF2; bestScore = mRelocScore[pKF2]; }
+        }
+        lAccScoreAndMatch.push_back({accScore, pBestKF});
+        if (accScore > bestAccScore) bestAccScore = accScore;
+    }
+    const float minScoreToRetain = 0.75f * bestAccScore;
+    std::vector<char> added(n_kf, 0);
+    int n_out = 0;
+    for (auto& it : lAccScoreAndMatch) {
+        if (it.first > minScoreToRetain && !added[it.second]) { out[n_out++] = it.second; added[it.second] = 1; }
+    }
+    return n_out;
+}

@@ -78,6 +78,16 @@ _SIGNATURES = {
     "borb_search_by_projection_sim3": (C.c_int, [vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                                  vp, i32p]),
     "borb_search_for_initialization": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, i32p]),
+    "borb_distinctive_descriptors": (C.c_int, [vp, vp, vp, C.c_int, vp]),
+    "borb_kfdb_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "borb_kfdb_destroy": (C.c_int, [vp]),
+    "borb_kfdb_clear": (C.c_int, [vp]),
+    "borb_kfdb_add": (C.c_int, [vp, vp, vp, vp, C.c_int, i32p]),
+    "borb_kfdb_erase": (C.c_int, [vp, C.c_int32]),
+    "borb_kfdb_set_has_mp": (C.c_int, [vp, C.c_int32, vp]),
+    "borb_kfdb_size": (C.c_int, [vp, i32p, C.POINTER(C.c_uint64)]),
+    "borb_kfdb_query": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, i32p]),
+    "borb_search_by_bow_db": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_float, C.c_int, vp, vp]),
     "borb_fuse": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                             vp, i32p]),
     "borb_search_by_sim3": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

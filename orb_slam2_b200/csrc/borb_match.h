@@ -81,6 +81,12 @@ struct KfDev {                    // device-side borb_keyframe_view
     const float* level_sigma2;
 };
 
+struct BowDev {                   // one keyframe's BowVector in the device-resident database (null / 0 when erased)
+    const uint32_t* word;         // ascending
+    const double* value;
+    int n;
+};
+
 struct TriArgs { float F[9]; float ex, ey; int only_stereo, check_ori; };
 
 struct VocDev {                   // views into the packed blob
@@ -99,6 +105,9 @@ int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_
                            cudaStream_t s);
 int launch_initialization(const ProjArgs& A, const borb_keypoint* keys1, int n1, int32_t* match12, int32_t* ev_idx, uint8_t* ev_bin,
                           float* prev, int* n_matches, cudaStream_t s);
+int launch_kfdb_score(const BowDev* table, int n_slots, const uint32_t* qword, const double* qvalue, int nq, int32_t* common, float* score,
+                      uint32_t* first_word, cudaStream_t s);
+int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx, cudaStream_t s);
 int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best_idx, int* n_found, cudaStream_t s);
 int launch_sim3_agree(const int32_t* match1, const int32_t* match2, int n1, int n2, int32_t* match12, int* n_found, cudaStream_t s);
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,

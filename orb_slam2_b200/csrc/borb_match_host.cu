@@ -526,6 +526,31 @@ borb_status borb_search_for_initialization(borb_matcher* m, const borb_frame_vie
     return BORB_OK;
 }
 
+borb_status borb_distinctive_descriptors(borb_matcher* m, const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx) {
+    if (!m || !offsets || !best_idx || n_points < 0) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (n_points == 0) return BORB_OK;
+    const int total_desc = offsets[n_points];
+    for (int i = 0; i < n_points; i++)
+        if (offsets[i + 1] < offsets[i] || offsets[i] < 0 || offsets[i + 1] - offsets[i] >= (1 << 16)) { set_error("offsets must ascend; at most 65535 observations per MapPoint"); return BORB_ERR_INVALID_ARG; }
+    if (total_desc > 0 && !desc) { set_error("null descriptors"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(m->device));
+    Stager st(m);
+    const size_t o_d = st.add(desc, (size_t)total_desc * 32);
+    const size_t o_o = st.add(offsets, (size_t)(n_points + 1) * 4);
+    const size_t input_end = st.off;
+    const size_t o_b = st.reserve((size_t)n_points * 4);
+    const size_t total = st.off;
+    st.off = input_end;
+    borb_status s = commit(st, total);
+    if (s != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    m->launches += launch_distinctive(b + o_d, (const int32_t*)(b + o_o), n_points, (int32_t*)(b + o_b), m->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaMemcpyAsync(best_idx, b + o_b, (size_t)n_points * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    return BORB_OK;
+}
+
 static borb_status bow_common(borb_matcher* m, const borb_keyframe_view* qs, int n_q, const borb_keyframe_view* t, int mode, float nnratio,
                               int check_ori, int32_t* match, int32_t* n_matches) {
     // mode 0: qs[0..n_q) keyframes vs ONE frame t, out stride t->n.   mode 1: n_q == 1, q = kf1, t = kf2, out stride q->n.
@@ -578,6 +603,209 @@ borb_status borb_search_by_bow_kf(borb_matcher* m, const borb_keyframe_view* kf1
     if (s == BORB_OK) s = check_kf(kf2, "borb_search_by_bow_kf(kf2)");
     if (s != BORB_OK) return s;
     return bow_common(m, kf1, 1, kf2, 1, nnratio, check_orientation, match12, n_matches);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident keyframe database: KeyFrameDatabase (src/KeyFrameDatabase.cc) + the keyframe-side inputs of SearchByBoW.
+struct borb_kfdb {
+    int device = 0;
+    struct Entry { uint8_t* block = nullptr; KfDev dev{}; BowDev bow{nullptr, nullptr, 0}; uint8_t* has_mp = nullptr; bool alive = false; };
+    std::vector<Entry> entries;
+    BowDev* d_table = nullptr;      // mirrors entries[*].bow
+    size_t table_cap = 0;
+    bool dirty = true;
+    size_t bytes = 0;
+};
+
+borb_status borb_kfdb_create(int device, borb_kfdb** out) {
+    if (!out) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { set_error("no CUDA device: the keyframe database is GPU-resident"); return BORB_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) { set_error("device %d out of range", device); return BORB_ERR_INVALID_ARG; }
+    borb_kfdb* db = new borb_kfdb();
+    db->device = device;
+    *out = db;
+    return BORB_OK;
+}
+
+borb_status borb_kfdb_clear(borb_kfdb* db) {
+    if (!db) return BORB_OK;
+    cudaSetDevice(db->device);
+    cudaDeviceSynchronize();
+    for (auto& e : db->entries) cudaFree(e.block);
+    db->entries.clear();
+    db->dirty = true;
+    db->bytes = 0;
+    return BORB_OK;
+}
+
+borb_status borb_kfdb_destroy(borb_kfdb* db) {
+    if (!db) return BORB_OK;
+    borb_kfdb_clear(db);
+    cudaFree(db->d_table);
+    delete db;
+    return BORB_OK;
+}
+
+borb_status borb_kfdb_add(borb_kfdb* db, const borb_keyframe_view* kf, const uint32_t* bow_word, const double* bow_value, int n_bow,
+                          int32_t* slot_out) {
+    if (!db || !kf || !slot_out || n_bow < 0 || (n_bow > 0 && (!bow_word || !bow_value))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    borb_status s = check_kf(kf, "borb_kfdb_add");
+    if (s != BORB_OK) return s;
+    for (int i = 1; i < n_bow; i++)
+        if (bow_word[i] <= bow_word[i - 1]) { set_error("BowVector words must ascend (std::map order)"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(db->device));
+    // one device block per keyframe: [keys | desc | has_mp | u_right | node | start | idx | bow words | bow values]
+    size_t off = 0;
+    auto put = [&](size_t bytes) { off = (off + 255) & ~size_t(255); const size_t o = off; off += bytes; return o; };
+    const int total_idx = kf->fv.n_nodes > 0 ? kf->fv.start[kf->fv.n_nodes] : 0;
+    const size_t o_keys = put((size_t)kf->n * sizeof(borb_keypoint)), o_desc = put((size_t)kf->n * 32), o_hm = put((size_t)kf->n);
+    const size_t o_ur = put(kf->u_right ? (size_t)kf->n * 4 : 0);
+    const size_t o_node = put((size_t)kf->fv.n_nodes * 4), o_start = put((size_t)(kf->fv.n_nodes + 1) * 4), o_idx = put((size_t)total_idx * 4);
+    const size_t o_bw = put((size_t)n_bow * 4), o_bv = put((size_t)n_bow * 8);
+    const size_t total = off + 256;
+    std::vector<uint8_t> h(total, 0);
+    if (kf->n) {
+        std::memcpy(&h[o_keys], kf->keys_un, (size_t)kf->n * sizeof(borb_keypoint));
+        std::memcpy(&h[o_desc], kf->desc, (size_t)kf->n * 32);
+        if (kf->has_mp) std::memcpy(&h[o_hm], kf->has_mp, (size_t)kf->n);
+        if (kf->u_right) std::memcpy(&h[o_ur], kf->u_right, (size_t)kf->n * 4);
+    }
+    if (kf->fv.n_nodes) {
+        std::memcpy(&h[o_node], kf->fv.node_id, (size_t)kf->fv.n_nodes * 4);
+        std::memcpy(&h[o_start], kf->fv.start, (size_t)(kf->fv.n_nodes + 1) * 4);
+        std::memcpy(&h[o_idx], kf->fv.feat_idx, (size_t)total_idx * 4);
+    }
+    if (n_bow) { std::memcpy(&h[o_bw], bow_word, (size_t)n_bow * 4); std::memcpy(&h[o_bv], bow_value, (size_t)n_bow * 8); }
+    borb_kfdb::Entry e;
+    BORB_CUDA(cudaMalloc(&e.block, total));
+    BORB_CUDA(cudaMemcpy(e.block, h.data(), total, cudaMemcpyHostToDevice));
+    uint8_t* b = e.block;
+    e.dev.n = kf->n; e.dev.nn = kf->fv.n_nodes;
+    e.dev.keys = (const borb_keypoint*)(b + o_keys); e.dev.desc = b + o_desc; e.dev.has_mp = b + o_hm;
+    e.dev.u_right = kf->u_right ? (const float*)(b + o_ur) : nullptr;
+    e.dev.node = (const uint32_t*)(b + o_node); e.dev.start = (const int32_t*)(b + o_start); e.dev.idx = (const uint32_t*)(b + o_idx);
+    e.dev.scale_factors = nullptr; e.dev.level_sigma2 = nullptr;
+    e.has_mp = b + o_hm;
+    e.bow.word = (const uint32_t*)(b + o_bw); e.bow.value = (const double*)(b + o_bv); e.bow.n = n_bow;
+    e.alive = true;
+    db->entries.push_back(e);
+    db->dirty = true;
+    db->bytes += total;
+    *slot_out = (int32_t)db->entries.size() - 1;
+    return BORB_OK;
+}
+
+borb_status borb_kfdb_erase(borb_kfdb* db, int32_t slot) {
+    if (!db || slot < 0 || slot >= (int)db->entries.size() || !db->entries[slot].alive) { set_error("bad keyframe slot"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(db->device));
+    BORB_CUDA(cudaDeviceSynchronize());
+    borb_kfdb::Entry& e = db->entries[slot];
+    cudaFree(e.block);
+    e = borb_kfdb::Entry();
+    db->dirty = true;
+    return BORB_OK;
+}
+
+borb_status borb_kfdb_set_has_mp(borb_kfdb* db, int32_t slot, const uint8_t* has_mp) {
+    if (!db || !has_mp || slot < 0 || slot >= (int)db->entries.size() || !db->entries[slot].alive) { set_error("bad keyframe slot"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(db->device));
+    BORB_CUDA(cudaMemcpy(db->entries[slot].has_mp, has_mp, (size_t)db->entries[slot].dev.n, cudaMemcpyHostToDevice));
+    return BORB_OK;
+}
+
+borb_status borb_kfdb_size(const borb_kfdb* db, int32_t* n_slots, uint64_t* device_bytes) {
+    if (!db) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (n_slots) *n_slots = (int32_t)db->entries.size();
+    if (device_bytes) *device_bytes = db->bytes;
+    return BORB_OK;
+}
+
+static borb_status kfdb_sync_table(borb_kfdb* db, cudaStream_t stream) {
+    if (!db->dirty) return BORB_OK;
+    const size_t n = db->entries.size();
+    if (n > db->table_cap) {
+        BORB_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(db->d_table); db->d_table = nullptr;
+        db->table_cap = n + n / 2 + 64;
+        BORB_CUDA(cudaMalloc(&db->d_table, db->table_cap * sizeof(BowDev)));
+    }
+    std::vector<BowDev> t(n);
+    for (size_t i = 0; i < n; i++) t[i] = db->entries[i].alive ? db->entries[i].bow : BowDev{nullptr, nullptr, 0};
+    if (n) BORB_CUDA(cudaMemcpy(db->d_table, t.data(), n * sizeof(BowDev), cudaMemcpyHostToDevice));
+    db->dirty = false;
+    return BORB_OK;
+}
+
+borb_status borb_kfdb_query(borb_matcher* m, borb_kfdb* db, const uint32_t* bow_word, const double* bow_value, int n_bow,
+                            int32_t* common_words, float* score, uint32_t* first_word, int cap, int32_t* n_slots) {
+    if (!m || !db || !common_words || !score || !first_word || !n_slots || n_bow < 0 || (n_bow > 0 && (!bow_word || !bow_value))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (m->device != db->device) { set_error("matcher and keyframe database live on different devices"); return BORB_ERR_INVALID_ARG; }
+    const int n = (int)db->entries.size();
+    *n_slots = n;
+    if (cap < n) { set_error("output capacity %d < %d database slots", cap, n); return BORB_ERR_CAPACITY; }
+    if (n == 0) return BORB_OK;
+    for (int i = 1; i < n_bow; i++)
+        if (bow_word[i] <= bow_word[i - 1]) { set_error("BowVector words must ascend (std::map order)"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(m->device));
+    borb_status s = kfdb_sync_table(db, m->stream);
+    if (s != BORB_OK) return s;
+    Stager st(m);
+    const size_t o_w = st.add(bow_word, (size_t)n_bow * 4), o_v = st.add(bow_value, (size_t)n_bow * 8);
+    const size_t input_end = st.off;
+    const size_t o_c = st.reserve((size_t)n * 4), o_s = st.reserve((size_t)n * 4), o_f = st.reserve((size_t)n * 4);
+    const size_t total = st.off;
+    st.off = input_end;
+    if ((s = commit(st, total)) != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    m->launches += launch_kfdb_score(db->d_table, n, (const uint32_t*)(b + o_w), (const double*)(b + o_v), n_bow, (int32_t*)(b + o_c),
+                                     (float*)(b + o_s), (uint32_t*)(b + o_f), m->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaMemcpyAsync(common_words, b + o_c, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(score, b + o_s, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(first_word, b + o_f, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    return BORB_OK;
+}
+
+borb_status borb_search_by_bow_db(borb_matcher* m, borb_kfdb* db, const int32_t* slots, int n_kf, const borb_keyframe_view* frame,
+                                  float nnratio, int check_orientation, int32_t* match, int32_t* n_matches) {
+    if (!m || !db || !frame || !match || !n_matches || n_kf < 0 || (n_kf > 0 && !slots)) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (m->device != db->device) { set_error("matcher and keyframe database live on different devices"); return BORB_ERR_INVALID_ARG; }
+    borb_status s = check_kf(frame, "borb_search_by_bow_db(frame)");
+    if (s != BORB_OK) return s;
+    if (n_kf == 0) return BORB_OK;
+    std::vector<KfDev> qd(n_kf);
+    for (int i = 0; i < n_kf; i++) {
+        if (slots[i] < 0 || slots[i] >= (int)db->entries.size() || !db->entries[slots[i]].alive) { set_error("slot %d is not a live keyframe", slots[i]); return BORB_ERR_INVALID_ARG; }
+        qd[i] = db->entries[slots[i]].dev;
+    }
+    BORB_CUDA(cudaSetDevice(m->device));
+    // only the frame and the table of keyframe descriptors-of-descriptors travel; the keyframes are resident
+    Stager st(m);
+    const KfOffsets to = stage_kf(st, frame);
+    const size_t o_qd = st.reserve((size_t)n_kf * sizeof(KfDev)), o_td = st.reserve(sizeof(KfDev));
+    const size_t input_end = st.off;
+    const int out_stride = frame->n;
+    const size_t o_match = st.reserve((size_t)n_kf * (out_stride > 0 ? out_stride : 1) * 4);
+    const size_t o_bins = st.reserve((size_t)n_kf * (out_stride > 0 ? out_stride : 1));
+    const size_t o_nm = st.reserve((size_t)n_kf * 4);
+    const size_t total = st.off;
+    st.off = input_end;
+    if ((s = ensure_arena(m, total)) != BORB_OK) return s;
+    const KfDev td = kf_dev(m, frame, to);
+    st.items.push_back({qd.data(), {o_qd, (size_t)n_kf * sizeof(KfDev)}});
+    st.items.push_back({&td, {o_td, sizeof(KfDev)}});
+    if ((s = commit(st, total)) != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    m->launches += launch_bow_match((const KfDev*)(b + o_qd), (const KfDev*)(b + o_td), n_kf, 0, nnratio, check_orientation,
+                                    (int32_t*)(b + o_match), out_stride, b + o_bins, (int32_t*)(b + o_nm), frame->n, m->stream);
+    BORB_CUDA(cudaGetLastError());
+    if (out_stride > 0) BORB_CUDA(cudaMemcpyAsync(match, b + o_match, (size_t)n_kf * out_stride * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, (size_t)n_kf * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    return BORB_OK;
 }
 
 borb_status borb_search_for_triangulation(borb_matcher* m, const borb_keyframe_view* kf1, const borb_keyframe_view* kf2, const float* F12,

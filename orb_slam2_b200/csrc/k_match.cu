@@ -529,6 +529,94 @@ __global__ void __launch_bounds__(256) sim3_agree_kernel(const int32_t* __restri
     match12[i1] = out;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307), batched: a warp per MapPoint, a lane per row of the
+// distance matrix.  The row median (sorted row[(int)(0.5*(N-1))], self-distance included) comes from a 257-bin counting
+// histogram kept in local memory; first minimal median wins (lowest row index).
+__global__ void __launch_bounds__(128) distinctive_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ offsets,
+                                                          int n_points, int32_t* __restrict__ best_idx) {
+    const int lane = threadIdx.x & 31;
+    const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= n_points) return;
+    const int o0 = offsets[pt], N = offsets[pt + 1] - o0;
+    if (N <= 0) { if (lane == 0) best_idx[pt] = -1; return; }
+    const uint32_t* D = reinterpret_cast<const uint32_t*>(desc) + (size_t)o0 * 8;
+    const int k = (int)(0.5 * (double)(N - 1));
+    unsigned bestKey = 0xFFFFFFFFu;                              // median << 20 | row
+    for (int i = lane; i < N; i += 32) {
+        uint16_t hist[257];
+#pragma unroll 1
+        for (int b = 0; b < 257; b++) hist[b] = 0;
+        uint32_t a[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) a[w] = D[(size_t)i * 8 + w];
+#pragma unroll 1
+        for (int j = 0; j < N; j++) {
+            int d = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) d += __popc(a[w] ^ D[(size_t)j * 8 + w]);
+            hist[d]++;
+        }
+        int cum = 0, median = 256;
+#pragma unroll 1
+        for (int b = 0; b < 257; b++) {
+            cum += hist[b];
+            if (cum > k) { median = b; break; }
+        }
+        bestKey = min(bestKey, ((unsigned)median << 20) | (unsigned)i);
+    }
+    bestKey = warp_min(bestKey);
+    if (lane == 0) best_idx[pt] = (int)(bestKey & 0xFFFFFu);
+}
+
+// KeyFrameDatabase query (src/KeyFrameDatabase.cc:76-197, 199-310): for every keyframe of the device-resident database,
+// the number of words it shares with the query BowVector (what the inverted-file walk counts, :211-224) and
+// DBoW2::L1Scoring::score (ScoringObject.cpp:23-71).  A warp per keyframe: lanes take 32 consecutive keyframe words,
+// binary-search them in the query, and the matching terms are added in ascending word order (double, the order of the
+// reference's merge loop) so that the score is bit-identical.
+__global__ void __launch_bounds__(256) kfdb_score_kernel(const BowDev* __restrict__ table, int n_slots, const uint32_t* __restrict__ qword,
+                                                         const double* __restrict__ qvalue, int nq, int32_t* __restrict__ common,
+                                                         float* __restrict__ score, uint32_t* __restrict__ first_word) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= n_slots) return;
+    const BowDev kf = table[slot];
+    double acc = 0.0;
+    int ncommon = 0;
+    uint32_t first = 0xFFFFFFFFu;
+    for (int base = 0; base < kf.n; base += 32) {
+        const int i = base + lane;
+        bool found = false;
+        double term = 0.0;
+        uint32_t w = 0;
+        if (i < kf.n) {
+            w = kf.word[i];
+            int lo = 0, hi = nq;                                  // lower_bound of w in the query words
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (qword[mid] < w) lo = mid + 1; else hi = mid;
+            }
+            if (lo < nq && qword[lo] == w) {
+                found = true;
+                const double vi = qvalue[lo], wi = kf.value[i];   // v1 = query (F->mBowVec), v2 = keyframe
+                term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
+            }
+        }
+        unsigned bal = __ballot_sync(0xFFFFFFFFu, found);
+        if (bal && first == 0xFFFFFFFFu) first = __shfl_sync(0xFFFFFFFFu, w, __ffs(bal) - 1);
+        ncommon += __popc(bal);
+        while (bal) {                                             // ordered accumulation: ascending word id
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            acc = __dadd_rn(acc, __shfl_sync(0xFFFFFFFFu, term, src));
+        }
+    }
+    if (lane == 0) {
+        common[slot] = ncommon;
+        score[slot] = (float)(-acc / 2.0);                        // float si = mpVoc->score(...) (:240)
+        first_word[slot] = first;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ BoW guided search
 // mode 0: SearchByBoW(KeyFrame*, Frame&)   — q = keyframe (needs has_mp), t = frame;   out match[t.n]  = q index
 // mode 1: SearchByBoW(KeyFrame*, KeyFrame*) — q = kf1, t = kf2 (both need has_mp);      out match[q.n]  = t index
@@ -765,6 +853,15 @@ int launch_initialization(const ProjArgs& A, const borb_keypoint* keys1, int n1,
     const size_t smem = (size_t)((A.n + 1) & ~1) * 2 + (size_t)A.n * 2 + 16;
     init_resolve_kernel<<<1, 32, smem, s>>>(A, keys1, n1, match12, ev_idx, ev_bin, prev, n_matches);
     return 2;
+}
+int launch_kfdb_score(const BowDev* table, int n_slots, const uint32_t* qword, const double* qvalue, int nq, int32_t* common, float* score,
+                      uint32_t* first_word, cudaStream_t s) {
+    if (n_slots > 0) kfdb_score_kernel<<<(n_slots + 7) / 8, 256, 0, s>>>(table, n_slots, qword, qvalue, nq, common, score, first_word);
+    return 1;
+}
+int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx, cudaStream_t s) {
+    if (n_points > 0) distinctive_kernel<<<(n_points + 3) / 4, 128, 0, s>>>(desc, offsets, n_points, best_idx);
+    return 1;
 }
 int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best_idx, int* n_found, cudaStream_t s) {
     cudaMemsetAsync(n_found, 0, sizeof(int), s);

@@ -292,6 +292,17 @@ class ORBmatcher:
                                                        int(self.mbCheckOrientation), _p(m12), C.byref(nm)), "borb_search_for_initialization")
         return nm.value, m12[:n1], prev[:n1]
 
+    def ComputeDistinctiveDescriptors(self, groups) -> np.ndarray:
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307) for a batch of MapPoints: groups[p] = (N_p,32)
+        uint8 descriptors of the point's observations.  Returns best[p] = index of the medoid-by-median descriptor (-1 if empty)."""
+        groups = [np.ascontiguousarray(g, np.uint8).reshape(-1, 32) for g in groups]
+        off = np.zeros(len(groups) + 1, np.int32)
+        off[1:] = np.cumsum([len(g) for g in groups])
+        desc = np.ascontiguousarray(np.concatenate(groups, 0)) if len(groups) and off[-1] > 0 else np.zeros((1, 32), np.uint8)
+        best = np.full(max(len(groups), 1), -1, np.int32)
+        check(self._lib.borb_distinctive_descriptors(self._h, _p(desc), _p(off), len(groups), _p(best)), "borb_distinctive_descriptors")
+        return best[:len(groups)]
+
     def Fuse(self, pKF: FrameView, P: WorldPointsView, Tcw: np.ndarray, Ow: np.ndarray, K: Tuple[float, float, float, float], bf: float,
              th: float = 3.0, Scw: bool = False) -> Tuple[int, np.ndarray]:
         """Search part of Fuse(pKF, vpMapPoints, th) — src/ORBmatcher.cc:825-970 — or, with Scw=True, of
@@ -360,6 +371,113 @@ class ORBmatcher:
                                                       int(bOnlyStereo), int(self.mbCheckOrientation), _p(pairs), cap, C.byref(n)),
               "borb_search_for_triangulation")
         return pairs[:n.value]
+
+
+class KeyFrameDatabase:
+    """KeyFrameDatabase (include/KeyFrameDatabase.h) with the keyframes resident in HBM.  add/erase/clear mirror
+    src/KeyFrameDatabase.cc:41-73; query() is the data-parallel part of DetectLoopCandidates / DetectRelocalizationCandidates
+    (shared-word count + L1 score for every keyframe in one launch); DetectRelocalizationCandidates() finishes the
+    reference's procedure on the host from those arrays and the caller's covisibility lists."""
+
+    def __init__(self, matcher: "ORBmatcher", device: int = 0):
+        self._lib = _lib.load()
+        self._m = matcher
+        h = C.c_void_p()
+        check(self._lib.borb_kfdb_create(device, C.byref(h)), "borb_kfdb_create")
+        self._h = h
+        self._seq = []                  # insertion sequence number per slot (inverted-file list order)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.borb_kfdb_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def _bow_arrays(bow):
+        w = np.fromiter(bow.keys(), np.uint32, len(bow)); v = np.fromiter(bow.values(), np.float64, len(bow))
+        o = np.argsort(w, kind="stable")
+        return np.ascontiguousarray(w[o]), np.ascontiguousarray(v[o])
+
+    def add(self, pKF: KeyFrameView, mBowVec: Dict[int, float]) -> int:
+        w, v = self._bow_arrays(mBowVec)
+        slot = C.c_int32(-1)
+        kc = pKF._c()
+        check(self._lib.borb_kfdb_add(self._h, C.byref(kc), _p(w), _p(v), len(w), C.byref(slot)), "borb_kfdb_add")
+        self._seq.append(len(self._seq))
+        return slot.value
+
+    def erase(self, slot: int) -> None:
+        check(self._lib.borb_kfdb_erase(self._h, int(slot)), "borb_kfdb_erase")
+
+    def clear(self) -> None:
+        check(self._lib.borb_kfdb_clear(self._h), "borb_kfdb_clear")
+        self._seq = []
+
+    def set_has_mp(self, slot: int, has_mp: np.ndarray) -> None:
+        hm = np.ascontiguousarray(has_mp, np.uint8)
+        check(self._lib.borb_kfdb_set_has_mp(self._h, int(slot), _p(hm)), "borb_kfdb_set_has_mp")
+
+    def size(self) -> Tuple[int, int]:
+        n = C.c_int32(0); b = C.c_uint64(0)
+        check(self._lib.borb_kfdb_size(self._h, C.byref(n), C.byref(b)), "borb_kfdb_size")
+        return n.value, b.value
+
+    def query(self, mBowVec: Dict[int, float]):
+        """Returns (common_words[int32], score[float32], first_word[uint32]) with one entry per slot."""
+        w, v = self._bow_arrays(mBowVec)
+        n = self.size()[0]
+        cw = np.zeros(max(n, 1), np.int32); sc = np.zeros(max(n, 1), np.float32); fw = np.zeros(max(n, 1), np.uint32)
+        ns = C.c_int32(0)
+        check(self._lib.borb_kfdb_query(self._m._h, self._h, _p(w), _p(v), len(w), _p(cw), _p(sc), _p(fw), len(cw), C.byref(ns)),
+              "borb_kfdb_query")
+        return cw[:n], sc[:n], fw[:n]
+
+    def DetectRelocalizationCandidates(self, mBowVec: Dict[int, float], covisibility) -> list:
+        """src/KeyFrameDatabase.cc:199-310.  covisibility(slot) -> up to 10 slots (GetBestCovisibilityKeyFrames(10))."""
+        cw, sc, fw = self.query(mBowVec)
+        sharing = np.nonzero(cw > 0)[0]
+        if len(sharing) == 0:
+            return []
+        # lKFsSharingWords order: first shared word, then insertion order into that word's list (:211-224)
+        sharing = sorted(sharing.tolist(), key=lambda s: (int(fw[s]), self._seq[s]))
+        maxCommonWords = int(cw[sharing].max())
+        minCommonWords = int(np.float32(maxCommonWords) * np.float32(0.8))
+        scored = [(np.float32(sc[s]), s) for s in sharing if cw[s] > minCommonWords]
+        if not scored:
+            return []
+        acc, bestAcc = [], np.float32(0)
+        for si, s in scored:
+            bestScore, accScore, best = si, si, s
+            for s2 in covisibility(s):
+                if cw[s2] <= 0:
+                    continue                                  # mnRelocQuery != F->mnId: shares no word with the query
+                # mRelocScore is only assigned to keyframes above minCommonWords (:236-243); others still hold their old value.
+                # The reference reads that stale field; a fresh database has 0 there, which is what the mirror uses.
+                r = np.float32(sc[s2]) if cw[s2] > minCommonWords else np.float32(0)
+                accScore = np.float32(accScore + r)
+                if r > bestScore:
+                    best, bestScore = s2, r
+            acc.append((accScore, best))
+            if accScore > bestAcc:
+                bestAcc = accScore
+        minScoreToRetain = np.float32(0.75) * bestAcc
+        out, seen = [], set()
+        for a, s in acc:
+            if a > minScoreToRetain and s not in seen:
+                out.append(s); seen.add(s)
+        return out
+
+    def SearchByBoW(self, slots, F: KeyFrameView):
+        """SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:159-288) for database keyframes `slots` against frame F."""
+        sl = np.ascontiguousarray(slots, np.int32)
+        fc = F._c()
+        nF = len(F.mvKeysUn)
+        match = np.full((len(sl), max(nF, 1)), -1, np.int32)
+        nm = np.zeros(max(len(sl), 1), np.int32)
+        m = self._m
+        check(self._lib.borb_search_by_bow_db(m._h, self._h, _p(sl), len(sl), C.byref(fc), m.mfNNratio, int(m.mbCheckOrientation),
+                                              _p(match), _p(nm)), "borb_search_by_bow_db")
+        return nm[:len(sl)], match[:, :nF]
 
 
 class ORBVocabulary:

@@ -246,3 +246,24 @@ def test_search_for_initialization(M, oracle, views, seed, window, ratio, ori):
     n_o2, m_o2, p_o2 = oracle.port_search_for_initialization(F1, F2, p_o, max(window // 2, 5), ratio, ori)
     n_g2, m_g2, p_g2 = M.ORBmatcher(ratio, ori).SearchForInitialization(F1, F2, p_g, max(window // 2, 5))
     assert n_g2 == n_o2 and np.array_equal(m_g2, m_o2) and np.array_equal(p_g2, p_o2)
+
+
+def test_distinctive_descriptors(M, oracle, views):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:242-307), batched over MapPoints."""
+    rng = np.random.default_rng(5)
+    d = views[7]["dl"]
+    groups = []
+    for n in [1, 2, 3, 4, 5, 8, 13, 33, 64, 100, 300, 0, 7]:
+        base = d[rng.integers(0, len(d))]
+        g = np.repeat(base[None], n, 0).copy()
+        flips = rng.integers(0, 256, (n, 12))
+        for i in range(n):                                    # noisy copies of one descriptor: a realistic observation set
+            for b in flips[i][: rng.integers(0, 12)]:
+                g[i, b >> 3] ^= np.uint8(1 << (b & 7))
+        groups.append(g)
+    groups.append(np.repeat(d[:1], 6, 0))                     # all identical: every median 0, first index wins
+    groups.append(d[rng.integers(0, len(d), 40)])             # unrelated descriptors
+    got = M.ORBmatcher().ComputeDistinctiveDescriptors(groups)
+    want = np.array([oracle.port_distinctive_descriptor(g) for g in groups], np.int32)
+    assert np.array_equal(got, want), (got, want)
+    assert want[11] == -1 and want[13] == 0

@@ -207,3 +207,28 @@ def test_fuse_sim3_initialization_invariants(oracle, views):
     assert np.array_equal(p[hit], np.stack([views["kr"]["x"][m[hit]], views["kr"]["y"][m[hit]]], 1))
     untouched = np.setdiff1d(np.arange(len(prev)), hit)
     assert np.array_equal(p[untouched], prev[untouched])
+
+
+def test_bow_score_and_reloc_candidates_restatements(oracle):
+    """L1 score against a dense numpy evaluation; DetectRelocalizationCandidates against hand-checkable cases."""
+    rng = np.random.default_rng(6)
+    def rand_bow(n_words, n):
+        w = np.sort(rng.choice(n_words, n, replace=False))
+        v = rng.random(n); v /= v.sum()
+        return dict(zip(w.tolist(), v.tolist()))
+    for _ in range(20):
+        a, b = rand_bow(500, 120), rand_bow(500, 150)
+        s, c, f = oracle.port_bow_score(a, b)
+        da = np.zeros(500); db = np.zeros(500)
+        da[list(a)] = list(a.values()); db[list(b)] = list(b.values())
+        shared = sorted(set(a) & set(b))
+        assert c == len(shared) and (f == shared[0] if shared else f == 0xFFFFFFFF)
+        assert abs(s - (1.0 - 0.5 * np.abs(da - db).sum())) < 1e-12          # ||v-w||_1 identity (Nister 2006), both L1-normalised
+    assert oracle.port_bow_score(a, a)[0] == pytest.approx(1.0, abs=1e-15)
+    # three keyframes: 0 and 1 share the query's words, 2 shares none; 1 is 0's covisible neighbour and scores higher
+    q = {1: 0.5, 2: 0.5}
+    bows = [{1: 0.6, 2: 0.2, 9: 0.2}, {1: 0.5, 2: 0.5}, {7: 1.0}]
+    neigh = np.full((3, 10), -1, np.int32); neigh[0, 0] = 1; neigh[1, 0] = 0; neigh[2, 0] = 0
+    assert oracle.port_detect_reloc_candidates(bows, 16, q, neigh).tolist() == [1]      # both groups elect keyframe 1, listed once
+    assert oracle.port_detect_reloc_candidates(bows, 16, {7: 1.0}, neigh).tolist() == [2]
+    assert oracle.port_detect_reloc_candidates(bows, 16, {5: 1.0}, neigh).tolist() == []

@@ -35,3 +35,9 @@ voc = M.ORBVocabulary.from_arrays(e["parent"], e["is_leaf"], e["desc"], e["weigh
 kf1, kf2 = mf.keyframe_views(v, pv, 3, levelsup=1)
 print("bow", mt.SearchByBoW(kf1, kf2)[0], mt.SearchByBoW_KF(kf1, kf2)[0], len(mt.SearchForTriangulation(kf1, kf2, mf.rectified_F12(1), (-1000.0, 200.0))))
 print("voc", voc.transform_raw(v["dl"], 1)[0][:4])
+db = M.KeyFrameDatabase(mt)
+bow1, _ = voc.transform(v["dl"], 1)
+bow2, _ = voc.transform(v["dr"], 1)
+db.add(kf1, bow1); db.add(kf2, bow2)
+print("kfdb", db.query(bow1)[0], db.SearchByBoW([0, 1], kf2)[0])
+print("distinctive", mt.ComputeDistinctiveDescriptors([v["dl"][:9], v["dl"][:1], v["dl"][:0], v["dl"][:70]]))
