@@ -1,0 +1,93 @@
+"""Secondary measurements for BASELINE.json configs[2] and configs[4] (parity-test configurations, not bench lines):
+   config 2: RGB-D TUM-shaped 640x480 extract + SearchByProjection against 300 local MapPoints — us per call;
+   config 4: EuRoC-shaped 752x480 @1200 features, loop-closure / relocalisation against a 2000-keyframe database:
+             one KeyFrameDatabase query (shared words + L1 score for all keyframes) and SearchByBoW against all
+             2000 resident keyframes.
+All times are wall-clock around the public Python call (host buffers in, results out), median of `--reps`.
+usage: python tools/bench_configs.py [--kfs 2000] [--reps 20]  -> one JSON line per config on stdout."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from orb_slam2_b200 import matcher as M, sharding, synth                      # noqa: E402
+from orb_slam2_b200.extractor import ORBextractor                              # noqa: E402
+
+
+def med(f, reps):
+    f()
+    t = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); f(); t.append(time.perf_counter() - t0)
+    return float(np.median(t))
+
+
+def config2(reps):
+    X = ORBextractor(1000)
+    img0, img1 = synth.mono_frame(1, 0, 0, 640, 480), synth.mono_frame(1, 0, 1, 640, 480)
+    k0, d0 = X(img0)
+    k1, d1 = X(img0)          # the "current" frame sees the same scene; 300 of its features stand in for local MapPoints
+    rng = np.random.default_rng(0)
+    sel = rng.choice(len(k0), 300, replace=False)
+    F = M.FrameView(k1, d1, X.GetScaleFactors(), (0.0, 0.0, 640.0, 480.0))
+    mps = M.MapPointsView(k0["x"][sel] + rng.normal(0, 1.5, 300).astype(np.float32), k0["y"][sel] + rng.normal(0, 1.5, 300).astype(np.float32),
+                          np.zeros(300, np.float32), k0["octave"][sel].astype(np.int32), np.full(300, 0.9, np.float32), d0[sel])
+    mt = M.ORBmatcher(0.8, True)
+    n, _ = mt.SearchByProjection(F, mps, 3.0)
+    t_match = med(lambda: mt.SearchByProjection(F, mps, 3.0), reps)
+    t_ext = med(lambda: X(img1), reps)
+    return {"config": "configs[2]: TUM-shaped 640x480 @1000, extract + SearchByProjection vs 300 local MapPoints", "matches": int(n),
+            "extract_ms": t_ext * 1e3, "search_by_projection_us": t_match * 1e6, "frames_per_s_serial": 1.0 / (t_ext + t_match)}
+
+
+def config4(n_kf, reps):
+    voc = M.ORBVocabulary.from_arrays(*sharding.random_vocabulary_arrays(10, 6, 7), 10, 6)
+    X = ORBextractor(1200)
+    rng = np.random.default_rng(1)
+    n_src = 40
+    outs = X.extract_batch([synth.mono_frame(50 + i, 0, 0, 752, 480) for i in range(n_src)])
+    mt = M.ORBmatcher(0.75, True)
+    db = M.KeyFrameDatabase(mt)
+    t_add = 0.0
+    n_feat = 0
+    for j in range(n_kf):
+        k, d = outs[j % n_src]
+        if j >= n_src:                                         # derive further keyframes by flipping ~4 % of the descriptor bits
+            flip = (rng.random((len(d), 32, 8)) < 0.04)
+            d = d ^ np.packbits(flip, axis=2, bitorder="little").reshape(len(d), 32)
+        bow, fv = voc.transform(d, 4)
+        kf = M.KeyFrameView(mvKeysUn=k, mDescriptors=d, mFeatVec=fv, has_mp=np.ones(len(k), np.uint8))
+        t0 = time.perf_counter(); db.add(kf, bow); t_add += time.perf_counter() - t0
+        n_feat += len(k)
+    qk, qd = outs[3]
+    flip = (rng.random((len(qd), 32, 8)) < 0.02)
+    qd = qd ^ np.packbits(flip, axis=2, bitorder="little").reshape(len(qd), 32)
+    qbow, qfv = voc.transform(qd, 4)
+    F = M.KeyFrameView(mvKeysUn=qk, mDescriptors=qd, mFeatVec=qfv)
+    cw, sc, fw = db.query(qbow)
+    t_query = med(lambda: db.query(qbow), reps)
+    slots = np.arange(n_kf, dtype=np.int32)
+    nm, match = db.SearchByBoW(slots, F)
+    t_bow = med(lambda: db.SearchByBoW(slots, F), max(3, reps // 4))
+    top = np.argsort(-sc)[:20].astype(np.int32)
+    t_bow20 = med(lambda: db.SearchByBoW(top, F), reps)
+    db_bytes = db.size()[1]
+    return {"config": f"configs[4]: EuRoC-shaped 752x480 @1200, {n_kf}-keyframe resident database (vocabulary k=10 L=6, random tree)",
+            "keyframes": n_kf, "features_per_keyframe": n_feat / n_kf, "db_device_MB": db_bytes / 1e6, "add_ms_per_keyframe": t_add / n_kf * 1e3,
+            "kfdb_query_us": t_query * 1e6, "best_common_words": int(cw.max()), "best_score": float(sc.max()),
+            "search_by_bow_all_ms": t_bow * 1e3, "search_by_bow_all_matches_max": int(nm.max()),
+            "search_by_bow_all_descriptor_GBps": n_feat * 32 / t_bow / 1e9,
+            "search_by_bow_top20_us": t_bow20 * 1e6}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kfs", type=int, default=2000)
+    ap.add_argument("--reps", type=int, default=20)
+    a = ap.parse_args()
+    print(json.dumps(config2(a.reps)), flush=True)
+    print(json.dumps(config4(a.kfs, a.reps)), flush=True)
