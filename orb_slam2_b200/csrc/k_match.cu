@@ -57,9 +57,7 @@ __device__ void three_maxima(const int* cnt, int& ind1, int& ind2, int& ind3) {
 }
 
 __device__ __forceinline__ unsigned warp_min(unsigned v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, off));
-    return v;
+    return __reduce_min_sync(0xFFFFFFFFu, v);        // REDUX: one instruction instead of a 5-step shuffle chain (the replays are latency chains)
 }
 
 }  // namespace
@@ -190,12 +188,73 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
     if (lane == 0) A.cand_cnt[iMP] = count;
 }
 
+// Order-dependent claiming (a feature taken by an earlier query is skipped by later ones) without walking the queries one
+// by one.  The CTA packs the candidate lists into shared memory, then works in ROUNDS: every unresolved query writes its
+// index into owner[f] (atomicMin) for each of its candidates f; a query whose index survives on ALL its candidates has
+// no unresolved predecessor touching them, so its sequential outcome is already determined — all such queries resolve
+// in parallel (they share no candidate).  Rounds = depth of the conflict chain (a handful for points spread over the
+// image); after REPLAY_ROUNDS rounds, or when the lists do not fit, one warp finishes the rest in index order.
+constexpr int REPLAY_THREADS = 1024;
+constexpr int REPLAY_ROUNDS = 48;
+constexpr int REPLAY_ECAP = 24576;        // packed candidate entries kept in shared memory; lists beyond it are read from global
+
+struct ReplayLists { const int* offs; const uint32_t* ent; const uint8_t* obs; };
+
+__device__ __forceinline__ ReplayLists stage_replay_lists(const ProjArgs& A, uint32_t* base) {
+    __shared__ int part[REPLAY_THREADS];
+    int* offs = reinterpret_cast<int*>(base);
+    uint32_t* ent = base + (A.n_mp + 1);
+    uint8_t* obs = reinterpret_cast<uint8_t*>(ent + REPLAY_ECAP);
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int C = (A.n_mp + REPLAY_THREADS - 1) / REPLAY_THREADS;
+    const int i0 = min(A.n_mp, tid * C), i1 = min(A.n_mp, i0 + C);
+    int sum = 0;
+    for (int i = i0; i < i1; i++) sum += A.cand_cnt[i];
+    part[tid] = sum;
+    __syncthreads();
+    if (tid < 32) {
+        int v[REPLAY_THREADS / 32], sl = 0;
+#pragma unroll
+        for (int k = 0; k < REPLAY_THREADS / 32; k++) { v[k] = part[tid * (REPLAY_THREADS / 32) + k]; sl += v[k]; }
+        int incl = sl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+        int run = incl - sl;
+#pragma unroll
+        for (int k = 0; k < REPLAY_THREADS / 32; k++) { part[tid * (REPLAY_THREADS / 32) + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    int run = part[tid];
+    for (int i = i0; i < i1; i++) {
+        offs[i] = run;
+        run += A.cand_cnt[i];
+        obs[i] = (A.mp_has_obs == nullptr || A.mp_has_obs[i]) ? 1 : 0;
+    }
+    if (i1 == A.n_mp && (i0 < i1 || tid == 0)) offs[A.n_mp] = run;       // the thread that owns the tail (thread 0 if there is nothing)
+    __syncthreads();
+    for (int i = wrp; i < A.n_mp; i += REPLAY_THREADS / 32) {
+        const int o = offs[i], cnt = offs[i + 1] - o;
+        const uint32_t* c = A.cand + (size_t)i * A.n;
+        for (int p = lane; p < cnt; p += 32)
+            if (o + p < REPLAY_ECAP) ent[o + p] = c[p];
+    }
+    __syncthreads();
+    return ReplayLists{offs, ent, obs};
+}
+__host__ __device__ inline size_t replay_smem_words(int n_mp) { return (size_t)(n_mp + 1) + REPLAY_ECAP + (size_t)(n_mp + 3) / 4; }
+
 // One warp replays the map points in order (the occupancy skip is order dependent).
-__global__ void __launch_bounds__(32) proj_resolve_kernel(ProjArgs A, int32_t* __restrict__ match_feat, int* __restrict__ n_matches) {
-    extern __shared__ uint32_t held[];       // bit per frame feature: holds a MapPoint with observations
-    const int lane = threadIdx.x;
+// Shared body of the two resolve kernels.  LAST = false: SearchByProjection(F, vpMapPoints) — best/second-best with the
+// ratio test (:98-121), out[iq] = feature.  LAST = true: the pose-projection overloads — best only, threshold th_dist,
+// out[feature] = iq and a match event for the rotation histogram.
+template <bool LAST>
+__device__ __forceinline__ void resolve_rounds(const ProjArgs& A, uint32_t* rsm, int32_t* __restrict__ out, int32_t* __restrict__ ev_idx,
+                                               int* nev_sh, int* nm_sh) {
+    __shared__ int unresolved, round_left;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int words = (A.n + 31) / 32;
-    for (int w = lane; w < words; w += 32) {
+    uint32_t* held = rsm;                    // bit per frame feature: occupied (LAST: by a MapPoint with observations or any, per overload)
+    for (int w = tid; w < words; w += REPLAY_THREADS) {
         uint32_t bits = 0;
         if (A.occupied != nullptr)
             for (int b = 0; b < 32; b++) {
@@ -204,12 +263,18 @@ __global__ void __launch_bounds__(32) proj_resolve_kernel(ProjArgs A, int32_t* _
             }
         held[w] = bits;
     }
-    __syncwarp();
-    int nm = 0;
-    for (int iMP = 0; iMP < A.n_mp; iMP++) {
-        const int cnt = A.cand_cnt[iMP];
-        const uint32_t* c = A.cand + (size_t)iMP * A.n;
-        // per lane: two smallest keys (dist << 16 | position) among its unheld candidates
+    uint32_t* owner = rsm + words;                                            // A.n entries
+    uint8_t* done = reinterpret_cast<uint8_t*>(owner + A.n);                  // A.n_mp flags
+    const ReplayLists Lq = stage_replay_lists(A, rsm + words + A.n + (A.n_mp + 3) / 4);
+    const bool fits = Lq.offs[A.n_mp] <= REPLAY_ECAP;
+    for (int i = tid; i < A.n_mp; i += REPLAY_THREADS) done[i] = 0;
+    if (tid == 0) { unresolved = A.n_mp; round_left = fits ? REPLAY_ROUNDS : 0; *nev_sh = 0; *nm_sh = 0; }
+    __syncthreads();
+
+    // resolves query iq against the current `held`; returns through out / events; must be called by a whole warp
+    auto resolve = [&](int iq, bool atomic) {
+        const int o = Lq.offs[iq], cnt = Lq.offs[iq + 1] - o;
+        const uint32_t* c = fits ? Lq.ent + o : A.cand + (size_t)iq * A.n;
         unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
         for (int p = lane; p < cnt; p += 32) {
             const uint32_t e = c[p];
@@ -219,30 +284,75 @@ __global__ void __launch_bounds__(32) proj_resolve_kernel(ProjArgs A, int32_t* _
             if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
         }
         const unsigned best = warp_min(k1);
-        const unsigned second = warp_min(k1 == best ? k2 : k1);
         int m = -1;
         if (best != 0xFFFFFFFFu) {
             const int bestDist = (int)(best >> 16);
-            if (bestDist <= TH_HIGH) {
-                const uint32_t eb = c[best & 0xFFFFu];
+            const uint32_t eb = c[best & 0xFFFFu];
+            if (LAST) {
+                if (bestDist <= A.th_dist) m = (int)(eb & 0xFFFF);
+            } else if (bestDist <= TH_HIGH) {
+                const unsigned second = warp_min(k1 == best ? k2 : k1);
                 const int bestLevel = (int)(eb >> 25);
                 int bestDist2 = 256, bestLevel2 = -1;
                 if (second != 0xFFFFFFFFu) { bestDist2 = (int)(second >> 16); bestLevel2 = (int)(c[second & 0xFFFFu] >> 25); }
-                if (!(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2))) {
-                    m = (int)(eb & 0xFFFF);
-                    nm++;
-                    if (lane == 0 && (A.mp_has_obs == nullptr || A.mp_has_obs[iMP])) held[m >> 5] |= 1u << (m & 31);
-                }
+                if (!(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2))) m = (int)(eb & 0xFFFF);
             }
         }
-        if (lane == 0) match_feat[iMP] = m;
+        if (lane == 0) {
+            if (!LAST) out[iq] = m;
+            if (m >= 0) {
+                if (Lq.obs[iq]) { if (atomic) atomicOr(&held[m >> 5], 1u << (m & 31)); else held[m >> 5] |= 1u << (m & 31); }
+                if (LAST) { out[m] = iq; ev_idx[atomicAdd(nev_sh, 1)] = m | (iq << 16); }     // match event: feature | query << 16
+                atomicAdd(nm_sh, 1);
+            }
+        }
+    };
+
+    while (true) {
+        if (unresolved == 0 || round_left == 0) break;                       // uniform: written before the last barrier
+        for (int f = tid; f < A.n; f += REPLAY_THREADS) owner[f] = 0xFFFFFFFFu;
+        __syncthreads();
+        for (int iq = wrp; iq < A.n_mp; iq += REPLAY_THREADS / 32) {
+            if (done[iq]) continue;
+            const int o = Lq.offs[iq], cnt = Lq.offs[iq + 1] - o;
+            for (int p = lane; p < cnt; p += 32) atomicMin(&owner[Lq.ent[o + p] & 0xFFFF], (uint32_t)iq);
+        }
+        __syncthreads();
+        int finished = 0;
+        for (int iq = wrp; iq < A.n_mp; iq += REPLAY_THREADS / 32) {
+            if (done[iq]) continue;
+            const int o = Lq.offs[iq], cnt = Lq.offs[iq + 1] - o;
+            bool mine = true;
+            for (int p = lane; p < cnt; p += 32) mine = mine && owner[Lq.ent[o + p] & 0xFFFF] == (uint32_t)iq;
+            if (!__all_sync(0xFFFFFFFFu, mine)) continue;
+            resolve(iq, true);
+            if (lane == 0) done[iq] = 1;
+            finished++;
+        }
+        if (lane == 0 && finished) atomicSub(&unresolved, finished);
+        if (tid == 0) round_left--;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid >= 32 || unresolved == 0) return;
+    for (int iq = 0; iq < A.n_mp; iq++) {                                    // the rest, in index order, by one warp
+        if (done[iq]) continue;
+        resolve(iq, false);
         __syncwarp();
     }
-    if (lane == 0) *n_matches = nm;
+}
+__host__ __device__ inline size_t resolve_smem_words(int n, int n_mp) {
+    return (size_t)(n + 31) / 32 + (size_t)n + (size_t)(n_mp + 3) / 4 + replay_smem_words(n_mp);
 }
 
-// SearchByProjection(CurrentFrame, LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470.  Projection of the last frame's
-// map points with the current pose (float32 (r0*p0 + r1*p1) + r2*p2, then + t: cv::Mat product order) and the search window.
+__global__ void __launch_bounds__(REPLAY_THREADS) proj_resolve_kernel(ProjArgs A, int32_t* __restrict__ match_feat, int* __restrict__ n_matches) {
+    extern __shared__ uint32_t rsm[];
+    __shared__ int nev_sh, nm_sh;
+    resolve_rounds<false>(A, rsm, match_feat, nullptr, &nev_sh, &nm_sh);
+    __syncthreads();
+    if (threadIdx.x == 0) *n_matches = nm_sh;
+}
+
 // glibc (>= 2.28) logf for positive normal finite x — the function MapPoint::PredictScale calls (src/MapPoint.cc:393,410;
 // `log` resolves to the float overload).  ARM optimized-routines algorithm in double; checked on the CPU against glibc for
 // every positive normal float, with and without FMA contraction: 0 mismatches.
@@ -361,62 +471,37 @@ __global__ void __launch_bounds__(256) project_points_kernel(LastArgs L) {
 
 // One warp replays the last frame's map points in order: best candidate only (:1397-1424), occupancy by observations,
 // rotation histogram over the MATCH EVENTS (a feature re-claimed later appears twice, exactly as rotHist does).
-__global__ void __launch_bounds__(32) proj_resolve_last_kernel(ProjArgs A, const borb_keypoint* __restrict__ cur_keys,
-                                                               int32_t* __restrict__ state_cur, int32_t* __restrict__ ev_idx,
-                                                               uint8_t* __restrict__ ev_bin, int* __restrict__ n_matches) {
-    extern __shared__ uint32_t held[];
+__global__ void __launch_bounds__(REPLAY_THREADS) proj_resolve_last_kernel(ProjArgs A, const borb_keypoint* __restrict__ cur_keys,
+                                                                           int32_t* __restrict__ state_cur, int32_t* __restrict__ ev_idx,
+                                                                           uint8_t* __restrict__ ev_bin, int* __restrict__ n_matches) {
+    extern __shared__ uint32_t rsm[];
     __shared__ int hist[32];
-    const int lane = threadIdx.x;
-    const int words = (A.n + 31) / 32;
-    for (int w = lane; w < words; w += 32) {
-        uint32_t bits = 0;
-        if (A.occupied != nullptr)
-            for (int b = 0; b < 32; b++) {
-                const int i = w * 32 + b;
-                if (i < A.n && A.occupied[i]) bits |= 1u << b;
-            }
-        held[w] = bits;
-    }
-    for (int i = lane; i < A.n; i += 32) state_cur[i] = -1;
-    hist[lane] = 0;
-    __syncwarp();
-    int nev = 0;
-    for (int iq = 0; iq < A.n_mp; iq++) {
-        const int cnt = A.cand_cnt[iq];
-        const uint32_t* c = A.cand + (size_t)iq * A.n;
-        unsigned k1 = 0xFFFFFFFFu;
-        for (int p = lane; p < cnt; p += 32) {
-            const uint32_t e = c[p];
-            const int idx = e & 0xFFFF;
-            if ((held[idx >> 5] >> (idx & 31)) & 1u) continue;
-            k1 = min(k1, (((e >> 16) & 0x1FFu) << 16) | (unsigned)p);
-        }
-        const unsigned best = warp_min(k1);
-        if (best != 0xFFFFFFFFu && (int)(best >> 16) <= A.th_dist) {
-            const int m = (int)(c[best & 0xFFFFu] & 0xFFFF);
-            if (lane == 0) {
-                state_cur[m] = iq;
-                if (A.mp_has_obs == nullptr || A.mp_has_obs[iq]) held[m >> 5] |= 1u << (m & 31);
-                ev_idx[nev] = m;
-                if (A.check_ori) {
-                    const int b = rot_bin(A.q_angle[iq], cur_keys[m].angle);
-                    ev_bin[nev] = (uint8_t)b;
-                    hist[b]++;
-                }
-            }
-            nev++;
+    __shared__ int nev_sh, nm_sh;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < A.n; i += REPLAY_THREADS) state_cur[i] = -1;
+    if (tid < 32) hist[tid] = 0;
+    __syncthreads();                                                          // state_cur is rewritten by the resolving warps
+    resolve_rounds<true>(A, rsm, state_cur, ev_idx, &nev_sh, &nm_sh);
+    __syncthreads();
+    if (tid >= 32) return;
+    const int nev = nev_sh;
+    int nm = nm_sh;
+    if (A.check_ori) {
+        // rotation histogram over the MATCH EVENTS (a feature re-claimed later appears twice, exactly as rotHist does)
+        for (int e = lane; e < nev; e += 32) {
+            const int ev = ev_idx[e];
+            const int b = rot_bin(A.q_angle[ev >> 16], cur_keys[ev & 0xFFFF].angle);
+            ev_bin[e] = (uint8_t)b;
+            atomicAdd(&hist[b], 1);
         }
         __syncwarp();
-    }
-    int nm = nev;
-    if (A.check_ori) {
         int i1, i2, i3;
         three_maxima(hist, i1, i2, i3);
-        // serial cull in histogram-bin order is order independent for the final state: every event of a culled bin nulls its feature
+        // culling is order independent for the final state: every event of a culled bin nulls its feature
         int removed = 0;
         for (int e = lane; e < nev; e += 32) {
             const int b = ev_bin[e];
-            if (b != i1 && b != i2 && b != i3) { state_cur[ev_idx[e]] = -2; removed++; }
+            if (b != i1 && b != i2 && b != i3) { state_cur[ev_idx[e] & 0xFFFF] = -2; removed++; }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, off);
@@ -620,78 +705,152 @@ __global__ void __launch_bounds__(256) kfdb_score_kernel(const BowDev* __restric
 // ------------------------------------------------------------------------------------------------ BoW guided search
 // mode 0: SearchByBoW(KeyFrame*, Frame&)   — q = keyframe (needs has_mp), t = frame;   out match[t.n]  = q index
 // mode 1: SearchByBoW(KeyFrame*, KeyFrame*) — q = kf1, t = kf2 (both need has_mp);      out match[q.n]  = t index
-__global__ void __launch_bounds__(128) bow_match_kernel(const KfDev* __restrict__ qs, const KfDev* __restrict__ ts, int n_pairs, int mode,
-                                                        float nnratio, int check_ori, int32_t* __restrict__ match, int out_stride,
-                                                        uint8_t* __restrict__ bins, int32_t* __restrict__ n_matches, int max_t) {
+// Per shared node the nq x nt distance matrix is computed first, all lanes busy and all loads in flight at once
+// (the greedy claim makes the ROWS sequential, not the distances); the replay then walks the rows over the
+// matrix in shared memory.  BOW_DCAP matrix entries per warp; wider nodes are processed in row chunks.
+constexpr int BOW_WARPS = 8;        // warps per (keyframe, frame) pair: FeatureVector nodes are independent (a feature lives in
+                                    // exactly one node, so claims never cross nodes) and are dealt round-robin to the warps
+constexpr int BOW_DCAP = 1024;      // distance-matrix entries per warp
+constexpr int BOW_JCAP = 1024;      // widest target bucket the matrix path handles; beyond it rows fall back to direct evaluation
+constexpr int BOW_RCAP = 256;       // rows per chunk
+constexpr int BOW_WARP_WORDS = BOW_DCAP / 2 + BOW_JCAP / 2 + BOW_RCAP / 2;
+
+__global__ void __launch_bounds__(32 * BOW_WARPS) bow_match_kernel(const KfDev* __restrict__ qs, const KfDev* __restrict__ ts, int n_pairs,
+                                                                   int mode, float nnratio, int check_ori, int32_t* __restrict__ match,
+                                                                   int out_stride, uint8_t* __restrict__ bins,
+                                                                   int32_t* __restrict__ n_matches, int max_t) {
     extern __shared__ uint32_t sm[];
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const int pair = blockIdx.x * (blockDim.x >> 5) + wrp;
-    if (pair >= n_pairs) return;
+    __shared__ int hist[32];
+    __shared__ int nm_total;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, tid = threadIdx.x;
+    const int pair = blockIdx.x;
     const int words = (max_t + 31) / 32;
-    uint32_t* claimed = sm + (size_t)wrp * (words + 32);
-    int* hist = reinterpret_cast<int*>(claimed + words);
+    uint32_t* claimed = sm;                                                      // bit per target feature, shared by the CTA
+    uint16_t* D = reinterpret_cast<uint16_t*>(sm + words + (size_t)wrp * BOW_WARP_WORDS);   // distances of the current row chunk
+    uint16_t* J = D + BOW_DCAP;                                                  // target feature per column (0xFFFF = unusable)
+    uint16_t* R = J + BOW_JCAP;                                                  // query feature per row of the chunk
     const KfDev q = qs[pair];
     const KfDev t = ts[mode == 0 ? 0 : pair];
     int32_t* out = match + (size_t)pair * out_stride;
     uint8_t* bin = bins + (size_t)pair * out_stride;
     const int nout = mode == 0 ? t.n : q.n;
-    for (int i = lane; i < nout; i += 32) out[i] = -1;
-    for (int w = lane; w < words; w += 32) claimed[w] = 0;
-    if (lane < 32) hist[lane] = 0;
-    __syncwarp();
+    for (int i = tid; i < nout; i += 32 * BOW_WARPS) out[i] = -1;
+    for (int w = tid; w < words; w += 32 * BOW_WARPS) claimed[w] = 0;
+    if (tid < 32) hist[tid] = 0;
+    if (tid == 0) nm_total = 0;
+    __syncthreads();
     int nm = 0;
-    for (int a = 0; a < q.nn; a++) {
+    int lo = 0;                                                                  // merge-join cursor in the target's node list (:180-264)
+    for (int a = wrp; a < q.nn; a += BOW_WARPS) {
         const uint32_t node = q.node[a];
-        // lower_bound in the target's node list (merge-join of two ordered maps, :180-264)
-        int lo = 0, hi = t.nn;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (t.node[mid] < node) lo = mid + 1; else hi = mid; }
-        if (lo >= t.nn || t.node[lo] != node) continue;
-        const int ts0 = t.start[lo], ts1 = t.start[lo + 1];
-        for (int iq = q.start[a]; iq < q.start[a + 1]; iq++) {
-            const int r = (int)q.idx[iq];
-            if (q.has_mp == nullptr || !q.has_mp[r]) continue;
-            const uint32_t* dq = reinterpret_cast<const uint32_t*>(q.desc + (size_t)r * 32);
-            unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-            for (int p = ts0 + lane; p < ts1; p += 32) {
-                const int j = (int)t.idx[p];
-                if ((claimed[j >> 5] >> (j & 31)) & 1u) continue;
-                if (mode == 1 && (t.has_mp == nullptr || !t.has_mp[j])) continue;
-                const int dist = ham_words(dq, reinterpret_cast<const uint32_t*>(t.desc + (size_t)j * 32));
-                const unsigned key = ((unsigned)dist << 16) | (unsigned)(p - ts0);
-                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+        // advance the cursor to the first target node >= node: 32 nodes per probe
+        while (lo < t.nn) {
+            const int c = lo + lane;
+            const unsigned ge = __ballot_sync(0xFFFFFFFFu, c >= t.nn || t.node[c] >= node);
+            if (ge) { lo += __ffs(ge) - 1; break; }
+            lo += 32;
+        }
+        if (lo >= t.nn) break;
+        if (t.node[lo] != node) continue;
+        const int ts0 = t.start[lo], nt = t.start[lo + 1] - ts0;
+        const int qs0 = q.start[a], nq = q.start[a + 1] - qs0;
+        if (nt <= 0 || nq <= 0) continue;
+        const bool matrix = nt <= BOW_JCAP;
+        __syncwarp();
+        if (matrix) {
+            for (int p = lane; p < nt; p += 32) {
+                const int j = (int)t.idx[ts0 + p];
+                J[p] = (mode == 1 && (t.has_mp == nullptr || !t.has_mp[j])) ? 0xFFFFu : (uint16_t)j;
             }
-            const unsigned best = warp_min(k1);
-            const unsigned second = warp_min(k1 == best ? k2 : k1);
-            if (best == 0xFFFFFFFFu) continue;
-            const int bestDist1 = (int)(best >> 16);
-            const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
-            const bool pass = mode == 0 ? (bestDist1 <= TH_LOW) : (bestDist1 < TH_LOW);
-            if (pass && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
-                const int j = (int)t.idx[ts0 + (int)(best & 0xFFFFu)];
-                if (lane == 0) {
-                    claimed[j >> 5] |= 1u << (j & 31);
-                    const int o = mode == 0 ? j : r;
-                    out[o] = mode == 0 ? r : j;
-                    if (check_ori) {
-                        const int b = rot_bin(q.keys[r].angle, t.keys[j].angle);
-                        bin[o] = (uint8_t)b;
-                        hist[b]++;
+        }
+        const int rows_per_chunk = matrix ? min(BOW_RCAP, max(1, BOW_DCAP / nt)) : BOW_RCAP;
+        for (int r0 = 0; r0 < nq; r0 += rows_per_chunk) {
+            const int nr = min(rows_per_chunk, nq - r0);
+            __syncwarp();
+            for (int i = lane; i < nr; i += 32) R[i] = (uint16_t)q.idx[qs0 + r0 + i];
+            __syncwarp();
+            if (matrix && nr * nt <= BOW_DCAP) {
+                for (int e = lane; e < nr * nt; e += 32) {
+                    const int i = e / nt, p = e - i * nt;
+                    const int j = J[p];
+                    D[e] = j == 0xFFFF ? (uint16_t)0x1FF
+                                       : (uint16_t)ham_words(reinterpret_cast<const uint32_t*>(q.desc + (size_t)R[i] * 32),
+                                                             reinterpret_cast<const uint32_t*>(t.desc + (size_t)j * 32));
+                }
+            }
+            const bool have_d = matrix && nr * nt <= BOW_DCAP;                   // (a single row wider than the matrix is evaluated directly)
+            __syncwarp();
+            for (int g0 = 0; g0 < nr; g0 += 32) {
+                // row metadata for 32 rows at once: one round of global latency instead of one per row
+                const int il = g0 + lane;
+                const int r_l = il < nr ? (int)R[il] : 0;
+                const bool ok_l = il < nr && q.has_mp != nullptr && q.has_mp[r_l] != 0;
+                const float ang_l = (ok_l && check_ori) ? q.keys[r_l].angle : 0.f;
+                const unsigned okmask = __ballot_sync(0xFFFFFFFFu, ok_l);
+                const int ng = min(32, nr - g0);
+                for (int ii = 0; ii < ng; ii++) {
+                    if (!((okmask >> ii) & 1u)) continue;
+                    const int i = g0 + ii;
+                    const int r = __shfl_sync(0xFFFFFFFFu, r_l, ii);
+                    const float qa = __shfl_sync(0xFFFFFFFFu, ang_l, ii);
+                    unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+                    if (have_d) {
+                        for (int p = lane; p < nt; p += 32) {
+                            const int j = J[p];
+                            if (j == 0xFFFF || ((claimed[j >> 5] >> (j & 31)) & 1u)) continue;
+                            const unsigned key = ((unsigned)D[i * nt + p] << 16) | (unsigned)p;
+                            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                        }
+                    } else {                                                      // bucket wider than the matrix: direct evaluation
+                        const uint32_t* dq = reinterpret_cast<const uint32_t*>(q.desc + (size_t)r * 32);
+                        for (int p = lane; p < nt; p += 32) {
+                            const int j = (int)t.idx[ts0 + p];
+                            if ((claimed[j >> 5] >> (j & 31)) & 1u) continue;
+                            if (mode == 1 && (t.has_mp == nullptr || !t.has_mp[j])) continue;
+                            const int dist = ham_words(dq, reinterpret_cast<const uint32_t*>(t.desc + (size_t)j * 32));
+                            const unsigned key = ((unsigned)dist << 16) | (unsigned)p;
+                            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                        }
+                    }
+                    const unsigned best = warp_min(k1);
+                    const unsigned second = warp_min(k1 == best ? k2 : k1);
+                    if (best == 0xFFFFFFFFu) continue;
+                    const int bestDist1 = (int)(best >> 16);
+                    const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
+                    const bool pass = mode == 0 ? (bestDist1 <= TH_LOW) : (bestDist1 < TH_LOW);
+                    if (pass && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
+                        const int pb = (int)(best & 0xFFFFu);
+                        const int j = (int)t.idx[ts0 + pb];
+                        if (lane == 0) {
+                            atomicOr(&claimed[j >> 5], 1u << (j & 31));          // other warps own other nodes' bits of the same word
+                            const int o = mode == 0 ? j : r;
+                            out[o] = mode == 0 ? r : j;
+                            if (check_ori) {
+                                const int b2 = rot_bin(qa, t.keys[j].angle);
+                                bin[o] = (uint8_t)b2;
+                                atomicAdd(&hist[b2], 1);
+                            }
+                        }
+                        nm++;
+                        __syncwarp();
                     }
                 }
-                nm++;
-                __syncwarp();
             }
         }
     }
-    __syncwarp();
+    if (lane == 0 && nm) atomicAdd(&nm_total, nm);
+    __threadfence_block();
+    __syncthreads();
+    if (wrp != 0) return;
+    nm = nm_total;
     if (check_ori) {
         int i1, i2, i3;
         three_maxima(hist, i1, i2, i3);
         int removed = 0;
         for (int i = lane; i < nout; i += 32)
             if (out[i] >= 0) {
-                const int b = bin[i];
-                if (b != i1 && b != i2 && b != i3) { out[i] = -1; removed++; }
+                const int b2 = bin[i];
+                if (b2 != i1 && b2 != i2 && b2 != i3) { out[i] = -1; removed++; }
             }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, off);
@@ -833,8 +992,9 @@ int launch_grid_sort(const borb_keypoint* keys, int n, float minX, float minY, f
 }
 int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s) {
     if (A.n_mp > 0) proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
-    const int words = (A.n + 31) / 32;
-    proj_resolve_kernel<<<1, 32, words * 4, s>>>(A, match_feat, n_matches);
+    const size_t smem = resolve_smem_words(A.n, A.n_mp) * 4;
+    cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    proj_resolve_kernel<<<1, REPLAY_THREADS, smem, s>>>(A, match_feat, n_matches);
     return 2;
 }
 int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_cur, int32_t* ev_idx, uint8_t* ev_bin, int* n_matches,
@@ -843,8 +1003,9 @@ int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_
         project_points_kernel<<<(L.n_last + 255) / 256, 256, 0, s>>>(L);
         proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
     }
-    const int words = (A.n + 31) / 32;
-    proj_resolve_last_kernel<<<1, 32, words * 4, s>>>(A, A.keys, state_cur, ev_idx, ev_bin, n_matches);
+    const size_t smem = resolve_smem_words(A.n, A.n_mp) * 4;
+    cudaFuncSetAttribute(proj_resolve_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    proj_resolve_last_kernel<<<1, REPLAY_THREADS, smem, s>>>(A, A.keys, state_cur, ev_idx, ev_bin, n_matches);
     return 3;
 }
 int launch_initialization(const ProjArgs& A, const borb_keypoint* keys1, int n1, int32_t* match12, int32_t* ev_idx, uint8_t* ev_bin,
@@ -880,9 +1041,9 @@ int launch_sim3_agree(const int32_t* match1, const int32_t* match2, int n1, int 
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
                      int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s) {
     const int words = (max_t + 31) / 32;
-    const size_t smem = (size_t)4 * (words + 32) * 4;
+    const size_t smem = (size_t)(words + BOW_WARPS * BOW_WARP_WORDS) * 4;
     cudaFuncSetAttribute(bow_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    bow_match_kernel<<<(n_pairs + 3) / 4, 128, smem, s>>>(qs, ts, n_pairs, mode, nnratio, check_ori, match, out_stride, bins, n_matches, max_t);
+    bow_match_kernel<<<n_pairs, 32 * BOW_WARPS, smem, s>>>(qs, ts, n_pairs, mode, nnratio, check_ori, match, out_stride, bins, n_matches, max_t);
     return 1;
 }
 int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,

@@ -3,7 +3,8 @@
    config 4: EuRoC-shaped 752x480 @1200 features, loop-closure / relocalisation against a 2000-keyframe database:
              one KeyFrameDatabase query (shared words + L1 score for all keyframes) and SearchByBoW against all
              2000 resident keyframes.
-All times are wall-clock around the public Python call (host buffers in, results out), median of `--reps`.
+All times are wall-clock around the public Python call (host buffers in, results out), median of `--reps`, taken right
+after a burst of extraction work so that the SM clocks are where a running tracker keeps them.
 usage: python tools/bench_configs.py [--kfs 2000] [--reps 20]  -> one JSON line per config on stdout."""
 import argparse
 import json
@@ -18,8 +19,23 @@ from orb_slam2_b200 import matcher as M, sharding, synth                      # 
 from orb_slam2_b200.extractor import ORBextractor                              # noqa: E402
 
 
+_WARM = {}
+
+
+def warm_clocks(seconds=0.4):
+    """A lightly loaded GPU idles at low SM clocks, which would inflate every us-scale number below; in the tracker the
+    extractor keeps the clocks up.  Run extraction work for a moment right before a timed block."""
+    if "x" not in _WARM:
+        _WARM["x"] = ORBextractor(2000)
+        _WARM["imgs"] = [synth.mono_frame(9, 0, i, *synth.KITTI) for i in range(16)]
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        _WARM["x"].extract_batch(_WARM["imgs"])
+
+
 def med(f, reps):
     f()
+    warm_clocks()
     t = []
     for _ in range(reps):
         t0 = time.perf_counter(); f(); t.append(time.perf_counter() - t0)
@@ -40,8 +56,17 @@ def config2(reps):
     n, _ = mt.SearchByProjection(F, mps, 3.0)
     t_match = med(lambda: mt.SearchByProjection(F, mps, 3.0), reps)
     t_ext = med(lambda: X(img1), reps)
+    # motion-model tracking: every feature of the last frame carries a MapPoint (SearchByProjection(CurrentFrame, LastFrame))
+    K = (525.0, 525.0, 319.5, 239.5)
+    z = rng.uniform(2.0, 20.0, len(k0)).astype(np.float32)
+    Pw = np.stack([(k0["x"] - K[2]) * z / K[0], (k0["y"] - K[3]) * z / K[1], z], 1).astype(np.float32)
+    Last = M.LastFrameView(mvKeysUn=k0, world_pos=Pw, descriptors=d0)
+    Tcw = np.eye(4, dtype=np.float32)[:3]
+    nl, _ = mt.SearchByProjectionLast(F, Last, Tcw, K, 40.0, 7.0)
+    t_last = med(lambda: mt.SearchByProjectionLast(F, Last, Tcw, K, 40.0, 7.0), reps)
     return {"config": "configs[2]: TUM-shaped 640x480 @1000, extract + SearchByProjection vs 300 local MapPoints", "matches": int(n),
-            "extract_ms": t_ext * 1e3, "search_by_projection_us": t_match * 1e6, "frames_per_s_serial": 1.0 / (t_ext + t_match)}
+            "extract_ms": t_ext * 1e3, "search_by_projection_us": t_match * 1e6, "frames_per_s_serial": 1.0 / (t_ext + t_match),
+            "search_by_projection_last_frame_us": t_last * 1e6, "last_frame_queries": int(len(k0)), "last_frame_matches": int(nl)}
 
 
 def config4(n_kf, reps):
