@@ -118,6 +118,13 @@ BORB_API borb_status borb_extract_batch_device(borb_extractor* e, const uint8_t*
                                       size_t pitch, size_t image_stride, borb_keypoint* kps, uint8_t* desc, int cap,
                                       int* n_out);
 
+/* Pixel format of the HOST images given to the extract / stereo entry points of this handle (default 1 = CV_8UC1).
+ * With 3 or 4 channels the conversion Tracking::GrabImageStereo/RGBD/Monocular performs before calling the extractor —
+ * cv::cvtColor(RGB2GRAY | BGR2GRAY | RGBA2GRAY | BGRA2GRAY), src/Tracking.cc:172-197,211-223,243-255 — is fused into the
+ * upload: only the raw camera frame crosses PCIe.  rgb_order = Tracking::mbRGB (1: R first, 0: B first).
+ * `stride` arguments are then bytes per row of the interleaved image. */
+BORB_API borb_status borb_extractor_set_input_format(borb_extractor* e, int channels, int rgb_order);
+
 /* mvImagePyramid[level] of image `image` of the last batch (include/ORBextractor.h:85), copied to
  * a caller buffer of at least h*w bytes (tight rows).  Pass dst=NULL to query w/h only. */
 BORB_API borb_status borb_extractor_pyramid(borb_extractor* e, int image, int level, uint8_t* dst, int* w, int* h);
@@ -279,6 +286,19 @@ BORB_API borb_status borb_search_by_sim3(borb_matcher* m, const borb_frame_view*
                                          const float* T2w, const float* S12, const float* S21, float fx, float fy, float cx, float cy,
                                          float log_scale_factor1, float log_scale_factor2, float th, int32_t* match12,
                                          int32_t* n_found);
+
+/* Tracking::SearchLocalPoints (src/Tracking.cc:1148-1194) in one call: Frame::isInFrustum (src/Frame.cc:269-325) for every
+ * candidate MapPoint, then ORBmatcher::SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:45-129) on those in view —
+ * the projections never leave the device.  pts->valid[i] = the point reaches isInFrustum (:1171-1175: not already matched
+ * in this frame, not bad); has_obs[i] = Observations()>0 (NULL: all).  Tcw = [mRcw | mtcw], Ow = mOw, mbf, log_scale_factor =
+ * Frame members; viewing_cos_limit = 0.5 at the call site.  in_view[i] = mbTrackInView (the caller runs IncreaseVisible on
+ * it); proj_x/proj_y/proj_xr/level/view_cos (each may be NULL) = mTrackProjX/Y/XR, mnTrackScaleLevel, mTrackViewCos
+ * (0 where not in view); match_feat / n_matches as in borb_search_by_projection. */
+BORB_API borb_status borb_search_local_points(borb_matcher* m, const borb_frame_view* frame, const borb_worldpoints_view* pts,
+                                              const uint8_t* has_obs, const float* Tcw, const float* Ow, float fx, float fy, float cx,
+                                              float cy, float mbf, float viewing_cos_limit, float log_scale_factor, float th,
+                                              float nnratio, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr,
+                                              int32_t* level, float* view_cos, int32_t* match_feat, int32_t* n_matches);
 
 /* ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12,
  * int windowSize) — src/ORBmatcher.cc:405-520 (Tracking::MonocularInitialization, src/Tracking.cc:599).

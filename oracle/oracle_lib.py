@@ -409,6 +409,24 @@ def port_detect_reloc_candidates(kf_bows, n_words, q_bow, neigh):
     return out[:n].copy()
 
 
+def port_is_in_frustum(F, P, Tcw, Ow, K, mbf, viewing_cos_limit=0.5):
+    """Frame::isInFrustum (Frame.cc:269-325) for every point of P; returns dict of the MapPoint track fields."""
+    lib = _plib()
+    wp, md, mx, mn, va = _points_args(P)
+    nr = _a(P.normal, np.float32)
+    T = _a(np.asarray(Tcw, np.float32)[:3, :4].reshape(12), np.float32); ow = _a(np.asarray(Ow, np.float32).reshape(3), np.float32)
+    n = len(wp)
+    inv = np.zeros(max(n, 1), np.uint8); px = np.zeros(max(n, 1), np.float32); py = np.zeros(max(n, 1), np.float32)
+    pxr = np.zeros(max(n, 1), np.float32); lv = np.zeros(max(n, 1), np.int32); vc = np.zeros(max(n, 1), np.float32)
+    fn = lib.orbport_is_in_frustum
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p] + [C.c_float] * 11 + [C.c_int] + [C.c_void_p] * 6
+    cnt = fn(_ptr(wp), _ptr(nr), _ptr(mx), _ptr(mn), _ptr(va), n, _ptr(T), _ptr(ow), float(K[0]), float(K[1]), float(K[2]), float(K[3]),
+             float(mbf), *[float(b) for b in F.bounds], float(viewing_cos_limit), _log_scale(F), len(F.mvScaleFactors), _ptr(inv), _ptr(px),
+             _ptr(py), _ptr(pxr), _ptr(lv), _ptr(vc))
+    return dict(count=cnt, in_view=inv[:n], proj_x=px[:n], proj_y=py[:n], proj_xr=pxr[:n], level=lv[:n], view_cos=vc[:n])
+
+
 def _kf_args(kf):
     k = _a(kf.mvKeysUn, KP_DTYPE); d = _a(kf.mDescriptors, np.uint8)
     hm = _a(kf.has_mp, np.uint8) if kf.has_mp is not None else np.zeros(len(k), np.uint8)

@@ -943,3 +943,45 @@ extern "C" int orbport_detect_reloc_candidates(int n_kf, const int32_t* kf_start
     }
     return n_out;
 }
+
+// Frame::isInFrustum — reference src/Frame.cc:269-325, for n MapPoints (Tracking::SearchLocalPoints, src/Tracking.cc:1167-1180).
+// Tcw = [mRcw | mtcw], Ow = mOw.  Outputs are the fields the reference stores on the MapPoint: mbTrackInView,
+// mTrackProjX, mTrackProjY, mTrackProjXR, mnTrackScaleLevel, mTrackViewCos (untouched where in_view = 0).
+extern "C" int orbport_is_in_frustum(const float* world_pos, const float* normal, const float* max_distance, const float* min_distance,
+                                     const uint8_t* valid, int n, const float* Tcw, const float* Ow, float fx, float fy, float cx,
+                                     float cy, float mbf, float minX, float minY, float maxX, float maxY, float viewingCosLimit,
+                                     float log_scale_factor, int n_levels, uint8_t* in_view, float* proj_x, float* proj_y,
+                                     float* proj_xr, int32_t* level, float* view_cos) {
+    int count = 0;
+    for (int i = 0; i < n; i++) {
+        in_view[i] = 0;
+        if (valid && !valid[i]) continue;
+        const float* P = world_pos + 3 * (size_t)i;
+        const float PcX = ((Tcw[0] * P[0] + Tcw[1] * P[1]) + Tcw[2] * P[2]) + Tcw[3];
+        const float PcY = ((Tcw[4] * P[0] + Tcw[5] * P[1]) + Tcw[6] * P[2]) + Tcw[7];
+        const float PcZ = ((Tcw[8] * P[0] + Tcw[9] * P[1]) + Tcw[10] * P[2]) + Tcw[11];
+        if (PcZ < 0.0f) continue;
+        const float invz = 1.0f / PcZ;
+        const float u = fx * PcX * invz + cx;
+        const float v = fy * PcY * invz + cy;
+        if (u < minX || u > maxX) continue;
+        if (v < minY || v > maxY) continue;
+        if (!(u == u) || !(v == v)) continue;              // NaN (PcZ == 0): the reference would go on with undefined grid cells
+        const float maxDistance = 1.2f * max_distance[i];
+        const float minDistance = 0.8f * min_distance[i];
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        const float dist = norm3(PO);
+        if (dist < minDistance || dist > maxDistance) continue;
+        const float viewCos = dot3(PO, normal + 3 * (size_t)i) / dist;
+        if (viewCos < viewingCosLimit) continue;
+        const int nPredictedLevel = predict_scale(max_distance[i], dist, log_scale_factor, n_levels);
+        in_view[i] = 1;
+        proj_x[i] = u;
+        proj_xr[i] = u - mbf * invz;
+        proj_y[i] = v;
+        level[i] = nPredictedLevel;
+        view_cos[i] = viewCos;
+        count++;
+    }
+    return count;
+}

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "borb_stage_times_total": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "borb_extractor_stream": (C.c_int, [vp, C.POINTER(vp)]),
     "borb_matcher_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "borb_extractor_set_input_format": (C.c_int, [vp, C.c_int, C.c_int]),
     "borb_matcher_destroy": (C.c_int, [vp]),
     "borb_search_by_projection": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, vp, i32p]),
     "borb_search_by_projection_last": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -88,6 +89,7 @@ _SIGNATURES = {
     "borb_kfdb_size": (C.c_int, [vp, i32p, C.POINTER(C.c_uint64)]),
     "borb_kfdb_query": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, i32p]),
     "borb_search_by_bow_db": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_float, C.c_int, vp, vp]),
+    "borb_search_local_points": (C.c_int, [vp, vp, vp, vp, vp, vp] + [C.c_float] * 9 + [vp] * 7 + [i32p]),
     "borb_fuse": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                             vp, i32p]),
     "borb_search_by_sim3": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

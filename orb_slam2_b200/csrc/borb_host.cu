@@ -312,14 +312,15 @@ borb_status enqueue_extract(borb_extractor* e, int n) {
 // packed landing buffer and a kernel re-pitches them; otherwise one 2-D copy per image.
 borb_status upload_slots(borb_extractor* e, const uint8_t* const* slots, int n, int w, int h, int stride) {
     const Geometry& g = e->geom;
+    const int ch = e->in_channels;
+    if (stride < w * ch) { set_error("stride %d smaller than a row of %d %d-channel pixels", stride, w, ch); return BORB_ERR_INVALID_ARG; }
     const size_t img_bytes = (size_t)stride * h;
-    bool contiguous = n > 1;
+    bool contiguous = n > 1 || ch > 1;
     for (int k = 0; k < n; k++) {
         if (!slots[k]) { set_error("image %d is NULL", k); return BORB_ERR_INVALID_ARG; }
         if (slots[k] != slots[0] + (size_t)k * img_bytes) contiguous = false;
     }
-    if (contiguous) {
-        const size_t need = img_bytes * n;
+    auto need_stage = [&](size_t need) -> borb_status {
         if (e->ws.stage_bytes < need) {
             BORB_CUDA(cudaStreamSynchronize(e->stream));
             cudaFree(e->ws.stage);
@@ -327,8 +328,24 @@ borb_status upload_slots(borb_extractor* e, const uint8_t* const* slots, int n, 
             BORB_CUDA(cudaMalloc(&e->ws.stage, need));
             e->ws.stage_bytes = need;
         }
+        return BORB_OK;
+    };
+    if (contiguous) {
+        const size_t need = img_bytes * n;
+        borb_status st = need_stage(need);
+        if (st != BORB_OK) return st;
         BORB_CUDA(cudaMemcpyAsync(e->ws.stage, slots[0], need, cudaMemcpyHostToDevice, e->stream));
-        e->launches += launch_repack(g, e->ws, e->ws.stage, stride, img_bytes, n, e->stream);
+        if (ch == 1) e->launches += launch_repack(g, e->ws, e->ws.stage, stride, img_bytes, n, e->stream);
+        else e->launches += launch_repack_color(g, e->ws, e->ws.stage, stride, img_bytes, ch, e->in_rgb, n, e->stream);
+        return BORB_OK;
+    }
+    if (ch > 1) {                       // scattered colour images: packed landing rows, then the converting re-pitch
+        const size_t row = (size_t)w * ch;
+        borb_status st = need_stage(row * h * n);
+        if (st != BORB_OK) return st;
+        for (int k = 0; k < n; k++)
+            BORB_CUDA(cudaMemcpy2DAsync(e->ws.stage + (size_t)k * row * h, row, slots[k], stride, row, h, cudaMemcpyHostToDevice, e->stream));
+        e->launches += launch_repack_color(g, e->ws, e->ws.stage, (int)row, row * h, ch, e->in_rgb, n, e->stream);
         return BORB_OK;
     }
     for (int k = 0; k < n; k++) {
@@ -596,6 +613,14 @@ borb_status borb_extract_batch_device(borb_extractor* e, const uint8_t* d_gray, 
     if ((st = download_kps(e, 0, n, 1, kps, desc, cap, n_out)) != BORB_OK) return st;
     mark(e, 8);
     return borb_sync(e);
+}
+
+borb_status borb_extractor_set_input_format(borb_extractor* e, int channels, int rgb_order) {
+    if (!e) { set_error("null handle"); return BORB_ERR_INVALID_ARG; }
+    if (channels != 1 && channels != 3 && channels != 4) { set_error("channels must be 1, 3 or 4 (CV_8UC1 / C3 / C4)"); return BORB_ERR_INVALID_ARG; }
+    e->in_channels = channels;
+    e->in_rgb = rgb_order ? 1 : 0;
+    return BORB_OK;
 }
 
 borb_status borb_extractor_pyramid(borb_extractor* e, int image, int level, uint8_t* dst, int* w, int* h) {

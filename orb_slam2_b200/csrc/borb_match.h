@@ -42,6 +42,10 @@ struct ProjArgs {                 // device pointers
 
 struct LastArgs {                 // inputs of project_points_kernel
     int variant;                  // 0: (CurrentFrame, LastFrame) :1328   1: (CurrentFrame, KeyFrame) :1472   2: (KeyFrame, Scw) :290
+                                  // 3: Frame::isInFrustum (src/Frame.cc:269-325), feeding SearchByProjection(F, vpMapPoints)
+    float view_cos_limit;         // variant 3
+    int32_t* level_out;           // variant 3: mnTrackScaleLevel
+    float* viewcos_out;           // variant 3: mTrackViewCos
     int n_last;
     const borb_keypoint* last_keys;   // variant 0 only (octave, angle of the last-frame feature)
     const float* q_angle_in;      // variant 1: angle of the observing keyframe feature (may be null)
@@ -108,6 +112,7 @@ int launch_initialization(const ProjArgs& A, const borb_keypoint* keys1, int n1,
 int launch_kfdb_score(const BowDev* table, int n_slots, const uint32_t* qword, const double* qvalue, int nq, int32_t* common, float* score,
                       uint32_t* first_word, cudaStream_t s);
 int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx, cudaStream_t s);
+int launch_frustum_projection(const LastArgs& L, const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s);
 int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best_idx, int* n_found, cudaStream_t s);
 int launch_sim3_agree(const int32_t* match1, const int32_t* match2, int n1, int n2, int32_t* match12, int* n_found, cudaStream_t s);
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,

@@ -467,6 +467,93 @@ borb_status borb_search_by_sim3(borb_matcher* m, const borb_frame_view* kf1, con
     return BORB_OK;
 }
 
+borb_status borb_search_local_points(borb_matcher* m, const borb_frame_view* F, const borb_worldpoints_view* pts, const uint8_t* has_obs,
+                                     const float* Tcw, const float* Ow, float fx, float fy, float cx, float cy, float mbf,
+                                     float viewing_cos_limit, float log_scale_factor, float th, float nnratio, uint8_t* in_view,
+                                     float* proj_x, float* proj_y, float* proj_xr, int32_t* level, float* view_cos,
+                                     int32_t* match_feat, int32_t* n_matches) {
+    if (!m || !F || !pts || !Tcw || !Ow || !in_view || !match_feat || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *n_matches = 0;
+    const int nq = pts->n;
+    if (F->n < 0 || F->n > MATCH_MAX_FEATURES || nq < 0 || nq > MATCH_MAX_FEATURES) { set_error("feature count outside [0,%d]", MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    for (int i = 0; i < nq; i++) { in_view[i] = 0; match_feat[i] = -1; }
+    if (nq == 0) return BORB_OK;
+    if (!pts->world_pos || !pts->desc || !pts->max_distance || !pts->min_distance || !pts->normal) { set_error("incomplete world-points view"); return BORB_ERR_INVALID_ARG; }
+    if (F->n_levels < 1 || !F->scale_factors || !(F->max_x > F->min_x) || !(F->max_y > F->min_y) || (F->n > 0 && (!F->keys_un || !F->desc))) {
+        set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG;
+    }
+    if (!(log_scale_factor > 0.f)) { set_error("log_scale_factor must be positive (Frame::mfLogScaleFactor)"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(m->device));
+    Stager st(m);
+    const int nf = F->n > 0 ? F->n : 1;
+    const size_t o_keys = st.add(F->keys_un, (size_t)F->n * sizeof(borb_keypoint));
+    const size_t o_desc = st.add(F->desc, (size_t)F->n * 32);
+    const size_t o_ur = F->u_right ? st.add(F->u_right, (size_t)F->n * 4) : 0;
+    const size_t o_occ = F->occupied ? st.add(F->occupied, (size_t)F->n) : 0;
+    const size_t o_sf = st.add(F->scale_factors, (size_t)F->n_levels * 4);
+    const size_t o_wp = st.add(pts->world_pos, (size_t)nq * 12), o_md = st.add(pts->desc, (size_t)nq * 32);
+    const size_t o_vin = pts->valid ? st.add(pts->valid, (size_t)nq) : 0;
+    const size_t o_obs = has_obs ? st.add(has_obs, (size_t)nq) : 0;
+    const size_t o_mx = st.add(pts->max_distance, (size_t)nq * 4), o_mn = st.add(pts->min_distance, (size_t)nq * 4);
+    const size_t o_nr = st.add(pts->normal, (size_t)nq * 12);
+    const size_t input_end = st.off;
+    const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
+    const size_t o_px = st.reserve((size_t)nq * 4), o_py = st.reserve((size_t)nq * 4), o_pxr = st.reserve((size_t)nq * 4), o_rad = st.reserve((size_t)nq * 4);
+    const size_t o_ang = st.reserve((size_t)nq * 4), o_minl = st.reserve((size_t)nq * 4), o_maxl = st.reserve((size_t)nq * 4), o_val = st.reserve((size_t)nq);
+    const size_t o_lvl = st.reserve((size_t)nq * 4), o_vc = st.reserve((size_t)nq * 4);
+    const size_t o_cand = st.reserve((size_t)nq * nf * 4), o_cc = st.reserve((size_t)nq * 4);
+    const size_t o_match = st.reserve((size_t)nq * 4), o_nm = st.reserve(16);
+    const size_t total = st.off;
+    st.off = input_end;
+    borb_status s = commit(st, total);
+    if (s != BORB_OK) return s;
+    uint8_t* b = m->arena;
+    BORB_CUDA(cudaMemsetAsync(b + o_lvl, 0, (size_t)nq * 4, m->stream));       // fields of points outside the frustum read as 0
+    BORB_CUDA(cudaMemsetAsync(b + o_vc, 0, (size_t)nq * 4, m->stream));
+    LastArgs L{};
+    L.variant = 3; L.n_last = nq; L.world_pos = (const float*)(b + o_wp);
+    L.max_distance = (const float*)(b + o_mx); L.min_distance = (const float*)(b + o_mn); L.normal = (const float*)(b + o_nr);
+    for (int i = 0; i < 3; i++) L.Ow[i] = Ow[i];
+    L.log_scale = log_scale_factor; L.n_levels = F->n_levels; L.view_cos_limit = viewing_cos_limit;
+    L.valid_in = pts->valid ? b + o_vin : nullptr;
+    for (int i = 0; i < 12; i++) L.T[i] = Tcw[i];
+    L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.bf = mbf; L.th = th;
+    L.minX = F->min_x; L.minY = F->min_y; L.maxX = F->max_x; L.maxY = F->max_y;
+    L.scale_factors = (const float*)(b + o_sf);
+    L.proj_x = (float*)(b + o_px); L.proj_y = (float*)(b + o_py); L.proj_xr = (float*)(b + o_pxr); L.radius = (float*)(b + o_rad);
+    L.angle = (float*)(b + o_ang); L.minl = (int32_t*)(b + o_minl); L.maxl = (int32_t*)(b + o_maxl); L.valid_out = b + o_val;
+    L.level_out = (int32_t*)(b + o_lvl); L.viewcos_out = (float*)(b + o_vc);
+    ProjArgs A{};
+    A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
+    A.u_right = F->u_right ? (const float*)(b + o_ur) : nullptr;
+    A.occupied = F->occupied ? b + o_occ : nullptr;
+    A.minX = F->min_x; A.minY = F->min_y;
+    A.invW = (float)GRID_COLS / (float)(F->max_x - F->min_x);
+    A.invH = (float)GRID_ROWS / (float)(F->max_y - F->min_y);
+    A.scale_factors = (const float*)(b + o_sf);
+    A.cell_start = (const int*)(b + o_cs); A.cell_idx = (const int*)(b + o_ci);
+    A.n_mp = nq; A.proj_x = L.proj_x; A.proj_y = L.proj_y; A.proj_xr = L.proj_xr; A.view_cos = L.viewcos_out; A.level = L.level_out;
+    A.mp_desc = b + o_md; A.mp_valid = b + o_val; A.mp_has_obs = has_obs ? b + o_obs : nullptr;
+    A.th = th; A.nnratio = nnratio;
+    A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
+    A.mode = 0;
+    if (F->n > 0) m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
+    else BORB_CUDA(cudaMemsetAsync(b + o_cs, 0, (size_t)(GRID_CELLS + 1) * 4, m->stream));
+    m->launches += launch_frustum_projection(L, A, (int32_t*)(b + o_match), (int*)(b + o_nm), m->stream);
+    BORB_CUDA(cudaGetLastError());
+    cudaStream_t q = m->stream;
+    BORB_CUDA(cudaMemcpyAsync(in_view, b + o_val, (size_t)nq, cudaMemcpyDeviceToHost, q));
+    if (proj_x) BORB_CUDA(cudaMemcpyAsync(proj_x, b + o_px, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
+    if (proj_y) BORB_CUDA(cudaMemcpyAsync(proj_y, b + o_py, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
+    if (proj_xr) BORB_CUDA(cudaMemcpyAsync(proj_xr, b + o_pxr, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
+    if (level) BORB_CUDA(cudaMemcpyAsync(level, b + o_lvl, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
+    if (view_cos) BORB_CUDA(cudaMemcpyAsync(view_cos, b + o_vc, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
+    BORB_CUDA(cudaMemcpyAsync(match_feat, b + o_match, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
+    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, q));
+    BORB_CUDA(cudaStreamSynchronize(q));
+    return BORB_OK;
+}
+
 borb_status borb_search_for_initialization(borb_matcher* m, const borb_frame_view* f1, const borb_frame_view* f2, float* prev_matched,
                                            int window_size, float nnratio, int check_orientation, int32_t* matches12, int32_t* n_matches) {
     if (!m || !f1 || !f2 || !prev_matched || !matches12 || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }

@@ -417,7 +417,15 @@ __global__ void __launch_bounds__(256) project_points_kernel(LastArgs L) {
             q1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T2[4], xc), __fmul_rn(L.T2[5], yc)), __fmul_rn(L.T2[6], zc)), L.T2[7]);
             q2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(L.T2[8], xc), __fmul_rn(L.T2[9], yc)), __fmul_rn(L.T2[10], zc)), L.T2[11]);
         }
-        if (L.variant == 2) {
+        if (L.variant == 3) {                                                 // Frame::isInFrustum (src/Frame.cc:269-325)
+            if (zc < 0.0f) ok = false;
+            const float invz = __fdiv_rn(1.0f, zc);                           // 1.0f/PcZ (:286)
+            u = __fadd_rn(__fmul_rn(__fmul_rn(L.fx, xc), invz), L.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(L.fy, yc), invz), L.cy);
+            if (u < L.minX || u > L.maxX || v < L.minY || v > L.maxY) ok = false;
+            if (!(u == u) || !(v == v)) ok = false;
+            ur = __fsub_rn(u, __fmul_rn(L.bf, invz));                         // mTrackProjXR (:319)
+        } else if (L.variant == 2) {
             if (q2 < 0.0f) ok = false;                                        // depth must be positive (:329-330)
             const float invz = L.invz_double ? (float)(1.0 / (double)q2) : __fdiv_rn(1.0f, q2);   // (:1014,:1164) / (:333,:861)
             const float x = __fmul_rn(q0, invz), y = __fmul_rn(q1, invz);
@@ -455,15 +463,24 @@ __global__ void __launch_bounds__(256) project_points_kernel(LastArgs L) {
                 const double dot = __dadd_rn(__dadd_rn(__dmul_rn(d0, (double)N[0]), __dmul_rn(d1, (double)N[1])), __dmul_rn(d2, (double)N[2]));
                 if (dot < __dmul_rn(0.5, (double)dist)) ok = false;
             }
+            float vcos = 0.f;
+            if (ok && L.variant == 3) {                                       // viewCos = PO.dot(Pn)/dist (:305-308)
+                const float* N = L.normal + 3 * (size_t)i;
+                const double dot = __dadd_rn(__dadd_rn(__dmul_rn(d0, (double)N[0]), __dmul_rn(d1, (double)N[1])), __dmul_rn(d2, (double)N[2]));
+                vcos = (float)__ddiv_rn(dot, (double)dist);
+                if (vcos < L.view_cos_limit) ok = false;
+            }
             if (ok) {
                 const int lvl = predict_scale(mx, dist, L.log_scale, L.n_levels);
                 radius = __fmul_rn(L.th, L.scale_factors[lvl]);
                 minl = lvl - 1;
                 maxl = L.variant == 1 ? lvl + 1 : lvl;
+                if (L.variant == 3) { L.level_out[i] = lvl; L.viewcos_out[i] = vcos; }
             }
             ang = L.q_angle_in != nullptr ? L.q_angle_in[i] : 0.f;
         }
     }
+    if (L.variant == 3 && !ok) { u = 0.f; v = 0.f; ur = 0.f; }              // the MapPoint's track fields stay untouched (reported as 0)
     L.proj_x[i] = u; L.proj_y[i] = v; L.proj_xr[i] = ur; L.radius[i] = radius; L.minl[i] = minl; L.maxl[i] = maxl;
     L.angle[i] = ang;
     L.valid_out[i] = ok ? 1 : 0;
@@ -1023,6 +1040,10 @@ int launch_kfdb_score(const BowDev* table, int n_slots, const uint32_t* qword, c
 int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx, cudaStream_t s) {
     if (n_points > 0) distinctive_kernel<<<(n_points + 3) / 4, 128, 0, s>>>(desc, offsets, n_points, best_idx);
     return 1;
+}
+int launch_frustum_projection(const LastArgs& L, const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s) {
+    if (L.n_last > 0) project_points_kernel<<<(L.n_last + 255) / 256, 256, 0, s>>>(L);
+    return 1 + launch_projection(A, match_feat, n_matches, s);
 }
 int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best_idx, int* n_found, cudaStream_t s) {
     cudaMemsetAsync(n_found, 0, sizeof(int), s);

@@ -105,6 +105,29 @@ __global__ void __launch_bounds__(256) repack_kernel(const uint8_t* __restrict__
     *reinterpret_cast<uint32_t*>(pyr + (size_t)img * image_stride + l0.pyr_off + (size_t)y * l0.pitch + x0) = v;
 }
 
+// Colour input: Tracking::GrabImage* convert with cv::cvtColor(RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY) before the
+// extractor is called (reference src/Tracking.cc:172-197, 211-223, 243-255).  Fused into the re-pitch of the upload;
+// OpenCV 4.13 8-bit semantics (checked exhaustively over all 2^24 colours against cv2):
+//   Y = (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+__global__ void __launch_bounds__(256) repack_color_kernel(const uint8_t* __restrict__ stage, int src_stride, size_t src_image_bytes,
+                                                           int channels, int rgb, uint8_t* __restrict__ pyr, LevelGeom l0,
+                                                           unsigned image_stride) {
+    const int img = blockIdx.z, y = blockIdx.y;
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x0 >= l0.w) return;
+    const uint8_t* S = stage + (size_t)img * src_image_bytes + (size_t)y * src_stride + (size_t)x0 * channels;
+    const int cr = rgb ? 9798 : 3735, cb = rgb ? 3735 : 9798;      // weight of channel 0 / channel 2
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (x0 + i < l0.w) {
+            const uint8_t* px = S + i * channels;
+            const int yv = (px[0] * cr + px[1] * 19235 + px[2] * cb + 16384) >> 15;
+            v |= (uint32_t)yv << (8 * i);
+        }
+    *reinterpret_cast<uint32_t*>(pyr + (size_t)img * image_stride + l0.pyr_off + (size_t)y * l0.pitch + x0) = v;
+}
+
 // reflect-101 padding of level 0 (columns w .. w+7 = columns w-2 .. w-9), after any kind of upload
 __global__ void __launch_bounds__(256) pad_level0_kernel(uint8_t* __restrict__ pyr, LevelGeom l0, unsigned image_stride) {
     const int y = blockIdx.x * 256 + threadIdx.x, img = blockIdx.y;
@@ -122,6 +145,13 @@ int launch_repack(const Geometry& g, const Workspace& ws, const uint8_t* stage, 
 }
 
 constexpr int PYR_ROWS = 2;
+
+int launch_repack_color(const Geometry& g, const Workspace& ws, const uint8_t* stage, int src_stride, size_t src_image_bytes, int channels,
+                        int rgb, int n_images, cudaStream_t s) {
+    dim3 grid((g.lv[0].w + 1023) / 1024, g.lv[0].h, n_images);
+    repack_color_kernel<<<grid, 256, 0, s>>>(stage, src_stride, src_image_bytes, channels, rgb, ws.pyr, g.lv[0], g.pyr_image_stride);
+    return 1;
+}
 
 int launch_pyramid(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s) {
     int launches = 0;

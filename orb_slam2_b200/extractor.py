@@ -74,13 +74,27 @@ class ORBextractor:
         check(self._lib.borb_extractor_reserve(self._h, width, height, max_images), "borb_extractor_reserve")
 
     # ---- operator() (ORBextractor.cc:1043): image -> (keypoints[N] KP_DTYPE, descriptors[N,32] u8)
+    def set_input_format(self, channels: int, mbRGB: bool = True) -> None:
+        """Colour frames (H, W, 3|4) are converted to gray on the GPU exactly as Tracking::GrabImage* does with cv::cvtColor
+        (src/Tracking.cc:172-197); mbRGB = Camera.RGB of the settings file (1: RGB order, 0: BGR)."""
+        self.mbRGB = bool(mbRGB)
+        self._set_format(channels)
+
+    def _set_format(self, channels: int) -> None:
+        key = (int(channels), bool(getattr(self, "mbRGB", True)))
+        if getattr(self, "_fmt", (1, True)) != key:
+            check(self._lib.borb_extractor_set_input_format(self._h, key[0], int(key[1])), "borb_extractor_set_input_format")
+            self._fmt = key
+
     def __call__(self, image: np.ndarray, mask=None) -> Tuple[np.ndarray, np.ndarray]:
         if image is None or image.size == 0:
             return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
-        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:1050)"
-        if image.strides[1] != 1:
+        assert image.dtype == np.uint8 and image.ndim in (2, 3), "CV_8UC1 expected (ORBextractor.cc:1050); 3/4 channels: see set_input_format"
+        ch = 1 if image.ndim == 2 else image.shape[2]
+        self._set_format(ch)
+        if image.strides[-1] != 1 or (ch > 1 and image.strides[1] != ch):
             image = np.ascontiguousarray(image)
-        h, w = image.shape
+        h, w = image.shape[:2]
         cap = self.capacity(w, h)
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
@@ -95,8 +109,9 @@ class ORBextractor:
         if n == 0:
             return []
         images = [np.ascontiguousarray(im, np.uint8) for im in images]
-        h, w = images[0].shape
-        assert all(im.shape == (h, w) for im in images), "a batch holds images of one size"
+        h, w = images[0].shape[:2]
+        assert all(im.shape == images[0].shape for im in images), "a batch holds images of one size"
+        self._set_format(1 if images[0].ndim == 2 else images[0].shape[2])
         cap = self.capacity(w, h)
         kps = np.zeros((n, cap), KP_DTYPE)
         desc = np.zeros((n, cap, 32), np.uint8)

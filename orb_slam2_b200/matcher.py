@@ -273,6 +273,29 @@ class ORBmatcher:
                                                        float(K[3]), logs, int(th), _p(state), C.byref(nm)), "borb_search_by_projection_sim3")
         return nm.value, state[:n]
 
+    def SearchLocalPoints(self, F: FrameView, P: WorldPointsView, Tcw: np.ndarray, Ow: np.ndarray, K: Tuple[float, float, float, float],
+                          mbf: float, th: float = 1.0, has_obs: Optional[np.ndarray] = None, viewingCosLimit: float = 0.5):
+        """Tracking::SearchLocalPoints (src/Tracking.cc:1148-1194): Frame::isInFrustum for every point of P, then
+        SearchByProjection(F, vpMapPoints, th) on those in view, in one call.  Returns a dict with in_view, the MapPoint track
+        fields (proj_x, proj_y, proj_xr, level, view_cos), match (feature per point or -1) and nmatches."""
+        fv, pv, logs, n, keep = self._points_call(F, P, with_stereo=True)
+        T = np.ascontiguousarray(np.asarray(Tcw, np.float32)[:3, :4]).reshape(12)
+        ow = np.ascontiguousarray(np.asarray(Ow, np.float32).reshape(3))
+        ho = np.ascontiguousarray(has_obs, np.uint8) if has_obs is not None else None
+        nq = len(P.world_pos)
+        m1 = max(nq, 1)
+        out = dict(in_view=np.zeros(m1, np.uint8), proj_x=np.zeros(m1, np.float32), proj_y=np.zeros(m1, np.float32),
+                   proj_xr=np.zeros(m1, np.float32), level=np.zeros(m1, np.int32), view_cos=np.zeros(m1, np.float32),
+                   match=np.full(m1, -1, np.int32))
+        nm = C.c_int32(0)
+        check(self._lib.borb_search_local_points(self._h, C.byref(fv), C.byref(pv), _p(ho), _p(T), _p(ow), float(K[0]), float(K[1]), float(K[2]),
+                                                 float(K[3]), float(mbf), float(viewingCosLimit), logs, float(th), self.mfNNratio,
+                                                 _p(out["in_view"]), _p(out["proj_x"]), _p(out["proj_y"]), _p(out["proj_xr"]), _p(out["level"]),
+                                                 _p(out["view_cos"]), _p(out["match"]), C.byref(nm)), "borb_search_local_points")
+        out = {k: v[:nq] for k, v in out.items()}
+        out["nmatches"] = nm.value
+        return out
+
     def SearchForInitialization(self, F1: FrameView, F2: FrameView, vbPrevMatched: np.ndarray, windowSize: int = 10):
         """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — src/ORBmatcher.cc:405-520.
         Returns (nmatches, vnMatches12[F1.N], updated vbPrevMatched (N,2))."""

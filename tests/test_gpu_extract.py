@@ -179,3 +179,30 @@ def test_full_size_properties(X):
     # flipping the image left-right changes the keypoints (sanity: results depend on the input)
     kf, _ = G(imgs[0][:, ::-1].copy())
     assert not np.array_equal(kf["x"][:50], res[0][0]["x"][:50])
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_colour_input_is_converted_like_cvtcolor(X, channels, rgb):
+    """Tracking::GrabImage* call cv::cvtColor(RGB2GRAY/BGR2GRAY/RGBA2GRAY/BGRA2GRAY) first (src/Tracking.cc:172-197);
+    the conversion is fused into the upload.  Level 0 must equal cv2's gray image, the keypoints those of the gray path."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    gray = synth.mono_frame(71, 0, 0, 640, 480)
+    col = np.stack([np.clip(gray.astype(np.int32) + rng.integers(-40, 41, gray.shape), 0, 255).astype(np.uint8) for _ in range(channels)], 2)
+    code = {(3, True): cv2.COLOR_RGB2GRAY, (3, False): cv2.COLOR_BGR2GRAY, (4, True): cv2.COLOR_RGBA2GRAY, (4, False): cv2.COLOR_BGRA2GRAY}[(channels, rgb)]
+    want = cv2.cvtColor(col, code)
+    G = X(1000)
+    G.set_input_format(channels, rgb)
+    kc, dc = G(col)
+    assert np.array_equal(G.pyramid(0), want)
+    kg, dg = X(1000)(want)
+    assert_kps_equal(kc, dc, kg, dg)
+    # batch of scattered colour frames, and a strided view
+    outs = G.extract_batch([col, col[:, ::-1].copy()])
+    assert np.array_equal(outs[0][0], kc) and np.array_equal(outs[0][1], dc)
+    wide = np.zeros((480, 700, channels), np.uint8); wide[:, :640] = col
+    kv, dv = G(wide[:, :640])
+    assert np.array_equal(kv, kc) and np.array_equal(dv, dc)
+    # back to gray on the same handle
+    kb, db = G(want)
+    assert_kps_equal(kb, db, kg, dg)

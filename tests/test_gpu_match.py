@@ -267,3 +267,24 @@ def test_distinctive_descriptors(M, oracle, views):
     want = np.array([oracle.port_distinctive_descriptor(g) for g in groups], np.int32)
     assert np.array_equal(got, want), (got, want)
     assert want[11] == -1 and want[13] == 0
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+@pytest.mark.parametrize("th,ratio", [(1.0, 0.8), (3.0, 0.8), (5.0, 0.9)])
+def test_search_local_points_frustum_plus_projection(M, oracle, views, seed, th, ratio):
+    """Frame::isInFrustum (src/Frame.cc:269-325) + SearchByProjection(F, vpMapPoints, th) (src/ORBmatcher.cc:45-129) fused."""
+    v = views[seed]
+    F, P, Tcw, Ow, K = mf.world_points_case(v, seed + 70)
+    F = M.FrameView(F.mvKeysUn, F.mDescriptors, F.mvScaleFactors, F.bounds, mvuRight=v["ur"], occupied=F.occupied)
+    rng = np.random.default_rng(seed)
+    has_obs = (rng.random(len(P.world_pos)) < 0.9).astype(np.uint8)
+    fr = oracle.port_is_in_frustum(F, P, Tcw, Ow, K, 40.0, 0.5)
+    mps = M.MapPointsView(fr["proj_x"], fr["proj_y"], fr["proj_xr"], fr["level"], fr["view_cos"], P.descriptors, valid=fr["in_view"],
+                          has_obs=has_obs)
+    n_o, m_o = oracle.port_search_by_projection(F, mps, th, ratio)
+    got = M.ORBmatcher(ratio, True).SearchLocalPoints(F, P, Tcw, Ow, K, 40.0, th, has_obs=has_obs)
+    assert fr["count"] > 200 and n_o > 30
+    assert np.array_equal(got["in_view"], fr["in_view"])
+    for f in ("proj_x", "proj_y", "proj_xr", "level", "view_cos"):
+        assert np.array_equal(got[f], fr[f]), f                           # bit-identical floats, not just close
+    assert got["nmatches"] == n_o and np.array_equal(got["match"], m_o), int((got["match"] != m_o).sum())
