@@ -125,6 +125,14 @@ BORB_API borb_status borb_extract_batch_device(borb_extractor* e, const uint8_t*
  * `stride` arguments are then bytes per row of the interleaved image. */
 BORB_API borb_status borb_extractor_set_input_format(borb_extractor* e, int channels, int rgb_order);
 
+/* Stereo rectification fused into the upload: cv::remap(imLeft, imLeftRect, M1l, M2l, cv::INTER_LINEAR) /
+ * (imRight, ..., M1r, M2r, ...) of Examples/Stereo/stereo_euroc.cc:136-137 with the CV_32FC1 maps the caller built once
+ * with cv::initUndistortRectifyMap (:96-98).  which = 0: mono / left, 1: right (install 0 first; in the stereo entry
+ * points even images use set 0 and odd images set 1).  map_x / map_y: dst_h x dst_w floats; NULL removes the set(s).
+ * Afterwards the extract / stereo entry points take RAW src_w x src_h CV_8UC1 frames and work on dst_w x dst_h. */
+BORB_API borb_status borb_extractor_set_rectify_maps(borb_extractor* e, int which, const float* map_x, const float* map_y, int src_w,
+                                                     int src_h, int dst_w, int dst_h);
+
 /* mvImagePyramid[level] of image `image` of the last batch (include/ORBextractor.h:85), copied to
  * a caller buffer of at least h*w bytes (tight rows).  Pass dst=NULL to query w/h only. */
 BORB_API borb_status borb_extractor_pyramid(borb_extractor* e, int image, int level, uint8_t* dst, int* w, int* h);

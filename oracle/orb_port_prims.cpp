@@ -21,4 +21,11 @@ void orbport_fast_atan2(const float* y, const float* x, float* out, int n) {
     for (int i = 0; i < n; i++) out[i] = orbprims::fast_atan2(y[i], x[i]);
 }
 int orbport_reflect101(int p, int len) { return orbprims::reflect101(p, len); }
+void orbport_cvt_color_to_gray(const uint8_t* src, int w, int h, int sstep, int channels, int rgb_order, uint8_t* dst, int dstep) {
+    orbprims::cvt_color_to_gray_u8(src, w, h, (size_t)sstep, channels, rgb_order != 0, dst, (size_t)dstep);
+}
+void orbport_remap_linear(const uint8_t* src, int sw, int sh, int sstep, const float* mx, const float* my, uint8_t* dst, int dw, int dh,
+                          int dstep) {
+    orbprims::remap_linear_u8(src, sw, sh, (size_t)sstep, mx, my, dst, dw, dh, (size_t)dstep);
+}
 }

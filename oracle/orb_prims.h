@@ -280,4 +280,34 @@ static inline float fast_atan2(float y, float x) {
     return a;
 }
 
+// cv::cvtColor(src, dst, COLOR_RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY) on CV_8U — what Tracking::GrabImage* applies to
+// colour frames (reference src/Tracking.cc:172-197).  OpenCV 4.13: Y = (R*9798 + G*19235 + B*3735 + 2^14) >> 15.
+static inline void cvt_color_to_gray_u8(const uint8_t* src, int w, int h, size_t sstep, int channels, bool rgb_order, uint8_t* dst,
+                                        size_t dstep) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p = src + y * sstep + (size_t)x * channels;
+            const int R = rgb_order ? p[0] : p[2], G = p[1], B = rgb_order ? p[2] : p[0];
+            dst[y * dstep + x] = (uint8_t)((R * 9798 + G * 19235 + B * 3735 + 16384) >> 15);
+        }
+}
+
+// cv::remap(src, dst, map_x, map_y, INTER_LINEAR) (BORDER_CONSTANT 0) with CV_32FC1 maps on CV_8UC1 — the per-frame
+// rectification of reference Examples/Stereo/stereo_euroc.cc:136-137.  OpenCV fixed point: 1/32-px coordinates by
+// cvRound, bilinear weights scaled to 2^15 (exact for 1/32 fractions), result (sum + 2^14) >> 15.
+static inline void remap_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, const float* mx, const float* my, uint8_t* dst,
+                                   int dw, int dh, size_t dstep) {
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            const int sx = cv_round(mx[(size_t)y * dw + x] * 32.f), sy = cv_round(my[(size_t)y * dw + x] * 32.f);
+            int ix = sx >> 5, iy = sy >> 5;
+            ix = ix < -32768 ? -32768 : (ix > 32767 ? 32767 : ix);
+            iy = iy < -32768 ? -32768 : (iy > 32767 ? 32767 : iy);
+            const int fx = sx & 31, fy = sy & 31;
+            auto tap = [&](int yy, int xx) -> int { return (xx >= 0 && xx < sw && yy >= 0 && yy < sh) ? src[yy * sstep + xx] : 0; };
+            const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+            dst[y * dstep + x] = (uint8_t)((tap(iy, ix) * w00 + tap(iy, ix + 1) * w01 + tap(iy + 1, ix) * w10 + tap(iy + 1, ix + 1) * w11 + 16384) >> 15);
+        }
+}
+
 }  // namespace orbprims

@@ -307,15 +307,26 @@ borb_status enqueue_extract(borb_extractor* e, int n) {
     return BORB_OK;
 }
 
+// With rectification maps installed the caller hands in RAW frames; the pipeline works on the rectified size.
+borb_status rectified_size(borb_extractor* e, int w, int h, int* gw, int* gh) {
+    if (!e->d_map[0][0]) return BORB_OK;
+    if (w != e->map_src_w || h != e->map_src_h) {
+        set_error("rectification maps were built for %dx%d raw frames, got %dx%d", e->map_src_w, e->map_src_h, w, h);
+        return BORB_ERR_INVALID_ARG;
+    }
+    *gw = e->map_dst_w; *gh = e->map_dst_h;
+    return BORB_OK;
+}
+
 // Host images -> level 0.  slots[k] is the host pointer of batch image k (k = 0..n-1).  When the n images form
 // one contiguous block in slot order (camera frames in one pinned buffer) they travel as ONE 1-D copy into a
 // packed landing buffer and a kernel re-pitches them; otherwise one 2-D copy per image.
-borb_status upload_slots(borb_extractor* e, const uint8_t* const* slots, int n, int w, int h, int stride) {
+borb_status upload_slots(borb_extractor* e, const uint8_t* const* slots, int n, int w, int h, int stride, bool stereo_pairs = false) {
     const Geometry& g = e->geom;
     const int ch = e->in_channels;
     if (stride < w * ch) { set_error("stride %d smaller than a row of %d %d-channel pixels", stride, w, ch); return BORB_ERR_INVALID_ARG; }
     const size_t img_bytes = (size_t)stride * h;
-    bool contiguous = n > 1 || ch > 1;
+    bool contiguous = n > 1 || ch > 1 || e->d_map[0][0] != nullptr;
     for (int k = 0; k < n; k++) {
         if (!slots[k]) { set_error("image %d is NULL", k); return BORB_ERR_INVALID_ARG; }
         if (slots[k] != slots[0] + (size_t)k * img_bytes) contiguous = false;
@@ -330,6 +341,20 @@ borb_status upload_slots(borb_extractor* e, const uint8_t* const* slots, int n, 
         }
         return BORB_OK;
     };
+    if (e->d_map[0][0]) {               // raw frames: rectify while re-pitching (w, h are the RAW size here)
+        if (ch != 1) { set_error("rectification maps apply to CV_8UC1 frames"); return BORB_ERR_UNSUPPORTED; }
+        const size_t src_img = contiguous ? img_bytes : (size_t)w * h;
+        const int src_stride = contiguous ? stride : w;
+        borb_status st = need_stage(src_img * n);
+        if (st != BORB_OK) return st;
+        if (contiguous) BORB_CUDA(cudaMemcpyAsync(e->ws.stage, slots[0], src_img * n, cudaMemcpyHostToDevice, e->stream));
+        else
+            for (int k = 0; k < n; k++)
+                BORB_CUDA(cudaMemcpy2DAsync(e->ws.stage + (size_t)k * src_img, w, slots[k], stride, w, h, cudaMemcpyHostToDevice, e->stream));
+        e->launches += launch_repack_remap(g, e->ws, e->ws.stage, src_stride, src_img, w, h, e->d_map[0][0], e->d_map[0][1],
+                                           stereo_pairs ? e->d_map[1][0] : nullptr, stereo_pairs ? e->d_map[1][1] : nullptr, n, e->stream);
+        return BORB_OK;
+    }
     if (contiguous) {
         const size_t need = img_bytes * n;
         borb_status st = need_stage(need);
@@ -515,6 +540,8 @@ borb_status borb_extractor_destroy(borb_extractor* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     free_workspace(e->ws);
+    for (int a = 0; a < 2; a++)
+        for (int c = 0; c < 2; c++) cudaFree(e->d_map[a][c]);
     if (e->h_counts) cudaFreeHost(e->h_counts);
     for (auto& x : e->ev) cudaEventDestroy(x);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -566,7 +593,9 @@ borb_status borb_extract_batch_enqueue(borb_extractor* e, const uint8_t* const* 
     if (st != BORB_OK) return st;
     if (n == 0) return BORB_OK;
     if (!gray || cap < 0 || stride < w) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
-    if ((st = ensure(e, w, h, n)) != BORB_OK) return st;
+    int gw = w, gh = h;
+    if ((st = rectified_size(e, w, h, &gw, &gh)) != BORB_OK) return st;
+    if ((st = ensure(e, gw, gh, n)) != BORB_OK) return st;
     begin_step(e);
     mark(e, 0);
     if ((st = upload_slots(e, gray, n, w, h, stride)) != BORB_OK) return st;
@@ -613,6 +642,34 @@ borb_status borb_extract_batch_device(borb_extractor* e, const uint8_t* d_gray, 
     if ((st = download_kps(e, 0, n, 1, kps, desc, cap, n_out)) != BORB_OK) return st;
     mark(e, 8);
     return borb_sync(e);
+}
+
+borb_status borb_extractor_set_rectify_maps(borb_extractor* e, int which, const float* map_x, const float* map_y, int src_w, int src_h,
+                                            int dst_w, int dst_h) {
+    if (!e || which < 0 || which > 1) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(e->device));
+    BORB_CUDA(cudaStreamSynchronize(e->stream));
+    if (!map_x || !map_y) {                                  // remove (set 0 removes both)
+        for (int s2 = which; s2 < 2; s2++)
+            for (int c = 0; c < 2; c++) { cudaFree(e->d_map[s2][c]); e->d_map[s2][c] = nullptr; }
+        return BORB_OK;
+    }
+    if (src_w <= 0 || src_h <= 0 || dst_w <= 0 || dst_h <= 0) { set_error("bad map geometry"); return BORB_ERR_INVALID_ARG; }
+    if (which == 1 && (!e->d_map[0][0] || src_w != e->map_src_w || src_h != e->map_src_h || dst_w != e->map_dst_w || dst_h != e->map_dst_h)) {
+        set_error("install the left maps (set 0) first; both sets share one geometry"); return BORB_ERR_STATE;
+    }
+    const size_t bytes = (size_t)dst_w * dst_h * sizeof(float);
+    const float* src[2] = {map_x, map_y};
+    for (int c = 0; c < 2; c++) {
+        cudaFree(e->d_map[which][c]); e->d_map[which][c] = nullptr;
+        BORB_CUDA(cudaMalloc(&e->d_map[which][c], bytes));
+        BORB_CUDA(cudaMemcpy(e->d_map[which][c], src[c], bytes, cudaMemcpyHostToDevice));
+    }
+    if (which == 0) {
+        e->map_src_w = src_w; e->map_src_h = src_h; e->map_dst_w = dst_w; e->map_dst_h = dst_h;
+        for (int c = 0; c < 2; c++) { cudaFree(e->d_map[1][c]); e->d_map[1][c] = nullptr; }      // a new left set invalidates the right one
+    }
+    return BORB_OK;
 }
 
 borb_status borb_extractor_set_input_format(borb_extractor* e, int channels, int rgb_order) {
@@ -754,13 +811,15 @@ borb_status borb_stereo_frames_enqueue(borb_extractor* e, const uint8_t* const* 
     if (st != BORB_OK) return st;
     if (n_pairs == 0) return BORB_OK;
     if (!left || !right || stride < w || !(b > 0.f)) { set_error("bad arguments"); return BORB_ERR_INVALID_ARG; }
-    if ((st = ensure(e, w, h, 2 * n_pairs)) != BORB_OK) return st;
+    int gw = w, gh = h;
+    if ((st = rectified_size(e, w, h, &gw, &gh)) != BORB_OK) return st;
+    if ((st = ensure(e, gw, gh, 2 * n_pairs)) != BORB_OK) return st;
     begin_step(e);
     mark(e, 0);
     {
         std::vector<const uint8_t*> slots(2 * (size_t)n_pairs);
         for (int p = 0; p < n_pairs; p++) { slots[2 * p] = left[p]; slots[2 * p + 1] = right[p]; }
-        if ((st = upload_slots(e, slots.data(), 2 * n_pairs, w, h, stride)) != BORB_OK) return st;
+        if ((st = upload_slots(e, slots.data(), 2 * n_pairs, w, h, stride, true)) != BORB_OK) return st;
     }
     if ((st = enqueue_extract(e, 2 * n_pairs)) != BORB_OK) return st;
     if ((st = enqueue_stereo(e, e, n_pairs, nullptr, nullptr, bf, b)) != BORB_OK) return st;

@@ -101,6 +101,8 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 // ---- kernel launchers (each returns the number of kernel launches it issued) -----------------
+int launch_repack_remap(const Geometry& g, const Workspace& ws, const uint8_t* stage, int src_stride, size_t src_image_bytes, int src_w,
+                        int src_h, const float* mx0, const float* my0, const float* mx1, const float* my1, int n_images, cudaStream_t s);
 int launch_repack_color(const Geometry& g, const Workspace& ws, const uint8_t* stage, int src_stride, size_t src_image_bytes, int channels,
                         int rgb, int n_images, cudaStream_t s);
 int launch_repack(const Geometry& g, const Workspace& ws, const uint8_t* stage, int src_stride, size_t src_image_bytes,
@@ -146,6 +148,9 @@ struct borb_extractor {
     int last_n_images = 0;       // images of the last batch (0: none)
     int in_channels = 1;         // host input pixel format (borb_extractor_set_input_format): 1 gray, 3 RGB/BGR, 4 RGBA/BGRA
     int in_rgb = 1;              // 1: R first (mbRGB), 0: B first
+    // rectification maps (borb_extractor_set_rectify_maps): set 0 = mono / left, set 1 = right; device float maps
+    float* d_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int map_src_w = 0, map_src_h = 0, map_dst_w = 0, map_dst_h = 0;
     uint64_t launches = 0;
     // stage timing: a ring of event sets so that many queued steps can be timed without host syncs
     static constexpr int EV_RING = 128;

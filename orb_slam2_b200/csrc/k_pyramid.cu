@@ -128,6 +128,42 @@ __global__ void __launch_bounds__(256) repack_color_kernel(const uint8_t* __rest
     *reinterpret_cast<uint32_t*>(pyr + (size_t)img * image_stride + l0.pyr_off + (size_t)y * l0.pitch + x0) = v;
 }
 
+// Stereo rectification of the raw camera frame, fused into the upload: cv::remap(im, imRect, M1, M2, cv::INTER_LINEAR) of
+// reference Examples/Stereo/stereo_euroc.cc:136-137 with the CV_32FC1 maps of cv::initUndistortRectifyMap (:96-98).
+// OpenCV semantics (pinned against cv2.remap in tests/test_oracle_prims.py): coordinates to 1/32 px with cvRound,
+//   sx = cvRound(mapx*32), ix = sx >> 5, fx = sx & 31 (same for y); weights (32-fx)(32-fy)*32 ... (sum 2^15, exact);
+//   out = (sum w*p + 2^14) >> 15; taps outside the source read 0 (BORDER_CONSTANT).
+// Image k of the batch uses map set (k & 1) when two sets are given (left / right), else set 0.
+__global__ void __launch_bounds__(256) repack_remap_kernel(const uint8_t* __restrict__ stage, int src_stride, size_t src_image_bytes,
+                                                           int src_w, int src_h, const float* __restrict__ mx0,
+                                                           const float* __restrict__ my0, const float* __restrict__ mx1,
+                                                           const float* __restrict__ my1, uint8_t* __restrict__ pyr, LevelGeom l0,
+                                                           unsigned image_stride) {
+    const int img = blockIdx.z, y = blockIdx.y;
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x0 >= l0.w) return;
+    const bool second = (img & 1) && mx1 != nullptr;
+    const float* MX = second ? mx1 : mx0;
+    const float* MY = second ? my1 : my0;
+    const uint8_t* S = stage + (size_t)img * src_image_bytes;
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (x0 + i < l0.w) {
+            const size_t o = (size_t)y * l0.w + x0 + i;
+            const int sx = __float2int_rn(__fmul_rn(MX[o], 32.f)), sy = __float2int_rn(__fmul_rn(MY[o], 32.f));
+            const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));     // saturate_cast<short>
+            const int fx = sx & 31, fy = sy & 31;
+            auto tap = [&](int yy, int xx) -> int {
+                return (xx >= 0 && xx < src_w && yy >= 0 && yy < src_h) ? (int)S[(size_t)yy * src_stride + xx] : 0;
+            };
+            const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+            const int r = (tap(iy, ix) * w00 + tap(iy, ix + 1) * w01 + tap(iy + 1, ix) * w10 + tap(iy + 1, ix + 1) * w11 + 16384) >> 15;
+            v |= (uint32_t)r << (8 * i);
+        }
+    *reinterpret_cast<uint32_t*>(pyr + (size_t)img * image_stride + l0.pyr_off + (size_t)y * l0.pitch + x0) = v;
+}
+
 // reflect-101 padding of level 0 (columns w .. w+7 = columns w-2 .. w-9), after any kind of upload
 __global__ void __launch_bounds__(256) pad_level0_kernel(uint8_t* __restrict__ pyr, LevelGeom l0, unsigned image_stride) {
     const int y = blockIdx.x * 256 + threadIdx.x, img = blockIdx.y;
@@ -145,6 +181,14 @@ int launch_repack(const Geometry& g, const Workspace& ws, const uint8_t* stage, 
 }
 
 constexpr int PYR_ROWS = 2;
+
+int launch_repack_remap(const Geometry& g, const Workspace& ws, const uint8_t* stage, int src_stride, size_t src_image_bytes, int src_w,
+                        int src_h, const float* mx0, const float* my0, const float* mx1, const float* my1, int n_images, cudaStream_t s) {
+    dim3 grid((g.lv[0].w + 1023) / 1024, g.lv[0].h, n_images);
+    repack_remap_kernel<<<grid, 256, 0, s>>>(stage, src_stride, src_image_bytes, src_w, src_h, mx0, my0, mx1, my1, ws.pyr, g.lv[0],
+                                             g.pyr_image_stride);
+    return 1;
+}
 
 int launch_repack_color(const Geometry& g, const Workspace& ws, const uint8_t* stage, int src_stride, size_t src_image_bytes, int channels,
                         int rgb, int n_images, cudaStream_t s) {

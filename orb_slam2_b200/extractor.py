@@ -80,6 +80,22 @@ class ORBextractor:
         self.mbRGB = bool(mbRGB)
         self._set_format(channels)
 
+    def set_rectify_maps(self, which: int, map_x: Optional[np.ndarray], map_y: Optional[np.ndarray], src_size: Optional[Tuple[int, int]] = None) -> None:
+        """cv::remap(im, imRect, M1, M2, INTER_LINEAR) of Examples/Stereo/stereo_euroc.cc:136-137 fused into the upload.  which: 0 mono /
+        left, 1 right; map_x / map_y: (dst_h, dst_w) float32 maps from cv::initUndistortRectifyMap; src_size = (w, h) of the raw
+        frames (default: same as the maps).  None removes the maps."""
+        if map_x is None or map_y is None:
+            check(self._lib.borb_extractor_set_rectify_maps(self._h, int(which), None, None, 0, 0, 0, 0), "borb_extractor_set_rectify_maps")
+            return
+        mx = np.ascontiguousarray(map_x, np.float32); my = np.ascontiguousarray(map_y, np.float32)
+        assert mx.shape == my.shape and mx.ndim == 2
+        dh, dw = mx.shape
+        sw, sh = src_size if src_size is not None else (dw, dh)
+        check(self._lib.borb_extractor_set_rectify_maps(self._h, int(which), ptr(mx), ptr(my), int(sw), int(sh), dw, dh),
+              "borb_extractor_set_rectify_maps")
+        if which == 0:
+            self._rect_size = (dw, dh)
+
     def _set_format(self, channels: int) -> None:
         key = (int(channels), bool(getattr(self, "mbRGB", True)))
         if getattr(self, "_fmt", (1, True)) != key:

@@ -115,3 +115,45 @@ def test_constant_shift_property_full_size(X):
         assert np.all(np.abs(disp - d) < 0.75 * scale) and np.median(np.abs(disp - d)) < 0.3
         assert np.allclose(o["mvDepth"][m], np.float32(BF) / disp, rtol=1e-6)
     assert all(np.array_equal(out[0]["mvuRight"], o["mvuRight"]) for o in out[1:])
+
+
+def test_rectification_fused_into_upload_equals_cv2_remap():
+    """Examples/Stereo/stereo_euroc.cc:136-137 rectify every frame with cv::remap before TrackStereo; with the maps installed on
+    the handle the RAW frames are uploaded and rectified on the GPU: level 0 must equal cv2.remap's output bit for bit, and
+    keypoints / descriptors / stereo matches those of the pre-rectified path."""
+    cv2 = pytest.importorskip("cv2")
+    from orb_slam2_b200.extractor import ORBextractor
+    w, h = synth.EUROC
+
+    def maps(flip):
+        K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+        D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]) * flip
+        R = cv2.Rodrigues(np.array([0.003, -0.002, 0.001]) * flip)[0]
+        P = np.array([[435.2, 0, 367.45], [0, 435.2, 252.2], [0, 0, 1]])
+        return cv2.initUndistortRectifyMap(K, D, R, P, (w, h), cv2.CV_32F)
+    M1l, M2l = maps(1.0)
+    M1r, M2r = maps(0.9)
+    pairs = [synth.stereo_pair(80 + i, 0, 0, w, h)[:2] for i in range(3)]
+    rect = [(cv2.remap(L, M1l, M2l, cv2.INTER_LINEAR), cv2.remap(R, M1r, M2r, cv2.INTER_LINEAR)) for L, R in pairs]
+    bf, fx = 47.9, 435.2
+    ref = ORBextractor(1200).stereo_frames([p[0] for p in rect], [p[1] for p in rect], bf, fx)
+    G = ORBextractor(1200)
+    G.set_rectify_maps(0, M1l, M2l)
+    G.set_rectify_maps(1, M1r, M2r)
+    got = G.stereo_frames([p[0] for p in pairs], [p[1] for p in pairs], bf, fx)
+    for i in range(3):
+        assert np.array_equal(G.pyramid(0, image=2 * i), rect[i][0]) and np.array_equal(G.pyramid(0, image=2 * i + 1), rect[i][1])
+        for k in ("mvKeys", "mDescriptors", "mvKeysRight", "mDescriptorsRight", "mvuRight", "mvDepth"):
+            assert np.array_equal(got[i][k], ref[i][k]), (i, k)
+        assert (got[i]["mvuRight"] >= 0).sum() > 100
+    # monocular call on the same handle: set 0 only
+    km, dm = G(pairs[1][0])
+    kr, dr = ORBextractor(1200)(rect[1][0])
+    assert np.array_equal(km, kr) and np.array_equal(dm, dr)
+    # a raw frame of the wrong size is an error, removing the maps restores the plain path
+    from orb_slam2_b200._lib import BorbError
+    with pytest.raises(BorbError):
+        G(pairs[0][0][:400])
+    G.set_rectify_maps(0, None, None)
+    kp, dp = G(rect[1][0])
+    assert np.array_equal(kp, kr) and np.array_equal(dp, dr)

@@ -104,3 +104,51 @@ def test_reflect101(lib):
         pad = min(19, 3 * n)
         got = [lib.orbport_reflect101(p, n) for p in range(-pad, n + pad)]
         assert got == ref.tolist()
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_cvtcolor_to_gray_matches_cv2(lib, channels, rgb):
+    """Tracking::GrabImage* (src/Tracking.cc:172-197) convert colour frames with cv::cvtColor before extraction."""
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (97, 131, channels), dtype=np.uint8)
+    code = {(3, True): cv2.COLOR_RGB2GRAY, (3, False): cv2.COLOR_BGR2GRAY, (4, True): cv2.COLOR_RGBA2GRAY, (4, False): cv2.COLOR_BGRA2GRAY}[(channels, rgb)]
+    want = cv2.cvtColor(img, code)
+    got = np.zeros((97, 131), np.uint8)
+    lib.orbport_cvt_color_to_gray(img.ctypes.data_as(u8p), 131, 97, img.strides[0], channels, int(rgb), got.ctypes.data_as(u8p), got.strides[0])
+    assert np.array_equal(got, want)
+    if channels == 3 and rgb:                                   # every colour once (2^24 pixels)
+        r = np.arange(256, dtype=np.uint8)
+        full = np.ascontiguousarray(np.stack(np.meshgrid(r, r, r, indexing="ij"), -1).reshape(4096, 4096, 3))
+        want = cv2.cvtColor(full, cv2.COLOR_RGB2GRAY)
+        got = np.zeros((4096, 4096), np.uint8)
+        lib.orbport_cvt_color_to_gray(full.ctypes.data_as(u8p), 4096, 4096, full.strides[0], 3, 1, got.ctypes.data_as(u8p), got.strides[0])
+        assert np.array_equal(got, want)
+
+
+def _euroc_maps(w, h, flip=1.0):
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]) * flip
+    R = cv2.Rodrigues(np.array([0.003, -0.002, 0.001]) * flip)[0]
+    P = np.array([[435.2, 0, 367.45], [0, 435.2, 252.2], [0, 0, 1]])
+    return cv2.initUndistortRectifyMap(K, D, R, P, (w, h), cv2.CV_32F)
+
+
+def test_remap_linear_matches_cv2(lib):
+    """cv::remap(..., INTER_LINEAR) with CV_32FC1 maps (Examples/Stereo/stereo_euroc.cc:96-98,136-137)."""
+    rng = np.random.default_rng(4)
+    cases = []
+    w, h = synth.EUROC
+    cases.append((synth.mono_frame(6, 0, 0, w, h),) + tuple(_euroc_maps(w, h)))
+    img = rng.integers(0, 256, (120, 160), dtype=np.uint8)
+    yy, xx = np.mgrid[0:120, 0:160].astype(np.float32)
+    mx = (xx + 6 * np.sin(yy / 17) + rng.normal(0, 0.3, (120, 160)) - 3).astype(np.float32)      # leaves the image on every side
+    my = (yy + 5 * np.cos(xx / 23) + rng.normal(0, 0.3, (120, 160)) - 2).astype(np.float32)
+    cases.append((img, mx, my))
+    cases.append((img, (xx[:90, :100] * 1.5 + 0.25).astype(np.float32).copy(), (yy[:90, :100] * 1.25 - 0.5).astype(np.float32).copy()))   # dst != src size
+    for im, m1, m2 in cases:
+        want = cv2.remap(im, m1, m2, cv2.INTER_LINEAR)
+        got = np.zeros(m1.shape, np.uint8)
+        m1c, m2c = np.ascontiguousarray(m1), np.ascontiguousarray(m2)
+        lib.orbport_remap_linear(im.ctypes.data_as(u8p), im.shape[1], im.shape[0], im.strides[0], m1c.ctypes.data_as(f32p),
+                                 m2c.ctypes.data_as(f32p), got.ctypes.data_as(u8p), m1.shape[1], m1.shape[0], got.strides[0])
+        assert np.array_equal(got, want), int((got != want).sum())
