@@ -20,7 +20,7 @@
 namespace borb {
 
 template <int ROWS>
-__global__ void __launch_bounds__(256) pyr_resize_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ pyr_out,
+__global__ void __launch_bounds__(256, 6) pyr_resize_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ pyr_out,
                                                          const int16_t* __restrict__ tabs, LevelGeom src, LevelGeom dst,
                                                          unsigned image_stride) {
     const int img = blockIdx.z;
