@@ -27,7 +27,7 @@ struct ProjArgs {                 // device pointers
     float th, nnratio;
     uint32_t* cand;               // n_mp x n
     int* cand_cnt;                // n_mp
-    // mode 1 (SearchByProjection(CurrentFrame, LastFrame)): the window is precomputed per query by project_last_kernel
+    // mode 1 (SearchByProjection(CurrentFrame, LastFrame)): the window is precomputed per query by project_points_kernel
     const float* q_radius;        // null in mode 0
     const int32_t* q_minl;
     const int32_t* q_maxl;
@@ -37,7 +37,7 @@ struct ProjArgs {                 // device pointers
     int th_dist;                  // mode 1: accept bestDist <= th_dist (TH_HIGH / ORBdist / TH_LOW)
     int chi2;                     // 1: Fuse(pKF, vpMapPoints, th) reprojection gates per candidate (:907-931)
     const float* inv_sigma2;      // chi2: mvInvLevelSigma2
-    uint8_t* q_valid_out;         // mode 1: validity written by project_last_kernel (aliases mp_valid)
+    uint8_t* q_valid_out;         // mode 1: validity written by project_points_kernel (aliases mp_valid)
 };
 
 struct LastArgs {                 // inputs of project_points_kernel
