@@ -427,6 +427,25 @@ def port_is_in_frustum(F, P, Tcw, Ow, K, mbf, viewing_cos_limit=0.5):
     return dict(count=cnt, in_view=inv[:n], proj_x=px[:n], proj_y=py[:n], proj_xr=pxr[:n], level=lv[:n], view_cos=vc[:n])
 
 
+def port_detect_loop_candidates(kf_bows, n_words, q_bow, connected, neigh, min_score):
+    """KeyFrameDatabase::DetectLoopCandidates (KeyFrameDatabase.cc:76-197) over keyframes added in list order."""
+    lib = _plib()
+    start = np.zeros(len(kf_bows) + 1, np.int32)
+    start[1:] = np.cumsum([len(b) for b in kf_bows])
+    kw = _a(np.concatenate([np.fromiter(b.keys(), np.uint32, len(b)) for b in kf_bows] + [np.zeros(0, np.uint32)]), np.uint32)
+    kv = _a(np.concatenate([np.fromiter(b.values(), np.float64, len(b)) for b in kf_bows] + [np.zeros(0, np.float64)]), np.float64)
+    qw = _a(np.fromiter(q_bow.keys(), np.uint32, len(q_bow)), np.uint32); qv = _a(np.fromiter(q_bow.values(), np.float64, len(q_bow)), np.float64)
+    ng = _a(np.asarray(neigh, np.int32).reshape(len(kf_bows), 10), np.int32)
+    cn = _a(np.asarray(connected, np.uint8), np.uint8)
+    out = np.zeros(max(len(kf_bows), 1), np.int32)
+    fn = lib.orbport_detect_loop_candidates
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    n = fn(len(kf_bows), _ptr(start), _ptr(kw), _ptr(kv), int(n_words), _ptr(qw), _ptr(qv), len(qw), _ptr(cn), _ptr(ng),
+           float(np.float32(min_score)), _ptr(out))
+    return out[:n].copy()
+
+
 def _kf_args(kf):
     k = _a(kf.mvKeysUn, KP_DTYPE); d = _a(kf.mDescriptors, np.uint8)
     hm = _a(kf.has_mp, np.uint8) if kf.has_mp is not None else np.zeros(len(k), np.uint8)

@@ -985,3 +985,66 @@ extern "C" int orbport_is_in_frustum(const float* world_pos, const float* normal
     }
     return count;
 }
+
+// KeyFrameDatabase::DetectLoopCandidates(KeyFrame* pKF, float minScore) — reference src/KeyFrameDatabase.cc:76-197, restated
+// with a real inverted file like orbport_detect_reloc_candidates.  connected[k] = 1 if keyframe k is in
+// pKF->GetConnectedKeyFrames() (the query keyframe itself is normally not in the database yet, :LoopClosing.cc:147).
+extern "C" int orbport_detect_loop_candidates(int n_kf, const int32_t* kf_start, const uint32_t* kf_word, const double* kf_value,
+                                              int n_words, const uint32_t* q_word, const double* q_value, int nq,
+                                              const uint8_t* connected, const int32_t* neigh, float minScore, int32_t* out) {
+    std::vector<std::vector<int>> mvInvertedFile(n_words);
+    for (int k = 0; k < n_kf; k++)
+        for (int e = kf_start[k]; e < kf_start[k + 1]; e++) mvInvertedFile[kf_word[e]].push_back(k);
+    std::vector<int> mnLoopWords(n_kf, 0);
+    std::vector<char> queried(n_kf, 0);           // pKFi->mnLoopQuery == pKF->mnId
+    std::vector<float> mLoopScore(n_kf, 0.f);
+    std::vector<int> lKFsSharingWords;
+    for (int i = 0; i < nq; i++) {
+        if (q_word[i] >= (uint32_t)n_words) continue;
+        for (int pKFi : mvInvertedFile[q_word[i]]) {
+            if (!queried[pKFi]) {
+                mnLoopWords[pKFi] = 0;
+                if (!connected[pKFi]) { queried[pKFi] = 1; lKFsSharingWords.push_back(pKFi); }
+            }
+            mnLoopWords[pKFi]++;
+        }
+    }
+    if (lKFsSharingWords.empty()) return 0;
+    std::vector<std::pair<float, int>> lScoreAndMatch;
+    int maxCommonWords = 0;
+    for (int k : lKFsSharingWords) if (mnLoopWords[k] > maxCommonWords) maxCommonWords = mnLoopWords[k];
+    const int minCommonWords = maxCommonWords * 0.8f;
+    for (int k : lKFsSharingWords) {
+        if (mnLoopWords[k] > minCommonWords) {
+            const int s0 = kf_start[k], n2 = kf_start[k + 1] - s0;
+            const float si = (float)orbport_bow_score_l1(q_word, q_value, nq, kf_word + s0, kf_value + s0, n2, nullptr, nullptr);
+            mLoopScore[k] = si;
+            if (si >= minScore) lScoreAndMatch.push_back({si, k});
+        }
+    }
+    if (lScoreAndMatch.empty()) return 0;
+    std::vector<std::pair<float, int>> lAccScoreAndMatch;
+    float bestAccScore = minScore;
+    for (auto& it : lScoreAndMatch) {
+        const int pKFi = it.second;
+        float bestScore = it.first;
+        float accScore = it.first;
+        int pBestKF = pKFi;
+        for (int j = 0; j < 10; j++) {
+            const int pKF2 = neigh[(size_t)pKFi * 10 + j];
+            if (pKF2 < 0) break;
+            if (queried[pKF2] && mnLoopWords[pKF2] > minCommonWords) {
+                accScore += mLoopScore[pKF2];
+                if (mLoopScore[pKF2] > bestScore) { pBestKF = pKF2; bestScore = mLoopScore[pKF2]; }
+            }
+        }
+        lAccScoreAndMatch.push_back({accScore, pBestKF});
+        if (accScore > bestAccScore) bestAccScore = accScore;
+    }
+    const float minScoreToRetain = 0.75f * bestAccScore;
+    std::vector<char> added(n_kf, 0);
+    int n_out = 0;
+    for (auto& it : lAccScoreAndMatch)
+        if (it.first > minScoreToRetain && !added[it.second]) { out[n_out++] = it.second; added[it.second] = 1; }
+    return n_out;
+}

@@ -396,6 +396,80 @@ class ORBmatcher:
         return pairs[:n.value]
 
 
+def _sharing_order(cw, fw, seq, skip=()):
+    """lKFsSharingWords: keyframes sharing a word with the query, in the order the inverted-file walk meets them — by first
+    shared word id, then by insertion into that word's list (src/KeyFrameDatabase.cc:86-108, :211-224)."""
+    s = [int(i) for i in np.nonzero(np.asarray(cw) > 0)[0] if int(i) not in skip]
+    return sorted(s, key=lambda i: (int(fw[i]), seq[i]))
+
+
+def relocalization_candidates(cw, sc, fw, seq, covisibility) -> list:
+    """The host part of KeyFrameDatabase::DetectRelocalizationCandidates (src/KeyFrameDatabase.cc:226-310) from the per-keyframe
+    shared-word counts `cw`, float L1 scores `sc` and first shared words `fw` (borb_kfdb_query)."""
+    sharing = _sharing_order(cw, fw, seq)
+    if not sharing:
+        return []
+    maxCommonWords = max(int(cw[s]) for s in sharing)
+    minCommonWords = int(np.float32(maxCommonWords) * np.float32(0.8))
+    scored = [(np.float32(sc[s]), s) for s in sharing if cw[s] > minCommonWords]
+    if not scored:
+        return []
+    acc, bestAcc = [], np.float32(0)
+    for si, s in scored:
+        bestScore, accScore, best = si, si, s
+        for s2 in covisibility(s):
+            if cw[s2] <= 0:
+                continue                                  # mnRelocQuery != F->mnId: shares no word with the query
+            # mRelocScore is only assigned to keyframes above minCommonWords (:236-243); others still hold their old value.
+            # The reference reads that stale field; a fresh database has 0 there, which is what the mirror uses.
+            r = np.float32(sc[s2]) if cw[s2] > minCommonWords else np.float32(0)
+            accScore = np.float32(accScore + r)
+            if r > bestScore:
+                best, bestScore = s2, r
+        acc.append((accScore, best))
+        if accScore > bestAcc:
+            bestAcc = accScore
+    minScoreToRetain = np.float32(0.75) * bestAcc
+    out, seen = [], set()
+    for a, s in acc:
+        if a > minScoreToRetain and s not in seen:
+            out.append(s); seen.add(s)
+    return out
+
+
+def loop_candidates(cw, sc, fw, seq, connected, covisibility, minScore) -> list:
+    """The host part of KeyFrameDatabase::DetectLoopCandidates (src/KeyFrameDatabase.cc:110-197); `connected` = slots of the
+    query keyframe's connected keyframes (never candidates, :96-101)."""
+    minScore = np.float32(minScore)
+    sharing = _sharing_order(cw, fw, seq, skip=connected)
+    if not sharing:
+        return []
+    maxCommonWords = max(int(cw[s]) for s in sharing)
+    minCommonWords = int(np.float32(maxCommonWords) * np.float32(0.8))
+    in_list = set(sharing)
+    scored = [(np.float32(sc[s]), s) for s in sharing if cw[s] > minCommonWords and np.float32(sc[s]) >= minScore]
+    if not scored:
+        return []
+    acc, bestAcc = [], minScore
+    for si, s in scored:
+        bestScore, accScore, best = si, si, s
+        for s2 in covisibility(s):
+            if s2 in in_list and cw[s2] > minCommonWords:                 # mnLoopQuery == pKF->mnId && mnLoopWords > minCommonWords (:157)
+                r = np.float32(sc[s2])
+                accScore = np.float32(accScore + r)
+                if r > bestScore:
+                    best, bestScore = s2, r
+        acc.append((accScore, best))
+        if accScore > bestAcc:
+            bestAcc = accScore
+    minScoreToRetain = np.float32(0.75) * bestAcc
+    out, seen = [], set()
+    for a, s in acc:
+        if a > minScoreToRetain and s not in seen:
+            out.append(s); seen.add(s)
+    return out
+
+
 class KeyFrameDatabase:
     """KeyFrameDatabase (include/KeyFrameDatabase.h) with the keyframes resident in HBM.  add/erase/clear mirror
     src/KeyFrameDatabase.cc:41-73; query() is the data-parallel part of DetectLoopCandidates / DetectRelocalizationCandidates
@@ -458,37 +532,12 @@ class KeyFrameDatabase:
     def DetectRelocalizationCandidates(self, mBowVec: Dict[int, float], covisibility) -> list:
         """src/KeyFrameDatabase.cc:199-310.  covisibility(slot) -> up to 10 slots (GetBestCovisibilityKeyFrames(10))."""
         cw, sc, fw = self.query(mBowVec)
-        sharing = np.nonzero(cw > 0)[0]
-        if len(sharing) == 0:
-            return []
-        # lKFsSharingWords order: first shared word, then insertion order into that word's list (:211-224)
-        sharing = sorted(sharing.tolist(), key=lambda s: (int(fw[s]), self._seq[s]))
-        maxCommonWords = int(cw[sharing].max())
-        minCommonWords = int(np.float32(maxCommonWords) * np.float32(0.8))
-        scored = [(np.float32(sc[s]), s) for s in sharing if cw[s] > minCommonWords]
-        if not scored:
-            return []
-        acc, bestAcc = [], np.float32(0)
-        for si, s in scored:
-            bestScore, accScore, best = si, si, s
-            for s2 in covisibility(s):
-                if cw[s2] <= 0:
-                    continue                                  # mnRelocQuery != F->mnId: shares no word with the query
-                # mRelocScore is only assigned to keyframes above minCommonWords (:236-243); others still hold their old value.
-                # The reference reads that stale field; a fresh database has 0 there, which is what the mirror uses.
-                r = np.float32(sc[s2]) if cw[s2] > minCommonWords else np.float32(0)
-                accScore = np.float32(accScore + r)
-                if r > bestScore:
-                    best, bestScore = s2, r
-            acc.append((accScore, best))
-            if accScore > bestAcc:
-                bestAcc = accScore
-        minScoreToRetain = np.float32(0.75) * bestAcc
-        out, seen = [], set()
-        for a, s in acc:
-            if a > minScoreToRetain and s not in seen:
-                out.append(s); seen.add(s)
-        return out
+        return relocalization_candidates(cw, sc, fw, self._seq, covisibility)
+
+    def DetectLoopCandidates(self, mBowVec: Dict[int, float], connected, covisibility, minScore: float) -> list:
+        """src/KeyFrameDatabase.cc:76-197.  connected: slots of pKF->GetConnectedKeyFrames(); covisibility as above."""
+        cw, sc, fw = self.query(mBowVec)
+        return loop_candidates(cw, sc, fw, self._seq, set(int(c) for c in connected), covisibility, minScore)
 
     def SearchByBoW(self, slots, F: KeyFrameView):
         """SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:159-288) for database keyframes `slots` against frame F."""

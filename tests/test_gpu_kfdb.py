@@ -81,6 +81,27 @@ def test_relocalization_candidates_match_oracle(world, oracle):
         assert got == want.tolist() and len(got) >= 1, (got, want)
 
 
+def test_loop_candidates_match_oracle(world, oracle):
+    """KeyFrameDatabase::DetectLoopCandidates (src/KeyFrameDatabase.cc:76-197) from the GPU query + the host logic."""
+    M = world["M"]
+    mt = M.ORBmatcher(0.75, True)
+    db = M.KeyFrameDatabase(mt)
+    for kf, bow in zip(world["kfs"], world["bows"]):
+        db.add(kf, bow)
+    rng = np.random.default_rng(13)
+    neigh = np.full((N_KF, 10), -1, np.int32)
+    for s in range(N_KF):
+        nb = [x for x in (s - 1, s + 1, s + 2) if 0 <= x < N_KF] + rng.integers(0, N_KF, 2).tolist()
+        nb = [x for x in dict.fromkeys(nb) if x != s][:10]
+        neigh[s, :len(nb)] = nb
+    covis = lambda s: [int(x) for x in neigh[s] if x >= 0]
+    for q, conn, min_score in ((world["qbow"], [6, 30], 0.0), (world["bows"][20], [19, 20, 21], 0.02), (world["bows"][41], [], 0.15)):
+        connected = np.zeros(N_KF, np.uint8); connected[conn] = 1
+        got = db.DetectLoopCandidates(q, conn, covis, min_score)
+        want = oracle.port_detect_loop_candidates(world["bows"], world["n_words"], q, connected, neigh, min_score).tolist()
+        assert got == want, (got, want)
+
+
 def test_search_by_bow_against_resident_keyframes(world, oracle):
     M = world["M"]
     mt = M.ORBmatcher(0.75, True)

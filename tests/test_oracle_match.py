@@ -232,3 +232,46 @@ def test_bow_score_and_reloc_candidates_restatements(oracle):
     assert oracle.port_detect_reloc_candidates(bows, 16, q, neigh).tolist() == [1]      # both groups elect keyframe 1, listed once
     assert oracle.port_detect_reloc_candidates(bows, 16, {7: 1.0}, neigh).tolist() == [2]
     assert oracle.port_detect_reloc_candidates(bows, 16, {5: 1.0}, neigh).tolist() == []
+
+
+def test_keyframe_database_host_logic_equals_restated_reference(oracle):
+    """orb_slam2_b200.matcher.relocalization_candidates / loop_candidates (the host half of the device-resident keyframe
+    database: ordering, thresholds, covisibility accumulation) against the restatements of KeyFrameDatabase.cc that walk a real
+    inverted file.  The per-keyframe inputs the GPU query provides (shared words, float L1 score, first shared word) come
+    from the oracle here, so the whole chain is checked without a GPU."""
+    from orb_slam2_b200 import matcher as M
+    rng = np.random.default_rng(12)
+    n_words, n_kf = 800, 60
+    centers = [rng.choice(n_words, 90, replace=False) for _ in range(6)]           # six "places"
+
+    def bow_near(c):
+        keep = centers[c][rng.random(90) < 0.8]
+        extra = rng.choice(n_words, 25, replace=False)
+        w = np.unique(np.concatenate([keep, extra]))
+        v = rng.random(len(w)); v /= v.sum()
+        return dict(zip(w.tolist(), v.tolist()))
+    place = rng.integers(0, 6, n_kf)
+    bows = [bow_near(int(p)) for p in place]
+    neigh = np.full((n_kf, 10), -1, np.int32)
+    for s in range(n_kf):
+        same = [int(x) for x in np.nonzero(place == place[s])[0] if x != s]
+        nb = list(dict.fromkeys(same[:4] + rng.integers(0, n_kf, 3).tolist()))
+        nb = [x for x in nb if x != s][:10]
+        neigh[s, :len(nb)] = nb
+    covis = lambda s: [int(x) for x in neigh[s] if x >= 0]
+    seq = list(range(n_kf))
+    checked = 0
+    for q in [bow_near(0), bow_near(3), bows[17], {5: 1.0}, {}]:
+        per = [oracle.port_bow_score(q, b) for b in bows]
+        sc = np.array([np.float32(p[0]) for p in per], np.float32); cw = np.array([p[1] for p in per], np.int32); fw = np.array([p[2] for p in per], np.uint32)
+        got = M.relocalization_candidates(cw, sc, fw, seq, covis)
+        want = oracle.port_detect_reloc_candidates(bows, n_words, q, neigh).tolist()
+        assert got == want, (got, want)
+        for min_score, conn in [(0.0, []), (0.05, [3, 17, 20]), (0.3, list(range(0, n_kf, 2)))]:
+            connected = np.zeros(n_kf, np.uint8); connected[conn] = 1
+            got = M.loop_candidates(cw, sc, fw, seq, set(conn), covis, min_score)
+            want = oracle.port_detect_loop_candidates(bows, n_words, q, connected, neigh, min_score).tolist()
+            assert got == want, (min_score, conn, got, want)
+            assert not set(got) & set(conn)
+            checked += len(want)
+    assert checked > 10
