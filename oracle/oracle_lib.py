@@ -549,3 +549,261 @@ class PortVocabulary:
             self._lib.orbport_voc_free(self._h)
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own src/ORBmatcher.cc, compiled verbatim (oracle/_ref/libmatchref.so, see oracle/Makefile and
+# oracle/matchref_wrap.cpp).  These wrappers take the same view objects as the port_* functions above and return the
+# results in the port's conventions, so a test can assert  port(x) == ref(x)  directly.
+MATCHREF_SO = os.path.join(HERE, "_ref", "libmatchref.so")
+
+
+def have_matchref() -> bool:
+    return os.path.exists(MATCHREF_SO)
+
+
+def _mlib():
+    return C.CDLL(MATCHREF_SO)
+
+
+def _f32(a, n=None):
+    return _a(np.asarray(a, np.float32).reshape(-1) if n is None else np.asarray(a, np.float32).reshape(n), np.float32)
+
+
+def _T12(T):
+    return _a(np.asarray(T, np.float32)[:3, :4].reshape(12), np.float32)
+
+
+def ref_descriptor_distance(a, b):
+    lib = _mlib()
+    a = _a(a, np.uint8); b = _a(b, np.uint8)
+    lib.matchref_descriptor_distance.restype = C.c_int
+    lib.matchref_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+    return lib.matchref_descriptor_distance(_ptr(a), _ptr(b))
+
+
+def ref_decompose_scw(Scw):
+    """ORBmatcher.cc:298-303 with the shim's cv::Mat arithmetic -> (Tcw 3x4 = [Rcw|tcw], Ow)."""
+    lib = _mlib()
+    T = np.zeros(12, np.float32); ow = np.zeros(3, np.float32); s = _T12(Scw)
+    lib.matchref_decompose_scw.argtypes = [C.c_void_p] * 3
+    lib.matchref_decompose_scw(_ptr(s), _ptr(T), _ptr(ow))
+    return T.reshape(3, 4), ow
+
+
+def ref_sim3_mats(s12, R12, t12):
+    lib = _mlib()
+    S12 = np.zeros(12, np.float32); S21 = np.zeros(12, np.float32)
+    r = _f32(R12, 9); t = _f32(t12, 3)
+    lib.matchref_sim3_mats.argtypes = [C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.matchref_sim3_mats(float(np.float32(s12)), _ptr(r), _ptr(t), _ptr(S12), _ptr(S21))
+    return S12.reshape(3, 4), S21.reshape(3, 4)
+
+
+def ref_camera_center(Tcw):
+    lib = _mlib()
+    ow = np.zeros(3, np.float32); T = _T12(Tcw)
+    lib.matchref_camera_center.argtypes = [C.c_void_p] * 2
+    lib.matchref_camera_center(_ptr(T), _ptr(ow))
+    return ow
+
+
+def ref_epipole(Ow1, T2w, K2):
+    lib = _mlib()
+    o = _f32(Ow1, 3); T = _T12(T2w); ex = C.c_float(); ey = C.c_float()
+    lib.matchref_epipole.argtypes = [C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p] * 2
+    lib.matchref_epipole(_ptr(o), _ptr(T), *[float(x) for x in K2], C.addressof(ex), C.addressof(ey))
+    return float(ex.value), float(ey.value)
+
+
+def ref_forward_backward(TcwCur, TcwLast, mb, bMono):
+    lib = _mlib()
+    a = _T12(TcwCur); b = _T12(TcwLast); f = C.c_int(); w = C.c_int()
+    lib.matchref_forward_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    lib.matchref_forward_backward(_ptr(a), _ptr(b), float(mb), int(bMono), C.addressof(f), C.addressof(w))
+    return bool(f.value), bool(w.value)
+
+
+def _opt(a, dt):
+    return _a(a, dt) if a is not None else None
+
+
+def _p0(a):
+    return _ptr(a) if a is not None else None
+
+
+def ref_search_by_projection(F, mps, th, nnratio):
+    """-> (nmatches, owner[F.N]): index of the map point in F.mvpMapPoints[idx] afterwards, -3 prior occupant, -1 none."""
+    lib = _mlib()
+    k = _a(F.mvKeysUn, KP_DTYPE); d = _a(F.mDescriptors, np.uint8); ur = _opt(F.mvuRight, np.float32); oc = _opt(F.occupied, np.uint8)
+    sf = _a(F.mvScaleFactors, np.float32)
+    px = _a(mps.mTrackProjX, np.float32); py = _a(mps.mTrackProjY, np.float32); pxr = _a(mps.mTrackProjXR, np.float32)
+    lv = _a(mps.mnTrackScaleLevel, np.int32); vc = _a(mps.mTrackViewCos, np.float32); md = _a(mps.descriptors, np.uint8)
+    va = _opt(mps.valid, np.uint8); ho = _opt(mps.has_obs, np.uint8)
+    owner = np.full(max(len(k), 1), -1, np.int32)
+    fn = lib.matchref_search_by_projection
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_float, C.c_float, C.c_void_p]
+    n = fn(_ptr(k), _ptr(d), _p0(ur), _p0(oc), len(k), *[float(b) for b in F.bounds], _ptr(sf), len(sf), len(px), _ptr(px), _ptr(py),
+           _ptr(pxr), _ptr(lv), _ptr(vc), _ptr(md), _p0(va), _p0(ho), float(th), float(np.float32(nnratio)), _ptr(owner))
+    return n, owner[:len(k)]
+
+
+def owner_from_matches(F, mps, match):
+    """What F.mvpMapPoints looks like after applying the port's per-map-point matches in order (ORBmatcher.cc:123)."""
+    owner = np.where(np.asarray(F.occupied if F.occupied is not None else np.zeros(len(F.mvKeysUn)), bool), -3, -1).astype(np.int32)
+    for i, f in enumerate(match):
+        if f >= 0:
+            owner[f] = i
+    return owner
+
+
+def owner_from_state(occupied, state):
+    """Port state (>=0 query, -1 untouched, -2 culled) -> pointer view: index, -3 prior occupant, -1 NULL."""
+    occ = np.asarray(occupied if occupied is not None else np.zeros(len(state)), bool)
+    return np.where(state >= 0, state, np.where((state == -1) & occ, -3, -1)).astype(np.int32)
+
+
+def ref_search_by_projection_last(Cur, Last, TcwCur, TcwLast, K, bf, mb, th, bMono, check_ori):
+    lib = _mlib()
+    k = _a(Cur.mvKeysUn, KP_DTYPE); d = _a(Cur.mDescriptors, np.uint8); ur = _opt(Cur.mvuRight, np.float32); oc = _opt(Cur.occupied, np.uint8)
+    sf = _a(Cur.mvScaleFactors, np.float32)
+    lk = _a(Last.mvKeysUn, KP_DTYPE); wp = _a(Last.world_pos, np.float32); ld = _a(Last.descriptors, np.uint8)
+    va = _opt(Last.valid, np.uint8); ho = _opt(Last.has_obs, np.uint8)
+    Tc = _T12(TcwCur); Tl = _T12(TcwLast)
+    owner = np.full(max(len(k), 1), -1, np.int32)
+    fn = lib.matchref_search_by_projection_last
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2
+                   + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p])
+    n = fn(_ptr(k), _ptr(d), _p0(ur), _p0(oc), len(k), *[float(b) for b in Cur.bounds], _ptr(sf), len(sf), _ptr(lk), _ptr(wp), _ptr(ld),
+           _p0(va), _p0(ho), len(lk), _ptr(Tc), _ptr(Tl), float(K[0]), float(K[1]), float(K[2]), float(K[3]), float(bf), float(mb),
+           float(th), int(bMono), int(check_ori), _ptr(owner))
+    return n, owner[:len(k)]
+
+
+def ref_search_by_projection_kf(Cur, P, Tcw, K, th, orb_dist, check_ori):
+    lib = _mlib()
+    k = _a(Cur.mvKeysUn, KP_DTYPE); d = _a(Cur.mDescriptors, np.uint8); oc = _opt(Cur.occupied, np.uint8)
+    sf = _a(Cur.mvScaleFactors, np.float32)
+    wp, md, mx, mn, va = _points_args(P)
+    ang = _a(P.angle, np.float32); T = _T12(Tcw)
+    owner = np.full(max(len(k), 1), -1, np.int32)
+    fn = lib.matchref_search_by_projection_kf
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 3 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 6 + [C.c_int]
+                   + [C.c_void_p] + [C.c_float] * 5 + [C.c_int, C.c_int, C.c_void_p])
+    n = fn(_ptr(k), _ptr(d), _p0(oc), len(k), *[float(b) for b in Cur.bounds], _ptr(sf), len(sf), _log_scale(Cur), _ptr(ang), _ptr(wp),
+           _ptr(md), _ptr(mx), _ptr(mn), _ptr(va), len(wp), _ptr(T), float(K[0]), float(K[1]), float(K[2]), float(K[3]), float(th),
+           int(orb_dist), int(check_ori), _ptr(owner))
+    return n, owner[:len(k)]
+
+
+def ref_search_by_projection_sim3(KF, P, Scw, K, th):
+    lib = _mlib()
+    k = _a(KF.mvKeysUn, KP_DTYPE); d = _a(KF.mDescriptors, np.uint8); oc = _opt(KF.occupied, np.uint8)
+    sf = _a(KF.mvScaleFactors, np.float32)
+    wp, md, mx, mn, va = _points_args(P)
+    nr = _a(P.normal, np.float32); S = _T12(Scw)
+    owner = np.full(max(len(k), 1), -1, np.int32)
+    fn = lib.matchref_search_by_projection_sim3
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 3 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 6 + [C.c_int]
+                   + [C.c_void_p] + [C.c_float] * 4 + [C.c_int, C.c_void_p])
+    n = fn(_ptr(k), _ptr(d), _p0(oc), len(k), *[float(b) for b in KF.bounds], _ptr(sf), len(sf), _log_scale(KF), _ptr(wp), _ptr(md), _ptr(mx),
+           _ptr(mn), _ptr(nr), _ptr(va), len(wp), _ptr(S), float(K[0]), float(K[1]), float(K[2]), float(K[3]), int(th), _ptr(owner))
+    return n, owner[:len(k)]
+
+
+def ref_search_by_bow(kf, F, nnratio, check_ori):
+    lib = _mlib()
+    k1, d1, hm1, nd1, st1, fi1 = _kf_args(kf)
+    k2, d2, _, nd2, st2, fi2 = _kf_args(F)
+    match = np.full(max(len(k2), 1), -1, np.int32)
+    fn = lib.matchref_search_by_bow_kf_f
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_float, C.c_int, C.c_void_p]
+    n = fn(_ptr(k1), _ptr(d1), _ptr(hm1), len(k1), len(nd1), _ptr(nd1), _ptr(st1), _ptr(fi1), _ptr(k2), _ptr(d2), len(k2), len(nd2),
+           _ptr(nd2), _ptr(st2), _ptr(fi2), float(np.float32(nnratio)), int(check_ori), _ptr(match))
+    return n, match[:len(k2)]
+
+
+def ref_search_by_bow_kf(kf1, kf2, nnratio, check_ori):
+    lib = _mlib()
+    k1, d1, hm1, nd1, st1, fi1 = _kf_args(kf1)
+    k2, d2, hm2, nd2, st2, fi2 = _kf_args(kf2)
+    match = np.full(max(len(k1), 1), -1, np.int32)
+    fn = lib.matchref_search_by_bow_kf_kf
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 3) * 2 + [C.c_float, C.c_int, C.c_void_p]
+    n = fn(_ptr(k1), _ptr(d1), _ptr(hm1), len(k1), len(nd1), _ptr(nd1), _ptr(st1), _ptr(fi1), _ptr(k2), _ptr(d2), _ptr(hm2), len(k2),
+           len(nd2), _ptr(nd2), _ptr(st2), _ptr(fi2), float(np.float32(nnratio)), int(check_ori), _ptr(match))
+    return n, match[:len(k1)]
+
+
+def ref_search_for_triangulation(kf1, kf2, F12, Ow1, T2w, K2, only_stereo, check_ori):
+    lib = _mlib()
+    k1, d1, hm1, nd1, st1, fi1 = _kf_args(kf1)
+    k2, d2, hm2, nd2, st2, fi2 = _kf_args(kf2)
+    ur1 = _a(kf1.mvuRight, np.float32); ur2 = _a(kf2.mvuRight, np.float32)
+    f = _f32(F12, 9); o = _f32(Ow1, 3); T = _T12(T2w)
+    sf2 = _a(kf2.mvScaleFactors, np.float32); sg2 = _a(kf2.mvLevelSigma2, np.float32)
+    pairs = np.zeros((max(len(k1), 1), 2), np.int32)
+    fn = lib.matchref_search_for_triangulation
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 3) * 2 + [C.c_void_p] * 3 + [C.c_float] * 4 + [C.c_void_p] * 2 + [C.c_int] * 3 + [C.c_void_p]
+    n = fn(_ptr(k1), _ptr(d1), _ptr(hm1), _ptr(ur1), len(k1), len(nd1), _ptr(nd1), _ptr(st1), _ptr(fi1), _ptr(k2), _ptr(d2), _ptr(hm2),
+           _ptr(ur2), len(k2), len(nd2), _ptr(nd2), _ptr(st2), _ptr(fi2), _ptr(f), _ptr(o), _ptr(T), *[float(x) for x in K2], _ptr(sf2),
+           _ptr(sg2), len(sf2), int(only_stereo), int(check_ori), _ptr(pairs))
+    return pairs[:n].copy()
+
+
+def ref_search_for_initialization(F1, F2, prev_matched, window, nnratio, check_ori):
+    lib = _mlib()
+    k1 = _a(F1.mvKeysUn, KP_DTYPE); d1 = _a(F1.mDescriptors, np.uint8)
+    k2 = _a(F2.mvKeysUn, KP_DTYPE); d2 = _a(F2.mDescriptors, np.uint8)
+    prev = np.ascontiguousarray(np.asarray(prev_matched, np.float32).reshape(-1, 2)).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    fn = lib.matchref_search_for_initialization
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = fn(_ptr(k1), _ptr(d1), len(k1), _ptr(k2), _ptr(d2), len(k2), *[float(b) for b in F2.bounds], _ptr(prev), int(window),
+           float(np.float32(nnratio)), int(check_ori), _ptr(m12))
+    return n, m12[:len(k1)], prev
+
+
+def ref_search_by_sim3(KF1, KF2, P1, P2, T1w, T2w, s12, R12, t12, K, th):
+    lib = _mlib()
+    k1 = _a(KF1.mvKeysUn, KP_DTYPE); d1 = _a(KF1.mDescriptors, np.uint8); sf1 = _a(KF1.mvScaleFactors, np.float32)
+    k2 = _a(KF2.mvKeysUn, KP_DTYPE); d2 = _a(KF2.mDescriptors, np.uint8); sf2 = _a(KF2.mvScaleFactors, np.float32)
+    b1 = _f32(KF1.bounds, 4); b2 = _f32(KF2.bounds, 4)
+    wp1, md1, mx1, mn1, va1 = _points_args(P1)
+    wp2, md2, mx2, mn2, va2 = _points_args(P2)
+    Ta = _T12(T1w); Tb = _T12(T2w); r = _f32(R12, 9); t = _f32(t12, 3)
+    match = np.full(max(len(k1), 1), -1, np.int32)
+    fn = lib.matchref_search_by_sim3
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float] * 2 + [C.c_int] + [C.c_void_p] * 10 + [C.c_void_p] * 2
+                   + [C.c_float, C.c_void_p, C.c_void_p] + [C.c_float] * 5 + [C.c_void_p])
+    n = fn(_ptr(k1), _ptr(d1), len(k1), _ptr(b1), _ptr(sf1), _log_scale(KF1), _ptr(k2), _ptr(d2), len(k2), _ptr(b2), _ptr(sf2),
+           _log_scale(KF2), len(sf1), _ptr(wp1), _ptr(md1), _ptr(mx1), _ptr(mn1), _ptr(va1), _ptr(wp2), _ptr(md2), _ptr(mx2), _ptr(mn2),
+           _ptr(va2), _ptr(Ta), _ptr(Tb), float(np.float32(s12)), _ptr(r), _ptr(t), float(K[0]), float(K[1]), float(K[2]), float(K[3]),
+           float(th), _ptr(match))
+    return n, match[:len(k1)]
+
+
+def ref_fuse(KF, P, Tcw_or_Scw, Ow, K, bf, th, scw):
+    lib = _mlib()
+    k = _a(KF.mvKeysUn, KP_DTYPE); d = _a(KF.mDescriptors, np.uint8); sf = _a(KF.mvScaleFactors, np.float32)
+    ur = _opt(KF.mvuRight, np.float32); inv = _opt(KF.mvInvLevelSigma2, np.float32)
+    wp, md, mx, mn, va = _points_args(P)
+    nr = _a(P.normal, np.float32); T = _T12(Tcw_or_Scw); ow = _f32(Ow, 3)
+    best = np.full(max(len(wp), 1), -1, np.int32)
+    fn = lib.matchref_fuse
+    fn.restype = C.c_int
+    fn.argtypes = ([C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 6 + [C.c_int]
+                   + [C.c_void_p] * 2 + [C.c_float] * 6 + [C.c_int, C.c_void_p])
+    n = fn(_ptr(k), _ptr(d), _p0(ur), _p0(inv), len(k), *[float(b) for b in KF.bounds], _ptr(sf), len(sf), _log_scale(KF), _ptr(wp),
+           _ptr(md), _ptr(mx), _ptr(mn), _ptr(nr), _ptr(va), len(wp), _ptr(T), _ptr(ow), float(K[0]), float(K[1]), float(K[2]), float(K[3]),
+           float(bf), float(th), int(scw), _ptr(best))
+    return n, best[:len(wp)]
