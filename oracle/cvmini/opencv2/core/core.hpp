@@ -64,6 +64,24 @@ public:
             for (int c = 0; c < cols; c++) m.at<float>(c, r) = at<float>(r, c);
         return m;
     }
+    // u8 -> f32 (or a plain copy); `dst` may be *this (a view becomes an independent float matrix, as in OpenCV)
+    void convertTo(Mat& dst, int t) const {
+        Mat m(rows, cols, t);
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++) {
+                const float v = type_ == CV_32F ? at<float>(r, c) : (float)at<uchar>(r, c);
+                if (t == CV_32F) m.at<float>(r, c) = v; else m.at<uchar>(r, c) = (uchar)v;
+            }
+        dst = m;
+    }
+    static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
+    static Mat ones(int r, int c, int t) {
+        Mat m(r, c, t);
+        for (int i = 0; i < r; i++)
+            for (int j = 0; j < c; j++) { if (t == CV_32F) m.at<float>(i, j) = 1.f; else m.at<uchar>(i, j) = 1; }
+        return m;
+    }
+    Mat reshape(int) const { return *this; }        // only on paths the oracle never runs (UndistortKeyPoints)
     double dot(const Mat& o) const {                // float inputs, products and sum in double, index order
         double s = 0;
         for (int r = 0; r < rows; r++)
@@ -110,6 +128,27 @@ inline Mat operator*(double s, const Mat& a) {
 }
 inline Mat operator*(const Mat& a, double s) { return s * a; }
 inline Mat operator/(const Mat& a, double s) { return (1.0 / s) * a; }
+
+enum { NORM_L1 = 2 };
+inline double norm(const Mat& a, const Mat& b, int /*NORM_L1*/) {      // sum |a-b| in double (exact for the integer-valued SAD patches)
+    double s = 0;
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < a.cols; j++) s += std::fabs((double)a.at<float>(i, j) - (double)b.at<float>(i, j));
+    return s;
+}
+inline void undistortPoints(const Mat&, Mat&, const Mat&, const Mat&, const Mat&, const Mat&) {}   // never run by the oracle
+
+// cv::Mat_<float>(3,1) << x, y, z   (Frame::UnprojectStereo)
+template <typename T> class Mat_ : public Mat {
+public:
+    Mat_(int r, int c) : Mat(r, c, CV_32F) {}
+    struct Init {
+        Mat_* m; int i;
+        Init& operator,(T v) { m->template at<T>(i / m->cols, i % m->cols) = v; i++; return *this; }
+        operator Mat() const { return *m; }
+    };
+    Init operator<<(T v) { this->template at<T>(0, 0) = v; return Init{this, 1}; }
+};
 
 inline double norm(const Mat& a) {
     double s = 0;

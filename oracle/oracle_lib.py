@@ -807,3 +807,67 @@ def ref_fuse(KF, P, Tcw_or_Scw, Ow, K, bf, th, scw):
            _ptr(md), _ptr(mx), _ptr(mn), _ptr(nr), _ptr(va), len(wp), _ptr(T), _ptr(ow), float(K[0]), float(K[1]), float(K[2]), float(K[3]),
            float(bf), float(th), int(scw), _ptr(best))
     return n, best[:len(wp)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own src/Frame.cc compiled verbatim against its real include/Frame.h (oracle/_ref/libframeref.so,
+# oracle/frameref_wrap.cpp): ComputeStereoMatches, the feature grid, isInFrustum.
+FRAMEREF_SO = os.path.join(HERE, "_ref", "libframeref.so")
+
+
+def have_frameref() -> bool:
+    return os.path.exists(FRAMEREF_SO)
+
+
+def ref_stereo(kL, dL, kR, dR, pyrL, pyrR, scale, inv_scale, bf, fx):
+    """Frame::ComputeStereoMatches of the reference source; same arguments and outputs as port_stereo (without the SAD)."""
+    lib = C.CDLL(FRAMEREF_SO)
+    nlev = len(pyrL)
+    pyrL = [np.ascontiguousarray(p, np.uint8) for p in pyrL]
+    pyrR = [np.ascontiguousarray(p, np.uint8) for p in pyrR]
+    lw = np.array([p.shape[1] for p in pyrL], np.int32)
+    lh = np.array([p.shape[0] for p in pyrL], np.int32)
+    PL = (C.c_void_p * nlev)(*[p.ctypes.data for p in pyrL])
+    PR = (C.c_void_p * nlev)(*[p.ctypes.data for p in pyrR])
+    kL = np.ascontiguousarray(kL); kR = np.ascontiguousarray(kR)
+    dL = np.ascontiguousarray(dL, np.uint8); dR = np.ascontiguousarray(dR, np.uint8)
+    n = len(kL)
+    ur = np.zeros(max(n, 1), np.float32); dp = np.zeros(max(n, 1), np.float32)
+    scale = np.ascontiguousarray(scale, np.float32); inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+    b = np.float32(bf) / np.float32(fx)
+    lib.frameref_stereo.restype = C.c_int
+    lib.frameref_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.frameref_stereo(kL.ctypes.data, dL.ctypes.data, n, kR.ctypes.data, dR.ctypes.data, len(kR), PL, PR, lw.ctypes.data, lh.ctypes.data,
+                        nlev, scale.ctypes.data, inv_scale.ctypes.data, float(bf), float(b), ur.ctypes.data, dp.ctypes.data)
+    return ur[:n], dp[:n]
+
+
+def ref_features_in_area(keys, bounds, x, y, r, min_level, max_level):
+    lib = C.CDLL(FRAMEREF_SO)
+    keys = _a(keys, KP_DTYPE)
+    out = np.zeros(max(len(keys), 1), np.int32)
+    lib.frameref_features_in_area.restype = C.c_int
+    lib.frameref_features_in_area.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = lib.frameref_features_in_area(_ptr(keys), len(keys), *[float(b) for b in bounds], float(x), float(y), float(r), min_level,
+                                      max_level, _ptr(out), len(out))
+    return out[:n]
+
+
+def ref_is_in_frustum(F, P, Tcw, K, mbf, viewing_cos_limit=0.5):
+    """Frame::isInFrustum of the reference source; returns the same dict as port_is_in_frustum plus 'Ow' (mOw from SetPose)."""
+    lib = C.CDLL(FRAMEREF_SO)
+    wp, md, mx, mn, va = _points_args(P)
+    nr = _a(P.normal, np.float32)
+    T = _a(np.asarray(Tcw, np.float32)[:3, :4].reshape(12), np.float32)
+    n = len(wp)
+    inv = np.zeros(max(n, 1), np.uint8); px = np.zeros(max(n, 1), np.float32); py = np.zeros(max(n, 1), np.float32)
+    pxr = np.zeros(max(n, 1), np.float32); lv = np.zeros(max(n, 1), np.int32); vc = np.zeros(max(n, 1), np.float32)
+    ow = np.zeros(3, np.float32)
+    fn = lib.frameref_is_in_frustum
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p] + [C.c_float] * 11 + [C.c_int] + [C.c_void_p] * 7
+    cnt = fn(_ptr(wp), _ptr(nr), _ptr(mx), _ptr(mn), _ptr(va), n, _ptr(T), float(K[0]), float(K[1]), float(K[2]), float(K[3]), float(mbf),
+             *[float(b) for b in F.bounds], float(viewing_cos_limit), _log_scale(F), len(F.mvScaleFactors), _ptr(inv), _ptr(px), _ptr(py),
+             _ptr(pxr), _ptr(lv), _ptr(vc), _ptr(ow))
+    return dict(count=cnt, in_view=inv[:n], proj_x=px[:n], proj_y=py[:n], proj_xr=pxr[:n], level=lv[:n], view_cos=vc[:n], Ow=ow)
