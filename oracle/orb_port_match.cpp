@@ -7,9 +7,13 @@
 //   ORBmatcher::SearchForTriangulation                            src/ORBmatcher.cc:657-823, CheckDistEpipolarLine :140-157
 //   ORBmatcher::ComputeThreeMaxima / DescriptorDistance           src/ORBmatcher.cc:1601-1663
 //   TemplatedVocabulary::transform / loadFromTextFile             Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259, 1338-1424
-// ORBmatcher.cc / Frame.cc cannot be compiled on their own (they include the whole type graph), and the
-// reference holds no tests for them: parity for these functions is pinned by these restatements only
-// ("parity unpinned" by the reference itself — SURVEY.md §8c).
+// (further down: the other SearchByProjection overloads, SearchForInitialization, SearchBySim3, Fuse x2, Frame::isInFrustum,
+//  MapPoint::PredictScale / ComputeDistinctiveDescriptors, L1Scoring::score, KeyFrameDatabase candidate detection.)
+// The reference holds no tests for these functions ("parity unpinned" by the reference itself — SURVEY.md §8c).  The
+// restatements are pinned to the reference SOURCE instead: src/ORBmatcher.cc and src/Frame.cc are compiled verbatim
+// against plain-data stand-ins of the types they point to (oracle/_ref/libmatchref.so, libframeref.so; oracle/Makefile)
+// and tests/test_oracle_match_ref.py / test_oracle_frame_ref.py assert equality on every fixture.  The vocabulary,
+// scoring and keyframe-database functions have no such pin (re-derived a second time in numpy, tests/test_oracle_match.py).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
