@@ -9,7 +9,10 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #define CV_8U 0
@@ -36,6 +39,8 @@ public:
         data = buf->data();
     }
     static int esz(int t) { return t == CV_32F ? 4 : 1; }
+    void create(int r, int c, int t) { *this = Mat(r, c, t); }
+    void release() { *this = Mat(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     int type() const { return type_; }
     template <typename T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
@@ -136,6 +141,32 @@ inline double norm(const Mat& a, const Mat& b, int /*NORM_L1*/) {      // sum |a
         for (int j = 0; j < a.cols; j++) s += std::fabs((double)a.at<float>(i, j) - (double)b.at<float>(i, j));
     return s;
 }
+// cv::FileStorage / cv::FileNode: only so that the YAML save/load members of DBoW2's TemplatedVocabulary (virtual, hence always
+// instantiated) compile; the oracle loads vocabularies through loadFromTextFile and never calls them.
+class FileNode {
+public:
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0.0; }
+    operator float() const { return 0.f; }
+    operator std::string() const { return std::string(); }
+};
+class FileStorage {
+public:
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const char*, int) {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    template <typename T> FileStorage& operator<<(const T&) { return *this; }
+};
+
 inline void undistortPoints(const Mat&, Mat&, const Mat&, const Mat&, const Mat&, const Mat&) {}   // never run by the oracle
 
 // cv::Mat_<float>(3,1) << x, y, z   (Frame::UnprojectStereo)

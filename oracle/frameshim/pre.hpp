@@ -19,6 +19,8 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <sstream>
+#include <thread>
 #include <vector>
 
 #include <opencv2/core/core.hpp>
@@ -82,3 +84,7 @@ public:
 };
 
 }  // namespace ORB_SLAM2
+
+// AssignFeaturesToGrid is a private member of the reference's Frame; the wrapper has to call it.  Defined here, after every
+// standard header has been seen (libstdc++ does not survive the redefinition), and before Frame.h is.
+#define private public

@@ -871,3 +871,70 @@ def ref_is_in_frustum(F, P, Tcw, K, mbf, viewing_cos_limit=0.5):
              *[float(b) for b in F.bounds], float(viewing_cos_limit), _log_scale(F), len(F.mvScaleFactors), _ptr(inv), _ptr(px), _ptr(py),
              _ptr(pxr), _ptr(lv), _ptr(vc), _ptr(ow))
     return dict(count=cnt, in_view=inv[:n], proj_x=px[:n], proj_y=py[:n], proj_xr=pxr[:n], level=lv[:n], view_cos=vc[:n], Ow=ow)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's DBoW2 and src/KeyFrameDatabase.cc compiled verbatim (oracle/_ref/libdbowref.so, oracle/dbowref_wrap.cpp).
+DBOWREF_SO = os.path.join(HERE, "_ref", "libdbowref.so")
+
+
+def have_dbowref() -> bool:
+    return os.path.exists(DBOWREF_SO)
+
+
+class RefVocabulary:
+    """ORBVocabulary of the reference (DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>), loaded with its own loadFromTextFile."""
+
+    def __init__(self, text_path):
+        self._lib = C.CDLL(DBOWREF_SO)
+        self._lib.dbowref_voc_load_text.restype = C.c_void_p
+        self._lib.dbowref_voc_load_text.argtypes = [C.c_char_p]
+        self._h = self._lib.dbowref_voc_load_text(str(text_path).encode())
+        if not self._h:
+            raise RuntimeError("loadFromTextFile failed")
+        self._lib.dbowref_voc_words.argtypes = [C.c_void_p]
+        self.words = self._lib.dbowref_voc_words(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.dbowref_voc_destroy.argtypes = [C.c_void_p]
+            self._lib.dbowref_voc_destroy(self._h)
+            self._h = None
+
+    def transform(self, desc, levelsup):
+        """-> (bow {word: value}, fv_node, fv_start, fv_idx)"""
+        d = _a(desc, np.uint8)
+        n = len(d)
+        bw = np.zeros(max(n, 1), np.uint32); bv = np.zeros(max(n, 1), np.float64); nb = C.c_int(0)
+        fn_ = np.zeros(max(n, 1), np.uint32); fs = np.zeros(max(n, 1) + 1, np.int32); fi = np.zeros(max(n, 1), np.uint32); nn = C.c_int(0)
+        f = self._lib.dbowref_transform
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        f(self._h, _ptr(d), n, int(levelsup), _ptr(bw), _ptr(bv), C.addressof(nb), _ptr(fn_), _ptr(fs), _ptr(fi), C.addressof(nn))
+        k, a = nb.value, nn.value
+        return dict(zip(bw[:k].tolist(), bv[:k].tolist())), fn_[:a].copy(), fs[:a + 1].copy(), fi[:fs[a]].copy()
+
+    def score(self, bow1, bow2):
+        w1 = _a(np.fromiter(bow1.keys(), np.uint32, len(bow1)), np.uint32); v1 = _a(np.fromiter(bow1.values(), np.float64, len(bow1)), np.float64)
+        w2 = _a(np.fromiter(bow2.keys(), np.uint32, len(bow2)), np.uint32); v2 = _a(np.fromiter(bow2.values(), np.float64, len(bow2)), np.float64)
+        f = self._lib.dbowref_score
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        return float(f(self._h, _ptr(w1) if len(w1) else None, _ptr(v1) if len(v1) else None, len(w1), _ptr(w2) if len(w2) else None,
+                       _ptr(v2) if len(v2) else None, len(w2)))
+
+    def detect_candidates(self, loop, kf_bows, q_bow, connected, neigh, min_score=0.0):
+        start = np.zeros(len(kf_bows) + 1, np.int32)
+        start[1:] = np.cumsum([len(b) for b in kf_bows])
+        kw = _a(np.concatenate([np.fromiter(b.keys(), np.uint32, len(b)) for b in kf_bows] + [np.zeros(0, np.uint32)]), np.uint32)
+        kv = _a(np.concatenate([np.fromiter(b.values(), np.float64, len(b)) for b in kf_bows] + [np.zeros(0, np.float64)]), np.float64)
+        qw = _a(np.fromiter(q_bow.keys(), np.uint32, len(q_bow)), np.uint32); qv = _a(np.fromiter(q_bow.values(), np.float64, len(q_bow)), np.float64)
+        ng = _a(np.asarray(neigh, np.int32).reshape(len(kf_bows), 10), np.int32)
+        cn = _a(np.asarray(connected if connected is not None else np.zeros(len(kf_bows)), np.uint8), np.uint8)
+        out = np.zeros(max(len(kf_bows), 1), np.int32)
+        f = self._lib.dbowref_detect_candidates
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        n = f(self._h, int(loop), len(kf_bows), _ptr(start), _ptr(kw), _ptr(kv), _ptr(qw) if len(qw) else None, _ptr(qv) if len(qv) else None,
+              len(qw), _ptr(cn), _ptr(ng), float(np.float32(min_score)), _ptr(out))
+        return out[:n].tolist()

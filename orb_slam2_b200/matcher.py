@@ -470,6 +470,25 @@ def loop_candidates(cw, sc, fw, seq, connected, covisibility, minScore) -> list:
     return out
 
 
+def bow_and_featvec(word, weight, node):
+    """The bookkeeping half of TemplatedVocabulary::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1150-1194) from the
+    per-feature results of the tree descent (word id, word weight, node id at level L-levelsup): BowVector::addWeight in
+    feature order for every feature whose word weight is > 0 ("not stopped"), L1 normalisation with the norm summed in map
+    (word id) order, FeatureVector::addFeature in feature order."""
+    word = np.asarray(word); weight = np.asarray(weight, np.float64); node = np.asarray(node)
+    bow: Dict[int, float] = {}
+    keep = weight > 0
+    for i in np.nonzero(keep)[0]:
+        w = int(word[i])
+        bow[w] = bow.get(w, 0.0) + float(weight[i])
+    norm = 0.0                                   # plain left-to-right accumulation: Python >= 3.12's sum() is compensated, the
+    for _, v in sorted(bow.items()):             # reference's `norm += fabs(it->second)` loop (BowVector.cpp:67-70) is not
+        norm += abs(v)
+    if norm > 0.0:
+        bow = {k: v / norm for k, v in bow.items()}
+    return dict(sorted(bow.items())), FeatureVector.from_nodes(node, keep)
+
+
 class KeyFrameDatabase:
     """KeyFrameDatabase (include/KeyFrameDatabase.h) with the keyframes resident in HBM.  add/erase/clear mirror
     src/KeyFrameDatabase.cc:41-73; query() is the data-parallel part of DetectLoopCandidates / DetectRelocalizationCandidates
@@ -607,14 +626,5 @@ class ORBVocabulary:
 
     def transform(self, descriptors: np.ndarray, levelsup: int = 4):
         """transform(features, BowVector, FeatureVector, levelsup) (:1127-1194) for TF-IDF / L1 (ORBvoc.txt "10 6 0 0"):
-        the tree descent runs on the GPU; the ordered-map bookkeeping is done here in feature order, as the reference does."""
-        word, weight, node = self.transform_raw(descriptors, levelsup)
-        bow: Dict[int, float] = {}
-        keep = weight > 0                               # "not stopped"
-        for i in np.nonzero(keep)[0]:
-            w = int(word[i])
-            bow[w] = bow.get(w, 0.0) + float(weight[i])     # BowVector::addWeight, accumulated in feature order
-        norm = sum(abs(v) for _, v in sorted(bow.items()))   # L1, summed in map (word id) order
-        if norm > 0.0:
-            bow = {k: v / norm for k, v in bow.items()}
-        return dict(sorted(bow.items())), FeatureVector.from_nodes(node, keep)
+        the tree descent runs on the GPU; the ordered-map bookkeeping is done on the host in feature order, as the reference does."""
+        return bow_and_featvec(*self.transform_raw(descriptors, levelsup))
