@@ -63,6 +63,7 @@ public:
         for (int r = 0; r < rows; r++) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz(type_));
         return m;
     }
+    void copyTo(Mat& dst) const { dst = clone(); }
     Mat t() const {
         Mat m(cols, rows, CV_32F);
         for (int r = 0; r < rows; r++)

@@ -938,3 +938,51 @@ class RefVocabulary:
         n = f(self._h, int(loop), len(kf_bows), _ptr(start), _ptr(kw), _ptr(kv), _ptr(qw) if len(qw) else None, _ptr(qv) if len(qv) else None,
               len(qw), _ptr(cn), _ptr(ng), float(np.float32(min_score)), _ptr(out))
         return out[:n].tolist()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's src/MapPoint.cc compiled verbatim against its real include/MapPoint.h (oracle/_ref/libmapref.so).
+MAPREF_SO = os.path.join(HERE, "_ref", "libmapref.so")
+
+
+def have_mapref() -> bool:
+    return os.path.exists(MAPREF_SO)
+
+
+def ref_predict_scale(max_distance, dist, log_scale, n_levels, use_frame=False):
+    lib = C.CDLL(MAPREF_SO)
+    mx = _a(max_distance, np.float32); ds = _a(dist, np.float32)
+    out = np.zeros(max(len(mx), 1), np.int32)
+    lib.mapref_predict_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    lib.mapref_predict_scale(_ptr(mx), _ptr(ds), len(mx), float(np.float32(log_scale)), int(n_levels), int(use_frame), _ptr(out))
+    return out[:len(mx)]
+
+
+def port_predict_scale(max_distance, dist, log_scale, n_levels):
+    lib = _plib()
+    mx = _a(max_distance, np.float32); ds = _a(dist, np.float32)
+    out = np.zeros(max(len(mx), 1), np.int32)
+    lib.orbport_predict_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.orbport_predict_scale(_ptr(mx), _ptr(ds), len(mx), float(np.float32(log_scale)), int(n_levels), _ptr(out))
+    return out[:len(mx)]
+
+
+def ref_distance_invariance(max_distance, min_distance):
+    lib = C.CDLL(MAPREF_SO)
+    mx = _a(max_distance, np.float32); mn = _a(min_distance, np.float32)
+    omx = np.zeros(max(len(mx), 1), np.float32); omn = np.zeros(max(len(mx), 1), np.float32)
+    lib.mapref_distance_invariance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.mapref_distance_invariance(_ptr(mx), _ptr(mn), len(mx), _ptr(omx), _ptr(omn))
+    return omx[:len(mx)], omn[:len(mx)]
+
+
+def ref_distinctive_descriptor(desc, bad=None):
+    """MapPoint::ComputeDistinctiveDescriptors of the reference source -> the chosen 32-byte descriptor (None if none)."""
+    lib = C.CDLL(MAPREF_SO)
+    d = _a(np.asarray(desc, np.uint8).reshape(-1, 32), np.uint8)
+    b = _a(bad, np.uint8) if bad is not None else None
+    out = np.zeros(32, np.uint8)
+    lib.mapref_distinctive_descriptor.restype = C.c_int
+    lib.mapref_distinctive_descriptor.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    ok = lib.mapref_distinctive_descriptor(_ptr(d) if len(d) else None, _ptr(b) if b is not None else None, len(d), _ptr(out))
+    return out if ok else None

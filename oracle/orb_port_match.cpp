@@ -1052,3 +1052,8 @@ extern "C" int orbport_detect_loop_candidates(int n_kf, const int32_t* kf_start,
         if (it.first > minScoreToRetain && !added[it.second]) { out[n_out++] = it.second; added[it.second] = 1; }
     return n_out;
 }
+
+// element-wise MapPoint::PredictScale, exported for tests/test_oracle_map_ref.py
+extern "C" void orbport_predict_scale(const float* max_distance, const float* dist, int n, float log_scale, int n_levels, int32_t* out) {
+    for (int i = 0; i < n; i++) out[i] = predict_scale(max_distance[i], dist[i], log_scale, n_levels);
+}
