@@ -152,3 +152,19 @@ def test_remap_linear_matches_cv2(lib):
         lib.orbport_remap_linear(im.ctypes.data_as(u8p), im.shape[1], im.shape[0], im.strides[0], m1c.ctypes.data_as(f32p),
                                  m2c.ctypes.data_as(f32p), got.ctypes.data_as(u8p), m1.shape[1], m1.shape[0], got.strides[0])
         assert np.array_equal(got, want), int((got != want).sum())
+
+
+def test_small_float_gemm_order_matches_cv2():
+    """The cv::Mat products of the matcher / frame code (Rcw*p3Dw+tcw, -Rcw.t()*tcw, ...) are OpenCV gemm calls on 3x3 / 3x1
+    CV_32F matrices.  oracle/cvmini (used by the verbatim builds of ORBmatcher.cc / Frame.cc), the restatements and the CUDA
+    kernels all evaluate them as ((a0*b0 + a1*b1) + a2*b2) + c in float32, no FMA; cv2 agrees on every sample."""
+    rng = np.random.default_rng(0)
+    f32 = np.float32
+    for _ in range(5000):
+        R = rng.normal(0, 1, (3, 3)).astype(f32); p = rng.normal(0, 5, (3, 1)).astype(f32); t = rng.normal(0, 2, (3, 1)).astype(f32)
+        mine = np.array([[f32(f32(f32(R[i, 0] * p[0, 0]) + f32(R[i, 1] * p[1, 0])) + f32(R[i, 2] * p[2, 0])) + t[i, 0]] for i in range(3)], f32)
+        assert np.array_equal(cv2.gemm(R, p, 1.0, t, 1.0), mine)
+        assert np.array_equal(cv2.gemm(R, p, 1.0, None, 0.0) + t, mine)
+        M = rng.normal(0, 1, (3, 3)).astype(f32)
+        mm = np.array([[f32(f32(f32(R[i, 0] * M[0, j]) + f32(R[i, 1] * M[1, j])) + f32(R[i, 2] * M[2, j])) for j in range(3)] for i in range(3)], f32)
+        assert np.array_equal(cv2.gemm(R, M, 1.0, None, 0.0), mm)
