@@ -288,3 +288,15 @@ def test_search_local_points_frustum_plus_projection(M, oracle, views, seed, th,
     for f in ("proj_x", "proj_y", "proj_xr", "level", "view_cos"):
         assert np.array_equal(got[f], fr[f]), f                           # bit-identical floats, not just close
     assert got["nmatches"] == n_o and np.array_equal(got["match"], m_o), int((got["match"] != m_o).sum())
+
+
+from tests.golden_match_cases import CASES as GOLDEN_CASES, flatten as golden_flatten     # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_matches_reference_golden_vectors(M, oracle, name):
+    """tests/golden/match_ref.npz holds what the reference's own src/ORBmatcher.cc (compiled verbatim, oracle/_ref/libmatchref.so)
+    produced for these seeded cases (tests/golden/make_golden_match.py); the CUDA library must reproduce it bit for bit."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "match_ref.npz"))
+    build, _port, gpu = GOLDEN_CASES[name]
+    assert np.array_equal(golden_flatten(gpu(M, build(oracle))), g[name])
