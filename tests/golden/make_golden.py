@@ -1,8 +1,9 @@
 """Generates tests/golden/*.npz from the REFERENCE ITSELF (oracle/_ref: /root/reference/src/ORBextractor.cc
 compiled verbatim + cv shim pinned to cv2 4.13 + monotonic allocator) — run in the build container where
 /root/reference exists:   python tests/golden/make_golden.py
-The stereo vectors come from the line-by-line restatement of Frame.cc:466-640 (the reference's Frame.cc
-cannot be compiled without the whole type graph), fed with the reference extractor's outputs."""
+The stereo vectors were written with the line-by-line restatement of Frame.cc:466-640 fed with the reference extractor's outputs;
+tests/test_golden_oracle.py::test_stereo_golden_equals_verbatim_frame_cc shows that the reference's own Frame.cc, compiled verbatim
+(oracle/_ref/libframeref.so), produces exactly the same numbers."""
 import os
 import sys
 
