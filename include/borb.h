@@ -414,6 +414,9 @@ BORB_API borb_status borb_bow_transform(borb_voc* v, const uint8_t* desc, int n,
 BORB_API borb_status borb_debug_candidates(borb_extractor* e, int image, int level, int32_t* xys, int cap, int* n_out);
 BORB_API borb_status borb_debug_selected(borb_extractor* e, int image, int level, int32_t* xys, int cap, int* n_out);
 BORB_API borb_status borb_debug_blurred(borb_extractor* e, int image, int level, uint8_t* dst, int* w, int* h);
+/* Ablation of fast_kernel for the speed-of-light table in profiles/ (0 = full kernel, the only mode that produces
+ * keypoints; 1 = TMA tile load only, 2 = + packed reject pass, 3 = + exact scores without NMS / emit). */
+BORB_API borb_status borb_debug_set_fast_mode(borb_extractor* e, int mode);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 BORB_API borb_status borb_launch_count(const borb_extractor* e, uint64_t* n);
 /* Device time (ms, CUDA events on the handle's stream) of each stage of the last batch:

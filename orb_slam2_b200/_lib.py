@@ -107,6 +107,7 @@ _SIGNATURES = {
     "borb_debug_candidates": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, i32p]),
     "borb_debug_selected": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, i32p]),
     "borb_debug_blurred": (C.c_int, [vp, C.c_int, C.c_int, vp, i32p, i32p]),
+    "borb_debug_set_fast_mode": (C.c_int, [vp, C.c_int]),
     "borb_launch_count": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
     "borb_stage_times": (C.c_int, [vp, f32p]),
     "borb_set_timing": (C.c_int, [vp, C.c_int]),

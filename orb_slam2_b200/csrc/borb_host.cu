@@ -21,6 +21,24 @@ void set_error(const char* fmt, ...) {
     tl_error = buf;
 }
 
+bool allow_max_smem(const void* func) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& d : done)
+        if (d.first == func && d.second == dev) return true;
+    cudaFuncAttributes fa;
+    int optin = 0;
+    cudaError_t e = cudaFuncGetAttributes(&fa, func);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e != cudaSuccess) { set_error("raising the shared-memory limit failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return false; }
+    done.push_back({func, dev});
+    return true;
+}
+
 namespace {
 
 inline int cv_round_f(float v) { return (int)lrintf(v); }     // cvRound: round-half-even
@@ -122,6 +140,7 @@ borb_status build_geometry(borb_extractor* e, int w, int h, std::vector<int16_t>
     std::memset(&g, 0, sizeof(g));
     const int L = e->cfg.n_levels;
     g.nlevels = L; g.w = w; g.h = h;
+    g.fast_mode = e->fast_mode;
     g.ini_th = e->cfg.ini_th_fast < 0 ? 0 : (e->cfg.ini_th_fast > 255 ? 255 : e->cfg.ini_th_fast);
     g.min_th = e->cfg.min_th_fast < 0 ? 0 : (e->cfg.min_th_fast > 255 ? 255 : e->cfg.min_th_fast);
     for (int i = 0; i < 16; i++) g.umax[i] = e->umax[i];
@@ -738,6 +757,13 @@ borb_status borb_debug_candidates(borb_extractor* e, int image, int level, int32
 }
 borb_status borb_debug_selected(borb_extractor* e, int image, int level, int32_t* xys, int cap, int* n_out) {
     return debug_list(e, image, level, true, xys, cap, n_out);
+}
+
+borb_status borb_debug_set_fast_mode(borb_extractor* e, int mode) {
+    if (!e || mode < 0 || mode > 3) { set_error("fast mode must be 0..3"); return BORB_ERR_INVALID_ARG; }
+    e->fast_mode = mode;
+    if (e->have_geom) e->geom.fast_mode = mode;
+    return BORB_OK;
 }
 
 borb_status borb_launch_count(const borb_extractor* e, uint64_t* n) {

@@ -55,6 +55,8 @@ struct Geometry {
     int nlevels;
     int w, h;
     int ini_th, min_th;
+    int fast_mode;              // 0: full kernel.  Ablation (borb_debug_set_fast_mode): 1 = TMA tile load only, 2 = + packed reject,
+                                // 3 = + exact scores (no NMS / emit)
     int fast_blocks;            // FAST CTAs per image (all levels)
     unsigned pyr_image_stride;  // bytes
     unsigned cand_image_stride; // entries
@@ -91,6 +93,11 @@ struct Workspace {
 };
 
 void set_error(const char* fmt, ...);
+// Raises `func`'s dynamic shared-memory limit to the device's opt-in maximum (minus the kernel's static shared memory),
+// ONCE per (kernel, device) under a mutex.  The attribute is per function and per device and is shared by every handle
+// on every host thread, so it must never be lowered between another thread's set and launch (handles on the Tracking,
+// LocalMapping and LoopClosing threads launch the same kernels concurrently).  Returns false (and sets the error) on failure.
+bool allow_max_smem(const void* func);
 #define BORB_CUDA(call)                                                                             \
     do {                                                                                            \
         cudaError_t _e = (call);                                                                    \
@@ -151,6 +158,7 @@ struct borb_extractor {
     // rectification maps (borb_extractor_set_rectify_maps): set 0 = mono / left, set 1 = right; device float maps
     float* d_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int map_src_w = 0, map_src_h = 0, map_dst_w = 0, map_dst_h = 0;
+    int fast_mode = 0;           // fast_kernel ablation mode (borb_debug_set_fast_mode)
     uint64_t launches = 0;
     // stage timing: a ring of event sets so that many queued steps can be timed without host syncs
     static constexpr int EV_RING = 128;

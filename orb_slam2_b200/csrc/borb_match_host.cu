@@ -208,7 +208,7 @@ borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F,
     borb_status s = commit(st, total);
     if (s != BORB_OK) return s;
     uint8_t* b = m->arena;
-    ProjArgs A;
+    ProjArgs A{};
     A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
     A.u_right = F->u_right ? (const float*)(b + o_ur) : nullptr;
     A.occupied = F->occupied ? b + o_occ : nullptr;
@@ -313,7 +313,7 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     borb_status s = commit(st, total);
     if (s != BORB_OK) return s;
     uint8_t* b = m->arena;
-    LastArgs L;
+    LastArgs L{};
     L.variant = Q.variant;
     L.n_last = nq; L.last_keys = Q.keys ? (const borb_keypoint*)(b + o_lk) : nullptr; L.world_pos = (const float*)(b + o_wp);
     L.q_angle_in = Q.angle ? (const float*)(b + o_qa) : nullptr;
@@ -332,7 +332,7 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     L.forward = Q.forward; L.backward = Q.backward;
     L.proj_x = (float*)(b + o_px); L.proj_y = (float*)(b + o_py); L.proj_xr = (float*)(b + o_pxr); L.radius = (float*)(b + o_rad);
     L.angle = (float*)(b + o_ang); L.minl = (int32_t*)(b + o_minl); L.maxl = (int32_t*)(b + o_maxl); L.valid_out = b + o_val;
-    ProjArgs A;
+    ProjArgs A{};
     A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
     A.u_right = stereo ? (const float*)(b + o_ur) : nullptr;
     A.occupied = F->occupied ? b + o_occ : nullptr;

@@ -177,6 +177,10 @@ __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Ge
         "}\n" ::"r"(smem_u32(&bar))
         : "memory");
     __syncthreads();
+    if (g.fast_mode == 1) {                 // ablation: tile load only (one word per thread consumed so the copy is observed)
+        if (reinterpret_cast<const uint32_t*>(tile)[tid] == 0x12345678u && cand_cnt[0] == -1) cand[0] = 1;
+        return;
+    }
 
     // Pass A works at iniThFAST only: a cell falls back to minThFAST only if it has NO kept corner at iniThFAST
     // (ORBextractor.cc:809-816), and a pixel with S < ini can neither be kept at ini nor suppress one that is.
@@ -279,6 +283,10 @@ __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Ge
         }
     }
     __syncthreads();
+    if (g.fast_mode == 2) {                 // ablation: load + packed reject
+        if (wqn == -1) cand[0] = 1;
+        return;
+    }
 
     // ---- 1b. dense scoring pass over the deferred words
     {
@@ -305,6 +313,10 @@ __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Ge
     }
     __syncthreads();
     int nq = qn;
+    if (g.fast_mode == 3) {                 // ablation: load + reject + exact scores
+        if (nq == -1) cand[0] = 1;
+        return;
+    }
 
     uint32_t* out = cand + (size_t)img * g.cand_image_stride + L.cand_off;
     int* cnt = cand_cnt + img * g.nlevels + l;

@@ -1003,14 +1003,14 @@ int launch_grid_sort(const borb_keypoint* keys, int n, float minX, float minY, f
                      cudaStream_t s) {
     int K = 32;
     while (K < n) K <<= 1;
-    cudaFuncSetAttribute(grid_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K * 4);
+    allow_max_smem((const void*)grid_sort_kernel);
     grid_sort_kernel<<<1, 1024, K * 4, s>>>(keys, n, minX, minY, invW, invH, K, cell_start, cell_idx);
     return 1;
 }
 int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s) {
     if (A.n_mp > 0) proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
     const size_t smem = resolve_smem_words(A.n, A.n_mp) * 4;
-    cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    allow_max_smem((const void*)proj_resolve_kernel);
     proj_resolve_kernel<<<1, REPLAY_THREADS, smem, s>>>(A, match_feat, n_matches);
     return 2;
 }
@@ -1021,7 +1021,7 @@ int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_
         proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
     }
     const size_t smem = resolve_smem_words(A.n, A.n_mp) * 4;
-    cudaFuncSetAttribute(proj_resolve_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    allow_max_smem((const void*)proj_resolve_last_kernel);
     proj_resolve_last_kernel<<<1, REPLAY_THREADS, smem, s>>>(A, A.keys, state_cur, ev_idx, ev_bin, n_matches);
     return 3;
 }
@@ -1063,7 +1063,7 @@ int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, fl
                      int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s) {
     const int words = (max_t + 31) / 32;
     const size_t smem = (size_t)(words + BOW_WARPS * BOW_WARP_WORDS) * 4;
-    cudaFuncSetAttribute(bow_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    allow_max_smem((const void*)bow_match_kernel);
     bow_match_kernel<<<n_pairs, 32 * BOW_WARPS, smem, s>>>(qs, ts, n_pairs, mode, nnratio, check_ori, match, out_stride, bins, n_matches, max_t);
     return 1;
 }

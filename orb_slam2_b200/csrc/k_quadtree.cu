@@ -308,8 +308,7 @@ int launch_quadtree(const Geometry& g, const Workspace& ws, int n_images, cudaSt
     int maxC = 0;
     for (int l = 0; l < g.nlevels; l++) maxC = g.lv[l].node_cap > maxC ? g.lv[l].node_cap : maxC;
     const size_t smem = quadtree_smem_bytes(maxC);
-    // per-device attribute; cheap, so set on every launch (handles may live on different GPUs)
-    cudaFuncSetAttribute(quadtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    allow_max_smem((const void*)quadtree_kernel);      // once per device; never lowered (handles on other threads share it)
     dim3 grid(g.nlevels, n_images);
     quadtree_kernel<<<grid, 256, smem, s>>>(g, ws.cand, ws.cand_cnt, ws.pnode, ws.sel, ws.sel_cnt);
     return 1;
