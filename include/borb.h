@@ -388,6 +388,18 @@ BORB_API borb_status borb_search_by_bow_db(borb_matcher* m, borb_kfdb* db, const
                                            const borb_keyframe_view* frame, float nnratio, int check_orientation, int32_t* match,
                                            int32_t* n_matches);
 
+/* The same search returning COMPACT results — the form to use against many keyframes (BASELINE configs[4]: one frame
+ * against a 2000-keyframe database; the dense matrix above would be 9.7 MB of D2H per query).  slots == NULL searches
+ * slots 0..n_kf-1 (n_kf must equal the slot count; erased slots give 0 matches).  n_matches[k] = return value of
+ * SearchByBoW for keyframe k.  If pairs != NULL: keyframe k's matches are pairs[pair_offset[k] .. + n_matches[k]), each
+ * (frame feature index) | (keyframe feature index) << 16, in FeatureVector order of the frame (node id, then feature index);
+ * the blocks of different keyframes are packed in no particular order.  *n_pairs_total = sum of n_matches; more than pairs_cap
+ * => BORB_ERR_CAPACITY (counts and offsets are still valid). */
+BORB_API borb_status borb_search_by_bow_db_pairs(borb_matcher* m, borb_kfdb* db, const int32_t* slots, int n_kf,
+                                                 const borb_keyframe_view* frame, float nnratio, int check_orientation,
+                                                 int32_t* n_matches, int32_t* pair_offset, uint32_t* pairs, int pairs_cap,
+                                                 int32_t* n_pairs_total);
+
 /* ---------------------------------------------------------------- vocabulary (BoW feeder) ---- */
 /* ORBVocabulary = DBoW2::TemplatedVocabulary<FORB> (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h).  The tree lives
  * in HBM as one packed blob (so it can be broadcast over NCCL once and shared by every stream of a GPU). */
@@ -417,6 +429,9 @@ BORB_API borb_status borb_debug_blurred(borb_extractor* e, int image, int level,
 /* Ablation of fast_kernel for the speed-of-light table in profiles/ (0 = full kernel, the only mode that produces
  * keypoints; 1 = TMA tile load only, 2 = + packed reject pass, 3 = + exact scores without NMS / emit). */
 BORB_API borb_status borb_debug_set_fast_mode(borb_extractor* e, int mode);
+/* Distance arithmetic of the database SearchByBoW kernel: 1 (default) = carry-save adder tree + 4 POPC per 256-bit distance,
+ * 0 = 8 POPC.  Same results; kept switchable for the measurement in profiles/. */
+BORB_API borb_status borb_debug_set_bow_csa(int on);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 BORB_API borb_status borb_launch_count(const borb_extractor* e, uint64_t* n);
 /* Device time (ms, CUDA events on the handle's stream) of each stage of the last batch:

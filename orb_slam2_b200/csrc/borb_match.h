@@ -91,6 +91,41 @@ struct BowDev {                   // one keyframe's BowVector in the device-resi
     int n;
 };
 
+struct KfStream {                  // one keyframe of the device-resident database, features permuted into FeatureVector order
+    const uint32_t* node;         // nn node ids, ascending
+    const int32_t* start;         // nn + 1 row offsets
+    const uint16_t* orig;         // m: feature index of row r (mFeatVec order: node, then feature index)
+    const float* angle;           // m: mvKeysUn[orig].angle
+    const uint8_t* hasmp;         // m: MapPoint present && !isBad(), per row
+    const uint8_t* desc;          // m x 32, 16-byte aligned
+    int nn, m, n, pad;
+};
+
+struct BowDbArgs {                // bowdb_match_kernel (k_bowdb.cu)
+    const KfStream* table;        // one entry per database slot (nn = 0: erased)
+    const int32_t* slots;         // n_kf slots to search, or null = slots 0..n_kf-1
+    int n_kf, parts;              // work items = n_kf x parts (a keyframe's nodes are split into `parts` ranges)
+    const uint8_t* frame_block;   // packed query frame (FrameBlockHdr + sections), 16-byte aligned, frame_bytes % 16 == 0
+    int frame_bytes, frame_in_smem;
+    float nnratio;
+    int check_ori;
+    uint32_t* table_out;          // n_kf x m_frame, preset to 0xFFFFFFFF
+    int* work_counter;            // preset to 0
+};
+
+struct BowDbFinal {               // bowdb_finalize_kernel
+    const uint32_t* table_out;
+    int n_kf, mf, check_ori;
+    const uint16_t* forig;        // frame feature index per frame position
+    int32_t* n_matches;           // n_kf
+    int32_t* pair_off;            // n_kf (may be null)
+    uint32_t* pairs;              // frame feature | keyframe feature << 16 (may be null)
+    int pairs_cap;
+    int* cursor;                  // preset to 0
+    int32_t* dense;               // n_kf x dense_stride preset to -1 (may be null): match[k][frame feature] = keyframe feature
+    int dense_stride;
+};
+
 struct TriArgs { float F[9]; float ex, ey; int only_stereo, check_ori; };
 
 struct VocDev {                   // views into the packed blob
@@ -117,6 +152,8 @@ int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best
 int launch_sim3_agree(const int32_t* match1, const int32_t* match2, int n1, int n2, int32_t* match12, int* n_found, cudaStream_t s);
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
                      int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s);
+int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, bool csa, int n_sm, cudaStream_t s);
+size_t bowdb_smem_bytes(int frame_bytes, bool frame_in_smem);
 int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,
                          int32_t* n_pairs, cudaStream_t s);
 int launch_bow_transform(const VocDev& V, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node,

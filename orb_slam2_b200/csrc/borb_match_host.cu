@@ -1,5 +1,6 @@
 // Host side of the matcher / vocabulary entry points of the C ABI (include/borb.h): snapshots arrive as plain host
 // arrays, are staged into one device arena per call, and every result is produced by the CUDA kernels in k_match.cu.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -694,14 +695,28 @@ borb_status borb_search_by_bow_kf(borb_matcher* m, const borb_keyframe_view* kf1
 
 // ---------------------------------------------------------------------------------------------------------------
 // Device-resident keyframe database: KeyFrameDatabase (src/KeyFrameDatabase.cc) + the keyframe-side inputs of SearchByBoW.
+// A keyframe is kept as a STREAM RECORD (k_bowdb.cu): features permuted into FeatureVector order so that a node's
+// descriptors are consecutive rows.  The reference guards add / erase / Detect*Candidates with mMutex (they run on the
+// LoopClosing, Tracking and LocalMapping threads); the handle carries the same mutex.
 struct borb_kfdb {
     int device = 0;
-    struct Entry { uint8_t* block = nullptr; KfDev dev{}; BowDev bow{nullptr, nullptr, 0}; uint8_t* has_mp = nullptr; bool alive = false; };
+    std::mutex mu;
+    struct Entry {
+        uint8_t* block = nullptr;
+        KfStream stream{};
+        BowDev bow{nullptr, nullptr, 0};
+        uint8_t* d_hasmp = nullptr;          // m bytes inside block (row order)
+        std::vector<uint16_t> orig;          // host copy of the row -> feature permutation (borb_kfdb_set_has_mp)
+        int n = 0;
+        bool alive = false;
+    };
     std::vector<Entry> entries;
     BowDev* d_table = nullptr;      // mirrors entries[*].bow
+    KfStream* d_stream = nullptr;   // mirrors entries[*].stream
     size_t table_cap = 0;
     bool dirty = true;
     size_t bytes = 0;
+    int n_sm = 0;
 };
 
 borb_status borb_kfdb_create(int device, borb_kfdb** out) {
@@ -712,25 +727,31 @@ borb_status borb_kfdb_create(int device, borb_kfdb** out) {
     if (device < 0 || device >= n) { set_error("device %d out of range", device); return BORB_ERR_INVALID_ARG; }
     borb_kfdb* db = new borb_kfdb();
     db->device = device;
+    cudaDeviceGetAttribute(&db->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (db->n_sm < 1) db->n_sm = 1;
     *out = db;
     return BORB_OK;
 }
 
-borb_status borb_kfdb_clear(borb_kfdb* db) {
-    if (!db) return BORB_OK;
+static void kfdb_clear_locked(borb_kfdb* db) {
     cudaSetDevice(db->device);
     cudaDeviceSynchronize();
     for (auto& e : db->entries) cudaFree(e.block);
     db->entries.clear();
     db->dirty = true;
     db->bytes = 0;
+}
+
+borb_status borb_kfdb_clear(borb_kfdb* db) {
+    if (!db) return BORB_OK;
+    std::lock_guard<std::mutex> lk(db->mu);
+    kfdb_clear_locked(db);
     return BORB_OK;
 }
 
 borb_status borb_kfdb_destroy(borb_kfdb* db) {
     if (!db) return BORB_OK;
-    borb_kfdb_clear(db);
-    cudaFree(db->d_table);
+    { std::lock_guard<std::mutex> lk(db->mu); kfdb_clear_locked(db); cudaFree(db->d_table); cudaFree(db->d_stream); }
     delete db;
     return BORB_OK;
 }
@@ -742,42 +763,49 @@ borb_status borb_kfdb_add(borb_kfdb* db, const borb_keyframe_view* kf, const uin
     if (s != BORB_OK) return s;
     for (int i = 1; i < n_bow; i++)
         if (bow_word[i] <= bow_word[i - 1]) { set_error("BowVector words must ascend (std::map order)"); return BORB_ERR_INVALID_ARG; }
+    const int nn = kf->fv.n_nodes;
+    const int m = nn > 0 ? kf->fv.start[nn] : 0;
+    for (int a = 0; a < nn; a++)
+        if (kf->fv.start[a + 1] < kf->fv.start[a] || (a > 0 && kf->fv.node_id[a] <= kf->fv.node_id[a - 1])) { set_error("FeatureVector nodes must ascend"); return BORB_ERR_INVALID_ARG; }
+    for (int r = 0; r < m; r++)
+        if (kf->fv.feat_idx[r] >= (uint32_t)kf->n) { set_error("FeatureVector index %u outside the keyframe's %d features", kf->fv.feat_idx[r], kf->n); return BORB_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(db->mu);
     BORB_CUDA(cudaSetDevice(db->device));
-    // one device block per keyframe: [keys | desc | has_mp | u_right | node | start | idx | bow words | bow values]
+    // one device block per keyframe: [node | start | orig | angle | hasmp | desc (rows in FeatureVector order) | bow words | bow values]
     size_t off = 0;
     auto put = [&](size_t bytes) { off = (off + 255) & ~size_t(255); const size_t o = off; off += bytes; return o; };
-    const int total_idx = kf->fv.n_nodes > 0 ? kf->fv.start[kf->fv.n_nodes] : 0;
-    const size_t o_keys = put((size_t)kf->n * sizeof(borb_keypoint)), o_desc = put((size_t)kf->n * 32), o_hm = put((size_t)kf->n);
-    const size_t o_ur = put(kf->u_right ? (size_t)kf->n * 4 : 0);
-    const size_t o_node = put((size_t)kf->fv.n_nodes * 4), o_start = put((size_t)(kf->fv.n_nodes + 1) * 4), o_idx = put((size_t)total_idx * 4);
+    const size_t o_node = put((size_t)nn * 4), o_start = put((size_t)(nn + 1) * 4), o_orig = put((size_t)m * 2), o_ang = put((size_t)m * 4);
+    const size_t o_hm = put((size_t)m), o_desc = put((size_t)m * 32);
     const size_t o_bw = put((size_t)n_bow * 4), o_bv = put((size_t)n_bow * 8);
     const size_t total = off + 256;
     std::vector<uint8_t> h(total, 0);
-    if (kf->n) {
-        std::memcpy(&h[o_keys], kf->keys_un, (size_t)kf->n * sizeof(borb_keypoint));
-        std::memcpy(&h[o_desc], kf->desc, (size_t)kf->n * 32);
-        if (kf->has_mp) std::memcpy(&h[o_hm], kf->has_mp, (size_t)kf->n);
-        if (kf->u_right) std::memcpy(&h[o_ur], kf->u_right, (size_t)kf->n * 4);
-    }
-    if (kf->fv.n_nodes) {
-        std::memcpy(&h[o_node], kf->fv.node_id, (size_t)kf->fv.n_nodes * 4);
-        std::memcpy(&h[o_start], kf->fv.start, (size_t)(kf->fv.n_nodes + 1) * 4);
-        std::memcpy(&h[o_idx], kf->fv.feat_idx, (size_t)total_idx * 4);
+    borb_kfdb::Entry e;
+    e.orig.resize(m);
+    if (nn) {
+        std::memcpy(&h[o_node], kf->fv.node_id, (size_t)nn * 4);
+        std::memcpy(&h[o_start], kf->fv.start, (size_t)(nn + 1) * 4);
+        uint16_t* orig = reinterpret_cast<uint16_t*>(&h[o_orig]);
+        float* ang = reinterpret_cast<float*>(&h[o_ang]);
+        for (int r = 0; r < m; r++) {
+            const uint32_t f = kf->fv.feat_idx[r];
+            orig[r] = (uint16_t)f; e.orig[r] = (uint16_t)f;
+            ang[r] = kf->keys_un[f].angle;
+            h[o_hm + r] = kf->has_mp ? kf->has_mp[f] : 0;
+            std::memcpy(&h[o_desc + (size_t)r * 32], kf->desc + (size_t)f * 32, 32);
+        }
     }
     if (n_bow) { std::memcpy(&h[o_bw], bow_word, (size_t)n_bow * 4); std::memcpy(&h[o_bv], bow_value, (size_t)n_bow * 8); }
-    borb_kfdb::Entry e;
     BORB_CUDA(cudaMalloc(&e.block, total));
     BORB_CUDA(cudaMemcpy(e.block, h.data(), total, cudaMemcpyHostToDevice));
     uint8_t* b = e.block;
-    e.dev.n = kf->n; e.dev.nn = kf->fv.n_nodes;
-    e.dev.keys = (const borb_keypoint*)(b + o_keys); e.dev.desc = b + o_desc; e.dev.has_mp = b + o_hm;
-    e.dev.u_right = kf->u_right ? (const float*)(b + o_ur) : nullptr;
-    e.dev.node = (const uint32_t*)(b + o_node); e.dev.start = (const int32_t*)(b + o_start); e.dev.idx = (const uint32_t*)(b + o_idx);
-    e.dev.scale_factors = nullptr; e.dev.level_sigma2 = nullptr;
-    e.has_mp = b + o_hm;
+    e.stream.node = (const uint32_t*)(b + o_node); e.stream.start = (const int32_t*)(b + o_start); e.stream.orig = (const uint16_t*)(b + o_orig);
+    e.stream.angle = (const float*)(b + o_ang); e.stream.hasmp = b + o_hm; e.stream.desc = b + o_desc;
+    e.stream.nn = nn; e.stream.m = m; e.stream.n = kf->n; e.stream.pad = 0;
+    e.d_hasmp = b + o_hm;
+    e.n = kf->n;
     e.bow.word = (const uint32_t*)(b + o_bw); e.bow.value = (const double*)(b + o_bv); e.bow.n = n_bow;
     e.alive = true;
-    db->entries.push_back(e);
+    db->entries.push_back(std::move(e));
     db->dirty = true;
     db->bytes += total;
     *slot_out = (int32_t)db->entries.size() - 1;
@@ -785,9 +813,11 @@ borb_status borb_kfdb_add(borb_kfdb* db, const borb_keyframe_view* kf, const uin
 }
 
 borb_status borb_kfdb_erase(borb_kfdb* db, int32_t slot) {
-    if (!db || slot < 0 || slot >= (int)db->entries.size() || !db->entries[slot].alive) { set_error("bad keyframe slot"); return BORB_ERR_INVALID_ARG; }
+    if (!db) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(db->mu);
+    if (slot < 0 || slot >= (int)db->entries.size() || !db->entries[slot].alive) { set_error("bad keyframe slot"); return BORB_ERR_INVALID_ARG; }
     BORB_CUDA(cudaSetDevice(db->device));
-    BORB_CUDA(cudaDeviceSynchronize());
+    BORB_CUDA(cudaDeviceSynchronize());           // queries enqueued under the mutex may still be reading the block
     borb_kfdb::Entry& e = db->entries[slot];
     cudaFree(e.block);
     e = borb_kfdb::Entry();
@@ -796,31 +826,48 @@ borb_status borb_kfdb_erase(borb_kfdb* db, int32_t slot) {
 }
 
 borb_status borb_kfdb_set_has_mp(borb_kfdb* db, int32_t slot, const uint8_t* has_mp) {
-    if (!db || !has_mp || slot < 0 || slot >= (int)db->entries.size() || !db->entries[slot].alive) { set_error("bad keyframe slot"); return BORB_ERR_INVALID_ARG; }
+    if (!db || !has_mp) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(db->mu);
+    if (slot < 0 || slot >= (int)db->entries.size() || !db->entries[slot].alive) { set_error("bad keyframe slot"); return BORB_ERR_INVALID_ARG; }
     BORB_CUDA(cudaSetDevice(db->device));
-    BORB_CUDA(cudaMemcpy(db->entries[slot].has_mp, has_mp, (size_t)db->entries[slot].dev.n, cudaMemcpyHostToDevice));
+    const borb_kfdb::Entry& e = db->entries[slot];
+    std::vector<uint8_t> rows(e.orig.size());
+    for (size_t r = 0; r < rows.size(); r++) rows[r] = has_mp[e.orig[r]];
+    if (!rows.empty()) BORB_CUDA(cudaMemcpy(e.d_hasmp, rows.data(), rows.size(), cudaMemcpyHostToDevice));
     return BORB_OK;
 }
 
 borb_status borb_kfdb_size(const borb_kfdb* db, int32_t* n_slots, uint64_t* device_bytes) {
     if (!db) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(const_cast<borb_kfdb*>(db)->mu);
     if (n_slots) *n_slots = (int32_t)db->entries.size();
     if (device_bytes) *device_bytes = db->bytes;
     return BORB_OK;
 }
 
+// caller holds db->mu
 static borb_status kfdb_sync_table(borb_kfdb* db, cudaStream_t stream) {
     if (!db->dirty) return BORB_OK;
     const size_t n = db->entries.size();
     if (n > db->table_cap) {
-        BORB_CUDA(cudaStreamSynchronize(stream));
+        BORB_CUDA(cudaDeviceSynchronize());
         cudaFree(db->d_table); db->d_table = nullptr;
+        cudaFree(db->d_stream); db->d_stream = nullptr;
         db->table_cap = n + n / 2 + 64;
         BORB_CUDA(cudaMalloc(&db->d_table, db->table_cap * sizeof(BowDev)));
+        BORB_CUDA(cudaMalloc(&db->d_stream, db->table_cap * sizeof(KfStream)));
     }
+    (void)stream;
     std::vector<BowDev> t(n);
-    for (size_t i = 0; i < n; i++) t[i] = db->entries[i].alive ? db->entries[i].bow : BowDev{nullptr, nullptr, 0};
-    if (n) BORB_CUDA(cudaMemcpy(db->d_table, t.data(), n * sizeof(BowDev), cudaMemcpyHostToDevice));
+    std::vector<KfStream> st(n);
+    for (size_t i = 0; i < n; i++) {
+        t[i] = db->entries[i].alive ? db->entries[i].bow : BowDev{nullptr, nullptr, 0};
+        st[i] = db->entries[i].alive ? db->entries[i].stream : KfStream{};
+    }
+    if (n) {
+        BORB_CUDA(cudaMemcpy(db->d_table, t.data(), n * sizeof(BowDev), cudaMemcpyHostToDevice));
+        BORB_CUDA(cudaMemcpy(db->d_stream, st.data(), n * sizeof(KfStream), cudaMemcpyHostToDevice));
+    }
     db->dirty = false;
     return BORB_OK;
 }
@@ -829,26 +876,32 @@ borb_status borb_kfdb_query(borb_matcher* m, borb_kfdb* db, const uint32_t* bow_
                             int32_t* common_words, float* score, uint32_t* first_word, int cap, int32_t* n_slots) {
     if (!m || !db || !common_words || !score || !first_word || !n_slots || n_bow < 0 || (n_bow > 0 && (!bow_word || !bow_value))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
     if (m->device != db->device) { set_error("matcher and keyframe database live on different devices"); return BORB_ERR_INVALID_ARG; }
-    const int n = (int)db->entries.size();
-    *n_slots = n;
-    if (cap < n) { set_error("output capacity %d < %d database slots", cap, n); return BORB_ERR_CAPACITY; }
-    if (n == 0) return BORB_OK;
     for (int i = 1; i < n_bow; i++)
         if (bow_word[i] <= bow_word[i - 1]) { set_error("BowVector words must ascend (std::map order)"); return BORB_ERR_INVALID_ARG; }
-    BORB_CUDA(cudaSetDevice(m->device));
-    borb_status s = kfdb_sync_table(db, m->stream);
-    if (s != BORB_OK) return s;
-    Stager st(m);
-    const size_t o_w = st.add(bow_word, (size_t)n_bow * 4), o_v = st.add(bow_value, (size_t)n_bow * 8);
-    const size_t input_end = st.off;
-    const size_t o_c = st.reserve((size_t)n * 4), o_s = st.reserve((size_t)n * 4), o_f = st.reserve((size_t)n * 4);
-    const size_t total = st.off;
-    st.off = input_end;
-    if ((s = commit(st, total)) != BORB_OK) return s;
-    uint8_t* b = m->arena;
-    m->launches += launch_kfdb_score(db->d_table, n, (const uint32_t*)(b + o_w), (const double*)(b + o_v), n_bow, (int32_t*)(b + o_c),
-                                     (float*)(b + o_s), (uint32_t*)(b + o_f), m->stream);
-    BORB_CUDA(cudaGetLastError());
+    uint8_t* b = nullptr;
+    size_t o_c = 0, o_s = 0, o_f = 0;
+    int n = 0;
+    {
+        std::lock_guard<std::mutex> lk(db->mu);       // held across the table sync and the kernel enqueue (erase() synchronises the device before freeing)
+        n = (int)db->entries.size();
+        *n_slots = n;
+        if (cap < n) { set_error("output capacity %d < %d database slots", cap, n); return BORB_ERR_CAPACITY; }
+        if (n == 0) return BORB_OK;
+        BORB_CUDA(cudaSetDevice(m->device));
+        borb_status s = kfdb_sync_table(db, m->stream);
+        if (s != BORB_OK) return s;
+        Stager st(m);
+        const size_t o_w = st.add(bow_word, (size_t)n_bow * 4), o_v = st.add(bow_value, (size_t)n_bow * 8);
+        const size_t input_end = st.off;
+        o_c = st.reserve((size_t)n * 4); o_s = st.reserve((size_t)n * 4); o_f = st.reserve((size_t)n * 4);
+        const size_t total = st.off;
+        st.off = input_end;
+        if ((s = commit(st, total)) != BORB_OK) return s;
+        b = m->arena;
+        m->launches += launch_kfdb_score(db->d_table, n, (const uint32_t*)(b + o_w), (const double*)(b + o_v), n_bow, (int32_t*)(b + o_c),
+                                         (float*)(b + o_s), (uint32_t*)(b + o_f), m->stream);
+        BORB_CUDA(cudaGetLastError());
+    }
     BORB_CUDA(cudaMemcpyAsync(common_words, b + o_c, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaMemcpyAsync(score, b + o_s, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaMemcpyAsync(first_word, b + o_f, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -856,43 +909,143 @@ borb_status borb_kfdb_query(borb_matcher* m, borb_kfdb* db, const uint32_t* bow_
     return BORB_OK;
 }
 
+static std::atomic<int> g_bow_csa{1};
+borb_status borb_debug_set_bow_csa(int on) { g_bow_csa.store(on ? 1 : 0); return BORB_OK; }
+
+namespace {
+
+struct FrameBlockHdrHost { int32_t nn, m, n, off_node, off_start, off_orig, off_angle, off_desc, bytes, pad[7]; };   // == FrameBlockHdr (k_bowdb.cu)
+
+// Packs the query frame into FeatureVector order (k_bowdb.cu: FrameBlockHdr + sections) inside `dst` (16-byte aligned).
+size_t frame_block_bytes(const borb_keyframe_view* f) {
+    const int nn = f->fv.n_nodes, m = nn > 0 ? f->fv.start[nn] : 0;
+    size_t off = sizeof(FrameBlockHdrHost);
+    auto put = [&](size_t bytes) { off = (off + 15) & ~size_t(15); off += bytes; };
+    put((size_t)nn * 4); put((size_t)(nn + 1) * 4); put((size_t)m * 2); put((size_t)m * 4); put((size_t)m * 32);
+    return (off + 15) & ~size_t(15);
+}
+void pack_frame_block(const borb_keyframe_view* f, uint8_t* dst) {
+    const int nn = f->fv.n_nodes, m = nn > 0 ? f->fv.start[nn] : 0;
+    FrameBlockHdrHost h{};
+    size_t off = sizeof(FrameBlockHdrHost);
+    auto put = [&](size_t bytes) { off = (off + 15) & ~size_t(15); const size_t o = off; off += bytes; return o; };
+    h.nn = nn; h.m = m; h.n = f->n;
+    h.off_node = (int32_t)put((size_t)nn * 4); h.off_start = (int32_t)put((size_t)(nn + 1) * 4); h.off_orig = (int32_t)put((size_t)m * 2);
+    h.off_angle = (int32_t)put((size_t)m * 4); h.off_desc = (int32_t)put((size_t)m * 32);
+    h.bytes = (int32_t)((off + 15) & ~size_t(15));
+    std::memcpy(dst, &h, sizeof(h));
+    if (nn) std::memcpy(dst + h.off_node, f->fv.node_id, (size_t)nn * 4);
+    if (nn) std::memcpy(dst + h.off_start, f->fv.start, (size_t)(nn + 1) * 4);
+    else { const int32_t z = 0; std::memcpy(dst + h.off_start, &z, 4); }
+    uint16_t* orig = reinterpret_cast<uint16_t*>(dst + h.off_orig);
+    float* ang = reinterpret_cast<float*>(dst + h.off_angle);
+    for (int r = 0; r < m; r++) {
+        const uint32_t j = f->fv.feat_idx[r];
+        orig[r] = (uint16_t)j;
+        ang[r] = f->keys_un[j].angle;
+        std::memcpy(dst + h.off_desc + (size_t)r * 32, f->desc + (size_t)j * 32, 32);
+    }
+}
+
+// Shared body of the two database searches.  dense != null: match[k * frame->n + j]; pairs != null: compact list.
+borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, int n_kf, const borb_keyframe_view* frame, float nnratio,
+                         int check_ori, int32_t* dense, int32_t* n_matches, int32_t* pair_offset, uint32_t* pairs, int pairs_cap,
+                         int32_t* n_pairs_total) {
+    if (m->device != db->device) { set_error("matcher and keyframe database live on different devices"); return BORB_ERR_INVALID_ARG; }
+    borb_status s = check_kf(frame, "SearchByBoW(database, frame)");
+    if (s != BORB_OK) return s;
+    if (n_pairs_total) *n_pairs_total = 0;
+    if (n_kf == 0) return BORB_OK;
+    const int nn = frame->fv.n_nodes, mf = nn > 0 ? frame->fv.start[nn] : 0;
+    for (int a = 0; a < nn; a++)
+        if (frame->fv.start[a + 1] < frame->fv.start[a] || (a > 0 && frame->fv.node_id[a] <= frame->fv.node_id[a - 1])) { set_error("FeatureVector nodes must ascend"); return BORB_ERR_INVALID_ARG; }
+    for (int r = 0; r < mf; r++)
+        if (frame->fv.feat_idx[r] >= (uint32_t)frame->n) { set_error("FeatureVector index outside the frame's features"); return BORB_ERR_INVALID_ARG; }
+    if (dense) for (size_t i = 0; i < (size_t)n_kf * frame->n; i++) dense[i] = -1;
+    for (int i = 0; i < n_kf; i++) { n_matches[i] = 0; if (pair_offset) pair_offset[i] = 0; }
+    if (mf == 0) return BORB_OK;
+    uint8_t* b = nullptr;
+    size_t o_nm = 0, o_po = 0, o_pairs = 0, o_dense = 0, o_ctr = 0;
+    const size_t fbytes = frame_block_bytes(frame);
+    int dense_stride = frame->n;
+    {
+        std::lock_guard<std::mutex> lk(db->mu);
+        const int n_slots = (int)db->entries.size();
+        if (!slots && n_kf != n_slots) { set_error("slots == NULL searches every slot: n_kf must be %d", n_slots); return BORB_ERR_INVALID_ARG; }
+        if (slots)
+            for (int i = 0; i < n_kf; i++)
+                if (slots[i] < 0 || slots[i] >= n_slots || !db->entries[slots[i]].alive) { set_error("slot %d is not a live keyframe", slots[i]); return BORB_ERR_INVALID_ARG; }
+        BORB_CUDA(cudaSetDevice(m->device));
+        if ((s = kfdb_sync_table(db, m->stream)) != BORB_OK) return s;
+        Stager st(m);
+        const size_t o_fb = st.reserve(fbytes);                                  // filled in place below
+        const size_t o_sl = slots ? st.add(slots, (size_t)n_kf * 4) : 0;
+        const size_t input_end = st.off;
+        o_ctr = st.reserve(256);                                                   // work counter | pair cursor
+        o_nm = st.reserve((size_t)n_kf * 4); o_po = st.reserve((size_t)n_kf * 4);
+        const size_t o_tab = st.reserve((size_t)n_kf * mf * 4);
+        o_pairs = pairs ? st.reserve((size_t)pairs_cap * 4 + 16) : 0;
+        o_dense = dense ? st.reserve((size_t)n_kf * dense_stride * 4) : 0;
+        const size_t total = st.off;
+        st.off = input_end;
+        if ((s = ensure_host(m, input_end)) != BORB_OK) return s;
+        if ((s = ensure_arena(m, total)) != BORB_OK) return s;
+        BORB_CUDA(cudaStreamSynchronize(m->stream));
+        pack_frame_block(frame, m->h_stage + o_fb);
+        if ((s = commit(st, total)) != BORB_OK) return s;
+        b = m->arena;
+        BORB_CUDA(cudaMemsetAsync(b + o_ctr, 0, 256, m->stream));
+        BORB_CUDA(cudaMemsetAsync(b + o_tab, 0xFF, (size_t)n_kf * mf * 4, m->stream));
+        if (dense) BORB_CUDA(cudaMemsetAsync(b + o_dense, 0xFF, (size_t)n_kf * dense_stride * 4, m->stream));
+        BowDbArgs A{};
+        A.table = db->d_stream; A.slots = slots ? (const int32_t*)(b + o_sl) : nullptr; A.n_kf = n_kf;
+        const int warps = db->n_sm * 2 * 16;
+        int parts = (4 * warps + n_kf - 1) / n_kf;
+        A.parts = parts < 1 ? 1 : (parts > 32 ? 32 : parts);
+        A.frame_block = b + o_fb; A.frame_bytes = (int)fbytes;
+        A.frame_in_smem = bowdb_smem_bytes((int)fbytes, true) <= 200 * 1024 ? 1 : 0;
+        A.nnratio = nnratio; A.check_ori = check_ori;
+        A.table_out = (uint32_t*)(b + o_tab); A.work_counter = (int*)(b + o_ctr);
+        BowDbFinal F{};
+        F.table_out = A.table_out; F.n_kf = n_kf; F.mf = mf; F.check_ori = check_ori;
+        F.forig = (const uint16_t*)(b + o_fb + reinterpret_cast<const FrameBlockHdrHost*>(m->h_stage + o_fb)->off_orig);
+        F.n_matches = (int32_t*)(b + o_nm); F.pair_off = (int32_t*)(b + o_po);
+        F.pairs = pairs ? (uint32_t*)(b + o_pairs) : nullptr; F.pairs_cap = pairs_cap; F.cursor = (int*)(b + o_ctr + 64);
+        F.dense = dense ? (int32_t*)(b + o_dense) : nullptr; F.dense_stride = dense_stride;
+        m->launches += launch_bowdb(A, F, g_bow_csa.load() != 0, db->n_sm, m->stream);
+        BORB_CUDA(cudaGetLastError());
+    }
+    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, (size_t)n_kf * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (pair_offset) BORB_CUDA(cudaMemcpyAsync(pair_offset, b + o_po, (size_t)n_kf * 4, cudaMemcpyDeviceToHost, m->stream));
+    int32_t total_pairs = 0;
+    if (pairs) BORB_CUDA(cudaMemcpyAsync(&total_pairs, b + o_ctr + 64, 4, cudaMemcpyDeviceToHost, m->stream));
+    if (dense) BORB_CUDA(cudaMemcpyAsync(dense, b + o_dense, (size_t)n_kf * dense_stride * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    if (pairs) {
+        if (n_pairs_total) *n_pairs_total = total_pairs;
+        const int ncopy = total_pairs < pairs_cap ? total_pairs : pairs_cap;
+        if (ncopy > 0) {
+            BORB_CUDA(cudaMemcpyAsync(pairs, b + o_pairs, (size_t)ncopy * 4, cudaMemcpyDeviceToHost, m->stream));
+            BORB_CUDA(cudaStreamSynchronize(m->stream));
+        }
+        if (total_pairs > pairs_cap) { set_error("%d matched pairs, capacity %d", total_pairs, pairs_cap); return BORB_ERR_CAPACITY; }
+    }
+    return BORB_OK;
+}
+
+}  // namespace
+
 borb_status borb_search_by_bow_db(borb_matcher* m, borb_kfdb* db, const int32_t* slots, int n_kf, const borb_keyframe_view* frame,
                                   float nnratio, int check_orientation, int32_t* match, int32_t* n_matches) {
-    if (!m || !db || !frame || !match || !n_matches || n_kf < 0 || (n_kf > 0 && !slots)) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
-    if (m->device != db->device) { set_error("matcher and keyframe database live on different devices"); return BORB_ERR_INVALID_ARG; }
-    borb_status s = check_kf(frame, "borb_search_by_bow_db(frame)");
-    if (s != BORB_OK) return s;
-    if (n_kf == 0) return BORB_OK;
-    std::vector<KfDev> qd(n_kf);
-    for (int i = 0; i < n_kf; i++) {
-        if (slots[i] < 0 || slots[i] >= (int)db->entries.size() || !db->entries[slots[i]].alive) { set_error("slot %d is not a live keyframe", slots[i]); return BORB_ERR_INVALID_ARG; }
-        qd[i] = db->entries[slots[i]].dev;
-    }
-    BORB_CUDA(cudaSetDevice(m->device));
-    // only the frame and the table of keyframe descriptors-of-descriptors travel; the keyframes are resident
-    Stager st(m);
-    const KfOffsets to = stage_kf(st, frame);
-    const size_t o_qd = st.reserve((size_t)n_kf * sizeof(KfDev)), o_td = st.reserve(sizeof(KfDev));
-    const size_t input_end = st.off;
-    const int out_stride = frame->n;
-    const size_t o_match = st.reserve((size_t)n_kf * (out_stride > 0 ? out_stride : 1) * 4);
-    const size_t o_bins = st.reserve((size_t)n_kf * (out_stride > 0 ? out_stride : 1));
-    const size_t o_nm = st.reserve((size_t)n_kf * 4);
-    const size_t total = st.off;
-    st.off = input_end;
-    if ((s = ensure_arena(m, total)) != BORB_OK) return s;
-    const KfDev td = kf_dev(m, frame, to);
-    st.items.push_back({qd.data(), {o_qd, (size_t)n_kf * sizeof(KfDev)}});
-    st.items.push_back({&td, {o_td, sizeof(KfDev)}});
-    if ((s = commit(st, total)) != BORB_OK) return s;
-    uint8_t* b = m->arena;
-    m->launches += launch_bow_match((const KfDev*)(b + o_qd), (const KfDev*)(b + o_td), n_kf, 0, nnratio, check_orientation,
-                                    (int32_t*)(b + o_match), out_stride, b + o_bins, (int32_t*)(b + o_nm), frame->n, m->stream);
-    BORB_CUDA(cudaGetLastError());
-    if (out_stride > 0) BORB_CUDA(cudaMemcpyAsync(match, b + o_match, (size_t)n_kf * out_stride * 4, cudaMemcpyDeviceToHost, m->stream));
-    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, (size_t)n_kf * 4, cudaMemcpyDeviceToHost, m->stream));
-    BORB_CUDA(cudaStreamSynchronize(m->stream));
-    return BORB_OK;
+    if (!m || !db || !frame || !match || !n_matches || n_kf < 0) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    return bowdb_search(m, db, slots, n_kf, frame, nnratio, check_orientation, match, n_matches, nullptr, nullptr, 0, nullptr);
+}
+
+borb_status borb_search_by_bow_db_pairs(borb_matcher* m, borb_kfdb* db, const int32_t* slots, int n_kf, const borb_keyframe_view* frame,
+                                        float nnratio, int check_orientation, int32_t* n_matches, int32_t* pair_offset, uint32_t* pairs,
+                                        int pairs_cap, int32_t* n_pairs_total) {
+    if (!m || !db || !frame || !n_matches || n_kf < 0 || pairs_cap < 0 || (pairs && !pair_offset)) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    return bowdb_search(m, db, slots, n_kf, frame, nnratio, check_orientation, nullptr, n_matches, pair_offset, pairs, pairs_cap, n_pairs_total);
 }
 
 borb_status borb_search_for_triangulation(borb_matcher* m, const borb_keyframe_view* kf1, const borb_keyframe_view* kf2, const float* F12,

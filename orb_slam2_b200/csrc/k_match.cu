@@ -675,47 +675,59 @@ __global__ void __launch_bounds__(128) distinctive_kernel(const uint8_t* __restr
 // DBoW2::L1Scoring::score (ScoringObject.cpp:23-71).  A warp per keyframe: lanes take 32 consecutive keyframe words,
 // binary-search them in the query, and the matching terms are added in ascending word order (double, the order of the
 // reference's merge loop) so that the score is bit-identical.
-__global__ void __launch_bounds__(256) kfdb_score_kernel(const BowDev* __restrict__ table, int n_slots, const uint32_t* __restrict__ qword,
-                                                         const double* __restrict__ qvalue, int nq, int32_t* __restrict__ common,
+__global__ void __launch_bounds__(256) kfdb_score_kernel(const BowDev* __restrict__ table, int n_slots, const uint32_t* __restrict__ qword_g,
+                                                         const double* __restrict__ qvalue_g, int nq, int in_smem, int32_t* __restrict__ common,
                                                          float* __restrict__ score, uint32_t* __restrict__ first_word) {
+    extern __shared__ __align__(16) uint8_t kq_sm[];
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (slot >= n_slots) return;
-    const BowDev kf = table[slot];
-    double acc = 0.0;
-    int ncommon = 0;
-    uint32_t first = 0xFFFFFFFFu;
-    for (int base = 0; base < kf.n; base += 32) {
-        const int i = base + lane;
-        bool found = false;
-        double term = 0.0;
-        uint32_t w = 0;
-        if (i < kf.n) {
-            w = kf.word[i];
-            int lo = 0, hi = nq;                                  // lower_bound of w in the query words
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (qword[mid] < w) lo = mid + 1; else hi = mid;
-            }
-            if (lo < nq && qword[lo] == w) {
-                found = true;
-                const double vi = qvalue[lo], wi = kf.value[i];   // v1 = query (F->mBowVec), v2 = keyframe
-                term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
-            }
-        }
-        unsigned bal = __ballot_sync(0xFFFFFFFFu, found);
-        if (bal && first == 0xFFFFFFFFu) first = __shfl_sync(0xFFFFFFFFu, w, __ffs(bal) - 1);
-        ncommon += __popc(bal);
-        while (bal) {                                             // ordered accumulation: ascending word id
-            const int src = __ffs(bal) - 1;
-            bal &= bal - 1;
-            acc = __dadd_rn(acc, __shfl_sync(0xFFFFFFFFu, term, src));
-        }
+    // the query BowVector is probed ~10 x per keyframe word: keep it in shared memory (values first: 8-byte aligned)
+    const uint32_t* qword = qword_g;
+    const double* qvalue = qvalue_g;
+    if (in_smem) {
+        double* sv = reinterpret_cast<double*>(kq_sm);
+        uint32_t* sw = reinterpret_cast<uint32_t*>(sv + nq);
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) { sv[i] = qvalue_g[i]; sw[i] = qword_g[i]; }
+        __syncthreads();
+        qword = sw; qvalue = sv;
     }
-    if (lane == 0) {
-        common[slot] = ncommon;
-        score[slot] = (float)(-acc / 2.0);                        // float si = mpVoc->score(...) (:240)
-        first_word[slot] = first;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); slot < n_slots; slot += warps_total) {
+        const BowDev kf = table[slot];
+        double acc = 0.0;
+        int ncommon = 0;
+        uint32_t first = 0xFFFFFFFFu;
+        for (int base = 0; base < kf.n; base += 32) {
+            const int i = base + lane;
+            bool found = false;
+            double term = 0.0;
+            uint32_t w = 0;
+            if (i < kf.n) {
+                w = kf.word[i];
+                int lo = 0, hi = nq;                                  // lower_bound of w in the query words
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (qword[mid] < w) lo = mid + 1; else hi = mid;
+                }
+                if (lo < nq && qword[lo] == w) {
+                    found = true;
+                    const double vi = qvalue[lo], wi = kf.value[i];   // v1 = query (F->mBowVec), v2 = keyframe
+                    term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
+                }
+            }
+            unsigned bal = __ballot_sync(0xFFFFFFFFu, found);
+            if (bal && first == 0xFFFFFFFFu) first = __shfl_sync(0xFFFFFFFFu, w, __ffs(bal) - 1);
+            ncommon += __popc(bal);
+            while (bal) {                                             // ordered accumulation: ascending word id
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                acc = __dadd_rn(acc, __shfl_sync(0xFFFFFFFFu, term, src));
+            }
+        }
+        if (lane == 0) {
+            common[slot] = ncommon;
+            score[slot] = (float)(-acc / 2.0);                        // float si = mpVoc->score(...) (:240)
+            first_word[slot] = first;
+        }
     }
 }
 
@@ -1034,7 +1046,14 @@ int launch_initialization(const ProjArgs& A, const borb_keypoint* keys1, int n1,
 }
 int launch_kfdb_score(const BowDev* table, int n_slots, const uint32_t* qword, const double* qvalue, int nq, int32_t* common, float* score,
                       uint32_t* first_word, cudaStream_t s) {
-    if (n_slots > 0) kfdb_score_kernel<<<(n_slots + 7) / 8, 256, 0, s>>>(table, n_slots, qword, qvalue, nq, common, score, first_word);
+    if (n_slots > 0) {
+        const size_t smem = (size_t)nq * 12 + 16;
+        const int in_smem = smem <= 160 * 1024;
+        if (in_smem) allow_max_smem((const void*)kfdb_score_kernel);
+        int ctas = (n_slots + 7) / 8;
+        if (ctas > 148 * 4) ctas = 148 * 4;                           // persistent: the query is staged once per CTA
+        kfdb_score_kernel<<<ctas, 256, in_smem ? smem : 0, s>>>(table, n_slots, qword, qvalue, nq, in_smem, common, score, first_word);
+    }
     return 1;
 }
 int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best_idx, cudaStream_t s) {

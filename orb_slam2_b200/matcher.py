@@ -571,6 +571,26 @@ class KeyFrameDatabase:
         return nm[:len(sl)], match[:, :nF]
 
 
+    def SearchByBoWPairs(self, slots, F: KeyFrameView, pairs_cap: Optional[int] = None, want_pairs: bool = True):
+        """SearchByBoW of frame F against database keyframes `slots` (None = every slot) with compact results:
+        returns (nmatches[n_kf], pair_offset[n_kf], pairs) where pairs[off[k]:off[k]+nm[k]] = (frame feature | keyframe feature << 16)."""
+        m = self._m
+        fc = F._c()
+        if slots is None:
+            n_kf, sl = self.size()[0], None
+        else:
+            sl = np.ascontiguousarray(slots, np.int32); n_kf = len(sl)
+        nF = len(F.mvKeysUn)
+        cap = int(pairs_cap) if pairs_cap is not None else max(n_kf * nF, 1)
+        nm = np.zeros(max(n_kf, 1), np.int32); off = np.zeros(max(n_kf, 1), np.int32)
+        pairs = np.zeros(cap if want_pairs else 1, np.uint32)
+        tot = C.c_int32(0)
+        check(self._lib.borb_search_by_bow_db_pairs(m._h, self._h, _p(sl), n_kf, C.byref(fc), m.mfNNratio, int(m.mbCheckOrientation), _p(nm),
+                                                    _p(off), _p(pairs) if want_pairs else None, cap if want_pairs else 0, C.byref(tot)),
+              "borb_search_by_bow_db_pairs")
+        return nm[:n_kf], off[:n_kf], pairs[:tot.value] if want_pairs else None
+
+
 class ORBVocabulary:
     """ORBVocabulary = DBoW2::TemplatedVocabulary<FORB> (include/ORBVocabulary.h), device resident."""
 

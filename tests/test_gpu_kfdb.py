@@ -124,3 +124,105 @@ def test_search_by_bow_against_resident_keyframes(world, oracle):
     nm2, match2 = db.SearchByBoW([7], F)
     n_o, m_o = oracle.port_search_by_bow(kf7, F, 0.75, True)
     assert nm2[0] == n_o and np.array_equal(match2[0], m_o)
+
+
+def _pairs_to_dense(nm, off, pairs, n_f):
+    out = np.full((len(nm), n_f), -1, np.int32)
+    for k in range(len(nm)):
+        pr = pairs[off[k]:off[k] + nm[k]]
+        j, r = (pr & 0xFFFF).astype(np.int64), (pr >> 16).astype(np.int32)
+        assert len(np.unique(j)) == len(j)
+        out[k, j] = r
+    return out
+
+
+@pytest.mark.parametrize("levelsup", [1, 2, 3, 4])
+@pytest.mark.parametrize("csa", [1, 0])
+def test_search_by_bow_pairs_all_bucket_shapes(oracle, levelsup, csa):
+    """The compact database search against the restated SearchByBoW for every bucket geometry of the kernel: levelsup 1 = ~1000
+    single-feature nodes, 2 = ~100 nodes of ~8, 3 = 10 nodes of ~80 (multi-tile matrix), 4 = one node with every feature
+    (direct evaluation); with and without the orientation cull; CSA and plain POPC distance arithmetic."""
+    from orb_slam2_b200 import _lib, matcher as M
+    from orb_slam2_b200.extractor import ORBextractor
+    _lib.check(_lib.load().borb_debug_set_bow_csa(csa), "set_bow_csa")
+    try:
+        pv = oracle.PortVocabulary.random(10, 4, 5)
+        e = pv.export()
+        voc = M.ORBVocabulary.from_arrays(e["parent"], e["is_leaf"], e["desc"], e["weight"], e["k"], e["L"])
+        X = ORBextractor(800)
+        rng = np.random.default_rng(17 + levelsup)
+        base = [synth.mono_frame(300 + i // 3, 0, 0, 640, 480) for i in range(9)]
+        imgs = [np.clip(b.astype(np.int32) + rng.integers(-6, 7, b.shape), 0, 255).astype(np.uint8) for b in base]
+        outs = X.extract_batch(imgs)
+        kfs, bows = [], []
+        for k, d in outs:
+            bow, fv = voc.transform(d, levelsup)
+            kfs.append(M.KeyFrameView(mvKeysUn=k, mDescriptors=d, mFeatVec=fv, has_mp=(rng.random(len(k)) < 0.6).astype(np.uint8)))
+            bows.append(bow)
+        qk, qd = X(np.clip(base[4].astype(np.int32) + rng.integers(-8, 9, base[4].shape), 0, 255).astype(np.uint8))
+        qbow, qfv = voc.transform(qd, levelsup)
+        F = M.KeyFrameView(mvKeysUn=qk, mDescriptors=qd, mFeatVec=qfv)
+        for ori in (True, False):
+            mt = M.ORBmatcher(0.75, ori)
+            db = M.KeyFrameDatabase(mt)
+            for kf, bow in zip(kfs, bows):
+                db.add(kf, bow)
+            nm, off, pairs = db.SearchByBoWPairs(None, F)
+            dense = _pairs_to_dense(nm, off, pairs, len(qk))
+            nm_d, dense_d = db.SearchByBoW(np.arange(len(kfs), dtype=np.int32), F)
+            assert np.array_equal(nm, nm_d) and np.array_equal(dense, dense_d)
+            for s in range(len(kfs)):
+                n_o, m_o = oracle.port_search_by_bow(kfs[s], F, 0.75, ori)
+                assert nm[s] == n_o and np.array_equal(dense[s], m_o), (levelsup, ori, s)
+            assert nm.max() > 10
+            # counts only, a slot subset with a repeat, and an erased slot
+            nm2, _, none = db.SearchByBoWPairs([3, 4, 4, 0], F, want_pairs=False)
+            assert none is None and np.array_equal(nm2, nm[[3, 4, 4, 0]])
+            db.erase(2)
+            nm3, off3, pairs3 = db.SearchByBoWPairs(None, F)
+            assert nm3[2] == 0 and np.array_equal(np.delete(nm3, 2), np.delete(nm, 2))
+            assert np.array_equal(_pairs_to_dense(nm3, off3, pairs3, len(qk))[[0, 1, 3, 8]], dense[[0, 1, 3, 8]])
+    finally:
+        _lib.check(_lib.load().borb_debug_set_bow_csa(1), "set_bow_csa")
+
+
+def test_config4_real_size_2000_keyframes(oracle):
+    """BASELINE configs[4] at its own size: EuRoC-shaped 752x480 @1200 features, k=10 L=6 vocabulary, 2000 resident keyframes.
+    KeyFrameDatabase query (common words, L1 scores) and SearchByBoW against ALL keyframes equal the restated reference."""
+    from orb_slam2_b200 import matcher as M, sharding
+    from orb_slam2_b200.extractor import ORBextractor
+    n_kf, n_src = 2000, 40
+    arrs = sharding.random_vocabulary_arrays(10, 6, 7)
+    voc = M.ORBVocabulary.from_arrays(*arrs, 10, 6)
+    X = ORBextractor(1200)
+    rng = np.random.default_rng(1)
+    outs = X.extract_batch([synth.mono_frame(50 + i, 0, 0, 752, 480) for i in range(n_src)])
+    mt = M.ORBmatcher(0.75, True)
+    db = M.KeyFrameDatabase(mt)
+    kfs, bows = [], []
+    for j in range(n_kf):
+        k, d = outs[j % n_src]
+        if j >= n_src:
+            flip = (rng.random((len(d), 32, 8)) < 0.04)
+            d = d ^ np.packbits(flip, axis=2, bitorder="little").reshape(len(d), 32)
+        bow, fv = voc.transform(d, 4)
+        kf = M.KeyFrameView(mvKeysUn=k, mDescriptors=d, mFeatVec=fv, has_mp=(rng.random(len(k)) < 0.8).astype(np.uint8))
+        db.add(kf, bow)
+        kfs.append(kf); bows.append(bow)
+    qk, qd = outs[3]
+    flip = (rng.random((len(qd), 32, 8)) < 0.02)
+    qd = qd ^ np.packbits(flip, axis=2, bitorder="little").reshape(len(qd), 32)
+    qbow, qfv = voc.transform(qd, 4)
+    F = M.KeyFrameView(mvKeysUn=qk, mDescriptors=qd, mFeatVec=qfv)
+    assert len(qk) >= 1200 and all(len(k.mvKeysUn) >= 1200 for k in kfs[:n_src])
+    cw, sc, fw = db.query(qbow)
+    for s in rng.choice(n_kf, 64, replace=False).tolist() + [3, 43]:
+        so, co, fo = oracle.port_bow_score(qbow, bows[s])
+        assert cw[s] == co and fw[s] == fo and sc[s] == np.float32(so), s
+    nm, off, pairs = db.SearchByBoWPairs(None, F)
+    assert int(nm.sum()) == len(pairs)
+    dense = _pairs_to_dense(nm, off, pairs, len(qk))
+    for s in range(n_kf):
+        n_o, m_o = oracle.port_search_by_bow(kfs[s], F, 0.75, True)
+        assert nm[s] == n_o and np.array_equal(dense[s], m_o), s
+    assert nm[3] > 300 and nm.max() == nm[3::n_src].max()

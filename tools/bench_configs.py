@@ -96,15 +96,18 @@ def config4(n_kf, reps):
     cw, sc, fw = db.query(qbow)
     t_query = med(lambda: db.query(qbow), reps)
     slots = np.arange(n_kf, dtype=np.int32)
-    nm, match = db.SearchByBoW(slots, F)
-    t_bow = med(lambda: db.SearchByBoW(slots, F), max(3, reps // 4))
+    nm, off, pairs = db.SearchByBoWPairs(None, F)
+    cap = int(nm.sum()) + 1024
+    t_bow = med(lambda: db.SearchByBoWPairs(None, F, pairs_cap=cap), reps)
+    t_bow_counts = med(lambda: db.SearchByBoWPairs(None, F, want_pairs=False), reps)
     top = np.argsort(-sc)[:20].astype(np.int32)
     t_bow20 = med(lambda: db.SearchByBoW(top, F), reps)
     db_bytes = db.size()[1]
     return {"config": f"configs[4]: EuRoC-shaped 752x480 @1200, {n_kf}-keyframe resident database (vocabulary k=10 L=6, random tree)",
             "keyframes": n_kf, "features_per_keyframe": n_feat / n_kf, "db_device_MB": db_bytes / 1e6, "add_ms_per_keyframe": t_add / n_kf * 1e3,
             "kfdb_query_us": t_query * 1e6, "best_common_words": int(cw.max()), "best_score": float(sc.max()),
-            "search_by_bow_all_ms": t_bow * 1e3, "search_by_bow_all_matches_max": int(nm.max()),
+            "search_by_bow_all_ms": t_bow * 1e3, "search_by_bow_all_counts_only_ms": t_bow_counts * 1e3, "search_by_bow_all_pairs": int(nm.sum()),
+            "search_by_bow_all_matches_max": int(nm.max()),
             "search_by_bow_all_descriptor_GBps": n_feat * 32 / t_bow / 1e9,
             "search_by_bow_top20_us": t_bow20 * 1e6}
 
