@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BORB_VERSION 1
+#define BORB_VERSION 2
 #define BORB_MAX_LEVELS 16
 #define BORB_MAX_DIM 4095 /* image width/height limit (candidates pack x,y in 12 bits) */
 
@@ -183,6 +183,7 @@ BORB_API borb_status borb_matcher_destroy(borb_matcher* m);
 
 /* Frame snapshot for SearchByProjection (include/Frame.h): undistorted keypoints, descriptors, stereo
  * coordinate, image bounds of the 64x48 feature grid (mnMinX.. / src/Frame.cc:97-102), scale factors. */
+typedef struct borb_frame borb_frame;   /* device-resident Frame, see borb_frame_create below */
 typedef struct borb_frame_view {
     int32_t n;                     /* N */
     const borb_keypoint* keys_un;  /* mvKeysUn */
@@ -192,6 +193,9 @@ typedef struct borb_frame_view {
     float min_x, min_y, max_x, max_y;
     int32_t n_levels;
     const float* scale_factors;    /* mvScaleFactors */
+    const borb_frame* resident;    /* NULL, or a device-resident copy of this frame: then n, keys_un, desc, u_right, the bounds and
+                                      scale_factors above are ignored (taken from the resident frame, whose feature grid is already
+                                      built) and only `occupied` is read from the host */
 } borb_frame_view;
 
 /* Local map points that passed Frame::isInFrustum (src/Frame.cc:269-325), in vpMapPoints order. */

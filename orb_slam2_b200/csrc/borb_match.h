@@ -2,10 +2,32 @@
 #pragma once
 #include "borb_internal.h"
 
+// Device-resident Frame (include/borb.h: borb_frame_create / borb_frame_from_extractor): what the windowed searches read of a
+// Frame — mvKeysUn, mDescriptors, mvuRight, mvScaleFactors and the 64x48 feature grid (Frame::AssignFeaturesToGrid) — kept in
+// HBM across the matcher calls of one Track().
+struct borb_frame {
+    int device = 0;
+    int n = 0, n_levels = 0;
+    float min_x = 0, min_y = 0, max_x = 0, max_y = 0;
+    uint8_t* block = nullptr;       // one allocation: keys | desc | u_right | depth | scale factors | cell_start | cell_idx
+    size_t block_bytes = 0;
+    int cap = 0;                    // features the block can hold
+    borb_keypoint* keys = nullptr;
+    uint8_t* desc = nullptr;
+    float* u_right = nullptr;       // null: monocular
+    float* depth = nullptr;
+    float* sf = nullptr;
+    int* cell_start = nullptr;
+    int* cell_idx = nullptr;
+    cudaEvent_t ready = nullptr;    // recorded after the last kernel that writes the block
+};
+
 namespace borb {
 
 constexpr int GRID_COLS = 64, GRID_ROWS = 48;     // FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.h:37-38)
 constexpr int GRID_CELLS = GRID_COLS * GRID_ROWS;
+constexpr int CAND_UNSORTED = 0x40000000;           // flag in cand_cnt: list longer than the sort capacity, kept in position order
+constexpr int CAND_COUNT_MASK = 0x3FFFFFFF;
 constexpr int MATCH_MAX_FEATURES = 8192;          // per frame / keyframe (grid sort and claim bitsets live in smem)
 
 struct ProjArgs {                 // device pointers
@@ -139,6 +161,8 @@ struct VocDev {                   // views into the packed blob
 
 int launch_grid_sort(const borb_keypoint* keys, int n, float minX, float minY, float invW, float invH, int* cell_start, int* cell_idx,
                      cudaStream_t s);
+void launch_candidates(const ProjArgs& A, cudaStream_t s);
+void launch_resolve(const ProjArgs& A, bool last, int32_t* out, int32_t* ev_idx, uint8_t* ev_bin, int* n_matches, cudaStream_t s);
 int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s);
 int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_cur, int32_t* hist_idx, uint8_t* hist_bin, int* n_matches,
                            cudaStream_t s);

@@ -83,6 +83,74 @@ borb_status commit(Stager& st, size_t total_with_scratch) {
     return BORB_OK;
 }
 
+// ---- frame side of the windowed searches: staged from the host view per call, or taken from a device-resident borb_frame
+struct FrameInfo { int n, n_levels; float min_x, min_y, max_x, max_y; bool has_ur; const borb_frame* rf; };
+struct FrameStage { size_t keys = 0, desc = 0, ur = 0, occ = 0, sf = 0, cs = 0, ci = 0; bool ur_p = false, occ_p = false; };
+
+FrameInfo frame_info(const borb_frame_view* F) {
+    FrameInfo I{};
+    I.rf = F->resident;
+    if (I.rf) {
+        I.n = I.rf->n; I.n_levels = I.rf->n_levels; I.min_x = I.rf->min_x; I.min_y = I.rf->min_y; I.max_x = I.rf->max_x; I.max_y = I.rf->max_y;
+        I.has_ur = I.rf->u_right != nullptr;
+    } else {
+        I.n = F->n; I.n_levels = F->n_levels; I.min_x = F->min_x; I.min_y = F->min_y; I.max_x = F->max_x; I.max_y = F->max_y;
+        I.has_ur = F->u_right != nullptr;
+    }
+    return I;
+}
+// the per-call inputs of the frame (everything for a host view; only `occupied` for a resident frame)
+FrameStage stage_frame(Stager& st, const borb_frame_view* F, const FrameInfo& I, bool want_ur) {
+    FrameStage fs;
+    if (!I.rf) {
+        fs.keys = st.add(F->keys_un, (size_t)I.n * sizeof(borb_keypoint));
+        fs.desc = st.add(F->desc, (size_t)I.n * 32);
+        fs.ur_p = want_ur && F->u_right != nullptr;
+        if (fs.ur_p) fs.ur = st.add(F->u_right, (size_t)I.n * 4);
+        fs.sf = st.add(F->scale_factors, (size_t)(F->scale_factors ? I.n_levels : 0) * 4);
+    } else fs.ur_p = want_ur && I.has_ur;
+    fs.occ_p = F->occupied != nullptr;
+    if (fs.occ_p) fs.occ = st.add(F->occupied, (size_t)I.n);
+    return fs;
+}
+void reserve_grid(Stager& st, const FrameInfo& I, FrameStage& fs) {
+    if (I.rf) return;
+    fs.cs = st.reserve((size_t)(GRID_CELLS + 1) * 4);
+    fs.ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
+}
+// fills the frame fields of A after commit(); builds the grid for a host view, waits for the resident frame otherwise
+borb_status bind_frame(borb_matcher* m, const FrameInfo& I, const FrameStage& fs, ProjArgs& A) {
+    uint8_t* b = m->arena;
+    A.n = I.n;
+    A.minX = I.min_x; A.minY = I.min_y;
+    A.invW = (float)GRID_COLS / (float)(I.max_x - I.min_x);      // mfGridElementWidthInv (Frame.cc:101)
+    A.invH = (float)GRID_ROWS / (float)(I.max_y - I.min_y);
+    A.occupied = fs.occ_p ? b + fs.occ : nullptr;
+    if (I.rf) {
+        A.keys = I.rf->keys; A.desc = I.rf->desc; A.u_right = fs.ur_p ? I.rf->u_right : nullptr; A.scale_factors = I.rf->sf;
+        A.cell_start = I.rf->cell_start; A.cell_idx = I.rf->cell_idx;
+        BORB_CUDA(cudaStreamWaitEvent(m->stream, I.rf->ready, 0));
+    } else {
+        A.keys = (const borb_keypoint*)(b + fs.keys); A.desc = b + fs.desc;
+        A.u_right = fs.ur_p ? (const float*)(b + fs.ur) : nullptr;
+        A.scale_factors = (const float*)(b + fs.sf);
+        A.cell_start = (const int*)(b + fs.cs); A.cell_idx = (const int*)(b + fs.ci);
+        if (I.n > 0) m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + fs.cs), (int*)(b + fs.ci), m->stream);
+        else BORB_CUDA(cudaMemsetAsync(b + fs.cs, 0, (size_t)(GRID_CELLS + 1) * 4, m->stream));
+    }
+    return BORB_OK;
+}
+borb_status check_frame(const borb_frame_view* F, const FrameInfo& I, const borb_matcher* m) {
+    if (I.n < 0 || I.n > MATCH_MAX_FEATURES) { set_error("frame has %d features (limit %d)", I.n, MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    if (I.rf) {
+        if (I.rf->device != m->device) { set_error("resident frame and matcher live on different devices"); return BORB_ERR_INVALID_ARG; }
+        return BORB_OK;
+    }
+    if (I.n > 0 && (!F->keys_un || !F->desc)) { set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG; }
+    if (I.n_levels < 1 || !F->scale_factors || !(I.max_x > I.min_x) || !(I.max_y > I.min_y)) { set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG; }
+    return BORB_OK;
+}
+
 struct KfOffsets { size_t keys, desc, has_mp, u_right, node, start, idx, sf, sig; bool has_mp_p, ur_p; };
 
 borb_status check_kf(const borb_keyframe_view* v, const char* what) {
@@ -180,51 +248,40 @@ borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F,
                                       int32_t* match_feat, int32_t* n_matches) {
     if (!m || !F || !P || !match_feat || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
     *n_matches = 0;
-    if (F->n < 0 || F->n > MATCH_MAX_FEATURES || P->n < 0) { set_error("frame has %d features (limit %d)", F->n, MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    const FrameInfo I = frame_info(F);
+    borb_status s = check_frame(F, I, m);
+    if (s != BORB_OK) return s;
+    if (P->n < 0 || P->n > MATCH_MAX_FEATURES) { set_error("%d map points (limit %d per call)", P->n, MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
     if (P->n == 0) return BORB_OK;
-    if (F->n == 0) { for (int i = 0; i < P->n; i++) match_feat[i] = -1; return BORB_OK; }
-    if (!F->keys_un || !F->desc || !F->scale_factors || !P->proj_x || !P->proj_y || !P->proj_xr || !P->level || !P->view_cos || !P->desc ||
-        !(F->max_x > F->min_x) || !(F->max_y > F->min_y)) { set_error("incomplete frame / map point view"); return BORB_ERR_INVALID_ARG; }
+    if (I.n == 0) { for (int i = 0; i < P->n; i++) match_feat[i] = -1; return BORB_OK; }
+    if (!P->proj_x || !P->proj_y || !P->proj_xr || !P->level || !P->view_cos || !P->desc) { set_error("incomplete map point view"); return BORB_ERR_INVALID_ARG; }
     for (int i = 0; i < P->n; i++)
-        if ((!P->valid || P->valid[i]) && (P->level[i] < 0 || P->level[i] >= F->n_levels)) { set_error("map point %d: predicted level out of range", i); return BORB_ERR_INVALID_ARG; }
+        if ((!P->valid || P->valid[i]) && (P->level[i] < 0 || P->level[i] >= I.n_levels)) { set_error("map point %d: predicted level out of range", i); return BORB_ERR_INVALID_ARG; }
     BORB_CUDA(cudaSetDevice(m->device));
     Stager st(m);
-    const size_t o_keys = st.add(F->keys_un, (size_t)F->n * sizeof(borb_keypoint));
-    const size_t o_desc = st.add(F->desc, (size_t)F->n * 32);
-    const size_t o_ur = F->u_right ? st.add(F->u_right, (size_t)F->n * 4) : 0;
-    const size_t o_occ = F->occupied ? st.add(F->occupied, (size_t)F->n) : 0;
-    const size_t o_sf = st.add(F->scale_factors, (size_t)F->n_levels * 4);
+    FrameStage fs = stage_frame(st, F, I, true);
     const size_t o_px = st.add(P->proj_x, (size_t)P->n * 4), o_py = st.add(P->proj_y, (size_t)P->n * 4), o_pxr = st.add(P->proj_xr, (size_t)P->n * 4);
     const size_t o_lvl = st.add(P->level, (size_t)P->n * 4), o_vc = st.add(P->view_cos, (size_t)P->n * 4);
     const size_t o_md = st.add(P->desc, (size_t)P->n * 32);
     const size_t o_val = P->valid ? st.add(P->valid, (size_t)P->n) : 0;
     const size_t o_obs = P->has_obs ? st.add(P->has_obs, (size_t)P->n) : 0;
+    const size_t input_end = st.off;
     // device-only scratch
-    const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
-    const size_t o_cand = st.reserve((size_t)P->n * F->n * 4), o_cc = st.reserve((size_t)P->n * 4);
+    reserve_grid(st, I, fs);
+    const size_t o_cand = st.reserve((size_t)P->n * I.n * 4), o_cc = st.reserve((size_t)P->n * 4);
     const size_t o_match = st.reserve((size_t)P->n * 4), o_nm = st.reserve(16);
-    const size_t input_end = o_cs;
     const size_t total = st.off;
     st.off = input_end;
-    borb_status s = commit(st, total);
-    if (s != BORB_OK) return s;
+    if ((s = commit(st, total)) != BORB_OK) return s;
     uint8_t* b = m->arena;
     ProjArgs A{};
-    A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
-    A.u_right = F->u_right ? (const float*)(b + o_ur) : nullptr;
-    A.occupied = F->occupied ? b + o_occ : nullptr;
-    A.minX = F->min_x; A.minY = F->min_y;
-    A.invW = (float)GRID_COLS / (float)(F->max_x - F->min_x);      // mfGridElementWidthInv (Frame.cc:101)
-    A.invH = (float)GRID_ROWS / (float)(F->max_y - F->min_y);
-    A.scale_factors = (const float*)(b + o_sf);
-    A.cell_start = (const int*)(b + o_cs); A.cell_idx = (const int*)(b + o_ci);
+    if ((s = bind_frame(m, I, fs, A)) != BORB_OK) return s;
     A.n_mp = P->n; A.proj_x = (const float*)(b + o_px); A.proj_y = (const float*)(b + o_py); A.proj_xr = (const float*)(b + o_pxr);
     A.view_cos = (const float*)(b + o_vc); A.level = (const int32_t*)(b + o_lvl); A.mp_desc = b + o_md;
     A.mp_valid = P->valid ? b + o_val : nullptr; A.mp_has_obs = P->has_obs ? b + o_obs : nullptr;
-    A.th = th; A.nnratio = nnratio;
+    A.th = th; A.nnratio = nnratio; A.th_dist = TH_HIGH;
     A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
-    A.q_radius = nullptr; A.q_minl = nullptr; A.q_maxl = nullptr; A.mode = 0; A.check_ori = 0; A.q_angle = nullptr; A.q_valid_out = nullptr;
-    m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
+    A.mode = 0;
     m->launches += launch_projection(A, (int32_t*)(b + o_match), (int*)(b + o_nm), m->stream);
     BORB_CUDA(cudaGetLastError());
     BORB_CUDA(cudaMemcpyAsync(match_feat, b + o_match, (size_t)P->n * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -262,21 +319,22 @@ struct PointQuery {
 
 static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* F, const PointQuery& Q, int32_t* state, int32_t* n_matches) {
     *n_matches = 0;
-    if (F->n < 0 || F->n > MATCH_MAX_FEATURES || Q.n < 0 || Q.n > MATCH_MAX_FEATURES) { set_error("feature count outside [0,%d]", MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
-    const int n_out = Q.argmin ? Q.n : F->n;
+    const FrameInfo I = frame_info(F);
+    borb_status s = check_frame(F, I, m);
+    if (s != BORB_OK) return s;
+    if (Q.n < 0 || Q.n > MATCH_MAX_FEATURES) { set_error("%d query points (limit %d per call)", Q.n, MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    const int n_out = Q.argmin ? Q.n : I.n;
     if (state) for (int i = 0; i < n_out; i++) state[i] = -1;
     if (Q.to_aux) {                 // caller sized m->aux; "no match" everywhere until the kernels say otherwise
         BORB_CUDA(cudaSetDevice(m->device));
         if (Q.n > 0) BORB_CUDA(cudaMemsetAsync(m->aux + Q.aux_off, 0xFF, (size_t)Q.n * 4, m->stream));
     }
-    if (F->n == 0 || Q.n == 0) return BORB_OK;
-    if (!F->keys_un || !F->desc || !F->scale_factors || F->n_levels < 1 || !Q.world_pos || !Q.desc || !(F->max_x > F->min_x) || !(F->max_y > F->min_y)) {
-        set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG;
-    }
+    if (I.n == 0 || Q.n == 0) return BORB_OK;
+    if (!Q.world_pos || !Q.desc) { set_error("incomplete query view"); return BORB_ERR_INVALID_ARG; }
     if (Q.variant == 0) {
         if (!Q.keys) { set_error("incomplete last-frame view"); return BORB_ERR_INVALID_ARG; }
         for (int i = 0; i < Q.n; i++)
-            if (Q.keys[i].octave < 0 || Q.keys[i].octave >= F->n_levels) { set_error("last-frame keypoint %d: octave out of range", i); return BORB_ERR_INVALID_ARG; }
+            if (Q.keys[i].octave < 0 || Q.keys[i].octave >= I.n_levels) { set_error("last-frame keypoint %d: octave out of range", i); return BORB_ERR_INVALID_ARG; }
     } else {
         if (!Q.max_distance || !Q.min_distance || (!Q.Ow && !Q.chain) || (Q.variant == 2 && Q.use_normal && !Q.normal) ||
             (Q.variant == 1 && Q.check_ori && !Q.angle) || (Q.chain && !Q.T2) || (Q.chi2 && !Q.inv_sigma2)) {
@@ -287,12 +345,7 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     BORB_CUDA(cudaSetDevice(m->device));
     Stager st(m);
     const int nq = Q.n;
-    const bool stereo = (Q.variant == 0 || Q.chi2) && F->u_right != nullptr;
-    const size_t o_keys = st.add(F->keys_un, (size_t)F->n * sizeof(borb_keypoint));
-    const size_t o_desc = st.add(F->desc, (size_t)F->n * 32);
-    const size_t o_ur = stereo ? st.add(F->u_right, (size_t)F->n * 4) : 0;
-    const size_t o_occ = F->occupied ? st.add(F->occupied, (size_t)F->n) : 0;
-    const size_t o_sf = st.add(F->scale_factors, (size_t)F->n_levels * 4);
+    FrameStage fs = stage_frame(st, F, I, Q.variant == 0 || Q.chi2);
     const size_t o_lk = Q.keys ? st.add(Q.keys, (size_t)nq * sizeof(borb_keypoint)) : 0;
     const size_t o_wp = st.add(Q.world_pos, (size_t)nq * 12);
     const size_t o_md = st.add(Q.desc, (size_t)nq * 32);
@@ -302,18 +355,19 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     const size_t o_mn = Q.min_distance ? st.add(Q.min_distance, (size_t)nq * 4) : 0;
     const size_t o_nr = Q.normal ? st.add(Q.normal, (size_t)nq * 12) : 0;
     const size_t o_qa = Q.angle ? st.add(Q.angle, (size_t)nq * 4) : 0;
-    const size_t o_is2 = Q.chi2 ? st.add(Q.inv_sigma2, (size_t)F->n_levels * 4) : 0;
+    const size_t o_is2 = Q.chi2 ? st.add(Q.inv_sigma2, (size_t)I.n_levels * 4) : 0;
     const size_t input_end = st.off;
-    const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
+    reserve_grid(st, I, fs);
     const size_t o_px = st.reserve((size_t)nq * 4), o_py = st.reserve((size_t)nq * 4), o_pxr = st.reserve((size_t)nq * 4), o_rad = st.reserve((size_t)nq * 4);
     const size_t o_ang = st.reserve((size_t)nq * 4), o_minl = st.reserve((size_t)nq * 4), o_maxl = st.reserve((size_t)nq * 4), o_val = st.reserve((size_t)nq);
-    const size_t o_cand = st.reserve((size_t)nq * F->n * 4), o_cc = st.reserve((size_t)nq * 4);
-    const size_t o_state = st.reserve((size_t)(F->n > nq ? F->n : nq) * 4), o_evi = st.reserve((size_t)nq * 4), o_evb = st.reserve((size_t)nq), o_nm = st.reserve(16);
+    const size_t o_cand = st.reserve((size_t)nq * I.n * 4), o_cc = st.reserve((size_t)nq * 4);
+    const size_t o_state = st.reserve((size_t)(I.n > nq ? I.n : nq) * 4), o_evi = st.reserve((size_t)nq * 4), o_evb = st.reserve((size_t)nq), o_nm = st.reserve(16);
     const size_t total = st.off;
     st.off = input_end;
-    borb_status s = commit(st, total);
-    if (s != BORB_OK) return s;
+    if ((s = commit(st, total)) != BORB_OK) return s;
     uint8_t* b = m->arena;
+    ProjArgs A{};
+    if ((s = bind_frame(m, I, fs, A)) != BORB_OK) return s;
     LastArgs L{};
     L.variant = Q.variant;
     L.n_last = nq; L.last_keys = Q.keys ? (const borb_keypoint*)(b + o_lk) : nullptr; L.world_pos = (const float*)(b + o_wp);
@@ -322,26 +376,17 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     L.min_distance = Q.min_distance ? (const float*)(b + o_mn) : nullptr;
     L.normal = Q.normal ? (const float*)(b + o_nr) : nullptr;
     for (int i = 0; i < 3; i++) L.Ow[i] = Q.Ow ? Q.Ow[i] : 0.f;
-    L.log_scale = Q.log_scale; L.n_levels = F->n_levels;
+    L.log_scale = Q.log_scale; L.n_levels = I.n_levels;
     L.invz_double = Q.invz_double; L.use_normal = Q.use_normal; L.chain = Q.chain;
     for (int i = 0; i < 12; i++) L.T2[i] = Q.chain ? Q.T2[i] : 0.f;
     L.valid_in = Q.valid ? b + o_vin : nullptr;
     for (int i = 0; i < 12; i++) L.T[i] = Q.Tcw[i];
     L.fx = Q.fx; L.fy = Q.fy; L.cx = Q.cx; L.cy = Q.cy; L.bf = Q.bf; L.th = Q.th;
-    L.minX = F->min_x; L.minY = F->min_y; L.maxX = F->max_x; L.maxY = F->max_y;
-    L.scale_factors = (const float*)(b + o_sf);
+    L.minX = I.min_x; L.minY = I.min_y; L.maxX = I.max_x; L.maxY = I.max_y;
+    L.scale_factors = A.scale_factors;
     L.forward = Q.forward; L.backward = Q.backward;
     L.proj_x = (float*)(b + o_px); L.proj_y = (float*)(b + o_py); L.proj_xr = (float*)(b + o_pxr); L.radius = (float*)(b + o_rad);
     L.angle = (float*)(b + o_ang); L.minl = (int32_t*)(b + o_minl); L.maxl = (int32_t*)(b + o_maxl); L.valid_out = b + o_val;
-    ProjArgs A{};
-    A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
-    A.u_right = stereo ? (const float*)(b + o_ur) : nullptr;
-    A.occupied = F->occupied ? b + o_occ : nullptr;
-    A.minX = F->min_x; A.minY = F->min_y;
-    A.invW = (float)GRID_COLS / (float)(F->max_x - F->min_x);
-    A.invH = (float)GRID_ROWS / (float)(F->max_y - F->min_y);
-    A.scale_factors = (const float*)(b + o_sf);
-    A.cell_start = (const int*)(b + o_cs); A.cell_idx = (const int*)(b + o_ci);
     A.n_mp = nq; A.proj_x = L.proj_x; A.proj_y = L.proj_y; A.proj_xr = L.proj_xr; A.view_cos = nullptr; A.level = nullptr;
     A.mp_desc = b + o_md; A.mp_valid = b + o_val; A.mp_has_obs = Q.has_obs ? b + o_obs : nullptr;
     A.th = Q.th; A.nnratio = 0.f;
@@ -350,7 +395,6 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     A.th_dist = Q.th_dist;
     A.chi2 = Q.chi2; A.inv_sigma2 = Q.chi2 ? (const float*)(b + o_is2) : nullptr;
     A.q_valid_out = b + o_val;
-    m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
     if (Q.argmin) m->launches += launch_projection_argmin(L, A, (int32_t*)(b + o_state), (int*)(b + o_nm), m->stream);
     else m->launches += launch_projection_last(L, A, (int32_t*)(b + o_state), (int32_t*)(b + o_evi), b + o_evb, (int*)(b + o_nm), m->stream);
     BORB_CUDA(cudaGetLastError());
@@ -425,13 +469,14 @@ borb_status borb_search_by_sim3(borb_matcher* m, const borb_frame_view* kf1, con
                                 int32_t* match12, int32_t* n_found) {
     if (!m || !kf1 || !kf2 || !pts1 || !pts2 || !T1w || !T2w || !S12 || !S21 || !match12 || !n_found) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
     *n_found = 0;
-    if (pts1->n != kf1->n || pts2->n != kf2->n) { set_error("SearchBySim3: one MapPoint slot per keyframe feature (GetMapPointMatches)"); return BORB_ERR_INVALID_ARG; }
-    for (int i = 0; i < kf1->n; i++) match12[i] = -1;
-    if (kf1->n == 0 || kf2->n == 0) return BORB_OK;
+    const int n1 = frame_info(kf1).n, n2 = frame_info(kf2).n;
+    if (pts1->n != n1 || pts2->n != n2) { set_error("SearchBySim3: one MapPoint slot per keyframe feature (GetMapPointMatches)"); return BORB_ERR_INVALID_ARG; }
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    if (n1 == 0 || n2 == 0) return BORB_OK;
     borb_frame_view F1 = *kf1, F2 = *kf2;
     F1.occupied = nullptr; F2.occupied = nullptr;
     BORB_CUDA(cudaSetDevice(m->device));
-    const size_t need = (size_t)kf1->n + (size_t)kf2->n;
+    const size_t need = (size_t)n1 + (size_t)n2;
     if (m->aux_count < need) {
         cudaFree(m->aux); m->aux = nullptr; m->aux_count = 0;
         BORB_CUDA(cudaMalloc(&m->aux, need * 4));
@@ -450,19 +495,19 @@ borb_status borb_search_by_sim3(borb_matcher* m, const borb_frame_view* kf1, con
     R.variant = 2; R.n = pts2->n; R.world_pos = pts2->world_pos; R.desc = pts2->desc; R.valid = pts2->valid;
     R.max_distance = pts2->max_distance; R.min_distance = pts2->min_distance;
     R.Tcw = T2w; R.chain = 1; R.T2 = S12; R.fx = fx; R.fy = fy; R.cx = cx; R.cy = cy; R.th = th; R.log_scale = log_scale_factor1;
-    R.th_dist = 100; R.argmin = 1; R.invz_double = 1; R.to_aux = 1; R.aux_off = (size_t)kf1->n;
+    R.th_dist = 100; R.argmin = 1; R.invz_double = 1; R.to_aux = 1; R.aux_off = (size_t)n1;
     s = run_point_projection(m, &F1, R, nullptr, &nm);
     if (s != BORB_OK) return s;
     // agreement test (:1302-1323) on the device
     Stager st(m);
-    const size_t o_out = st.reserve((size_t)kf1->n * 4), o_nf = st.reserve(16);
+    const size_t o_out = st.reserve((size_t)n1 * 4), o_nf = st.reserve(16);
     const size_t total = st.off;
     st.off = 0;
     if ((s = commit(st, total)) != BORB_OK) return s;
     uint8_t* b = m->arena;
-    m->launches += launch_sim3_agree(m->aux, m->aux + kf1->n, kf1->n, kf2->n, (int32_t*)(b + o_out), (int*)(b + o_nf), m->stream);
+    m->launches += launch_sim3_agree(m->aux, m->aux + n1, n1, n2, (int32_t*)(b + o_out), (int*)(b + o_nf), m->stream);
     BORB_CUDA(cudaGetLastError());
-    BORB_CUDA(cudaMemcpyAsync(match12, b + o_out, (size_t)kf1->n * 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(match12, b + o_out, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaMemcpyAsync(n_found, b + o_nf, 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaStreamSynchronize(m->stream));
     return BORB_OK;

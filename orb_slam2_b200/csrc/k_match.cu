@@ -1,17 +1,13 @@
 // Hamming-distance matchers of the ORB front-end (reference src/ORBmatcher.cc) and the BoW feeder.
 //
-//   grid_sort_kernel + proj_candidates_kernel + proj_resolve_kernel
-//       Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc:230-245, 327-392) and
-//       ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129).
-//       Candidate enumeration and the 256-bit distances are parallel (a warp per map point, candidates kept in
-//       the reference's (ix, iy, insertion) order); the order-dependent part — a feature claimed by an earlier
-//       map point is skipped by later ones (:87-89,:123) — is replayed exactly by one warp walking the map
-//       points in order over the precomputed lists.  best/second-best of the reference's scan ==
-//       lexicographic minimum / second minimum of (distance, list position).
-//   bow_match_kernel      SearchByBoW(KeyFrame*,Frame&) (:159-288) and SearchByBoW(KeyFrame*,KeyFrame*) (:522-655):
-//       one warp per (keyframe, frame) pair walks the keyframe's FeatureVector in order (the greedy "already
-//       claimed" skip is sequential, :209/:576) with the inner candidate loop spread over the 32 lanes
-//       (8 x __popc per candidate, warp-shuffle argmin); rotation-histogram cull (:267-285) at the end.
+//   grid_sort_kernel      Frame::AssignFeaturesToGrid (src/Frame.cc:230-245): (cell, insertion) order by a bitonic sort in shared
+//       memory.  The windowed search itself (GetFeaturesInArea + claim resolution) lives in k_proj.cu.
+//   project_points_kernel the pose projections / frustum tests that feed it (src/ORBmatcher.cc:290-403,1328-1599, src/Frame.cc:269-325).
+//   bow_match_kernel      SearchByBoW(KeyFrame*,Frame&) (:159-288) and SearchByBoW(KeyFrame*,KeyFrame*) (:522-655) for keyframes
+//       staged from the host: a CTA per (keyframe, frame) pair deals the FeatureVector nodes to 8 warps (a feature lives in
+//       exactly one node, so the greedy "already claimed" skip, :209/:576, never crosses nodes); per node the distance matrix is
+//       computed with all lanes busy, then the rows are replayed in order; rotation-histogram cull (:267-285) at the end.
+//       (The database-resident search of one frame against thousands of keyframes is k_bowdb.cu.)
 //   triangulation_kernel  SearchForTriangulation (:657-823): no sequential dependence (vbMatched2 is never set in
 //       the reference), "dist<=bestDist, later wins" == min over (distance, -position); epipolar tests as :140-157.
 //   bow_transform_kernel  TemplatedVocabulary::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259):
@@ -104,254 +100,7 @@ __global__ void __launch_bounds__(1024) grid_sort_kernel(const borb_keypoint* __
 }
 
 // ------------------------------------------------------------------------------------------------ projection
-// cand entry: idx | dist << 16 | octave << 25
-__global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
-    const int lane = threadIdx.x & 31;
-    const int iMP = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (iMP >= A.n_mp) return;
-    uint32_t* out = A.cand + (size_t)iMP * A.n;
-    int count = 0;
-    if (A.mp_valid == nullptr || A.mp_valid[iMP]) {
-        float rs;
-        int minLevel, maxLevel;
-        if (A.mode == 0) {
-            const int lvl = A.level[iMP];
-            float r = A.view_cos[iMP] > 0.998 ? 2.5f : 4.0f;     // RadiusByViewingCos (:131-137)
-            if (A.th != 1.0f) r = __fmul_rn(r, A.th);
-            rs = __fmul_rn(r, A.scale_factors[lvl]);
-            minLevel = lvl - 1; maxLevel = lvl;
-        } else {
-            rs = A.q_radius[iMP]; minLevel = A.q_minl[iMP]; maxLevel = A.q_maxl[iMP];
-        }
-        const float x = A.proj_x[iMP], y = A.proj_y[iMP];
-        // GetFeaturesInArea(x, y, rs, lvl-1, lvl)  (Frame.cc:327-380)
-        const int c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, A.minX), rs), A.invW)));
-        const int c1x = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, A.minX), rs), A.invW)));
-        const int c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, A.minY), rs), A.invH)));
-        const int c1y = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, A.minY), rs), A.invH)));
-        if (!(c0x >= GRID_COLS || c1x < 0 || c0y >= GRID_ROWS || c1y < 0)) {
-            const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
-            const uint32_t* dm = reinterpret_cast<const uint32_t*>(A.mp_desc + (size_t)iMP * 32);
-            const float xr = A.proj_xr[iMP];
-            for (int ix = c0x; ix <= c1x; ix++)
-                for (int iy = c0y; iy <= c1y; iy++) {
-                    const int cell = ix * GRID_ROWS + iy;
-                    const int s0 = A.cell_start[cell], s1 = A.cell_start[cell + 1];
-                    for (int base = s0; base < s1; base += 32) {
-                        const int e = base + lane;
-                        bool ok = false;
-                        uint32_t entry = 0;
-                        if (e < s1) {
-                            const int idx = A.cell_idx[e];
-                            const borb_keypoint kp = A.keys[idx];
-                            ok = true;
-                            if (bCheckLevels) {
-                                if (kp.octave < minLevel) ok = false;
-                                if (maxLevel >= 0 && kp.octave > maxLevel) ok = false;
-                            }
-                            if (ok) {
-                                const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
-                                ok = fabsf(dx) < rs && fabsf(dy) < rs;
-                            }
-                            if (ok && A.u_right != nullptr && !A.chi2) { // stereo consistency (:91-96)
-                                const float ur = A.u_right[idx];
-                                if (ur > 0) {
-                                    const float er = fabsf(__fsub_rn(xr, ur));
-                                    if (er > rs) ok = false;
-                                }
-                            }
-                            if (ok && A.chi2) {                          // Fuse reprojection gates (:907-931)
-                                const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
-                                const float kr = A.u_right != nullptr ? A.u_right[idx] : -1.0f;
-                                const float inv = A.inv_sigma2[kp.octave];
-                                if (kr >= 0) {
-                                    const float er = __fsub_rn(xr, kr);
-                                    const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
-                                    if ((double)__fmul_rn(e2, inv) > 7.8) ok = false;
-                                } else {
-                                    const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-                                    if ((double)__fmul_rn(e2, inv) > 5.99) ok = false;
-                                }
-                            }
-                            if (ok) {
-                                const int dist = ham_words(dm, reinterpret_cast<const uint32_t*>(A.desc + (size_t)idx * 32));
-                                entry = (uint32_t)idx | ((uint32_t)dist << 16) | ((uint32_t)kp.octave << 25);
-                            }
-                        }
-                        const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
-                        if (ok) out[count + __popc(bal & ((1u << lane) - 1))] = entry;
-                        count += __popc(bal);
-                    }
-                }
-        }
-    }
-    if (lane == 0) A.cand_cnt[iMP] = count;
-}
-
-// Order-dependent claiming (a feature taken by an earlier query is skipped by later ones) without walking the queries one
-// by one.  The CTA packs the candidate lists into shared memory, then works in ROUNDS: every unresolved query writes its
-// index into owner[f] (atomicMin) for each of its candidates f; a query whose index survives on ALL its candidates has
-// no unresolved predecessor touching them, so its sequential outcome is already determined — all such queries resolve
-// in parallel (they share no candidate).  Rounds = depth of the conflict chain (a handful for points spread over the
-// image); after REPLAY_ROUNDS rounds, or when the lists do not fit, one warp finishes the rest in index order.
-constexpr int REPLAY_THREADS = 1024;
-constexpr int REPLAY_ROUNDS = 48;
-constexpr int REPLAY_ECAP = 24576;        // packed candidate entries kept in shared memory; lists beyond it are read from global
-
-struct ReplayLists { const int* offs; const uint32_t* ent; const uint8_t* obs; };
-
-__device__ __forceinline__ ReplayLists stage_replay_lists(const ProjArgs& A, uint32_t* base) {
-    __shared__ int part[REPLAY_THREADS];
-    int* offs = reinterpret_cast<int*>(base);
-    uint32_t* ent = base + (A.n_mp + 1);
-    uint8_t* obs = reinterpret_cast<uint8_t*>(ent + REPLAY_ECAP);
-    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int C = (A.n_mp + REPLAY_THREADS - 1) / REPLAY_THREADS;
-    const int i0 = min(A.n_mp, tid * C), i1 = min(A.n_mp, i0 + C);
-    int sum = 0;
-    for (int i = i0; i < i1; i++) sum += A.cand_cnt[i];
-    part[tid] = sum;
-    __syncthreads();
-    if (tid < 32) {
-        int v[REPLAY_THREADS / 32], sl = 0;
-#pragma unroll
-        for (int k = 0; k < REPLAY_THREADS / 32; k++) { v[k] = part[tid * (REPLAY_THREADS / 32) + k]; sl += v[k]; }
-        int incl = sl;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-        int run = incl - sl;
-#pragma unroll
-        for (int k = 0; k < REPLAY_THREADS / 32; k++) { part[tid * (REPLAY_THREADS / 32) + k] = run; run += v[k]; }
-    }
-    __syncthreads();
-    int run = part[tid];
-    for (int i = i0; i < i1; i++) {
-        offs[i] = run;
-        run += A.cand_cnt[i];
-        obs[i] = (A.mp_has_obs == nullptr || A.mp_has_obs[i]) ? 1 : 0;
-    }
-    if (i1 == A.n_mp && (i0 < i1 || tid == 0)) offs[A.n_mp] = run;       // the thread that owns the tail (thread 0 if there is nothing)
-    __syncthreads();
-    for (int i = wrp; i < A.n_mp; i += REPLAY_THREADS / 32) {
-        const int o = offs[i], cnt = offs[i + 1] - o;
-        const uint32_t* c = A.cand + (size_t)i * A.n;
-        for (int p = lane; p < cnt; p += 32)
-            if (o + p < REPLAY_ECAP) ent[o + p] = c[p];
-    }
-    __syncthreads();
-    return ReplayLists{offs, ent, obs};
-}
-__host__ __device__ inline size_t replay_smem_words(int n_mp) { return (size_t)(n_mp + 1) + REPLAY_ECAP + (size_t)(n_mp + 3) / 4; }
-
-// One warp replays the map points in order (the occupancy skip is order dependent).
-// Shared body of the two resolve kernels.  LAST = false: SearchByProjection(F, vpMapPoints) — best/second-best with the
-// ratio test (:98-121), out[iq] = feature.  LAST = true: the pose-projection overloads — best only, threshold th_dist,
-// out[feature] = iq and a match event for the rotation histogram.
-template <bool LAST>
-__device__ __forceinline__ void resolve_rounds(const ProjArgs& A, uint32_t* rsm, int32_t* __restrict__ out, int32_t* __restrict__ ev_idx,
-                                               int* nev_sh, int* nm_sh) {
-    __shared__ int unresolved, round_left;
-    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int words = (A.n + 31) / 32;
-    uint32_t* held = rsm;                    // bit per frame feature: occupied (LAST: by a MapPoint with observations or any, per overload)
-    for (int w = tid; w < words; w += REPLAY_THREADS) {
-        uint32_t bits = 0;
-        if (A.occupied != nullptr)
-            for (int b = 0; b < 32; b++) {
-                const int i = w * 32 + b;
-                if (i < A.n && A.occupied[i]) bits |= 1u << b;
-            }
-        held[w] = bits;
-    }
-    uint32_t* owner = rsm + words;                                            // A.n entries
-    uint8_t* done = reinterpret_cast<uint8_t*>(owner + A.n);                  // A.n_mp flags
-    const ReplayLists Lq = stage_replay_lists(A, rsm + words + A.n + (A.n_mp + 3) / 4);
-    const bool fits = Lq.offs[A.n_mp] <= REPLAY_ECAP;
-    for (int i = tid; i < A.n_mp; i += REPLAY_THREADS) done[i] = 0;
-    if (tid == 0) { unresolved = A.n_mp; round_left = fits ? REPLAY_ROUNDS : 0; *nev_sh = 0; *nm_sh = 0; }
-    __syncthreads();
-
-    // resolves query iq against the current `held`; returns through out / events; must be called by a whole warp
-    auto resolve = [&](int iq, bool atomic) {
-        const int o = Lq.offs[iq], cnt = Lq.offs[iq + 1] - o;
-        const uint32_t* c = fits ? Lq.ent + o : A.cand + (size_t)iq * A.n;
-        unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-        for (int p = lane; p < cnt; p += 32) {
-            const uint32_t e = c[p];
-            const int idx = e & 0xFFFF;
-            if ((held[idx >> 5] >> (idx & 31)) & 1u) continue;
-            const unsigned key = (((e >> 16) & 0x1FFu) << 16) | (unsigned)p;
-            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
-        }
-        const unsigned best = warp_min(k1);
-        int m = -1;
-        if (best != 0xFFFFFFFFu) {
-            const int bestDist = (int)(best >> 16);
-            const uint32_t eb = c[best & 0xFFFFu];
-            if (LAST) {
-                if (bestDist <= A.th_dist) m = (int)(eb & 0xFFFF);
-            } else if (bestDist <= TH_HIGH) {
-                const unsigned second = warp_min(k1 == best ? k2 : k1);
-                const int bestLevel = (int)(eb >> 25);
-                int bestDist2 = 256, bestLevel2 = -1;
-                if (second != 0xFFFFFFFFu) { bestDist2 = (int)(second >> 16); bestLevel2 = (int)(c[second & 0xFFFFu] >> 25); }
-                if (!(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2))) m = (int)(eb & 0xFFFF);
-            }
-        }
-        if (lane == 0) {
-            if (!LAST) out[iq] = m;
-            if (m >= 0) {
-                if (Lq.obs[iq]) { if (atomic) atomicOr(&held[m >> 5], 1u << (m & 31)); else held[m >> 5] |= 1u << (m & 31); }
-                if (LAST) { out[m] = iq; ev_idx[atomicAdd(nev_sh, 1)] = m | (iq << 16); }     // match event: feature | query << 16
-                atomicAdd(nm_sh, 1);
-            }
-        }
-    };
-
-    while (true) {
-        if (unresolved == 0 || round_left == 0) break;                       // uniform: written before the last barrier
-        for (int f = tid; f < A.n; f += REPLAY_THREADS) owner[f] = 0xFFFFFFFFu;
-        __syncthreads();
-        for (int iq = wrp; iq < A.n_mp; iq += REPLAY_THREADS / 32) {
-            if (done[iq]) continue;
-            const int o = Lq.offs[iq], cnt = Lq.offs[iq + 1] - o;
-            for (int p = lane; p < cnt; p += 32) atomicMin(&owner[Lq.ent[o + p] & 0xFFFF], (uint32_t)iq);
-        }
-        __syncthreads();
-        int finished = 0;
-        for (int iq = wrp; iq < A.n_mp; iq += REPLAY_THREADS / 32) {
-            if (done[iq]) continue;
-            const int o = Lq.offs[iq], cnt = Lq.offs[iq + 1] - o;
-            bool mine = true;
-            for (int p = lane; p < cnt; p += 32) mine = mine && owner[Lq.ent[o + p] & 0xFFFF] == (uint32_t)iq;
-            if (!__all_sync(0xFFFFFFFFu, mine)) continue;
-            resolve(iq, true);
-            if (lane == 0) done[iq] = 1;
-            finished++;
-        }
-        if (lane == 0 && finished) atomicSub(&unresolved, finished);
-        if (tid == 0) round_left--;
-        __syncthreads();
-    }
-    __syncthreads();
-    if (tid >= 32 || unresolved == 0) return;
-    for (int iq = 0; iq < A.n_mp; iq++) {                                    // the rest, in index order, by one warp
-        if (done[iq]) continue;
-        resolve(iq, false);
-        __syncwarp();
-    }
-}
-__host__ __device__ inline size_t resolve_smem_words(int n, int n_mp) {
-    return (size_t)(n + 31) / 32 + (size_t)n + (size_t)(n_mp + 3) / 4 + replay_smem_words(n_mp);
-}
-
-__global__ void __launch_bounds__(REPLAY_THREADS) proj_resolve_kernel(ProjArgs A, int32_t* __restrict__ match_feat, int* __restrict__ n_matches) {
-    extern __shared__ uint32_t rsm[];
-    __shared__ int nev_sh, nm_sh;
-    resolve_rounds<false>(A, rsm, match_feat, nullptr, &nev_sh, &nm_sh);
-    __syncthreads();
-    if (threadIdx.x == 0) *n_matches = nm_sh;
-}
+// (candidate enumeration and claim resolution: k_proj.cu)
 
 // glibc (>= 2.28) logf for positive normal finite x — the function MapPoint::PredictScale calls (src/MapPoint.cc:393,410;
 // `log` resolves to the float overload).  ARM optimized-routines algorithm in double; checked on the CPU against glibc for
@@ -486,47 +235,6 @@ __global__ void __launch_bounds__(256) project_points_kernel(LastArgs L) {
     L.valid_out[i] = ok ? 1 : 0;
 }
 
-// One warp replays the last frame's map points in order: best candidate only (:1397-1424), occupancy by observations,
-// rotation histogram over the MATCH EVENTS (a feature re-claimed later appears twice, exactly as rotHist does).
-__global__ void __launch_bounds__(REPLAY_THREADS) proj_resolve_last_kernel(ProjArgs A, const borb_keypoint* __restrict__ cur_keys,
-                                                                           int32_t* __restrict__ state_cur, int32_t* __restrict__ ev_idx,
-                                                                           uint8_t* __restrict__ ev_bin, int* __restrict__ n_matches) {
-    extern __shared__ uint32_t rsm[];
-    __shared__ int hist[32];
-    __shared__ int nev_sh, nm_sh;
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < A.n; i += REPLAY_THREADS) state_cur[i] = -1;
-    if (tid < 32) hist[tid] = 0;
-    __syncthreads();                                                          // state_cur is rewritten by the resolving warps
-    resolve_rounds<true>(A, rsm, state_cur, ev_idx, &nev_sh, &nm_sh);
-    __syncthreads();
-    if (tid >= 32) return;
-    const int nev = nev_sh;
-    int nm = nm_sh;
-    if (A.check_ori) {
-        // rotation histogram over the MATCH EVENTS (a feature re-claimed later appears twice, exactly as rotHist does)
-        for (int e = lane; e < nev; e += 32) {
-            const int ev = ev_idx[e];
-            const int b = rot_bin(A.q_angle[ev >> 16], cur_keys[ev & 0xFFFF].angle);
-            ev_bin[e] = (uint8_t)b;
-            atomicAdd(&hist[b], 1);
-        }
-        __syncwarp();
-        int i1, i2, i3;
-        three_maxima(hist, i1, i2, i3);
-        // culling is order independent for the final state: every event of a culled bin nulls its feature
-        int removed = 0;
-        for (int e = lane; e < nev; e += 32) {
-            const int b = ev_bin[e];
-            if (b != i1 && b != i2 && b != i3) { state_cur[ev_idx[e] & 0xFFFF] = -2; removed++; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, off);
-        nm -= removed;
-    }
-    if (lane == 0) *n_matches = nm;
-}
-
 // SearchForInitialization (:405-520): one warp replays F1's level-0 features in order.  A candidate i2 is skipped
 // when an earlier feature already holds it with a distance <= ours (vMatchedDistance, :441-442); a better match
 // displaces the earlier owner (:462-466).  vMatchedDistance / vnMatches21 live in shared memory.
@@ -544,7 +252,7 @@ __global__ void __launch_bounds__(32) init_resolve_kernel(ProjArgs A, const borb
     __syncwarp();
     int nm = 0, nev = 0;
     for (int i1 = 0; i1 < n1; i1++) {
-        const int cnt = A.cand_cnt[i1];
+        const int cnt = A.cand_cnt[i1] & CAND_COUNT_MASK;
         if (cnt == 0) continue;
         const uint32_t* c = A.cand + (size_t)i1 * A.n;
         unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
@@ -608,7 +316,7 @@ __global__ void __launch_bounds__(256) proj_argmin_kernel(ProjArgs A, int32_t* _
     const int lane = threadIdx.x & 31;
     const int iq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (iq >= A.n_mp) return;
-    const int cnt = A.cand_cnt[iq];
+    const int cnt = A.cand_cnt[iq] & CAND_COUNT_MASK;
     const uint32_t* c = A.cand + (size_t)iq * A.n;
     unsigned k1 = 0xFFFFFFFFu;
     for (int p = lane; p < cnt; p += 32) k1 = min(k1, (((c[p] >> 16) & 0x1FFu) << 16) | (unsigned)p);
@@ -1020,26 +728,22 @@ int launch_grid_sort(const borb_keypoint* keys, int n, float minX, float minY, f
     return 1;
 }
 int launch_projection(const ProjArgs& A, int32_t* match_feat, int* n_matches, cudaStream_t s) {
-    if (A.n_mp > 0) proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
-    const size_t smem = resolve_smem_words(A.n, A.n_mp) * 4;
-    allow_max_smem((const void*)proj_resolve_kernel);
-    proj_resolve_kernel<<<1, REPLAY_THREADS, smem, s>>>(A, match_feat, n_matches);
+    launch_candidates(A, s);
+    launch_resolve(A, false, match_feat, nullptr, nullptr, n_matches, s);
     return 2;
 }
 int launch_projection_last(const LastArgs& L, const ProjArgs& A, int32_t* state_cur, int32_t* ev_idx, uint8_t* ev_bin, int* n_matches,
                            cudaStream_t s) {
     if (L.n_last > 0) {
         project_points_kernel<<<(L.n_last + 255) / 256, 256, 0, s>>>(L);
-        proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
+        launch_candidates(A, s);
     }
-    const size_t smem = resolve_smem_words(A.n, A.n_mp) * 4;
-    allow_max_smem((const void*)proj_resolve_last_kernel);
-    proj_resolve_last_kernel<<<1, REPLAY_THREADS, smem, s>>>(A, A.keys, state_cur, ev_idx, ev_bin, n_matches);
+    launch_resolve(A, true, state_cur, ev_idx, ev_bin, n_matches, s);
     return 3;
 }
 int launch_initialization(const ProjArgs& A, const borb_keypoint* keys1, int n1, int32_t* match12, int32_t* ev_idx, uint8_t* ev_bin,
                           float* prev, int* n_matches, cudaStream_t s) {
-    proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
+    launch_candidates(A, s);
     const size_t smem = (size_t)((A.n + 1) & ~1) * 2 + (size_t)A.n * 2 + 16;
     init_resolve_kernel<<<1, 32, smem, s>>>(A, keys1, n1, match12, ev_idx, ev_bin, prev, n_matches);
     return 2;
@@ -1068,7 +772,7 @@ int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best
     cudaMemsetAsync(n_found, 0, sizeof(int), s);
     if (A.n_mp > 0) {
         project_points_kernel<<<(L.n_last + 255) / 256, 256, 0, s>>>(L);
-        proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
+        launch_candidates(A, s);
         proj_argmin_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A, best_idx, n_found);
     }
     return 3;
