@@ -198,6 +198,15 @@ typedef struct borb_frame_view {
                                       built) and only `occupied` is read from the host */
 } borb_frame_view;
 
+/* Device-resident Frame: uploads the view once (keypoints, descriptors, mvuRight, scale factors) and builds the 64x48 feature
+ * grid of Frame::AssignFeaturesToGrid (src/Frame.cc:230-245) ONCE, so that the matcher calls of one Track() — SearchLocalPoints
+ * (src/Tracking.cc:1148-1194), SearchByProjection(CurrentFrame, LastFrame) (:867-898), relocalisation — stop re-uploading
+ * ~100 KB and re-sorting the grid per call: put the handle into borb_frame_view::resident.  The frame may be used by any
+ * matcher on the same device (creation records an event the users wait on).  Destroyed frames are recycled. */
+BORB_API borb_status borb_frame_create(borb_matcher* m, const borb_frame_view* view, borb_frame** out);
+BORB_API borb_status borb_frame_destroy(borb_frame* f);
+BORB_API borb_status borb_frame_info(const borb_frame* f, int32_t* n, int32_t* n_levels, int32_t* has_u_right);
+
 /* Local map points that passed Frame::isInFrustum (src/Frame.cc:269-325), in vpMapPoints order. */
 typedef struct borb_mappoint_view {
     int32_t n;

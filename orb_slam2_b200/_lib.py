@@ -72,6 +72,9 @@ _SIGNATURES = {
     "borb_extractor_set_input_format": (C.c_int, [vp, C.c_int, C.c_int]),
     "borb_extractor_set_rectify_maps": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "borb_matcher_destroy": (C.c_int, [vp]),
+    "borb_frame_create": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "borb_frame_destroy": (C.c_int, [vp]),
+    "borb_frame_info": (C.c_int, [vp, i32p, i32p, i32p]),
     "borb_search_by_projection": (C.c_int, [vp, vp, vp, C.c_float, C.c_float, vp, i32p]),
     "borb_search_by_projection_last": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                                  C.c_int, C.c_int, C.c_int, vp, i32p]),

@@ -16,6 +16,8 @@ struct borb_frame {
     uint8_t* desc = nullptr;
     float* u_right = nullptr;       // null: monocular
     float* depth = nullptr;
+    float* ur_store = nullptr;      // storage behind u_right / depth (always allocated)
+    float* depth_store = nullptr;
     float* sf = nullptr;
     int* cell_start = nullptr;
     int* cell_idx = nullptr;

@@ -20,6 +20,9 @@ struct borb_matcher {
     uint64_t launches = 0;
     int32_t* aux = nullptr;         // small device buffer that survives an arena re-layout (SearchBySim3: first direction's matches)
     size_t aux_count = 0;
+    uint8_t* h_out = nullptr;       // pinned landing buffer for results (one D2H per call)
+    size_t h_out_bytes = 0;
+    std::vector<int32_t> sel;       // indices of the valid queries of the current call
 };
 
 struct borb_voc {
@@ -67,6 +70,18 @@ borb_status ensure_host(borb_matcher* m, size_t bytes) {
     const size_t want = bytes + bytes / 2 + (1 << 16);
     BORB_CUDA(cudaMallocHost(&m->h_stage, want));
     m->h_bytes = want;
+    return BORB_OK;
+}
+
+borb_status ensure_out(borb_matcher* m, size_t bytes) {
+    bytes += 4096;
+    if (m->h_out_bytes >= bytes) return BORB_OK;
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->h_out) cudaFreeHost(m->h_out);
+    m->h_out = nullptr; m->h_out_bytes = 0;
+    const size_t want = bytes + bytes / 2 + (1 << 16);
+    BORB_CUDA(cudaMallocHost(&m->h_out, want));
+    m->h_out_bytes = want;
     return BORB_OK;
 }
 
@@ -239,8 +254,101 @@ borb_status borb_matcher_destroy(borb_matcher* m) {
     cudaFree(m->arena);
     cudaFree(m->aux);
     if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->h_out) cudaFreeHost(m->h_out);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
+    return BORB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident Frame.  Blocks of destroyed frames are recycled (a tracker creates one per camera frame).
+namespace {
+std::mutex g_frame_pool_mu;
+std::vector<borb_frame*> g_frame_pool;
+
+borb_status frame_alloc(int device, int n, int n_levels, bool stereo, borb_frame** out) {
+    borb_frame* f = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_frame_pool_mu);
+        for (size_t i = 0; i < g_frame_pool.size(); i++)
+            if (g_frame_pool[i]->device == device && g_frame_pool[i]->cap >= n) { f = g_frame_pool[i]; g_frame_pool.erase(g_frame_pool.begin() + i); break; }
+    }
+    if (!f) {
+        f = new borb_frame();
+        f->device = device;
+        f->cap = n < 2048 ? 2048 : ((n + 1023) & ~1023);
+        size_t off = 0;
+        auto put = [&](size_t bytes) { off = (off + 255) & ~size_t(255); const size_t o = off; off += bytes; return o; };
+        const size_t o_k = put((size_t)f->cap * sizeof(borb_keypoint)), o_d = put((size_t)f->cap * 32), o_u = put((size_t)f->cap * 4), o_z = put((size_t)f->cap * 4);
+        const size_t o_s = put(BORB_MAX_LEVELS * 4), o_cs = put((size_t)(GRID_CELLS + 1) * 4), o_ci = put((size_t)MATCH_MAX_FEATURES * 4 + 16);
+        cudaError_t e = cudaMalloc(&f->block, off + 256);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming);
+        if (e != cudaSuccess) { set_error("frame allocation failed: %s", cudaGetErrorString(e)); cudaFree(f->block); delete f; return BORB_ERR_CUDA; }
+        f->block_bytes = off + 256;
+        f->keys = (borb_keypoint*)(f->block + o_k); f->desc = f->block + o_d; f->ur_store = (float*)(f->block + o_u); f->depth_store = (float*)(f->block + o_z);
+        f->sf = (float*)(f->block + o_s); f->cell_start = (int*)(f->block + o_cs); f->cell_idx = (int*)(f->block + o_ci);
+    }
+    // u_right / depth storage always exists; the pointers are nulled for a monocular frame
+    f->u_right = stereo ? f->ur_store : nullptr;
+    f->depth = stereo ? f->depth_store : nullptr;
+    f->n = n; f->n_levels = n_levels;
+    *out = f;
+    return BORB_OK;
+}
+}  // namespace
+
+borb_status borb_frame_create(borb_matcher* m, const borb_frame_view* v, borb_frame** out) {
+    if (!m || !v || !out) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (v->resident) { set_error("the view already refers to a resident frame"); return BORB_ERR_INVALID_ARG; }
+    const FrameInfo I = frame_info(v);
+    borb_status s = check_frame(v, I, m);
+    if (s != BORB_OK) return s;
+    if (I.n_levels > BORB_MAX_LEVELS) { set_error("too many levels"); return BORB_ERR_INVALID_ARG; }
+    BORB_CUDA(cudaSetDevice(m->device));
+    borb_frame* f = nullptr;
+    if ((s = frame_alloc(m->device, I.n, I.n_levels, v->u_right != nullptr, &f)) != BORB_OK) return s;
+    f->min_x = I.min_x; f->min_y = I.min_y; f->max_x = I.max_x; f->max_y = I.max_y;
+    Stager st(m);
+    const size_t o_k = st.add(v->keys_un, (size_t)I.n * sizeof(borb_keypoint)), o_d = st.add(v->desc, (size_t)I.n * 32);
+    const size_t o_u = v->u_right ? st.add(v->u_right, (size_t)I.n * 4) : 0;
+    const size_t o_s = st.add(v->scale_factors, (size_t)I.n_levels * 4);
+    if ((s = commit(st, st.off)) != BORB_OK) { borb_frame_destroy(f); return s; }
+    uint8_t* b = m->arena;
+    cudaStream_t q = m->stream;
+    if (I.n > 0) {
+        BORB_CUDA(cudaMemcpyAsync(f->keys, b + o_k, (size_t)I.n * sizeof(borb_keypoint), cudaMemcpyDeviceToDevice, q));
+        BORB_CUDA(cudaMemcpyAsync(f->desc, b + o_d, (size_t)I.n * 32, cudaMemcpyDeviceToDevice, q));
+        if (v->u_right) BORB_CUDA(cudaMemcpyAsync(f->u_right, b + o_u, (size_t)I.n * 4, cudaMemcpyDeviceToDevice, q));
+    }
+    BORB_CUDA(cudaMemcpyAsync(f->sf, b + o_s, (size_t)I.n_levels * 4, cudaMemcpyDeviceToDevice, q));
+    const float invW = (float)GRID_COLS / (float)(I.max_x - I.min_x), invH = (float)GRID_ROWS / (float)(I.max_y - I.min_y);
+    if (I.n > 0) m->launches += launch_grid_sort(f->keys, I.n, I.min_x, I.min_y, invW, invH, f->cell_start, f->cell_idx, q);
+    else BORB_CUDA(cudaMemsetAsync(f->cell_start, 0, (size_t)(GRID_CELLS + 1) * 4, q));
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaEventRecord(f->ready, q));
+    BORB_CUDA(cudaStreamSynchronize(q));              // the staging arena is reused by the next call on this matcher
+    *out = f;
+    return BORB_OK;
+}
+
+borb_status borb_frame_destroy(borb_frame* f) {
+    if (!f) return BORB_OK;
+    std::lock_guard<std::mutex> lk(g_frame_pool_mu);
+    if (g_frame_pool.size() < 16) { g_frame_pool.push_back(f); return BORB_OK; }
+    cudaSetDevice(f->device);
+    cudaEventSynchronize(f->ready);
+    cudaFree(f->block);
+    cudaEventDestroy(f->ready);
+    delete f;
+    return BORB_OK;
+}
+
+borb_status borb_frame_info(const borb_frame* f, int32_t* n, int32_t* n_levels, int32_t* has_u_right) {
+    if (!f) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (n) *n = f->n;
+    if (n_levels) *n_levels = f->n_levels;
+    if (has_u_right) *has_u_right = f->u_right != nullptr;
     return BORB_OK;
 }
 
@@ -520,83 +628,109 @@ borb_status borb_search_local_points(borb_matcher* m, const borb_frame_view* F, 
                                      int32_t* match_feat, int32_t* n_matches) {
     if (!m || !F || !pts || !Tcw || !Ow || !in_view || !match_feat || !n_matches) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
     *n_matches = 0;
-    const int nq = pts->n;
-    if (F->n < 0 || F->n > MATCH_MAX_FEATURES || nq < 0 || nq > MATCH_MAX_FEATURES) { set_error("feature count outside [0,%d]", MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
-    for (int i = 0; i < nq; i++) { in_view[i] = 0; match_feat[i] = -1; }
-    if (nq == 0) return BORB_OK;
-    if (!pts->world_pos || !pts->desc || !pts->max_distance || !pts->min_distance || !pts->normal) { set_error("incomplete world-points view"); return BORB_ERR_INVALID_ARG; }
-    if (F->n_levels < 1 || !F->scale_factors || !(F->max_x > F->min_x) || !(F->max_y > F->min_y) || (F->n > 0 && (!F->keys_un || !F->desc))) {
-        set_error("incomplete frame view"); return BORB_ERR_INVALID_ARG;
+    const int n_all = pts->n;
+    const FrameInfo I = frame_info(F);
+    borb_status s = check_frame(F, I, m);
+    if (s != BORB_OK) return s;
+    if (n_all < 0) { set_error("negative point count"); return BORB_ERR_INVALID_ARG; }
+    for (int i = 0; i < n_all; i++) {
+        in_view[i] = 0; match_feat[i] = -1;
+        if (proj_x) proj_x[i] = 0.f;
+        if (proj_y) proj_y[i] = 0.f;
+        if (proj_xr) proj_xr[i] = 0.f;
+        if (level) level[i] = 0;
+        if (view_cos) view_cos[i] = 0.f;
     }
+    if (n_all == 0) return BORB_OK;
+    if (!pts->world_pos || !pts->desc || !pts->max_distance || !pts->min_distance || !pts->normal) { set_error("incomplete world-points view"); return BORB_ERR_INVALID_ARG; }
     if (!(log_scale_factor > 0.f)) { set_error("log_scale_factor must be positive (Frame::mfLogScaleFactor)"); return BORB_ERR_INVALID_ARG; }
+    // Only the points that reach isInFrustum travel (src/Tracking.cc:1171-1175 skips the already-matched and the bad ones): a
+    // KITTI-scale local map lists ten thousand points of which a fraction is valid, and the reference has no limit on the list.
+    std::vector<int32_t>& sel = m->sel;
+    sel.clear();
+    for (int i = 0; i < n_all; i++)
+        if (!pts->valid || pts->valid[i]) sel.push_back(i);
+    const int nq = (int)sel.size();
+    if (nq == 0) return BORB_OK;
+    if (nq > MATCH_MAX_FEATURES) { set_error("%d valid local map points (limit %d per call)", nq, MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+    const bool gather = nq != n_all;
     BORB_CUDA(cudaSetDevice(m->device));
     Stager st(m);
-    const int nf = F->n > 0 ? F->n : 1;
-    const size_t o_keys = st.add(F->keys_un, (size_t)F->n * sizeof(borb_keypoint));
-    const size_t o_desc = st.add(F->desc, (size_t)F->n * 32);
-    const size_t o_ur = F->u_right ? st.add(F->u_right, (size_t)F->n * 4) : 0;
-    const size_t o_occ = F->occupied ? st.add(F->occupied, (size_t)F->n) : 0;
-    const size_t o_sf = st.add(F->scale_factors, (size_t)F->n_levels * 4);
-    const size_t o_wp = st.add(pts->world_pos, (size_t)nq * 12), o_md = st.add(pts->desc, (size_t)nq * 32);
-    const size_t o_vin = pts->valid ? st.add(pts->valid, (size_t)nq) : 0;
-    const size_t o_obs = has_obs ? st.add(has_obs, (size_t)nq) : 0;
-    const size_t o_mx = st.add(pts->max_distance, (size_t)nq * 4), o_mn = st.add(pts->min_distance, (size_t)nq * 4);
-    const size_t o_nr = st.add(pts->normal, (size_t)nq * 12);
+    const int nf = I.n > 0 ? I.n : 1;
+    FrameStage fs = stage_frame(st, F, I, true);
+    // gathered inputs are written straight into the pinned staging buffer after the layout is known (src = nullptr)
+    const size_t o_wp = st.add(gather ? nullptr : pts->world_pos, (size_t)nq * 12), o_md = st.add(gather ? nullptr : pts->desc, (size_t)nq * 32);
+    const size_t o_obs = has_obs ? st.add(gather ? nullptr : has_obs, (size_t)nq) : 0;
+    const size_t o_mx = st.add(gather ? nullptr : pts->max_distance, (size_t)nq * 4), o_mn = st.add(gather ? nullptr : pts->min_distance, (size_t)nq * 4);
+    const size_t o_nr = st.add(gather ? nullptr : pts->normal, (size_t)nq * 12);
     const size_t input_end = st.off;
-    const size_t o_cs = st.reserve((size_t)(GRID_CELLS + 1) * 4), o_ci = st.reserve((size_t)MATCH_MAX_FEATURES * 4 + 16);
-    const size_t o_px = st.reserve((size_t)nq * 4), o_py = st.reserve((size_t)nq * 4), o_pxr = st.reserve((size_t)nq * 4), o_rad = st.reserve((size_t)nq * 4);
-    const size_t o_ang = st.reserve((size_t)nq * 4), o_minl = st.reserve((size_t)nq * 4), o_maxl = st.reserve((size_t)nq * 4), o_val = st.reserve((size_t)nq);
-    const size_t o_lvl = st.reserve((size_t)nq * 4), o_vc = st.reserve((size_t)nq * 4);
+    reserve_grid(st, I, fs);
+    const size_t o_rad = st.reserve((size_t)nq * 4), o_ang = st.reserve((size_t)nq * 4), o_minl = st.reserve((size_t)nq * 4), o_maxl = st.reserve((size_t)nq * 4);
     const size_t o_cand = st.reserve((size_t)nq * nf * 4), o_cc = st.reserve((size_t)nq * 4);
-    const size_t o_match = st.reserve((size_t)nq * 4), o_nm = st.reserve(16);
+    // results, contiguous so that ONE device-to-host copy brings them back: px | py | pxr | level | viewcos | match | nm | valid
+    const size_t o_res = st.reserve((size_t)nq * 25 + 64);
+    const size_t o_px = o_res, o_py = o_px + (size_t)nq * 4, o_pxr = o_py + (size_t)nq * 4, o_lvl = o_pxr + (size_t)nq * 4, o_vc = o_lvl + (size_t)nq * 4;
+    const size_t o_match = o_vc + (size_t)nq * 4, o_nm = o_match + (size_t)nq * 4, o_val = o_nm + 16;
+    const size_t res_bytes = (size_t)nq * 25 + 16;
     const size_t total = st.off;
     st.off = input_end;
-    borb_status s = commit(st, total);
-    if (s != BORB_OK) return s;
+    if ((s = ensure_host(m, input_end)) != BORB_OK) return s;
+    if ((s = ensure_out(m, res_bytes)) != BORB_OK) return s;
+    if (gather) {
+        BORB_CUDA(cudaStreamSynchronize(m->stream));
+        uint8_t* h = m->h_stage;
+        for (int k = 0; k < nq; k++) {
+            const int i = sel[k];
+            std::memcpy(h + o_wp + (size_t)k * 12, pts->world_pos + (size_t)i * 3, 12);
+            std::memcpy(h + o_md + (size_t)k * 32, pts->desc + (size_t)i * 32, 32);
+            if (has_obs) h[o_obs + k] = has_obs[i];
+            std::memcpy(h + o_mx + (size_t)k * 4, pts->max_distance + i, 4);
+            std::memcpy(h + o_mn + (size_t)k * 4, pts->min_distance + i, 4);
+            std::memcpy(h + o_nr + (size_t)k * 12, pts->normal + (size_t)i * 3, 12);
+        }
+    }
+    if ((s = commit(st, total)) != BORB_OK) return s;
     uint8_t* b = m->arena;
-    BORB_CUDA(cudaMemsetAsync(b + o_lvl, 0, (size_t)nq * 4, m->stream));       // fields of points outside the frustum read as 0
-    BORB_CUDA(cudaMemsetAsync(b + o_vc, 0, (size_t)nq * 4, m->stream));
+    BORB_CUDA(cudaMemsetAsync(b + o_lvl, 0, (size_t)nq * 8, m->stream));       // level | viewcos of points outside the frustum read as 0
+    ProjArgs A{};
+    if ((s = bind_frame(m, I, fs, A)) != BORB_OK) return s;
     LastArgs L{};
     L.variant = 3; L.n_last = nq; L.world_pos = (const float*)(b + o_wp);
     L.max_distance = (const float*)(b + o_mx); L.min_distance = (const float*)(b + o_mn); L.normal = (const float*)(b + o_nr);
     for (int i = 0; i < 3; i++) L.Ow[i] = Ow[i];
-    L.log_scale = log_scale_factor; L.n_levels = F->n_levels; L.view_cos_limit = viewing_cos_limit;
-    L.valid_in = pts->valid ? b + o_vin : nullptr;
+    L.log_scale = log_scale_factor; L.n_levels = I.n_levels; L.view_cos_limit = viewing_cos_limit;
+    L.valid_in = nullptr;
     for (int i = 0; i < 12; i++) L.T[i] = Tcw[i];
     L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.bf = mbf; L.th = th;
-    L.minX = F->min_x; L.minY = F->min_y; L.maxX = F->max_x; L.maxY = F->max_y;
-    L.scale_factors = (const float*)(b + o_sf);
+    L.minX = I.min_x; L.minY = I.min_y; L.maxX = I.max_x; L.maxY = I.max_y;
+    L.scale_factors = A.scale_factors;
     L.proj_x = (float*)(b + o_px); L.proj_y = (float*)(b + o_py); L.proj_xr = (float*)(b + o_pxr); L.radius = (float*)(b + o_rad);
     L.angle = (float*)(b + o_ang); L.minl = (int32_t*)(b + o_minl); L.maxl = (int32_t*)(b + o_maxl); L.valid_out = b + o_val;
     L.level_out = (int32_t*)(b + o_lvl); L.viewcos_out = (float*)(b + o_vc);
-    ProjArgs A{};
-    A.n = F->n; A.keys = (const borb_keypoint*)(b + o_keys); A.desc = b + o_desc;
-    A.u_right = F->u_right ? (const float*)(b + o_ur) : nullptr;
-    A.occupied = F->occupied ? b + o_occ : nullptr;
-    A.minX = F->min_x; A.minY = F->min_y;
-    A.invW = (float)GRID_COLS / (float)(F->max_x - F->min_x);
-    A.invH = (float)GRID_ROWS / (float)(F->max_y - F->min_y);
-    A.scale_factors = (const float*)(b + o_sf);
-    A.cell_start = (const int*)(b + o_cs); A.cell_idx = (const int*)(b + o_ci);
     A.n_mp = nq; A.proj_x = L.proj_x; A.proj_y = L.proj_y; A.proj_xr = L.proj_xr; A.view_cos = L.viewcos_out; A.level = L.level_out;
     A.mp_desc = b + o_md; A.mp_valid = b + o_val; A.mp_has_obs = has_obs ? b + o_obs : nullptr;
-    A.th = th; A.nnratio = nnratio;
+    A.th = th; A.nnratio = nnratio; A.th_dist = TH_HIGH;
     A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
     A.mode = 0;
-    if (F->n > 0) m->launches += launch_grid_sort(A.keys, A.n, A.minX, A.minY, A.invW, A.invH, (int*)(b + o_cs), (int*)(b + o_ci), m->stream);
-    else BORB_CUDA(cudaMemsetAsync(b + o_cs, 0, (size_t)(GRID_CELLS + 1) * 4, m->stream));
     m->launches += launch_frustum_projection(L, A, (int32_t*)(b + o_match), (int*)(b + o_nm), m->stream);
     BORB_CUDA(cudaGetLastError());
-    cudaStream_t q = m->stream;
-    BORB_CUDA(cudaMemcpyAsync(in_view, b + o_val, (size_t)nq, cudaMemcpyDeviceToHost, q));
-    if (proj_x) BORB_CUDA(cudaMemcpyAsync(proj_x, b + o_px, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
-    if (proj_y) BORB_CUDA(cudaMemcpyAsync(proj_y, b + o_py, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
-    if (proj_xr) BORB_CUDA(cudaMemcpyAsync(proj_xr, b + o_pxr, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
-    if (level) BORB_CUDA(cudaMemcpyAsync(level, b + o_lvl, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
-    if (view_cos) BORB_CUDA(cudaMemcpyAsync(view_cos, b + o_vc, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
-    BORB_CUDA(cudaMemcpyAsync(match_feat, b + o_match, (size_t)nq * 4, cudaMemcpyDeviceToHost, q));
-    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, q));
-    BORB_CUDA(cudaStreamSynchronize(q));
+    BORB_CUDA(cudaMemcpyAsync(m->h_out, b + o_res, res_bytes, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    const uint8_t* r = m->h_out;
+    const float* rpx = (const float*)r; const float* rpy = rpx + nq; const float* rpxr = rpy + nq;
+    const int32_t* rlvl = (const int32_t*)(rpxr + nq); const float* rvc = (const float*)(rlvl + nq);
+    const int32_t* rmatch = (const int32_t*)(rvc + nq);
+    *n_matches = *(const int32_t*)(rmatch + nq);
+    const uint8_t* rval = r + (o_val - o_res);
+    for (int k = 0; k < nq; k++) {
+        const int i = sel[k];
+        in_view[i] = rval[k]; match_feat[i] = rmatch[k];
+        if (proj_x) proj_x[i] = rpx[k];
+        if (proj_y) proj_y[i] = rpy[k];
+        if (proj_xr) proj_xr[i] = rpxr[k];
+        if (level) level[i] = rlvl[k];
+        if (view_cos) view_cos[i] = rvc[k];
+    }
     return BORB_OK;
 }
 

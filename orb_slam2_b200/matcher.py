@@ -22,7 +22,7 @@ TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30        # src/ORBmatcher.cc:37-39
 class _FrameViewC(C.Structure):
     _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("occupied", C.c_void_p),
                 ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("n_levels", C.c_int32),
-                ("scale_factors", C.c_void_p)]
+                ("scale_factors", C.c_void_p), ("resident", C.c_void_p)]
 
 
 class _MapPointViewC(C.Structure):
@@ -88,6 +88,51 @@ class FrameView:
     occupied: Optional[np.ndarray] = None                 # mvpMapPoints[i] && Observations()>0 (or != NULL, per overload)
     mfLogScaleFactor: Optional[float] = None              # Frame::mfLogScaleFactor; default logf(mvScaleFactors[1])
     mvInvLevelSigma2: Optional[np.ndarray] = None         # only read by Fuse(pKF, vpMapPoints, th)
+    resident: Optional["ResidentFrame"] = None            # device-resident copy (borb_frame): only `occupied` travels per call
+
+    def _view(self, with_ur: bool = True):
+        """(ctypes view, arrays to keep alive).  With a resident frame only `occupied` is read from the host."""
+        oc = np.ascontiguousarray(self.occupied, np.uint8) if self.occupied is not None else None
+        sf = np.ascontiguousarray(self.mvScaleFactors, np.float32)
+        if self.resident is not None:
+            return _FrameViewC(0, None, None, None, _p(oc), 0.0, 0.0, 0.0, 0.0, len(sf), None, self.resident._h), [oc, sf]
+        k = np.ascontiguousarray(self.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(self.mDescriptors, np.uint8)
+        ur = np.ascontiguousarray(self.mvuRight, np.float32) if (with_ur and self.mvuRight is not None) else None
+        return _FrameViewC(len(k), _p(k), _p(d), _p(ur), _p(oc), *[float(x) for x in self.bounds], len(sf), _p(sf), None), [k, d, ur, oc, sf]
+
+    def make_resident(self, matcher: "ORBmatcher") -> "FrameView":
+        """Uploads the frame once (borb_frame_create: keypoints, descriptors, mvuRight, feature grid) and returns a view that
+        refers to the device copy."""
+        import dataclasses
+        return dataclasses.replace(self, resident=ResidentFrame(matcher, self))
+
+
+class ResidentFrame:
+    """borb_frame: a Frame's features and 64x48 grid kept in HBM across the matcher calls of one Track()."""
+
+    def __init__(self, matcher: "ORBmatcher", F: "FrameView"):
+        self._lib = _lib.load()
+        fv, keep = FrameView._view(dataclass_replace_resident(F), True)
+        h = C.c_void_p()
+        check(self._lib.borb_frame_create(matcher._h, C.byref(fv), C.byref(h)), "borb_frame_create")
+        self._h = h
+        self.n = len(F.mvKeysUn)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.borb_frame_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def dataclass_replace_resident(F):
+    import dataclasses
+    return dataclasses.replace(F, resident=None)
 
 
 @dataclass
@@ -191,11 +236,7 @@ class ORBmatcher:
 
     def SearchByProjection(self, F: FrameView, mps: MapPointsView, th: float = 3.0) -> Tuple[int, np.ndarray]:
         """src/ORBmatcher.cc:45-129.  Returns (nmatches, match_feat[n_mp]): frame feature that received map point i, or -1."""
-        k = np.ascontiguousarray(F.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(F.mDescriptors, np.uint8)
-        ur = np.ascontiguousarray(F.mvuRight, np.float32) if F.mvuRight is not None else None
-        oc = np.ascontiguousarray(F.occupied, np.uint8) if F.occupied is not None else None
-        sf = np.ascontiguousarray(F.mvScaleFactors, np.float32)
-        fv = _FrameViewC(len(k), _p(k), _p(d), _p(ur), _p(oc), *[float(x) for x in F.bounds], len(sf), _p(sf))
+        fv, keep = F._view()
         px = np.ascontiguousarray(mps.mTrackProjX, np.float32); py = np.ascontiguousarray(mps.mTrackProjY, np.float32)
         pxr = np.ascontiguousarray(mps.mTrackProjXR, np.float32); lv = np.ascontiguousarray(mps.mnTrackScaleLevel, np.int32)
         vc = np.ascontiguousarray(mps.mTrackViewCos, np.float32); md = np.ascontiguousarray(mps.descriptors, np.uint8)
@@ -212,11 +253,8 @@ class ORBmatcher:
                                th: float, bForward: bool = False, bBackward: bool = False) -> Tuple[int, np.ndarray]:
         """SearchByProjection(CurrentFrame, LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470.  Tcw: (3,4) or (4,4) current pose;
         K = (fx, fy, cx, cy).  Returns (nmatches, state[cur.N]): >=0 last-frame index now matched, -1 untouched, -2 culled."""
-        k = np.ascontiguousarray(Cur.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(Cur.mDescriptors, np.uint8)
-        ur = np.ascontiguousarray(Cur.mvuRight, np.float32) if Cur.mvuRight is not None else None
-        oc = np.ascontiguousarray(Cur.occupied, np.uint8) if Cur.occupied is not None else None
-        sf = np.ascontiguousarray(Cur.mvScaleFactors, np.float32)
-        fv = _FrameViewC(len(k), _p(k), _p(d), _p(ur), _p(oc), *[float(x) for x in Cur.bounds], len(sf), _p(sf))
+        fv, keep = Cur._view()
+        k = Cur.mvKeysUn
         lk = np.ascontiguousarray(Last.mvKeysUn, KP_DTYPE); wp = np.ascontiguousarray(Last.world_pos, np.float32)
         ld = np.ascontiguousarray(Last.descriptors, np.uint8)
         va = np.ascontiguousarray(Last.valid, np.uint8) if Last.valid is not None else None
@@ -231,12 +269,9 @@ class ORBmatcher:
         return n.value, state[:len(k)]
 
     def _points_call(self, F: FrameView, P: WorldPointsView, with_stereo: bool = False):
-        k = np.ascontiguousarray(F.mvKeysUn, KP_DTYPE); d = np.ascontiguousarray(F.mDescriptors, np.uint8)
-        oc = np.ascontiguousarray(F.occupied, np.uint8) if F.occupied is not None else None
+        fv, keep = F._view(with_stereo)
+        k = F.mvKeysUn
         sf = np.ascontiguousarray(F.mvScaleFactors, np.float32)
-        ur = np.ascontiguousarray(F.mvuRight, np.float32) if (with_stereo and F.mvuRight is not None) else None
-        fv = _FrameViewC(len(k), _p(k), _p(d), _p(ur), _p(oc), *[float(x) for x in F.bounds], len(sf), _p(sf))
-        keep = [k, d, oc, sf, ur]
         arrs = []
         for a, dt in ((P.world_pos, np.float32), (P.descriptors, np.uint8), (P.max_distance, np.float32), (P.min_distance, np.float32),
                       (P.normal, np.float32), (P.angle, np.float32), (P.valid, np.uint8)):

@@ -300,3 +300,75 @@ def test_matches_reference_golden_vectors(M, oracle, name):
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "match_ref.npz"))
     build, _port, gpu = GOLDEN_CASES[name]
     assert np.array_equal(golden_flatten(gpu(M, build(oracle))), g[name])
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+def test_resident_frame_gives_the_same_results(M, oracle, views, seed):
+    """borb_frame (device-resident Frame, §8 f4): the three Tracking-thread searches through a resident frame equal the
+    host-view calls and the oracle; the resident frame is reused across calls and across matcher handles."""
+    v = views[seed]
+    mt, mt2 = M.ORBmatcher(0.8, True), M.ORBmatcher(0.9, True)
+    F, mps = mf.projection_case(v, seed + 10, n_mp=400)
+    FR = F.make_resident(mt)
+    n_o, m_o = oracle.port_search_by_projection(F, mps, 3.0, 0.8)
+    for _ in range(2):
+        n_g, m_g = mt.SearchByProjection(FR, mps, 3.0)
+        assert n_g == n_o and np.array_equal(m_g, m_o)
+    # the occupancy mask still travels per call
+    import dataclasses
+    occ2 = np.zeros(len(F.mvKeysUn), np.uint8); occ2[::3] = 1
+    F2, FR2 = dataclasses.replace(F, occupied=occ2), dataclasses.replace(FR, occupied=occ2)
+    n_o2, m_o2 = oracle.port_search_by_projection(F2, mps, 3.0, 0.8)
+    n_g2, m_g2 = mt.SearchByProjection(FR2, mps, 3.0)
+    assert n_g2 == n_o2 and np.array_equal(m_g2, m_o2) and not np.array_equal(m_o2, m_o)
+    # motion-model search on another matcher handle (another thread's stream) against the same resident frame
+    Cur, Last, Tcw, K = mf.last_frame_case(v, seed + 20)
+    CurR = Cur.make_resident(mt)
+    n_o3, s_o3 = oracle.port_search_by_projection_last(Cur, Last, Tcw, K, 40.0, 7.0, False, False, True)
+    n_g3, s_g3 = mt2.SearchByProjectionLast(CurR, Last, Tcw, K, 40.0, 7.0)
+    assert n_g3 == n_o3 and np.array_equal(s_g3, s_o3)
+    # SearchLocalPoints
+    Fw, P, Tcw2, Ow, K2 = mf.world_points_case(v, seed + 70)
+    Fw = M.FrameView(Fw.mvKeysUn, Fw.mDescriptors, Fw.mvScaleFactors, Fw.bounds, mvuRight=v["ur"], occupied=Fw.occupied)
+    a = mt.SearchLocalPoints(Fw, P, Tcw2, Ow, K2, 40.0, 3.0)
+    b = mt.SearchLocalPoints(Fw.make_resident(mt), P, Tcw2, Ow, K2, 40.0, 3.0)
+    assert a["nmatches"] == b["nmatches"] > 30
+    for f in a:
+        assert np.array_equal(a[f], b[f]), f
+
+
+def test_search_local_points_skips_invalid_points(M, oracle, views):
+    """Points that never reach isInFrustum (already matched / bad, src/Tracking.cc:1171-1175) are not staged: results of the
+    valid ones are unchanged and the invalid ones read 'not in view'."""
+    v = views[7]
+    F, P, Tcw, Ow, K = mf.world_points_case(v, 77)
+    F = M.FrameView(F.mvKeysUn, F.mDescriptors, F.mvScaleFactors, F.bounds, mvuRight=v["ur"], occupied=F.occupied)
+    import dataclasses
+    rng = np.random.default_rng(5)
+    valid = (rng.random(len(P.world_pos)) < 0.6).astype(np.uint8)
+    Pv = dataclasses.replace(P, valid=valid)
+    mt = M.ORBmatcher(0.8, True)
+    got = mt.SearchLocalPoints(F, Pv, Tcw, Ow, K, 40.0, 3.0)
+    fr = oracle.port_is_in_frustum(F, Pv, Tcw, Ow, K, 40.0, 0.5)
+    mps = M.MapPointsView(fr["proj_x"], fr["proj_y"], fr["proj_xr"], fr["level"], fr["view_cos"], P.descriptors, valid=fr["in_view"])
+    n_o, m_o = oracle.port_search_by_projection(F, mps, 3.0, 0.8)
+    assert np.array_equal(got["in_view"], fr["in_view"]) and not np.any(got["in_view"][valid == 0])
+    for f in ("proj_x", "proj_y", "proj_xr", "level", "view_cos"):
+        assert np.array_equal(got[f], fr[f]), f
+    assert got["nmatches"] == n_o > 20 and np.array_equal(got["match"], m_o)
+
+
+@pytest.mark.parametrize("th", [40.0, 150.0])
+def test_long_candidate_lists(M, oracle, views, th):
+    """Candidate lists beyond one warp (sorted in place up to 128 entries) and beyond the sort capacity (kept in position order,
+    resolved by full scans): huge search windows on the motion-model search and on SearchByProjection(F, MapPoints)."""
+    v = views[8]
+    Cur, Last, Tcw, K = mf.last_frame_case(v, 31)
+    for fw, bw in ((False, False), (True, False)):
+        n_o, s_o = oracle.port_search_by_projection_last(Cur, Last, Tcw, K, 40.0, th, fw, bw, True)
+        n_g, s_g = M.ORBmatcher(0.9, True).SearchByProjectionLast(Cur, Last, Tcw, K, 40.0, th, fw, bw)
+        assert n_g == n_o > 20 and np.array_equal(s_g, s_o), int((s_g != s_o).sum())
+    F, mps = mf.projection_case(v, 19, n_mp=300)
+    n_o, m_o = oracle.port_search_by_projection(F, mps, th, 0.9)
+    n_g, m_g = M.ORBmatcher(0.9, True).SearchByProjection(F, mps, th)
+    assert n_g == n_o and np.array_equal(m_g, m_o), int((m_g != m_o).sum())
