@@ -205,6 +205,30 @@ typedef struct borb_frame_view {
  * matcher on the same device (creation records an event the users wait on).  Destroyed frames are recycled. */
 BORB_API borb_status borb_frame_create(borb_matcher* m, const borb_frame_view* view, borb_frame** out);
 BORB_API borb_status borb_frame_destroy(borb_frame* f);
+
+/* Camera.* of the settings file as Tracking builds mK / mDistCoef / mbf (src/Tracking.cc:54-90). */
+typedef struct borb_camera {
+    float fx, fy, cx, cy;
+    float k1, k2, p1, p2, k3;      /* k1 == 0 => mvKeysUn = mvKeys (src/Frame.cc:406-410) */
+    float bf;                      /* Camera.bf */
+} borb_camera;
+
+/* The tail of the Frame constructors (src/Frame.cc:61-117 stereo, :119-178 RGB-D, :180-233 monocular) ON THE DEVICE for images
+ * of the LAST batch of extractor `e` — keypoints and descriptors go from the extractor's workspace into resident frames without
+ * crossing PCIe:  Frame::UndistortKeyPoints (:404-434, cv::undistortPoints restated: double arithmetic, 5 iterations),
+ * Frame::ComputeStereoFromRGBD (:643-664) and Frame::AssignFeaturesToGrid (:230-245).
+ *   images[i], n_keys[i]   image index inside the batch and its keypoint count (n_out of the extract call)
+ *   mode 0 monocular; 1 stereo: mvuRight / mvDepth are the association borb_stereo_frames computed for pair images[i]/2
+ *        (images[i] must be the LEFT image, an even index); 2 RGB-D: depth[i] = host depth map of that frame, registered to
+ *        the image (same width x height), depth_type 0 = CV_32F metres, 1 = CV_16U raw with depth_factor = mDepthMapFactor
+ *        (the convertTo of Tracking::GrabImageRGBD, src/Tracking.cc:227-228, is fused into the lookup)
+ *   keys_un / u_right / depth_out   optional host copies (mvKeysUn, mvuRight, mvDepth), n_frames x cap entries
+ *   bounds4   mnMinX, mnMinY, mnMaxX, mnMaxY (Frame::ComputeImageBounds, :436-464)
+ *   frames    n_frames resident frames; use them through borb_frame_view::resident, release with borb_frame_destroy. */
+BORB_API borb_status borb_frames_from_extractor(borb_matcher* m, borb_extractor* e, const int32_t* images, int n_frames,
+                                                const int32_t* n_keys, const borb_camera* cam, int mode, const void* const* depth,
+                                                int depth_type, float depth_factor, int depth_stride_bytes, borb_keypoint* keys_un,
+                                                float* u_right, float* depth_out, int cap, float* bounds4, borb_frame** frames);
 BORB_API borb_status borb_frame_info(const borb_frame* f, int32_t* n, int32_t* n_levels, int32_t* has_u_right);
 
 /* Local map points that passed Frame::isInFrustum (src/Frame.cc:269-325), in vpMapPoints order. */

@@ -87,7 +87,7 @@ public:
             for (int j = 0; j < c; j++) { if (t == CV_32F) m.at<float>(i, j) = 1.f; else m.at<uchar>(i, j) = 1; }
         return m;
     }
-    Mat reshape(int) const { return *this; }        // only on paths the oracle never runs (UndistortKeyPoints)
+    Mat reshape(int) const { return *this; }        // N x 2 CV_32F <-> N x 1 CV_32FC2: the same memory; undistortPoints below reads N x 2
     double dot(const Mat& o) const {                // float inputs, products and sum in double, index order
         double s = 0;
         for (int r = 0; r < rows; r++)
@@ -168,7 +168,45 @@ public:
     template <typename T> FileStorage& operator<<(const T&) { return *this; }
 };
 
-inline void undistortPoints(const Mat&, Mat&, const Mat&, const Mat&, const Mat&, const Mat&) {}   // never run by the oracle
+// cv::undistortPoints(src, dst, cameraMatrix, distCoeffs, R = empty, P) as OpenCV 4.x evaluates it for CV_32FC2 points
+// (calib3d/undistort.dispatch.cpp, cvUndistortPointsInternal with the default TermCriteria(MAX_ITER, 5, 0.01)): camera
+// matrix and coefficients widened to double, x = (u - cx) * (1/fx), FIVE fixed-point iterations of the Brown model
+// (k1 k2 p1 p2 k3 [k4 k5 k6]; thin-prism and tilt terms are zero here, the tilt step multiplies by the identity),
+// re-projection with P, result narrowed to float.  Restated from the published algorithm; pinned against cv2 4.13 in
+// tests/test_oracle_frame_ref.py.  src: N x 2 CV_32F (the reference's reshape(2) is a no-op in this Mat); dst may be src.
+inline void undistortPoints(const Mat& src, Mat& dst, const Mat& Kc, const Mat& D, const Mat& /*R*/, const Mat& P) {
+    double k[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int nd = D.empty() ? 0 : D.rows * D.cols;
+    for (int i = 0; i < nd && i < 12; i++) k[i] = (double)D.at<float>(i);
+    const double fx = Kc.at<float>(0, 0), fy = Kc.at<float>(1, 1), cx = Kc.at<float>(0, 2), cy = Kc.at<float>(1, 2);
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double RR[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (!P.empty())
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) RR[r][c] = (double)P.at<float>(r, c);
+    Mat out = (dst.data == src.data) ? dst : Mat(src.rows, src.cols, CV_32F);
+    for (int i = 0; i < src.rows; i++) {
+        double x = src.at<float>(i, 0), y = src.at<float>(i, 1);
+        const double u = x, v = y;
+        x = (x - cx) * ifx; y = (y - cy) * ify;
+        if (nd > 0) {
+            const double x0 = x, y0 = y;
+            for (int j = 0; j < 5; j++) {
+                const double r2 = x * x + y * y;
+                const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+                if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+                const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+                const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+                x = (x0 - deltaX) * icdist; y = (y0 - deltaY) * icdist;
+            }
+        }
+        const double xx = RR[0][0] * x + RR[0][1] * y + RR[0][2];
+        const double yy = RR[1][0] * x + RR[1][1] * y + RR[1][2];
+        const double ww = 1. / (RR[2][0] * x + RR[2][1] * y + RR[2][2]);
+        out.at<float>(i, 0) = (float)(xx * ww); out.at<float>(i, 1) = (float)(yy * ww);
+    }
+    dst = out;
+}
 
 // cv::Mat_<float>(3,1) << x, y, z   (Frame::UnprojectStereo)
 template <typename T> class Mat_ : public Mat {

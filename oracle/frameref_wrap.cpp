@@ -117,4 +117,30 @@ int frameref_is_in_frustum(const float* world_pos, const float* normal, const fl
     return count;
 }
 
+// The RGB-D constructor's data-parallel steps (src/Frame.cc:143-145, :160-176): UndistortKeyPoints (:404-434),
+// ComputeStereoFromRGBD (:643-664) and ComputeImageBounds (:436-464), run unmodified.  K4 = fx fy cx cy; dist: n_dist
+// coefficients k1 k2 p1 p2 [k3] exactly as Tracking builds mDistCoef (src/Tracking.cc:69-79); depth: h x w floats.
+int frameref_rgbd(const orbport_kp* keys, int n, const float* K4, const float* dist, int n_dist, float bf, const float* depth, int w, int h,
+                  orbport_kp* keys_un, float* u_right, float* depth_out, float* bounds4) {
+    Frame F;
+    F.mK = cv::Mat(3, 3, CV_32F);
+    F.mK.at<float>(0, 0) = K4[0]; F.mK.at<float>(1, 1) = K4[1]; F.mK.at<float>(0, 2) = K4[2]; F.mK.at<float>(1, 2) = K4[3]; F.mK.at<float>(2, 2) = 1.f;
+    F.mDistCoef = cv::Mat(n_dist, 1, CV_32F);
+    for (int i = 0; i < n_dist; i++) F.mDistCoef.at<float>(i) = dist[i];
+    F.mbf = bf;
+    F.N = n;
+    F.mvKeys = make_keys(keys, n);
+    cv::Mat im(h, w, CV_8U), imDepth(h, w, CV_32F);
+    std::memcpy(imDepth.data, depth, (size_t)w * h * 4);
+    F.ComputeImageBounds(im);
+    bounds4[0] = Frame::mnMinX; bounds4[1] = Frame::mnMinY; bounds4[2] = Frame::mnMaxX; bounds4[3] = Frame::mnMaxY;
+    if (n == 0) return 0;
+    F.UndistortKeyPoints();
+    F.ComputeStereoFromRGBD(imDepth);
+    int cnt = 0;
+    std::memcpy(keys_un, F.mvKeysUn.data(), (size_t)n * sizeof(orbport_kp));
+    for (int i = 0; i < n; i++) { u_right[i] = F.mvuRight[i]; depth_out[i] = F.mvDepth[i]; cnt += F.mvDepth[i] > 0; }
+    return cnt;
+}
+
 }  // extern "C"

@@ -986,3 +986,50 @@ def ref_distinctive_descriptor(desc, bad=None):
     lib.mapref_distinctive_descriptor.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     ok = lib.mapref_distinctive_descriptor(_ptr(d) if len(d) else None, _ptr(b) if b is not None else None, len(d), _ptr(out))
     return out if ok else None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# RGB-D leg of the Frame constructor (src/Frame.cc:119-178): UndistortKeyPoints, ComputeStereoFromRGBD, ComputeImageBounds.
+def _rgbd_call(fn, keys, K4, dist, bf, depth):
+    keys = _a(keys, KP_DTYPE)
+    n = len(keys)
+    K4 = _a(K4, np.float32); dist = _a(dist, np.float32); depth = _a(depth, np.float32)
+    h, w = depth.shape
+    ku = np.zeros(max(n, 1), KP_DTYPE); ur = np.zeros(max(n, 1), np.float32); dp = np.zeros(max(n, 1), np.float32); b4 = np.zeros(4, np.float32)
+    return keys, n, K4, dist, depth, w, h, ku, ur, dp, b4
+
+
+def ref_rgbd_frame(keys, K4, dist, bf, depth):
+    """The reference's own UndistortKeyPoints + ComputeStereoFromRGBD + ComputeImageBounds (libframeref.so)."""
+    lib = C.CDLL(FRAMEREF_SO)
+    keys, n, K4, dist, depth, w, h, ku, ur, dp, b4 = _rgbd_call(None, keys, K4, dist, bf, depth)
+    lib.frameref_rgbd.restype = C.c_int
+    lib.frameref_rgbd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+    cnt = lib.frameref_rgbd(_ptr(keys), n, _ptr(K4), _ptr(dist), len(dist), float(bf), _ptr(depth), w, h, _ptr(ku), _ptr(ur), _ptr(dp), _ptr(b4))
+    return dict(keys_un=ku[:n], u_right=ur[:n], depth=dp[:n], bounds=b4, count=cnt)
+
+
+def port_rgbd_frame(keys, K4, dist, bf, depth):
+    """Restatement (oracle/orb_port_frame.cpp); same outputs as ref_rgbd_frame."""
+    lib = _plib()
+    keys, n, K4, dist, depth, w, h, ku, ur, dp, b4 = _rgbd_call(None, keys, K4, dist, bf, depth)
+    lib.orbport_undistort_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.orbport_undistort_keypoints.restype = None
+    lib.orbport_image_bounds.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.orbport_image_bounds.restype = None
+    lib.orbport_stereo_from_rgbd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    lib.orbport_stereo_from_rgbd.restype = C.c_int
+    lib.orbport_undistort_keypoints(_ptr(keys), n, _ptr(K4), _ptr(dist), len(dist), _ptr(ku))
+    lib.orbport_image_bounds(w, h, _ptr(K4), _ptr(dist), len(dist), _ptr(b4))
+    cnt = lib.orbport_stereo_from_rgbd(_ptr(keys), _ptr(ku), n, _ptr(depth), w, h, float(bf), _ptr(ur), _ptr(dp))
+    return dict(keys_un=ku[:n], u_right=ur[:n], depth=dp[:n], bounds=b4, count=cnt)
+
+
+def port_depth_to_float(raw, factor):
+    lib = _plib()
+    raw = _a(raw, np.uint16)
+    out = np.zeros(raw.shape, np.float32)
+    lib.orbport_depth_to_float.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+    lib.orbport_depth_to_float.restype = None
+    lib.orbport_depth_to_float(_ptr(raw), raw.size, float(np.float32(factor)), _ptr(out))
+    return out

@@ -150,6 +150,22 @@ struct BowDbFinal {               // bowdb_finalize_kernel
     int dense_stride;
 };
 
+struct FrameJob {                 // one frame of borb_frames_from_extractor (k_frame.cu)
+    const borb_keypoint* src_keys;   // the extractor's mvKeys of that image
+    const uint8_t* src_desc;
+    const float* src_ur;             // stereo: the extractor's mvuRight / mvDepth of the pair
+    const float* src_depth;
+    const void* depth_img;           // RGB-D: depth map in HBM (w x h, tight rows)
+    borb_keypoint* keys;             // destination borb_frame fields
+    uint8_t* desc;
+    float* u_right;
+    float* depth;
+    int* cell_start;
+    int* cell_idx;
+    int n;
+    float min_x, min_y, inv_w, inv_h;
+};
+
 struct TriArgs { float F[9]; float ex, ey; int only_stereo, check_ori; };
 
 struct VocDev {                   // views into the packed blob
@@ -178,6 +194,9 @@ int launch_projection_argmin(const LastArgs& L, const ProjArgs& A, int32_t* best
 int launch_sim3_agree(const int32_t* match1, const int32_t* match2, int n1, int n2, int32_t* match12, int* n_found, cudaStream_t s);
 int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, float nnratio, int check_ori, int32_t* match,
                      int out_stride, uint8_t* bins, int32_t* n_matches, int max_t, cudaStream_t s);
+void host_image_bounds(int w, int h, const borb_camera& c, float* b4);
+int launch_frame_build(const FrameJob* d_jobs, int n_jobs, int max_n, const borb_camera& cam, int mode, int depth_type, float depth_factor, int w,
+                       int h, int out_cap, borb_keypoint* keys_out, float* ur_out, float* depth_out, cudaStream_t s);
 int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, bool csa, int n_sm, cudaStream_t s);
 size_t bowdb_smem_bytes(int frame_bytes, bool frame_in_smem);
 int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,

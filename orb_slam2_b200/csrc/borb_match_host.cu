@@ -23,6 +23,7 @@ struct borb_matcher {
     uint8_t* h_out = nullptr;       // pinned landing buffer for results (one D2H per call)
     size_t h_out_bytes = 0;
     std::vector<int32_t> sel;       // indices of the valid queries of the current call
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // cross-stream ordering with an extractor handle (borb_frames_from_extractor)
 };
 
 struct borb_voc {
@@ -255,6 +256,7 @@ borb_status borb_matcher_destroy(borb_matcher* m) {
     cudaFree(m->aux);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->h_out) cudaFreeHost(m->h_out);
+    if (m->ev_a) { cudaEventDestroy(m->ev_a); cudaEventDestroy(m->ev_b); }
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return BORB_OK;
@@ -341,6 +343,105 @@ borb_status borb_frame_destroy(borb_frame* f) {
     cudaFree(f->block);
     cudaEventDestroy(f->ready);
     delete f;
+    return BORB_OK;
+}
+
+borb_status borb_frames_from_extractor(borb_matcher* m, borb_extractor* e, const int32_t* images, int n_frames, const int32_t* n_keys,
+                                       const borb_camera* cam, int mode, const void* const* depth, int depth_type, float depth_factor,
+                                       int depth_stride_bytes, borb_keypoint* keys_un, float* u_right, float* depth_out, int cap,
+                                       float* bounds4, borb_frame** frames) {
+    if (!m || !e || !cam || !frames || n_frames < 0 || (n_frames > 0 && (!images || !n_keys))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (mode < 0 || mode > 2 || (mode == 2 && !depth) || (depth_type != 0 && depth_type != 1)) { set_error("bad mode / depth arguments"); return BORB_ERR_INVALID_ARG; }
+    if (!e->have_geom || e->last_n_images < 1) { set_error("no extracted batch on this extractor handle"); return BORB_ERR_STATE; }
+    if (e->device != m->device) { set_error("extractor and matcher live on different devices"); return BORB_ERR_INVALID_ARG; }
+    if ((keys_un || u_right || depth_out) && cap < 0) { set_error("negative capacity"); return BORB_ERR_INVALID_ARG; }
+    const Geometry& g = e->geom;
+    const int w = g.w, h = g.h, nl = g.nlevels;
+    float b4[4];
+    host_image_bounds(w, h, *cam, b4);
+    if (bounds4) std::memcpy(bounds4, b4, sizeof(b4));
+    for (int i = 0; i < n_frames; i++) frames[i] = nullptr;
+    if (n_frames == 0) return BORB_OK;
+    int max_n = 0;
+    for (int i = 0; i < n_frames; i++) {
+        if (images[i] < 0 || images[i] >= e->last_n_images) { set_error("image %d is not part of the extractor's last batch", images[i]); return BORB_ERR_INVALID_ARG; }
+        if (n_keys[i] < 0 || n_keys[i] > g.sel_image_stride || n_keys[i] > MATCH_MAX_FEATURES) { set_error("frame %d: %d keypoints outside [0, %d]", i, n_keys[i], MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+        if (mode == 1 && (images[i] & 1)) { set_error("stereo mode takes LEFT images (even indices) of borb_stereo_frames"); return BORB_ERR_INVALID_ARG; }
+        if (mode == 2 && !depth[i]) { set_error("frame %d: null depth map", i); return BORB_ERR_INVALID_ARG; }
+        max_n = n_keys[i] > max_n ? n_keys[i] : max_n;
+    }
+    BORB_CUDA(cudaSetDevice(m->device));
+    borb_status s = BORB_OK;
+    for (int i = 0; i < n_frames && s == BORB_OK; i++) {
+        s = frame_alloc(m->device, n_keys[i], nl, mode != 0, &frames[i]);
+        if (s == BORB_OK) { frames[i]->min_x = b4[0]; frames[i]->min_y = b4[1]; frames[i]->max_x = b4[2]; frames[i]->max_y = b4[3]; }
+    }
+    auto fail = [&](borb_status st) { for (int i = 0; i < n_frames; i++) { borb_frame_destroy(frames[i]); frames[i] = nullptr; } return st; };
+    if (s != BORB_OK) return fail(s);
+    const size_t px = depth_type == 1 ? 2 : 4;
+    const size_t depth_img_bytes = mode == 2 ? (size_t)w * h * px : 0;
+    if (mode == 2 && depth_stride_bytes < (int)(w * px)) { set_error("depth stride %d smaller than a row", depth_stride_bytes); return fail(BORB_ERR_INVALID_ARG); }
+    const int ocap = (keys_un || u_right || depth_out) ? cap : 0;
+    Stager st(m);
+    const size_t o_jobs = st.reserve((size_t)n_frames * sizeof(FrameJob));
+    const size_t o_sf = st.add(e->scale.data(), (size_t)nl * 4);
+    const size_t input_end = st.off;
+    const size_t o_depth = st.reserve(depth_img_bytes * n_frames + 16);
+    const size_t o_ko = st.reserve((size_t)n_frames * ocap * sizeof(borb_keypoint) + 16);
+    const size_t o_uo = st.reserve((size_t)n_frames * ocap * 4 + 16), o_do = st.reserve((size_t)n_frames * ocap * 4 + 16);
+    const size_t total = st.off;
+    st.off = input_end;
+    if ((s = ensure_host(m, input_end)) != BORB_OK) return fail(s);
+    if ((s = ensure_arena(m, total)) != BORB_OK) return fail(s);
+    if ((s = ensure_out(m, (size_t)n_frames * ocap * (sizeof(borb_keypoint) + 8))) != BORB_OK) return fail(s);
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    uint8_t* b = m->arena;
+    FrameJob* hj = reinterpret_cast<FrameJob*>(m->h_stage + o_jobs);
+    const float invW = (float)GRID_COLS / (float)(b4[2] - b4[0]), invH = (float)GRID_ROWS / (float)(b4[3] - b4[1]);
+    for (int i = 0; i < n_frames; i++) {
+        FrameJob& J = hj[i];
+        borb_frame* f = frames[i];
+        const int img = images[i];
+        J.src_keys = e->ws.kps + (size_t)img * g.sel_image_stride;
+        J.src_desc = e->ws.desc + (size_t)img * g.sel_image_stride * 32;
+        J.src_ur = mode == 1 ? e->ws.u_right + (size_t)(img / 2) * g.sel_image_stride : nullptr;
+        J.src_depth = mode == 1 ? e->ws.depth + (size_t)(img / 2) * g.sel_image_stride : nullptr;
+        J.depth_img = mode == 2 ? b + o_depth + (size_t)i * depth_img_bytes : nullptr;
+        J.keys = f->keys; J.desc = f->desc; J.u_right = f->ur_store; J.depth = f->depth_store;
+        J.cell_start = f->cell_start; J.cell_idx = f->cell_idx;
+        J.n = n_keys[i]; J.min_x = b4[0]; J.min_y = b4[1]; J.inv_w = invW; J.inv_h = invH;
+    }
+    if ((s = commit(st, total)) != BORB_OK) return fail(s);
+    cudaStream_t q = m->stream;
+    // the extractor's results must be complete, and its next batch must not overwrite them while they are being read
+    if (!m->ev_a) { BORB_CUDA(cudaEventCreateWithFlags(&m->ev_a, cudaEventDisableTiming)); BORB_CUDA(cudaEventCreateWithFlags(&m->ev_b, cudaEventDisableTiming)); }
+    BORB_CUDA(cudaEventRecord(m->ev_a, e->stream));
+    BORB_CUDA(cudaStreamWaitEvent(q, m->ev_a, 0));
+    if (mode == 2)
+        for (int i = 0; i < n_frames; i++)
+            BORB_CUDA(cudaMemcpy2DAsync(b + o_depth + (size_t)i * depth_img_bytes, (size_t)w * px, depth[i], (size_t)depth_stride_bytes, (size_t)w * px, h,
+                                        cudaMemcpyHostToDevice, q));
+    for (int i = 0; i < n_frames; i++) BORB_CUDA(cudaMemcpyAsync(frames[i]->sf, b + o_sf, (size_t)nl * 4, cudaMemcpyDeviceToDevice, q));
+    m->launches += launch_frame_build((const FrameJob*)(b + o_jobs), n_frames, max_n, *cam, mode, depth_type, depth_factor, w, h, ocap,
+                                      keys_un ? (borb_keypoint*)(b + o_ko) : nullptr, (u_right || depth_out) ? (float*)(b + o_uo) : nullptr,
+                                      (float*)(b + o_do), q);
+    BORB_CUDA(cudaGetLastError());
+    for (int i = 0; i < n_frames; i++) BORB_CUDA(cudaEventRecord(frames[i]->ready, q));
+    BORB_CUDA(cudaEventRecord(m->ev_b, q));
+    BORB_CUDA(cudaStreamWaitEvent(e->stream, m->ev_b, 0));
+    uint8_t* ho = m->h_out;
+    const size_t kb = (size_t)n_frames * ocap * sizeof(borb_keypoint), fb = (size_t)n_frames * ocap * 4;
+    if (ocap > 0) {
+        if (keys_un) BORB_CUDA(cudaMemcpyAsync(ho, b + o_ko, kb, cudaMemcpyDeviceToHost, q));
+        if (u_right) BORB_CUDA(cudaMemcpyAsync(ho + kb, b + o_uo, fb, cudaMemcpyDeviceToHost, q));
+        if (depth_out) BORB_CUDA(cudaMemcpyAsync(ho + kb + fb, b + o_do, fb, cudaMemcpyDeviceToHost, q));
+    }
+    BORB_CUDA(cudaStreamSynchronize(q));
+    if (ocap > 0) {
+        if (keys_un) std::memcpy(keys_un, ho, kb);
+        if (u_right) std::memcpy(u_right, ho + kb, fb);
+        if (depth_out) std::memcpy(depth_out, ho + kb + fb, fb);
+    }
     return BORB_OK;
 }
 

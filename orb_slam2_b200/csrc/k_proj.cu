@@ -193,23 +193,23 @@ __global__ void __launch_bounds__(256) proj_resolve_kernel(ProjArgs A, const bor
     uint32_t* ent = tag + A.n;                              // first RES_K entries of every list
     int* cnts = reinterpret_cast<int*>(ent + (size_t)A.n_mp * RES_K);
     uint8_t* obs = reinterpret_cast<uint8_t*>(cnts + A.n_mp);
-    for (int w = tid; w < words; w += T) {
-        uint32_t bits = 0;
-        if (A.occupied != nullptr)
-            for (int b = 0; b < 32; b++) {
-                const int i = w * 32 + b;
-                if (i < A.n && A.occupied[i]) bits |= 1u << b;
-            }
-        held[w] = bits;
+    for (int i0 = 0; i0 < words * 32; i0 += T) {            // T is a multiple of 32: a warp builds one word per pass with a ballot
+        const int i = i0 + tid;
+        const bool occ = A.occupied != nullptr && i < A.n && A.occupied[i] != 0;
+        const unsigned bits = __ballot_sync(0xFFFFFFFFu, occ);
+        if (lane == 0 && (i >> 5) < words) held[i >> 5] = bits;
     }
     for (int i = tid; i < A.n; i += T) tag[i] = 0xFFFFFFFFu;
-    for (int i = tid; i < A.n_mp; i += T) {
-        cnts[i] = A.cand_cnt[i];
-        obs[i] = (A.mp_has_obs == nullptr || A.mp_has_obs[i]) ? 1 : 0;
-    }
-    for (int e = tid; e < A.n_mp * RES_K; e += T) {
-        const int iq = e / RES_K, k = e - iq * RES_K;
-        ent[e] = k < (A.cand_cnt[iq] & CAND_COUNT_MASK) ? A.cand[(size_t)iq * A.n + k] : 0u;
+    for (int iq = tid; iq < A.n_mp; iq += T) {
+        // the first RES_K entries are read unconditionally (the row has A.n >= 1 slots) so that the loads do not wait for the count
+        uint32_t e[RES_K];
+#pragma unroll
+        for (int k = 0; k < RES_K; k++) e[k] = k < A.n ? A.cand[(size_t)iq * A.n + k] : 0u;
+        const int c = A.cand_cnt[iq];
+        cnts[iq] = c;
+        obs[iq] = (A.mp_has_obs == nullptr || A.mp_has_obs[iq]) ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < RES_K; k++) ent[iq * RES_K + k] = k < (c & CAND_COUNT_MASK) ? e[k] : 0u;
     }
     if (LAST) for (int i = tid; i < A.n; i += T) out[i] = -1;
     if (tid < 32) hist[tid] = 0;

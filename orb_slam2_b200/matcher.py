@@ -130,6 +130,48 @@ class ResidentFrame:
             pass
 
 
+class _CameraC(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3", "bf")]
+
+
+def frames_from_extractor(matcher: "ORBmatcher", extractor, images, n_keys, K, dist=(0, 0, 0, 0, 0), bf: float = 0.0, mode: int = 0,
+                          depth=None, depth_factor: float = 1.0, want_host: bool = True):
+    """borb_frames_from_extractor: the Frame constructor tail (UndistortKeyPoints, ComputeStereoFromRGBD, AssignFeaturesToGrid,
+    src/Frame.cc:404-434,643-664,230-245) on the device for images of the extractor's last batch.  K = (fx, fy, cx, cy),
+    dist = (k1, k2, p1, p2, k3); mode 0 mono / 1 stereo / 2 RGB-D with depth = list of (h,w) float32 (metres) or uint16 (raw) maps.
+    Returns (frames, host) where frames[i] is a FrameView bound to the resident frame and host = dict(keys_un, u_right, depth, bounds)."""
+    lib = _lib.load()
+    images = np.ascontiguousarray(images, np.int32); nk = np.ascontiguousarray(n_keys, np.int32)
+    nf = len(images)
+    d5 = list(dist) + [0.0] * (5 - len(dist))
+    cam = _CameraC(*[float(x) for x in K], *[float(x) for x in d5], float(bf))
+    cap = int(nk.max()) if nf else 0
+    ku = np.zeros((nf, max(cap, 1)), KP_DTYPE); ur = np.full((nf, max(cap, 1)), -1, np.float32); dp = np.full((nf, max(cap, 1)), -1, np.float32)
+    b4 = np.zeros(4, np.float32)
+    handles = (C.c_void_p * max(nf, 1))()
+    dptr, dtype_flag, stride, keep = None, 0, 0, []
+    if mode == 2:
+        keep = [np.ascontiguousarray(d) for d in depth]
+        dtype_flag = 1 if keep[0].dtype == np.uint16 else 0
+        keep = [np.ascontiguousarray(d, np.uint16 if dtype_flag else np.float32) for d in keep]
+        stride = keep[0].strides[0]
+        dptr = (C.c_void_p * nf)(*[d.ctypes.data for d in keep])
+    check(lib.borb_frames_from_extractor(matcher._h, extractor._h, _p(images), nf, _p(nk), C.byref(cam), int(mode), dptr, dtype_flag,
+                                         float(np.float32(depth_factor)), int(stride), _p(ku) if want_host else None,
+                                         _p(ur) if want_host else None, _p(dp) if want_host else None, cap, _p(b4), handles),
+          "borb_frames_from_extractor")
+    sf = extractor.GetScaleFactors()
+    out = []
+    for i in range(nf):
+        rf = ResidentFrame.__new__(ResidentFrame)
+        rf._lib, rf._h, rf.n = lib, C.c_void_p(handles[i]), int(nk[i])
+        n = int(nk[i])
+        out.append(FrameView(mvKeysUn=ku[i, :n], mDescriptors=np.zeros((n, 32), np.uint8), mvScaleFactors=sf, bounds=tuple(float(x) for x in b4),
+                             mvuRight=ur[i, :n] if mode else None, resident=rf))
+    return out, dict(keys_un=[ku[i, :nk[i]] for i in range(nf)], u_right=[ur[i, :nk[i]] for i in range(nf)],
+                     depth=[dp[i, :nk[i]] for i in range(nf)], bounds=b4)
+
+
 def dataclass_replace_resident(F):
     import dataclasses
     return dataclasses.replace(F, resident=None)
