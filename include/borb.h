@@ -221,6 +221,7 @@ typedef struct borb_camera {
  *   mode 0 monocular; 1 stereo: mvuRight / mvDepth are the association borb_stereo_frames computed for pair images[i]/2
  *        (images[i] must be the LEFT image, an even index); 2 RGB-D: depth[i] = host depth map of that frame, registered to
  *        the image (same width x height), depth_type 0 = CV_32F metres, 1 = CV_16U raw with depth_factor = mDepthMapFactor
+ *        (+4: depth[i] are DEVICE pointers to tightly packed maps, no copy)
  *        (the convertTo of Tracking::GrabImageRGBD, src/Tracking.cc:227-228, is fused into the lookup)
  *   keys_un / u_right / depth_out   optional host copies (mvKeysUn, mvuRight, mvDepth), n_frames x cap entries
  *   bounds4   mnMinX, mnMinY, mnMaxX, mnMaxY (Frame::ComputeImageBounds, :436-464)
@@ -457,7 +458,18 @@ BORB_API borb_status borb_voc_from_blob(void* d_blob, size_t bytes, int device, 
 BORB_API borb_status borb_bow_transform(borb_voc* v, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight,
                                         int32_t* node);
 
+/* Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:395-402, src/KeyFrame.cc:59-68): mBowVec and mFeatVec of n descriptors in
+ * one call — tree descent on the GPU, the ordered-map bookkeeping of TemplatedVocabulary::transform (:1150-1194) on the host.
+ * bow_word / bow_value: BowVector in word order (capacity n), *n_bow entries; fv_node / fv_start / fv_idx: FeatureVector as CSR
+ * (capacities n, n + 1, n), *n_nodes nodes — the layout borb_featvec_view and borb_kfdb_add take. */
+BORB_API borb_status borb_compute_bow(borb_voc* v, const uint8_t* desc, int n, int levelsup, uint32_t* bow_word, double* bow_value,
+                                      int32_t* n_bow, uint32_t* fv_node, int32_t* fv_start, uint32_t* fv_idx, int32_t* n_nodes);
+
 /* ---------------------------------------------------------------- introspection -------------- */
+/* Device time (CUDA events on the matcher's stream) of the kernels of the last borb_search_by_bow_db* call on this handle. */
+BORB_API borb_status borb_matcher_set_timing(borb_matcher* m, int enable);
+BORB_API borb_status borb_matcher_last_kernel_ms(borb_matcher* m, float* ms);
+BORB_API borb_status borb_matcher_launch_count(const borb_matcher* m, uint64_t* n);
 /* Per-stage intermediates of the last batch, for parity tests (tests/ compare each stage with the
  * oracle).  xys: (x, y, score) int32 triples in level pixel coordinates. */
 BORB_API borb_status borb_debug_candidates(borb_extractor* e, int image, int level, int32_t* xys, int cap, int* n_out);

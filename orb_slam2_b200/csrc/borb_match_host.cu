@@ -1,6 +1,8 @@
 // Host side of the matcher / vocabulary entry points of the C ABI (include/borb.h): snapshots arrive as plain host
 // arrays, are staged into one device arena per call, and every result is produced by the CUDA kernels in k_match.cu.
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +26,9 @@ struct borb_matcher {
     size_t h_out_bytes = 0;
     std::vector<int32_t> sel;       // indices of the valid queries of the current call
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // cross-stream ordering with an extractor handle (borb_frames_from_extractor)
+    bool timing = false;            // borb_matcher_set_timing: CUDA events around the kernels of the database search
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    float last_ms = 0.f;
 };
 
 struct borb_voc {
@@ -257,6 +262,7 @@ borb_status borb_matcher_destroy(borb_matcher* m) {
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->h_out) cudaFreeHost(m->h_out);
     if (m->ev_a) { cudaEventDestroy(m->ev_a); cudaEventDestroy(m->ev_b); }
+    if (m->t0) { cudaEventDestroy(m->t0); cudaEventDestroy(m->t1); }
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return BORB_OK;
@@ -351,6 +357,8 @@ borb_status borb_frames_from_extractor(borb_matcher* m, borb_extractor* e, const
                                        int depth_stride_bytes, borb_keypoint* keys_un, float* u_right, float* depth_out, int cap,
                                        float* bounds4, borb_frame** frames) {
     if (!m || !e || !cam || !frames || n_frames < 0 || (n_frames > 0 && (!images || !n_keys))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    const bool depth_on_device = (depth_type & 4) != 0;
+    depth_type &= 3;
     if (mode < 0 || mode > 2 || (mode == 2 && !depth) || (depth_type != 0 && depth_type != 1)) { set_error("bad mode / depth arguments"); return BORB_ERR_INVALID_ARG; }
     if (!e->have_geom || e->last_n_images < 1) { set_error("no extracted batch on this extractor handle"); return BORB_ERR_STATE; }
     if (e->device != m->device) { set_error("extractor and matcher live on different devices"); return BORB_ERR_INVALID_ARG; }
@@ -379,7 +387,7 @@ borb_status borb_frames_from_extractor(borb_matcher* m, borb_extractor* e, const
     auto fail = [&](borb_status st) { for (int i = 0; i < n_frames; i++) { borb_frame_destroy(frames[i]); frames[i] = nullptr; } return st; };
     if (s != BORB_OK) return fail(s);
     const size_t px = depth_type == 1 ? 2 : 4;
-    const size_t depth_img_bytes = mode == 2 ? (size_t)w * h * px : 0;
+    const size_t depth_img_bytes = (mode == 2 && !depth_on_device) ? (size_t)w * h * px : 0;
     if (mode == 2 && depth_stride_bytes < (int)(w * px)) { set_error("depth stride %d smaller than a row", depth_stride_bytes); return fail(BORB_ERR_INVALID_ARG); }
     const int ocap = (keys_un || u_right || depth_out) ? cap : 0;
     Stager st(m);
@@ -406,7 +414,7 @@ borb_status borb_frames_from_extractor(borb_matcher* m, borb_extractor* e, const
         J.src_desc = e->ws.desc + (size_t)img * g.sel_image_stride * 32;
         J.src_ur = mode == 1 ? e->ws.u_right + (size_t)(img / 2) * g.sel_image_stride : nullptr;
         J.src_depth = mode == 1 ? e->ws.depth + (size_t)(img / 2) * g.sel_image_stride : nullptr;
-        J.depth_img = mode == 2 ? b + o_depth + (size_t)i * depth_img_bytes : nullptr;
+        J.depth_img = mode == 2 ? (depth_on_device ? depth[i] : (const void*)(b + o_depth + (size_t)i * depth_img_bytes)) : nullptr;
         J.keys = f->keys; J.desc = f->desc; J.u_right = f->ur_store; J.depth = f->depth_store;
         J.cell_start = f->cell_start; J.cell_idx = f->cell_idx;
         J.n = n_keys[i]; J.min_x = b4[0]; J.min_y = b4[1]; J.inv_w = invW; J.inv_h = invH;
@@ -417,7 +425,7 @@ borb_status borb_frames_from_extractor(borb_matcher* m, borb_extractor* e, const
     if (!m->ev_a) { BORB_CUDA(cudaEventCreateWithFlags(&m->ev_a, cudaEventDisableTiming)); BORB_CUDA(cudaEventCreateWithFlags(&m->ev_b, cudaEventDisableTiming)); }
     BORB_CUDA(cudaEventRecord(m->ev_a, e->stream));
     BORB_CUDA(cudaStreamWaitEvent(q, m->ev_a, 0));
-    if (mode == 2)
+    if (mode == 2 && !depth_on_device)
         for (int i = 0; i < n_frames; i++)
             BORB_CUDA(cudaMemcpy2DAsync(b + o_depth + (size_t)i * depth_img_bytes, (size_t)w * px, depth[i], (size_t)depth_stride_bytes, (size_t)w * px, h,
                                         cudaMemcpyHostToDevice, q));
@@ -1292,7 +1300,9 @@ borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, i
         F.n_matches = (int32_t*)(b + o_nm); F.pair_off = (int32_t*)(b + o_po);
         F.pairs = pairs ? (uint32_t*)(b + o_pairs) : nullptr; F.pairs_cap = pairs_cap; F.cursor = (int*)(b + o_ctr + 64);
         F.dense = dense ? (int32_t*)(b + o_dense) : nullptr; F.dense_stride = dense_stride;
+        if (m->timing) BORB_CUDA(cudaEventRecord(m->t0, m->stream));
         m->launches += launch_bowdb(A, F, g_bow_csa.load() != 0, db->n_sm, m->stream);
+        if (m->timing) BORB_CUDA(cudaEventRecord(m->t1, m->stream));
         BORB_CUDA(cudaGetLastError());
     }
     BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, (size_t)n_kf * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -1301,6 +1311,7 @@ borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, i
     if (pairs) BORB_CUDA(cudaMemcpyAsync(&total_pairs, b + o_ctr + 64, 4, cudaMemcpyDeviceToHost, m->stream));
     if (dense) BORB_CUDA(cudaMemcpyAsync(dense, b + o_dense, (size_t)n_kf * dense_stride * 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->timing) { float ms = 0.f; if (cudaEventElapsedTime(&ms, m->t0, m->t1) == cudaSuccess) m->last_ms = ms; else cudaGetLastError(); }
     if (pairs) {
         if (n_pairs_total) *n_pairs_total = total_pairs;
         const int ncopy = total_pairs < pairs_cap ? total_pairs : pairs_cap;
@@ -1492,6 +1503,67 @@ borb_status borb_bow_transform(borb_voc* v, const uint8_t* desc, int n, int leve
     BORB_CUDA(cudaMemcpyAsync(weight, d_w, (size_t)n * 8, cudaMemcpyDeviceToHost, v->stream));
     BORB_CUDA(cudaMemcpyAsync(node, d_node, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
     BORB_CUDA(cudaStreamSynchronize(v->stream));
+    return BORB_OK;
+}
+
+// Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:395-402, src/KeyFrame.cc:59-68): the tree descent on the GPU
+// (borb_bow_transform), then the ordered-map bookkeeping of TemplatedVocabulary::transform (TemplatedVocabulary.h:1150-1194) in
+// C++: BowVector::addWeight in feature order for every feature whose word weight is > 0, L1 normalisation with the norm summed
+// in word order (BowVector.cpp:60-79), FeatureVector::addFeature in feature order.
+borb_status borb_compute_bow(borb_voc* v, const uint8_t* desc, int n, int levelsup, uint32_t* bow_word, double* bow_value, int32_t* n_bow,
+                             uint32_t* fv_node, int32_t* fv_start, uint32_t* fv_idx, int32_t* n_nodes) {
+    if (!v || n < 0 || !n_bow || !n_nodes || (n > 0 && (!desc || !bow_word || !bow_value || !fv_node || !fv_start || !fv_idx))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    *n_bow = 0; *n_nodes = 0;
+    if (fv_start) fv_start[0] = 0;
+    if (n == 0) return BORB_OK;
+    std::vector<int32_t> word(n), node(n);
+    std::vector<double> weight(n);
+    borb_status s = borb_bow_transform(v, desc, n, levelsup, word.data(), weight.data(), node.data());
+    if (s != BORB_OK) return s;
+    // stable sort of the kept features by word / by node: equal keys stay in feature order, as std::map insertion does
+    std::vector<int32_t> keep;
+    keep.reserve(n);
+    for (int i = 0; i < n; i++) if (weight[i] > 0) keep.push_back(i);
+    std::vector<int32_t> byw(keep), byn(keep);
+    std::stable_sort(byw.begin(), byw.end(), [&](int a, int b) { return word[a] < word[b]; });
+    std::stable_sort(byn.begin(), byn.end(), [&](int a, int b) { return node[a] < node[b]; });
+    int nb = 0;
+    for (size_t k = 0; k < byw.size(); k++) {
+        const int i = byw[k];
+        if (nb > 0 && bow_word[nb - 1] == (uint32_t)word[i]) bow_value[nb - 1] += weight[i];     // vit->second += v
+        else { bow_word[nb] = (uint32_t)word[i]; bow_value[nb] = weight[i]; nb++; }
+    }
+    double norm = 0.0;
+    for (int k = 0; k < nb; k++) norm += std::fabs(bow_value[k]);
+    if (norm > 0.0) for (int k = 0; k < nb; k++) bow_value[k] /= norm;
+    int nn = 0;
+    for (size_t k = 0; k < byn.size(); k++) {
+        const int i = byn[k];
+        if (nn == 0 || fv_node[nn - 1] != (uint32_t)node[i]) { fv_node[nn] = (uint32_t)node[i]; fv_start[nn] = (int32_t)k; nn++; }
+        fv_idx[k] = (uint32_t)i;
+    }
+    fv_start[nn] = (int32_t)byn.size();
+    *n_bow = nb; *n_nodes = nn;
+    return BORB_OK;
+}
+
+// Device time (CUDA events on the matcher's stream) of the kernels of the last database search on this handle, for bench.py's roofline.
+borb_status borb_matcher_set_timing(borb_matcher* m, int enable) {
+    if (!m) return BORB_ERR_INVALID_ARG;
+    BORB_CUDA(cudaSetDevice(m->device));
+    if (enable && !m->t0) { BORB_CUDA(cudaEventCreate(&m->t0)); BORB_CUDA(cudaEventCreate(&m->t1)); }
+    m->timing = enable != 0;
+    m->last_ms = 0.f;
+    return BORB_OK;
+}
+borb_status borb_matcher_last_kernel_ms(borb_matcher* m, float* ms) {
+    if (!m || !ms) return BORB_ERR_INVALID_ARG;
+    *ms = m->last_ms;
+    return BORB_OK;
+}
+borb_status borb_matcher_launch_count(const borb_matcher* m, uint64_t* n) {
+    if (!m || !n) return BORB_ERR_INVALID_ARG;
+    *n = m->launches;
     return BORB_OK;
 }
 

@@ -155,15 +155,15 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, 2) bowdb_match_kernel(BowDbArg
                 const int b = __shfl_sync(0xFFFFFFFFu, fbn, src);
                 const int qs = __shfl_sync(0xFFFFFFFFu, qs_l, src), nq = __shfl_sync(0xFFFFFFFFu, nq_l, src);
                 const int ts = fstart[b], nt = fstart[b + 1] - ts;
-                // column geometry: one tile of P2 <= 32 columns (G row groups), or ntile tiles of 32
+                // column geometry: one tile of P2 <= 32 columns (G = 32 / P2 row groups), or ntile tiles of 32
                 const int ntile = (nt + 31) >> 5;
-                int P2 = 32;
-                if (nt <= 16) { P2 = 1; while (P2 < nt) P2 <<= 1; }
-                const int G = ntile == 1 ? 32 / P2 : 1;
-                const int g = lane / P2, p = lane - g * P2;
+                const int lp = nt <= 1 ? 0 : (nt > 16 ? 5 : 32 - __clz(nt - 1));   // log2 of the padded tile width
+                const int P2 = 1 << lp;
+                const int G = ntile == 1 ? 32 >> lp : 1;
+                const int g = ntile == 1 ? lane >> lp : 0, p = ntile == 1 ? (lane & (P2 - 1)) : lane;
                 const int stride = ntile == 1 ? P2 : ntile * 32;
                 const bool direct = stride > BDB_DCAP;                     // bucket wider than the matrix: rows evaluated one by one
-                const int DR = direct ? 1 : BDB_DCAP / stride;             // rows per distance pass
+                const int DR = direct ? 1 : (ntile == 1 ? min(32, BDB_DCAP >> lp) : min(32, BDB_DCAP / stride));   // rows per distance pass
                 uint32_t claimed = 0;                                      // ntile == 1: claimed columns of this unit
                 if (ntile > 1) { for (int w = lane; w < ntile; w += 32) claim[w] = 0; }
                 uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0;
@@ -183,13 +183,15 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, 2) bowdb_match_kernel(BowDbArg
                     __syncwarp();
                     for (int v0 = 0; v0 < nv; v0 += DR) {
                         const int ndr = min(DR, nv - v0);
-                        // ---- distances
+                        // ---- distances; `low` collects the rows that have a distance <= TH_LOW at all: a row without one can neither
+                        //      match nor claim (:226), so the in-order replay below only visits those
+                        unsigned low = 0;
                         if (!direct) {
                             if (ntile == 1) {
                                 for (int v = g; v < ndr; v += G) {
                                     const int row = R[v0 + v];
                                     const int d = ham256<CSA>(Q[row * 2], Q[row * 2 + 1], t0, t1);
-                                    if (p < nt) D[v * stride + p] = (uint16_t)d;
+                                    if (p < nt) { D[(v << lp) + p] = (uint16_t)d; if (d <= TH_LOW) low |= 1u << v; }
                                 }
                             } else {
                                 for (int c = 0; c < ntile; c++) {
@@ -199,18 +201,21 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, 2) bowdb_match_kernel(BowDbArg
                                     for (int v = 0; v < ndr; v++) {
                                         const int row = R[v0 + v];
                                         const int d = ham256<CSA>(Q[row * 2], Q[row * 2 + 1], u0, u1);
-                                        if (col < nt) D[v * stride + col] = (uint16_t)d;
+                                        if (col < nt) { D[v * stride + col] = (uint16_t)d; if (d <= TH_LOW) low |= 1u << v; }
                                     }
                                 }
                             }
-                        }
+                            low = __reduce_or_sync(0xFFFFFFFFu, low);
+                        } else low = 1u;
                         __syncwarp();
-                        // ---- replay the rows in order (:192-251)
-                        for (int v = 0; v < ndr; v++) {
+                        // ---- replay the candidate rows in order (:192-251)
+                        while (low) {
+                            const int v = __ffs(low) - 1;
+                            low &= low - 1;
                             const int row = R[v0 + v];
                             unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
                             if (ntile == 1) {
-                                if (lane < nt && !((claimed >> lane) & 1u)) k1 = ((unsigned)D[v * stride + lane] << 16) | (unsigned)lane;
+                                if (lane < nt && !((claimed >> lane) & 1u)) k1 = ((unsigned)D[(v << lp) + lane] << 16) | (unsigned)lane;
                             } else {
                                 for (int col = lane; col < nt; col += 32) {
                                     if ((claim[col >> 5] >> (col & 31)) & 1u) continue;

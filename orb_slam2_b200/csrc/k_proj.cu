@@ -9,11 +9,14 @@
 //       sorted by (distance, position): every consumer needs the lexicographic minimum / second minimum under some exclusion
 //       set, which on a sorted list is "the first entries that are not excluded".
 //   proj_resolve_kernel<LAST>   the reference's sequential side effect: a query skips features that an EARLIER query of the same
-//       call has claimed (:87-89,:123 / :1401-1403,:1428).  One warp takes 32 consecutive queries at a time: every lane picks the
-//       first non-excluded entries of its sorted list, where "excluded" = held before the batch or currently claimed by a LOWER
-//       lane of the batch (shared-memory tag per feature, atomicMin of the lane id); claims are republished and the picks
-//       repeated until no lane changes.  Lane 0 is right after one round, lane 1 after two, ...: the fixpoint is the sequential
-//       result, reached in ~2 rounds unless neighbouring queries really fight over a feature (worst case 32).
+//       call has claimed (:87-89,:123 / :1401-1403,:1428).  The CTA takes a WAVE of up to 1024 consecutive queries, a thread per
+//       query: every thread picks the first non-excluded entries of its sorted list, where "excluded" = held before the wave or
+//       currently claimed by an EARLIER query of the wave (shared-memory tag per feature, atomicMin of the thread id); claims are
+//       republished and the picks repeated until no thread changes.  Query 0 is right after one round, a query whose chain of
+//       earlier competitors has depth d after d + 1 rounds: the fixpoint is the sequential result, reached in 2-4 rounds unless
+//       neighbouring queries really fight over features.  (A single warp walking the queries costs ~5 cycles per dependent
+//       instruction with nothing to hide them: 2 us per 32 queries; the waves make the depth of the conflict chain, not the
+//       number of queries, the cost.)
 //       LAST = false: best / second-best + ratio test (:98-121), out[query] = feature.
 //       LAST = true : best only, threshold th_dist, out[feature] = query, match events for the rotation histogram (:1426-1466).
 // All float tests use _rn intrinsics (no FMA contraction) so comparisons match the reference bit for bit.
@@ -182,10 +185,11 @@ size_t resolve_smem_bytes(int n, int n_mp) {
 }
 
 template <bool LAST>
-__global__ void __launch_bounds__(256) proj_resolve_kernel(ProjArgs A, const borb_keypoint* __restrict__ cur_keys, int32_t* __restrict__ out,
+__global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjArgs A, const borb_keypoint* __restrict__ cur_keys, int32_t* __restrict__ out,
                                                            int32_t* __restrict__ ev_idx, uint8_t* __restrict__ ev_bin, int* __restrict__ n_matches) {
     extern __shared__ uint32_t rsm[];
     __shared__ int hist[32];
+    __shared__ int cnt_nm, cnt_ev, cnt_rm;
     const int tid = threadIdx.x, lane = tid & 31, T = blockDim.x;
     const int words = (A.n + 31) / 32;
     uint32_t* held = rsm;                                   // bit per frame feature: occupied before the call or claimed during it
@@ -213,12 +217,12 @@ __global__ void __launch_bounds__(256) proj_resolve_kernel(ProjArgs A, const bor
     }
     if (LAST) for (int i = tid; i < A.n; i += T) out[i] = -1;
     if (tid < 32) hist[tid] = 0;
+    if (tid == 0) { cnt_nm = 0; cnt_ev = 0; cnt_rm = 0; }
     __syncthreads();
-    if (tid >= 32) return;
 
-    int nm = 0, nev = 0;
-    for (int base = 0; base < A.n_mp; base += 32) {
-        const int iq = base + lane;
+    // ---- waves of T consecutive queries, a thread per query; tag = lowest thread of the wave currently claiming the feature
+    for (int base = 0; base < A.n_mp; base += T) {
+        const int iq = base + tid;
         const int craw = iq < A.n_mp ? cnts[iq] : 0;
         const int cnt = craw & CAND_COUNT_MASK;
         const bool sorted = !(craw & CAND_UNSORTED);
@@ -229,13 +233,13 @@ __global__ void __launch_bounds__(256) proj_resolve_kernel(ProjArgs A, const bor
         while (true) {
             m = -1;
             if (active) {
-                // first (and for the ratio test second) entry that is neither held nor claimed by a lower lane
+                // first (and for the ratio test second) entry that is neither held nor claimed by an earlier query of the wave
                 uint32_t e1 = 0xFFFFFFFFu, e2 = 0xFFFFFFFFu;
                 if (sorted) {
                     for (int p = 0; p < cnt; p++) {
                         const uint32_t e = p < RES_K ? ent[iq * RES_K + p] : glist[p];
                         const int idx = e & 0xFFFF;
-                        if (((held[idx >> 5] >> (idx & 31)) & 1u) || tag[idx] < (uint32_t)lane) continue;
+                        if (((held[idx >> 5] >> (idx & 31)) & 1u) || tag[idx] < (uint32_t)tid) continue;
                         if (e1 == 0xFFFFFFFFu) { e1 = e; if (LAST) break; }
                         else { e2 = e; break; }
                     }
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(256) proj_resolve_kernel(ProjArgs A, const bor
                     for (int p = 0; p < cnt; p++) {
                         const uint32_t e = glist[p];
                         const int idx = e & 0xFFFF;
-                        if (((held[idx >> 5] >> (idx & 31)) & 1u) || tag[idx] < (uint32_t)lane) continue;
+                        if (((held[idx >> 5] >> (idx & 31)) & 1u) || tag[idx] < (uint32_t)tid) continue;
                         const unsigned key = (((e >> 16) & 0x1FFu) << 16) | (unsigned)p;
                         if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
                     }
@@ -264,50 +268,52 @@ __global__ void __launch_bounds__(256) proj_resolve_kernel(ProjArgs A, const bor
                 }
             }
             claim = (m >= 0 && has_obs) ? m : -1;             // only MapPoints with observations block later queries (:87-89)
-            if (!__any_sync(0xFFFFFFFFu, claim != prev)) break;
+            if (!__syncthreads_or(claim != prev)) break;      // (also: every pick has read the tags before they change)
             if (prev >= 0) tag[prev] = 0xFFFFFFFFu;
-            __syncwarp();
-            if (claim >= 0) atomicMin(&tag[claim], (uint32_t)lane);
-            __syncwarp();
+            __syncthreads();
+            if (claim >= 0) atomicMin(&tag[claim], (uint32_t)tid);
+            __syncthreads();
             prev = claim;
         }
-        // commit the batch
+        // commit the wave
         if (claim >= 0) { atomicOr(&held[claim >> 5], 1u << (claim & 31)); tag[claim] = 0xFFFFFFFFu; }
         const unsigned accm = __ballot_sync(0xFFFFFFFFu, m >= 0);
         if (LAST) {
+            int ebase = 0;
+            if (lane == 0 && accm) ebase = atomicAdd(&cnt_ev, __popc(accm));
+            ebase = __shfl_sync(0xFFFFFFFFu, ebase, 0);
             if (m >= 0) {
                 atomicMax(&out[m], iq);                       // CurrentFrame.mvpMapPoints[bestIdx2] = pMP: a later query overwrites (:1428)
-                ev_idx[nev + __popc(accm & ((1u << lane) - 1))] = m | (iq << 16);     // match event: feature | query << 16
+                ev_idx[ebase + __popc(accm & ((1u << lane) - 1))] = m | (iq << 16);     // match event: feature | query << 16
             }
-            nev += __popc(accm);
         } else if (iq < A.n_mp) out[iq] = m;
-        nm += __popc(accm);
-        __syncwarp();
+        if (lane == 0 && accm) atomicAdd(&cnt_nm, __popc(accm));
+        __syncthreads();
     }
     if (LAST && A.check_ori) {
         __threadfence_block();
-        __syncwarp();
+        __syncthreads();
+        const int nev = cnt_ev;
         // rotation histogram over the MATCH EVENTS (a feature re-claimed later appears twice, exactly as rotHist does)
-        for (int e = lane; e < nev; e += 32) {
+        for (int e = tid; e < nev; e += T) {
             const int ev = ev_idx[e];
             const int b = rot_bin(A.q_angle[ev >> 16], cur_keys[ev & 0xFFFF].angle);
             ev_bin[e] = (uint8_t)b;
             atomicAdd(&hist[b], 1);
         }
-        __syncwarp();
+        __syncthreads();
         int i1, i2, i3;
         three_maxima(hist, i1, i2, i3);
         // culling is order independent for the final state: every event of a culled bin nulls its feature
         int removed = 0;
-        for (int e = lane; e < nev; e += 32) {
+        for (int e = tid; e < nev; e += T) {
             const int b = ev_bin[e];
             if (b != i1 && b != i2 && b != i3) { out[ev_idx[e] & 0xFFFF] = -2; removed++; }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, off);
-        nm -= removed;
+        if (removed) atomicAdd(&cnt_rm, removed);
     }
-    if (lane == 0) *n_matches = nm;
+    __syncthreads();
+    if (tid == 0) *n_matches = cnt_nm - cnt_rm;
 }
 
 void launch_candidates(const ProjArgs& A, cudaStream_t s) {
@@ -316,12 +322,13 @@ void launch_candidates(const ProjArgs& A, cudaStream_t s) {
 
 void launch_resolve(const ProjArgs& A, bool last, int32_t* out, int32_t* ev_idx, uint8_t* ev_bin, int* n_matches, cudaStream_t s) {
     const size_t smem = resolve_smem_bytes(A.n, A.n_mp);
+    const int threads = A.n_mp > 512 ? 1024 : (A.n_mp > 256 ? 512 : 256);     // one wave covers the whole call when it can
     if (last) {
         allow_max_smem((const void*)proj_resolve_kernel<true>);
-        proj_resolve_kernel<true><<<1, 256, smem, s>>>(A, A.keys, out, ev_idx, ev_bin, n_matches);
+        proj_resolve_kernel<true><<<1, threads, smem, s>>>(A, A.keys, out, ev_idx, ev_bin, n_matches);
     } else {
         allow_max_smem((const void*)proj_resolve_kernel<false>);
-        proj_resolve_kernel<false><<<1, 256, smem, s>>>(A, A.keys, out, ev_idx, ev_bin, n_matches);
+        proj_resolve_kernel<false><<<1, threads, smem, s>>>(A, A.keys, out, ev_idx, ev_bin, n_matches);
     }
 }
 

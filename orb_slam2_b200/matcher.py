@@ -721,6 +721,18 @@ class ORBVocabulary:
         check(self._lib.borb_bow_transform(self._h, _p(d), n, levelsup, _p(word), _p(weight), _p(node)), "borb_bow_transform")
         return word[:n], weight[:n], node[:n]
 
+    def ComputeBoW(self, descriptors: np.ndarray, levelsup: int = 4):
+        """Frame::ComputeBoW (src/Frame.cc:395-402) through borb_compute_bow: (mBowVec as {word: value}, mFeatVec) with the
+        ordered-map bookkeeping done in C++ — same results as transform() below."""
+        d = np.ascontiguousarray(descriptors, np.uint8)
+        n = len(d)
+        bw = np.zeros(max(n, 1), np.uint32); bv = np.zeros(max(n, 1), np.float64)
+        fn = np.zeros(max(n, 1), np.uint32); fs = np.zeros(n + 1, np.int32); fi = np.zeros(max(n, 1), np.uint32)
+        nb, nn = C.c_int32(0), C.c_int32(0)
+        check(self._lib.borb_compute_bow(self._h, _p(d), n, levelsup, _p(bw), _p(bv), C.byref(nb), _p(fn), _p(fs), _p(fi), C.byref(nn)), "borb_compute_bow")
+        nb, nn = nb.value, nn.value
+        return dict(zip(bw[:nb].tolist(), bv[:nb].tolist())), FeatureVector(fn[:nn].copy(), fs[:nn + 1].copy(), fi[:fs[nn]].copy())
+
     def transform(self, descriptors: np.ndarray, levelsup: int = 4):
         """transform(features, BowVector, FeatureVector, levelsup) (:1127-1194) for TF-IDF / L1 (ORBvoc.txt "10 6 0 0"):
         the tree descent runs on the GPU; the ordered-map bookkeeping is done on the host in feature order, as the reference does."""

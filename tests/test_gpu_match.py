@@ -372,3 +372,16 @@ def test_long_candidate_lists(M, oracle, views, th):
     n_o, m_o = oracle.port_search_by_projection(F, mps, th, 0.9)
     n_g, m_g = M.ORBmatcher(0.9, True).SearchByProjection(F, mps, th)
     assert n_g == n_o and np.array_equal(m_g, m_o), int((m_g != m_o).sum())
+
+
+def test_compute_bow_equals_the_reference_bookkeeping(M, oracle, views):
+    """borb_compute_bow (Frame::ComputeBoW, src/Frame.cc:395-402): BowVector / FeatureVector built in C++ equal the Python mirror of
+    TemplatedVocabulary::transform's map bookkeeping, which tests/test_oracle_dbow_ref.py pins to the verbatim DBoW2 (bit-exact doubles)."""
+    pv = oracle.PortVocabulary.random(10, 5, 21)
+    e = pv.export()
+    voc = M.ORBVocabulary.from_arrays(e["parent"], e["is_leaf"], e["desc"], e["weight"], e["k"], e["L"])
+    for d, levelsup in ((views[7]["dl"], 4), (views[8]["dr"], 3), (views[7]["dl"][:1], 4), (views[7]["dl"][:0], 4)):
+        bow_c, fv_c = voc.ComputeBoW(d, levelsup)
+        bow_p, fv_p = voc.transform(d, levelsup)
+        assert list(bow_c.items()) == list(bow_p.items())                  # same words, same order, bit-identical doubles
+        assert np.array_equal(fv_c.node_id, fv_p.node_id) and np.array_equal(fv_c.start, fv_p.start) and np.array_equal(fv_c.feat_idx, fv_p.feat_idx)
