@@ -404,4 +404,41 @@ int matchref_fuse(const orbport_kp* kf_keys_un, const uint8_t* kf_desc, const fl
     return n;
 }
 
+// ---- bench.py's CPU arm for BASELINE configs[4]: the reference keeps its KeyFrames in memory, so the stand-ins are built
+// once (outside the timed region) and the timed sweep is nothing but ORBmatcher::SearchByBoW(pKF, F, out) per keyframe.
+struct KfHandle { KeyFrame K; std::vector<MapPoint> pool; };
+struct FrHandle { Frame F; };
+void* matchref_kf_create(const orbport_kp* keys, const uint8_t* desc, const uint8_t* has_mp, int n, int nn, const uint32_t* node,
+                         const int32_t* start, const uint32_t* idx) {
+    KfHandle* h = new KfHandle();
+    build_keyframe(h->K, FrameArgs{keys, desc, nullptr, n, 0, 0, 1, 1, nullptr, 0, 1.f});
+    fill_featvec(h->K.mFeatVec, nn, node, start, idx);
+    h->pool.resize(n);
+    for (int i = 0; i < n; i++) if (has_mp && has_mp[i]) h->K.mvpMapPoints[i] = &h->pool[i];
+    return h;
+}
+void matchref_kf_destroy(void* h) { delete (KfHandle*)h; }
+void* matchref_frame_create(const orbport_kp* keys, const uint8_t* desc, int n, int nn, const uint32_t* node, const int32_t* start,
+                            const uint32_t* idx) {
+    FrHandle* h = new FrHandle();
+    build_frame(h->F, FrameArgs{keys, desc, nullptr, n, 0, 0, 1, 1, nullptr, 0, 1.f});
+    fill_featvec(h->F.mFeatVec, nn, node, start, idx);
+    return h;
+}
+void matchref_frame_destroy(void* h) { delete (FrHandle*)h; }
+// match_f: n_kf x f_n (may be null): index of the keyframe feature matched to frame feature j, or -1
+int matchref_search_by_bow_sweep(void* const* kfs, int n_kf, void* frame, float nnratio, int check_ori, int32_t* nmatches, int32_t* match_f) {
+    FrHandle* f = (FrHandle*)frame;
+    ORBmatcher m(nnratio, check_ori != 0);
+    int total = 0;
+    for (int k = 0; k < n_kf; k++) {
+        KfHandle* h = (KfHandle*)kfs[k];
+        std::vector<MapPoint*> out;
+        nmatches[k] = m.SearchByBoW(&h->K, f->F, out);
+        total += nmatches[k];
+        if (match_f) for (int j = 0; j < f->F.N; j++) match_f[(size_t)k * f->F.N + j] = index_of(h->pool, out[j]);
+    }
+    return total;
+}
+
 }  // extern "C"

@@ -1033,3 +1033,82 @@ def port_depth_to_float(raw, factor):
     lib.orbport_depth_to_float.restype = None
     lib.orbport_depth_to_float(_ptr(raw), raw.size, float(np.float32(factor)), _ptr(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Batch helpers for bench.py's CPU arms (BASELINE configs[4]): keyframes built once, the timed sweep is the reference's loop.
+def port_compute_bow(voc: "PortVocabulary", desc, levelsup=4):
+    """(words[uint32], values[float64], FeatureVector CSR (node, start, idx)) — TemplatedVocabulary::transform with std::map bookkeeping."""
+    lib = _plib()
+    d = _a(desc, np.uint8)
+    n = len(d)
+    bw = np.zeros(max(n, 1), np.uint32); bv = np.zeros(max(n, 1), np.float64)
+    fn_ = np.zeros(max(n, 1), np.uint32); fs = np.zeros(n + 1, np.int32); fi = np.zeros(max(n, 1), np.uint32)
+    nb, nn = C.c_int32(0), C.c_int32(0)
+    lib.orbport_compute_bow.restype = None
+    lib.orbport_compute_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+    lib.orbport_compute_bow(voc._h, _ptr(d), n, levelsup, _ptr(bw), _ptr(bv), C.addressof(nb), _ptr(fn_), _ptr(fs), _ptr(fi), C.addressof(nn))
+    return bw[:nb.value].copy(), bv[:nb.value].copy(), (fn_[:nn.value].copy(), fs[:nn.value + 1].copy(), fi[:fs[nn.value]].copy())
+
+
+class PortScoreSweep:
+    """KeyFrameDatabase scoring loop (src/KeyFrameDatabase.cc:127,:240) over many keyframes in one C call."""
+
+    def __init__(self, kf_bows):
+        self.lib = _plib()
+        self.off = np.zeros(len(kf_bows) + 1, np.int32)
+        self.off[1:] = np.cumsum([len(w) for w, _ in kf_bows])
+        self.w = _a(np.concatenate([w for w, _ in kf_bows]) if kf_bows else np.zeros(0), np.uint32)
+        self.v = _a(np.concatenate([v for _, v in kf_bows]) if kf_bows else np.zeros(0), np.float64)
+        self.n = len(kf_bows)
+        self.score = np.zeros(max(self.n, 1), np.float32); self.common = np.zeros(max(self.n, 1), np.int32)
+        self.lib.orbport_bow_score_sweep.restype = None
+        self.lib.orbport_bow_score_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+
+    def __call__(self, qw, qv):
+        qw = _a(qw, np.uint32); qv = _a(qv, np.float64)
+        self.lib.orbport_bow_score_sweep(_ptr(qw), _ptr(qv), len(qw), _ptr(self.w), _ptr(self.v), _ptr(self.off), self.n, _ptr(self.score), _ptr(self.common))
+        return self.score[:self.n], self.common[:self.n]
+
+
+class RefBowSweep:
+    """The reference's ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (src/ORBmatcher.cc:159-288, compiled verbatim) for one
+    frame against many keyframes that are built once — what relocalisation / loop closing does with KeyFrames it already holds."""
+
+    def __init__(self, kfs):
+        self.lib = _mlib()
+        L = self.lib
+        L.matchref_kf_create.restype = C.c_void_p
+        L.matchref_kf_create.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 3
+        L.matchref_kf_destroy.argtypes = [C.c_void_p]
+        L.matchref_frame_create.restype = C.c_void_p
+        L.matchref_frame_create.argtypes = [C.c_void_p] * 2 + [C.c_int, C.c_int] + [C.c_void_p] * 3
+        L.matchref_frame_destroy.argtypes = [C.c_void_p]
+        L.matchref_search_by_bow_sweep.restype = C.c_int
+        L.matchref_search_by_bow_sweep.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        self.h = []
+        for kf in kfs:
+            k, d, hm, nd, st, fi = _kf_args(kf)
+            self.h.append(L.matchref_kf_create(_ptr(k), _ptr(d), _ptr(hm), len(k), len(nd), _ptr(nd), _ptr(st), _ptr(fi)))
+        self.arr = (C.c_void_p * max(len(self.h), 1))(*self.h)
+        self.nm = np.zeros(max(len(self.h), 1), np.int32)
+
+    def frame(self, F):
+        k, d, _, nd, st, fi = _kf_args(F)
+        return self.lib.matchref_frame_create(_ptr(k), _ptr(d), len(k), len(nd), _ptr(nd), _ptr(st), _ptr(fi)), len(k)
+
+    def free_frame(self, fh):
+        self.lib.matchref_frame_destroy(fh[0])
+
+    def sweep(self, fh, nnratio, check_ori, want_matches=False):
+        match = np.full((len(self.h), max(fh[1], 1)), -1, np.int32) if want_matches else None
+        self.lib.matchref_search_by_bow_sweep(self.arr, len(self.h), fh[0], float(np.float32(nnratio)), int(check_ori), _ptr(self.nm),
+                                              _ptr(match) if want_matches else None)
+        return self.nm[:len(self.h)].copy(), (match[:, :fh[1]] if want_matches else None)
+
+    def __del__(self):
+        try:
+            for h in self.h:
+                self.lib.matchref_kf_destroy(h)
+        except Exception:
+            pass

@@ -444,6 +444,50 @@ void orbport_voc_transform(void* h, const uint8_t* desc, int n, int levelsup, in
     }
 }
 
+double orbport_bow_score_l1(const uint32_t* w1, const double* v1, int n1, const uint32_t* w2, const double* v2, int n2, int32_t* common, uint32_t* first);
+
+// TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1127-1194) for TF-IDF / L1:
+// std::map bookkeeping as the reference does it, flattened to arrays (words ascending; nodes ascending, features in order).
+void orbport_compute_bow(void* h, const uint8_t* desc, int n, int levelsup, uint32_t* bow_word, double* bow_value, int32_t* n_bow,
+                         uint32_t* fv_node, int32_t* fv_start, uint32_t* fv_idx, int32_t* n_nodes) {
+    std::vector<int32_t> word(n > 0 ? n : 1), node(n > 0 ? n : 1);
+    std::vector<double> weight(n > 0 ? n : 1);
+    orbport_voc_transform(h, desc, n, levelsup, word.data(), weight.data(), node.data());
+    std::map<uint32_t, double> bow;
+    std::map<uint32_t, std::vector<uint32_t>> fv;
+    for (int i = 0; i < n; i++)
+        if (weight[i] > 0) {
+            auto it = bow.lower_bound((uint32_t)word[i]);                         // BowVector::addWeight
+            if (it != bow.end() && !(bow.key_comp()((uint32_t)word[i], it->first))) it->second += weight[i];
+            else bow.insert(it, std::make_pair((uint32_t)word[i], weight[i]));
+            fv[(uint32_t)node[i]].push_back((uint32_t)i);                         // FeatureVector::addFeature
+        }
+    double norm = 0.0;                                                            // BowVector::normalize(L1)
+    for (auto& kv : bow) norm += std::fabs(kv.second);
+    if (norm > 0.0) for (auto& kv : bow) kv.second /= norm;
+    int nb = 0;
+    for (auto& kv : bow) { bow_word[nb] = kv.first; bow_value[nb] = kv.second; nb++; }
+    int nn = 0, pos = 0;
+    fv_start[0] = 0;
+    for (auto& kv : fv) {
+        fv_node[nn] = kv.first;
+        for (uint32_t f : kv.second) fv_idx[pos++] = f;
+        fv_start[++nn] = pos;
+    }
+    *n_bow = nb; *n_nodes = nn;
+}
+
+// the scoring loop of KeyFrameDatabase::Detect*Candidates (src/KeyFrameDatabase.cc:127,:240) over n_kf keyframes whose BowVectors
+// are concatenated (offsets kf_off[n_kf + 1]): float si = mpVoc->score(query, kf)
+void orbport_bow_score_sweep(const uint32_t* q_word, const double* q_value, int nq, const uint32_t* kf_word, const double* kf_value,
+                             const int32_t* kf_off, int n_kf, float* score, int32_t* common) {
+    for (int k = 0; k < n_kf; k++) {
+        int32_t c = 0; uint32_t first = 0;
+        score[k] = (float)orbport_bow_score_l1(q_word, q_value, nq, kf_word + kf_off[k], kf_value + kf_off[k], kf_off[k + 1] - kf_off[k], &c, &first);
+        if (common) common[k] = c;
+    }
+}
+
 }  // extern "C"
 
 // ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470.

@@ -13,8 +13,12 @@ def _run(args):
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, cwd=ROOT, timeout=600)
 
 
-def test_reference_arm_prints_one_contract_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-pairs-per-thread", "1"])
+import pytest
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 4])
+def test_reference_arm_prints_one_contract_line(cfg):
+    r = _run(["--impl", "reference", "--config", str(cfg), "--steps", "1", "--warmup", "1", "--ref-items-per-thread", "1", "--keyframes", "2000"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
@@ -25,7 +29,7 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "configs[1]" in d["config"]["workload"]
+    assert f"configs[{cfg}]" in d["config"]["workload"]
 
 
 def test_b200_arm_needs_a_gpu():
