@@ -218,7 +218,8 @@ def build_cpu_data(cfg: int, rank: int = 0, n_kf: int = 2000, sample: int = 64):
         mps = []
         for i, im in enumerate(imgs):
             k, d = E(im)
-            mps.append(make_mappoints(k, d, E.scale, np.random.default_rng([SEED, rank, i, 5])))
+            ku = O.port_rgbd_frame(k, np.array(TUM1_K, np.float32), np.array(TUM1_DIST, np.float32), TUM1_BF, depths_f[i])["keys_un"]
+            mps.append(make_mappoints(ku, d, E.scale, np.random.default_rng([SEED, rank, i, 5])))     # projections live in the undistorted image
         return imgs, depths_f, mps
     # cfg 4: a database sample is enough for the CPU arm (cost is linear in the keyframes): `sample` keyframes per thread
     voc = O.PortVocabulary.random(10, 6, 7)
@@ -594,9 +595,11 @@ def run_config2(args, env: Env):
     mp_views, mp_keep, first = [], [], {}
     for j in range(NBUF):
         outs = exts[0].extract_batch([himg[j, i] for i in range(B)])
+        _, hst = M.frames_from_extractor(mats[0], exts[0], np.arange(B), [len(k) for k, _ in outs], TUM1_K, TUM1_DIST, bf=TUM1_BF, mode=2,
+                                         depth=[hdep[j, i] for i in range(B)], depth_factor=TUM1_DEPTH_FACTOR)
         row = []
         for i, (k, d) in enumerate(outs):
-            m = make_mappoints(k, d, sf, np.random.default_rng([SEED, rank, j, i]))
+            m = make_mappoints(hst["keys_un"][i], d, sf, np.random.default_rng([SEED, rank, j, i]))     # projections live in the undistorted image
             arrs = [np.ascontiguousarray(m[f]) for f in ("px", "py", "pxr", "lvl", "vc", "desc")]
             mp_keep.append(arrs)
             row.append(M._MapPointViewC(len(arrs[0]), *[a.ctypes.data for a in arrs], None, None))

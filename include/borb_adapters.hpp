@@ -21,6 +21,7 @@ inline void check(borb_status s, const char* where) {
 }
 }  // namespace borb
 
+#ifndef BORB_ADAPTER_NO_EXTRACTOR   /* borb_matcher_adapters.hpp alone: define it to skip the cv::InputArray-based extractor class */
 namespace ORB_SLAM2 {
 
 class ORBextractor {
@@ -108,3 +109,4 @@ inline void ComputeStereoMatches(ORB_SLAM2::ORBextractor& left, ORB_SLAM2::ORBex
     check(borb_stereo_match2(left.handle(), right.handle(), mbf, mb, mvuRight.data(), mvDepth.data(), N), "borb_stereo_match2");
 }
 }  // namespace borb
+#endif  /* BORB_ADAPTER_NO_EXTRACTOR */

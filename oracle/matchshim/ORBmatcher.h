@@ -91,6 +91,8 @@ public:
     int Observations() { return nObs; }
     float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
+    float GetMaxDistance() { return mfMaxDistance; }      // the two getters include/borb_matcher_adapters.hpp asks a maintainer to add
+    float GetMinDistance() { return mfMinDistance; }
     bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
     int GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? (int)mObservations[pKF] : -1; }
     void AddObservation(KeyFrame*, size_t idx) { fusedIdx = (int)idx; }   // recorded, not applied (see matchref_wrap.cpp)

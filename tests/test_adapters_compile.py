@@ -43,65 +43,23 @@ def test_adapters_compile_and_link(tmp_path):
         assert "no CUDA device" in r.stdout or "no CPU path" in r.stdout or "CUDA" in r.stdout, r.stdout
 
 
-MATCHER_PROG = textwrap.dedent(r'''
-    #include <opencv2/core/core.hpp>
-    #include <map>
-    #include "borb_matcher_adapters.hpp"
-    #include <cstdio>
-    // Mock types with the member names of the reference classes the adapters touch (include/MapPoint.h, Frame.h, KeyFrame.h).
-    struct MapPoint {
-        bool mbTrackInView = true; float mTrackProjX = 100, mTrackProjY = 80, mTrackProjXR = 90, mTrackViewCos = 0.9f; int mnTrackScaleLevel = 0;
-        cv::Mat desc = cv::Mat(1, 32, CV_8U), pos = cv::Mat(3, 4, CV_8U), nrm = cv::Mat(3, 4, CV_8U);   // 3x1 CV_32F stand-ins (4 bytes per row)
-        bool isBad() { return false; }
-        int Observations() { return 1; }
-        cv::Mat GetDescriptor() { return desc; }
-        cv::Mat GetWorldPos() { return pos; }
-        cv::Mat GetNormal() { return nrm; }
-        float GetMaxDistance() { return 10.f; }
-        float GetMinDistance() { return 1.f; }
-        void IncreaseVisible(int = 1) {}
-    };
-    typedef std::map<unsigned, std::vector<unsigned> > FeatureVector;
-    struct Frame {
-        int N = 0; std::vector<cv::KeyPoint> mvKeysUn; cv::Mat mDescriptors; std::vector<float> mvuRight; std::vector<MapPoint*> mvpMapPoints;
-        std::vector<bool> mvbOutlier; std::vector<float> mvScaleFactors = std::vector<float>(8, 1.f); cv::Mat mTcw = cv::Mat(4, 16, CV_8U);
-        float fx = 500, fy = 500, cx = 320, cy = 240, mbf = 40, mfLogScaleFactor = 0.1823f; FeatureVector mFeatVec;
-        static float mnMinX, mnMinY, mnMaxX, mnMaxY;
-        cv::Mat GetCameraCenter() { return cv::Mat(3, 4, CV_8U); }
-    };
-    float Frame::mnMinX = 0, Frame::mnMinY = 0, Frame::mnMaxX = 640, Frame::mnMaxY = 480;
-    struct KeyFrame {
-        std::vector<cv::KeyPoint> mvKeysUn; cv::Mat mDescriptors; FeatureVector mFeatVec; std::vector<MapPoint*> mps;
-        std::vector<MapPoint*> GetMapPointMatches() { return mps; }
-    };
-    int main() {
-        try {
-            Frame F, L; KeyFrame K; MapPoint p; std::vector<MapPoint*> v(1, &p), out;
-            int n = borb::adapt::SearchByProjection(F, v, 3.f, 0.8f);
-            n += borb::adapt::SearchByProjectionLast(F, L, 7.f, false, false, true);
-            n += borb::adapt::SearchByBoW(&K, F, out, 0.7f, true);
-            n += borb::adapt::SearchLocalPoints(F, v, 1.f, 0.8f, [](MapPoint*) { return false; });
-            std::printf("matches %d\n", n);
-        } catch (const std::exception& e) { std::printf("error: %s\n", e.what()); return 3; }
-        return 0;
-    }
-''')
-
-
-def test_matcher_adapters_compile_and_link(tmp_path):
-    """Every template of include/borb_matcher_adapters.hpp instantiates against types with the reference's member names and
-    links against libborb.so (without a GPU the run must surface the library's error: there is no CPU path)."""
-    import __graft_entry__ as g
-    so = os.path.join(ROOT, "orb_slam2_b200", "libborb.so")
+def test_matcher_adapter_library_builds_and_exports_the_reference_entry_points():
+    """integration/ORBmatcher_borb.cc (every ORBmatcher method through include/borb_matcher_adapters.hpp) compiles against the
+    oracle's Frame / KeyFrame / MapPoint stand-ins and links libborb.so: oracle/_ref/libadaptmatch.so exports the same entry
+    points as the verbatim libmatchref.so.  It is EXECUTED on the GPU by tests/test_gpu_adapters.py."""
+    import ctypes
+    import pytest
+    from oracle import oracle_lib as O
+    O.build()
+    so = os.path.join(ROOT, "oracle", "_ref", "libadaptmatch.so")
     if not os.path.exists(so):
-        g.build()
-    src = tmp_path / "matcher_adapter_check.cpp"
-    src.write_text(MATCHER_PROG)
-    exe = tmp_path / "matcher_adapter_check"
-    cmd = ["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "cvshim"),
-           str(src), "-o", str(exe), so, f"-Wl,-rpath,{os.path.dirname(so)}"]
-    subprocess.check_call(cmd)
-    r = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert r.returncode in (0, 3), r
-    if r.returncode == 3:
-        assert "CUDA" in r.stdout or "device" in r.stdout, r.stdout
+        pytest.skip("needs the reference tree (DBoW2 FeatureVector) at build time")
+    lib = ctypes.CDLL(so)
+    for name in ("matchref_search_by_projection", "matchref_search_by_projection_last", "matchref_search_by_projection_kf",
+                 "matchref_search_by_projection_sim3", "matchref_search_by_bow_kf_f", "matchref_search_by_bow_kf_kf",
+                 "matchref_search_for_triangulation", "matchref_search_for_initialization", "matchref_search_by_sim3", "matchref_fuse",
+                 "matchref_descriptor_distance"):
+        assert hasattr(lib, name), name
+    # the adapter library depends on the product, not on the reference's matcher
+    deps = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "libborb.so" in deps
