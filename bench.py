@@ -101,15 +101,19 @@ def make_rgbd(stream_id: int, n: int, w: int, h: int):
     return imgs, depths
 
 
-def make_mappoints(keys, desc, scale_factors, rng):
+def make_mappoints(keys, desc, scale_factors, rng, u_right=None):
     """300 'local MapPoints' for a frame: a random subset of its own features as seen a moment earlier — projection jittered by
     ~1.5 px, predicted level = the feature's octave (what Frame::isInFrustum leaves in mTrackProj* / mnTrackScaleLevel)."""
     n = min(N_MAPPOINTS, len(keys))
     sel = rng.choice(len(keys), n, replace=False)
     px = (keys["x"][sel] + rng.normal(0, 1.5, n)).astype(np.float32)
     py = (keys["y"][sel] + rng.normal(0, 1.5, n)).astype(np.float32)
-    return dict(px=px, py=py, pxr=(px - 20.0).astype(np.float32), lvl=keys["octave"][sel].astype(np.int32), vc=np.full(n, 0.9, np.float32),
-                desc=np.ascontiguousarray(desc[sel]))
+    # mTrackProjXR = u - mbf/z of the MapPoint: consistent with the feature's own mvuRight where the depth sensor saw it
+    pxr = (px - 20.0).astype(np.float32)
+    if u_right is not None:
+        ur = np.asarray(u_right, np.float32)[sel]
+        pxr = np.where(ur >= 0, ur + (px - keys["x"][sel]), pxr).astype(np.float32)
+    return dict(px=px, py=py, pxr=pxr, lvl=keys["octave"][sel].astype(np.int32), vc=np.full(n, 0.9, np.float32), desc=np.ascontiguousarray(desc[sel]))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -218,8 +222,8 @@ def build_cpu_data(cfg: int, rank: int = 0, n_kf: int = 2000, sample: int = 64):
         mps = []
         for i, im in enumerate(imgs):
             k, d = E(im)
-            ku = O.port_rgbd_frame(k, np.array(TUM1_K, np.float32), np.array(TUM1_DIST, np.float32), TUM1_BF, depths_f[i])["keys_un"]
-            mps.append(make_mappoints(ku, d, E.scale, np.random.default_rng([SEED, rank, i, 5])))     # projections live in the undistorted image
+            fr = O.port_rgbd_frame(k, np.array(TUM1_K, np.float32), np.array(TUM1_DIST, np.float32), TUM1_BF, depths_f[i])
+            mps.append(make_mappoints(fr["keys_un"], d, E.scale, np.random.default_rng([SEED, rank, i, 5]), fr["u_right"]))   # projections live in the undistorted image
         return imgs, depths_f, mps
     # cfg 4: a database sample is enough for the CPU arm (cost is linear in the keyframes): `sample` keyframes per thread
     voc = O.PortVocabulary.random(10, 6, 7)
@@ -599,7 +603,7 @@ def run_config2(args, env: Env):
                                          depth=[hdep[j, i] for i in range(B)], depth_factor=TUM1_DEPTH_FACTOR)
         row = []
         for i, (k, d) in enumerate(outs):
-            m = make_mappoints(hst["keys_un"][i], d, sf, np.random.default_rng([SEED, rank, j, i]))     # projections live in the undistorted image
+            m = make_mappoints(hst["keys_un"][i], d, sf, np.random.default_rng([SEED, rank, j, i]), hst["u_right"][i])     # projections live in the undistorted image
             arrs = [np.ascontiguousarray(m[f]) for f in ("px", "py", "pxr", "lvl", "vc", "desc")]
             mp_keep.append(arrs)
             row.append(M._MapPointViewC(len(arrs[0]), *[a.ctypes.data for a in arrs], None, None))
@@ -692,7 +696,7 @@ def run_config2(args, env: Env):
 
     env.clocks.start()
     run_passes(pass_resident, Wm * NH)
-    assert hs[0].matches > B * 100, "warm-up produced too few matches"
+    assert hs[0].matches > B * 100, f"warm-up produced too few matches ({hs[0].matches} for {B} frames)"
     torch.cuda.synchronize(); t0 = time.perf_counter()
     run_passes(pass_resident, NH * 2)
     torch.cuda.synchronize()
