@@ -687,12 +687,19 @@ def run_config2(args, env: Env):
     # NH host threads = NH camera-stream groups, each with its own extractor + matcher handle (ctypes releases the GIL)
     def run_passes(fn, n_total):
         """n_total passes dealt round-robin to the NH handle threads."""
+        errs = []
+
         def body(t):
-            for k in range(t, n_total, NH):
-                fn(hs[t], k)
+            try:
+                for k in range(t, n_total, NH):
+                    fn(hs[t], k)
+            except BaseException as ex:       # a worker thread must not die silently
+                errs.append(ex)
         ths = [threading.Thread(target=body, args=(t,)) for t in range(NH)]
         for th in ths: th.start()
         for th in ths: th.join()
+        if errs:
+            raise errs[0]
 
     env.clocks.start()
     run_passes(pass_resident, Wm * NH)

@@ -452,6 +452,18 @@ BORB_API borb_status borb_voc_destroy(borb_voc* v);
 BORB_API borb_status borb_voc_blob(const borb_voc* v, void** d_blob, size_t* bytes);
 /* Adopt a packed blob that already sits in this device's memory (receiver side of the broadcast). */
 BORB_API borb_status borb_voc_from_blob(void* d_blob, size_t bytes, int device, borb_voc** out);
+/* NCCL without torch, for a C++ Tracking host: the vocabulary is parsed by ONE rank (src/System.cc:65 loads the 145 MB
+ * text on every process) and broadcast over NVLink into every GPU's HBM.  libnccl.so.2 is resolved with dlopen at the first call
+ * (BORB_ERR_UNSUPPORTED if absent); libborb.so itself does not link NCCL.
+ *   borb_nccl_unique_id: ncclGetUniqueId (128 bytes) on one rank, handed to the others by the host's own means;
+ *   borb_nccl_comm_create / _destroy: ncclCommInitRank / ncclCommDestroy — or pass an ncclComm_t the host already owns;
+ *   borb_voc_broadcast: two ncclBroadcast calls (size, blob).  On `root` pass the loaded vocabulary and get it back in *out;
+ *   elsewhere pass NULL and receive a vocabulary backed by the received blob.  nccl_comm = the rank's ncclComm_t. */
+BORB_API borb_status borb_nccl_unique_id(uint8_t* id128);
+BORB_API borb_status borb_nccl_comm_create(const uint8_t* id128, int world_size, int rank, int device, void** nccl_comm);
+BORB_API borb_status borb_nccl_comm_destroy(void* nccl_comm);
+BORB_API borb_status borb_voc_broadcast(borb_voc* root_voc, void* nccl_comm, int root, int rank, int device, borb_voc** out);
+
 /* TemplatedVocabulary::transform(feature, id, weight, nid, levelsup) for n descriptors (:1218-1259): word id,
  * word weight and the node id at level L-levelsup per feature.  Frame::ComputeBoW (src/Frame.cc:395-402) builds
  * mBowVec / mFeatVec from these on the host side of the adapter. */

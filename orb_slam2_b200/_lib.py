@@ -112,6 +112,10 @@ _SIGNATURES = {
     "borb_debug_candidates": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, i32p]),
     "borb_debug_selected": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, i32p]),
     "borb_debug_blurred": (C.c_int, [vp, C.c_int, C.c_int, vp, i32p, i32p]),
+    "borb_nccl_unique_id": (C.c_int, [vp]),
+    "borb_nccl_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "borb_nccl_comm_destroy": (C.c_int, [vp]),
+    "borb_voc_broadcast": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "borb_compute_bow": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, i32p, vp, vp, vp, i32p]),
     "borb_matcher_set_timing": (C.c_int, [vp, C.c_int]),
     "borb_matcher_last_kernel_ms": (C.c_int, [vp, f32p]),

@@ -24,6 +24,8 @@ struct borb_frame {
     cudaEvent_t ready = nullptr;    // recorded after the last kernel that writes the block
 };
 
+extern "C" void borb_voc_adopt_ownership(borb_voc* v);     // internal (borb_nccl.cu): the vocabulary now owns its blob
+
 namespace borb {
 
 constexpr int GRID_COLS = 64, GRID_ROWS = 48;     // FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.h:37-38)

@@ -388,7 +388,7 @@ borb_status borb_frames_from_extractor(borb_matcher* m, borb_extractor* e, const
     if (s != BORB_OK) return fail(s);
     const size_t px = depth_type == 1 ? 2 : 4;
     const size_t depth_img_bytes = (mode == 2 && !depth_on_device) ? (size_t)w * h * px : 0;
-    if (mode == 2 && depth_stride_bytes < (int)(w * px)) { set_error("depth stride %d smaller than a row", depth_stride_bytes); return fail(BORB_ERR_INVALID_ARG); }
+    if (mode == 2 && !depth_on_device && depth_stride_bytes < (int)(w * px)) { set_error("depth stride %d smaller than a row", depth_stride_bytes); return fail(BORB_ERR_INVALID_ARG); }
     const int ocap = (keys_un || u_right || depth_out) ? cap : 0;
     Stager st(m);
     const size_t o_jobs = st.reserve((size_t)n_frames * sizeof(FrameJob));
@@ -1480,6 +1480,9 @@ borb_status borb_voc_from_blob(void* d_blob, size_t bytes, int device, borb_voc*
     *out = v;
     return BORB_OK;
 }
+
+// internal: the vocabulary takes ownership of a blob it adopted (receiver side of borb_voc_broadcast)
+extern "C" void borb_voc_adopt_ownership(borb_voc* v) { if (v) v->owns = true; }
 
 borb_status borb_bow_transform(borb_voc* v, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node) {
     if (!v || n < 0 || (n > 0 && (!desc || !word || !weight || !node))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
