@@ -120,11 +120,11 @@ struct BowDev {                   // one keyframe's BowVector in the device-resi
 struct KfStream {                  // one keyframe of the device-resident database, features permuted into FeatureVector order
     const uint32_t* node;         // nn node ids, ascending
     const int32_t* start;         // nn + 1 row offsets
-    const uint16_t* orig;         // m: feature index of row r (mFeatVec order: node, then feature index)
-    const float* angle;           // m: mvKeysUn[orig].angle
-    const uint8_t* hasmp;         // m: MapPoint present && !isBad(), per row
+    const uint2* meta;            // m rows: x = feature index (mFeatVec order: node, then feature index) | good-MapPoint flag << 16,
+                                  //         y = bits of mvKeysUn[feature].angle
     const uint8_t* desc;          // m x 32, 16-byte aligned
     int nn, m, n, pad;
+    const void* pad2[2];
 };
 
 struct BowDbArgs {                // bowdb_match_kernel (k_bowdb.cu)

@@ -343,7 +343,7 @@ borb_status borb_frame_create(borb_matcher* m, const borb_frame_view* v, borb_fr
 borb_status borb_frame_destroy(borb_frame* f) {
     if (!f) return BORB_OK;
     std::lock_guard<std::mutex> lk(g_frame_pool_mu);
-    if (g_frame_pool.size() < 16) { g_frame_pool.push_back(f); return BORB_OK; }
+    if (g_frame_pool.size() < 1024) { g_frame_pool.push_back(f); return BORB_OK; }     // ~170 KB each; a multi-stream server keeps hundreds alive
     cudaSetDevice(f->device);
     cudaEventSynchronize(f->ready);
     cudaFree(f->block);
@@ -486,9 +486,10 @@ borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F,
     // device-only scratch
     reserve_grid(st, I, fs);
     const size_t o_cand = st.reserve((size_t)P->n * I.n * 4), o_cc = st.reserve((size_t)P->n * 4);
-    const size_t o_match = st.reserve((size_t)P->n * 4), o_nm = st.reserve(16);
+    const size_t o_match = st.reserve((size_t)P->n * 4 + 16), o_nm = o_match + (size_t)P->n * 4;      // results contiguous: one D2H
     const size_t total = st.off;
     st.off = input_end;
+    if ((s = ensure_out(m, (size_t)P->n * 4 + 16)) != BORB_OK) return s;
     if ((s = commit(st, total)) != BORB_OK) return s;
     uint8_t* b = m->arena;
     ProjArgs A{};
@@ -501,9 +502,10 @@ borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F,
     A.mode = 0;
     m->launches += launch_projection(A, (int32_t*)(b + o_match), (int*)(b + o_nm), m->stream);
     BORB_CUDA(cudaGetLastError());
-    BORB_CUDA(cudaMemcpyAsync(match_feat, b + o_match, (size_t)P->n * 4, cudaMemcpyDeviceToHost, m->stream));
-    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
+    BORB_CUDA(cudaMemcpyAsync(m->h_out, b + o_match, (size_t)P->n * 4 + 4, cudaMemcpyDeviceToHost, m->stream));    // pinned landing buffer
     BORB_CUDA(cudaStreamSynchronize(m->stream));
+    std::memcpy(match_feat, m->h_out, (size_t)P->n * 4);
+    std::memcpy(n_matches, m->h_out + (size_t)P->n * 4, 4);
     return BORB_OK;
 }
 
@@ -578,9 +580,12 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     const size_t o_px = st.reserve((size_t)nq * 4), o_py = st.reserve((size_t)nq * 4), o_pxr = st.reserve((size_t)nq * 4), o_rad = st.reserve((size_t)nq * 4);
     const size_t o_ang = st.reserve((size_t)nq * 4), o_minl = st.reserve((size_t)nq * 4), o_maxl = st.reserve((size_t)nq * 4), o_val = st.reserve((size_t)nq);
     const size_t o_cand = st.reserve((size_t)nq * I.n * 4), o_cc = st.reserve((size_t)nq * 4);
-    const size_t o_state = st.reserve((size_t)(I.n > nq ? I.n : nq) * 4), o_evi = st.reserve((size_t)nq * 4), o_evb = st.reserve((size_t)nq), o_nm = st.reserve(16);
+    const size_t n_state = (size_t)(I.n > nq ? I.n : nq);
+    const size_t o_state = st.reserve(n_state * 4 + 16), o_nm = o_state + n_state * 4;       // results contiguous: one D2H
+    const size_t o_evi = st.reserve((size_t)nq * 4), o_evb = st.reserve((size_t)nq);
     const size_t total = st.off;
     st.off = input_end;
+    if ((s = ensure_out(m, n_state * 4 + 16)) != BORB_OK) return s;
     if ((s = commit(st, total)) != BORB_OK) return s;
     uint8_t* b = m->arena;
     ProjArgs A{};
@@ -617,11 +622,16 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     BORB_CUDA(cudaGetLastError());
     if (Q.to_aux) {
         BORB_CUDA(cudaMemcpyAsync(m->aux + Q.aux_off, b + o_state, (size_t)n_out * 4, cudaMemcpyDeviceToDevice, m->stream));
-    } else {
-        BORB_CUDA(cudaMemcpyAsync(state, b + o_state, (size_t)n_out * 4, cudaMemcpyDeviceToHost, m->stream));
+        BORB_CUDA(cudaMemcpyAsync(m->h_out, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
+        BORB_CUDA(cudaStreamSynchronize(m->stream));
+        std::memcpy(n_matches, m->h_out, 4);
+        return BORB_OK;
     }
-    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, 4, cudaMemcpyDeviceToHost, m->stream));
+    // state and the match count sit next to each other only when n_out == n_state; copy the span that covers both
+    BORB_CUDA(cudaMemcpyAsync(m->h_out, b + o_state, n_state * 4 + 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaStreamSynchronize(m->stream));
+    std::memcpy(state, m->h_out, (size_t)n_out * 4);
+    std::memcpy(n_matches, m->h_out + n_state * 4, 4);
     return BORB_OK;
 }
 
@@ -993,8 +1003,9 @@ struct borb_kfdb {
         uint8_t* block = nullptr;
         KfStream stream{};
         BowDev bow{nullptr, nullptr, 0};
-        uint8_t* d_hasmp = nullptr;          // m bytes inside block (row order)
-        std::vector<uint16_t> orig;          // host copy of the row -> feature permutation (borb_kfdb_set_has_mp)
+        uint8_t* d_meta = nullptr;           // m x 8 bytes inside block (row order)
+        std::vector<uint16_t> orig;          // host copy of the row -> feature permutation
+        std::vector<uint32_t> meta;          // host copy of the row records (borb_kfdb_set_has_mp rewrites the flag)
         int n = 0;
         bool alive = false;
     };
@@ -1062,8 +1073,7 @@ borb_status borb_kfdb_add(borb_kfdb* db, const borb_keyframe_view* kf, const uin
     // one device block per keyframe: [node | start | orig | angle | hasmp | desc (rows in FeatureVector order) | bow words | bow values]
     size_t off = 0;
     auto put = [&](size_t bytes) { off = (off + 255) & ~size_t(255); const size_t o = off; off += bytes; return o; };
-    const size_t o_node = put((size_t)nn * 4), o_start = put((size_t)(nn + 1) * 4), o_orig = put((size_t)m * 2), o_ang = put((size_t)m * 4);
-    const size_t o_hm = put((size_t)m), o_desc = put((size_t)m * 32);
+    const size_t o_node = put((size_t)nn * 4), o_start = put((size_t)(nn + 1) * 4), o_meta = put((size_t)m * 8), o_desc = put((size_t)m * 32);
     const size_t o_bw = put((size_t)n_bow * 4), o_bv = put((size_t)n_bow * 8);
     const size_t total = off + 256;
     std::vector<uint8_t> h(total, 0);
@@ -1072,13 +1082,14 @@ borb_status borb_kfdb_add(borb_kfdb* db, const borb_keyframe_view* kf, const uin
     if (nn) {
         std::memcpy(&h[o_node], kf->fv.node_id, (size_t)nn * 4);
         std::memcpy(&h[o_start], kf->fv.start, (size_t)(nn + 1) * 4);
-        uint16_t* orig = reinterpret_cast<uint16_t*>(&h[o_orig]);
-        float* ang = reinterpret_cast<float*>(&h[o_ang]);
+        uint32_t* meta = reinterpret_cast<uint32_t*>(&h[o_meta]);
+        e.meta.resize((size_t)m * 2);
         for (int r = 0; r < m; r++) {
             const uint32_t f = kf->fv.feat_idx[r];
-            orig[r] = (uint16_t)f; e.orig[r] = (uint16_t)f;
-            ang[r] = kf->keys_un[f].angle;
-            h[o_hm + r] = kf->has_mp ? kf->has_mp[f] : 0;
+            e.orig[r] = (uint16_t)f;
+            meta[2 * r] = f | ((kf->has_mp && kf->has_mp[f]) ? 0x10000u : 0u);
+            std::memcpy(&meta[2 * r + 1], &kf->keys_un[f].angle, 4);
+            e.meta[2 * r] = meta[2 * r]; e.meta[2 * r + 1] = meta[2 * r + 1];
             std::memcpy(&h[o_desc + (size_t)r * 32], kf->desc + (size_t)f * 32, 32);
         }
     }
@@ -1086,10 +1097,10 @@ borb_status borb_kfdb_add(borb_kfdb* db, const borb_keyframe_view* kf, const uin
     BORB_CUDA(cudaMalloc(&e.block, total));
     BORB_CUDA(cudaMemcpy(e.block, h.data(), total, cudaMemcpyHostToDevice));
     uint8_t* b = e.block;
-    e.stream.node = (const uint32_t*)(b + o_node); e.stream.start = (const int32_t*)(b + o_start); e.stream.orig = (const uint16_t*)(b + o_orig);
-    e.stream.angle = (const float*)(b + o_ang); e.stream.hasmp = b + o_hm; e.stream.desc = b + o_desc;
+    e.stream.node = (const uint32_t*)(b + o_node); e.stream.start = (const int32_t*)(b + o_start); e.stream.meta = (const uint2*)(b + o_meta);
+    e.stream.desc = b + o_desc;
     e.stream.nn = nn; e.stream.m = m; e.stream.n = kf->n; e.stream.pad = 0;
-    e.d_hasmp = b + o_hm;
+    e.d_meta = b + o_meta;
     e.n = kf->n;
     e.bow.word = (const uint32_t*)(b + o_bw); e.bow.value = (const double*)(b + o_bv); e.bow.n = n_bow;
     e.alive = true;
@@ -1118,10 +1129,10 @@ borb_status borb_kfdb_set_has_mp(borb_kfdb* db, int32_t slot, const uint8_t* has
     std::lock_guard<std::mutex> lk(db->mu);
     if (slot < 0 || slot >= (int)db->entries.size() || !db->entries[slot].alive) { set_error("bad keyframe slot"); return BORB_ERR_INVALID_ARG; }
     BORB_CUDA(cudaSetDevice(db->device));
-    const borb_kfdb::Entry& e = db->entries[slot];
-    std::vector<uint8_t> rows(e.orig.size());
-    for (size_t r = 0; r < rows.size(); r++) rows[r] = has_mp[e.orig[r]];
-    if (!rows.empty()) BORB_CUDA(cudaMemcpy(e.d_hasmp, rows.data(), rows.size(), cudaMemcpyHostToDevice));
+    borb_kfdb::Entry& e = db->entries[slot];
+    for (size_t r = 0; r < e.orig.size(); r++) e.meta[2 * r] = (uint32_t)e.orig[r] | (has_mp[e.orig[r]] ? 0x10000u : 0u);
+    BORB_CUDA(cudaDeviceSynchronize());           // a search enqueued under the mutex may still be reading the records
+    if (!e.meta.empty()) BORB_CUDA(cudaMemcpy(e.d_meta, e.meta.data(), e.meta.size() * 4, cudaMemcpyHostToDevice));
     return BORB_OK;
 }
 
@@ -1287,7 +1298,7 @@ borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, i
         if (dense) BORB_CUDA(cudaMemsetAsync(b + o_dense, 0xFF, (size_t)n_kf * dense_stride * 4, m->stream));
         BowDbArgs A{};
         A.table = db->d_stream; A.slots = slots ? (const int32_t*)(b + o_sl) : nullptr; A.n_kf = n_kf;
-        const int warps = db->n_sm * 2 * 16;
+        const int warps = db->n_sm * 3 * 8;
         int parts = (4 * warps + n_kf - 1) / n_kf;
         A.parts = parts < 1 ? 1 : (parts > 32 ? 32 : parts);
         A.frame_block = b + o_fb; A.frame_bytes = (int)fbytes;

@@ -26,7 +26,7 @@ namespace borb {
 
 namespace {
 
-constexpr int BDB_WARPS = 16;
+constexpr int BDB_WARPS = 8;                  // 3 CTAs of 8 warps per SM: 85 registers per thread keep the loop invariants out of the distance loop
 constexpr int BDB_ROWS = 32;                 // keyframe rows per chunk (per-warp row buffer)
 constexpr int BDB_DCAP = 512;                // distance-matrix entries per warp
 constexpr int BDB_CLAIM_WORDS = MATCH_MAX_FEATURES / 32;
@@ -79,7 +79,7 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
 struct FrameBlockHdr { int32_t nn, m, n, off_node, off_start, off_orig, off_angle, off_desc, bytes, pad[7]; };
 
 template <bool CSA>
-__global__ void __launch_bounds__(32 * BDB_WARPS, 2) bowdb_match_kernel(BowDbArgs A) {
+__global__ void __launch_bounds__(32 * BDB_WARPS, 3) bowdb_match_kernel(BowDbArgs A) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) unsigned long long bar;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
@@ -174,9 +174,10 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, 2) bowdb_match_kernel(BowDbArg
                     // ---- keyframe rows of this chunk: one coalesced 16-byte load per lane and half row
                     const uint4* src4 = reinterpret_cast<const uint4*>(K.desc) + (size_t)(qs + r0) * 2;
                     for (int e = lane; e < nr * 2; e += 32) Q[e] = src4[e];
-                    const bool ok_l = lane < nr && K.hasmp[qs + r0 + lane] != 0;          // good MapPoint (:196-202)
-                    const int orig_l = lane < nr ? (int)K.orig[qs + r0 + lane] : 0;
-                    const float ang_l = (ok_l && A.check_ori) ? K.angle[qs + r0 + lane] : 0.f;
+                    const uint2 meta = lane < nr ? K.meta[qs + r0 + lane] : make_uint2(0u, 0u);   // feature index | good-MapPoint flag << 16, angle
+                    const bool ok_l = (meta.x >> 16) != 0;                                 // good MapPoint (:196-202)
+                    const int orig_l = (int)(meta.x & 0xFFFFu);
+                    const float ang_l = __uint_as_float(meta.y);
                     const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok_l);
                     if (ok_l) R[__popc(okm & ((1u << lane) - 1))] = (uint8_t)lane;
                     const int nv = __popc(okm);
@@ -188,10 +189,16 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, 2) bowdb_match_kernel(BowDbArg
                         unsigned low = 0;
                         if (!direct) {
                             if (ntile == 1) {
+                                // lanes p >= nt hold an all-zero column: they compute into the row's padding (stride P2) and never flag
+                                const uint32_t colmask = p < nt ? 0xFFFFFFFFu : 0u;
+                                uint16_t* Dp = D + p;
+                                const uint8_t* Rv = R + v0;
+#pragma unroll 2
                                 for (int v = g; v < ndr; v += G) {
-                                    const int row = R[v0 + v];
+                                    const int row = Rv[v];
                                     const int d = ham256<CSA>(Q[row * 2], Q[row * 2 + 1], t0, t1);
-                                    if (p < nt) { D[(v << lp) + p] = (uint16_t)d; if (d <= TH_LOW) low |= 1u << v; }
+                                    Dp[v << lp] = (uint16_t)d;
+                                    low |= (d <= TH_LOW ? (1u << v) : 0u) & colmask;
                                 }
                             } else {
                                 for (int c = 0; c < ntile; c++) {
@@ -313,7 +320,7 @@ int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, bool csa, int n_sm, cu
     const size_t smem = bowdb_smem_bytes(A.frame_bytes, A.frame_in_smem != 0);
     const int items = A.n_kf * A.parts;
     int ctas = (items + BDB_WARPS - 1) / BDB_WARPS;
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int per_sm = smem <= 74 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
     if (ctas > n_sm * per_sm) ctas = n_sm * per_sm;
     if (ctas < 1) ctas = 1;
     if (csa) {

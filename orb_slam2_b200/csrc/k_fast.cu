@@ -119,63 +119,98 @@ __device__ __forceinline__ uint32_t score_word(const uint32_t (&R0)[7], const ui
 
 struct TMaps { CUtensorMap m[BORB_MAX_LEVELS]; };
 
+struct TileDesc { int img, l, ncell, x0, x1, y0, y1, pad; };
+
+// Persistent CTAs: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (a tile = up to 4 whole cells of one cell
+// row of one level of one image) with a TWO-STAGE TMA ring: while the 8 warps work on tile i in tile[s], thread 0 has already
+// decoded tile i+1 and started its cp.async.bulk.tensor into tile[s^1] (one mbarrier per stage, phase parity (i>>1)&1).  The
+// per-CTA prologue (level lookup, cell geometry, tensor-map fetch) and the exposed TMA latency, ~35 % of the stall samples of
+// the one-tile-per-CTA kernel (profiles/r02_fast_ablation.md), are paid once per CTA / hidden behind the previous tile.
 __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ TMaps tm,
-                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_cnt) {
-    __shared__ __align__(128) uint8_t tile[TROWS * TP];
-    __shared__ __align__(16) uint8_t score[60 * TP];     // S(p) in TILE coordinates (same columns as `tile`)
+                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_cnt, int n_images) {
+    extern __shared__ __align__(128) uint8_t tiles_dyn[];   // two TMA stages of TROWS x TP bytes (dynamic: static shared memory is capped at 48 KB)
+    uint8_t (*tiles)[TROWS * TP] = reinterpret_cast<uint8_t (*)[TROWS * TP]>(tiles_dyn);
+    __shared__ __align__(16) uint8_t score[60 * TP];     // S(p) in TILE coordinates (same columns as the tile)
     __shared__ uint16_t queue[QCAP];                      // corners: row << 8 | tile column
     __shared__ uint16_t wqueue[60 * 32];                  // words (row << 5 | lane) deferred to the dense scoring pass
-    __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ TileDesc desc[2];
     __shared__ uint32_t scoredRow[60];                    // per tile row: lanes whose word has an exact score in `score`
     __shared__ int qn, wqn, needB;
     __shared__ int cellHasIni[128 / 30 + 1];
     __shared__ uint8_t cellOf[128];
 
-    const int img = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blkBase) l++;
-    const LevelGeom& L = g.lv[l];
-    const int local = blockIdx.x - L.blkBase;
-    const int cellRow = local / L.blkCols, blkCol = local - cellRow * L.blkCols;
-    const int cell0 = blkCol * L.cellsPerBlk;
-    const int ncell = min(L.cellsPerBlk, L.nCols - cell0);
-    const int x0 = EDGE + cell0 * L.wCell, x1 = min(x0 + ncell * L.wCell, L.w - EDGE);
-    const int y0 = EDGE + cellRow * L.hCell, y1 = min(y0 + L.hCell, L.h - EDGE);
-    if (x0 >= x1 || y0 >= y1) return;
-    const int tw = x1 - x0, th = y1 - y0;
     const int tid = threadIdx.x;
     const int lane = tid & 31, wrp = tid >> 5;
-
-    // ---- 0. TMA: tile rows y0-3 .. y0+hCell+2, columns xs .. xs+159 of image `img`, level l
-    const int xs = (x0 - 4) & ~15;          // 16-byte aligned box start (TMA requirement)
-    const int off = x0 - xs;                // tile column of domain pixel xx = 0   (4..19)
+    const int total = g.fast_blocks * n_images;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
+    // producer (thread 0): decode tile t into desc[st] and start its TMA load — tile rows y0-3 .. y0+hCell+2, columns xs .. xs+159
+    auto produce = [&](int t, int st) {
+        TileDesc d;
+        d.img = t / g.fast_blocks;
+        const int blk = t - d.img * g.fast_blocks;
+        int l = 0;
+        while (l + 1 < g.nlevels && blk >= g.lv[l + 1].blkBase) l++;
+        const LevelGeom& L = g.lv[l];
+        const int local = blk - L.blkBase;
+        const int cellRow = local / L.blkCols, blkCol = local - cellRow * L.blkCols;
+        const int cell0 = blkCol * L.cellsPerBlk;
+        d.l = l; d.pad = 0;
+        d.ncell = min(L.cellsPerBlk, L.nCols - cell0);
+        d.x0 = EDGE + cell0 * L.wCell; d.x1 = min(d.x0 + d.ncell * L.wCell, L.w - EDGE);
+        d.y0 = EDGE + cellRow * L.hCell; d.y1 = min(d.y0 + L.hCell, L.h - EDGE);
+        desc[st] = d;
+        if (d.x0 >= d.x1 || d.y0 >= d.y1) {           // degenerate strip: nothing to load, complete the phase
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[st])) : "memory");
+            return;
+        }
+        const int xs = (d.x0 - 4) & ~15;              // 16-byte aligned box start (TMA requirement)
         const uint32_t bytes = (uint32_t)TP * (uint32_t)(L.hCell + 6);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[st])), "r"(bytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tm.m[l])), "r"(xs), "r"(y0 - 3), "r"(img), "r"(smem_u32(&bar))
+            ::"r"(smem_u32(tiles[st])), "l"(reinterpret_cast<uint64_t>(&tm.m[l])), "r"(xs), "r"(d.y0 - 3), "r"(d.img), "r"(smem_u32(&bar[st]))
+            : "memory");
+    };
+    if (tid == 0 && (int)blockIdx.x < total) produce(blockIdx.x, 0);
+
+    for (int it = 0;; it++) {
+    const int tcur = blockIdx.x + it * gridDim.x;
+    if (tcur >= total) break;
+    const int stg = it & 1;
+    // tiles[stg^1] / desc[stg^1] were last read in iteration it-1, which ended with the __syncthreads at the bottom of this loop
+    if (tid == 0 && tcur + (int)gridDim.x < total) produce(tcur + gridDim.x, stg ^ 1);
+    {
+        const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "FAST_TMA_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra FAST_TMA_DONE;\n"
+            "bra FAST_TMA_WAIT;\n"
+            "FAST_TMA_DONE:\n"
+            "}\n" ::"r"(smem_u32(&bar[stg])), "r"(parity)
             : "memory");
     }
-    // overlap with the copy: bookkeeping
+    [&]() {
+    const TileDesc TD = desc[stg];
+    const uint8_t* tile = tiles[stg];
+    const int img = TD.img, l = TD.l, ncell = TD.ncell;
+    const LevelGeom& L = g.lv[l];
+    const int x0 = TD.x0, x1 = TD.x1, y0 = TD.y0, y1 = TD.y1;
+    if (x0 >= x1 || y0 >= y1) return;
+    const int tw = x1 - x0, th = y1 - y0;
+    const int xs = (x0 - 4) & ~15;
+    const int off = x0 - xs;                // tile column of domain pixel xx = 0   (4..19)
     if (tid < 128 / 30 + 1) cellHasIni[tid] = 0;
     if (tid < 128) cellOf[tid] = (uint8_t)(tid / L.wCell);
     if (tid == 0) { qn = 0; wqn = 0; needB = 0; }
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "FAST_TMA_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@p bra FAST_TMA_DONE;\n"
-        "bra FAST_TMA_WAIT;\n"
-        "FAST_TMA_DONE:\n"
-        "}\n" ::"r"(smem_u32(&bar))
-        : "memory");
     __syncthreads();
     if (g.fast_mode == 1) {                 // ablation: tile load only (one word per thread consumed so the copy is observed)
         if (reinterpret_cast<const uint32_t*>(tile)[tid] == 0x12345678u && cand_cnt[0] == -1) cand[0] = 1;
@@ -435,6 +470,9 @@ __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Ge
         __syncthreads();
         emit(nq);
     }
+    }();
+    __syncthreads();                       // every warp is done with tiles[stg], the score map and the queues
+    }
 }
 
 // ---- host: tensor maps (one per level: 3-D {x, y, image} view of the pyramid buffer)
@@ -476,8 +514,12 @@ borb_status build_fast_tmaps(const Geometry& g, const Workspace& ws, void* out_t
 size_t fast_tmaps_bytes() { return sizeof(TMaps); }
 
 int launch_fast(const Geometry& g, const Workspace& ws, int n_images, cudaStream_t s) {
-    dim3 grid(g.fast_blocks, n_images);
-    fast_kernel<<<grid, 256, 0, s>>>(g, *reinterpret_cast<const TMaps*>(ws.fast_tmaps), ws.cand, ws.cand_cnt);
+    static int n_sm = 0;
+    if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm < 1) n_sm = 148; }
+    const int total = g.fast_blocks * n_images;
+    const int grid = total < n_sm * 4 ? total : n_sm * 4;           // persistent: 4 resident CTAs per SM walk the tiles
+    allow_max_smem((const void*)fast_kernel);
+    if (grid > 0) fast_kernel<<<grid, 256, 2 * TROWS * TP, s>>>(g, *reinterpret_cast<const TMaps*>(ws.fast_tmaps), ws.cand, ws.cand_cnt, n_images);
     return 1;
 }
 
