@@ -45,6 +45,7 @@ namespace {
 constexpr int TP = 160;                 // TMA box width == smem tile pitch (bytes).  TMA needs a 16-byte aligned start
                                         // column, so the box starts at xs = (x0-4) & ~15 and domain px xx sits at column xx+off
 constexpr int TROWS = 66;               // hCell <= 60, + 3 halo rows above and below
+constexpr int TSTAGE = (TROWS * TP + 127) & ~127;   // bytes per TMA stage: the shared-memory destination of cp.async.bulk.tensor must be 128-byte aligned
 constexpr int QCAP = 60 * 128;          // queue capacity >= every pixel of the largest tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,7 +130,7 @@ struct TileDesc { int img, l, ncell, x0, x1, y0, y1, pad; };
 __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ TMaps tm,
                                                    uint32_t* __restrict__ cand, int* __restrict__ cand_cnt, int n_images) {
     extern __shared__ __align__(128) uint8_t tiles_dyn[];   // two TMA stages of TROWS x TP bytes (dynamic: static shared memory is capped at 48 KB)
-    uint8_t (*tiles)[TROWS * TP] = reinterpret_cast<uint8_t (*)[TROWS * TP]>(tiles_dyn);
+    uint8_t (*tiles)[TSTAGE] = reinterpret_cast<uint8_t (*)[TSTAGE]>(tiles_dyn);
     __shared__ __align__(16) uint8_t score[60 * TP];     // S(p) in TILE coordinates (same columns as the tile)
     __shared__ uint16_t queue[QCAP];                      // corners: row << 8 | tile column
     __shared__ uint16_t wqueue[60 * 32];                  // words (row << 5 | lane) deferred to the dense scoring pass
@@ -519,7 +520,7 @@ int launch_fast(const Geometry& g, const Workspace& ws, int n_images, cudaStream
     const int total = g.fast_blocks * n_images;
     const int grid = total < n_sm * 4 ? total : n_sm * 4;           // persistent: 4 resident CTAs per SM walk the tiles
     allow_max_smem((const void*)fast_kernel);
-    if (grid > 0) fast_kernel<<<grid, 256, 2 * TROWS * TP, s>>>(g, *reinterpret_cast<const TMaps*>(ws.fast_tmaps), ws.cand, ws.cand_cnt, n_images);
+    if (grid > 0) fast_kernel<<<grid, 256, 2 * TSTAGE, s>>>(g, *reinterpret_cast<const TMaps*>(ws.fast_tmaps), ws.cand, ws.cand_cnt, n_images);
     return 1;
 }
 
