@@ -90,18 +90,11 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 }  // namespace
 
-// v2 (round 2): the two windows a keypoint reads — 31 x 31 of the unblurred level for the moments, 39 x 39 of the blurred level for
-// the 512 rotated taps (|offset| <= 18) — are first staged into per-warp shared memory with aligned 8-byte row loads
-// (one L1 wavefront per few rows); the scattered byte taps then hit shared-memory banks instead of 16 x ~20 L1 wavefronts per
-// keypoint (the v1 kernel ran at 82 % of the L1 wavefront peak, profiles/r01_step_v6_ncu_summary.md).
-constexpr int DW_B = 48, DH_B = 39;      // blurred window: 39 rows x 48 bytes (39 px + up to 7 of alignment)
-constexpr int DW_U = 40, DH_U = 31;      // unblurred window: 31 rows x 40 bytes
-__global__ void __launch_bounds__(256, 6) describe_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ pyr,
+// 32 registers (8 CTAs/SM): the kernel is bound by gather latency and L1 wavefronts, occupancy pays (0.173 -> 0.150 ms)
+__global__ void __launch_bounds__(256, 8) describe_kernel(const __grid_constant__ Geometry g, const uint8_t* __restrict__ pyr,
                                                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ sel,
                                                        const int* __restrict__ sel_cnt, borb_keypoint* __restrict__ kps,
                                                        uint8_t* __restrict__ desc, int* __restrict__ nkp) {
-    __shared__ __align__(8) uint8_t win_b[8][DH_B * DW_B];
-    __shared__ __align__(8) uint8_t win_u[8][DH_U * DW_U];
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -128,31 +121,14 @@ __global__ void __launch_bounds__(256, 6) describe_kernel(const __grid_constant_
     // lane = column u of the 31x31 window; the disc is symmetric (umax[v] >= |u| <=> |v| <= umax[|u|]), so a lane's
     // rows are |v| <= vmax.  One multiply-add per pixel: acc += I * (v * 2^13 + 1) carries the column sum (< 2^13) in
     // the low bits and sum_v v*I above them; m10 = sum_u u * (column sum), m01 = sum_u sum_v v * I(u,v).
-    uint8_t* wb = win_b[threadIdx.x >> 5];
-    uint8_t* wu = win_u[threadIdx.x >> 5];
-    // stage both windows (rows are 128-byte pitched and every level starts 128-byte aligned: 8-byte aligned loads)
-    const int xb8 = (px - 19) & ~7, xu8 = (px - HALF_PATCH) & ~7;
-    {
-        const uint8_t* sb = blur + lvl_off + (size_t)(py - 19) * pitch + xb8;
-        for (int e = lane; e < DH_B * (DW_B / 8); e += 32) {
-            const int r = e / (DW_B / 8), w = e - r * (DW_B / 8);
-            *reinterpret_cast<uint2*>(wb + r * DW_B + w * 8) = *reinterpret_cast<const uint2*>(sb + (size_t)r * pitch + w * 8);
-        }
-        const uint8_t* su = pyr + lvl_off + (size_t)(py - HALF_PATCH) * pitch + xu8;
-        for (int e = lane; e < DH_U * (DW_U / 8); e += 32) {
-            const int r = e / (DW_U / 8), w = e - r * (DW_U / 8);
-            *reinterpret_cast<uint2*>(wu + r * DW_U + w * 8) = *reinterpret_cast<const uint2*>(su + (size_t)r * pitch + w * 8);
-        }
-    }
-    __syncwarp();
     const int u = lane - HALF_PATCH;
     const int vmax = lane < 31 ? g.umax[u < 0 ? -u : u] : -1;
-    const uint8_t* col = wu + (px - HALF_PATCH - xu8) + (lane < 31 ? lane : 0);         // top of this lane's column in the staged window
+    const uint8_t* col = pyr + lvl_off + (size_t)(py - HALF_PATCH) * pitch + (px + u);   // top of this lane's column
     int acc = 0;
 #pragma unroll
     for (int vv = -HALF_PATCH; vv <= HALF_PATCH; vv++) {
         if ((vv < 0 ? -vv : vv) <= vmax) acc += (int)*col * (vv * 8192 + 1);
-        col += DW_U;
+        col += pitch;
     }
     const int colsum = acc & 8191;
     int m01 = acc >> 13;                                   // exact: 0 <= colsum < 2^13
@@ -167,7 +143,7 @@ __global__ void __launch_bounds__(256, 6) describe_kernel(const __grid_constant_
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float t = __fmul_rn(angle, factorPI);
     const float a = glibc_sincosf(t, 1), b = glibc_sincosf(t, 0);
-    const uint8_t* cb = wb + 19 * DW_B + (px - xb8);                                    // the keypoint inside the staged blurred window
+    const uint8_t* cb = blur + lvl_off + (size_t)py * pitch + px;
     unsigned mine = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -178,7 +154,7 @@ __global__ void __launch_bounds__(256, 6) describe_kernel(const __grid_constant_
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = cb[r0 * DW_B + q0], t1 = cb[r1 * DW_B + q1];
+        const int t0 = cb[r0 * pitch + q0], t1 = cb[r1 * pitch + q1];
         const unsigned word = __ballot_sync(0xFFFFFFFFu, t0 < t1);
         if (lane == j) mine = word;
     }
