@@ -120,7 +120,8 @@ struct BowDev {                   // one keyframe's BowVector in the device-resi
 struct KfStream {                  // one keyframe of the device-resident database, features permuted into FeatureVector order
     const uint32_t* node;         // nn node ids, ascending
     const int32_t* start;         // nn + 1 row offsets
-    const uint2* meta;            // m rows: x = feature index (mFeatVec order: node, then feature index) | good-MapPoint flag << 16,
+    const uint2* meta;            // m rows: x = feature index (mFeatVec order: node, then feature index) | good-MapPoint flag << 16
+                                  //             | index of the row's node in node[] << 17 (nn <= MATCH_MAX_FEATURES < 2^15),
                                   //         y = bits of mvKeysUn[feature].angle
     const uint8_t* desc;          // m x 32, 16-byte aligned
     int nn, m, n, pad;
@@ -130,7 +131,7 @@ struct KfStream {                  // one keyframe of the device-resident databa
 struct BowDbArgs {                // bowdb_match_kernel (k_bowdb.cu)
     const KfStream* table;        // one entry per database slot (nn = 0: erased)
     const int32_t* slots;         // n_kf slots to search, or null = slots 0..n_kf-1
-    int n_kf, parts;              // work items = n_kf x parts (a keyframe's nodes are split into `parts` ranges)
+    int n_kf, n_items;            // keyframes to search; work items (frame node x keyframe range, the work list inside frame_block)
     const uint8_t* frame_block;   // packed query frame (FrameBlockHdr + sections), 16-byte aligned, frame_bytes % 16 == 0
     int frame_bytes, frame_in_smem;
     float nnratio;
@@ -200,7 +201,7 @@ void host_image_bounds(int w, int h, const borb_camera& c, float* b4);
 int launch_frame_build(const FrameJob* d_jobs, int n_jobs, int max_n, const borb_camera& cam, int mode, int depth_type, float depth_factor, int w,
                        int h, int out_cap, borb_keypoint* keys_out, float* ur_out, float* depth_out, cudaStream_t s);
 int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, bool csa, int n_sm, cudaStream_t s);
-size_t bowdb_smem_bytes(int frame_bytes, bool frame_in_smem);
+bool bowdb_frame_fits_smem(int frame_bytes);
 int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,
                          int32_t* n_pairs, cudaStream_t s);
 int launch_bow_transform(const VocDev& V, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight, int32_t* node,

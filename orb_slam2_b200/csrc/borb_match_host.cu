@@ -1084,10 +1084,12 @@ borb_status borb_kfdb_add(borb_kfdb* db, const borb_keyframe_view* kf, const uin
         std::memcpy(&h[o_start], kf->fv.start, (size_t)(nn + 1) * 4);
         uint32_t* meta = reinterpret_cast<uint32_t*>(&h[o_meta]);
         e.meta.resize((size_t)m * 2);
+        int a = 0;                                                     // node index of row r (rows are grouped by node)
         for (int r = 0; r < m; r++) {
+            while (a + 1 < nn && r >= kf->fv.start[a + 1]) a++;
             const uint32_t f = kf->fv.feat_idx[r];
             e.orig[r] = (uint16_t)f;
-            meta[2 * r] = f | ((kf->has_mp && kf->has_mp[f]) ? 0x10000u : 0u);
+            meta[2 * r] = f | ((kf->has_mp && kf->has_mp[f]) ? 0x10000u : 0u) | ((uint32_t)a << 17);
             std::memcpy(&meta[2 * r + 1], &kf->keys_un[f].angle, 4);
             e.meta[2 * r] = meta[2 * r]; e.meta[2 * r + 1] = meta[2 * r + 1];
             std::memcpy(&h[o_desc + (size_t)r * 32], kf->desc + (size_t)f * 32, 32);
@@ -1130,7 +1132,7 @@ borb_status borb_kfdb_set_has_mp(borb_kfdb* db, int32_t slot, const uint8_t* has
     if (slot < 0 || slot >= (int)db->entries.size() || !db->entries[slot].alive) { set_error("bad keyframe slot"); return BORB_ERR_INVALID_ARG; }
     BORB_CUDA(cudaSetDevice(db->device));
     borb_kfdb::Entry& e = db->entries[slot];
-    for (size_t r = 0; r < e.orig.size(); r++) e.meta[2 * r] = (uint32_t)e.orig[r] | (has_mp[e.orig[r]] ? 0x10000u : 0u);
+    for (size_t r = 0; r < e.orig.size(); r++) e.meta[2 * r] = (e.meta[2 * r] & ~0x10000u) | (has_mp[e.orig[r]] ? 0x10000u : 0u);
     BORB_CUDA(cudaDeviceSynchronize());           // a search enqueued under the mutex may still be reading the records
     if (!e.meta.empty()) BORB_CUDA(cudaMemcpy(e.d_meta, e.meta.data(), e.meta.size() * 4, cudaMemcpyHostToDevice));
     return BORB_OK;
@@ -1213,7 +1215,7 @@ borb_status borb_debug_set_bow_csa(int on) { g_bow_csa.store(on ? 1 : 0); return
 
 namespace {
 
-struct FrameBlockHdrHost { int32_t nn, m, n, off_node, off_start, off_orig, off_angle, off_desc, bytes, pad[7]; };   // == FrameBlockHdr (k_bowdb.cu)
+struct FrameBlockHdrHost { int32_t nn, m, n, off_node, off_start, off_orig, off_angle, off_desc, bytes, np, off_pnode, off_pcs, off_pstart, pad[3]; };   // == FrameBlockHdr (k_bowdb.cu)
 
 // Packs the query frame into FeatureVector order (k_bowdb.cu: FrameBlockHdr + sections) inside `dst` (16-byte aligned).
 size_t frame_block_bytes(const borb_keyframe_view* f) {
@@ -1221,9 +1223,11 @@ size_t frame_block_bytes(const borb_keyframe_view* f) {
     size_t off = sizeof(FrameBlockHdrHost);
     auto put = [&](size_t bytes) { off = (off + 15) & ~size_t(15); off += bytes; };
     put((size_t)nn * 4); put((size_t)(nn + 1) * 4); put((size_t)m * 2); put((size_t)m * 4); put((size_t)m * 32);
+    put((size_t)nn * 4); put((size_t)nn * 4); put((size_t)(nn + 1) * 4);
     return (off + 15) & ~size_t(15);
 }
-void pack_frame_block(const borb_keyframe_view* f, uint8_t* dst) {
+// Returns the number of work items of the sweep over n_kf keyframes (k_bowdb.cu: an item = one frame node x a range of keyframes).
+int pack_frame_block(const borb_keyframe_view* f, int n_kf, uint8_t* dst) {
     const int nn = f->fv.n_nodes, m = nn > 0 ? f->fv.start[nn] : 0;
     FrameBlockHdrHost h{};
     size_t off = sizeof(FrameBlockHdrHost);
@@ -1231,8 +1235,8 @@ void pack_frame_block(const borb_keyframe_view* f, uint8_t* dst) {
     h.nn = nn; h.m = m; h.n = f->n;
     h.off_node = (int32_t)put((size_t)nn * 4); h.off_start = (int32_t)put((size_t)(nn + 1) * 4); h.off_orig = (int32_t)put((size_t)m * 2);
     h.off_angle = (int32_t)put((size_t)m * 4); h.off_desc = (int32_t)put((size_t)m * 32);
+    h.off_pnode = (int32_t)put((size_t)nn * 4); h.off_pcs = (int32_t)put((size_t)nn * 4); h.off_pstart = (int32_t)put((size_t)(nn + 1) * 4);
     h.bytes = (int32_t)((off + 15) & ~size_t(15));
-    std::memcpy(dst, &h, sizeof(h));
     if (nn) std::memcpy(dst + h.off_node, f->fv.node_id, (size_t)nn * 4);
     if (nn) std::memcpy(dst + h.off_start, f->fv.start, (size_t)(nn + 1) * 4);
     else { const int32_t z = 0; std::memcpy(dst + h.off_start, &z, 4); }
@@ -1244,6 +1248,29 @@ void pack_frame_block(const borb_keyframe_view* f, uint8_t* dst) {
         ang[r] = f->keys_un[j].angle;
         std::memcpy(dst + h.off_desc + (size_t)r * 32, f->desc + (size_t)j * 32, 32);
     }
+    // work list: non-empty nodes, widest bucket first (the long items start first); keyframes per item ~ 1 / nt^2 so that an
+    // item is a few hundred column-loop iterations whatever the bucket width (a keyframe's bucket of the node is about as
+    // full as the frame's)
+    int32_t* pnode = reinterpret_cast<int32_t*>(dst + h.off_pnode);
+    int32_t* pcs = reinterpret_cast<int32_t*>(dst + h.off_pcs);
+    int32_t* pstart = reinterpret_cast<int32_t*>(dst + h.off_pstart);
+    int np = 0;
+    for (int a = 0; a < nn; a++)
+        if (f->fv.start[a + 1] > f->fv.start[a]) pnode[np++] = a;
+    std::stable_sort(pnode, pnode + np, [&](int32_t x, int32_t y) { return f->fv.start[x + 1] - f->fv.start[x] > f->fv.start[y + 1] - f->fv.start[y]; });
+    int items = 0;
+    for (int p = 0; p < np; p++) {
+        const long long nt = f->fv.start[pnode[p] + 1] - f->fv.start[pnode[p]];
+        long long cs = 2560 / (nt * nt);
+        cs = cs < 1 ? 1 : (cs > 32 ? 32 : cs);            // one 32-lane batch of keyframes per item at most
+        pcs[p] = (int32_t)cs;
+        pstart[p] = items;
+        items += (int)((n_kf + cs - 1) / cs);
+    }
+    pstart[np] = items;
+    h.np = np;
+    std::memcpy(dst, &h, sizeof(h));
+    return items;
 }
 
 // Shared body of the two database searches.  dense != null: match[k * frame->n + j]; pairs != null: compact list.
@@ -1290,7 +1317,7 @@ borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, i
         if ((s = ensure_host(m, input_end)) != BORB_OK) return s;
         if ((s = ensure_arena(m, total)) != BORB_OK) return s;
         BORB_CUDA(cudaStreamSynchronize(m->stream));
-        pack_frame_block(frame, m->h_stage + o_fb);
+        const int n_items = pack_frame_block(frame, n_kf, m->h_stage + o_fb);
         if ((s = commit(st, total)) != BORB_OK) return s;
         b = m->arena;
         BORB_CUDA(cudaMemsetAsync(b + o_ctr, 0, 256, m->stream));
@@ -1298,11 +1325,9 @@ borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, i
         if (dense) BORB_CUDA(cudaMemsetAsync(b + o_dense, 0xFF, (size_t)n_kf * dense_stride * 4, m->stream));
         BowDbArgs A{};
         A.table = db->d_stream; A.slots = slots ? (const int32_t*)(b + o_sl) : nullptr; A.n_kf = n_kf;
-        const int warps = db->n_sm * 3 * 8;
-        int parts = (4 * warps + n_kf - 1) / n_kf;
-        A.parts = parts < 1 ? 1 : (parts > 32 ? 32 : parts);
+        A.n_items = n_items;
         A.frame_block = b + o_fb; A.frame_bytes = (int)fbytes;
-        A.frame_in_smem = bowdb_smem_bytes((int)fbytes, true) <= 200 * 1024 ? 1 : 0;
+        A.frame_in_smem = bowdb_frame_fits_smem((int)fbytes) ? 1 : 0;
         A.nnratio = nnratio; A.check_ori = check_ori;
         A.table_out = (uint32_t*)(b + o_tab); A.work_counter = (int*)(b + o_ctr);
         BowDbFinal F{};

@@ -26,11 +26,11 @@ namespace borb {
 
 namespace {
 
-constexpr int BDB_WARPS = 8;                  // 3 CTAs of 8 warps per SM: 85 registers per thread keep the loop invariants out of the distance loop
-constexpr int BDB_ROWS = 32;                 // keyframe rows per chunk (per-warp row buffer)
-constexpr int BDB_DCAP = 512;                // distance-matrix entries per warp
+constexpr int BDB_WARPS = 32;                 // one 1024-thread CTA per SM (64 registers): 32 warps share one copy of the query frame
+constexpr int BDB_CTAS = 1;
+constexpr int BDB_QCAP = 64;                  // pending-row ring per warp
 constexpr int BDB_CLAIM_WORDS = MATCH_MAX_FEATURES / 32;
-constexpr int BDB_WARP_BYTES = BDB_ROWS * 32 + BDB_DCAP * 2 + BDB_CLAIM_WORDS * 4 + 64;   // Q rows | D | claim bits | row list
+constexpr int BDB_WARP_BYTES = BDB_CLAIM_WORDS * 4 + 32 * 24 + BDB_QCAP * 48;   // claim bits | keyframe runs of the batch | pending rows (descriptor halves, meta)
 constexpr int HISTO_LENGTH = 30;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,29 +76,36 @@ __device__ __forceinline__ void three_maxima(const int* cnt, int& ind1, int& ind
 
 // Packed query frame (built by the host, borb_match_host.cu:pack_frame_block): header, then 16-byte aligned sections.
 //   node[nn] u32 ascending | start[nn+1] i32 | orig[m] u16 | angle[m] f32 | desc[m][32]     (m = features inside nodes)
-struct FrameBlockHdr { int32_t nn, m, n, off_node, off_start, off_orig, off_angle, off_desc, bytes, pad[7]; };
+//   work list (np = non-empty frame nodes, widest bucket first): pnode[np] i32 node index | pcs[np] i32 keyframes per item |
+//   pstart[np+1] i32 cumulative item count
+struct FrameBlockHdr { int32_t nn, m, n, off_node, off_start, off_orig, off_angle, off_desc, bytes, np, off_pnode, off_pcs, off_pstart, pad[3]; };
 
-template <bool CSA>
-__global__ void __launch_bounds__(32 * BDB_WARPS, 3) bowdb_match_kernel(BowDbArgs A) {
+struct KfRun { const uint2* meta; const uint4* desc; int rs, off; };     // rows rs.. of one keyframe's bucket; off = first row's rank in the batch
+
+// Work decomposition.  An ITEM is (frame node b, a range of keyframes): every row of the item's batch is matched against the
+// SAME nt columns (the frame features of node b), so the column loop has a warp-uniform trip count and warp-uniform
+// shared-memory addresses (one broadcast wavefront per load), and all 32 lanes hold a live row.  The number of keyframes per
+// item shrinks with nt^2 (the host's work list), widest buckets first, so the items are of similar cost.
+template <bool CSA, bool FSM>
+__global__ void __launch_bounds__(32 * BDB_WARPS, BDB_CTAS) bowdb_match_kernel(BowDbArgs A) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) unsigned long long bar;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
-    // ---- the query frame: one bulk copy per CTA, reused for every keyframe this CTA processes
-    const uint8_t* fb = A.frame_block;
-    size_t scratch0 = 0;
-    if (A.frame_in_smem) {
+    // ---- the query frame: one bulk copy per CTA, reused for every item this CTA processes
+    const uint8_t* fb = FSM ? sm : A.frame_block;
+    const size_t scratch0 = FSM ? (((size_t)A.frame_bytes + 127) & ~size_t(127)) : 0;
+    if (FSM) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"((uint32_t)A.frame_bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(sm)), "l"(reinterpret_cast<uint64_t>(A.frame_block)), "r"((uint32_t)A.frame_bytes), "r"(smem_u32(&bar))
                          : "memory");
         }
+        __syncthreads();
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -109,228 +116,253 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, 3) bowdb_match_kernel(BowDbArg
             "BOWDB_DONE:\n"
             "}\n" ::"r"(smem_u32(&bar))
             : "memory");
-        fb = sm;
-        scratch0 = ((size_t)A.frame_bytes + 127) & ~size_t(127);
     }
     const FrameBlockHdr* H = reinterpret_cast<const FrameBlockHdr*>(fb);
-    const int nnf = H->nn, mf = H->m;
+    const int mf = H->m, np = H->np;
     const uint32_t* fnode = reinterpret_cast<const uint32_t*>(fb + H->off_node);
     const int32_t* fstart = reinterpret_cast<const int32_t*>(fb + H->off_start);
     const float* fangle = reinterpret_cast<const float*>(fb + H->off_angle);
     const uint4* fdesc = reinterpret_cast<const uint4*>(fb + H->off_desc);
+    const int32_t* pnode = reinterpret_cast<const int32_t*>(fb + H->off_pnode);
+    const int32_t* pcs = reinterpret_cast<const int32_t*>(fb + H->off_pcs);
+    const int32_t* pstart = reinterpret_cast<const int32_t*>(fb + H->off_pstart);
 
     uint8_t* ws = sm + scratch0 + (size_t)wrp * BDB_WARP_BYTES;
-    uint4* Q = reinterpret_cast<uint4*>(ws);                                  // BDB_ROWS x 32 bytes
-    uint16_t* D = reinterpret_cast<uint16_t*>(ws + BDB_ROWS * 32);            // BDB_DCAP distances
-    uint32_t* claim = reinterpret_cast<uint32_t*>(ws + BDB_ROWS * 32 + BDB_DCAP * 2);
-    uint8_t* R = ws + BDB_ROWS * 32 + BDB_DCAP * 2 + BDB_CLAIM_WORDS * 4;    // valid rows of the chunk
+    uint32_t* claim = reinterpret_cast<uint32_t*>(ws);                                   // claimed columns when the bucket is wider than 32
+    KfRun* run = reinterpret_cast<KfRun*>(ws + BDB_CLAIM_WORDS * 4);                      // the <= 32 keyframes of the current batch
+    // ring of pending rows with a good MapPoint: descriptor halves and {row, run, meta.x, meta.y}
+    uint4* qd0 = reinterpret_cast<uint4*>(ws + BDB_CLAIM_WORDS * 4 + 32 * sizeof(KfRun));
+    uint4* qd1 = qd0 + BDB_QCAP;
+    int4* qm = reinterpret_cast<int4*>(qd1 + BDB_QCAP);
 
-    const int items = A.n_kf * A.parts;
+    const int items = pstart[np];
     while (true) {
         int it = 0;
         if (lane == 0) it = atomicAdd(A.work_counter, 1);
         it = __shfl_sync(0xFFFFFFFFu, it, 0);
         if (it >= items) break;
-        const int qi = it / A.parts, part = it - qi * A.parts;
-        const int slot = A.slots ? A.slots[qi] : qi;
-        const KfStream K = A.table[slot];
-        if (K.nn <= 0) continue;
-        const int a0 = (int)((long long)K.nn * part / A.parts), a1 = (int)((long long)K.nn * (part + 1) / A.parts);
-        uint32_t* out = A.table_out + (size_t)qi * mf;
-        for (int ab = a0; ab < a1; ab += 32) {
-            // ---- merge-join of the two FeatureVectors (:180-264): 32 keyframe nodes looked up at once
-            int fbn = -1, qs_l = 0, nq_l = 0;
-            if (ab + lane < a1) {
-                const uint32_t node = K.node[ab + lane];
-                qs_l = K.start[ab + lane];
-                nq_l = K.start[ab + lane + 1] - qs_l;
-                int lo = 0, hi = nnf;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (fnode[mid] < node) lo = mid + 1; else hi = mid; }
-                if (lo < nnf && fnode[lo] == node && nq_l > 0 && fstart[lo + 1] > fstart[lo]) fbn = lo;
-            }
-            unsigned found = __ballot_sync(0xFFFFFFFFu, fbn >= 0);
-            while (found) {
-                const int src = __ffs(found) - 1;
-                found &= found - 1;
-                const int b = __shfl_sync(0xFFFFFFFFu, fbn, src);
-                const int qs = __shfl_sync(0xFFFFFFFFu, qs_l, src), nq = __shfl_sync(0xFFFFFFFFu, nq_l, src);
-                const int ts = fstart[b], nt = fstart[b + 1] - ts;
-                // column geometry: one tile of P2 <= 32 columns (G = 32 / P2 row groups), or ntile tiles of 32
-                const int ntile = (nt + 31) >> 5;
-                const int lp = nt <= 1 ? 0 : (nt > 16 ? 5 : 32 - __clz(nt - 1));   // log2 of the padded tile width
-                const int P2 = 1 << lp;
-                const int G = ntile == 1 ? 32 >> lp : 1;
-                const int g = ntile == 1 ? lane >> lp : 0, p = ntile == 1 ? (lane & (P2 - 1)) : lane;
-                const int stride = ntile == 1 ? P2 : ntile * 32;
-                const bool direct = stride > BDB_DCAP;                     // bucket wider than the matrix: rows evaluated one by one
-                const int DR = direct ? 1 : (ntile == 1 ? min(32, BDB_DCAP >> lp) : min(32, BDB_DCAP / stride));   // rows per distance pass
-                uint32_t claimed = 0;                                      // ntile == 1: claimed columns of this unit
-                if (ntile > 1) { for (int w = lane; w < ntile; w += 32) claim[w] = 0; }
-                uint4 t0 = make_uint4(0, 0, 0, 0), t1 = t0;
-                if (ntile == 1 && p < nt) { t0 = fdesc[(size_t)(ts + p) * 2]; t1 = fdesc[(size_t)(ts + p) * 2 + 1]; }
-                for (int r0 = 0; r0 < nq; r0 += BDB_ROWS) {
-                    const int nr = min(BDB_ROWS, nq - r0);
-                    __syncwarp();
-                    // ---- keyframe rows of this chunk: one coalesced 16-byte load per lane and half row
-                    const uint4* src4 = reinterpret_cast<const uint4*>(K.desc) + (size_t)(qs + r0) * 2;
-                    for (int e = lane; e < nr * 2; e += 32) Q[e] = src4[e];
-                    const uint2 meta = lane < nr ? K.meta[qs + r0 + lane] : make_uint2(0u, 0u);   // feature index | good-MapPoint flag << 16, angle
-                    const bool ok_l = (meta.x >> 16) != 0;                                 // good MapPoint (:196-202)
-                    const int orig_l = (int)(meta.x & 0xFFFFu);
-                    const float ang_l = __uint_as_float(meta.y);
-                    const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok_l);
-                    if (ok_l) R[__popc(okm & ((1u << lane) - 1))] = (uint8_t)lane;
-                    const int nv = __popc(okm);
-                    __syncwarp();
-                    for (int v0 = 0; v0 < nv; v0 += DR) {
-                        const int ndr = min(DR, nv - v0);
-                        // ---- distances; `low` collects the rows that have a distance <= TH_LOW at all: a row without one can neither
-                        //      match nor claim (:226), so the in-order replay below only visits those
-                        unsigned low = 0;
-                        if (!direct) {
-                            if (ntile == 1) {
-                                // lanes p >= nt hold an all-zero column: they compute into the row's padding (stride P2) and never flag
-                                const uint32_t colmask = p < nt ? 0xFFFFFFFFu : 0u;
-                                uint16_t* Dp = D + p;
-                                const uint8_t* Rv = R + v0;
-#pragma unroll 2
-                                for (int v = g; v < ndr; v += G) {
-                                    const int row = Rv[v];
-                                    const int d = ham256<CSA>(Q[row * 2], Q[row * 2 + 1], t0, t1);
-                                    Dp[v << lp] = (uint16_t)d;
-                                    low |= (d <= TH_LOW ? (1u << v) : 0u) & colmask;
-                                }
-                            } else {
-                                for (int c = 0; c < ntile; c++) {
-                                    const int col = c * 32 + lane;
-                                    uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
-                                    if (col < nt) { u0 = fdesc[(size_t)(ts + col) * 2]; u1 = fdesc[(size_t)(ts + col) * 2 + 1]; }
-                                    for (int v = 0; v < ndr; v++) {
-                                        const int row = R[v0 + v];
-                                        const int d = ham256<CSA>(Q[row * 2], Q[row * 2 + 1], u0, u1);
-                                        if (col < nt) { D[v * stride + col] = (uint16_t)d; if (d <= TH_LOW) low |= 1u << v; }
-                                    }
-                                }
-                            }
-                            low = __reduce_or_sync(0xFFFFFFFFu, low);
-                        } else low = 1u;
-                        __syncwarp();
-                        // ---- replay the candidate rows in order (:192-251)
-                        while (low) {
-                            const int v = __ffs(low) - 1;
-                            low &= low - 1;
-                            const int row = R[v0 + v];
-                            unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-                            if (ntile == 1) {
-                                if (lane < nt && !((claimed >> lane) & 1u)) k1 = ((unsigned)D[(v << lp) + lane] << 16) | (unsigned)lane;
-                            } else {
-                                for (int col = lane; col < nt; col += 32) {
-                                    if ((claim[col >> 5] >> (col & 31)) & 1u) continue;
-                                    unsigned dist;
-                                    if (!direct) dist = D[v * stride + col];
-                                    else dist = (unsigned)ham256<CSA>(Q[row * 2], Q[row * 2 + 1], fdesc[(size_t)(ts + col) * 2], fdesc[(size_t)(ts + col) * 2 + 1]);
-                                    const unsigned key = (dist << 16) | (unsigned)col;
-                                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
-                                }
-                            }
-                            const unsigned best = __reduce_min_sync(0xFFFFFFFFu, k1);
-                            if (best == 0xFFFFFFFFu) continue;
-                            const int bestDist1 = (int)(best >> 16);
-                            if (bestDist1 > TH_LOW) continue;                              // :226
-                            const unsigned second = __reduce_min_sync(0xFFFFFFFFu, k1 == best ? k2 : k1);
-                            const int bestDist2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
-                            if (!((float)bestDist1 < __fmul_rn(A.nnratio, (float)bestDist2))) continue;   // :228
-                            const int pb = (int)(best & 0xFFFFu);
-                            if (ntile == 1) claimed |= 1u << pb;
-                            else { if (lane == 0) claim[pb >> 5] |= 1u << (pb & 31); __syncwarp(); }
-                            const int r_orig = __shfl_sync(0xFFFFFFFFu, orig_l, row);
-                            const float qa = __shfl_sync(0xFFFFFFFFu, ang_l, row);
-                            if (lane == 0) {
-                                const int bin = A.check_ori ? rot_bin(qa, fangle[ts + pb]) : 0;
-                                out[ts + pb] = (uint32_t)r_orig | ((uint32_t)bin << 16);   // vpMapPointMatches[bestIdxF] = pMP (:232)
-                            }
-                        }
-                        __syncwarp();
+        int lo = 0, hi = np;                                      // largest p with pstart[p] <= it
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pstart[mid] <= it) lo = mid; else hi = mid; }
+        const int bf = pnode[lo], cs = pcs[lo];
+        const int k0 = (it - pstart[lo]) * cs, k1 = min(A.n_kf, k0 + cs);
+        const uint32_t node = fnode[bf];
+        const int ts = fstart[bf], nt = fstart[bf + 1] - ts;       // nt > 0 by construction of the work list
+        const bool wide = nt > 32;
+        const uint4* fd = fdesc + (size_t)ts * 2;
+
+        {
+            const int kb = k0;                                    // an item holds at most 32 keyframes (the host's work list)
+            // ---- lane j: keyframe kb + j; find the bucket of `node` in its FeatureVector (ascending node ids)
+            const int k = kb + lane;
+            int rs = 0, cnt = 0;
+            const uint2* kmeta = nullptr; const uint4* kdesc = nullptr;
+            if (k < k1) {
+                const KfStream* Kp = A.table + (A.slots ? A.slots[k] : k);
+                const int nn = Kp->nn;
+                if (nn > 0) {
+                    const uint32_t* kn = Kp->node;
+                    int idx = min(bf, nn - 1);                    // both lists are ascending subsets of the same level: try the same rank first
+                    if (kn[idx] != node) {
+                        int l2 = 0, h2 = nn;
+                        while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (kn[mid] < node) l2 = mid + 1; else h2 = mid; }
+                        idx = (l2 < nn && kn[l2] == node) ? l2 : -1;
+                    }
+                    if (idx >= 0) {
+                        const int32_t* st = Kp->start;
+                        rs = st[idx]; cnt = st[idx + 1] - rs;
+                        kmeta = Kp->meta; kdesc = reinterpret_cast<const uint4*>(Kp->desc);
                     }
                 }
             }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            __syncwarp();
+            run[lane] = KfRun{kmeta, kdesc, rs, incl - cnt};
+            __syncwarp();
+            int cur_run = -1;                  // keyframe (lane index of the batch) the claim state below belongs to
+            uint32_t claimed = 0;
+            int qn = 0, qh = 0;                // ring: qn pending rows starting at slot qh
+
+            // One batch: lane j owns the j-th pending row (rows stay in (keyframe, FeatureVector) order), its 256-bit descriptor
+            // in registers, and scans the nt columns: best / second best == lexicographic min / second min of (distance, column)
+            // (:207-224).  Then the rows that have a distance <= TH_LOW at all are replayed in row order against the claim state
+            // of their keyframe (:209, :226-251); every other row can neither match nor claim.
+            auto process = [&](int n_act) {
+                const bool act = lane < n_act;
+                int4 e = make_int4(0, 0, 0, 0);
+                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+                if (act) { const int sl = (qh + lane) & (BDB_QCAP - 1); e = qm[sl]; q0 = qd0[sl]; q1 = qd1[sl]; }
+                unsigned k1v = 0xFFFFFFFFu, k2v = 0xFFFFFFFFu;
+#pragma unroll 2
+                for (int c = 0; c < nt; c++) {
+                    const int d = ham256<CSA>(q0, q1, fd[2 * c], fd[2 * c + 1]);
+                    const unsigned key = ((unsigned)d << 16) | (unsigned)c;
+                    k2v = min(k2v, max(k1v, key));                 // second smallest so far (k1v <= k2v always)
+                    k1v = min(k1v, key);
+                }
+                unsigned low = __ballot_sync(0xFFFFFFFFu, act && (k1v >> 16) <= (unsigned)TH_LOW);
+                while (low) {
+                    const int L = __ffs(low) - 1;
+                    low &= low - 1;
+                    const int rL = __shfl_sync(0xFFFFFFFFu, e.y, L);
+                    unsigned kk1 = __shfl_sync(0xFFFFFFFFu, k1v, L), kk2 = __shfl_sync(0xFFFFFFFFu, k2v, L);
+                    if (rL != cur_run) {
+                        cur_run = rL; claimed = 0;
+                        if (wide) { for (int w = lane; w < ((nt + 31) >> 5); w += 32) claim[w] = 0; __syncwarp(); }
+                    }
+                    auto is_claimed = [&](unsigned col) -> bool { return wide ? ((claim[col >> 5] >> (col & 31)) & 1u) != 0 : ((claimed >> col) & 1u) != 0; };
+                    const bool stale = is_claimed(kk1 & 0xFFFFu) || (kk2 != 0xFFFFFFFFu && is_claimed(kk2 & 0xFFFFu));
+                    if (stale) {
+                        // a claimed column is this row's best or second best: rescan the bucket without the claimed columns, all lanes
+                        uint4 r0v, r1v;
+                        r0v.x = __shfl_sync(0xFFFFFFFFu, q0.x, L); r0v.y = __shfl_sync(0xFFFFFFFFu, q0.y, L);
+                        r0v.z = __shfl_sync(0xFFFFFFFFu, q0.z, L); r0v.w = __shfl_sync(0xFFFFFFFFu, q0.w, L);
+                        r1v.x = __shfl_sync(0xFFFFFFFFu, q1.x, L); r1v.y = __shfl_sync(0xFFFFFFFFu, q1.y, L);
+                        r1v.z = __shfl_sync(0xFFFFFFFFu, q1.z, L); r1v.w = __shfl_sync(0xFFFFFFFFu, q1.w, L);
+                        unsigned m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;
+                        for (int col = lane; col < nt; col += 32) {
+                            if (is_claimed((unsigned)col)) continue;
+                            const int d = ham256<CSA>(r0v, r1v, fd[2 * col], fd[2 * col + 1]);
+                            const unsigned key = ((unsigned)d << 16) | (unsigned)col;
+                            if (key < m1) { m2 = m1; m1 = key; } else if (key < m2) m2 = key;
+                        }
+                        kk1 = __reduce_min_sync(0xFFFFFFFFu, m1);
+                        kk2 = __reduce_min_sync(0xFFFFFFFFu, m1 == kk1 ? m2 : m1);
+                    }
+                    if (kk1 == 0xFFFFFFFFu) continue;
+                    const int bestDist1 = (int)(kk1 >> 16);
+                    if (bestDist1 > TH_LOW) continue;                                          // :226
+                    const int bestDist2 = kk2 == 0xFFFFFFFFu ? 256 : (int)(kk2 >> 16);
+                    if (!((float)bestDist1 < __fmul_rn(A.nnratio, (float)bestDist2))) continue;   // :228
+                    const unsigned pb = kk1 & 0xFFFFu;
+                    if (wide) { if (lane == 0) claim[pb >> 5] |= 1u << (pb & 31); __syncwarp(); }
+                    else claimed |= 1u << pb;
+                    const uint32_t mx = (uint32_t)__shfl_sync(0xFFFFFFFFu, e.z, L), my = (uint32_t)__shfl_sync(0xFFFFFFFFu, e.w, L);
+                    if (lane == 0) {
+                        const int bin = A.check_ori ? rot_bin(__uint_as_float(my), fangle[ts + pb]) : 0;
+                        A.table_out[(size_t)(kb + rL) * mf + ts + pb] = (mx & 0xFFFFu) | ((uint32_t)bin << 16);   // vpMapPointMatches[bestIdxF] = pMP (:232)
+                    }
+                }
+            };
+
+            // rows of the batch in (keyframe, row) order, 32 at a time; the loads of the next 32 are issued before the pending
+            // ones are processed, so their latency overlaps the column loop
+            auto fetch = [&](int base, int& src, int& row, uint2& meta, uint4& d0, uint4& d1) {
+                const int pos = base + lane;
+                src = 0; row = 0; meta = make_uint2(0u, 0u); d0 = make_uint4(0, 0, 0, 0); d1 = d0;
+                if (pos < total) {
+                    int l3 = 0, h3 = 32;                          // largest j with run[j].off <= pos (empty runs share their successor's off: pick the last)
+                    while (h3 - l3 > 1) { const int mid = (l3 + h3) >> 1; if (run[mid].off <= pos) l3 = mid; else h3 = mid; }
+                    src = l3;
+                    const KfRun r = run[src];
+                    row = r.rs + (pos - r.off);
+                    meta = r.meta[row];                           // feature | good-MapPoint flag << 16 | ..., angle
+                    d0 = r.desc[(size_t)row * 2]; d1 = r.desc[(size_t)row * 2 + 1];
+                }
+            };
+            int src, row; uint2 meta; uint4 d0, d1;
+            fetch(0, src, row, meta, d0, d1);
+            for (int base = 0; base < total; base += 32) {
+                const bool ok = ((meta.x >> 16) & 1u) != 0;       // good MapPoint (:196-202)
+                const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok);
+                if (ok) {
+                    const int sl = (qh + qn + __popc(okm & lt_mask)) & (BDB_QCAP - 1);
+                    qm[sl] = make_int4(row, src, (int)meta.x, (int)meta.y); qd0[sl] = d0; qd1[sl] = d1;
+                }
+                qn += __popc(okm);
+                if (base + 32 < total) fetch(base + 32, src, row, meta, d0, d1);
+                __syncwarp();
+                if (qn >= 32) {
+                    process(32);
+                    qh = (qh + 32) & (BDB_QCAP - 1); qn -= 32;
+                    __syncwarp();
+                }
+            }
+            if (qn > 0) { process(qn); __syncwarp(); }
         }
     }
 }
 
-// Rotation-consistency cull and compaction, a warp per keyframe.  table_out row: one u32 per frame position (FeatureVector
-// order): keyframe feature | bin << 16, or 0xFFFFFFFF.
-__global__ void __launch_bounds__(256) bowdb_finalize_kernel(BowDbFinal F) {
-    __shared__ int hist_all[8][32];
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const int k = blockIdx.x * 8 + wrp;
-    if (k >= F.n_kf) return;
-    int* hist = hist_all[wrp];
-    hist[lane] = 0;
-    __syncwarp();
+// Rotation-consistency cull and compaction, a 128-thread CTA per keyframe.  table_out row: one u32 per frame position
+// (FeatureVector order): keyframe feature | bin << 16, or 0xFFFFFFFF.  Survivors are written in frame-position order.
+constexpr int FIN_THREADS = 128;
+__global__ void __launch_bounds__(FIN_THREADS) bowdb_finalize_kernel(BowDbFinal F) {
+    __shared__ int hist[32];
+    __shared__ int warp_cnt[FIN_THREADS / 32];
+    __shared__ int s_off, s_i1, s_i2, s_i3;
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int k = blockIdx.x;
+    if (tid < 32) hist[tid] = 0;
+    __syncthreads();
     const uint32_t* row = F.table_out + (size_t)k * F.mf;
-    int total = 0;
-    for (int base = 0; base < F.mf; base += 32) {
-        const int i = base + lane;
-        const uint32_t e = i < F.mf ? row[i] : 0xFFFFFFFFu;
-        if (e != 0xFFFFFFFFu) { atomicAdd(&hist[(e >> 16) & 31], 1); total++; }
+    for (int i = tid; i < F.mf; i += FIN_THREADS) {
+        const uint32_t e = row[i];
+        if (e != 0xFFFFFFFFu) atomicAdd(&hist[(e >> 16) & 31], 1);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
-    __syncwarp();
-    int i1 = -1, i2 = -1, i3 = -1;
-    if (F.check_ori) three_maxima(hist, i1, i2, i3);
-    // count survivors, reserve the output range, then write in frame-position order
-    int kept = 0;
-    if (F.check_ori) {
-        for (int b = lane; b < HISTO_LENGTH; b += 32)
-            if (b == i1 || b == i2 || b == i3) kept += hist[b];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xFFFFFFFFu, kept, o);
-    } else kept = total;
-    int off = 0;
-    if (lane == 0) {
-        off = F.pairs ? atomicAdd(F.cursor, kept) : 0;
+    __syncthreads();
+    if (tid == 0) {
+        int i1 = -1, i2 = -1, i3 = -1, kept = 0;
+        if (F.check_ori) {
+            three_maxima(hist, i1, i2, i3);
+            for (int b = 0; b < HISTO_LENGTH; b++) if (b == i1 || b == i2 || b == i3) kept += hist[b];
+        } else {
+            for (int b = 0; b < 32; b++) kept += hist[b];
+        }
+        const int off = F.pairs ? atomicAdd(F.cursor, kept) : 0;
         F.n_matches[k] = kept;                                           // nmatches after the cull (:267-285)
         if (F.pair_off) F.pair_off[k] = off;
+        s_off = off; s_i1 = i1; s_i2 = i2; s_i3 = i3;
     }
-    off = __shfl_sync(0xFFFFFFFFu, off, 0);
+    __syncthreads();
     if (!F.pairs && !F.dense) return;
-    int run = 0;
-    for (int base = 0; base < F.mf; base += 32) {
-        const int i = base + lane;
+    const int i1 = s_i1, i2 = s_i2, i3 = s_i3;
+    int run = s_off;
+    for (int base = 0; base < F.mf; base += FIN_THREADS) {
+        const int i = base + tid;
         const uint32_t e = i < F.mf ? row[i] : 0xFFFFFFFFu;
         bool keep = e != 0xFFFFFFFFu;
         if (keep && F.check_ori) { const int b = (int)((e >> 16) & 31); keep = b == i1 || b == i2 || b == i3; }
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) warp_cnt[wrp] = __popc(bal);
+        __syncthreads();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < FIN_THREADS / 32; w++) { const int c = warp_cnt[w]; if (w < wrp) before += c; all += c; }
         if (keep) {
             const int j = (int)F.forig[i], r = (int)(e & 0xFFFFu);
-            if (F.pairs) { const int pos = off + run + __popc(bal & ((1u << lane) - 1)); if (pos < F.pairs_cap) F.pairs[pos] = (uint32_t)j | ((uint32_t)r << 16); }
+            if (F.pairs) { const int pos = run + before + __popc(bal & ((1u << lane) - 1)); if (pos < F.pairs_cap) F.pairs[pos] = (uint32_t)j | ((uint32_t)r << 16); }
             if (F.dense) F.dense[(size_t)k * F.dense_stride + j] = r;
         }
-        run += __popc(bal);
+        run += all;
+        __syncthreads();
     }
 }
 
-size_t bowdb_smem_bytes(int frame_bytes, bool frame_in_smem) {
-    return (frame_in_smem ? (((size_t)frame_bytes + 127) & ~size_t(127)) : 0) + (size_t)BDB_WARPS * BDB_WARP_BYTES;
+// Warps per CTA: as many as fit beside the query frame in one SM's shared memory (one CTA per SM), at least 8.
+static int bowdb_warps(int frame_bytes, bool fsm) {
+    const size_t frame = fsm ? (((size_t)frame_bytes + 127) & ~size_t(127)) : 0;
+    const size_t budget = 226 * 1024;
+    if (frame + 8 * (size_t)BDB_WARP_BYTES > budget) return 0;
+    const int w = (int)((budget - frame) / BDB_WARP_BYTES);
+    return w > BDB_WARPS ? BDB_WARPS : w;
 }
+
+bool bowdb_frame_fits_smem(int frame_bytes) { return bowdb_warps(frame_bytes, true) >= 8; }
 
 int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, bool csa, int n_sm, cudaStream_t s) {
-    const size_t smem = bowdb_smem_bytes(A.frame_bytes, A.frame_in_smem != 0);
-    const int items = A.n_kf * A.parts;
-    int ctas = (items + BDB_WARPS - 1) / BDB_WARPS;
-    const int per_sm = smem <= 74 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
-    if (ctas > n_sm * per_sm) ctas = n_sm * per_sm;
+    const bool fsm = A.frame_in_smem != 0;
+    const int warps = bowdb_warps(A.frame_bytes, fsm);
+    const size_t smem = (fsm ? (((size_t)A.frame_bytes + 127) & ~size_t(127)) : 0) + (size_t)warps * BDB_WARP_BYTES;
+    int ctas = (A.n_items + warps - 1) / warps;
+    if (ctas > n_sm * BDB_CTAS) ctas = n_sm * BDB_CTAS;
     if (ctas < 1) ctas = 1;
-    if (csa) {
-        allow_max_smem((const void*)bowdb_match_kernel<true>);
-        bowdb_match_kernel<true><<<ctas, 32 * BDB_WARPS, smem, s>>>(A);
-    } else {
-        allow_max_smem((const void*)bowdb_match_kernel<false>);
-        bowdb_match_kernel<false><<<ctas, 32 * BDB_WARPS, smem, s>>>(A);
-    }
-    bowdb_finalize_kernel<<<(F.n_kf + 7) / 8, 256, 0, s>>>(F);
+    void (*kern)(BowDbArgs) = csa ? (fsm ? bowdb_match_kernel<true, true> : bowdb_match_kernel<true, false>)
+                                  : (fsm ? bowdb_match_kernel<false, true> : bowdb_match_kernel<false, false>);
+    allow_max_smem((const void*)kern);
+    kern<<<ctas, 32 * warps, smem, s>>>(A);
+    bowdb_finalize_kernel<<<F.n_kf, FIN_THREADS, 0, s>>>(F);
     return 2;
 }
 

@@ -43,7 +43,7 @@ def test_python_binding_covers_the_header(lib):
 
 def test_version_and_status_strings(lib):
     so = lib.load()
-    assert so.borb_version() == 1
+    assert so.borb_version() == 2          # BORB_VERSION of include/borb.h
     assert b"no CPU path" in so.borb_status_str(2)
 
 
