@@ -19,6 +19,9 @@ struct borb_matcher {
     size_t arena_bytes = 0, arena_off = 0;
     uint8_t* h_stage = nullptr;     // pinned staging mirror of the arena's input part
     size_t h_bytes = 0;
+    const uint8_t* in_base = nullptr;   // where the kernels of the current call read the staged inputs: the arena, or (small calls
+                                        // on a resident frame) h_stage itself - pinned host memory is device-addressable (UVA), which
+                                        // saves the H2D copy and its DMA latency
     uint64_t launches = 0;
     int32_t* aux = nullptr;         // small device buffer that survives an arena re-layout (SearchBySim3: first direction's matches)
     size_t aux_count = 0;
@@ -38,8 +41,8 @@ struct borb_voc {
     size_t bytes = 0;
     VocDev dev;
     cudaStream_t stream = nullptr;
-    uint8_t* scratch = nullptr;
-    size_t scratch_bytes = 0;
+    uint8_t* scratch = nullptr;     // pinned HOST buffer of borb_bow_transform: descriptors in, (weight, word, node) out - the kernel reads
+    size_t scratch_bytes = 0;       // and writes it in place (UVA), so a call is one launch and one synchronize.  One caller at a time per handle.
 };
 
 namespace {
@@ -92,7 +95,9 @@ borb_status ensure_out(borb_matcher* m, size_t bytes) {
 }
 
 // copies the staged inputs; `extra` = device-only scratch bytes requested after the inputs
-borb_status commit(Stager& st, size_t total_with_scratch) {
+constexpr size_t ZERO_COPY_MAX = 96 * 1024;       // inputs up to this size are read in place by the kernels (each byte is read once)
+
+borb_status commit(Stager& st, size_t total_with_scratch, bool zero_copy = false) {
     borb_matcher* m = st.m;
     borb_status s = ensure_host(m, st.off);
     if (s != BORB_OK) return s;
@@ -100,7 +105,9 @@ borb_status commit(Stager& st, size_t total_with_scratch) {
     BORB_CUDA(cudaStreamSynchronize(m->stream));     // the staging buffer may still feed an earlier copy
     for (auto& it : st.items)
         if (it.first) std::memcpy(m->h_stage + it.second.first, it.first, it.second.second);
-    if (st.off) BORB_CUDA(cudaMemcpyAsync(m->arena, m->h_stage, st.off, cudaMemcpyHostToDevice, m->stream));
+    zero_copy = zero_copy && st.off <= ZERO_COPY_MAX;
+    if (st.off && !zero_copy) BORB_CUDA(cudaMemcpyAsync(m->arena, m->h_stage, st.off, cudaMemcpyHostToDevice, m->stream));
+    m->in_base = zero_copy ? m->h_stage : m->arena;
     return BORB_OK;
 }
 
@@ -141,12 +148,12 @@ void reserve_grid(Stager& st, const FrameInfo& I, FrameStage& fs) {
 }
 // fills the frame fields of A after commit(); builds the grid for a host view, waits for the resident frame otherwise
 borb_status bind_frame(borb_matcher* m, const FrameInfo& I, const FrameStage& fs, ProjArgs& A) {
-    uint8_t* b = m->arena;
+    uint8_t* b = m->arena;             // (a host view is never zero-copy: in_base == arena)
     A.n = I.n;
     A.minX = I.min_x; A.minY = I.min_y;
     A.invW = (float)GRID_COLS / (float)(I.max_x - I.min_x);      // mfGridElementWidthInv (Frame.cc:101)
     A.invH = (float)GRID_ROWS / (float)(I.max_y - I.min_y);
-    A.occupied = fs.occ_p ? b + fs.occ : nullptr;
+    A.occupied = fs.occ_p ? m->in_base + fs.occ : nullptr;
     if (I.rf) {
         A.keys = I.rf->keys; A.desc = I.rf->desc; A.u_right = fs.ur_p ? I.rf->u_right : nullptr; A.scale_factors = I.rf->sf;
         A.cell_start = I.rf->cell_start; A.cell_idx = I.rf->cell_idx;
@@ -490,19 +497,22 @@ borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F,
     const size_t total = st.off;
     st.off = input_end;
     if ((s = ensure_out(m, (size_t)P->n * 4 + 16)) != BORB_OK) return s;
-    if ((s = commit(st, total)) != BORB_OK) return s;
+    if ((s = commit(st, total, I.rf != nullptr)) != BORB_OK) return s;
     uint8_t* b = m->arena;
+    const uint8_t* in = m->in_base;
+    const bool direct = in != b;                       // small call on a resident frame: the result is written straight into h_out too
     ProjArgs A{};
     if ((s = bind_frame(m, I, fs, A)) != BORB_OK) return s;
-    A.n_mp = P->n; A.proj_x = (const float*)(b + o_px); A.proj_y = (const float*)(b + o_py); A.proj_xr = (const float*)(b + o_pxr);
-    A.view_cos = (const float*)(b + o_vc); A.level = (const int32_t*)(b + o_lvl); A.mp_desc = b + o_md;
-    A.mp_valid = P->valid ? b + o_val : nullptr; A.mp_has_obs = P->has_obs ? b + o_obs : nullptr;
+    A.n_mp = P->n; A.proj_x = (const float*)(in + o_px); A.proj_y = (const float*)(in + o_py); A.proj_xr = (const float*)(in + o_pxr);
+    A.view_cos = (const float*)(in + o_vc); A.level = (const int32_t*)(in + o_lvl); A.mp_desc = in + o_md;
+    A.mp_valid = P->valid ? in + o_val : nullptr; A.mp_has_obs = P->has_obs ? in + o_obs : nullptr;
     A.th = th; A.nnratio = nnratio; A.th_dist = TH_HIGH;
     A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
     A.mode = 0;
-    m->launches += launch_projection(A, (int32_t*)(b + o_match), (int*)(b + o_nm), m->stream);
+    int32_t* d_match = direct ? (int32_t*)m->h_out : (int32_t*)(b + o_match);
+    m->launches += launch_projection(A, d_match, (int*)(d_match + P->n), m->stream);
     BORB_CUDA(cudaGetLastError());
-    BORB_CUDA(cudaMemcpyAsync(m->h_out, b + o_match, (size_t)P->n * 4 + 4, cudaMemcpyDeviceToHost, m->stream));    // pinned landing buffer
+    if (!direct) BORB_CUDA(cudaMemcpyAsync(m->h_out, b + o_match, (size_t)P->n * 4 + 4, cudaMemcpyDeviceToHost, m->stream));    // pinned landing buffer
     BORB_CUDA(cudaStreamSynchronize(m->stream));
     std::memcpy(match_feat, m->h_out, (size_t)P->n * 4);
     std::memcpy(n_matches, m->h_out + (size_t)P->n * 4, 4);
@@ -586,22 +596,23 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     const size_t total = st.off;
     st.off = input_end;
     if ((s = ensure_out(m, n_state * 4 + 16)) != BORB_OK) return s;
-    if ((s = commit(st, total)) != BORB_OK) return s;
+    if ((s = commit(st, total, I.rf != nullptr)) != BORB_OK) return s;
     uint8_t* b = m->arena;
+    const uint8_t* in = m->in_base;
     ProjArgs A{};
     if ((s = bind_frame(m, I, fs, A)) != BORB_OK) return s;
     LastArgs L{};
     L.variant = Q.variant;
-    L.n_last = nq; L.last_keys = Q.keys ? (const borb_keypoint*)(b + o_lk) : nullptr; L.world_pos = (const float*)(b + o_wp);
-    L.q_angle_in = Q.angle ? (const float*)(b + o_qa) : nullptr;
-    L.max_distance = Q.max_distance ? (const float*)(b + o_mx) : nullptr;
-    L.min_distance = Q.min_distance ? (const float*)(b + o_mn) : nullptr;
-    L.normal = Q.normal ? (const float*)(b + o_nr) : nullptr;
+    L.n_last = nq; L.last_keys = Q.keys ? (const borb_keypoint*)(in + o_lk) : nullptr; L.world_pos = (const float*)(in + o_wp);
+    L.q_angle_in = Q.angle ? (const float*)(in + o_qa) : nullptr;
+    L.max_distance = Q.max_distance ? (const float*)(in + o_mx) : nullptr;
+    L.min_distance = Q.min_distance ? (const float*)(in + o_mn) : nullptr;
+    L.normal = Q.normal ? (const float*)(in + o_nr) : nullptr;
     for (int i = 0; i < 3; i++) L.Ow[i] = Q.Ow ? Q.Ow[i] : 0.f;
     L.log_scale = Q.log_scale; L.n_levels = I.n_levels;
     L.invz_double = Q.invz_double; L.use_normal = Q.use_normal; L.chain = Q.chain;
     for (int i = 0; i < 12; i++) L.T2[i] = Q.chain ? Q.T2[i] : 0.f;
-    L.valid_in = Q.valid ? b + o_vin : nullptr;
+    L.valid_in = Q.valid ? in + o_vin : nullptr;
     for (int i = 0; i < 12; i++) L.T[i] = Q.Tcw[i];
     L.fx = Q.fx; L.fy = Q.fy; L.cx = Q.cx; L.cy = Q.cy; L.bf = Q.bf; L.th = Q.th;
     L.minX = I.min_x; L.minY = I.min_y; L.maxX = I.max_x; L.maxY = I.max_y;
@@ -610,12 +621,12 @@ static borb_status run_point_projection(borb_matcher* m, const borb_frame_view* 
     L.proj_x = (float*)(b + o_px); L.proj_y = (float*)(b + o_py); L.proj_xr = (float*)(b + o_pxr); L.radius = (float*)(b + o_rad);
     L.angle = (float*)(b + o_ang); L.minl = (int32_t*)(b + o_minl); L.maxl = (int32_t*)(b + o_maxl); L.valid_out = b + o_val;
     A.n_mp = nq; A.proj_x = L.proj_x; A.proj_y = L.proj_y; A.proj_xr = L.proj_xr; A.view_cos = nullptr; A.level = nullptr;
-    A.mp_desc = b + o_md; A.mp_valid = b + o_val; A.mp_has_obs = Q.has_obs ? b + o_obs : nullptr;
+    A.mp_desc = in + o_md; A.mp_valid = b + o_val; A.mp_has_obs = Q.has_obs ? in + o_obs : nullptr;
     A.th = Q.th; A.nnratio = 0.f;
     A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
     A.q_radius = L.radius; A.q_minl = L.minl; A.q_maxl = L.maxl; A.mode = 1; A.check_ori = Q.check_ori; A.q_angle = L.angle;
     A.th_dist = Q.th_dist;
-    A.chi2 = Q.chi2; A.inv_sigma2 = Q.chi2 ? (const float*)(b + o_is2) : nullptr;
+    A.chi2 = Q.chi2; A.inv_sigma2 = Q.chi2 ? (const float*)(in + o_is2) : nullptr;
     A.q_valid_out = b + o_val;
     if (Q.argmin) m->launches += launch_projection_argmin(L, A, (int32_t*)(b + o_state), (int*)(b + o_nm), m->stream);
     else m->launches += launch_projection_last(L, A, (int32_t*)(b + o_state), (int32_t*)(b + o_evi), b + o_evb, (int*)(b + o_nm), m->stream);
@@ -808,14 +819,15 @@ borb_status borb_search_local_points(borb_matcher* m, const borb_frame_view* F, 
             std::memcpy(h + o_nr + (size_t)k * 12, pts->normal + (size_t)i * 3, 12);
         }
     }
-    if ((s = commit(st, total)) != BORB_OK) return s;
+    if ((s = commit(st, total, I.rf != nullptr)) != BORB_OK) return s;
     uint8_t* b = m->arena;
+    const uint8_t* in = m->in_base;
     BORB_CUDA(cudaMemsetAsync(b + o_lvl, 0, (size_t)nq * 8, m->stream));       // level | viewcos of points outside the frustum read as 0
     ProjArgs A{};
     if ((s = bind_frame(m, I, fs, A)) != BORB_OK) return s;
     LastArgs L{};
-    L.variant = 3; L.n_last = nq; L.world_pos = (const float*)(b + o_wp);
-    L.max_distance = (const float*)(b + o_mx); L.min_distance = (const float*)(b + o_mn); L.normal = (const float*)(b + o_nr);
+    L.variant = 3; L.n_last = nq; L.world_pos = (const float*)(in + o_wp);
+    L.max_distance = (const float*)(in + o_mx); L.min_distance = (const float*)(in + o_mn); L.normal = (const float*)(in + o_nr);
     for (int i = 0; i < 3; i++) L.Ow[i] = Ow[i];
     L.log_scale = log_scale_factor; L.n_levels = I.n_levels; L.view_cos_limit = viewing_cos_limit;
     L.valid_in = nullptr;
@@ -827,7 +839,7 @@ borb_status borb_search_local_points(borb_matcher* m, const borb_frame_view* F, 
     L.angle = (float*)(b + o_ang); L.minl = (int32_t*)(b + o_minl); L.maxl = (int32_t*)(b + o_maxl); L.valid_out = b + o_val;
     L.level_out = (int32_t*)(b + o_lvl); L.viewcos_out = (float*)(b + o_vc);
     A.n_mp = nq; A.proj_x = L.proj_x; A.proj_y = L.proj_y; A.proj_xr = L.proj_xr; A.view_cos = L.viewcos_out; A.level = L.level_out;
-    A.mp_desc = b + o_md; A.mp_valid = b + o_val; A.mp_has_obs = has_obs ? b + o_obs : nullptr;
+    A.mp_desc = in + o_md; A.mp_valid = b + o_val; A.mp_has_obs = has_obs ? in + o_obs : nullptr;
     A.th = th; A.nnratio = nnratio; A.th_dist = TH_HIGH;
     A.cand = (uint32_t*)(b + o_cand); A.cand_cnt = (int*)(b + o_cc);
     A.mode = 0;
@@ -1180,7 +1192,6 @@ borb_status borb_kfdb_query(borb_matcher* m, borb_kfdb* db, const uint32_t* bow_
     for (int i = 1; i < n_bow; i++)
         if (bow_word[i] <= bow_word[i - 1]) { set_error("BowVector words must ascend (std::map order)"); return BORB_ERR_INVALID_ARG; }
     uint8_t* b = nullptr;
-    size_t o_c = 0, o_s = 0, o_f = 0;
     int n = 0;
     {
         std::lock_guard<std::mutex> lk(db->mu);       // held across the table sync and the kernel enqueue (erase() synchronises the device before freeing)
@@ -1194,19 +1205,21 @@ borb_status borb_kfdb_query(borb_matcher* m, borb_kfdb* db, const uint32_t* bow_
         Stager st(m);
         const size_t o_w = st.add(bow_word, (size_t)n_bow * 4), o_v = st.add(bow_value, (size_t)n_bow * 8);
         const size_t input_end = st.off;
-        o_c = st.reserve((size_t)n * 4); o_s = st.reserve((size_t)n * 4); o_f = st.reserve((size_t)n * 4);
         const size_t total = st.off;
         st.off = input_end;
+        if ((s = ensure_out(m, (size_t)n * 12 + 64)) != BORB_OK) return s;
         if ((s = commit(st, total)) != BORB_OK) return s;
         b = m->arena;
-        m->launches += launch_kfdb_score(db->d_table, n, (const uint32_t*)(b + o_w), (const double*)(b + o_v), n_bow, (int32_t*)(b + o_c),
-                                         (float*)(b + o_s), (uint32_t*)(b + o_f), m->stream);
+        // the three result arrays are written by the kernel straight into the pinned landing buffer (device-addressable, UVA)
+        uint8_t* ho = m->h_out;
+        m->launches += launch_kfdb_score(db->d_table, n, (const uint32_t*)(b + o_w), (const double*)(b + o_v), n_bow, (int32_t*)ho,
+                                         (float*)(ho + (size_t)n * 4), (uint32_t*)(ho + (size_t)n * 8), m->stream);
         BORB_CUDA(cudaGetLastError());
     }
-    BORB_CUDA(cudaMemcpyAsync(common_words, b + o_c, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
-    BORB_CUDA(cudaMemcpyAsync(score, b + o_s, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
-    BORB_CUDA(cudaMemcpyAsync(first_word, b + o_f, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaStreamSynchronize(m->stream));
+    std::memcpy(common_words, m->h_out, (size_t)n * 4);
+    std::memcpy(score, m->h_out + (size_t)n * 4, (size_t)n * 4);
+    std::memcpy(first_word, m->h_out + (size_t)n * 8, (size_t)n * 4);
     return BORB_OK;
 }
 
@@ -1330,32 +1343,35 @@ borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, i
         A.frame_in_smem = bowdb_frame_fits_smem((int)fbytes) ? 1 : 0;
         A.nnratio = nnratio; A.check_ori = check_ori;
         A.table_out = (uint32_t*)(b + o_tab); A.work_counter = (int*)(b + o_ctr);
+        // results: counts, offsets and the compact pair list are written by the finalize kernel straight into the pinned landing
+        // buffer (device-addressable, UVA) - no device-to-host copies; the dense table (MBs) still goes through one copy
+        const size_t ho_nm = 0, ho_po = (size_t)n_kf * 4, ho_pairs = (size_t)n_kf * 8;
+        if ((s = ensure_out(m, (size_t)n_kf * 8 + (size_t)pairs_cap * 4 + 64)) != BORB_OK) return s;
+        uint8_t* ho = m->h_out;
         BowDbFinal F{};
         F.table_out = A.table_out; F.n_kf = n_kf; F.mf = mf; F.check_ori = check_ori;
         F.forig = (const uint16_t*)(b + o_fb + reinterpret_cast<const FrameBlockHdrHost*>(m->h_stage + o_fb)->off_orig);
-        F.n_matches = (int32_t*)(b + o_nm); F.pair_off = (int32_t*)(b + o_po);
-        F.pairs = pairs ? (uint32_t*)(b + o_pairs) : nullptr; F.pairs_cap = pairs_cap; F.cursor = (int*)(b + o_ctr + 64);
+        F.n_matches = (int32_t*)(ho + ho_nm); F.pair_off = (int32_t*)(ho + ho_po);
+        F.pairs = pairs ? (uint32_t*)(ho + ho_pairs) : nullptr; F.pairs_cap = pairs_cap; F.cursor = (int*)(b + o_ctr + 64);
         F.dense = dense ? (int32_t*)(b + o_dense) : nullptr; F.dense_stride = dense_stride;
         if (m->timing) BORB_CUDA(cudaEventRecord(m->t0, m->stream));
         m->launches += launch_bowdb(A, F, g_bow_csa.load() != 0, db->n_sm, m->stream);
         if (m->timing) BORB_CUDA(cudaEventRecord(m->t1, m->stream));
         BORB_CUDA(cudaGetLastError());
     }
-    BORB_CUDA(cudaMemcpyAsync(n_matches, b + o_nm, (size_t)n_kf * 4, cudaMemcpyDeviceToHost, m->stream));
-    if (pair_offset) BORB_CUDA(cudaMemcpyAsync(pair_offset, b + o_po, (size_t)n_kf * 4, cudaMemcpyDeviceToHost, m->stream));
-    int32_t total_pairs = 0;
-    if (pairs) BORB_CUDA(cudaMemcpyAsync(&total_pairs, b + o_ctr + 64, 4, cudaMemcpyDeviceToHost, m->stream));
     if (dense) BORB_CUDA(cudaMemcpyAsync(dense, b + o_dense, (size_t)n_kf * dense_stride * 4, cudaMemcpyDeviceToHost, m->stream));
     BORB_CUDA(cudaStreamSynchronize(m->stream));
     if (m->timing) { float ms = 0.f; if (cudaEventElapsedTime(&ms, m->t0, m->t1) == cudaSuccess) m->last_ms = ms; else cudaGetLastError(); }
+    const uint8_t* ho = m->h_out;
+    std::memcpy(n_matches, ho, (size_t)n_kf * 4);
+    if (pair_offset) std::memcpy(pair_offset, ho + (size_t)n_kf * 4, (size_t)n_kf * 4);
     if (pairs) {
-        if (n_pairs_total) *n_pairs_total = total_pairs;
-        const int ncopy = total_pairs < pairs_cap ? total_pairs : pairs_cap;
-        if (ncopy > 0) {
-            BORB_CUDA(cudaMemcpyAsync(pairs, b + o_pairs, (size_t)ncopy * 4, cudaMemcpyDeviceToHost, m->stream));
-            BORB_CUDA(cudaStreamSynchronize(m->stream));
-        }
-        if (total_pairs > pairs_cap) { set_error("%d matched pairs, capacity %d", total_pairs, pairs_cap); return BORB_ERR_CAPACITY; }
+        long long total_pairs = 0;
+        for (int i = 0; i < n_kf; i++) total_pairs += n_matches[i];
+        if (n_pairs_total) *n_pairs_total = (int32_t)total_pairs;
+        const long long ncopy = total_pairs < pairs_cap ? total_pairs : pairs_cap;
+        if (ncopy > 0) std::memcpy(pairs, ho + (size_t)n_kf * 8, (size_t)ncopy * 4);
+        if (total_pairs > pairs_cap) { set_error("%lld matched pairs, capacity %d", total_pairs, pairs_cap); return BORB_ERR_CAPACITY; }
     }
     return BORB_OK;
 }
@@ -1489,7 +1505,7 @@ borb_status borb_voc_destroy(borb_voc* v) {
     cudaSetDevice(v->device);
     if (v->stream) cudaStreamSynchronize(v->stream);
     if (v->owns) cudaFree(v->blob);
-    cudaFree(v->scratch);
+    if (v->scratch) cudaFreeHost(v->scratch);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
     return BORB_OK;
@@ -1527,21 +1543,22 @@ borb_status borb_bow_transform(borb_voc* v, const uint8_t* desc, int n, int leve
     const size_t need = (size_t)n * (32 + 4 + 8 + 4) + 1024;
     if (v->scratch_bytes < need) {
         BORB_CUDA(cudaStreamSynchronize(v->stream));
-        cudaFree(v->scratch); v->scratch = nullptr; v->scratch_bytes = 0;
-        BORB_CUDA(cudaMalloc(&v->scratch, need * 2));
+        if (v->scratch) cudaFreeHost(v->scratch);
+        v->scratch = nullptr; v->scratch_bytes = 0;
+        BORB_CUDA(cudaMallocHost(&v->scratch, need * 2));
         v->scratch_bytes = need * 2;
     }
-    uint8_t* d_desc = v->scratch;
-    double* d_w = (double*)(v->scratch + (((size_t)n * 32 + 255) & ~size_t(255)));
-    int32_t* d_word = (int32_t*)(d_w + n);
-    int32_t* d_node = d_word + n;
-    BORB_CUDA(cudaMemcpyAsync(d_desc, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
-    launch_bow_transform(v->dev, d_desc, n, levelsup, d_word, d_w, d_node, v->stream);
+    uint8_t* h_desc = v->scratch;
+    double* h_w = (double*)(v->scratch + (((size_t)n * 32 + 255) & ~size_t(255)));
+    int32_t* h_word = (int32_t*)(h_w + n);
+    int32_t* h_node = h_word + n;
+    std::memcpy(h_desc, desc, (size_t)n * 32);
+    launch_bow_transform(v->dev, h_desc, n, levelsup, h_word, h_w, h_node, v->stream);
     BORB_CUDA(cudaGetLastError());
-    BORB_CUDA(cudaMemcpyAsync(word, d_word, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
-    BORB_CUDA(cudaMemcpyAsync(weight, d_w, (size_t)n * 8, cudaMemcpyDeviceToHost, v->stream));
-    BORB_CUDA(cudaMemcpyAsync(node, d_node, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
     BORB_CUDA(cudaStreamSynchronize(v->stream));
+    std::memcpy(word, h_word, (size_t)n * 4);
+    std::memcpy(weight, h_w, (size_t)n * 8);
+    std::memcpy(node, h_node, (size_t)n * 4);
     return BORB_OK;
 }
 
@@ -1559,13 +1576,16 @@ borb_status borb_compute_bow(borb_voc* v, const uint8_t* desc, int n, int levels
     std::vector<double> weight(n);
     borb_status s = borb_bow_transform(v, desc, n, levelsup, word.data(), weight.data(), node.data());
     if (s != BORB_OK) return s;
-    // stable sort of the kept features by word / by node: equal keys stay in feature order, as std::map insertion does
-    std::vector<int32_t> keep;
-    keep.reserve(n);
-    for (int i = 0; i < n; i++) if (weight[i] > 0) keep.push_back(i);
-    std::vector<int32_t> byw(keep), byn(keep);
-    std::stable_sort(byw.begin(), byw.end(), [&](int a, int b) { return word[a] < word[b]; });
-    std::stable_sort(byn.begin(), byn.end(), [&](int a, int b) { return node[a] < node[b]; });
+    // kept features ordered by word / by node, equal keys in feature order (what std::map insertion in feature order gives):
+    // one 64-bit key (id << 32 | feature) per feature, plain sort
+    std::vector<uint64_t> kw, kn;
+    kw.reserve(n); kn.reserve(n);
+    for (int i = 0; i < n; i++)
+        if (weight[i] > 0) { kw.push_back(((uint64_t)(uint32_t)word[i] << 32) | (uint32_t)i); kn.push_back(((uint64_t)(uint32_t)node[i] << 32) | (uint32_t)i); }
+    std::sort(kw.begin(), kw.end());
+    std::sort(kn.begin(), kn.end());
+    std::vector<int32_t> byw(kw.size()), byn(kn.size());
+    for (size_t k = 0; k < kw.size(); k++) { byw[k] = (int32_t)(kw[k] & 0xFFFFFFFFu); byn[k] = (int32_t)(kn[k] & 0xFFFFFFFFu); }
     int nb = 0;
     for (size_t k = 0; k < byw.size(); k++) {
         const int i = byw[k];

@@ -694,7 +694,9 @@ __global__ void __launch_bounds__(256) bow_transform_kernel(VocDev V, const uint
     const int lane = threadIdx.x & 31;
     const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (f >= n) return;
-    const uint32_t* feat = reinterpret_cast<const uint32_t*>(desc + (size_t)f * 32);
+    // the descriptor is read ONCE into registers: `desc` may be pinned host memory (borb_bow_transform reads it in place)
+    const uint4 f0 = reinterpret_cast<const uint4*>(desc)[(size_t)f * 2], f1 = reinterpret_cast<const uint4*>(desc)[(size_t)f * 2 + 1];
+    const uint32_t feat[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
     const int nid_level = V.L - levelsup;
     int nid = 0, final_id = 0, level = 0;
     while (true) {

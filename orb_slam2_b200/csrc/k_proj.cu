@@ -68,19 +68,27 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
     uint32_t* out = A.cand + (size_t)iMP * A.n;
     int count = 0;
     bool unsorted = false;
-    if (A.mp_valid == nullptr || A.mp_valid[iMP]) {
+    // Every per-query input is fetched up front, independent loads back to back: in the small-call path they live in pinned
+    // HOST memory (borb_match_host.cu: in_base) and a dependent chain of PCIe round trips would dominate the kernel.
+    const uint8_t valid_q = A.mp_valid != nullptr ? A.mp_valid[iMP] : (uint8_t)1;
+    const int lvl_q = (A.mode == 0) ? A.level[iMP] : 0;
+    const float vc_q = (A.mode == 0) ? A.view_cos[iMP] : 0.f;
+    const float x = A.proj_x[iMP], y = A.proj_y[iMP];
+    const float xr = A.proj_xr[iMP];
+    const uint4 dm0 = reinterpret_cast<const uint4*>(A.mp_desc)[(size_t)iMP * 2], dm1 = reinterpret_cast<const uint4*>(A.mp_desc)[(size_t)iMP * 2 + 1];
+    const uint32_t dm[8] = {dm0.x, dm0.y, dm0.z, dm0.w, dm1.x, dm1.y, dm1.z, dm1.w};
+    if (valid_q) {
         float rs;
         int minLevel, maxLevel;
         if (A.mode == 0) {
-            const int lvl = A.level[iMP];
-            float r = A.view_cos[iMP] > 0.998 ? 2.5f : 4.0f;     // RadiusByViewingCos (:131-137)
+            const int lvl = lvl_q;
+            float r = vc_q > 0.998 ? 2.5f : 4.0f;     // RadiusByViewingCos (:131-137)
             if (A.th != 1.0f) r = __fmul_rn(r, A.th);
             rs = __fmul_rn(r, A.scale_factors[lvl]);
             minLevel = lvl - 1; maxLevel = lvl;
         } else {
             rs = A.q_radius[iMP]; minLevel = A.q_minl[iMP]; maxLevel = A.q_maxl[iMP];
         }
-        const float x = A.proj_x[iMP], y = A.proj_y[iMP];
         // GetFeaturesInArea(x, y, rs, minLevel, maxLevel)  (Frame.cc:327-380)
         const int c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, A.minX), rs), A.invW)));
         const int c1x = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, A.minX), rs), A.invW)));
@@ -88,7 +96,6 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
         const int c1y = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, A.minY), rs), A.invH)));
         if (!(c0x >= GRID_COLS || c1x < 0 || c0y >= GRID_ROWS || c1y < 0)) {
             const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
-            const float xr = A.proj_xr[iMP];
             auto passes = [&](int idx) -> bool {
                 const borb_keypoint kp = A.keys[idx];
                 if (bCheckLevels) {
@@ -141,7 +148,6 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
             }
             __syncwarp();
             // ---- 2. a lane per list entry: 256-bit distance
-            const uint32_t* dm = reinterpret_cast<const uint32_t*>(A.mp_desc + (size_t)iMP * 32);
             for (int e = lane; e < count; e += 32) {
                 const int idx = (int)out[e];
                 const int dist = ham_words(dm, reinterpret_cast<const uint32_t*>(A.desc + (size_t)idx * 32));
