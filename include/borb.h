@@ -490,9 +490,12 @@ BORB_API borb_status borb_debug_blurred(borb_extractor* e, int image, int level,
 /* Ablation of fast_kernel for the speed-of-light table in profiles/ (0 = full kernel, the only mode that produces
  * keypoints; 1 = TMA tile load only, 2 = + packed reject pass, 3 = + exact scores without NMS / emit). */
 BORB_API borb_status borb_debug_set_fast_mode(borb_extractor* e, int mode);
-/* Distance arithmetic of the database SearchByBoW kernel: 1 (default) = carry-save adder tree + 4 POPC per 256-bit distance,
- * 0 = 8 POPC.  Same results; kept switchable for the measurement in profiles/. */
-BORB_API borb_status borb_debug_set_bow_csa(int on);
+/* Distance arithmetic of the database SearchByBoW kernel: 2 (default) = three 3:2 compressors + 5 POPC per 256-bit distance,
+ * 1 = full carry-save adder tree + 4 POPC, 0 = 8 POPC.  Same results; kept switchable for the measurement in profiles/. */
+BORB_API borb_status borb_debug_set_bow_csa(int mode);
+/* Work-item size of the same kernel: keyframes per item = target / (bucket width)^2, clamped to [1, 32] (default 2560); a negative
+ * target selects the static item-to-warp schedule instead of the atomic work counter. */
+BORB_API borb_status borb_debug_set_bow_item_target(int target);
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 BORB_API borb_status borb_launch_count(const borb_extractor* e, uint64_t* n);
 /* Device time (ms, CUDA events on the handle's stream) of each stage of the last batch:

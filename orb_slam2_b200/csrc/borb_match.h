@@ -134,14 +134,17 @@ struct BowDbArgs {                // bowdb_match_kernel (k_bowdb.cu)
     int n_kf, n_items;            // keyframes to search; work items (frame node x keyframe range, the work list inside frame_block)
     const uint8_t* frame_block;   // packed query frame (FrameBlockHdr + sections), 16-byte aligned, frame_bytes % 16 == 0
     int frame_bytes, frame_in_smem;
+    int static_sched;             // 1: item i -> warp i mod (warps), 0: atomic work counter
     float nnratio;
     int check_ori;
     uint32_t* table_out;          // n_kf x m_frame, preset to 0xFFFFFFFF
+    int* hist_out;                // n_kf x 32 rotation-histogram counters, preset to 0
     int* work_counter;            // preset to 0
 };
 
 struct BowDbFinal {               // bowdb_finalize_kernel
     const uint32_t* table_out;
+    const int* hist;              // n_kf x 32 (BowDbArgs::hist_out)
     int n_kf, mf, check_ori;
     const uint16_t* forig;        // frame feature index per frame position
     int32_t* n_matches;           // n_kf
@@ -200,7 +203,7 @@ int launch_bow_match(const KfDev* qs, const KfDev* ts, int n_pairs, int mode, fl
 void host_image_bounds(int w, int h, const borb_camera& c, float* b4);
 int launch_frame_build(const FrameJob* d_jobs, int n_jobs, int max_n, const borb_camera& cam, int mode, int depth_type, float depth_factor, int w,
                        int h, int out_cap, borb_keypoint* keys_out, float* ur_out, float* depth_out, cudaStream_t s);
-int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, bool csa, int n_sm, cudaStream_t s);
+int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, int csa, int n_sm, cudaStream_t s);
 bool bowdb_frame_fits_smem(int frame_bytes);
 int launch_triangulation(const KfDev& q, const KfDev& t, const TriArgs& T, int32_t* vmatch, uint8_t* bins, int32_t* pairs, int cap,
                          int32_t* n_pairs, cudaStream_t s);

@@ -1223,8 +1223,11 @@ borb_status borb_kfdb_query(borb_matcher* m, borb_kfdb* db, const uint32_t* bow_
     return BORB_OK;
 }
 
-static std::atomic<int> g_bow_csa{1};
-borb_status borb_debug_set_bow_csa(int on) { g_bow_csa.store(on ? 1 : 0); return BORB_OK; }
+static std::atomic<int> g_bow_csa{2};
+static std::atomic<int> g_bow_item_target{8192};   // keyframes per work item = target / nt^2 (tuning knob of the measurement scripts)
+static std::atomic<int> g_bow_static{0};
+borb_status borb_debug_set_bow_item_target(int t) { g_bow_static.store(t < 0 ? 1 : 0); if (t < 0) t = -t; g_bow_item_target.store(t < 1 ? 1 : t); return BORB_OK; }
+borb_status borb_debug_set_bow_csa(int mode) { g_bow_csa.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); return BORB_OK; }
 
 namespace {
 
@@ -1274,7 +1277,7 @@ int pack_frame_block(const borb_keyframe_view* f, int n_kf, uint8_t* dst) {
     int items = 0;
     for (int p = 0; p < np; p++) {
         const long long nt = f->fv.start[pnode[p] + 1] - f->fv.start[pnode[p]];
-        long long cs = 2560 / (nt * nt);
+        long long cs = g_bow_item_target.load() / (nt * nt);
         cs = cs < 1 ? 1 : (cs > 32 ? 32 : cs);            // one 32-lane batch of keyframes per item at most
         pcs[p] = (int32_t)cs;
         pstart[p] = items;
@@ -1322,6 +1325,7 @@ borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, i
         const size_t input_end = st.off;
         o_ctr = st.reserve(256);                                                   // work counter | pair cursor
         o_nm = st.reserve((size_t)n_kf * 4); o_po = st.reserve((size_t)n_kf * 4);
+        const size_t o_hist = st.reserve((size_t)n_kf * 32 * 4);
         const size_t o_tab = st.reserve((size_t)n_kf * mf * 4);
         o_pairs = pairs ? st.reserve((size_t)pairs_cap * 4 + 16) : 0;
         o_dense = dense ? st.reserve((size_t)n_kf * dense_stride * 4) : 0;
@@ -1334,28 +1338,29 @@ borb_status bowdb_search(borb_matcher* m, borb_kfdb* db, const int32_t* slots, i
         if ((s = commit(st, total)) != BORB_OK) return s;
         b = m->arena;
         BORB_CUDA(cudaMemsetAsync(b + o_ctr, 0, 256, m->stream));
+        BORB_CUDA(cudaMemsetAsync(b + o_hist, 0, (size_t)n_kf * 32 * 4, m->stream));
         BORB_CUDA(cudaMemsetAsync(b + o_tab, 0xFF, (size_t)n_kf * mf * 4, m->stream));
         if (dense) BORB_CUDA(cudaMemsetAsync(b + o_dense, 0xFF, (size_t)n_kf * dense_stride * 4, m->stream));
         BowDbArgs A{};
         A.table = db->d_stream; A.slots = slots ? (const int32_t*)(b + o_sl) : nullptr; A.n_kf = n_kf;
-        A.n_items = n_items;
+        A.n_items = n_items; A.static_sched = g_bow_static.load();
         A.frame_block = b + o_fb; A.frame_bytes = (int)fbytes;
         A.frame_in_smem = bowdb_frame_fits_smem((int)fbytes) ? 1 : 0;
         A.nnratio = nnratio; A.check_ori = check_ori;
-        A.table_out = (uint32_t*)(b + o_tab); A.work_counter = (int*)(b + o_ctr);
+        A.table_out = (uint32_t*)(b + o_tab); A.work_counter = (int*)(b + o_ctr); A.hist_out = (int*)(b + o_hist);
         // results: counts, offsets and the compact pair list are written by the finalize kernel straight into the pinned landing
         // buffer (device-addressable, UVA) - no device-to-host copies; the dense table (MBs) still goes through one copy
         const size_t ho_nm = 0, ho_po = (size_t)n_kf * 4, ho_pairs = (size_t)n_kf * 8;
         if ((s = ensure_out(m, (size_t)n_kf * 8 + (size_t)pairs_cap * 4 + 64)) != BORB_OK) return s;
         uint8_t* ho = m->h_out;
         BowDbFinal F{};
-        F.table_out = A.table_out; F.n_kf = n_kf; F.mf = mf; F.check_ori = check_ori;
+        F.table_out = A.table_out; F.hist = A.hist_out; F.n_kf = n_kf; F.mf = mf; F.check_ori = check_ori;
         F.forig = (const uint16_t*)(b + o_fb + reinterpret_cast<const FrameBlockHdrHost*>(m->h_stage + o_fb)->off_orig);
         F.n_matches = (int32_t*)(ho + ho_nm); F.pair_off = (int32_t*)(ho + ho_po);
         F.pairs = pairs ? (uint32_t*)(ho + ho_pairs) : nullptr; F.pairs_cap = pairs_cap; F.cursor = (int*)(b + o_ctr + 64);
         F.dense = dense ? (int32_t*)(b + o_dense) : nullptr; F.dense_stride = dense_stride;
         if (m->timing) BORB_CUDA(cudaEventRecord(m->t0, m->stream));
-        m->launches += launch_bowdb(A, F, g_bow_csa.load() != 0, db->n_sm, m->stream);
+        m->launches += launch_bowdb(A, F, g_bow_csa.load(), db->n_sm, m->stream);
         if (m->timing) BORB_CUDA(cudaEventRecord(m->t1, m->stream));
         BORB_CUDA(cudaGetLastError());
     }

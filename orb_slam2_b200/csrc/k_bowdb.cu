@@ -35,15 +35,20 @@ constexpr int HISTO_LENGTH = 30;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool CSA>
+// 256-bit Hamming distance.  MODE 0: 8 POPC.  MODE 1: full carry-save adder tree, 4 POPC + 17 LOP3.  MODE 2 (default): three
+// 3:2 compressors, 5 POPC + 6 LOP3.  On sm_100 POPC issues on the XU pipe at 4 lanes/clk per SM sub-partition (8 cycles per
+// warp instruction) and LOP3 on the ALU pipe at 16 lanes/clk (2 cycles): per distance MODE 0 costs 64 XU cycles, MODE 1
+// 32 XU + ~60 ALU cycles (ALU-bound: ncu showed alu 73 %, xu 40 %), MODE 2 40 XU + ~34 ALU cycles - the balanced point.
+template <int MODE>
 __device__ __forceinline__ int ham256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
     const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
     const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
-    if (!CSA) return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
-    // carry-save adder tree: 8 words -> bit planes of weight 1, 2, 4, 8 (4 POPC instead of 8)
+    if (MODE == 0) return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
     const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 ^ x1));
     const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 ^ x4));
     const uint32_t s3 = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 ^ s2));
+    if (MODE == 2) return (__popc(s3) + __popc(x7)) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+    // full tree: 8 words -> bit planes of weight 1, 2, 4, 8
     const uint32_t ones = s3 ^ x7, c4 = s3 & x7;
     const uint32_t s5 = c1 ^ c2 ^ c3, c5 = (c1 & c2) | (c3 & (c1 ^ c2));
     const uint32_t twos = s5 ^ c4, c6 = s5 & c4;
@@ -86,7 +91,7 @@ struct KfRun { const uint2* meta; const uint4* desc; int rs, off; };     // rows
 // SAME nt columns (the frame features of node b), so the column loop has a warp-uniform trip count and warp-uniform
 // shared-memory addresses (one broadcast wavefront per load), and all 32 lanes hold a live row.  The number of keyframes per
 // item shrinks with nt^2 (the host's work list), widest buckets first, so the items are of similar cost.
-template <bool CSA, bool FSM>
+template <int CSA, bool FSM>
 __global__ void __launch_bounds__(32 * BDB_WARPS, BDB_CTAS) bowdb_match_kernel(BowDbArgs A) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) unsigned long long bar;
@@ -136,10 +141,15 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, BDB_CTAS) bowdb_match_kernel(B
     int4* qm = reinterpret_cast<int4*>(qd1 + BDB_QCAP);
 
     const int items = pstart[np];
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    int it_static = blockIdx.x + gridDim.x * wrp;                 // static schedule: consecutive (similar-cost) items go to different SMs
     while (true) {
         int it = 0;
-        if (lane == 0) it = atomicAdd(A.work_counter, 1);
-        it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (A.static_sched) { it = it_static; it_static += warps_total; }
+        else {
+            if (lane == 0) it = atomicAdd(A.work_counter, 1);
+            it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        }
         if (it >= items) break;
         int lo = 0, hi = np;                                      // largest p with pstart[p] <= it
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pstart[mid] <= it) lo = mid; else hi = mid; }
@@ -243,6 +253,7 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, BDB_CTAS) bowdb_match_kernel(B
                     if (lane == 0) {
                         const int bin = A.check_ori ? rot_bin(__uint_as_float(my), fangle[ts + pb]) : 0;
                         A.table_out[(size_t)(kb + rL) * mf + ts + pb] = (mx & 0xFFFFu) | ((uint32_t)bin << 16);   // vpMapPointMatches[bestIdxF] = pMP (:232)
+                        atomicAdd(&A.hist_out[(size_t)(kb + rL) * 32 + bin], 1);                                     // rotHist[bin].push_back (:241)
                     }
                 }
             };
@@ -287,19 +298,27 @@ __global__ void __launch_bounds__(32 * BDB_WARPS, BDB_CTAS) bowdb_match_kernel(B
 
 // Rotation-consistency cull and compaction, a 128-thread CTA per keyframe.  table_out row: one u32 per frame position
 // (FeatureVector order): keyframe feature | bin << 16, or 0xFFFFFFFF.  Survivors are written in frame-position order.
+// A warp owns a contiguous quarter of the row (its entries stay in registers between the passes when the row has at most
+// FIN_THREADS * FIN_REG positions), so the ordered compaction needs ballots and ONE block-level exchange of the warp totals.
 constexpr int FIN_THREADS = 128;
+constexpr int FIN_REG = 16;
 __global__ void __launch_bounds__(FIN_THREADS) bowdb_finalize_kernel(BowDbFinal F) {
     __shared__ int hist[32];
     __shared__ int warp_cnt[FIN_THREADS / 32];
     __shared__ int s_off, s_i1, s_i2, s_i3;
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int k = blockIdx.x;
-    if (tid < 32) hist[tid] = 0;
-    __syncthreads();
+    if (tid < 32) hist[tid] = F.hist[(size_t)k * 32 + tid];              // rotation histogram accumulated by the match kernel
     const uint32_t* row = F.table_out + (size_t)k * F.mf;
-    for (int i = tid; i < F.mf; i += FIN_THREADS) {
-        const uint32_t e = row[i];
-        if (e != 0xFFFFFFFFu) atomicAdd(&hist[(e >> 16) & 31], 1);
+    const int per_warp = (((F.mf + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32)) + 31) & ~31;      // positions per warp, whole 32-steps
+    const int w0 = wrp * per_warp, w1 = min(F.mf, w0 + per_warp);
+    const bool in_regs = per_warp <= 32 * FIN_REG;
+    const bool need_rows = F.pairs != nullptr || F.dense != nullptr;
+    uint32_t e[FIN_REG];
+#pragma unroll
+    for (int t = 0; t < FIN_REG; t++) {
+        const int i = w0 + t * 32 + lane;
+        e[t] = (need_rows && in_regs && i < w1) ? row[i] : 0xFFFFFFFFu;
     }
     __syncthreads();
     if (tid == 0) {
@@ -318,25 +337,41 @@ __global__ void __launch_bounds__(FIN_THREADS) bowdb_finalize_kernel(BowDbFinal 
     __syncthreads();
     if (!F.pairs && !F.dense) return;
     const int i1 = s_i1, i2 = s_i2, i3 = s_i3;
-    int run = s_off;
-    for (int base = 0; base < F.mf; base += FIN_THREADS) {
-        const int i = base + tid;
-        const uint32_t e = i < F.mf ? row[i] : 0xFFFFFFFFu;
-        bool keep = e != 0xFFFFFFFFu;
-        if (keep && F.check_ori) { const int b = (int)((e >> 16) & 31); keep = b == i1 || b == i2 || b == i3; }
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-        if (lane == 0) warp_cnt[wrp] = __popc(bal);
-        __syncthreads();
-        int before = 0, all = 0;
+    auto kept_entry = [&](uint32_t v) -> bool {
+        if (v == 0xFFFFFFFFu) return false;
+        if (!F.check_ori) return true;
+        const int b = (int)((v >> 16) & 31);
+        return b == i1 || b == i2 || b == i3;
+    };
+    // survivors per warp
+    int mine = 0;
+    if (in_regs) {
 #pragma unroll
-        for (int w = 0; w < FIN_THREADS / 32; w++) { const int c = warp_cnt[w]; if (w < wrp) before += c; all += c; }
+        for (int t = 0; t < FIN_REG; t++) mine += kept_entry(e[t]) ? 1 : 0;
+    } else {
+        for (int i = w0 + lane; i < w1; i += 32) mine += kept_entry(row[i]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+    if (lane == 0) warp_cnt[wrp] = mine;
+    __syncthreads();
+    int run = s_off;
+    for (int w = 0; w < wrp; w++) run += warp_cnt[w];
+    auto emit = [&](uint32_t v, int i) {
+        const bool keep = kept_entry(v);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
         if (keep) {
-            const int j = (int)F.forig[i], r = (int)(e & 0xFFFFu);
-            if (F.pairs) { const int pos = run + before + __popc(bal & ((1u << lane) - 1)); if (pos < F.pairs_cap) F.pairs[pos] = (uint32_t)j | ((uint32_t)r << 16); }
+            const int j = (int)F.forig[i], r = (int)(v & 0xFFFFu);
+            if (F.pairs) { const int pos = run + __popc(bal & ((1u << lane) - 1)); if (pos < F.pairs_cap) F.pairs[pos] = (uint32_t)j | ((uint32_t)r << 16); }
             if (F.dense) F.dense[(size_t)k * F.dense_stride + j] = r;
         }
-        run += all;
-        __syncthreads();
+        run += __popc(bal);
+    };
+    if (in_regs) {
+#pragma unroll
+        for (int t = 0; t < FIN_REG; t++) emit(e[t], w0 + t * 32 + lane);
+    } else {
+        for (int i0 = w0; i0 < w1; i0 += 32) { const int i = i0 + lane; emit(i < w1 ? row[i] : 0xFFFFFFFFu, i); }
     }
 }
 
@@ -351,15 +386,19 @@ static int bowdb_warps(int frame_bytes, bool fsm) {
 
 bool bowdb_frame_fits_smem(int frame_bytes) { return bowdb_warps(frame_bytes, true) >= 8; }
 
-int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, bool csa, int n_sm, cudaStream_t s) {
+int launch_bowdb(const BowDbArgs& A, const BowDbFinal& F, int csa, int n_sm, cudaStream_t s) {
     const bool fsm = A.frame_in_smem != 0;
     const int warps = bowdb_warps(A.frame_bytes, fsm);
     const size_t smem = (fsm ? (((size_t)A.frame_bytes + 127) & ~size_t(127)) : 0) + (size_t)warps * BDB_WARP_BYTES;
     int ctas = (A.n_items + warps - 1) / warps;
     if (ctas > n_sm * BDB_CTAS) ctas = n_sm * BDB_CTAS;
     if (ctas < 1) ctas = 1;
-    void (*kern)(BowDbArgs) = csa ? (fsm ? bowdb_match_kernel<true, true> : bowdb_match_kernel<true, false>)
-                                  : (fsm ? bowdb_match_kernel<false, true> : bowdb_match_kernel<false, false>);
+    void (*kern)(BowDbArgs) = nullptr;
+    switch (csa) {
+        case 0: kern = fsm ? bowdb_match_kernel<0, true> : bowdb_match_kernel<0, false>; break;
+        case 1: kern = fsm ? bowdb_match_kernel<1, true> : bowdb_match_kernel<1, false>; break;
+        default: kern = fsm ? bowdb_match_kernel<2, true> : bowdb_match_kernel<2, false>; break;
+    }
     allow_max_smem((const void*)kern);
     kern<<<ctas, 32 * warps, smem, s>>>(A);
     bowdb_finalize_kernel<<<F.n_kf, FIN_THREADS, 0, s>>>(F);

@@ -399,36 +399,53 @@ __global__ void __launch_bounds__(256) kfdb_score_kernel(const BowDev* __restric
         qword = sw; qvalue = sv;
     }
     const int warps_total = gridDim.x * (blockDim.x >> 5);
+    const int steps = nq > 0 ? 32 - __clz(nq) : 0;                    // iterations that finish any lower_bound over nq entries
+    constexpr int U = 8;                                              // keyframe words per lane in flight: the loads and the U searches overlap
     for (int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); slot < n_slots; slot += warps_total) {
         const BowDev kf = table[slot];
         double acc = 0.0;
         int ncommon = 0;
         uint32_t first = 0xFFFFFFFFu;
-        for (int base = 0; base < kf.n; base += 32) {
-            const int i = base + lane;
-            bool found = false;
-            double term = 0.0;
-            uint32_t w = 0;
-            if (i < kf.n) {
-                w = kf.word[i];
-                int lo = 0, hi = nq;                                  // lower_bound of w in the query words
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (qword[mid] < w) lo = mid + 1; else hi = mid;
-                }
-                if (lo < nq && qword[lo] == w) {
-                    found = true;
-                    const double vi = qvalue[lo], wi = kf.value[i];   // v1 = query (F->mBowVec), v2 = keyframe
-                    term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
+        for (int base = 0; base < kf.n; base += 32 * U) {
+            uint32_t w[U];
+            int lo[U], hi[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = base + u * 32 + lane;
+                w[u] = i < kf.n ? kf.word[i] : 0xFFFFFFFFu;
+                lo[u] = 0; hi[u] = i < kf.n ? nq : 0;
+            }
+            for (int st = 0; st < steps; st++) {                      // lower_bound of w[u] in the query words, U searches interleaved
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (lo[u] < hi[u]) {
+                        const int mid = (lo[u] + hi[u]) >> 1;
+                        if (qword[mid] < w[u]) lo[u] = mid + 1; else hi[u] = mid;
+                    }
                 }
             }
-            unsigned bal = __ballot_sync(0xFFFFFFFFu, found);
-            if (bal && first == 0xFFFFFFFFu) first = __shfl_sync(0xFFFFFFFFu, w, __ffs(bal) - 1);
-            ncommon += __popc(bal);
-            while (bal) {                                             // ordered accumulation: ascending word id
-                const int src = __ffs(bal) - 1;
-                bal &= bal - 1;
-                acc = __dadd_rn(acc, __shfl_sync(0xFFFFFFFFu, term, src));
+            double term[U];
+            bool found[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = base + u * 32 + lane;
+                found[u] = i < kf.n && lo[u] < nq && qword[lo[u]] == w[u];
+                term[u] = 0.0;
+                if (found[u]) {
+                    const double vi = qvalue[lo[u]], wi = kf.value[i];   // v1 = query (F->mBowVec), v2 = keyframe
+                    term[u] = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                unsigned bal = __ballot_sync(0xFFFFFFFFu, found[u]);
+                if (bal && first == 0xFFFFFFFFu) first = __shfl_sync(0xFFFFFFFFu, w[u], __ffs(bal) - 1);
+                ncommon += __popc(bal);
+                while (bal) {                                         // ordered accumulation: ascending word id
+                    const int src = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    acc = __dadd_rn(acc, __shfl_sync(0xFFFFFFFFu, term[u], src));
+                }
             }
         }
         if (lane == 0) {
@@ -756,9 +773,9 @@ int launch_kfdb_score(const BowDev* table, int n_slots, const uint32_t* qword, c
         const size_t smem = (size_t)nq * 12 + 16;
         const int in_smem = smem <= 160 * 1024;
         if (in_smem) allow_max_smem((const void*)kfdb_score_kernel);
-        int ctas = (n_slots + 7) / 8;
-        if (ctas > 148 * 4) ctas = 148 * 4;                           // persistent: the query is staged once per CTA
-        kfdb_score_kernel<<<ctas, 256, in_smem ? smem : 0, s>>>(table, n_slots, qword, qvalue, nq, in_smem, common, score, first_word);
+        int ctas = (n_slots + 3) / 4;                                 // 4 keyframes (warps) per CTA: 2000 keyframes spread over all SMs
+        if (ctas > 148 * 8) ctas = 148 * 8;                           // persistent: the query is staged once per CTA
+        kfdb_score_kernel<<<ctas, 128, in_smem ? smem : 0, s>>>(table, n_slots, qword, qvalue, nq, in_smem, common, score, first_word);
     }
     return 1;
 }
