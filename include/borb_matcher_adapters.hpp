@@ -15,7 +15,9 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <set>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -32,6 +34,38 @@ inline borb_matcher* thread_matcher(int device = 0) {
     return m;
 }
 
+// Device-resident copies of Frames (borb_frame: keypoints, descriptors, mvuRight and the 64x48 grid stay in HBM between the
+// matcher calls of one Tracking::Track()).  The code that builds a Frame registers the handle it got from
+// borb_frames_from_extractor / borb_frame_create under the Frame's address; every adapter below then searches the resident
+// copy (borb_frame_view::resident) and only the query side crosses PCIe.  Frame's copy constructor / destructor call
+// bind_resident(this, handle_of(other)) / unbind_resident(this) — or, without touching Frame, Tracking does it where it
+// assigns mCurrentFrame / mLastFrame.  A binding does not own the handle unless `owned` is set.
+struct ResidentRegistry {
+    std::mutex mu;
+    std::unordered_map<const void*, std::pair<borb_frame*, bool>> map;
+};
+inline ResidentRegistry& resident_registry() { static ResidentRegistry r; return r; }
+inline void unbind_resident(const void* frame) {
+    ResidentRegistry& r = resident_registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    auto it = r.map.find(frame);
+    if (it == r.map.end()) return;
+    if (it->second.second) borb_frame_destroy(it->second.first);
+    r.map.erase(it);
+}
+inline void bind_resident(const void* frame, borb_frame* h, bool owned = false) {
+    unbind_resident(frame);
+    ResidentRegistry& r = resident_registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    r.map[frame] = std::make_pair(h, owned);
+}
+inline const borb_frame* resident_of(const void* frame) {
+    ResidentRegistry& r = resident_registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    auto it = r.map.find(frame);
+    return it == r.map.end() ? nullptr : it->second.first;
+}
+
 template <class FrameT>
 inline borb_frame_view frame_view(const FrameT& F, const uint8_t* occupied) {
     static_assert(sizeof(cv::KeyPoint) == sizeof(borb_keypoint), "cv::KeyPoint must be the 28-byte POD layout");
@@ -44,8 +78,19 @@ inline borb_frame_view frame_view(const FrameT& F, const uint8_t* occupied) {
     v.min_x = F.mnMinX; v.min_y = F.mnMinY; v.max_x = F.mnMaxX; v.max_y = F.mnMaxY;   // static members of Frame in the reference
     v.n_levels = (int32_t)F.mvScaleFactors.size();
     v.scale_factors = F.mvScaleFactors.data();
-    v.resident = nullptr;
+    v.resident = resident_of(&F);
     return v;
+}
+
+// Uploads a Frame's own host members once (for Frames that were not built by borb_frames_from_extractor) and binds the copy.
+template <class FrameT>
+inline borb_frame* make_resident(const FrameT& F, int device = 0) {
+    unbind_resident(&F);
+    const borb_frame_view v = frame_view(F, nullptr);
+    borb_frame* h = nullptr;
+    check(borb_frame_create(thread_matcher(device), &v, &h), "borb_frame_create");
+    bind_resident(&F, h, true);
+    return h;
 }
 
 // DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) -> CSR, in map order

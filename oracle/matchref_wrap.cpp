@@ -10,6 +10,10 @@
 
 #include "ORBmatcher.h"
 #include "orb_port.h"
+#ifdef BORB_ADAPTER_NO_EXTRACTOR          // the build of the PRODUCT's adapters (oracle/Makefile: libadaptmatch.so), not of the reference
+#include <cstdlib>
+#include "borb_matcher_adapters.hpp"
+#endif
 
 using namespace ORB_SLAM2;
 
@@ -68,6 +72,11 @@ void build_frame(Frame& F, const FrameArgs& a) {
     F.mvpMapPoints.assign(a.n, nullptr);
     F.mvbOutlier.assign(a.n, false);
     F.grid.build(F.mvKeysUn, a.minX, a.minY, a.maxX, a.maxY);
+#ifdef BORB_ADAPTER_NO_EXTRACTOR
+    // tests/test_gpu_adapters.py runs every fixture a second time with the current frame device-resident (borb_frame)
+    if (std::getenv("BORB_ADAPT_RESIDENT") && a.n > 0 && a.sf) borb::adapt::make_resident(F);
+    else borb::adapt::unbind_resident(&F);
+#endif
 }
 void build_keyframe(KeyFrame& K, const FrameArgs& a) {
     K.N = a.n;

@@ -24,13 +24,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ADAPT_SO = os.path.join(ROOT, "oracle", "_ref", "libadaptmatch.so")
 
 
-@pytest.fixture(scope="module")
-def O(oracle):
+@pytest.fixture(scope="module", params=["host_view", "resident_frame"])
+def O(oracle, request):
+    """host_view: the adapters pass the Frame's host arrays with every call; resident_frame: the wrapper binds a device-resident
+    copy of every Frame it builds (borb::adapt::make_resident -> borb_frame_create), so the same fixtures exercise
+    borb_frame_view::resident through the adapters (BORB_ADAPT_RESIDENT is read by oracle/matchref_wrap.cpp per call)."""
     if not os.path.exists(ADAPT_SO):
         pytest.skip("oracle/_ref/libadaptmatch.so not built (needs the reference tree's DBoW2 FeatureVector at build time)")
     saved = oracle.MATCHREF_SO
     oracle.MATCHREF_SO = ADAPT_SO                     # every oracle.ref_* matcher call now runs the ADAPTERS on the GPU
+    if request.param == "resident_frame":
+        os.environ["BORB_ADAPT_RESIDENT"] = "1"
     yield oracle
+    os.environ.pop("BORB_ADAPT_RESIDENT", None)
     oracle.MATCHREF_SO = saved
 
 
