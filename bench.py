@@ -951,6 +951,13 @@ def run_config4(args, env: Env):
         return
     peak, peak_src = hbm_peak()
     achieved = db_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "bowdb_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"] * n_kf / tj["keyframes_per_launch"]
+        traffic_src = tj.get("source", "static ncu capture (profiles/), not measured in this run")
     h2d = Q * (2 * W * H) + Q * (int(nq.mean()) * (32 + 2 + 4 + 4 + 12) + 4096)
     d2h = Q * (2 * cap * 60 + 8 * cap + n_kf * 20 + int(state["pairs"]) * 4 + int(nq.mean()) * 16)
     cpu = None
@@ -971,7 +978,8 @@ def run_config4(args, env: Env):
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * inner_e, "d2h_bytes_per_step": d2h * inner_e},
             "roofline": {"kernel": "bowdb_match_kernel (+ bowdb_finalize_kernel)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": db_bytes, "mean_launch_ms": kernel_ms},
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": db_bytes, "mean_launch_ms": kernel_ms},
             "cpu_baseline": cpu}
     if voc_ms is not None:
         line["nccl"] = {"vocabulary_broadcast_ms": voc_ms, "vocabulary_bytes": voc_bytes}

@@ -88,4 +88,30 @@ int dbowref_detect_candidates(void* h, int loop, int n_kf, const int32_t* kf_sta
     return (int)res.size();
 }
 
+// A SEQUENCE of DetectRelocalizationCandidates calls on the same database and KeyFrame objects: KeyFrame::mRelocScore persists
+// between the queries, and the covisibility accumulation (:262-275) reads it for neighbours the current query did not score.
+// q_start: n_q + 1 offsets into q_word / q_value; out: n_q rows of `out_stride` slots, out_n[i] = candidates of query i.
+int dbowref_reloc_sequence(void* h, int n_kf, const int32_t* kf_start, const uint32_t* kf_word, const double* kf_value, int n_q,
+                           const int32_t* q_start, const uint32_t* q_word, const double* q_value, const int32_t* neigh, int32_t* out,
+                           int out_stride, int32_t* out_n) {
+    ORBVocabulary* voc = static_cast<ORBVocabulary*>(h);
+    KeyFrameDatabase db(*voc);
+    std::vector<KeyFrame> kfs(n_kf);
+    for (int k = 0; k < n_kf; k++) {
+        kfs[k].mnId = k;
+        kfs[k].mBowVec = make_bow(kf_word + kf_start[k], kf_value + kf_start[k], kf_start[k + 1] - kf_start[k]);
+        for (int j = 0; j < 10 && neigh[(size_t)k * 10 + j] >= 0; j++) kfs[k].covisible.push_back(&kfs[neigh[(size_t)k * 10 + j]]);
+    }
+    for (int k = 0; k < n_kf; k++) db.add(&kfs[k]);
+    for (int i = 0; i < n_q; i++) {
+        Frame F;
+        F.mnId = n_kf + 7 + i;
+        F.mBowVec = make_bow(q_word + q_start[i], q_value + q_start[i], q_start[i + 1] - q_start[i]);
+        const std::vector<KeyFrame*> res = db.DetectRelocalizationCandidates(&F);
+        out_n[i] = (int32_t)res.size();
+        for (size_t j = 0; j < res.size() && (int)j < out_stride; j++) out[(size_t)i * out_stride + j] = (int32_t)(res[j] - &kfs[0]);
+    }
+    return 0;
+}
+
 }  // extern "C"

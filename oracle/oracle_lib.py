@@ -939,6 +939,25 @@ class RefVocabulary:
               len(qw), _ptr(cn), _ptr(ng), float(np.float32(min_score)), _ptr(out))
         return out[:n].tolist()
 
+    def reloc_sequence(self, kf_bows, q_bows, neigh):
+        """DetectRelocalizationCandidates for every query of `q_bows` IN SEQUENCE on one database (KeyFrame::mRelocScore persists)."""
+        start = np.zeros(len(kf_bows) + 1, np.int32)
+        start[1:] = np.cumsum([len(b) for b in kf_bows])
+        kw = _a(np.concatenate([np.fromiter(b.keys(), np.uint32, len(b)) for b in kf_bows] + [np.zeros(0, np.uint32)]), np.uint32)
+        kv = _a(np.concatenate([np.fromiter(b.values(), np.float64, len(b)) for b in kf_bows] + [np.zeros(0, np.float64)]), np.float64)
+        qs = np.zeros(len(q_bows) + 1, np.int32)
+        qs[1:] = np.cumsum([len(b) for b in q_bows])
+        qw = _a(np.concatenate([np.fromiter(b.keys(), np.uint32, len(b)) for b in q_bows] + [np.zeros(1, np.uint32)]), np.uint32)
+        qv = _a(np.concatenate([np.fromiter(b.values(), np.float64, len(b)) for b in q_bows] + [np.zeros(1, np.float64)]), np.float64)
+        ng = _a(np.asarray(neigh, np.int32).reshape(len(kf_bows), 10), np.int32)
+        stride = max(len(kf_bows), 1)
+        out = np.zeros((len(q_bows), stride), np.int32); out_n = np.zeros(len(q_bows), np.int32)
+        f = self._lib.dbowref_reloc_sequence
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+        f(self._h, len(kf_bows), _ptr(start), _ptr(kw), _ptr(kv), len(q_bows), _ptr(qs), _ptr(qw), _ptr(qv), _ptr(ng), _ptr(out), stride, _ptr(out_n))
+        return [out[i, :out_n[i]].tolist() for i in range(len(q_bows))]
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # The reference's src/MapPoint.cc compiled verbatim against its real include/MapPoint.h (oracle/_ref/libmapref.so).

@@ -65,6 +65,12 @@ class ORBextractor:
     def GetScaleSigmaSquares(self) -> np.ndarray: return self._sigma2.copy()
     def GetInverseScaleSigmaSquares(self) -> np.ndarray: return self._inv_sigma2.copy()
 
+    def _work_capacity(self, raw_w: int, raw_h: int) -> int:
+        """Output capacity for frames of raw size (raw_w, raw_h): with rectification maps installed the extractor works on the
+        maps' destination size, which may differ from the raw frame's."""
+        rs = getattr(self, "_rect_size", None)
+        return self.capacity(*rs) if rs is not None else self.capacity(raw_w, raw_h)
+
     def capacity(self, width: int, height: int) -> int:
         cap = C.c_int32()
         check(self._lib.borb_extractor_capacity(self._h, width, height, C.byref(cap)), "borb_extractor_capacity")
@@ -86,6 +92,8 @@ class ORBextractor:
         frames (default: same as the maps).  None removes the maps."""
         if map_x is None or map_y is None:
             check(self._lib.borb_extractor_set_rectify_maps(self._h, int(which), None, None, 0, 0, 0, 0), "borb_extractor_set_rectify_maps")
+            if which == 0:
+                self._rect_size = None
             return
         mx = np.ascontiguousarray(map_x, np.float32); my = np.ascontiguousarray(map_y, np.float32)
         assert mx.shape == my.shape and mx.ndim == 2
@@ -111,7 +119,7 @@ class ORBextractor:
         if image.strides[-1] != 1 or (ch > 1 and image.strides[1] != ch):
             image = np.ascontiguousarray(image)
         h, w = image.shape[:2]
-        cap = self.capacity(w, h)
+        cap = self._work_capacity(w, h)
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         n = C.c_int32(0)
@@ -128,7 +136,7 @@ class ORBextractor:
         h, w = images[0].shape[:2]
         assert all(im.shape == images[0].shape for im in images), "a batch holds images of one size"
         self._set_format(1 if images[0].ndim == 2 else images[0].shape[2])
-        cap = self.capacity(w, h)
+        cap = self._work_capacity(w, h)
         kps = np.zeros((n, cap), KP_DTYPE)
         desc = np.zeros((n, cap, 32), np.uint8)
         cnt = np.zeros(n, np.int32)
@@ -175,7 +183,7 @@ class ORBextractor:
         lefts = [np.ascontiguousarray(im, np.uint8) for im in lefts]
         rights = [np.ascontiguousarray(im, np.uint8) for im in rights]
         h, w = lefts[0].shape
-        cap = self.capacity(w, h)
+        cap = self._work_capacity(w, h)
         b = np.float32(bf) / np.float32(fx)
         kl = np.zeros((n, cap), KP_DTYPE); kr = np.zeros((n, cap), KP_DTYPE)
         dl = np.zeros((n, cap, 32), np.uint8); dr = np.zeros((n, cap, 32), np.uint8)

@@ -480,15 +480,23 @@ def _sharing_order(cw, fw, seq, skip=()):
     return sorted(s, key=lambda i: (int(fw[i]), seq[i]))
 
 
-def relocalization_candidates(cw, sc, fw, seq, covisibility) -> list:
+def relocalization_candidates(cw, sc, fw, seq, covisibility, reloc_score: Optional[dict] = None) -> list:
     """The host part of KeyFrameDatabase::DetectRelocalizationCandidates (src/KeyFrameDatabase.cc:226-310) from the per-keyframe
-    shared-word counts `cw`, float L1 scores `sc` and first shared words `fw` (borb_kfdb_query)."""
+    shared-word counts `cw`, float L1 scores `sc` and first shared words `fw` (borb_kfdb_query).
+    `reloc_score` is the database's persistent {slot: KeyFrame::mRelocScore}: the reference assigns mRelocScore only to keyframes
+    above minCommonWords (:236-243) and the covisibility accumulation (:262-275) reads the field of EVERY neighbour that shares a
+    word with the query — for a neighbour below the threshold that is the value an EARLIER query left there.  Passing the same
+    dict to successive queries reproduces that; None (or a fresh dict) is a fresh database, where the field is 0."""
+    if reloc_score is None:
+        reloc_score = {}
     sharing = _sharing_order(cw, fw, seq)
     if not sharing:
         return []
     maxCommonWords = max(int(cw[s]) for s in sharing)
     minCommonWords = int(np.float32(maxCommonWords) * np.float32(0.8))
     scored = [(np.float32(sc[s]), s) for s in sharing if cw[s] > minCommonWords]
+    for si, s in scored:
+        reloc_score[s] = si                               # pKFi->mRelocScore = si (:241)
     if not scored:
         return []
     acc, bestAcc = [], np.float32(0)
@@ -497,9 +505,7 @@ def relocalization_candidates(cw, sc, fw, seq, covisibility) -> list:
         for s2 in covisibility(s):
             if cw[s2] <= 0:
                 continue                                  # mnRelocQuery != F->mnId: shares no word with the query
-            # mRelocScore is only assigned to keyframes above minCommonWords (:236-243); others still hold their old value.
-            # The reference reads that stale field; a fresh database has 0 there, which is what the mirror uses.
-            r = np.float32(sc[s2]) if cw[s2] > minCommonWords else np.float32(0)
+            r = np.float32(reloc_score.get(s2, 0.0))      # pKF2->mRelocScore: this query's score, or the stale one (see above)
             accScore = np.float32(accScore + r)
             if r > bestScore:
                 best, bestScore = s2, r
@@ -579,6 +585,7 @@ class KeyFrameDatabase:
         check(self._lib.borb_kfdb_create(device, C.byref(h)), "borb_kfdb_create")
         self._h = h
         self._seq = []                  # insertion sequence number per slot (inverted-file list order)
+        self._reloc_score = {}          # KeyFrame::mRelocScore per slot, persistent across queries as in the reference
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -601,10 +608,12 @@ class KeyFrameDatabase:
 
     def erase(self, slot: int) -> None:
         check(self._lib.borb_kfdb_erase(self._h, int(slot)), "borb_kfdb_erase")
+        self._reloc_score.pop(int(slot), None)
 
     def clear(self) -> None:
         check(self._lib.borb_kfdb_clear(self._h), "borb_kfdb_clear")
         self._seq = []
+        self._reloc_score = {}
 
     def set_has_mp(self, slot: int, has_mp: np.ndarray) -> None:
         hm = np.ascontiguousarray(has_mp, np.uint8)
@@ -628,7 +637,7 @@ class KeyFrameDatabase:
     def DetectRelocalizationCandidates(self, mBowVec: Dict[int, float], covisibility) -> list:
         """src/KeyFrameDatabase.cc:199-310.  covisibility(slot) -> up to 10 slots (GetBestCovisibilityKeyFrames(10))."""
         cw, sc, fw = self.query(mBowVec)
-        return relocalization_candidates(cw, sc, fw, self._seq, covisibility)
+        return relocalization_candidates(cw, sc, fw, self._seq, covisibility, self._reloc_score)
 
     def DetectLoopCandidates(self, mBowVec: Dict[int, float], connected, covisibility, minScore: float) -> list:
         """src/KeyFrameDatabase.cc:76-197.  connected: slots of pKF->GetConnectedKeyFrames(); covisibility as above."""

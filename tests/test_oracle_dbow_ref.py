@@ -94,3 +94,43 @@ def test_keyframe_database_equals_reference_source(world):
             assert M.loop_candidates(cw, sc, fw, seq, set(conn), covis, min_score) == ref
             total += len(ref)
     assert total > 10
+
+
+def test_relocalization_reads_stale_scores_like_the_reference(world):
+    """KeyFrame::mRelocScore is assigned only to keyframes above minCommonWords (src/KeyFrameDatabase.cc:236-243) but read for every
+    covisible neighbour that shares a word with the query (:262-275): on a long-running database a neighbour below the threshold
+    contributes the score an EARLIER query left there.  The product keeps that field per slot (KeyFrameDatabase._reloc_score);
+    a sequence of queries through the verbatim reference (one database, persistent KeyFrame objects) must give the same lists,
+    and the sequence must differ somewhere from what a fresh database returns for the same query (otherwise the case is vacuous)."""
+    from orb_slam2_b200 import matcher as M
+    O, rv = world["O"], world["rv"]
+    rng = np.random.default_rng(21)
+    n_words, n_kf = rv.words, 80
+    centers = [rng.choice(n_words, 120, replace=False) for _ in range(5)]
+
+    def bow_near(c, keep_p):
+        keep = centers[c][rng.random(120) < keep_p]
+        w = np.unique(np.concatenate([keep, rng.choice(n_words, 20, replace=False)]))
+        val = rng.random(len(w)); val /= val.sum()
+        return dict(zip(w.tolist(), val.tolist()))
+    place = rng.integers(0, 5, n_kf)
+    # keyframes share between 35 % and 95 % of their place's words: plenty of neighbours end up BELOW 0.8 x maxCommonWords
+    bows = [bow_near(int(p), float(rng.uniform(0.35, 0.95))) for p in place]
+    neigh = np.full((n_kf, 10), -1, np.int32)
+    for s in range(n_kf):
+        same = [int(x) for x in rng.permutation(np.nonzero(place == place[s])[0]) if x != s]
+        nb = [x for x in dict.fromkeys(same[:8] + rng.integers(0, n_kf, 2).tolist()) if x != s][:10]
+        neigh[s, :len(nb)] = nb
+    covis = lambda s: [int(x) for x in neigh[s] if x >= 0]
+    seq = list(range(n_kf))
+    queries = [bow_near(int(c), float(kp)) for c, kp in zip(rng.integers(0, 5, 14), rng.uniform(0.5, 0.95, 14))]
+    ref_seq = rv.reloc_sequence(bows, queries, neigh)
+    state = {}
+    differs_from_fresh = 0
+    for q, ref in zip(queries, ref_seq):
+        per = [O.port_bow_score(q, b) for b in bows]
+        sc = np.array([np.float32(p[0]) for p in per], np.float32); cw = np.array([p[1] for p in per], np.int32); fw = np.array([p[2] for p in per], np.uint32)
+        assert M.relocalization_candidates(cw, sc, fw, seq, covis, state) == ref
+        differs_from_fresh += M.relocalization_candidates(cw, sc, fw, seq, covis) != ref
+    assert sum(len(r) for r in ref_seq) > 10
+    assert differs_from_fresh > 0, "no query of the sequence depended on a stale mRelocScore: strengthen the fixture"
