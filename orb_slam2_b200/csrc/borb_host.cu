@@ -213,7 +213,7 @@ void free_workspace(Workspace& ws) {
     cudaFree(ws.pyr); cudaFree(ws.blur); cudaFree(ws.cand); cudaFree(ws.cand_cnt); cudaFree(ws.pnode); cudaFree(ws.sel);
     cudaFree(ws.sel_cnt); cudaFree(ws.kps); cudaFree(ws.desc); cudaFree(ws.nkp); cudaFree(ws.u_right); cudaFree(ws.depth);
     cudaFree(ws.sad); cudaFree(ws.tabs); cudaFree(ws.pair_idx); cudaFree(ws.st_bins); cudaFree(ws.st_recs); cudaFree(ws.stage);
-    free(ws.fast_tmaps);
+    free(ws.fast_tmaps); cudaFree(ws.fast_tiles);
     ws = Workspace();
 }
 
@@ -258,6 +258,7 @@ borb_status ensure(borb_extractor* e, int w, int h, int n_images) {
     ws.max_images = (int)n;
     ws.fast_tmaps = malloc(fast_tmaps_bytes());
     if ((st = build_fast_tmaps(g, ws, ws.fast_tmaps)) != BORB_OK) return st;
+    if ((st = build_fast_tiles(g, ws)) != BORB_OK) return st;
     e->have_geom = true;
     return BORB_OK;
 }

@@ -90,6 +90,8 @@ struct Workspace {
     uint8_t* stage = nullptr;      // tightly packed H2D landing buffer (grow-only)
     size_t stage_bytes = 0;
     void* fast_tmaps = nullptr;    // HOST: per-level CUtensorMap set for fast_kernel (passed by value at launch)
+    void* fast_tiles = nullptr;    // DEVICE: one 16-byte descriptor per FAST CTA of an image (k_fast.cu: FastTile), n = fast_n_tiles
+    int fast_n_tiles = 0;
 };
 
 void set_error(const char* fmt, ...);
@@ -136,6 +138,7 @@ size_t stereo_bins_bytes_per_pair();
 size_t stereo_rec_bytes();
 size_t quadtree_smem_bytes(int node_cap);
 borb_status build_fast_tmaps(const Geometry& g, const Workspace& ws, void* out_tmaps);
+borb_status build_fast_tiles(const Geometry& g, Workspace& ws);
 size_t fast_tmaps_bytes();
 
 }  // namespace borb
