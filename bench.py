@@ -871,36 +871,86 @@ def run_config4(args, env: Env):
     from orb_slam2_b200._lib import KP_DTYPE
     qk = [np.ascontiguousarray(o["kl"][q, :nq[q]].numpy()).view(KP_DTYPE).reshape(-1).copy() for q in range(Q)]
     qd = [np.ascontiguousarray(o["dl"][q, :nq[q]].numpy()).copy() for q in range(Q)]
-    # reusable call buffers
+    # NH query streams in flight per GPU (independent relocalising / loop-closing agents on one map): each host thread owns a matcher
+    # handle, a vocabulary handle (sharing the device blob), an extractor and its call buffers; the database is shared.
+    NH = max(1, args.handles)
     nmax = int(nq.max())
-    bw = np.zeros(nmax, np.uint32); bv = np.zeros(nmax, np.float64); fnode = np.zeros(nmax, np.uint32); fstart = np.zeros(nmax + 1, np.int32); fidx = np.zeros(nmax, np.uint32)
-    nb, nn = C.c_int32(0), C.c_int32(0)
-    cw = np.zeros(n_kf, np.int32); sc = np.zeros(n_kf, np.float32); fw = np.zeros(n_kf, np.uint32); ns = C.c_int32(0)
-    nm = np.zeros(n_kf, np.int32); off = np.zeros(n_kf, np.int32)
-    pairs_cap = n_kf * 64 + 65536
-    pairs = np.zeros(pairs_cap, np.uint32); npairs = C.c_int32(0)
-    kfv = M._KeyFrameViewC()
     vp = lambda a: a.ctypes.data
-    state = dict(pairs=0, best=0)
+    pairs_cap = n_kf * 64 + 65536
+    vptr, vbytes = voc.blob()
+
+    class QStream:
+        def __init__(self, t):
+            self.mt = mt if t == 0 else M.ORBmatcher(0.75, True, device=local_rank)
+            self.voc = voc if t == 0 else M.ORBVocabulary.from_blob(vptr, vbytes, device=local_rank)
+            self.X = X if t == 0 else ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank)
+            if t:
+                self.X.reserve(W, H, 2 * Q)
+            self.o = o if t == 0 else dict(kl=torch.empty((Q, cap, 28), dtype=torch.uint8).pin_memory(), kr=torch.empty((Q, cap, 28), dtype=torch.uint8).pin_memory(),
+                                           dl=torch.empty((Q, cap, 32), dtype=torch.uint8).pin_memory(), dr=torch.empty((Q, cap, 32), dtype=torch.uint8).pin_memory(),
+                                           nl=torch.zeros(Q, dtype=torch.int32).pin_memory(), nr=torch.zeros(Q, dtype=torch.int32).pin_memory(),
+                                           ur=torch.empty((Q, cap), dtype=torch.float32).pin_memory(), dp=torch.empty((Q, cap), dtype=torch.float32).pin_memory())
+            self.bw = np.zeros(nmax, np.uint32); self.bv = np.zeros(nmax, np.float64); self.fnode = np.zeros(nmax, np.uint32)
+            self.fstart = np.zeros(nmax + 1, np.int32); self.fidx = np.zeros(nmax, np.uint32)
+            self.nb, self.nn = C.c_int32(0), C.c_int32(0)
+            self.cw = np.zeros(n_kf, np.int32); self.sc = np.zeros(n_kf, np.float32); self.fw = np.zeros(n_kf, np.uint32); self.ns = C.c_int32(0)
+            self.nm = np.zeros(n_kf, np.int32); self.off = np.zeros(n_kf, np.int32)
+            self.pairs = np.zeros(pairs_cap, np.uint32); self.npairs = C.c_int32(0)
+            self.kfv = M._KeyFrameViewC()
+            self.n_pairs = 0
+
+        def extract(self):
+            oo = self.o
+            _lib.check(lib.borb_stereo_frames(self.X._h, pl, pr, Q, W, H, W, EUROC_BF, b, oo["kl"].data_ptr(), oo["dl"].data_ptr(), oo["nl"].data_ptr(),
+                                              oo["kr"].data_ptr(), oo["dr"].data_ptr(), oo["nr"].data_ptr(), oo["ur"].data_ptr(), oo["dp"].data_ptr(), cap), "stereo_frames")
+
+        def query(self, keys, desc, n):
+            """ComputeBoW -> KeyFrameDatabase scoring -> SearchByBoW against every keyframe (compact pairs)."""
+            _lib.check(lib.borb_compute_bow(self.voc._h, desc, n, 4, vp(self.bw), vp(self.bv), C.byref(self.nb), vp(self.fnode), vp(self.fstart), vp(self.fidx),
+                                            C.byref(self.nn)), "compute_bow")
+            _lib.check(lib.borb_kfdb_query(self.mt._h, db._h, vp(self.bw), vp(self.bv), self.nb.value, vp(self.cw), vp(self.sc), vp(self.fw), n_kf, C.byref(self.ns)), "kfdb_query")
+            kfv = self.kfv
+            kfv.n = n; kfv.keys_un = keys; kfv.desc = desc; kfv.has_mp = None; kfv.u_right = None
+            kfv.fv = M._FeatVecC(self.nn.value, vp(self.fnode), vp(self.fstart), vp(self.fidx)); kfv.n_levels = 0; kfv.scale_factors = None; kfv.level_sigma2 = None
+            _lib.check(lib.borb_search_by_bow_db_pairs(self.mt._h, db._h, None, n_kf, C.byref(kfv), 0.75, 1, vp(self.nm), vp(self.off), vp(self.pairs), pairs_cap,
+                                                       C.byref(self.npairs)), "search_by_bow_db_pairs")
+            self.n_pairs = self.npairs.value
+
+    qs = [QStream(t) for t in range(NH)]
+    s0 = qs[0]
+    bw, bv, fnode, fstart, fidx, nb, nn = s0.bw, s0.bv, s0.fnode, s0.fstart, s0.fidx, s0.nb, s0.nn
+    cw, sc, fw, nm, off, pairs = s0.cw, s0.sc, s0.fw, s0.nm, s0.off, s0.pairs
+    state = dict(pairs=0)
 
     def query(keys, desc, n):
-        """ComputeBoW -> KeyFrameDatabase scoring -> SearchByBoW against every keyframe (compact pairs)."""
-        _lib.check(lib.borb_compute_bow(voc._h, desc, n, 4, vp(bw), vp(bv), C.byref(nb), vp(fnode), vp(fstart), vp(fidx), C.byref(nn)), "compute_bow")
-        _lib.check(lib.borb_kfdb_query(mt._h, db._h, vp(bw), vp(bv), nb.value, vp(cw), vp(sc), vp(fw), n_kf, C.byref(ns)), "kfdb_query")
-        kfv.n = n; kfv.keys_un = keys; kfv.desc = desc; kfv.has_mp = None; kfv.u_right = None
-        kfv.fv = M._FeatVecC(nn.value, vp(fnode), vp(fstart), vp(fidx)); kfv.n_levels = 0; kfv.scale_factors = None; kfv.level_sigma2 = None
-        _lib.check(lib.borb_search_by_bow_db_pairs(mt._h, db._h, None, n_kf, C.byref(kfv), 0.75, 1, vp(nm), vp(off), vp(pairs), pairs_cap, C.byref(npairs)), "search_by_bow_db_pairs")
-        state["pairs"] = npairs.value
+        s0.query(keys, desc, n)
+        state["pairs"] = s0.n_pairs
 
-    def pass_resident(k):
+    def pass_resident(st, k):
         q = k % Q
-        query(qk[q].ctypes.data, qd[q].ctypes.data, int(nq[q]))
+        st.query(qk[q].ctypes.data, qd[q].ctypes.data, int(nq[q]))
 
-    def pass_e2e(k):
+    def pass_e2e(st, k):
         # one pass = Q query frames: stereo extraction of the Q pairs from host images, then the three calls per query
-        extract_queries()
+        st.extract()
         for q in range(Q):
-            query(o["kl"][q].data_ptr(), o["dl"][q].data_ptr(), int(o["nl"][q]))
+            st.query(st.o["kl"][q].data_ptr(), st.o["dl"][q].data_ptr(), int(st.o["nl"][q]))
+
+    def run_passes(fn, n_total):
+        """n_total passes dealt round-robin to the NH stream threads (ctypes releases the GIL during the calls)."""
+        errs = []
+
+        def body(t):
+            try:
+                for k in range(t, n_total, NH):
+                    fn(qs[t], k)
+            except BaseException as ex:
+                errs.append(ex)
+        ths = [threading.Thread(target=body, args=(t,)) for t in range(NH)]
+        for th in ths: th.start()
+        for th in ths: th.join()
+        if errs:
+            raise errs[0]
 
     # ---- parity before timing (rank 0): scores and SearchByBoW results of query 0 against the oracle on a keyframe sample
     parity = None
@@ -921,30 +971,31 @@ def run_config4(args, env: Env):
         parity = f"query 0: L1 scores and SearchByBoW matches against {len(kfs)} of the {n_kf} keyframes ({chk} matches) bit-identical to the oracle"
 
     env.clocks.start()
-    for k in range(Wm * 2):
-        pass_resident(k)
+    run_passes(pass_resident, Wm * 2 * NH)
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    for k in range(8):
-        pass_resident(k)
+    run_passes(pass_resident, 8 * NH)
     torch.cuda.synchronize()
-    inner = env.passes_per_step((time.perf_counter() - t0) / 8, K)
-    ml0 = _mlaunch(lib, mt)
-    ms, _ = timed(env, pass_resident, lambda: None, K, inner)
-    launches = _mlaunch(lib, mt) - ml0 + K * inner          # + the vocabulary descent kernel of every ComputeBoW
+    inner = env.passes_per_step((time.perf_counter() - t0) / (8 * NH), K)
+    ml0 = sum(_mlaunch(lib, x.mt) for x in qs)
+    ms, _ = timed(env, lambda k: None, lambda: run_passes(pass_resident, K * inner), 0, 0)
+    launches = sum(_mlaunch(lib, x.mt) for x in qs) - ml0 + K * inner       # + the vocabulary descent kernel of every ComputeBoW
     ms_max = env.max_over_ranks(ms)
     value = world * K * inner / (ms_max * 1e-3)
-    # device time of the database search kernels (CUDA events on the matcher's stream)
+    # device time of the database search kernels (CUDA events on the matcher's stream), one stream alone
     lib.borb_matcher_set_timing(mt._h, 1)
-    kms = []
+    kms, lat = [], []
     for k in range(16):
-        pass_resident(k)
+        t1 = time.perf_counter()
+        pass_resident(s0, k)
+        lat.append((time.perf_counter() - t1) * 1e6)
         f = C.c_float(0); lib.borb_matcher_last_kernel_ms(mt._h, C.byref(f)); kms.append(f.value)
     lib.borb_matcher_set_timing(mt._h, 0)
     kernel_ms = float(np.mean(kms))
-    for k in range(Wm):
-        pass_e2e(k)
+    query_us = float(np.median(lat))
+    state["pairs"] = s0.n_pairs
+    run_passes(pass_e2e, Wm * NH)
     inner_e = max(1, inner // Q)
-    _, e2e_wall = timed(env, pass_e2e, lambda: None, K, inner_e)
+    _, e2e_wall = timed(env, lambda k: None, lambda: run_passes(pass_e2e, K * inner_e), 0, 0)
     e2e_value = world * Q * K * inner_e / (env.max_over_ranks(e2e_wall) * 1e-3)
     clk = env.clocks.stop()
     if rank != 0:
@@ -971,8 +1022,8 @@ def run_config4(args, env: Env):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOADS[4], "keyframes": n_kf, "features_per_keyframe": n_feat / n_kf, "database_MB_in_HBM": db.size()[1] / 1e6,
                        "vocabulary": "k=10 L=6 seeded random tree of ORBvoc's shape (1,111,111 nodes)", "query_frames": Q, "passes_per_step": inner,
-                       "pairs_per_query": int(state["pairs"]),
-                       "parallelism": f"{world} independent maps / camera streams, one database per GPU (NCCL: vocabulary broadcast only)",
+                       "pairs_per_query": int(state["pairs"]), "query_streams_in_flight": NH,
+                       "parallelism": f"{world} GPUs x {NH} host threads, each an independent query stream on the GPU's database (no data-path collective; NCCL: vocabulary broadcast only)",
                        "cache": f"the database sweep reads {db_bytes / 1e6:.0f} MB per query vs 126 MB L2: successive queries do find part of it in L2 (the reference's relocalisation re-reads the same keyframes too)",
                        "e2e_pass": f"{Q} query frames: stereo extraction from host images + ComputeBoW + scoring + SearchByBoW each", "parity_checked": parity},
             "clocks": clk, "gpu_launches": int(launches),
@@ -980,6 +1031,8 @@ def run_config4(args, env: Env):
             "roofline": {"kernel": "bowdb_match_kernel (+ bowdb_finalize_kernel)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": db_bytes, "mean_launch_ms": kernel_ms},
+            "query_latency": {"call": "ComputeBoW + KeyFrameDatabase scoring + SearchByBoW vs all keyframes, one stream alone, host buffers in and out",
+                              "us_p50": query_us},
             "cpu_baseline": cpu}
     if voc_ms is not None:
         line["nccl"] = {"vocabulary_broadcast_ms": voc_ms, "vocabulary_bytes": voc_bytes}
@@ -996,13 +1049,15 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="config 2: RGB-D frames per pass per handle")
     ap.add_argument("--keyframes", type=int, default=2000, help="config 4: keyframes in the resident database")
     ap.add_argument("--queries", type=int, default=8, help="config 4: distinct query frames")
-    ap.add_argument("--handles", type=int, default=4, help="batches in flight per GPU (one CUDA stream / host thread each)")
+    ap.add_argument("--handles", type=int, default=None, help="batches / query streams in flight per GPU (one CUDA stream / host thread each); default 4, config 4: 8")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-items-per-thread", type=int, default=8)
     ap.add_argument("--ref-items-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
+    if args.handles is None:
+        args.handles = 8 if args.config == 4 else 4
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
