@@ -4,22 +4,25 @@
 //
 // Layout.  A keyframe is stored in the database as a STREAM RECORD: its features permuted into FeatureVector order (node id
 // ascending, feature index ascending inside a node — the order of the reference's two nested loops, :180-205), so that the
-// descriptors of a node are consecutive rows: every keyframe byte is read exactly once, by one warp, with coalesced 16-byte
-// loads.  The query frame is packed the same way by the host, fetched into shared memory ONCE per (persistent) CTA with a 1-D
-// TMA bulk copy (cp.async.bulk + mbarrier) and reused for every keyframe.
+// descriptors of a node are consecutive 32-byte rows and every keyframe byte is read exactly once.  The query frame is packed
+// the same way by the host (plus a work list), fetched into shared memory ONCE per (persistent, one per SM) CTA with a 1-D TMA
+// bulk copy (cp.async.bulk + mbarrier) and reused for every keyframe.
 //
 // Work decomposition.  A frame feature lives in exactly one node, so the greedy "frame feature already claimed" skip (:209)
-// never crosses nodes: a (keyframe, node) pair is an independent unit.  Items = (keyframe, contiguous range of its nodes);
-// warps of persistent CTAs take items from an atomic counter.  Per unit: the keyframe's rows are loaded into per-warp shared
-// memory, rows without a good MapPoint are dropped (:196-202), the (rows x columns) distance matrix is computed with all
-// lanes busy (a lane owns a column, its descriptor in registers; narrow nodes pack several rows per pass), then the rows are
-// replayed in order over the matrix: best / second-best == lexicographic min / second min of (distance, column) through REDUX,
-// TH_LOW and ratio tests exactly as :226-230.  A match is written to a (keyframe x frame-position) table; a second kernel
-// (warp per keyframe) builds the rotation histogram, applies ComputeThreeMaxima (:267-285) and compacts the survivors into
-// (frame feature, keyframe feature) pairs in (node, frame feature) order — deterministic, no atomics on the data path.
+// never crosses nodes: a (keyframe, node) bucket is an independent claim scope.  An ITEM is (one node of the query frame, a
+// range of <= 32 keyframes); warps take items from an atomic counter, widest buckets first, keyframes per item ~ 1 / nt^2.
+// Inside an item every row (keyframe feature with a good MapPoint, :196-202) meets the SAME nt columns (frame features of
+// the node): lane = row with its descriptor in registers, the column loop has a warp-uniform trip count and broadcast
+// shared-memory loads; best / second best == lexicographic min / second min of (distance, column).  Only rows that have a
+// distance <= TH_LOW at all can match or claim (:226); those are replayed in (keyframe, row) order against the bucket's
+// claim bits with the ratio test of :228 (a row whose best or second best was claimed meanwhile is rescanned by the warp).
+// A match goes to a (keyframe x frame-position) table and bumps the keyframe's rotation histogram; a second kernel (CTA per
+// keyframe) applies ComputeThreeMaxima (:267-285) and compacts the survivors into (frame feature, keyframe feature) pairs in
+// (node, frame feature) order — deterministic output.
 //
-// Bound: the POPC pipe (8 x POPC per 256-bit distance at 16 lanes/clk/SM; 28.8 M distances per 2000-keyframe sweep), then HBM
-// (86.4 MB per sweep); see DESIGN.md for the measured ceiling.  CSA = true trades half of the POPCs for LOP3 carry-save adders.
+// Bound (profiles/r02_bowdb_ncu_summary.md): not HBM (96 MB per 2000-keyframe sweep in 0.105 ms) and no longer the POPC
+// pipe (ham256<MODE>: 8 POPC, 4 POPC + carry-save tree, or 5 POPC + three 3:2 compressors run the sweep in the same time);
+// 40 % of the instructions are per-item / per-batch bookkeeping around the column loop.
 #include "borb_match.h"
 
 namespace borb {
