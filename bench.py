@@ -1049,7 +1049,7 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="config 2: RGB-D frames per pass per handle")
     ap.add_argument("--keyframes", type=int, default=2000, help="config 4: keyframes in the resident database")
     ap.add_argument("--queries", type=int, default=8, help="config 4: distinct query frames")
-    ap.add_argument("--handles", type=int, default=None, help="batches / query streams in flight per GPU (one CUDA stream / host thread each); default 4, config 4: 8")
+    ap.add_argument("--handles", type=int, default=None, help="batches / query streams in flight per GPU (one CUDA stream / host thread each); default: config 1 -> 6, configs 2 and 4 -> 8")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-items-per-thread", type=int, default=8)
     ap.add_argument("--ref-items-per-thread", type=int, default=4)
@@ -1057,7 +1057,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.handles is None:
-        args.handles = 8 if args.config == 4 else 4
+        args.handles = {1: 6, 2: 8, 4: 8}.get(args.config, 4)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -137,11 +137,11 @@ def _pairs_to_dense(nm, off, pairs, n_f):
 
 
 @pytest.mark.parametrize("levelsup", [1, 2, 3, 4])
-@pytest.mark.parametrize("csa", [1, 0])
+@pytest.mark.parametrize("csa", [2, 1, 0])
 def test_search_by_bow_pairs_all_bucket_shapes(oracle, levelsup, csa):
     """The compact database search against the restated SearchByBoW for every bucket geometry of the kernel: levelsup 1 = ~1000
     single-feature nodes, 2 = ~100 nodes of ~8, 3 = 10 nodes of ~80 (multi-tile matrix), 4 = one node with every feature
-    (direct evaluation); with and without the orientation cull; CSA and plain POPC distance arithmetic."""
+    (direct evaluation); with and without the orientation cull; the three distance-arithmetic modes (5-POPC hybrid, full carry-save tree, plain POPC)."""
     from orb_slam2_b200 import _lib, matcher as M
     from orb_slam2_b200.extractor import ORBextractor
     _lib.check(_lib.load().borb_debug_set_bow_csa(csa), "set_bow_csa")
@@ -183,7 +183,7 @@ def test_search_by_bow_pairs_all_bucket_shapes(oracle, levelsup, csa):
             assert nm3[2] == 0 and np.array_equal(np.delete(nm3, 2), np.delete(nm, 2))
             assert np.array_equal(_pairs_to_dense(nm3, off3, pairs3, len(qk))[[0, 1, 3, 8]], dense[[0, 1, 3, 8]])
     finally:
-        _lib.check(_lib.load().borb_debug_set_bow_csa(1), "set_bow_csa")
+        _lib.check(_lib.load().borb_debug_set_bow_csa(2), "set_bow_csa")
 
 
 def test_config4_real_size_2000_keyframes(oracle):
@@ -226,3 +226,46 @@ def test_config4_real_size_2000_keyframes(oracle):
         n_o, m_o = oracle.port_search_by_bow(kfs[s], F, 0.75, True)
         assert nm[s] == n_o and np.array_equal(dense[s], m_o), s
     assert nm[3] > 300 and nm.max() == nm[3::n_src].max()
+
+
+@pytest.mark.parametrize("n_frame,levelsup", [(6000, 2), (8192, 3), (3000, 2)])
+def test_search_by_bow_large_query_frames(oracle, n_frame, levelsup):
+    """Query frames at and beyond what fits next to the per-warp scratch in one SM's shared memory: 3000 features still use the
+    shared-memory frame block with fewer warps per CTA, 6000 / 8192 (the library's limit) read the block through L1 from global
+    memory (bowdb_match_kernel<., false>), with buckets far wider than 32 columns (claim bitset path).  Random descriptors, keyframes
+    derived from the frame by bit flips so that real matches exist; every keyframe against the restated SearchByBoW."""
+    from orb_slam2_b200 import matcher as M
+    from orb_slam2_b200._lib import KP_DTYPE
+    rng = np.random.default_rng(n_frame + levelsup)
+    pv = oracle.PortVocabulary.random(10, 4, 9)
+    e = pv.export()
+    voc = M.ORBVocabulary.from_arrays(e["parent"], e["is_leaf"], e["desc"], e["weight"], e["k"], e["L"])
+
+    def keys(n):
+        k = np.zeros(n, KP_DTYPE)
+        k["x"] = rng.uniform(20, 600, n).astype(np.float32); k["y"] = rng.uniform(20, 440, n).astype(np.float32)
+        k["angle"] = rng.uniform(0, 360, n).astype(np.float32); k["size"] = 31.0; k["octave"] = 0; k["class_id"] = -1
+        return k
+    qd = rng.integers(0, 256, (n_frame, 32), dtype=np.uint8)
+    qk = keys(n_frame)
+    qbow, qfv = voc.transform(qd, levelsup)
+    F = M.KeyFrameView(mvKeysUn=qk, mDescriptors=qd, mFeatVec=qfv)
+    mt = M.ORBmatcher(0.75, True)
+    db = M.KeyFrameDatabase(mt)
+    kfs = []
+    for j in range(5):
+        n = [1500, 900, 2400, 1, 700][j]
+        src = rng.choice(n_frame, n, replace=False)
+        flip = rng.random((n, 32, 8)) < [0.03, 0.06, 0.02, 0.0, 0.10][j]
+        d = qd[src] ^ np.packbits(flip, axis=2, bitorder="little").reshape(n, 32)
+        k = keys(n)
+        k["angle"] = (qk["angle"][src] + rng.choice([0.0, 0.0, 0.0, 95.0], n)).astype(np.float32) % np.float32(360)
+        bow, fv = voc.transform(d, levelsup)
+        kf = M.KeyFrameView(mvKeysUn=k, mDescriptors=d, mFeatVec=fv, has_mp=(rng.random(n) < 0.7).astype(np.uint8))
+        db.add(kf, bow); kfs.append(kf)
+    nm, off, pairs = db.SearchByBoWPairs(None, F)
+    dense = _pairs_to_dense(nm, off, pairs, n_frame)
+    for s, kf in enumerate(kfs):
+        n_o, m_o = oracle.port_search_by_bow(kf, F, 0.75, True)
+        assert nm[s] == n_o and np.array_equal(dense[s], m_o), s
+    assert nm[0] > 100 and nm[2] > 100
