@@ -610,6 +610,7 @@ def run_config2(args, env: Env):
             if j == 0 and i < 3:
                 first[i] = (k, d, m)
         mp_views.append(row)
+    mp_arrays = [(M._MapPointViewC * B)(*mp_views[j]) for j in range(NBUF)]          # contiguous view arrays for the batched call
     images = np.arange(B, dtype=np.int32)
 
     # ---- parity before timing (rank 0): extraction, frame tail and matches of the first frames against the oracle
@@ -633,6 +634,8 @@ def run_config2(args, env: Env):
             n_o, m_o = O.port_search_by_projection(F, mv, 3.0, 0.8)
             n_g, m_g = mats[0].SearchByProjection(frames[i], mv, 3.0)
             assert n_g == n_o and np.array_equal(m_g, m_o), "SearchByProjection differs from the oracle"
+            (n_b, m_b), = mats[0].SearchByProjectionBatch([frames[i]], [mv], 3.0)
+            assert n_b == n_o and np.array_equal(m_b, m_o), "batched SearchByProjection differs from the oracle"
             tot_m += n_g
         parity = f"frames 0-2 of buffer 0: keypoints, descriptors, mvKeysUn, mvuRight, mvDepth and {tot_m} SearchByProjection matches bit-identical to the oracle"
         del frames
@@ -654,6 +657,10 @@ def run_config2(args, env: Env):
         s.ku = torch.empty((B, cap, 28), dtype=torch.uint8).pin_memory(); s.ur = torch.empty((B, cap), dtype=torch.float32).pin_memory()
         s.dp = torch.empty((B, cap), dtype=torch.float32).pin_memory()
         s.matches = 0
+        s.fvs = (M._FrameViewC * B)(*[M._FrameViewC(0, None, None, None, None, 0.0, 0.0, 0.0, 0.0, 8, None, None) for _ in range(B)])
+        s.match_all = np.zeros((B, N_MAPPOINTS + 8), np.int32)
+        s.match_ptrs = (C.c_void_p * B)(*[s.match_all[i].ctypes.data for i in range(B)])
+        s.nms = np.zeros(B, np.int32)
         hs.append(s)
     dep_dev = [(C.c_void_p * B)(*[d_dep[j, i].data_ptr() for i in range(B)]) for j in range(NBUF)]
     dep_host = [(C.c_void_p * B)(*[h_dep[j, i].data_ptr() for i in range(B)]) for j in range(NBUF)]
@@ -661,11 +668,18 @@ def run_config2(args, env: Env):
     p_images, p_i32 = images.ctypes.data, C.POINTER(C.c_int32)
 
     def match_all(s, j):
-        tot = 0
-        for i in range(B):
-            s.fv.resident = s.frames[i]
-            _lib.check(lib.borb_search_by_projection(s.m._h, C.byref(s.fv), C.byref(mp_views[j][i]), 3.0, 0.8, s.match.ctypes.data, C.byref(s.nm)), "search_by_projection")
-            tot += s.nm.value
+        # the B frames of the pass belong to B independent camera streams: ONE batched call (one launch pair, one synchronisation)
+        if args.per_frame_calls:
+            tot = 0
+            for i in range(B):
+                s.fv.resident = s.frames[i]
+                _lib.check(lib.borb_search_by_projection(s.m._h, C.byref(s.fv), C.byref(mp_views[j][i]), 3.0, 0.8, s.match.ctypes.data, C.byref(s.nm)), "search_by_projection")
+                tot += s.nm.value
+        else:
+            for i in range(B):
+                s.fvs[i].resident = s.frames[i]
+            _lib.check(lib.borb_search_by_projection_batch(s.m._h, s.fvs, mp_arrays[j], B, 3.0, 0.8, s.match_ptrs, s.nms.ctypes.data), "search_by_projection_batch")
+            tot = int(s.nms.sum())
         for i in range(B):
             lib.borb_frame_destroy(s.frames[i])
         s.matches = tot
@@ -783,6 +797,7 @@ def run_config2(args, env: Env):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * inner, "d2h_bytes_per_step": d2h * inner},
             "roofline": {"kernel": "fast_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": fast_bytes, "mean_launch_ms": fast_ms},
+            "matcher_calls": "one borb_search_by_projection call per frame" if args.per_frame_calls else "one borb_search_by_projection_batch call per pass (the frames of a pass are independent camera streams)",
             "matcher_latency": {"call": "borb_search_by_projection on a device-resident frame, 300 MapPoints from host buffers, matches back to the host",
                                 "us_p50": float(np.median(lat)), "us_p10": float(np.percentile(lat, 10)), "us_p99": float(np.percentile(lat, 99)), "calls": int(len(lat))},
             "stage_ms_per_pass": stage_ms, "cpu_baseline": cpu}
@@ -1054,6 +1069,7 @@ def main():
     ap.add_argument("--cpu-items-per-thread", type=int, default=8)
     ap.add_argument("--ref-items-per-thread", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-frame-calls", action="store_true", help="config 2: one borb_search_by_projection call per frame instead of the batched call")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     if args.handles is None:

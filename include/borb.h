@@ -249,6 +249,13 @@ typedef struct borb_mappoint_view {
  * match_feat[i] = index of the frame feature that received map point i (F.mvpMapPoints[idx]=pMP), or -1. */
 BORB_API borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* frame, const borb_mappoint_view* mps,
                                                float th, float nnratio, int32_t* match_feat, int32_t* n_matches);
+/* The same search for n_jobs INDEPENDENT (frame, MapPoint list) pairs — e.g. the current frames of n camera streams — in one
+ * launch pair and one synchronisation: frames[j] (must be device-resident: borb_frame_view::resident) is searched with points[j],
+ * results go to match_feat[j][0 .. points[j].n) and n_matches[j], each identical to what the single call returns.  A single call
+ * is ~6 us of kernels behind ~30 us of launch and synchronisation latency; the batch amortises the latter over the streams, the
+ * way borb_extract_batch does for the images (no reference counterpart: the reference tracks one camera on one thread). */
+BORB_API borb_status borb_search_by_projection_batch(borb_matcher* m, const borb_frame_view* frames, const borb_mappoint_view* points,
+                                                     int n_jobs, float th, float nnratio, int32_t* const* match_feat, int32_t* n_matches);
 
 /* LastFrame snapshot for the motion-model search: per last-frame feature i the keypoint (octave, angle of mvKeysUn), the
  * world position and representative descriptor of its MapPoint, valid[i] = mvpMapPoints[i] && !mvbOutlier[i],

@@ -519,6 +519,103 @@ borb_status borb_search_by_projection(borb_matcher* m, const borb_frame_view* F,
     return BORB_OK;
 }
 
+// SearchByProjection(F, vpMapPoints, th) for MANY independent (frame, MapPoint list) jobs in one launch pair: the per-frame call
+// is a few microseconds of kernel work behind ~20 us of launch + synchronisation, so independent camera streams are batched the
+// same way the extractor batches their images.  Frames must be device-resident (borb_frames_from_extractor / borb_frame_create).
+borb_status borb_search_by_projection_batch(borb_matcher* m, const borb_frame_view* frames, const borb_mappoint_view* points, int n_jobs,
+                                            float th, float nnratio, int32_t* const* match_feat, int32_t* n_matches) {
+    if (!m || n_jobs < 0 || (n_jobs > 0 && (!frames || !points || !match_feat || !n_matches))) { set_error("null argument"); return BORB_ERR_INVALID_ARG; }
+    if (n_jobs == 0) return BORB_OK;
+    struct JobOff { size_t px, py, pxr, lvl, vc, md, val, obs, occ, cand, cc, out; bool live; };
+    std::vector<JobOff> J(n_jobs);
+    int max_n = 1, max_n_mp = 0;
+    for (int j = 0; j < n_jobs; j++) {
+        const borb_frame_view* F = &frames[j];
+        const borb_mappoint_view* P = &points[j];
+        n_matches[j] = 0;
+        if (!F->resident) { set_error("job %d: borb_search_by_projection_batch needs device-resident frames (borb_frame_view::resident)", j); return BORB_ERR_INVALID_ARG; }
+        const FrameInfo I = frame_info(F);
+        borb_status s = check_frame(F, I, m);
+        if (s != BORB_OK) return s;
+        if (!match_feat[j]) { set_error("job %d: null output", j); return BORB_ERR_INVALID_ARG; }
+        if (P->n < 0 || P->n > MATCH_MAX_FEATURES) { set_error("job %d: %d map points (limit %d per call)", j, P->n, MATCH_MAX_FEATURES); return BORB_ERR_INVALID_ARG; }
+        J[j].live = P->n > 0 && I.n > 0;
+        if (P->n > 0 && I.n == 0) for (int i = 0; i < P->n; i++) match_feat[j][i] = -1;
+        if (!J[j].live) continue;
+        if (!P->proj_x || !P->proj_y || !P->proj_xr || !P->level || !P->view_cos || !P->desc) { set_error("job %d: incomplete map point view", j); return BORB_ERR_INVALID_ARG; }
+        for (int i = 0; i < P->n; i++)
+            if ((!P->valid || P->valid[i]) && (P->level[i] < 0 || P->level[i] >= I.n_levels)) { set_error("job %d, map point %d: predicted level out of range", j, i); return BORB_ERR_INVALID_ARG; }
+        if (I.n > max_n) max_n = I.n;
+        if (P->n > max_n_mp) max_n_mp = P->n;
+    }
+    if (max_n_mp == 0) return BORB_OK;
+    BORB_CUDA(cudaSetDevice(m->device));
+    Stager st(m);
+    for (int j = 0; j < n_jobs; j++) {
+        if (!J[j].live) continue;
+        const borb_mappoint_view* P = &points[j];
+        const size_t n = (size_t)P->n;
+        J[j].px = st.add(P->proj_x, n * 4); J[j].py = st.add(P->proj_y, n * 4); J[j].pxr = st.add(P->proj_xr, n * 4);
+        J[j].lvl = st.add(P->level, n * 4); J[j].vc = st.add(P->view_cos, n * 4); J[j].md = st.add(P->desc, n * 32);
+        J[j].val = P->valid ? st.add(P->valid, n) : 0;
+        J[j].obs = P->has_obs ? st.add(P->has_obs, n) : 0;
+        J[j].occ = frames[j].occupied ? st.add(frames[j].occupied, (size_t)frames[j].resident->n) : 0;
+    }
+    const size_t o_jobs = st.add(nullptr, (size_t)n_jobs * sizeof(ProjArgs));        // filled in place below
+    const size_t input_end = st.off;
+    size_t out_bytes = 0;
+    for (int j = 0; j < n_jobs; j++) {
+        if (!J[j].live) continue;
+        const size_t n = (size_t)points[j].n, nf = (size_t)frames[j].resident->n;
+        J[j].cand = st.reserve(n * nf * 4); J[j].cc = st.reserve(n * 4);
+        J[j].out = out_bytes; out_bytes += ((n + 1) * 4 + 15) & ~size_t(15);
+    }
+    const size_t total = st.off;
+    st.off = input_end;
+    borb_status s;
+    if ((s = ensure_host(m, input_end)) != BORB_OK) return s;
+    if ((s = ensure_arena(m, total)) != BORB_OK) return s;
+    if ((s = ensure_out(m, out_bytes)) != BORB_OK) return s;
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    uint8_t* b = m->arena;
+    ProjArgs* hj = reinterpret_cast<ProjArgs*>(m->h_stage + o_jobs);
+    for (int j = 0; j < n_jobs; j++) {
+        ProjArgs A{};
+        if (J[j].live) {
+            const borb_frame* rf = frames[j].resident;
+            const borb_mappoint_view* P = &points[j];
+            A.n = rf->n;
+            A.minX = rf->min_x; A.minY = rf->min_y;
+            A.invW = (float)GRID_COLS / (float)(rf->max_x - rf->min_x);
+            A.invH = (float)GRID_ROWS / (float)(rf->max_y - rf->min_y);
+            A.keys = rf->keys; A.desc = rf->desc; A.u_right = rf->u_right; A.scale_factors = rf->sf;
+            A.cell_start = rf->cell_start; A.cell_idx = rf->cell_idx;
+            A.occupied = frames[j].occupied ? b + J[j].occ : nullptr;
+            A.n_mp = P->n; A.proj_x = (const float*)(b + J[j].px); A.proj_y = (const float*)(b + J[j].py); A.proj_xr = (const float*)(b + J[j].pxr);
+            A.view_cos = (const float*)(b + J[j].vc); A.level = (const int32_t*)(b + J[j].lvl); A.mp_desc = b + J[j].md;
+            A.mp_valid = P->valid ? b + J[j].val : nullptr; A.mp_has_obs = P->has_obs ? b + J[j].obs : nullptr;
+            A.th = th; A.nnratio = nnratio; A.th_dist = TH_HIGH;
+            A.cand = (uint32_t*)(b + J[j].cand); A.cand_cnt = (int*)(b + J[j].cc);
+            A.mode = 0;
+            A.out_match = (int32_t*)(m->h_out + J[j].out);                  // results land in pinned host memory directly (UVA)
+        }                                                                    // a dead job keeps n_mp = 0: both kernels skip it
+        hj[j] = A;
+    }
+    if ((s = commit(st, total)) != BORB_OK) return s;
+    for (int j = 0; j < n_jobs; j++)
+        if (J[j].live) BORB_CUDA(cudaStreamWaitEvent(m->stream, frames[j].resident->ready, 0));
+    m->launches += launch_projection_batch((const ProjArgs*)(b + o_jobs), n_jobs, max_n, max_n_mp, m->stream);
+    BORB_CUDA(cudaGetLastError());
+    BORB_CUDA(cudaStreamSynchronize(m->stream));
+    for (int j = 0; j < n_jobs; j++) {
+        if (!J[j].live) continue;
+        const size_t n = (size_t)points[j].n;
+        std::memcpy(match_feat[j], m->h_out + J[j].out, n * 4);
+        std::memcpy(&n_matches[j], m->h_out + J[j].out + n * 4, 4);
+    }
+    return BORB_OK;
+}
+
 // Shared body of the three SearchByProjection overloads that project world points with a pose:
 // variant 0 (CurrentFrame, LastFrame) :1328, 1 (CurrentFrame, KeyFrame) :1472, 2 (KeyFrame, Scw) :290.
 struct PointQuery {

@@ -61,7 +61,7 @@ __device__ void three_maxima(const int* cnt, int& ind1, int& ind2, int& ind3) { 
 }  // namespace
 
 // cand entry: idx | dist << 16 | octave << 25;   cand_cnt = count | CAND_UNSORTED
-__global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
+__device__ __forceinline__ void candidates_body(const ProjArgs& A) {
     const int lane = threadIdx.x & 31;
     const int iMP = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (iMP >= A.n_mp) return;
@@ -186,13 +186,17 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) {
     if (lane == 0) A.cand_cnt[iMP] = count | (unsorted ? CAND_UNSORTED : 0);
 }
 
+__global__ void __launch_bounds__(256) proj_candidates_kernel(ProjArgs A) { candidates_body(A); }
+// one launch for many independent (frame, MapPoint list) jobs: grid.y = job, the job's arguments come from device memory
+__global__ void __launch_bounds__(256) proj_candidates_batch_kernel(const ProjArgs* __restrict__ jobs) { candidates_body(jobs[blockIdx.y]); }
+
 size_t resolve_smem_bytes(int n, int n_mp) {
     return ((size_t)(n + 31) / 32 + (size_t)n + (size_t)n_mp * RES_K + (size_t)n_mp) * 4 + (size_t)n_mp + 64;
 }
 
 template <bool LAST>
-__global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjArgs A, const borb_keypoint* __restrict__ cur_keys, int32_t* __restrict__ out,
-                                                           int32_t* __restrict__ ev_idx, uint8_t* __restrict__ ev_bin, int* __restrict__ n_matches) {
+__device__ __forceinline__ void resolve_body(const ProjArgs& A, const borb_keypoint* __restrict__ cur_keys, int32_t* __restrict__ out,
+                                             int32_t* __restrict__ ev_idx, uint8_t* __restrict__ ev_bin, int* __restrict__ n_matches) {
     extern __shared__ uint32_t rsm[];
     __shared__ int hist[32];
     __shared__ int cnt_nm, cnt_ev, cnt_rm;
@@ -322,8 +326,30 @@ __global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjArgs A, const bo
     if (tid == 0) *n_matches = cnt_nm - cnt_rm;
 }
 
+template <bool LAST>
+__global__ void __launch_bounds__(1024) proj_resolve_kernel(ProjArgs A, const borb_keypoint* __restrict__ cur_keys, int32_t* __restrict__ out,
+                                                           int32_t* __restrict__ ev_idx, uint8_t* __restrict__ ev_bin, int* __restrict__ n_matches) {
+    resolve_body<LAST>(A, cur_keys, out, ev_idx, ev_bin, n_matches);
+}
+// a CTA per job (SearchByProjection(F, vpMapPoints) of many independent frames in one launch)
+__global__ void __launch_bounds__(1024) proj_resolve_batch_kernel(const ProjArgs* __restrict__ jobs) {
+    const ProjArgs& A = jobs[blockIdx.x];
+    if (A.n_mp <= 0) return;                        // a job without work (no MapPoints / empty frame) carries null pointers
+    resolve_body<false>(A, A.keys, A.out_match, nullptr, nullptr, reinterpret_cast<int*>(A.out_match + A.n_mp));
+}
+
 void launch_candidates(const ProjArgs& A, cudaStream_t s) {
     if (A.n_mp > 0) proj_candidates_kernel<<<(A.n_mp + 7) / 8, 256, 0, s>>>(A);
+}
+
+int launch_projection_batch(const ProjArgs* d_jobs, int n_jobs, int max_n, int max_n_mp, cudaStream_t s) {
+    if (n_jobs <= 0 || max_n_mp <= 0) return 0;
+    proj_candidates_batch_kernel<<<dim3((max_n_mp + 7) / 8, n_jobs), 256, 0, s>>>(d_jobs);
+    const size_t smem = resolve_smem_bytes(max_n, max_n_mp);
+    const int threads = max_n_mp > 512 ? 1024 : (max_n_mp > 256 ? 512 : 256);
+    allow_max_smem((const void*)proj_resolve_batch_kernel);
+    proj_resolve_batch_kernel<<<n_jobs, threads, smem, s>>>(d_jobs);
+    return 2;
 }
 
 void launch_resolve(const ProjArgs& A, bool last, int32_t* out, int32_t* ev_idx, uint8_t* ev_bin, int* n_matches, cudaStream_t s) {

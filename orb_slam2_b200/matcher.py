@@ -291,6 +291,30 @@ class ORBmatcher:
               "borb_search_by_projection")
         return n.value, match[:len(px)]
 
+    def SearchByProjectionBatch(self, frames: Sequence[FrameView], mps_list: Sequence[MapPointsView], th: float = 3.0):
+        """borb_search_by_projection_batch: SearchByProjection(F, vpMapPoints, th) of many independent device-resident frames in one
+        launch pair.  Returns [(nmatches, match_feat)] per job, each equal to the single call's result."""
+        n = len(frames)
+        assert n == len(mps_list)
+        FV = (_FrameViewC * n)()
+        MV = (_MapPointViewC * n)()
+        keep, outs = [], []
+        for j, (F, mps) in enumerate(zip(frames, mps_list)):
+            fv, k = F._view()
+            FV[j] = fv
+            px = np.ascontiguousarray(mps.mTrackProjX, np.float32); py = np.ascontiguousarray(mps.mTrackProjY, np.float32)
+            pxr = np.ascontiguousarray(mps.mTrackProjXR, np.float32); lv = np.ascontiguousarray(mps.mnTrackScaleLevel, np.int32)
+            vc = np.ascontiguousarray(mps.mTrackViewCos, np.float32); md = np.ascontiguousarray(mps.descriptors, np.uint8)
+            va = np.ascontiguousarray(mps.valid, np.uint8) if mps.valid is not None else None
+            ho = np.ascontiguousarray(mps.has_obs, np.uint8) if mps.has_obs is not None else None
+            MV[j] = _MapPointViewC(len(px), _p(px), _p(py), _p(pxr), _p(lv), _p(vc), _p(md), _p(va), _p(ho))
+            out = np.full(max(len(px), 1), -1, np.int32)
+            keep.append((k, px, py, pxr, lv, vc, md, va, ho)); outs.append(out)
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        nm = np.zeros(max(n, 1), np.int32)
+        check(self._lib.borb_search_by_projection_batch(self._h, FV, MV, n, float(th), self.mfNNratio, ptrs, _p(nm)), "borb_search_by_projection_batch")
+        return [(int(nm[j]), outs[j][:MV[j].n]) for j in range(n)]
+
     def SearchByProjectionLast(self, Cur: FrameView, Last: LastFrameView, Tcw: np.ndarray, K: Tuple[float, float, float, float], bf: float,
                                th: float, bForward: bool = False, bBackward: bool = False) -> Tuple[int, np.ndarray]:
         """SearchByProjection(CurrentFrame, LastFrame, th, bMono) — src/ORBmatcher.cc:1328-1470.  Tcw: (3,4) or (4,4) current pose;

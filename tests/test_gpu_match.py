@@ -385,3 +385,37 @@ def test_compute_bow_equals_the_reference_bookkeeping(M, oracle, views):
         bow_p, fv_p = voc.transform(d, levelsup)
         assert list(bow_c.items()) == list(bow_p.items())                  # same words, same order, bit-identical doubles
         assert np.array_equal(fv_c.node_id, fv_p.node_id) and np.array_equal(fv_c.start, fv_p.start) and np.array_equal(fv_c.feat_idx, fv_p.feat_idx)
+
+
+def test_search_by_projection_batch_equals_single_calls(M, oracle, views):
+    """borb_search_by_projection_batch: many independent (resident frame, MapPoint list) jobs in one launch pair — every job's
+    result equals the single call and the oracle; jobs of different sizes, with and without occupancy masks / validity flags,
+    an empty MapPoint list, and a list long enough for the 512- and 1024-thread resolve configurations."""
+    import dataclasses
+    mt = M.ORBmatcher(0.8, True)
+    frames, lists, want = [], [], []
+    for j, (seed, n_mp) in enumerate([(7, 300), (8, 40), (7, 700), (8, 0), (7, 1), (8, 300)]):
+        v = views[seed]
+        F, mps = mf.projection_case(v, 100 + j, n_mp=max(n_mp, 1))
+        if n_mp == 0:
+            mps = dataclasses.replace(mps, mTrackProjX=mps.mTrackProjX[:0], mTrackProjY=mps.mTrackProjY[:0], mTrackProjXR=mps.mTrackProjXR[:0],
+                                      mnTrackScaleLevel=mps.mnTrackScaleLevel[:0], mTrackViewCos=mps.mTrackViewCos[:0], descriptors=mps.descriptors[:0],
+                                      valid=None if mps.valid is None else mps.valid[:0], has_obs=None if mps.has_obs is None else mps.has_obs[:0])
+        if j % 2 == 1:
+            occ = np.zeros(len(F.mvKeysUn), np.uint8); occ[j::4] = 1
+            F = dataclasses.replace(F, occupied=occ)
+        FR = dataclasses.replace(F.make_resident(mt), occupied=F.occupied)
+        frames.append(FR); lists.append(mps)
+        want.append(oracle.port_search_by_projection(F, mps, 3.0, 0.8) if n_mp else (0, np.zeros(0, np.int32)))
+    got = mt.SearchByProjectionBatch(frames, lists, 3.0)
+    assert len(got) == len(want)
+    for j, ((n_g, m_g), (n_o, m_o)) in enumerate(zip(got, want)):
+        assert n_g == n_o and np.array_equal(m_g, m_o), j
+        if len(m_o):
+            n_s, m_s = mt.SearchByProjection(frames[j], lists[j], 3.0)
+            assert n_s == n_o and np.array_equal(m_s, m_o), j
+    assert got[0][0] > 50 and got[2][0] > 100
+    # a host view (not resident) is refused loudly
+    F0, mps0 = mf.projection_case(views[7], 100, n_mp=10)
+    with pytest.raises(Exception):
+        mt.SearchByProjectionBatch([F0], [mps0], 3.0)
