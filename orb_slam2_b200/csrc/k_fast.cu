@@ -135,10 +135,11 @@ __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Ge
     __shared__ __align__(128) uint8_t tile[TROWS * TP];
     __shared__ __align__(16) uint8_t score[60 * TP];     // S(p) in TILE coordinates (same columns as `tile`)
     __shared__ uint16_t queue[QCAP];                      // corners: row << 8 | tile column
-    __shared__ uint16_t wqueue[60 * 32];                  // words (row << 5 | lane) deferred to the dense scoring pass
+    __shared__ uint16_t wqueue[8 * 256];                  // words (row << 5 | lane) deferred to the dense scoring pass: one 256-entry
+    __shared__ int wcnt[8];                               // segment per warp (a warp owns <= 8 rows), filled without atomics
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t scoredRow[60];                    // per tile row: lanes whose word has an exact score in `score`
-    __shared__ int qn, wqn, needB;
+    __shared__ int qn, needB;
     __shared__ int cellHasIni[128 / 30 + 1];
     __shared__ uint8_t cellOf[128];
 
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Ge
     // overlap with the copy: bookkeeping
     if (tid < 128 / 30 + 1) cellHasIni[tid] = 0;
     if (tid < 128) cellOf[tid] = (uint8_t)(tid / wCell);
-    if (tid == 0) { qn = 0; wqn = 0; needB = 0; }
+    if (tid == 0) { qn = 0; needB = 0; }
     __syncthreads();
     asm volatile(
         "{\n"
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Ge
             if (4 * wc + b - off >= 0 && 4 * wc + b - off < tw) vmask |= 0x80u << (8 * b);
         // rolling window of 7 tile rows x 3 words; slot (j % 7) holds tile row (yy + j), j = 0..6 <=> dy = j-3
         uint32_t a0[7], a1[7], a2[7];
+        int wcount = 0;
         if (yBeg < yEnd) {
 #pragma unroll
             for (int j = 0; j < 6; j++) {
@@ -279,31 +281,34 @@ __global__ void __launch_bounds__(256, 4) fast_kernel(const __grid_constant__ Ge
                 if (lane == 0) scoredRow[yy] = bal;
                 // rejected words are final (S < iniTh: recorded as 0); survivors are scored in pass 1b with all lanes busy
                 if (!keep && vmask != 0) S32[yy * (TP / 4) + wc] = 0;
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&wqn, __popc(bal));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (keep) wqueue[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((yy << 5) | lane);
-                }
+                if (keep) wqueue[wrp * 256 + wcount + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((yy << 5) | lane);
+                wcount += __popc(bal);               // warp-uniform: the warp's segment needs no atomic
             }
         }
+        if (lane == 0) wcnt[wrp] = wcount;
     }
     __syncthreads();
     if (g.fast_mode == 2) {                 // ablation: load + packed reject
-        if (wqn == -1) cand[0] = 1;
+        if (wcnt[0] == -1) cand[0] = 1;
         return;
     }
 
-    // ---- 1b. dense scoring pass over the deferred words
+    // ---- 1b. dense scoring pass over the deferred words (the 8 segments read as one list)
     {
-        const int nw = wqn;
+        int c[8], nw = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { c[w] = wcnt[w]; nw += c[w]; }
         for (int eb = 0; eb < nw; eb += 256) {
             const int e = eb + tid;
             uint32_t sw = 0;
             int yy = 0, wc = wbase;
             const bool have = e < nw;
             if (have) {
-                const int we = wqueue[e];
+                int seg = 0, r = e;
+#pragma unroll
+                for (int w = 0; w < 7; w++)
+                    if (seg == w && r >= c[w]) { r -= c[w]; seg = w + 1; }
+                const int we = wqueue[seg * 256 + r];
                 yy = we >> 5;
                 wc = wbase + (we & 31);
                 uint32_t R0[7], R1[7], R2[7];
