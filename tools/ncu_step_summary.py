@@ -19,14 +19,17 @@ UNIT_SCALE = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, 
               "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
 
 
+PEAK = 6574.1     # GB/s, MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth of this pool's B200s)
+
+
 def main():
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ik, ig = hdr.index("Kernel Name"), hdr.index("Grid Size")
-    print("| kernel | grid | " + " | ".join(c[0] for c in COLS) + " |")
-    print("|---|---|" + "---|" * len(COLS))
+    print("| kernel | grid | " + " | ".join(c[0] for c in COLS) + " | DRAM GB/s | % of HBM peak |")
+    print("|---|---|" + "---|" * (len(COLS) + 2))
     for r in rows[2:]:
         cells = []
         for _, key, scale, fmt in COLS:
@@ -40,6 +43,11 @@ def main():
             v *= UNIT_SCALE.get(units[i], 1.0) * scale
             cells.append(fmt.format(v))
         name = r[ik].split("(")[0].replace("void ", "").replace("borb::", "")
+        try:                                   # achieved DRAM bandwidth of the launch against the measured HBM peak (MEASURED_PEAKS.json)
+            gbs = (float(cells[1]) + float(cells[2])) * 1e6 / (float(cells[0]) * 1e-6) / 1e9
+            cells += [f"{gbs:.0f}", f"{100 * gbs / PEAK:.1f}"]
+        except ValueError:
+            cells += ["—", "—"]
         print(f"| `{name}` | {r[ig]} | " + " | ".join(cells) + " |")
 
 
