@@ -63,3 +63,24 @@ def test_matcher_adapter_library_builds_and_exports_the_reference_entry_points()
     # the adapter library depends on the product, not on the reference's matcher
     deps = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
     assert "libborb.so" in deps
+
+
+def test_keyframe_database_adapter_library_builds_and_fails_loudly_without_a_gpu():
+    """integration/KeyFrameDatabase_borb.cc behind the reference's unchanged include/KeyFrameDatabase.h compiles against the
+    dbowshim stand-ins and links libborb.so (oracle/_ref/libadaptdbow.so, same entry points as the verbatim libdbowref.so).
+    Executed on the GPU by tests/test_gpu_adapters.py; here: the exports, the dependency, and — on a machine without a GPU —
+    that a database call surfaces the library's error instead of falling back to anything."""
+    import ctypes
+    import pytest
+    from oracle import oracle_lib as O
+    O.build()
+    so = os.path.join(ROOT, "oracle", "_ref", "libadaptdbow.so")
+    if not os.path.exists(so):
+        pytest.skip("needs the reference tree (DBoW2, KeyFrameDatabase.h) at build time")
+    lib = ctypes.CDLL(so)
+    for name in ("dbowref_voc_load_text", "dbowref_transform", "dbowref_score", "dbowref_detect_candidates", "dbowref_reloc_sequence"):
+        assert hasattr(lib, name), name
+    deps = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "libborb.so" in deps
+    syms = subprocess.run(["nm", "-DC", so], capture_output=True, text=True).stdout
+    assert "borb_kfdb_query" in syms and "borb_kfdb_add" in syms            # undefined here, resolved by libborb.so

@@ -142,3 +142,33 @@ def test_extractor_and_stereo_adapter_program(oracle, tmp_path):
     assert np.array_equal(kl, kl_o) and np.array_equal(kr, kr_o) and np.array_equal(dl, dl_o) and np.array_equal(dr, dr_o)
     assert np.array_equal(ur, ur_o) and np.array_equal(dp, dp_o) and (ur >= 0).sum() > 200
     assert np.array_equal(p3, E1.level(3))                              # mvImagePyramid through SyncPyramid
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# KeyFrameDatabase: integration/KeyFrameDatabase_borb.cc (the drop-in replacement of src/KeyFrameDatabase.cc) behind the real
+# include/KeyFrameDatabase.h, wrapped by the same oracle/dbowref_wrap.cpp as the verbatim build
+ADAPT_DBOW_SO = os.path.join(ROOT, "oracle", "_ref", "libadaptdbow.so")
+
+
+@pytest.fixture(scope="module")
+def world(oracle, tmp_path_factory):
+    """tests/test_oracle_dbow_ref.py's fixture with oracle.DBOWREF_SO pointing at the ADAPTER library: every
+    KeyFrameDatabase::add / DetectLoopCandidates / DetectRelocalizationCandidates call of those tests now runs
+    adapter -> borb_kfdb_add / borb_kfdb_query (GPU) -> the adapter's host part."""
+    if not os.path.exists(ADAPT_DBOW_SO):
+        pytest.skip("oracle/_ref/libadaptdbow.so not built (needs the reference tree at build time)")
+    saved = oracle.DBOWREF_SO
+    oracle.DBOWREF_SO = ADAPT_DBOW_SO
+    pv = oracle.PortVocabulary.random(10, 3, 5)
+    path = tmp_path_factory.mktemp("voc") / "voc.txt"
+    pv.save_text(str(path))
+    path.write_text(path.read_text().rstrip("\n"))
+    rv = oracle.RefVocabulary(path)                     # CDLL(ADAPT_DBOW_SO): its database entry points are the product's adapter
+    yield dict(O=oracle, pv=pv, rv=rv, v=mf.two_views(oracle, 7))
+    oracle.DBOWREF_SO = saved
+
+
+from tests import test_oracle_dbow_ref as TD      # noqa: E402
+
+test_keyframe_database_adapter_equals_reference_source = TD.test_keyframe_database_equals_reference_source
+test_keyframe_database_adapter_reads_stale_scores_like_the_reference = TD.test_relocalization_reads_stale_scores_like_the_reference
