@@ -84,3 +84,70 @@ def test_keyframe_database_adapter_library_builds_and_fails_loudly_without_a_gpu
     assert "libborb.so" in deps
     syms = subprocess.run(["nm", "-DC", so], capture_output=True, text=True).stdout
     assert "borb_kfdb_query" in syms and "borb_kfdb_add" in syms            # undefined here, resolved by libborb.so
+
+
+KFDB_MOCKS = {
+    "ORBVocabulary.h": "#pragma once\nnamespace ORB_SLAM2 { struct ORBVocabulary { unsigned size() const { return 0; } }; }\n",
+    "KeyFrameDatabase.h": r'''
+#pragma once
+#include <list>
+#include <mutex>
+#include <vector>
+#include "ORBVocabulary.h"
+namespace ORB_SLAM2 {
+class KeyFrame; class Frame;
+class KeyFrameDatabase {            // the interface of include/KeyFrameDatabase.h:41-75 (a declaration has to match)
+public:
+    KeyFrameDatabase(const ORBVocabulary& voc);
+    void add(KeyFrame* pKF);
+    void erase(KeyFrame* pKF);
+    void clear();
+    std::vector<KeyFrame*> DetectLoopCandidates(KeyFrame* pKF, float minScore);
+    std::vector<KeyFrame*> DetectRelocalizationCandidates(Frame* F);
+protected:
+    const ORBVocabulary* mpVoc;
+    std::vector<std::list<KeyFrame*> > mvInvertedFile;
+    std::mutex mMutex;
+};
+}
+''',
+    "KeyFrame.h": r'''
+#pragma once
+#include <map>
+#include <set>
+#include <vector>
+#include <opencv2/core/core.hpp>
+namespace DBoW2 {
+typedef std::map<unsigned, double> BowVector;
+typedef std::map<unsigned, std::vector<unsigned> > FeatureVector;
+}
+namespace ORB_SLAM2 {
+struct MapPoint { bool isBad() { return false; } };
+class KeyFrame {                    // the members the adapters touch, with the reference's names
+public:
+    long unsigned int mnId = 0, mnLoopQuery = 0, mnRelocQuery = 0;
+    int mnLoopWords = 0, mnRelocWords = 0;
+    float mLoopScore = 0, mRelocScore = 0;
+    DBoW2::BowVector mBowVec; DBoW2::FeatureVector mFeatVec;
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeysUn; cv::Mat mDescriptors; std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
+    std::vector<MapPoint*> GetMapPointMatches() { return std::vector<MapPoint*>(N, nullptr); }
+    std::set<KeyFrame*> GetConnectedKeyFrames() { return std::set<KeyFrame*>(); }
+    std::vector<KeyFrame*> GetBestCovisibilityKeyFrames(const int&) { return std::vector<KeyFrame*>(); }
+};
+}
+''',
+    "Frame.h": "#pragma once\n#include \"KeyFrame.h\"\nnamespace ORB_SLAM2 { class Frame { public: long unsigned int mnId = 0; DBoW2::BowVector mBowVec; }; }\n",
+}
+
+
+def test_keyframe_database_drop_in_compiles_with_resident_features(tmp_path):
+    """integration/KeyFrameDatabase_borb.cc in its default form (keyframe features uploaded for the resident SearchByBoW) against
+    headers that carry the reference's member names: syntax and template instantiation only (the GPU run uses the scoring-only
+    form because the verbatim build's KeyFrame stand-in has no features)."""
+    for name, text in KFDB_MOCKS.items():
+        (tmp_path / name).write_text(text)
+    cmd = ["g++", "-std=c++14", "-fsyntax-only", "-DBORB_ADAPTER_NO_EXTRACTOR", "-I", str(tmp_path), "-I", os.path.join(ROOT, "oracle", "cvmini"),
+           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "KeyFrameDatabase_borb.cc")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
