@@ -178,6 +178,13 @@ BORB_API borb_status borb_stereo_frames_device(borb_extractor* e, const uint8_t*
  * The pointer graphs the reference walks (Frame, KeyFrame, MapPoint) are snapshotted by the adapter into the
  * plain views below on the calling thread; results come back as indices. */
 typedef struct borb_matcher borb_matcher;
+/* Size envelope of every matcher / database call (the reference has no limits; these return BORB_ERR_INVALID_ARG instead of
+ * failing inside a launch): at most BORB_MATCH_MAX_FEATURES features per frame or keyframe, and at most that many VALID query
+ * points per call (MapPoints of SearchByProjection, last-frame features, world points).  The feature grid sort, the claim
+ * bitsets and the resolve kernel's per-query lists live in shared memory, which is what bounds them.  borb_search_local_points
+ * compacts the valid points before the check, so the limit applies to the points that reach Frame::isInFrustum, not to the
+ * length of Tracking::mvpLocalMapPoints (a KITTI-scale local map of 10^4+ points with a few hundred candidates is fine). */
+#define BORB_MATCH_MAX_FEATURES 8192
 BORB_API borb_status borb_matcher_create(int device, borb_matcher** out);
 BORB_API borb_status borb_matcher_destroy(borb_matcher* m);
 

@@ -33,6 +33,7 @@ constexpr int GRID_CELLS = GRID_COLS * GRID_ROWS;
 constexpr int CAND_UNSORTED = 0x40000000;           // flag in cand_cnt: list longer than the sort capacity, kept in position order
 constexpr int CAND_COUNT_MASK = 0x3FFFFFFF;
 constexpr int MATCH_MAX_FEATURES = 8192;          // per frame / keyframe (grid sort and claim bitsets live in smem)
+static_assert(MATCH_MAX_FEATURES == BORB_MATCH_MAX_FEATURES, "include/borb.h documents this limit");
 
 struct ProjArgs {                 // device pointers
     int n;                        // frame features
