@@ -40,3 +40,17 @@ def test_b200_arm_needs_a_gpu():
     r = _run(["--steps", "1", "--warmup", "1", "--pairs", "1", "--handles", "1", "--no-cpu-baseline"])
     assert r.returncode != 0                                       # loud failure, never a CPU-computed number
     assert not any(l.strip().startswith("{") and '"value"' in l for l in r.stdout.splitlines())
+
+
+def test_reference_arm_under_torchrun_prints_on_rank_0_only():
+    """The driver launches the reference arm like the B200 arm (torchrun, one process per GPU): rank 0 alone runs and prints
+    the line, the other ranks exit 0 without output and without work."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+           "--ref-items-per-thread", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
