@@ -151,3 +151,20 @@ def test_keyframe_database_drop_in_compiles_with_resident_features(tmp_path):
            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "KeyFrameDatabase_borb.cc")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_multistream_host_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """integration/example_multistream_host.cc — a C++ host written against the C ABI only (batched extraction, device-resident
+    frames, one batched SearchByProjection for all streams, self-checking) — compiles and links; without a GPU it must stop at the
+    first library call with the library's error (exit code 3), with one it runs its self-check (verified on the B200: every point
+    of every stream matched to its own feature)."""
+    so = os.path.join(ROOT, "orb_slam2_b200", "libborb.so")
+    exe = tmp_path / "example_host"
+    subprocess.check_call(["g++", "-std=c++14", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "example_multistream_host.cc"),
+                           so, f"-Wl,-rpath,{os.path.dirname(so)}", "-o", str(exe)])
+    r = subprocess.run([str(exe), "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode in (0, 3), r
+    if r.returncode == 3:
+        assert "no CUDA device" in r.stdout or "no CPU path" in r.stdout, r.stdout
+    else:
+        assert r.stdout.strip().endswith("ok")
