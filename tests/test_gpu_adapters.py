@@ -171,4 +171,7 @@ def world(oracle, tmp_path_factory):
 from tests import test_oracle_dbow_ref as TD      # noqa: E402
 
 test_keyframe_database_adapter_equals_reference_source = TD.test_keyframe_database_equals_reference_source
-test_keyframe_database_adapter_reads_stale_scores_like_the_reference = TD.test_relocalization_reads_stale_scores_like_the_reference
+
+
+def test_keyframe_database_adapter_reads_stale_scores_like_the_reference(world):
+    TD.test_relocalization_reads_stale_scores_like_the_reference(world, 21)
